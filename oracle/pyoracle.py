@@ -1,0 +1,604 @@
+"""CPU restatement of gpud's Xid/SXid match-and-classify path and the windowed aggregates.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under gpud_b200/ may import this module; only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the checker.
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+The regex strings are the reference's verbatim patterns run through Python `re` on *bytes*
+(so `\\d`, `\\s` are ASCII like Go RE2; both engines are leftmost-first).  Parity status:
+  * match / classify / health-state / thresholds / fabric: PINNED by the reference's own test
+    vectors in tests/golden/ (extracted by tools/gen_golden.py).
+  * windowed min/max/mean/EMA/p99/n_over: the reference has no implementation -> PARITY UNPINNED;
+    the definitions are ours (oracle/SPEC.md).
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CATALOG = json.load(open(os.path.join(_HERE, "catalog.json")))
+
+EV_UNKNOWN, EV_INFO, EV_WARNING, EV_CRITICAL, EV_FATAL = 0, 1, 2, 3, 4
+EVENT_NAMES = ["Unknown", "Info", "Warning", "Critical", "Fatal"]
+ACT_IGNORE, ACT_REBOOT, ACT_HW_INSPECTION, ACT_CHECK_APP = 1, 2, 3, 4
+ACTION_WIRE = {1: "IGNORE_NO_ACTION_REQUIRED", 2: "REBOOT_SYSTEM", 3: "HARDWARE_INSPECTION", 4: "CHECK_USER_APP_AND_GPU"}
+ACTION_NAMES = {1: "IgnoreNoActionRequired", 2: "RebootSystem", 3: "HardwareInspection", 4: "CheckUserAppAndGPU"}
+
+# --------------------------------------------------------------------------------------------
+# regexes: components/accelerator/nvidia/xid/kmsg.go:22,29,38,43 ; sxid/kmsg.go:17,20  (verbatim)
+# --------------------------------------------------------------------------------------------
+R1 = re.compile(rb"NVRM: Xid \(((?:PCI:)?[0-9a-fA-F:]+)\).*?: (\d+),")
+R2 = re.compile(rb"NVRM: Xid \(PCI:([0-9a-fA-F:]+)\): (\d+)(?:, pid=(\d+), name=([^,]+))?, ([A-Z_]+(?:/[A-Z_]+)?)[\t\n\f\r ]+(Nonfatal|Fatal)[\t\n\f\r ]+(XC[01])[\t\n\f\r ]+(i\d+)[\t\n\f\r ]+Link[\t\n\f\r ]+(-?\d+)[\t\n\f\r ]+\((0x[0-9a-fA-F]+)[\t\n\f\r ]+(0x[0-9a-fA-F]+)(?:[\t\n\f\r ]+(0x[0-9a-fA-F]+))?(?:[\t\n\f\r ]+(0x[0-9a-fA-F]+))?(?:[\t\n\f\r ]+(0x[0-9a-fA-F]+))?(?:[\t\n\f\r ]+(0x[0-9a-fA-F]+))?")
+R3 = re.compile(rb"(?s)NVRM:[\t\n\f\r ]+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\.0.*?fallen off the bus and is not responding to commands\.")
+R4 = re.compile(rb"NVRM:[\t\n\f\r ]+GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\.0:[\t\n\f\r ]+GPU has fallen off the bus\.?")
+R5 = re.compile(rb"SXid.*?: (\d+),")
+R6 = re.compile(rb"SXid \((PCI:[0-9a-fA-F:\.]+)\)")
+# NOTE: Go/RE2 `\s` is [\t\n\f\r ] (no \v); Python bytes `\s` also matches \v, hence the explicit class.
+
+INT64_MAX = (1 << 63) - 1
+
+
+def go_atoi(b: bytes) -> Optional[int]:
+    """strconv.Atoi on an optionally signed decimal string; None on range error (int is 64-bit)."""
+    v = int(b)
+    if v > INT64_MAX or v < -INT64_MAX - 1:
+        return None
+    return v
+
+
+def go_parse_uint32_base0(b: bytes) -> Optional[int]:
+    """strconv.ParseUint(s, 0, 32) for the `0x[0-9a-fA-F]+` strings the regex admits."""
+    v = int(b, 16)
+    return v if v <= 0xFFFFFFFF else None
+
+
+# --------------------------------------------------------------------------------------------
+# catalog tables + NVLink sub-code detail maps   (xid/xid.go:74-117, 2954-3343)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Detail:
+    code: int
+    description: str
+    event_type: int
+    actions: Optional[List[int]]          # None == SuggestedActionsByGPUd nil
+    sub_code: int = 0
+    sub_code_description: str = ""
+    error_status: int = 0
+    investigatory_hint: str = ""
+
+    def copy(self) -> "Detail":
+        return Detail(self.code, self.description, self.event_type,
+                      None if self.actions is None else list(self.actions),
+                      self.sub_code, self.sub_code_description, self.error_status, self.investigatory_hint)
+
+
+XID_DETAILS: Dict[int, Detail] = {
+    d["code"]: Detail(d["code"], d["description"], d["event_type"], list(d["actions"]) if d["actions"] else None)
+    for d in CATALOG["xid"]}
+MNEMONIC = {e["Code"]: e["Mnemonic"] for e in CATALOG["catalog_entries"]}
+NVLINK_RULES = CATALOG["nvlink_rules"]
+SXID_DETAILS = {d["sxid"]: d for d in CATALOG["sxid"]}
+
+
+def get_detail(code: int) -> Optional[Detail]:                      # xid.go:74-77
+    return XID_DETAILS.get(code)
+
+
+def event_type_from_severity(s: str) -> int:                         # xid.go:3263-3272
+    s = s.strip().lower()
+    if s in ("fatal", "fatal**", "link fatal", "link fatal?"):
+        return EV_FATAL
+    if s in ("non-fatal", "non-fatal*"):
+        return EV_WARNING
+    return EV_UNKNOWN
+
+
+def event_type_from_log_severity(s: str) -> int:                     # xid.go:3274-3283
+    s = s.strip().lower()
+    if s == "fatal":
+        return EV_FATAL
+    if s in ("nonfatal", "non-fatal"):
+        return EV_WARNING
+    return EV_UNKNOWN
+
+
+_FATAL_BUCKETS = {"CONTACT_SUPPORT", "CHECK_MECHANICALS", "WORKFLOW_NVLINK_ERR", "WORKFLOW_NVLINK5_ERR", "XID_154",
+                  "XID_154_EVAL", "RESTART_BM"}
+_CRIT_BUCKETS = {"RESET_GPU", "RESTART_APP", "RESTART_VM", "CHECK_UVM", "WORKFLOW_XID_48", "WORKFLOW_XID_45", "UPDATE_SWFW"}
+
+
+def event_type_from_immediate_bucket(b: str) -> int:                 # xid.go:3222-3246
+    if b in _FATAL_BUCKETS:
+        return EV_FATAL
+    if b in _CRIT_BUCKETS:
+        return EV_CRITICAL
+    if b in ("IGNORE", ""):
+        return EV_INFO
+    return EV_WARNING
+
+
+def suggested_actions_from_bucket(b: str) -> Optional[List[int]]:    # xid.go:3248-3261
+    if b in ("CONTACT_SUPPORT", "CHECK_MECHANICALS", "WORKFLOW_NVLINK_ERR", "WORKFLOW_NVLINK5_ERR", "XID_154", "XID_154_EVAL"):
+        return [ACT_HW_INSPECTION]
+    if b in ("RESET_GPU", "RESTART_BM", "RESTART_VM", "CHECK_UVM"):
+        return [ACT_REBOOT]
+    if b in ("RESTART_APP", "WORKFLOW_XID_45", "WORKFLOW_XID_48", "UPDATE_SWFW"):
+        return [ACT_CHECK_APP]
+    if b in ("IGNORE", ""):
+        return [ACT_IGNORE]
+    return None
+
+
+def max_event_type(a: int, b: int) -> int:                           # xid.go:3285-3305 (rank == numeric id)
+    return b if b > a else a
+
+
+def merge_actions(base, add):                                        # xid.go:3317-3336 (sorted by wire string)
+    if base is None:
+        return None if add is None else list(add)
+    if add is None:
+        return list(base)
+    return sorted(set(base) | set(add), key=lambda a: ACTION_WIRE[a])
+
+
+def sample_from_pattern(p: str) -> Optional[int]:                    # xid.go:3127-3145
+    if len(p) != 32:
+        return None
+    v = 0
+    for i, ch in enumerate(p):
+        if ch == "1":
+            v |= 1 << (31 - i)
+        elif ch not in "0-":
+            return None
+    return v
+
+
+def pattern_matches(p: str, intrinfo: int) -> bool:                  # xid.go:3147-3172
+    if p == "":
+        return True
+    if len(p) != 32:
+        return False
+    for i, ch in enumerate(p):
+        bit = (intrinfo >> (31 - i)) & 1
+        if ch == "1":
+            if bit == 0:
+                return False
+        elif ch == "0":
+            if bit == 1:
+                return False
+        elif ch != "-":
+            return False
+    return True
+
+
+def normalize_unit(s: str) -> str:                                   # xid.go:3203-3218
+    s = s.strip().upper().replace("-", "_")
+    return "".join(c for c in s if ("A" <= c <= "Z") or ("0" <= c <= "9") or c == "_")
+
+
+def unit_aliases(u: str) -> List[str]:                               # xid.go:3188-3201
+    al = [x for x in re.split(r"[/,() ]", u) if x]
+    if not al:
+        al = [u]
+    return al + [u]
+
+
+def unit_matches(rule_unit: str, log_unit: str) -> bool:             # xid.go:3174-3186
+    c = normalize_unit(log_unit)
+    if c == "":
+        return False
+    return any(normalize_unit(a) == c for a in unit_aliases(rule_unit))
+
+
+def sub_code_from_rule(r) -> Optional[int]:                          # xid.go:3117-3125
+    for k in ("IntrinfoPatternV2", "IntrinfoPatternV1"):
+        if r[k] != "":
+            v = sample_from_pattern(r[k])
+            if v is not None:
+                return (v >> 20) & 0x3F
+    return None
+
+
+def _build_nvlink_maps():                                            # xid.go:2997-3090
+    result: Dict[int, Dict[int, Detail]] = {}
+    by_status: Dict[int, Dict[int, Dict[int, Detail]]] = {}
+    for r in NVLINK_RULES:
+        if r["Xid"] < 144 or r["Xid"] > 150:
+            continue
+        sc = sub_code_from_rule(r)
+        if sc is None:
+            continue
+        result.setdefault(r["Xid"], {})
+        by_status.setdefault(r["Xid"], {}).setdefault(sc, {})
+        base = get_detail(r["Xid"])
+        if base is None:
+            continue
+        d = base.copy()
+        d.sub_code, d.sub_code_description, d.error_status = sc, r["Unit"], r["ErrorStatus"]
+        ev = event_type_from_severity(r["Severity"])
+        if ev == EV_UNKNOWN:
+            ev = event_type_from_immediate_bucket(r["Resolution"])
+        if ev != EV_UNKNOWN:
+            d.event_type = ev
+        acts = suggested_actions_from_bucket(r["Resolution"])
+        if acts is not None:
+            d.actions = list(acts)
+        ex = by_status[r["Xid"]][sc].get(r["ErrorStatus"])
+        if ex is not None:
+            d.event_type = max_event_type(ex.event_type, d.event_type)
+            d.actions = merge_actions(ex.actions, d.actions)
+        by_status[r["Xid"]][sc][r["ErrorStatus"]] = d
+        agg = result[r["Xid"]].get(sc)
+        if agg is None:
+            agg = base.copy()
+            agg.sub_code, agg.sub_code_description = sc, r["Unit"]
+        agg.actions = merge_actions(agg.actions, d.actions)
+        result[r["Xid"]][sc] = agg
+    # applyOperationalOverrides  (xid.go:3062-3089)
+    for sc, sdesc, desc in ((4, "NETIR_LINK_EVT/NETIR_LINK_DOWN (cartridge error)",
+                             "NVLINK: NETIR Link Event - Possible NVLink cartridge error (contact provider)"),
+                            (10, "NETIR_LINK_EVT/NETIR_LINK_DOWN (PHY timeout)",
+                             "NVLINK: NETIR Link Event - Physical layer retransmission timeout (contact provider)")):
+        if 149 in result and sc in result[149]:
+            d = result[149][sc]
+            d.event_type, d.sub_code_description, d.description, d.actions = EV_FATAL, sdesc, desc, [ACT_HW_INSPECTION]
+            if sc in by_status.get(149, {}):
+                for st in list(by_status[149][sc]):
+                    by_status[149][sc][st] = d.copy()
+    return result, by_status
+
+
+DETAILS_WITH_SUBCODES, DETAILS_BY_STATUS = _build_nvlink_maps()
+
+
+def get_detail_with_sub_code(xid: int, sc: int) -> Optional[Detail]:           # xid.go:79-93
+    sm = DETAILS_WITH_SUBCODES.get(xid)
+    if sm is not None:
+        if sc in sm:
+            return sm[sc].copy()
+        if 0 in sm:
+            return sm[0].copy()
+    return get_detail(xid)
+
+
+def get_detail_with_sub_code_and_status(xid: int, sc: int, st: int) -> Optional[Detail]:   # xid.go:97-107
+    d = DETAILS_BY_STATUS.get(xid, {}).get(sc, {}).get(st)
+    if d is not None:
+        return d.copy()
+    return get_detail_with_sub_code(xid, sc)
+
+
+@dataclass
+class ExtractedInfo:                                                  # xid/kmsg.go:84-98
+    device: str
+    xid: int
+    pid: str
+    process_name: str
+    unit: str
+    severity: str
+    xc: str
+    injected: str
+    link: int
+    intrinfo: int
+    error_status: int
+    extra: List[int]
+    sub_code: int
+
+
+def lookup_nvlink_rule(info: ExtractedInfo):                         # xid.go:3099-3114
+    for idx, r in enumerate(NVLINK_RULES):
+        if r["Xid"] != info.xid:
+            continue
+        if not unit_matches(r["Unit"], info.unit):
+            continue
+        if r["ErrorStatus"] != info.error_status:
+            continue
+        if pattern_matches(r["IntrinfoPatternV2"], info.intrinfo) or pattern_matches(r["IntrinfoPatternV1"], info.intrinfo):
+            return idx, r
+    return -1, None
+
+
+def detail_from_nvlink_info(info: ExtractedInfo) -> Optional[Detail]:           # xid.go:2954-2995
+    base = get_detail(info.xid)
+    if base is None:
+        return None
+    d = get_detail_with_sub_code_and_status(info.xid, info.sub_code, info.error_status) or base.copy()
+    _, rule = lookup_nvlink_rule(info)
+    if rule is not None:
+        ev = event_type_from_severity(rule["Severity"])
+        if ev == EV_UNKNOWN:
+            ev = event_type_from_immediate_bucket(rule["Resolution"])
+        if ev != EV_UNKNOWN:
+            d.event_type = ev
+        acts = suggested_actions_from_bucket(rule["Resolution"])
+        if acts is not None:
+            d.actions = list(acts)
+        d.error_status = rule["ErrorStatus"]
+        if rule["Investigatory"] not in ("", "IGNORE", "CONTACT_SUPPORT"):
+            d.investigatory_hint = rule["Investigatory"]
+    d.sub_code = info.sub_code
+    d.sub_code_description = info.unit
+    d.error_status = info.error_status
+    d.event_type = max_event_type(d.event_type, event_type_from_log_severity(info.severity))
+    if d.actions is None:
+        d.actions = None if base.actions is None else list(base.actions)
+    return d
+
+
+# --------------------------------------------------------------------------------------------
+# xid.Match / sxid.Match     (xid/kmsg.go:73-80,116-183,202-268 ; sxid/kmsg.go:28-73)
+# --------------------------------------------------------------------------------------------
+def extract_nvrm_xid_info(line: bytes) -> Tuple[int, str]:            # kmsg.go:73-80
+    m = R1.search(line)
+    if m:
+        v = go_atoi(m.group(2))
+        if v is not None:
+            return v, m.group(1).decode("latin-1")
+    return 0, ""
+
+
+def extract_nvrm_xid_info_extended(line: bytes) -> Optional[ExtractedInfo]:     # kmsg.go:116-183
+    m = R2.search(line)
+    if not m:
+        return None
+    code = go_atoi(m.group(2))
+    if code is None:
+        return None
+    intr = go_parse_uint32_base0(m.group(10))
+    if intr is None:
+        return None
+    es = go_parse_uint32_base0(m.group(11))
+    if es is None:
+        return None
+    link = go_atoi(m.group(9))
+    if link is None:
+        return None
+    extra = []
+    for i in range(12, 16):
+        g = m.group(i)
+        if not g:
+            continue
+        v = go_parse_uint32_base0(g)
+        if v is not None:
+            extra.append(v)
+    s = lambda i: (m.group(i) or b"").decode("latin-1")
+    return ExtractedInfo(s(1), code, s(3), s(4), s(5), s(6), s(7), s(8), link, intr, es, extra, (intr >> 20) & 0x3F)
+
+
+def normalize_pci_bdf(s: str) -> str:                                 # kmsg.go:259-268
+    if s.startswith("PCI:"):
+        s = s[4:]
+    s = s.strip()
+    if s.count(":") == 1:
+        s = "0000:" + s
+    if s == "":
+        return ""
+    return "PCI:" + s
+
+
+def extract_fallen_off_bus(line: bytes) -> Tuple[int, str]:           # kmsg.go:247-257
+    m = R4.search(line)
+    if m:
+        return 79, normalize_pci_bdf(m.group(1).decode("latin-1"))
+    m = R3.search(line)
+    if m:
+        return 79, normalize_pci_bdf(m.group(1).decode("latin-1"))
+    return 0, ""
+
+
+@dataclass
+class XidError:                                                       # kmsg.go:194-198
+    xid: int
+    device: str
+    detail: Detail
+    info: Optional[ExtractedInfo] = None
+
+
+def xid_match(line: bytes) -> Optional[XidError]:                     # kmsg.go:202-245
+    info = extract_nvrm_xid_info_extended(line)
+    if info is not None:
+        d = detail_from_nvlink_info(info)
+        if d is not None:
+            dev = info.device
+            if dev != "" and not dev.startswith("PCI:"):
+                dev = "PCI:" + dev
+            return XidError(info.xid, dev, d, info)
+    code, dev = extract_nvrm_xid_info(line)
+    if code != 0:
+        d = get_detail(code)
+        if d is None:
+            return None
+        return XidError(code, dev, d.copy())
+    code, dev = extract_fallen_off_bus(line)
+    if code != 0:
+        d = get_detail(code)
+        if d is None:
+            return None
+        return XidError(code, dev, d.copy())
+    return None
+
+
+def extract_sxid(line: bytes) -> int:                                 # sxid/kmsg.go:31-38
+    m = R5.search(line)
+    if m:
+        v = go_atoi(m.group(1))
+        if v is not None:
+            return v
+    return 0
+
+
+def extract_sxid_device(line: bytes) -> str:                          # sxid/kmsg.go:42-47
+    m = R6.search(line)
+    return m.group(1).decode("latin-1") if m else ""
+
+
+def sxid_match(line: bytes):                                          # sxid/kmsg.go:58-73
+    code = extract_sxid(line)
+    if code == 0:
+        return None
+    d = SXID_DETAILS.get(code)
+    if d is None:
+        return None
+    return {"sxid": code, "device": extract_sxid_device(line), "detail": d}
+
+
+def scan_lines(buf: bytes):
+    """The reference's buffer-scan form: split on '\\n', Match each line (xid/kmsg_test.go:252-267).
+    Returns hit dicts in (line, kind) order; kind 1 = xid, 2 = sxid."""
+    hits = []
+    off = 0
+    for ln, line in enumerate(buf.split(b"\n")):
+        x = xid_match(line)
+        if x is not None:
+            hits.append({"line": ln, "offset": off, "kind": 1, "code": x.xid, "device": x.device,
+                         "event_type": x.detail.event_type, "actions": x.detail.actions or [],
+                         "extended": x.info is not None,
+                         "sub_code": x.detail.sub_code, "unit": x.detail.sub_code_description,
+                         "error_status": x.detail.error_status,
+                         "intrinfo": x.info.intrinfo if x.info else 0, "link": x.info.link if x.info else 0,
+                         "hint": x.detail.investigatory_hint, "description": x.detail.description})
+        s = sxid_match(line)
+        if s is not None:
+            hits.append({"line": ln, "offset": off, "kind": 2, "code": s["sxid"], "device": s["device"],
+                         "event_type": s["detail"]["event_type"], "actions": s["detail"]["actions"],
+                         "extended": False, "sub_code": 0, "unit": "", "error_status": 0, "intrinfo": 0, "link": 0,
+                         "hint": "", "description": ""})
+        off += len(line) + 1
+    return hits
+
+
+# --------------------------------------------------------------------------------------------
+# /dev/kmsg record parsing + dedup      (pkg/kmsg/watcher.go:292-332 ; pkg/kmsg/deduper.go:63-125)
+# --------------------------------------------------------------------------------------------
+def parse_kmsg_line(boot_unix_us: int, line: str):
+    """Returns (priority, seq, ts_unix_us, message) or raises ValueError, like parseLine."""
+    parts = line.split(";", 1)                                        # watcher.go:294 SplitN(line, ";", 2)
+    if len(parts) < 2:
+        raise ValueError("invalid kmsg; must contain a ';'")
+    meta = parts[0].split(",")
+    if len(meta) < 3:
+        raise ValueError("invalid kmsg: must contain at least 3 ',' separated pieces at the start")
+    def atoi(s):
+        if not re.fullmatch(r"[+-]?\d+", s):
+            raise ValueError("could not parse %r" % s)
+        v = int(s)
+        if not (-(1 << 63) <= v < (1 << 63)):
+            raise ValueError("range")
+        return v
+    prio, seq, usec = atoi(meta[0]), atoi(meta[1]), atoi(meta[2])
+    return prio, seq, boot_unix_us + usec, parts[1]
+
+
+def dedup_key(ts_unix_s: int, message: str) -> str:                   # deduper.go:63-74
+    return "%d-%s" % (ts_unix_s - ts_unix_s % 60, message)
+
+
+# --------------------------------------------------------------------------------------------
+# health evolution     (xid/health_state.go:57-128 ; xid/component.go:614-642)
+# events: list of dicts newest-first: {"name": "error_xid"|"reboot"|"SetHealthy", "type": "Fatal"..,
+#         "xid": int, "actions": [ids] or None}
+# --------------------------------------------------------------------------------------------
+def trim_events_after_set_healthy(events):                            # component.go:630-642
+    for i, e in enumerate(events):
+        if e["name"] == "SetHealthy":
+            return events[:i] if i else []
+    return events
+
+
+def evolve_healthy_state(events, reboot_threshold: int = 2):
+    last_action = None
+    last_xid = None
+    last_health = 0
+    reboot_map: Dict[int, int] = {}
+    for e in reversed(events):
+        if e["name"] == "error_xid":
+            cur = {"Critical": 1, "Fatal": 2}.get(e.get("type", ""), 0)
+            if cur < last_health:
+                continue
+            last_health = cur
+            last_xid = e["xid"]
+            acts = e.get("actions")
+            if acts:
+                acts = list(acts)
+                if acts[0] == ACT_REBOOT:
+                    if e["xid"] not in reboot_map:
+                        reboot_map[e["xid"]] = 0
+                    elif reboot_map[e["xid"]] >= reboot_threshold:
+                        acts[0] = ACT_HW_INSPECTION
+                last_action = acts[:1]
+        elif e["name"] == "reboot":
+            if last_action and last_action[0] in (ACT_REBOOT, ACT_CHECK_APP):
+                last_health, last_action, last_xid = 0, None, None
+            for k in reboot_map:
+                reboot_map[k] += 1
+    return {"health": ["Healthy", "Degraded", "Unhealthy"][last_health], "actions": last_action, "xid": last_xid}
+
+
+# --------------------------------------------------------------------------------------------
+# threshold rules
+# --------------------------------------------------------------------------------------------
+def hw_slowdown_state(event_unix_s: List[int], window_minutes: int, threshold_freq_per_min: float):
+    """hw-slowdown/component.go:383-407: distinct event-minutes / window minutes >= threshold -> Unhealthy."""
+    if window_minutes <= 0:
+        return "Healthy", 0.0
+    mins = {t // 60 for t in event_unix_s}
+    freq = len(mins) / float(window_minutes)
+    return ("Unhealthy" if freq >= threshold_freq_per_min and len(mins) > 0 else "Healthy"), freq
+
+
+# --------------------------------------------------------------------------------------------
+# windowed aggregates  -- PARITY UNPINNED (no reference implementation), definitions in oracle/SPEC.md
+# --------------------------------------------------------------------------------------------
+def total_order_key(x: np.ndarray) -> np.ndarray:
+    """IEEE-754 totalOrder as an unsigned key: flip all bits of negatives, flip the sign bit of positives."""
+    b = np.ascontiguousarray(x, dtype=np.float64).view(np.uint64)
+    neg = (b >> np.uint64(63)).astype(bool)
+    return np.where(neg, ~b, b | np.uint64(1 << 63))
+
+
+def key_to_f64(k: np.ndarray) -> np.ndarray:
+    k = np.asarray(k, dtype=np.uint64)
+    pos = (k >> np.uint64(63)).astype(bool)
+    return np.where(pos, k & np.uint64((1 << 63) - 1), ~k).view(np.float64)
+
+
+def quantile_rank(m: int, q_num: int = 99, q_den: int = 100) -> int:
+    """1-based nearest rank ceil(m*q_num/q_den), clamped to [1, m]."""
+    r = (m * q_num + q_den - 1) // q_den
+    return max(1, min(m, r))
+
+
+def window_aggregates(x: np.ndarray, W: int, thr: float, alpha: float = 0.0, q_num: int = 99, q_den: int = 100):
+    """x: [n] f64 chronological samples of one field.  Returns dict of arrays [ceil(n/W)]."""
+    n = x.shape[0]
+    nw = (n + W - 1) // W
+    if alpha <= 0.0:
+        alpha = 2.0 / (W + 1.0)
+    out = {k: np.zeros(nw, dtype=np.float64) for k in ("min", "max", "mean", "ema", "p99")}
+    out["n_over"] = np.zeros(nw, dtype=np.uint64)
+    e = float(x[0]) if n else 0.0
+    for w in range(nw):
+        seg = x[w * W:min(n, (w + 1) * W)]
+        m = seg.shape[0]
+        k = np.sort(total_order_key(seg))
+        out["min"][w] = key_to_f64(k[:1])[0]
+        out["max"][w] = key_to_f64(k[-1:])[0]
+        out["p99"][w] = key_to_f64(k[quantile_rank(m, q_num, q_den) - 1:][:1])[0]
+        out["mean"][w] = float(np.sum(seg)) / m
+        out["n_over"][w] = int(np.count_nonzero(seg > thr))
+        for v in seg:                                   # ema_t = a*x_t + (1-a)*ema_{t-1}, ema_{-1} = x_0
+            e = alpha * float(v) + (1.0 - alpha) * e
+        out["ema"][w] = e
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# whole-box NVLink / fabric verdict  (nvlink/evaluate_threshold.go:77-188 ; device/fabric_state.go:115-177)
+# implemented in oracle/fabric.py to keep this file focused on the scan path
+# --------------------------------------------------------------------------------------------

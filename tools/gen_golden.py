@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""Extract the reference's own table-driven test vectors and fixtures into tests/golden/*.json.
+
+The reference tests are Go; no Go toolchain exists in this image, so the vectors (inputs and the
+expected values the Go tests assert) are lifted *as data* by parsing the struct-literal tables.
+Every output record carries `src` = reference file:line of the test function it came from.
+
+Run in the build container (needs /root/reference).  Outputs are committed; the GPU box only
+reads tests/golden/.
+"""
+import json
+import os
+import re
+import sys
+
+REF = os.environ.get("GPUD_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests/golden")
+
+TOK = re.compile(r"""
+    (?P<ws>\s+|//[^\n]*|/\*.*?\*/)
+  | (?P<str>"(?:[^"\\]|\\.)*"|`[^`]*`)
+  | (?P<num>-?0[xX][0-9a-fA-F_]+|-?\d[\d_]*(?:\.\d+)?(?:[eE][-+]?\d+)?)
+  | (?P<id>[A-Za-z_][\w\.]*)
+  | (?P<p>[{}\[\](),:+*&\-<>=!|;/%])
+""", re.X | re.S)
+
+
+def unquote(lit):
+    if lit.startswith("`"):
+        return lit[1:-1]
+    body = lit[1:-1]
+    out, i = [], 0
+    simple = {"n": "\n", "t": "\t", '"': '"', "\\": "\\", "'": "'", "r": "\r", "a": "\a", "b": "\b", "f": "\f", "v": "\v"}
+    while i < len(body):
+        c = body[i]
+        if c != "\\":
+            out.append(c); i += 1; continue
+        n = body[i + 1]
+        if n in simple:
+            out.append(simple[n]); i += 2
+        elif n == "x":
+            out.append(chr(int(body[i + 2:i + 4], 16))); i += 4
+        elif n == "u":
+            out.append(chr(int(body[i + 2:i + 6], 16))); i += 6
+        elif n in "01234567":
+            out.append(chr(int(body[i + 1:i + 4], 8))); i += 4
+        else:
+            raise ValueError(n)
+    return "".join(out)
+
+
+def tokenize(src):
+    pos, toks = 0, []
+    while pos < len(src):
+        m = TOK.match(src, pos)
+        if not m:
+            raise ValueError("tokenize at %r" % src[pos:pos + 40])
+        pos = m.end()
+        k = m.lastgroup
+        if k == "ws":
+            continue
+        toks.append((k, m.group(k)))
+    return toks
+
+
+class P:
+    def __init__(self, toks):
+        self.t, self.i = toks, 0
+
+    def peek(self, o=0):
+        return self.t[self.i + o] if self.i + o < len(self.t) else ("eof", "")
+
+    def next(self):
+        x = self.peek(); self.i += 1; return x
+
+    def expect(self, v):
+        x = self.next()
+        assert x[1] == v, (x, v, self.t[max(0, self.i - 8):self.i + 4])
+
+    def skip_type(self):
+        """Skip a type prefix such as []apiv1.RepairActionType, &Foo, map[string]string, *T."""
+        while True:
+            k, v = self.peek()
+            if v in ("&", "*"):
+                self.next()
+            elif v == "[":
+                self.next()
+                while self.peek()[1] != "]":
+                    self.next()
+                self.next()
+            elif k == "id" and v == "map":
+                self.next(); self.expect("[")
+                while self.peek()[1] != "]":
+                    self.next()
+                self.next()
+            elif k == "id" and v == "struct":
+                self.next(); self.expect("{")
+                d = 1
+                while d:
+                    x = self.next()[1]
+                    d += (x == "{") - (x == "}")
+            elif k == "id" and self.peek(1)[1] == "{":
+                self.next()
+                return
+            else:
+                return
+
+    def value(self):
+        k, v = self.peek()
+        if k == "str":
+            s = unquote(self.next()[1])
+            while self.peek()[1] == "+" and self.peek(1)[0] == "str":
+                self.next(); s += unquote(self.next()[1])
+            return s
+        if k == "num":
+            self.next()
+            v = v.replace("_", "")
+            try:
+                return int(v, 0)
+            except ValueError:
+                return float(v)
+        if v == "-" and self.peek(1)[0] == "num":
+            self.next()
+            return -self.value()
+        if v in ("&", "*", "[") or (k == "id" and (self.peek(1)[1] == "{" or v in ("map", "struct"))):
+            self.skip_type()
+            return self.composite()
+        if v == "{":
+            return self.composite()
+        if k == "id":
+            self.next()
+            if self.peek()[1] == "(":     # call: keep as opaque text  fn(args)
+                depth, parts = 0, [v]
+                while True:
+                    x = self.next()
+                    parts.append(x[1])
+                    depth += (x[1] == "(") - (x[1] == ")")
+                    if depth == 0:
+                        break
+                txt = "".join(parts)
+                while self.peek()[1] == ".":   # unlikely
+                    break
+                return {"$call": txt}
+            if v == "true":
+                return True
+            if v == "false":
+                return False
+            if v == "nil":
+                return None
+            return {"$id": v}
+        raise ValueError("value at %r" % (self.t[self.i:self.i + 6],))
+
+    def composite(self):
+        self.expect("{")
+        items, keyed = [], None
+        while self.peek()[1] != "}":
+            if (self.peek()[0] in ("id", "str", "num")) and self.peek(1)[1] == ":":
+                kk = self.next()
+                key = unquote(kk[1]) if kk[0] == "str" else kk[1]
+                self.next()
+                items.append((key, self.value()))
+                keyed = True
+            else:
+                items.append(self.value())
+            # tolerate binary expressions we do not need (e.g. a * b) by skipping to , or }
+            while self.peek()[1] not in (",", "}"):
+                self.next()
+            if self.peek()[1] == ",":
+                self.next()
+        self.expect("}")
+        if keyed:
+            return {k: v for k, v in items}
+        return items
+
+
+def find_func(src, name):
+    m = re.search(r"^func %s\(" % re.escape(name), src, re.M)
+    assert m, name
+    line = src.count("\n", 0, m.start()) + 1
+    # function body ends at next "\n}\n"
+    end = src.index("\n}\n", m.start())
+    return src[m.start():end], line
+
+
+def table(path, func, var=None):
+    """Return rows (list of dict) of the first `[]struct{...}{...}` table in func."""
+    src = open(os.path.join(REF, path)).read()
+    body, line = find_func(src, func)
+    pat = r"(?:%s)\s*:?=\s*\[\]struct\s*\{" % (var or r"\w+")
+    m = re.search(pat, body)
+    assert m, (path, func)
+    decl_end = body.index("}{", m.end())
+    fields = []
+    for ln in body[m.end():decl_end].split("\n"):
+        ln = ln.split("//")[0].strip()
+        if not ln:
+            continue
+        parts = ln.split()
+        names = [p.rstrip(",") for p in parts[:-1]] if len(parts) > 1 else [parts[0]]
+        # "a, b int" declares two fields
+        fields.extend(names if len(parts) > 1 else [])
+    toks = tokenize(body[decl_end + 1:])
+    rows = P(toks).composite()
+    out = []
+    for r in rows:
+        if isinstance(r, list):
+            r = {fields[i]: v for i, v in enumerate(r)}
+        out.append(r)
+    return out, "%s:%d" % (path, line)
+
+
+def ident(v):
+    """apiv1.EventTypeWarning -> 'Warning' etc."""
+    if isinstance(v, dict) and "$id" in v:
+        s = v["$id"].split(".")[-1]
+        for pre in ("EventType", "RepairActionType", "HealthStateType"):
+            if s.startswith(pre):
+                return s[len(pre):]
+        return s
+    if isinstance(v, list):
+        return [ident(x) for x in v]
+    if isinstance(v, dict):
+        return {k: ident(x) for k, x in v.items()}
+    return v
+
+
+def dump(name, obj):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, name), "w") as f:
+        json.dump(obj, f, indent=1, ensure_ascii=False)
+        f.write("\n")
+    n = sum(len(v["rows"]) if isinstance(v, dict) and "rows" in v else 1 for v in obj.values()) if isinstance(obj, dict) else len(obj)
+    print("%-32s %d vectors" % (name, n))
+
+
+def main():
+    X = "components/accelerator/nvidia/xid/"
+    S = "components/accelerator/nvidia/sxid/"
+    g = {}
+    for key, path, fn in [
+        ("extract_xid", X + "kmsg_test.go", "TestExtractNVRMXid"),
+        ("extract_device", X + "kmsg_test.go", "TestExtractNVRMXidDeviceUUID"),
+        ("match", X + "kmsg_test.go", "TestMatch"),
+        ("normalize_bdf", X + "kmsg_test.go", "TestNormalizePCIBDF"),
+        ("extended", X + "kmsg_extended_test.go", "TestExtractNVRMXidInfoExtended"),
+        ("subcode", X + "kmsg_extended_test.go", "TestCalculateSubCode"),
+        ("detail_with_subcode", X + "kmsg_extended_test.go", "TestGetDetailWithSubCode"),
+        ("match_nvlink_examples", X + "kmsg_extended_test.go", "TestMatchNVLinkExamples"),
+        ("nvlink_log_coverage", X + "nvlink_logs_test.go", "Test_NVLinkLogCoverage"),
+    ]:
+        rows, src = table(path, fn)
+        g[key] = {"src": src, "rows": ident(rows)}
+    # single-assert tests
+    g["short_match"] = {"src": X + "kmsg_extended_test.go:350", "rows": [
+        {"line": "NVRM: Xid (PCI:0018:01:00): 149, NETIR Fatal XC0 i0 Link -1 (0x000fe406", "extended_nil": True}]}
+    g["unknown_code"] = {"src": X + "kmsg_test.go:289", "rows": [
+        {"input": "NVRM: Xid (PCI:0000:05:00): 99999, unknown error", "expectNil": True}]}
+    g["status_specific"] = {"src": X + "xid_test.go:13", "rows": [
+        {"xid": 144, "unit": "SAW_MVB", "severity": "Nonfatal", "intrinfo": 0x21, "error_status": 0x8, "event": "Warning"},
+        {"xid": 144, "unit": "SAW_MVB", "severity": "Nonfatal", "intrinfo": 0x21, "error_status": 0x2, "event": "Fatal",
+         "actions_contain": ["RebootSystem"]},
+        {"xid": 144, "unit": "SAW_MVB", "severity": "Nonfatal", "intrinfo": 0x21, "error_status": 0xDEADBEEF, "event": "Warning"}]}
+    # fixture file: 43 dmesg lines -> exactly 5 x (119, PCI:0000:9b:00)   (kmsg_test.go:248-287)
+    lines = open(os.path.join(REF, X, "testdata/dmesg-with-xid-119.log")).read().split("\n")
+    g["dmesg_xid_119"] = {"src": X + "kmsg_test.go:248", "lines": lines,
+                          "rows": [{"xid": 119, "device": "PCI:0000:9b:00"}] * 5}
+    # injectable messages (kmsg.go:278-311): known ones + the generic template
+    src = open(os.path.join(REF, X, "kmsg.go")).read()
+    msgs = {}
+    for m in re.finditer(r"\n\t(\d+): \{\n\t\tPriority: \"(\w+)\",\n\t\tMessage:\s+(\"(?:[^\"\\]|\\.)*\"),", src):
+        msgs[int(m.group(1))] = {"priority": m.group(2), "message": unquote(m.group(3))}
+    assert sorted(msgs) == [63, 64, 69, 74, 79], sorted(msgs)
+    g["inject_messages"] = {"src": X + "kmsg.go:278", "known": {str(k): v for k, v in msgs.items()},
+                            "template": "NVRM: Xid (PCI:0000:04:00): %d, unknown", "rows": []}
+    dump("xid_kmsg.json", g)
+
+    s = {}
+    for key, fn in [("extract_sxid", "TestExtractNVSwitchSXid"), ("extract_device", "TestExtractNVSwitchSXidDeviceUUID"),
+                    ("match", "TestMatch")]:
+        rows, src = table(S + "kmsg_test.go", fn)
+        s[key] = {"src": src, "rows": ident(rows)}
+    dump("sxid_kmsg.json", s)
+
+    # pkg/kmsg parseLine + fixtures
+    K = "pkg/kmsg/"
+    k = {}
+    ksrc = open(os.path.join(REF, K, "watcher_test.go")).read()
+    for fn in re.findall(r"^func (Test\w*[Pp]arse\w*)\(", ksrc, re.M):
+        try:
+            rows, src = table(K + "watcher_test.go", fn)
+            k[fn] = {"src": src, "rows": ident(rows)}
+        except Exception as e:  # noqa
+            print("  skip", fn, type(e).__name__, e)
+    for fx in ("kmsg.1.log", "kmsg.2.peermem.log"):
+        p = os.path.join(REF, K, "testdata", fx)
+        if os.path.exists(p):
+            k["fixture:" + fx] = {"src": K + "testdata/" + fx, "rows": [],
+                                  "records": open(p, encoding="utf-8", errors="surrogateescape").read().split("\n")}
+    dump("pkg_kmsg.json", k)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
