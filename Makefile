@@ -1,0 +1,27 @@
+# Builds libgpud_b200.so (sm_100a only) and the oracle.  `python -c "import __graft_entry__ as g; g.build()"` calls this.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
+SRC := gpud_b200/csrc
+OBJS := $(SRC)/api.o $(SRC)/ring.o $(SRC)/select.o $(SRC)/kmsg_scan.o $(SRC)/fabric.o $(SRC)/catalog.o
+LIB := gpud_b200/libgpud_b200.so
+
+all: $(LIB) oracle
+
+$(SRC)/%.o: $(SRC)/%.cu $(SRC)/internal.h $(SRC)/catalog.h include/gpud_b200.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
+
+$(SRC)/catalog.o: $(SRC)/catalog.cpp $(SRC)/catalog.h $(SRC)/catalog_data.inc include/gpud_b200.h
+	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -f $(SRC)/*.o $(SRC)/*.ptxas.log $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,277 @@
+#!/usr/bin/env python3
+"""bench.py — counter-samples/sec of the telemetry hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config.workload, BASELINE configs[3] per GPU): 512 fields x 1 Mi-sample f64 ring (4 GiB, >> the 126 MB L2, so
+every step streams from HBM), tumbling W = 1000 windows, all six aggregates fused (min/max/mean/EMA/p99/n_over).
+A "step" = one pass of the hot path over the whole ring: the fused window-reduce kernel + the EMA carry kernel
+(+ at N > 1 the 128-byte NVLink/fabric summary all-gather and verdict).  Weak scaling: every GPU owns its own ring.
+
+`value`  : whole-job samples/s with the ring already resident in HBM (CUDA events on the launch stream, max over ranks).
+`e2e`    : same metric through the C ABI from pinned HOST rows: gpud_ring_push (H2D + append kernel) + reduce + D2H
+           of every aggregate, all inside the timed region.
+`roofline`: algorithmic bytes (8 B/sample) / the fused kernel's CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+`cpu_baseline`: the C oracle (oracle/oracle.c, "port": the Go reference cannot be built here and has no windowed
+           aggregation at all) on the host cores, bounded sample, rank 0 only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+F, CAP, W = 512, 1 << 20, 1000
+METRIC = "counter-samples/sec"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(steps, warmup, sample_fields, threads=0):
+    """Times the C oracle on a bounded sample of the same workload: `sample_fields` fields x CAP samples per step."""
+    from oracle import coracle
+    rng = np.random.default_rng(0x67707564)
+    ring = rng.random((sample_fields, CAP)) * 60.0 + 30.0
+    thr = np.full(sample_fields, 88.0)
+    cores = coracle.max_threads() if threads <= 0 else threads
+    for _ in range(warmup):
+        coracle.windows_fields(ring[: max(1, sample_fields // 8)], W, thr, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        coracle.windows_fields(ring, W, thr, threads=cores)
+    dt = (time.perf_counter() - t0) / steps
+    return sample_fields * CAP / dt, dt, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-fields", type=int, default=0, help="fields in the CPU sample (0 = auto, about 10-30 s of CPU work)")
+    ap.add_argument("--no-e2e", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    config = {"workload": "ring 512 fields x 1Mi f64 samples per GPU (4 GiB), W=1000 tumbling, fused min/max/mean/ema/p99/n_over",
+              "n_fields": F, "capacity": CAP, "window": W, "parallelism": "one ring per GPU, no data-path collective (weak)",
+              "l2": "input 4 GiB per GPU >> 126 MB L2; every step re-streams HBM"}
+
+    if a.impl == "reference":
+        # The reference's own CPU path for this metric does not exist (no windowed aggregation in gpud) and Go cannot be
+        # built here; the timed arm is the C oracle port with every host thread.  Rank 0 only.
+        if rank != 0:
+            return 0
+        from oracle import coracle
+        cores = coracle.max_threads()
+        fields = a.cpu_fields or max(8, min(F, cores * 8))
+        v, dt, cores = cpu_leg(max(1, a.steps), a.warmup, fields)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": "%d of 512 fields x 1Mi samples per step (C oracle, pthreads over fields)" % fields},
+                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import gpud_b200 as g
+    import synth
+
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = g.Context([local])
+    thr = np.full(F, 88.0)
+    ring = g.Ring(ctx, F, CAP, W, thresholds=thr, dev=local)
+    stream = torch.cuda.current_stream()
+    ring.set_stream(stream.cuda_stream)
+
+    # ---- synthetic resident data: gauge-like values generated on the device, appended through the real append kernel ----
+    gen = torch.Generator(device=dev).manual_seed(0x67707564 + rank)
+    chunk = 1 << 16
+    for i in range(CAP // chunk):
+        t = torch.rand((chunk, F), dtype=torch.float64, device=dev, generator=gen) * 60.0 + 30.0
+        ring.push_device(t.data_ptr(), chunk)
+    torch.cuda.synchronize()
+    del t
+
+    # fabric leg (N > 1): 128-byte summary per GPU, all-gather over NCCL, verdict kernel
+    fab_send = torch.zeros(128, dtype=torch.uint8, device=dev)
+    fab_all = torch.zeros(128 * world, dtype=torch.uint8, device=dev)
+    raw = g.FabricRaw()
+    raw.gpu_index, raw.nvlink_supported, raw.system_expected_nvlink, raw.n_links = rank, 1, 1, 18
+    for i in range(18):
+        raw.link_feature_enabled[i] = 1
+    for j in range(16):
+        raw.p2p_status[j] = 0 if (j < world and j != rank) else 0xFF
+    raw.fabric_valid, raw.fabric_state, raw.fabric_summary, raw.fabric_health_mask = 1, 3, 1, 0xAA
+
+    def step():
+        ring.reduce()
+        if world > 1:
+            ctx.fabric_pack(raw, fab_send.data_ptr(), dev=local, stream=stream.cuda_stream)
+            dist.all_gather_into_tensor(fab_all, fab_send)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    # per-kernel device time of the dominant kernel: re-run the same step K times reading the library's own events
+    for _ in range(a.steps):
+        ring.reduce()
+        kms.append(ring.kernel_ms())
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        v = ctx.fabric_verdict(fab_all.data_ptr(), world, world, dev=local)
+        assert v.nvlink_health == 0 and v.active == world, v.as_dict()
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / a.steps
+    samples_step = F * CAP * world
+    value = samples_step / (ms_step * 1e-3)
+    k_reduce = float(np.mean([k[0] for k in kms]))
+    k_carry = float(np.mean([k[1] for k in kms]))
+    peak, how = peaks()
+    achieved = F * CAP * 8 / (k_reduce * 1e-3) / 1e9
+
+    # ---- e2e: pinned host rows -> push (H2D + append) -> reduce -> D2H of all aggregates, every step ----
+    e2e = None
+    if not a.no_e2e:
+        rows_chunk = 1 << 18                                   # 1 GiB pinned, pushed 4x per step = the whole 4 GiB ring
+        host = torch.empty((rows_chunk, F), dtype=torch.float64).pin_memory()
+        host.uniform_(30.0, 90.0)
+        nw = (CAP + W - 1) // W
+        outs = {k: np.empty((F, nw), dtype=np.uint32 if k == "n_over" else np.float64) for k in g.OPS}
+        d2h = sum(o.nbytes for o in outs.values())
+
+        def e2e_step():
+            for _ in range(CAP // rows_chunk):
+                ring.push_ptr(host.data_ptr(), rows_chunk)
+            ring.reduce()
+            for k in g.OPS:
+                ctx._check(ring._L.gpud_ring_read(ring._h, g.OPS[k], C.c_void_p(outs[k].ctypes.data), outs[k].nbytes))
+
+        e2e_steps = max(2, min(a.steps, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+        if world > 1:
+            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        e2e = {"value": samples_step / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": F * CAP * 8, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e2e, "steps": e2e_steps}
+        del host
+
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import coracle
+        cores = coracle.max_threads()
+        fields = a.cpu_fields or max(8, min(F, cores * 8))
+        v, dt, cores = cpu_leg(1, 1, fields)
+        cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": "%d of 512 fields x 1Mi samples, one pass (C oracle oracle/oracle.c, pthreads over fields)" % fields}
+
+    ring.close()
+    ctx.close()
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "gpu_launches": (2 + (1 if world > 1 else 0)) * a.steps,
+                "clocks": clocks, "e2e": e2e,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "kernel": "k_window_reduce", "kernel_ms": k_reduce, "carry_kernel_ms": k_carry, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+                             if how == "measured" else "fallback 6650 GB/s (B200_PROFILING.md)", "algorithmic_bytes_per_launch": F * CAP * 8},
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,314 @@
+"""ctypes binding of include/gpud_b200.h (the same surface a cgo shim binds)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpud_b200.so")
+
+OPS = {"min": 0, "max": 1, "mean": 2, "ema": 3, "p99": 4, "n_over": 5}
+EVENT_NAMES = ["Unknown", "Info", "Warning", "Critical", "Fatal"]
+ACTION_WIRE = {1: "IGNORE_NO_ACTION_REQUIRED", 2: "REBOOT_SYSTEM", 3: "HARDWARE_INSPECTION", 4: "CHECK_USER_APP_AND_GPU"}
+SCAN_LINES, SCAN_RAW_KMSG = 0, 1
+MAX_LINKS, MAX_GPUS = 18, 16
+
+
+class GpudError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("gpud_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class RingCfg(C.Structure):
+    _fields_ = [("n_fields", C.c_int32), ("window", C.c_int32), ("capacity", C.c_int64), ("ema_alpha", C.c_double),
+                ("q_num", C.c_int32), ("q_den", C.c_int32), ("thresholds", C.POINTER(C.c_double))]
+
+
+class XidHit(C.Structure):
+    _fields_ = [("unit_index", C.c_int64), ("unit_offset", C.c_int64), ("dev_off", C.c_int64), ("dev_len", C.c_int32),
+                ("kind", C.c_int32), ("code", C.c_int32), ("flags", C.c_uint32), ("sub_code", C.c_int32),
+                ("kmsg_priority", C.c_int32), ("kmsg_seq", C.c_int64), ("kmsg_usec", C.c_int64), ("link", C.c_int64),
+                ("intrinfo", C.c_uint32), ("error_status", C.c_uint32), ("extra", C.c_uint32 * 4), ("n_extra", C.c_int32),
+                ("severity_fatal", C.c_int32), ("xc", C.c_int32), ("unit_name_off", C.c_int64), ("unit_name_len", C.c_int32),
+                ("pid_off", C.c_int64), ("pid_len", C.c_int32), ("pname_off", C.c_int64), ("pname_len", C.c_int32),
+                ("inj_off", C.c_int64), ("inj_len", C.c_int32), ("event_type", C.c_int32), ("n_actions", C.c_int32),
+                ("actions", C.c_int32 * 4), ("rule_index", C.c_int32), ("detail_variant", C.c_int32),
+                ("device", C.c_char * 40), ("unit_name", C.c_char * 40)]
+
+    def as_dict(self) -> dict:
+        na = self.n_actions
+        return {"line": self.unit_index, "offset": self.unit_offset, "kind": self.kind, "code": self.code,
+                "device": self.device.decode("latin-1"), "event_type": self.event_type,
+                "actions": [self.actions[i] for i in range(max(na, 0))], "actions_nil": na < 0,
+                "extended": bool(self.flags & 1), "sub_code": self.sub_code, "unit": self.unit_name.decode("latin-1"),
+                "error_status": self.error_status, "intrinfo": self.intrinfo, "link": self.link,
+                "rule_index": self.rule_index, "variant": self.detail_variant, "flags": self.flags,
+                "extra": [self.extra[i] for i in range(self.n_extra)], "severity_fatal": self.severity_fatal, "xc": self.xc,
+                "kmsg": (self.kmsg_priority, self.kmsg_seq, self.kmsg_usec)}
+
+
+class FabricRaw(C.Structure):
+    _fields_ = [("gpu_index", C.c_uint32), ("nvlink_supported", C.c_uint32), ("system_expected_nvlink", C.c_uint32),
+                ("n_links", C.c_uint32), ("link_feature_enabled", C.c_uint8 * MAX_LINKS), ("pad0", C.c_uint8 * 2),
+                ("link_replay_errors", C.c_uint64 * MAX_LINKS), ("link_recovery_errors", C.c_uint64 * MAX_LINKS),
+                ("link_crc_errors", C.c_uint64 * MAX_LINKS), ("p2p_status", C.c_uint8 * MAX_GPUS), ("fabric_valid", C.c_uint32),
+                ("fabric_state", C.c_uint8), ("fabric_summary", C.c_uint8), ("pad1", C.c_uint8 * 2), ("fabric_status", C.c_int32),
+                ("fabric_health_mask", C.c_uint32), ("clique_id", C.c_uint32)]
+
+
+class FabricLocal(C.Structure):
+    _fields_ = [("gpu_index", C.c_uint32), ("flags", C.c_uint32), ("n_links", C.c_uint32), ("links_enabled_mask", C.c_uint32),
+                ("replay_errors", C.c_uint64), ("recovery_errors", C.c_uint64), ("crc_errors", C.c_uint64),
+                ("p2p_status", C.c_uint8 * MAX_GPUS), ("fabric_state", C.c_uint8), ("fabric_summary", C.c_uint8),
+                ("fabric_issue_bits", C.c_uint8), ("pad0", C.c_uint8), ("fabric_status", C.c_int32),
+                ("fabric_health_mask", C.c_uint32), ("clique_id", C.c_uint32), ("pad1", C.c_uint8 * (128 - 76))]
+
+
+class FabricVerdict(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("nvlink_health", C.c_int32), ("nvlink_reason", C.c_int32), ("required", C.c_int32),
+                ("active", C.c_int32), ("inactive", C.c_int32), ("unsupported", C.c_int32), ("p2p_expected_pairs", C.c_int32),
+                ("p2p_probed_pairs", C.c_int32), ("p2p_ok_pairs", C.c_int32), ("p2p_ok_gpu_mask", C.c_uint32),
+                ("p2p_observed_status_mask", C.c_uint32), ("active_mask", C.c_uint32), ("inactive_mask", C.c_uint32),
+                ("unsupported_mask", C.c_uint32), ("fabric_healthy", C.c_int32), ("fabric_unhealthy_gpu_mask", C.c_uint32),
+                ("fabric_issue_bits", C.c_uint8 * MAX_GPUS), ("total_replay", C.c_uint64), ("total_recovery", C.c_uint64),
+                ("total_crc", C.c_uint64)]
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "fabric_issue_bits"}
+        d["fabric_issue_bits"] = list(self.fabric_issue_bits)
+        return d
+
+
+# every symbol include/gpud_b200.h declares (tests check the library exports each one)
+SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
+           "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
+           "gpud_ring_push_device", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_xid_classify",
+           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint",
+           "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
+           "gpud_fabric_gather_p2p"]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libgpud_b200.so (fails loudly if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GpudError(-2, "%s is missing: build it with `make` (or __graft_entry__.build())" % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    sig = {
+        "gpud_abi_version": (i32, []), "gpud_sizeof": (i32, [i32]),
+        "gpud_ctx_create": (i32, [C.POINTER(i32), i32, C.POINTER(vp)]), "gpud_ctx_destroy": (i32, [vp]),
+        "gpud_last_error": (i32, [vp, C.c_char_p, i32]),
+        "gpud_host_alloc": (i32, [i64, C.POINTER(vp)]), "gpud_host_free": (i32, [vp]),
+        "gpud_ring_create": (i32, [vp, i32, C.POINTER(RingCfg), C.POINTER(vp)]), "gpud_ring_destroy": (i32, [vp]),
+        "gpud_ring_set_stream": (i32, [vp, vp]), "gpud_ring_push": (i32, [vp, vp, i64]), "gpud_ring_push_device": (i32, [vp, vp, i64]),
+        "gpud_ring_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
+        "gpud_ring_reduce": (i32, [vp]), "gpud_ring_sync": (i32, [vp]),
+        "gpud_ring_kernel_ms": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]), "gpud_ring_read": (i32, [vp, i32, vp, i64]),
+        "gpud_ring_result_ptr": (i32, [vp, i32, C.POINTER(vp)]), "gpud_ring_reduce_range": (i32, [vp, i64, vp, vp]),
+        "gpud_kmsg_scan": (i32, [vp, i32, vp, i64, i32, C.POINTER(XidHit), i64, C.POINTER(i64), C.POINTER(i64)]),
+        "gpud_kmsg_scan_device": (i32, [vp, i32, vp, i64, i32, C.POINTER(XidHit), i64, C.POINTER(i64), C.POINTER(i64), vp]),
+        "gpud_xid_classify": (i32, [vp, i32, C.POINTER(XidHit), i64]),
+        "gpud_hit_detail_json": (i32, [C.POINTER(XidHit), i64, C.c_char_p, i32]),
+        "gpud_xid_description": (C.c_char_p, [i32, i32]), "gpud_xid_mnemonic": (C.c_char_p, [i32]),
+        "gpud_sxid_name": (C.c_char_p, [i32]), "gpud_nvlink_rule_hint": (C.c_char_p, [i32]),
+        "gpud_fabric_pack": (i32, [vp, i32, C.POINTER(FabricRaw), vp, vp]),
+        "gpud_fabric_verdict_device": (i32, [vp, i32, vp, i32, i32, C.POINTER(FabricVerdict), vp]),
+        "gpud_comm_unique_id": (i32, [vp]), "gpud_comm_init": (i32, [vp, i32, i32, i32, vp]),
+        "gpud_fabric_gather": (i32, [vp, i32, C.POINTER(FabricRaw), i32, C.POINTER(FabricLocal), C.POINTER(FabricVerdict)]),
+        "gpud_fabric_gather_p2p": (i32, [vp, C.POINTER(FabricRaw), i32, C.POINTER(FabricLocal), C.POINTER(FabricVerdict)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg)):
+        if L.gpud_sizeof(which) != C.sizeof(st):
+            raise GpudError(-1, "ABI layout mismatch for %s: C %d vs ctypes %d" % (st.__name__, L.gpud_sizeof(which), C.sizeof(st)))
+    _lib = L
+    return L
+
+
+class Context:
+    """gpud_ctx: one per process, naming the CUDA devices it drives."""
+
+    def __init__(self, devices: Sequence[int] = (0,)):
+        self._L = lib()
+        self.devices = list(devices)
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = self._L.gpud_ctx_create(arr, len(self.devices), C.byref(h))
+        if rc:
+            raise GpudError(rc, "gpud_ctx_create failed (no CUDA device? this path has no CPU fallback)")
+        self._h = h
+
+    def _check(self, rc: int):
+        if rc:
+            buf = C.create_string_buffer(512)
+            self._L.gpud_last_error(self._h, buf, 512)
+            raise GpudError(rc, buf.value.decode("utf-8", "replace"))
+
+    def close(self):
+        if self._h:
+            self._L.gpud_ctx_destroy(self._h)
+            self._h = None
+
+    # ---- kmsg scan ----
+    def kmsg_scan(self, buf: bytes, mode: int = SCAN_LINES, dev: Optional[int] = None, cap: int = 1 << 16):
+        """Scan host bytes; returns (hits: List[XidHit], n_units)."""
+        dev = self.devices[0] if dev is None else dev
+        n = len(buf)
+        src = (C.c_char * max(n, 1)).from_buffer_copy(buf if n else b"\0")
+        while True:
+            hits = (XidHit * cap)()
+            nh, nu = C.c_int64(), C.c_int64()
+            rc = self._L.gpud_kmsg_scan(self._h, dev, C.cast(src, C.c_void_p), n, mode, hits, cap, C.byref(nh), C.byref(nu))
+            if rc == -4 and nh.value > cap:
+                cap = int(nh.value)
+                continue
+            self._check(rc)
+            return [hits[i] for i in range(nh.value)], nu.value
+
+    def kmsg_scan_device(self, dev_ptr: int, length: int, mode: int = SCAN_LINES, dev: Optional[int] = None, cap: int = 1 << 16,
+                         stream: int = 0):
+        dev = self.devices[0] if dev is None else dev
+        hits = (XidHit * cap)()
+        nh, nu = C.c_int64(), C.c_int64()
+        rc = self._L.gpud_kmsg_scan_device(self._h, dev, C.c_void_p(dev_ptr), length, mode, hits, cap, C.byref(nh), C.byref(nu),
+                                           C.c_void_p(stream))
+        self._check(rc)
+        return [hits[i] for i in range(nh.value)], nu.value
+
+    def classify(self, hits: List[XidHit], dev: Optional[int] = None) -> List[XidHit]:
+        dev = self.devices[0] if dev is None else dev
+        arr = (XidHit * len(hits))(*hits)
+        self._check(self._L.gpud_xid_classify(self._h, dev, arr, len(hits)))
+        return [arr[i] for i in range(len(hits))]
+
+    def hit_json(self, hit: XidHit, unix_seconds: int = 0) -> str:
+        buf = C.create_string_buffer(4096)
+        rc = self._L.gpud_hit_detail_json(C.byref(hit), unix_seconds, buf, 4096)
+        if rc:
+            raise GpudError(rc, "gpud_hit_detail_json")
+        return buf.value.decode("utf-8")
+
+    # ---- fabric ----
+    def fabric_pack(self, raw: FabricRaw, dev_send_ptr: int, dev: Optional[int] = None, stream: int = 0):
+        dev = self.devices[0] if dev is None else dev
+        self._check(self._L.gpud_fabric_pack(self._h, dev, C.byref(raw), C.c_void_p(dev_send_ptr), C.c_void_p(stream)))
+
+    def fabric_verdict(self, dev_all_ptr: int, n: int, at_least: int = 0, dev: Optional[int] = None, stream: int = 0) -> FabricVerdict:
+        dev = self.devices[0] if dev is None else dev
+        v = FabricVerdict()
+        self._check(self._L.gpud_fabric_verdict_device(self._h, dev, C.c_void_p(dev_all_ptr), n, at_least, C.byref(v), C.c_void_p(stream)))
+        return v
+
+    def fabric_gather_p2p(self, raws: Sequence[FabricRaw], at_least: int = 0):
+        n = len(self.devices)
+        arr = (FabricRaw * n)(*raws)
+        allrec = (FabricLocal * n)()
+        vs = (FabricVerdict * n)()
+        self._check(self._L.gpud_fabric_gather_p2p(self._h, arr, at_least, allrec, vs))
+        return [allrec[i] for i in range(n)], [vs[i] for i in range(n)]
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes, dev: Optional[int] = None):
+        dev = self.devices[0] if dev is None else dev
+        b = C.create_string_buffer(unique_id, 128)
+        self._check(self._L.gpud_comm_init(self._h, dev, n_ranks, rank, b))
+
+    def fabric_gather(self, raw: FabricRaw, n_ranks: int, at_least: int = 0, dev: Optional[int] = None):
+        dev = self.devices[0] if dev is None else dev
+        allrec = (FabricLocal * n_ranks)()
+        v = FabricVerdict()
+        self._check(self._L.gpud_fabric_gather(self._h, dev, C.byref(raw), at_least, allrec, C.byref(v)))
+        return [allrec[i] for i in range(n_ranks)], v
+
+
+def comm_unique_id() -> bytes:
+    b = C.create_string_buffer(128)
+    rc = lib().gpud_comm_unique_id(b)
+    if rc:
+        raise GpudError(rc, "gpud_comm_unique_id (libnccl.so.2 not loadable?)")
+    return b.raw
+
+
+class Ring:
+    """gpud_ring: device-resident [F][CAP] sample ring with fused windowed aggregates."""
+
+    def __init__(self, ctx: Context, n_fields: int, capacity: int, window: int, thresholds: Optional[np.ndarray] = None,
+                 ema_alpha: float = 0.0, q_num: int = 0, q_den: int = 0, dev: Optional[int] = None):
+        self.ctx, self._L = ctx, ctx._L
+        self.F, self.cap, self.W = n_fields, capacity, window
+        cfg = RingCfg(n_fields, window, capacity, ema_alpha, q_num, q_den, None)
+        if thresholds is not None:
+            self._thr = np.ascontiguousarray(thresholds, dtype=np.float64)
+            assert self._thr.shape == (n_fields,)
+            cfg.thresholds = self._thr.ctypes.data_as(C.POINTER(C.c_double))
+        h = C.c_void_p()
+        ctx._check(self._L.gpud_ring_create(ctx._h, ctx.devices[0] if dev is None else dev, C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._L.gpud_ring_destroy(self._h)
+            self._h = None
+
+    def set_stream(self, cuda_stream: int):
+        self.ctx._check(self._L.gpud_ring_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def push(self, rows: np.ndarray):
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        assert rows.ndim == 2 and rows.shape[1] == self.F
+        self.ctx._check(self._L.gpud_ring_push(self._h, C.c_void_p(rows.ctypes.data), rows.shape[0]))
+
+    def push_ptr(self, host_ptr: int, n_rows: int):
+        self.ctx._check(self._L.gpud_ring_push(self._h, C.c_void_p(host_ptr), n_rows))
+
+    def push_device(self, dev_ptr: int, n_rows: int):
+        self.ctx._check(self._L.gpud_ring_push_device(self._h, C.c_void_p(dev_ptr), n_rows))
+
+    def counts(self):
+        t, c, w = C.c_int64(), C.c_int64(), C.c_int64()
+        self.ctx._check(self._L.gpud_ring_counts(self._h, C.byref(t), C.byref(c), C.byref(w)))
+        return t.value, c.value, w.value
+
+    def reduce(self):
+        self.ctx._check(self._L.gpud_ring_reduce(self._h))
+
+    def sync(self):
+        self.ctx._check(self._L.gpud_ring_sync(self._h))
+
+    def kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self.ctx._check(self._L.gpud_ring_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def read(self, op: str) -> np.ndarray:
+        _, _, nw = self.counts()
+        dt = np.uint32 if op == "n_over" else np.float64
+        out = np.empty((self.F, nw), dtype=dt)
+        self.ctx._check(self._L.gpud_ring_read(self._h, OPS[op], C.c_void_p(out.ctypes.data), out.nbytes))
+        return out
+
+    def result_ptr(self, op: str) -> int:
+        p = C.c_void_p()
+        self.ctx._check(self._L.gpud_ring_result_ptr(self._h, OPS[op], C.byref(p)))
+        return p.value
+
+    def reduce_all(self) -> dict:
+        self.reduce()
+        return {k: self.read(k) for k in OPS}
+
+    def reduce_range(self, last_n: int = 0) -> dict:
+        f64 = np.empty((5, self.F), dtype=np.float64)
+        nov = np.empty((self.F,), dtype=np.uint32)
+        self.ctx._check(self._L.gpud_ring_reduce_range(self._h, last_n, C.c_void_p(f64.ctypes.data), C.c_void_p(nov.ctypes.data)))
+        return {"min": f64[0], "max": f64[1], "mean": f64[2], "ema": f64[3], "p99": f64[4], "n_over": nov}

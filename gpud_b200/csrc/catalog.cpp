@@ -1,0 +1,335 @@
+// catalog.cpp — host-side construction of the device lookup tables and the catalog string accessors.
+// Follows xid/xid.go:2997-3090 (sub-code detail maps + operational overrides), :3099-3218 (rule matching inputs),
+// :3222-3283 (severity / bucket -> event type, bucket -> action).
+#include "catalog.h"
+
+#include <ctype.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gpud_b200.h"
+#include "catalog_data.inc"
+
+namespace {
+
+int event_from_severity(const char* s) {        // xid.go:3263-3272
+  std::string v(s);
+  while (!v.empty() && isspace((unsigned char)v.back())) v.pop_back();
+  size_t b = 0;
+  while (b < v.size() && isspace((unsigned char)v[b])) ++b;
+  v = v.substr(b);
+  for (auto& c : v) c = (char)tolower((unsigned char)c);
+  if (v == "fatal" || v == "fatal**" || v == "link fatal" || v == "link fatal?") return GPUD_EVENT_FATAL;
+  if (v == "non-fatal" || v == "non-fatal*") return GPUD_EVENT_WARNING;
+  return GPUD_EVENT_UNKNOWN;
+}
+
+bool in_list(const char* s, std::initializer_list<const char*> l) {
+  for (const char* x : l)
+    if (!strcmp(s, x)) return true;
+  return false;
+}
+
+int event_from_bucket(const char* b) {          // xid.go:3222-3246
+  if (in_list(b, {"CONTACT_SUPPORT", "CHECK_MECHANICALS", "WORKFLOW_NVLINK_ERR", "WORKFLOW_NVLINK5_ERR", "XID_154", "XID_154_EVAL", "RESTART_BM"}))
+    return GPUD_EVENT_FATAL;
+  if (in_list(b, {"RESET_GPU", "RESTART_APP", "RESTART_VM", "CHECK_UVM", "WORKFLOW_XID_48", "WORKFLOW_XID_45", "UPDATE_SWFW"}))
+    return GPUD_EVENT_CRITICAL;
+  if (in_list(b, {"IGNORE", ""})) return GPUD_EVENT_INFO;
+  return GPUD_EVENT_WARNING;
+}
+
+int action_from_bucket(const char* b) {         // xid.go:3248-3261 ; 0 = none
+  if (in_list(b, {"CONTACT_SUPPORT", "CHECK_MECHANICALS", "WORKFLOW_NVLINK_ERR", "WORKFLOW_NVLINK5_ERR", "XID_154", "XID_154_EVAL"}))
+    return GPUD_ACT_HARDWARE_INSPECTION;
+  if (in_list(b, {"RESET_GPU", "RESTART_BM", "RESTART_VM", "CHECK_UVM"})) return GPUD_ACT_REBOOT_SYSTEM;
+  if (in_list(b, {"RESTART_APP", "WORKFLOW_XID_45", "WORKFLOW_XID_48", "UPDATE_SWFW"})) return GPUD_ACT_CHECK_USER_APP_AND_GPU;
+  if (in_list(b, {"IGNORE", ""})) return GPUD_ACT_IGNORE_NO_ACTION_REQUIRED;
+  return 0;
+}
+
+const char* action_wire(int a) {                // api/v1/types.go:183-203
+  switch (a) {
+    case GPUD_ACT_IGNORE_NO_ACTION_REQUIRED: return "IGNORE_NO_ACTION_REQUIRED";
+    case GPUD_ACT_REBOOT_SYSTEM: return "REBOOT_SYSTEM";
+    case GPUD_ACT_HARDWARE_INSPECTION: return "HARDWARE_INSPECTION";
+    case GPUD_ACT_CHECK_USER_APP_AND_GPU: return "CHECK_USER_APP_AND_GPU";
+  }
+  return "";
+}
+
+// pattern "0/1/-" x32, MSB first -> (care, value); kind per catalog.h
+void compile_pattern(const char* p, uint32_t* care, uint32_t* val, uint8_t* kind) {
+  *care = *val = 0;
+  const size_t n = strlen(p);
+  if (n == 0) { *kind = 0; return; }
+  if (n != 32) { *kind = 2; return; }
+  for (int i = 0; i < 32; ++i) {
+    const int bit = 31 - i;
+    if (p[i] == '1') { *care |= 1u << bit; *val |= 1u << bit; }
+    else if (p[i] == '0') { *care |= 1u << bit; }
+    else if (p[i] != '-') { *kind = 2; return; }
+  }
+  *kind = 1;
+}
+
+// sampleFromPattern (xid.go:3127-3145): value with '1' bits set, false if empty / malformed
+bool sample_from_pattern(const char* p, uint32_t* v) {
+  uint32_t care, val;
+  uint8_t kind;
+  compile_pattern(p, &care, &val, &kind);
+  if (kind != 1) return false;
+  *v = val;
+  return true;
+}
+
+std::string normalize_unit(const std::string& s) {   // xid.go:3203-3218
+  size_t b = 0, e = s.size();
+  while (b < e && isspace((unsigned char)s[b])) ++b;
+  while (e > b && isspace((unsigned char)s[e - 1])) --e;
+  std::string o;
+  for (size_t i = b; i < e; ++i) {
+    char c = (char)toupper((unsigned char)s[i]);
+    if (c == '-') c = '_';
+    if ((c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_') o.push_back(c);
+  }
+  return o;
+}
+
+std::vector<std::string> unit_aliases(const std::string& u) {   // xid.go:3188-3201
+  std::vector<std::string> al;
+  std::string cur;
+  for (char c : u) {
+    if (c == '/' || c == ',' || c == '(' || c == ')' || c == ' ') {
+      if (!cur.empty()) al.push_back(cur);
+      cur.clear();
+    } else cur.push_back(c);
+  }
+  if (!cur.empty()) al.push_back(cur);
+  if (al.empty()) al.push_back(u);
+  al.push_back(u);
+  return al;
+}
+
+gpud_t_detail make_detail(int event, int n_actions, const int* acts) {
+  gpud_t_detail d;
+  memset(&d, 0, sizeof d);
+  d.present = 1;
+  d.event = (int8_t)event;
+  d.n_actions = (int8_t)n_actions;
+  for (int i = 0; i < 4 && i < n_actions; ++i) d.actions[i] = (int8_t)acts[i];
+  return d;
+}
+
+// mergeSuggestedActions (xid.go:3317-3336): set union, sorted by the wire string
+void merge_actions(gpud_t_detail* base, const gpud_t_detail& add) {
+  if (base->n_actions < 0) { base->n_actions = add.n_actions; memcpy(base->actions, add.actions, 4); return; }
+  if (add.n_actions < 0) return;
+  std::vector<int> set;
+  for (int i = 0; i < base->n_actions; ++i) set.push_back(base->actions[i]);
+  for (int i = 0; i < add.n_actions; ++i) set.push_back(add.actions[i]);
+  std::sort(set.begin(), set.end(), [](int a, int b) { return strcmp(action_wire(a), action_wire(b)) < 0; });
+  set.erase(std::unique(set.begin(), set.end()), set.end());
+  base->n_actions = (int8_t)std::min<size_t>(4, set.size());
+  for (int i = 0; i < base->n_actions; ++i) base->actions[i] = (int8_t)set[i];
+}
+
+gpud_tables g_tables;
+std::once_flag g_once;
+
+gpud_t_sub* find_sub(gpud_t_sub* arr, int n, int xid, int sc, bool with_status, uint32_t st) {
+  for (int i = 0; i < n; ++i)
+    if (arr[i].xid == xid && arr[i].sub_code == sc && (!with_status || arr[i].error_status == st)) return &arr[i];
+  return nullptr;
+}
+
+void build_tables() {
+  gpud_tables& T = g_tables;
+  memset(&T, 0, sizeof T);
+  for (int i = 0; i < GPUD_CAT_N_XID; ++i) {
+    const gpud_cat_xid_row& r = GPUD_CAT_XID[i];
+    // SuggestedActionsByGPUd == nil is encoded as n_actions -1
+    T.xid[r.code] = make_detail(r.event, r.n_actions > 0 ? r.n_actions : -1, r.actions);
+  }
+  T.n_rules = GPUD_CAT_N_RULES;
+  for (int i = 0; i < GPUD_CAT_N_RULES; ++i) {
+    const gpud_cat_rule_row& r = GPUD_CAT_RULES[i];
+    gpud_t_rule& o = T.rules[i];
+    o.xid = r.xid;
+    o.error_status = r.error_status;
+    compile_pattern(r.pat_v1, &o.v1_care, &o.v1_val, &o.v1_kind);
+    compile_pattern(r.pat_v2, &o.v2_care, &o.v2_val, &o.v2_kind);
+    int ev = event_from_severity(r.severity);
+    if (ev == GPUD_EVENT_UNKNOWN) ev = event_from_bucket(r.resolution);
+    o.rule_event = (int8_t)ev;
+    const int act = action_from_bucket(r.resolution);
+    o.rule_n_actions = act ? 1 : -1;
+    o.rule_action = (int8_t)act;
+    o.has_hint = (r.investigatory[0] && strcmp(r.investigatory, "IGNORE") && strcmp(r.investigatory, "CONTACT_SUPPORT")) ? 1 : 0;
+    std::vector<std::string> al;
+    for (auto& a : unit_aliases(r.unit)) {
+      std::string n = normalize_unit(a);
+      if (std::find(al.begin(), al.end(), n) == al.end()) al.push_back(n);
+    }
+    o.n_alias = 0;
+    for (auto& a : al) {
+      if (o.n_alias >= GPUD_T_ALIAS_MAX || a.size() >= GPUD_T_ALIAS_LEN) continue;   // sizes asserted by the generator's data
+      snprintf(o.alias[o.n_alias++], GPUD_T_ALIAS_LEN, "%s", a.c_str());
+    }
+  }
+  // buildNVLinkSubCodeDetails (xid.go:2997-3060)
+  for (int i = 0; i < GPUD_CAT_N_RULES; ++i) {
+    const gpud_cat_rule_row& r = GPUD_CAT_RULES[i];
+    if (r.xid < 144 || r.xid > 150) continue;
+    uint32_t sample;
+    int sc;
+    if (sample_from_pattern(r.pat_v2, &sample)) sc = (int)((sample >> 20) & 0x3F);
+    else if (sample_from_pattern(r.pat_v1, &sample)) sc = (int)((sample >> 20) & 0x3F);
+    else continue;
+    T.has_sub_map[r.xid] = 1;
+    const gpud_t_detail base = T.xid[r.xid];
+    if (!base.present) continue;
+    gpud_t_detail d = base;
+    if (T.rules[i].rule_event != GPUD_EVENT_UNKNOWN) d.event = T.rules[i].rule_event;
+    if (T.rules[i].rule_n_actions > 0) { d.n_actions = 1; memset(d.actions, 0, 4); d.actions[0] = T.rules[i].rule_action; }
+    gpud_t_sub* ex = find_sub(T.by_status, T.n_by_status, r.xid, sc, true, r.error_status);
+    if (ex) {
+      d.event = std::max(ex->d.event, d.event);                    // maxEventType: rank == numeric id
+      gpud_t_detail merged = ex->d;
+      merge_actions(&merged, d);
+      d.n_actions = merged.n_actions;
+      memcpy(d.actions, merged.actions, 4);
+      ex->d = d;
+    } else {
+      gpud_t_sub& s = T.by_status[T.n_by_status++];
+      s.xid = r.xid; s.sub_code = sc; s.error_status = r.error_status; s.d = d; s.variant = 0;
+    }
+    gpud_t_sub* agg = find_sub(T.by_sub, T.n_by_sub, r.xid, sc, false, 0);
+    if (!agg) {
+      agg = &T.by_sub[T.n_by_sub++];
+      agg->xid = r.xid; agg->sub_code = sc; agg->error_status = 0; agg->d = base; agg->variant = 0;
+    }
+    merge_actions(&agg->d, d);
+  }
+  // applyOperationalOverrides (xid.go:3062-3089)
+  const int over[2][2] = {{4, 1}, {10, 2}};
+  for (auto& ov : over) {
+    gpud_t_sub* s = find_sub(T.by_sub, T.n_by_sub, 149, ov[0], false, 0);
+    if (!s) continue;
+    const int hw = GPUD_ACT_HARDWARE_INSPECTION;
+    s->d = make_detail(GPUD_EVENT_FATAL, 1, &hw);
+    s->variant = ov[1];
+    for (int i = 0; i < T.n_by_status; ++i)
+      if (T.by_status[i].xid == 149 && T.by_status[i].sub_code == ov[0]) { T.by_status[i].d = s->d; T.by_status[i].variant = ov[1]; }
+  }
+  T.n_sxid = GPUD_CAT_N_SXID;
+  for (int i = 0; i < GPUD_CAT_N_SXID; ++i) {
+    const gpud_cat_sxid_row& r = GPUD_CAT_SXID[i];
+    T.sxid[i].code = r.sxid;
+    T.sxid[i].d = make_detail(r.event, r.n_actions > 0 ? r.n_actions : -1, r.actions);
+  }
+  std::sort(T.sxid, T.sxid + T.n_sxid, [](const gpud_t_sxid& a, const gpud_t_sxid& b) { return a.code < b.code; });
+}
+
+const gpud_cat_xid_row* xid_row(int code) {
+  for (int i = 0; i < GPUD_CAT_N_XID; ++i)
+    if (GPUD_CAT_XID[i].code == code) return &GPUD_CAT_XID[i];
+  return nullptr;
+}
+
+void json_escape(std::string& o, const char* s) {
+  for (; *s; ++s) {
+    unsigned char c = (unsigned char)*s;
+    switch (c) {   // encoding/json escapes: \" \\ \n \r \t, <,>,& as \u00XX, control chars as \u00XX
+      case '"': o += "\\\""; break;
+      case '\\': o += "\\\\"; break;
+      case '\n': o += "\\n"; break;
+      case '\r': o += "\\r"; break;
+      case '\t': o += "\\t"; break;
+      case '<': case '>': case '&': { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; break; }
+      default:
+        if (c < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+        else o.push_back((char)c);
+    }
+  }
+}
+
+}  // namespace
+
+const gpud_tables* gpud_host_tables(void) {
+  std::call_once(g_once, build_tables);
+  return &g_tables;
+}
+
+extern "C" const char* gpud_xid_description(int32_t code, int32_t variant) {
+  if (variant == 1) return "NVLINK: NETIR Link Event - Possible NVLink cartridge error (contact provider)";        // xid.go:3067
+  if (variant == 2) return "NVLINK: NETIR Link Event - Physical layer retransmission timeout (contact provider)";  // xid.go:3080
+  const gpud_cat_xid_row* r = xid_row(code);
+  return r ? r->description : "";
+}
+extern "C" const char* gpud_xid_mnemonic(int32_t code) {
+  const gpud_cat_xid_row* r = xid_row(code);
+  return r ? r->mnemonic : "";
+}
+extern "C" const char* gpud_sxid_name(int32_t code) {
+  for (int i = 0; i < GPUD_CAT_N_SXID; ++i)
+    if (GPUD_CAT_SXID[i].sxid == code) return GPUD_CAT_SXID[i].name;
+  return "";
+}
+extern "C" const char* gpud_nvlink_rule_hint(int32_t idx) {
+  if (idx < 0 || idx >= GPUD_CAT_N_RULES) return "";
+  const char* h = GPUD_CAT_RULES[idx].investigatory;
+  if (!h[0] || !strcmp(h, "IGNORE") || !strcmp(h, "CONTACT_SUPPORT")) return "";
+  return h;
+}
+
+// xidErrorEventDetail JSON (xid/health_state.go:284-315), field order and omitempty as encoding/json emits them;
+// time is RFC3339 UTC seconds like metav1.Time.
+extern "C" int32_t gpud_hit_detail_json(const gpud_xid_hit* h, int64_t unix_seconds, char* out, int32_t cap) {
+  if (!h || !out || cap < 2) return GPUD_E_INVALID;
+  if (h->kind == GPUD_KIND_SXID) {   // sxid events persist only the decimal code (sxid/component.go, health_state.go:113-142)
+    const int n = snprintf(out, (size_t)cap, "%d", h->code);
+    return n < cap ? GPUD_OK : GPUD_E_CAPACITY;
+  }
+  std::string o = "{\"time\":";
+  if (unix_seconds == 0) {
+    o += "null";
+  } else {
+    time_t t = (time_t)unix_seconds;
+    struct tm tmv;
+    gmtime_r(&t, &tmv);
+    char tb[40];
+    strftime(tb, sizeof tb, "\"%Y-%m-%dT%H:%M:%SZ\"", &tmv);
+    o += tb;
+  }
+  o += ",\"data_source\":\"kmsg\",\"device_uuid\":\"";
+  json_escape(o, h->device);
+  o += "\",\"xid\":" + std::to_string(h->code);
+  const bool ext = (h->flags & GPUD_HIT_EXTENDED) != 0;
+  if (ext && h->sub_code != 0) o += ",\"sub_code\":" + std::to_string(h->sub_code);
+  if (ext && h->unit_name[0]) { o += ",\"sub_code_description\":\""; json_escape(o, h->unit_name); o += "\""; }
+  if (ext && h->error_status != 0) o += ",\"error_status\":" + std::to_string(h->error_status);
+  const char* hint = (h->flags & GPUD_HIT_HAS_RULE) ? gpud_nvlink_rule_hint(h->rule_index) : "";
+  if (hint[0]) { o += ",\"investigatory_hint\":\""; json_escape(o, hint); o += "\""; }
+  const char* desc = gpud_xid_description(h->code, h->detail_variant);
+  if (desc[0]) { o += ",\"description\":\""; json_escape(o, desc); o += "\""; }
+  if (h->n_actions >= 0) {
+    o += ",\"suggested_actions_by_gpud\":{\"repair_actions\":[";
+    for (int i = 0; i < h->n_actions; ++i) {
+      if (i) o += ",";
+      o += "\"";
+      o += action_wire(h->actions[i]);
+      o += "\"";
+    }
+    o += "]}";
+  }
+  o += "}";
+  if ((int)o.size() + 1 > cap) return GPUD_E_CAPACITY;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return GPUD_OK;
+}

@@ -1,0 +1,74 @@
+// internal.h — shared by the translation units of libgpud_b200.so (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gpud_b200.h"
+
+struct gpud_scan_state;   // kmsg_scan.cu
+struct gpud_comm_state;   // fabric.cu
+
+struct gpud_ctx {
+  std::vector<int> devs;
+  std::mutex mu;
+  std::string last_error;
+  std::vector<gpud_scan_state*> scan;   // per dev slot, lazily created
+  std::vector<gpud_comm_state*> comm;   // per dev slot
+  std::vector<void*> fabric_tables;     // per dev slot: device table [GPUD_MAX_GPUS] x 128 B (+flags) for p2p gather
+  int sm_count = 148;
+};
+
+inline int32_t gpud_fail(gpud_ctx* ctx, int32_t code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+inline int32_t gpud_fail(gpud_ctx* ctx, int32_t code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    ctx->last_error = buf;
+  }
+  return code;
+}
+
+#define GPUD_CUDA(ctx, expr)                                                                      \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return gpud_fail((ctx), GPUD_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int gpud_dev_slot(gpud_ctx* ctx, int dev) {
+  for (size_t i = 0; i < ctx->devs.size(); ++i)
+    if (ctx->devs[i] == dev) return (int)i;
+  return -1;
+}
+
+// ---- device helpers --------------------------------------------------------------------------
+#ifdef __CUDACC__
+// IEEE-754 totalOrder key (oracle/SPEC.md): unsigned compare of the key == totalOrder of the doubles.
+__host__ __device__ __forceinline__ unsigned long long gpud_f64_key(unsigned long long bits) {
+  return bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ unsigned long long gpud_key_f64bits(unsigned long long key) {
+  return key ^ ((key >> 63) ? 0x8000000000000000ull : ~0ull);
+}
+#endif
+
+// view of a ring range after the per-window pass (ring.cu -> select.cu)
+struct gpud_range_view {
+  const double* ring; int F; int64_t cap, start, n; int Wp, nw;
+  const double *w_min, *w_max, *w_mean, *w_ema; const uint32_t* w_nover;
+  int q_num, q_den; cudaStream_t stream; gpud_ctx* ctx; int dev, sm_count;
+};
+int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v);
+
+void gpud_scan_state_free(gpud_scan_state*);
+void gpud_comm_state_free(gpud_comm_state*);

@@ -1,0 +1,806 @@
+// kmsg_scan.cu — kernels K5 (anchor filter + per-unit match automata) and K6 (catalog classification).
+//
+// Replaces, byte-exactly, the Go regexp path of
+//   xid.Match      components/accelerator/nvidia/xid/kmsg.go:202-245  (regexes :22 R1, :29 R2, :38 R3, :43 R4)
+//   sxid.Match     components/accelerator/nvidia/sxid/kmsg.go:58-73   (regexes :17 R5, :20 R6)
+//   catalog        xid/xid.go:74-117 (GetDetail...), :2954-2995 (detailFromNVLinkInfo), :3099-3218 (rule lookup)
+// applied to every unit (line / kmsg record) of a buffer, as in xid/kmsg_test.go:252-267 and xid/component.go:274-299.
+//
+// Structure (all HBM-bound integer/byte work, no tensor cores):
+//   k_scan_filter   streams the buffer once with 128-bit loads; per 512-byte warp chunk it counts unit separators and
+//                   flags the two rare bytes that every pattern needs ('V' of "NVRM:", 'X' of "SXid"); flagged bytes are
+//                   verified against their literal context and appended to a candidate list.  1 B/byte algorithmic.
+//   k_scan_prefix   exclusive scan of the per-chunk separator counts (unit numbering).
+//   k_scan_match    one thread per candidate anchor; the first anchor of a unit runs the exact leftmost-first automata
+//                   (every quantifier in R1-R6 is deterministic once the anchor is fixed; see the notes at each matcher),
+//                   then classifies against the device-resident catalog tables.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "catalog.h"
+#include "internal.h"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kChunk = 512;                 // bytes per warp step
+constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid ("
+constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVIDIA GPU "
+constexpr unsigned long long kFamS = 3ull;  // "SXid"
+
+struct ScanBuf {
+  const uint8_t* p;
+  int64_t len;
+};
+
+__device__ __forceinline__ int ld8(const ScanBuf& b, int64_t i) { return (i >= 0 && i < b.len) ? (int)__ldg(b.p + i) : -1; }
+__device__ __forceinline__ bool is_ws(int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\f' || c == '\r'; }   // RE2 \s
+__device__ __forceinline__ bool is_digit(int c) { return c >= '0' && c <= '9'; }
+__device__ __forceinline__ bool is_hex(int c) { return is_digit(c) || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F'); }
+__device__ __forceinline__ bool is_upper_us(int c) { return (c >= 'A' && c <= 'Z') || c == '_'; }
+
+// literal compare inside [.., e)
+template <int N>
+__device__ __forceinline__ bool lit_at(const ScanBuf& b, int64_t i, int64_t e, const char (&s)[N]) {
+  if (i + (N - 1) > e) return false;
+#pragma unroll
+  for (int k = 0; k < N - 1; ++k)
+    if (__ldg(b.p + i + k) != (uint8_t)s[k]) return false;
+  return true;
+}
+
+// family of an anchor at `a` ("NVRM:" already verified), 0 if the context rules it out for R1-R4
+__device__ unsigned long long nvrm_family(const ScanBuf& b, int64_t a, int64_t e) {
+  const int64_t p = a + 5;
+  if (lit_at(b, p, e, " Xid (")) return kFamX;
+  int64_t q = p;
+  while (q < e && is_ws(ld8(b, q))) ++q;
+  if (q == p) return 0;
+  if (lit_at(b, q, e, "GPU ") || lit_at(b, q, e, "The NVIDIA GPU ")) return kFamB;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5a filter
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void filter_rare(const ScanBuf& b, int64_t off, const uint4& w, unsigned mv, int mode, unsigned& sep,
+                                            unsigned long long* cands, unsigned long long* n_cand, unsigned long long cand_cap) {
+  const unsigned words[4] = {w.x, w.y, w.z, w.w};
+  for (int k = 0; k < 16; ++k) {
+    const int c = (words[k >> 2] >> ((k & 3) * 8)) & 0xff;
+    const int64_t i = off + k;
+    if (i >= b.len) break;
+    if (mode == GPUD_SCAN_RAW_KMSG && c == '\n') {
+      if (ld8(b, i + 1) == ' ') --sep;            // continuation line of the same record: not a separator
+    }
+    if (!mv) continue;
+    unsigned long long fam = 0;
+    if (c == 'V') {
+      if (ld8(b, i - 1) == 'N' && ld8(b, i + 1) == 'R' && ld8(b, i + 2) == 'M' && ld8(b, i + 3) == ':') fam = nvrm_family(b, i - 1, b.len);
+    } else if (c == 'X') {
+      if (ld8(b, i - 1) == 'S' && ld8(b, i + 1) == 'i' && ld8(b, i + 2) == 'd') fam = kFamS;
+    }
+    if (fam) {
+      const unsigned long long slot = atomicAdd(n_cand, 1ull);
+      if (slot < cand_cap) cands[slot] = (unsigned long long)(i - 1) | (fam << 60);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, int mode, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
+                                                      unsigned long long* n_cand, unsigned long long cand_cap) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t n_chunks = (b.len + kChunk - 1) / kChunk;
+  const bool aligned = ((uintptr_t)b.p & 15) == 0;
+  // each warp takes 4 consecutive chunks per step: four independent 128-bit loads in flight per lane
+  for (int64_t c0 = warp_g * 4; c0 < n_chunks; c0 += n_warps * 4) {
+    uint4 w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t off = (c0 + u) * kChunk + lane * 16;
+      w[u] = make_uint4(0, 0, 0, 0);
+      if (aligned && off + 16 <= b.len) {
+        w[u] = __ldcs(reinterpret_cast<const uint4*>(b.p + off));
+      } else if (off < b.len) {                  // ragged tail / unaligned caller buffer: bytewise
+        unsigned t[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 16 && off + k < b.len; ++k) t[k >> 2] |= (unsigned)__ldg(b.p + off + k) << ((k & 3) * 8);
+        w[u] = make_uint4(t[0], t[1], t[2], t[3]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t chunk = c0 + u;
+      if (chunk >= n_chunks) break;              // warp-uniform
+      const int64_t off = chunk * kChunk + lane * 16;
+      const unsigned nl = (__vcmpeq4(w[u].x, 0x0a0a0a0au) & 0x01010101u) + (__vcmpeq4(w[u].y, 0x0a0a0a0au) & 0x01010101u) +
+                          (__vcmpeq4(w[u].z, 0x0a0a0a0au) & 0x01010101u) + (__vcmpeq4(w[u].w, 0x0a0a0a0au) & 0x01010101u);
+      unsigned sep = (nl * 0x01010101u) >> 24;   // horizontal byte sum (each byte <= 4)
+      const unsigned mv = (__vcmpeq4(w[u].x, 0x56565656u) | __vcmpeq4(w[u].x, 0x58585858u)) | (__vcmpeq4(w[u].y, 0x56565656u) | __vcmpeq4(w[u].y, 0x58585858u)) |
+                          (__vcmpeq4(w[u].z, 0x56565656u) | __vcmpeq4(w[u].z, 0x58585858u)) | (__vcmpeq4(w[u].w, 0x56565656u) | __vcmpeq4(w[u].w, 0x58585858u));
+      if (mv || (mode == GPUD_SCAN_RAW_KMSG && nl)) filter_rare(b, off, w[u], mv, mode, sep, cands, n_cand, cand_cap);
+      sep = __reduce_add_sync(kFull, sep);
+      if (lane == 0) chunk_sep[chunk] = sep;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5b exclusive scan of chunk separator counts (single block; n is len/512)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan_prefix(const uint32_t* __restrict__ in, unsigned long long* __restrict__ out, int64_t n,
+                                                       unsigned long long* total) {
+  __shared__ unsigned long long s[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t b = t * per, e = min(n, b + per);
+  unsigned long long acc = 0;
+  for (int64_t i = b; i < e; ++i) acc += in[i];
+  s[t] = acc;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const unsigned long long v = t >= o ? s[t - o] : 0;
+    __syncthreads();
+    s[t] += v;
+    __syncthreads();
+  }
+  unsigned long long run = s[t] - acc;
+  for (int64_t i = b; i < e; ++i) {
+    out[i] = run;
+    run += in[i];
+  }
+  if (t == 1023) *total = s[1023];
+}
+
+// ---------------------------------------------------------------------------------------------
+// number parsing with Go semantics
+// ---------------------------------------------------------------------------------------------
+// strconv.Atoi on [-]digits: false on int64 range error (kmsg.go:75,126,163)
+__device__ bool go_atoi(const ScanBuf& b, int64_t s, int64_t e, long long* out) {
+  bool neg = false;
+  if (s < e && (ld8(b, s) == '-' || ld8(b, s) == '+')) { neg = ld8(b, s) == '-'; ++s; }
+  if (s >= e) return false;
+  unsigned long long v = 0;
+  const unsigned long long lim = neg ? 0x8000000000000000ull : 0x7fffffffffffffffull;
+  for (int64_t i = s; i < e; ++i) {
+    const int c = ld8(b, i);
+    if (!is_digit(c)) return false;
+    const unsigned d = (unsigned)(c - '0');
+    if (v > (lim - d) / 10ull) return false;
+    v = v * 10ull + d;
+  }
+  *out = neg ? (long long)(0ull - v) : (long long)v;
+  return true;
+}
+// strconv.ParseUint("0x…", 0, 32)
+__device__ bool go_parse_hex32(const ScanBuf& b, int64_t s, int64_t e, uint32_t* out) {
+  unsigned long long v = 0;
+  for (int64_t i = s + 2; i < e; ++i) {
+    const int c = ld8(b, i);
+    const unsigned d = is_digit(c) ? c - '0' : (c | 0x20) - 'a' + 10;
+    v = v * 16ull + d;
+    if (v > 0xffffffffull) return false;
+  }
+  *out = (uint32_t)v;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the automata.  [s, e) is the unit's message span; every function returns the match for the leftmost anchor
+// at which the whole pattern succeeds (Go FindStringSubmatch: leftmost-first).
+// ---------------------------------------------------------------------------------------------
+struct R1Match { int64_t dev_s, dev_e, code_s, code_e; };
+// R1  NVRM: Xid \(((?:PCI:)?[0-9a-fA-F:]+)\).*?: (\d+),
+//  - "PCI:" is taken iff present ('P','I' are not in the class, so the no-prefix branch dies on it);
+//  - the class run is maximal and must be followed by ')' (a shorter run would be followed by a class byte);
+//  - `.*?` stops at the first ": " digits+ "," and cannot cross '\n'.
+__device__ bool match_r1(const ScanBuf& b, int64_t s, int64_t e, R1Match* m) {
+  for (int64_t a = s; a + 11 <= e; ++a) {
+    if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM: Xid (")) continue;
+    int64_t p = a + 11, q = p;
+    if (lit_at(b, q, e, "PCI:")) q += 4;
+    int64_t r = q;
+    while (r < e && (is_hex(ld8(b, r)) || ld8(b, r) == ':')) ++r;
+    if (r == q || r >= e || ld8(b, r) != ')') continue;
+    for (int64_t i = r + 1; i < e; ++i) {
+      const int c = ld8(b, i);
+      if (c == '\n') break;
+      if (c == ':' && ld8(b, i + 1) == ' ' && is_digit(ld8(b, i + 2))) {
+        int64_t j = i + 2;
+        while (j < e && is_digit(ld8(b, j))) ++j;
+        if (j < e && ld8(b, j) == ',') {
+          m->dev_s = p; m->dev_e = r; m->code_s = i + 2; m->code_e = j;
+          return true;
+        }
+      }
+    }
+  }
+  return false;
+}
+
+struct R2Match {
+  int64_t dev_s, dev_e, code_s, code_e, pid_s, pid_e, name_s, name_e, unit_s, unit_e, inj_s, inj_e, link_s, link_e;
+  int64_t hex_s[6], hex_e[6];
+  int n_hex, fatal, xc;
+};
+__device__ __forceinline__ bool skip_ws1(const ScanBuf& b, int64_t& i, int64_t e) {   // \s+
+  const int64_t i0 = i;
+  while (i < e && is_ws(ld8(b, i))) ++i;
+  return i > i0;
+}
+__device__ __forceinline__ bool take_hexword(const ScanBuf& b, int64_t& i, int64_t e, int64_t* hs, int64_t* he) {   // 0x[0-9a-fA-F]+
+  if (ld8(b, i) != '0' || ld8(b, i + 1) != 'x') return false;
+  int64_t j = i + 2;
+  while (j < e && is_hex(ld8(b, j))) ++j;
+  if (j == i + 2) return false;
+  *hs = i; *he = j; i = j;
+  return true;
+}
+// R2 (kmsg.go:29).  Deterministic given the anchor: every greedy run is maximal and followed by a byte outside its class;
+// the optional ", pid=…, name=…" group is exclusive with the bare ", " continuation ('p' is not in [A-Z_]).
+__device__ bool match_r2(const ScanBuf& b, int64_t s, int64_t e, R2Match* m) {
+  for (int64_t a = s; a + 15 <= e; ++a) {
+    if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM: Xid (PCI:")) continue;
+    int64_t i = a + 15;
+    m->dev_s = i;
+    while (i < e && (is_hex(ld8(b, i)) || ld8(b, i) == ':')) ++i;
+    if (i == m->dev_s) continue;
+    m->dev_e = i;
+    if (!lit_at(b, i, e, "): ")) continue;
+    i += 3;
+    m->code_s = i;
+    while (i < e && is_digit(ld8(b, i))) ++i;
+    if (i == m->code_s) continue;
+    m->code_e = i;
+    m->pid_s = m->pid_e = m->name_s = m->name_e = 0;
+    if (lit_at(b, i, e, ", pid=")) {
+      int64_t j = i + 6;
+      m->pid_s = j;
+      while (j < e && is_digit(ld8(b, j))) ++j;
+      if (j == m->pid_s) continue;
+      m->pid_e = j;
+      if (!lit_at(b, j, e, ", name=")) continue;
+      j += 7;
+      m->name_s = j;
+      while (j < e && ld8(b, j) != ',') ++j;        // [^,]+ (newlines included)
+      if (j == m->name_s) continue;
+      m->name_e = j;
+      i = j;
+    }
+    if (!lit_at(b, i, e, ", ")) continue;
+    i += 2;
+    m->unit_s = i;
+    while (i < e && is_upper_us(ld8(b, i))) ++i;
+    if (i == m->unit_s) continue;
+    if (i + 1 < e && ld8(b, i) == '/' && is_upper_us(ld8(b, i + 1))) {
+      ++i;
+      while (i < e && is_upper_us(ld8(b, i))) ++i;
+    }
+    m->unit_e = i;
+    if (!skip_ws1(b, i, e)) continue;
+    if (lit_at(b, i, e, "Nonfatal")) { m->fatal = 0; i += 8; }
+    else if (lit_at(b, i, e, "Fatal")) { m->fatal = 1; i += 5; }
+    else continue;
+    if (!skip_ws1(b, i, e)) continue;
+    if (!lit_at(b, i, e, "XC") || (ld8(b, i + 2) != '0' && ld8(b, i + 2) != '1') || i + 3 > e) continue;
+    m->xc = ld8(b, i + 2) - '0';
+    i += 3;
+    if (!skip_ws1(b, i, e)) continue;
+    if (i >= e || ld8(b, i) != 'i') continue;
+    m->inj_s = i;
+    ++i;
+    { const int64_t d0 = i; while (i < e && is_digit(ld8(b, i))) ++i; if (i == d0) continue; }
+    m->inj_e = i;
+    if (!skip_ws1(b, i, e)) continue;
+    if (!lit_at(b, i, e, "Link")) continue;
+    i += 4;
+    if (!skip_ws1(b, i, e)) continue;
+    m->link_s = i;
+    if (i < e && ld8(b, i) == '-') ++i;
+    { const int64_t d0 = i; while (i < e && is_digit(ld8(b, i))) ++i; if (i == d0) continue; }
+    m->link_e = i;
+    if (!skip_ws1(b, i, e)) continue;
+    if (i >= e || ld8(b, i) != '(') continue;
+    ++i;
+    if (!take_hexword(b, i, e, &m->hex_s[0], &m->hex_e[0])) continue;
+    if (!skip_ws1(b, i, e)) continue;
+    if (!take_hexword(b, i, e, &m->hex_s[1], &m->hex_e[1])) continue;
+    m->n_hex = 2;
+    for (int k = 0; k < 4; ++k) {                  // (?:\s+(0x…))? x4: a failed group leaves the cursor where it was
+      int64_t j = i;
+      if (!skip_ws1(b, j, e)) break;
+      if (!take_hexword(b, j, e, &m->hex_s[m->n_hex], &m->hex_e[m->n_hex])) break;
+      ++m->n_hex;
+      i = j;
+    }
+    return true;
+  }
+  return false;
+}
+
+// BDF  (?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2}  followed by "\.0"; the two shapes are exclusive (byte 2 is hex vs ':')
+__device__ bool take_bdf(const ScanBuf& b, int64_t i, int64_t e, int64_t* bs, int64_t* be) {
+  auto hx = [&](int64_t k) { return k < e && is_hex(ld8(b, k)); };
+  if (hx(i) && hx(i + 1) && hx(i + 2) && hx(i + 3) && ld8(b, i + 4) == ':' && hx(i + 5) && hx(i + 6) && ld8(b, i + 7) == ':' && hx(i + 8) && hx(i + 9) && i + 10 <= e) {
+    *bs = i; *be = i + 10;
+    return true;
+  }
+  if (hx(i) && hx(i + 1) && ld8(b, i + 2) == ':' && hx(i + 3) && hx(i + 4) && i + 5 <= e) {
+    *bs = i; *be = i + 5;
+    return true;
+  }
+  return false;
+}
+// R4  NVRM:\s+GPU (BDF)\.0:\s+GPU has fallen off the bus\.?
+__device__ bool match_r4(const ScanBuf& b, int64_t s, int64_t e, int64_t* bs, int64_t* be) {
+  for (int64_t a = s; a + 5 <= e; ++a) {
+    if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM:")) continue;
+    int64_t i = a + 5;
+    if (!skip_ws1(b, i, e)) continue;
+    if (!lit_at(b, i, e, "GPU ")) continue;
+    i += 4;
+    if (!take_bdf(b, i, e, bs, be)) continue;
+    i = *be;
+    if (!lit_at(b, i, e, ".0:")) continue;
+    i += 3;
+    if (!skip_ws1(b, i, e)) continue;
+    if (!lit_at(b, i, e, "GPU has fallen off the bus")) continue;
+    return true;
+  }
+  return false;
+}
+// R3  (?s)NVRM:\s+The NVIDIA GPU (BDF)\.0.*?fallen off the bus and is not responding to commands\.
+__device__ bool match_r3(const ScanBuf& b, int64_t s, int64_t e, int64_t* bs, int64_t* be) {
+  for (int64_t a = s; a + 5 <= e; ++a) {
+    if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM:")) continue;
+    int64_t i = a + 5;
+    if (!skip_ws1(b, i, e)) continue;
+    if (!lit_at(b, i, e, "The NVIDIA GPU ")) continue;
+    i += 15;
+    if (!take_bdf(b, i, e, bs, be)) continue;
+    i = *be;
+    if (!lit_at(b, i, e, ".0")) continue;
+    i += 2;
+    for (int64_t k = i; k < e; ++k)
+      if (ld8(b, k) == 'f' && lit_at(b, k, e, "fallen off the bus and is not responding to commands.")) return true;
+  }
+  return false;
+}
+// R5  SXid.*?: (\d+),
+__device__ bool match_r5(const ScanBuf& b, int64_t s, int64_t e, int64_t* cs, int64_t* ce) {
+  for (int64_t a = s; a + 4 <= e; ++a) {
+    if (ld8(b, a) != 'S' || !lit_at(b, a, e, "SXid")) continue;
+    for (int64_t i = a + 4; i < e; ++i) {
+      const int c = ld8(b, i);
+      if (c == '\n') break;
+      if (c == ':' && ld8(b, i + 1) == ' ' && is_digit(ld8(b, i + 2))) {
+        int64_t j = i + 2;
+        while (j < e && is_digit(ld8(b, j))) ++j;
+        if (j < e && ld8(b, j) == ',') { *cs = i + 2; *ce = j; return true; }
+      }
+    }
+  }
+  return false;
+}
+// R6  SXid \((PCI:[0-9a-fA-F:\.]+)\)
+__device__ bool match_r6(const ScanBuf& b, int64_t s, int64_t e, int64_t* ds, int64_t* de) {
+  for (int64_t a = s; a + 10 <= e; ++a) {
+    if (ld8(b, a) != 'S' || !lit_at(b, a, e, "SXid (PCI:")) continue;
+    int64_t i = a + 10;
+    while (i < e && (is_hex(ld8(b, i)) || ld8(b, i) == ':' || ld8(b, i) == '.')) ++i;
+    if (i == a + 10 || i >= e || ld8(b, i) != ')') continue;
+    *ds = a + 6; *de = i;
+    return true;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6 classification against the device tables
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void set_detail(gpud_xid_hit* h, const gpud_t_detail& d) {
+  h->event_type = d.event;
+  h->n_actions = d.n_actions;
+  for (int i = 0; i < 4; ++i) h->actions[i] = (i < d.n_actions) ? d.actions[i] : 0;
+}
+
+__device__ bool pattern_ok(uint8_t kind, uint32_t care, uint32_t val, uint32_t intrinfo) {   // xid.go:3147-3172
+  if (kind == 0) return true;
+  if (kind == 2) return false;
+  return (intrinfo & care) == val;
+}
+
+// normalizeUnit(log unit) == normalizeUnit(alias) for any alias (xid.go:3174-3218)
+__device__ bool unit_matches(const gpud_t_rule& r, const char* unit) {
+  char norm[GPUD_T_ALIAS_LEN];
+  int n = 0;
+  // TrimSpace + ToUpper + '-'->'_' + keep [A-Z0-9_]
+  for (int i = 0; unit[i] && n < GPUD_T_ALIAS_LEN - 1; ++i) {
+    int c = (unsigned char)unit[i];
+    if (c >= 'a' && c <= 'z') c -= 32;
+    if (c == '-') c = '_';
+    if ((c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_') norm[n++] = (char)c;
+  }
+  norm[n] = 0;
+  if (n == 0) return false;
+  for (int a = 0; a < r.n_alias; ++a) {
+    int i = 0;
+    while (r.alias[a][i] && r.alias[a][i] == norm[i]) ++i;
+    if (r.alias[a][i] == 0 && norm[i] == 0) return true;
+  }
+  return false;
+}
+
+// detailFromNVLinkInfo (xid.go:2954-2995); returns false when the base code is unknown
+__device__ bool classify_extended(const gpud_tables* T, gpud_xid_hit* h) {
+  const int xid = h->code;
+  if (xid <= 0 || xid >= GPUD_T_MAX_XID || !T->xid[xid].present) return false;
+  const gpud_t_detail base = T->xid[xid];
+  gpud_t_detail d = base;
+  int variant = 0;
+  bool found = false;
+  for (int i = 0; i < T->n_by_status && !found; ++i)      // getDetailWithSubCodeAndStatus (xid.go:97-107)
+    if (T->by_status[i].xid == xid && T->by_status[i].sub_code == h->sub_code && T->by_status[i].error_status == h->error_status) {
+      d = T->by_status[i].d; variant = T->by_status[i].variant; found = true;
+    }
+  if (!found && T->has_sub_map[xid]) {                    // getDetailWithSubCode (xid.go:79-93)
+    for (int pass = 0; pass < 2 && !found; ++pass) {
+      const int want = pass == 0 ? h->sub_code : 0;
+      for (int i = 0; i < T->n_by_sub && !found; ++i)
+        if (T->by_sub[i].xid == xid && T->by_sub[i].sub_code == want) { d = T->by_sub[i].d; variant = T->by_sub[i].variant; found = true; }
+    }
+  }
+  h->rule_index = -1;
+  for (int i = 0; i < T->n_rules; ++i) {                  // lookupNVLinkRule (xid.go:3099-3114), table order
+    const gpud_t_rule& r = T->rules[i];
+    if (r.xid != xid || r.error_status != h->error_status) continue;
+    if (!unit_matches(r, h->unit_name)) continue;
+    if (pattern_ok(r.v2_kind, r.v2_care, r.v2_val, h->intrinfo) || pattern_ok(r.v1_kind, r.v1_care, r.v1_val, h->intrinfo)) {
+      h->rule_index = i;
+      h->flags |= GPUD_HIT_HAS_RULE;
+      if (r.rule_event != GPUD_EVENT_UNKNOWN) d.event = r.rule_event;
+      if (r.rule_n_actions > 0) { d.n_actions = 1; d.actions[0] = r.rule_action; d.actions[1] = d.actions[2] = d.actions[3] = 0; }
+      break;
+    }
+  }
+  const int log_ev = h->severity_fatal ? GPUD_EVENT_FATAL : GPUD_EVENT_WARNING;   // eventTypeFromLogSeverity
+  if (log_ev > d.event) d.event = (int8_t)log_ev;
+  if (d.n_actions < 0) { d.n_actions = base.n_actions; for (int i = 0; i < 4; ++i) d.actions[i] = base.actions[i]; }
+  set_detail(h, d);
+  h->detail_variant = variant;
+  return true;
+}
+
+__device__ bool classify_plain_xid(const gpud_tables* T, gpud_xid_hit* h) {   // GetDetail (xid.go:74-77)
+  const int xid = h->code;
+  if (xid <= 0 || xid >= GPUD_T_MAX_XID || !T->xid[xid].present) return false;
+  set_detail(h, T->xid[xid]);
+  h->rule_index = -1;
+  h->detail_variant = 0;
+  return true;
+}
+
+__device__ bool classify_sxid(const gpud_tables* T, gpud_xid_hit* h) {        // sxid.GetDetail (sxid/sxid.go:32-35)
+  int lo = 0, hi = T->n_sxid - 1;
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    if (T->sxid[mid].code == h->code) { set_detail(h, T->sxid[mid].d); h->rule_index = -1; h->detail_variant = 0; return true; }
+    if (T->sxid[mid].code < h->code) lo = mid + 1; else hi = mid - 1;
+  }
+  return false;
+}
+
+__device__ void copy_span(const ScanBuf& b, int64_t s, int64_t e, char* dst, int cap, const char* prefix) {
+  int n = 0;
+  if (prefix) for (; prefix[n]; ++n) dst[n] = prefix[n];
+  for (int64_t i = s; i < e && n < cap - 1; ++i) dst[n++] = (char)ld8(b, i);
+  dst[n] = 0;
+}
+
+// xid.Match on the span [s, e)  (kmsg.go:202-245)
+__device__ bool xid_match_unit(const ScanBuf& g, int64_t s, int64_t e, const gpud_tables* T, gpud_xid_hit* h) {
+  const ScanBuf b{g.p, e};      // every byte access of the automata is bounded by the unit end
+  R2Match m2;
+  if (match_r2(b, s, e, &m2)) {                         // ExtractNVRMXidInfoExtended (kmsg.go:116-183)
+    long long code, link;
+    uint32_t intr, es;
+    if (go_atoi(b, m2.code_s, m2.code_e, &code) && go_parse_hex32(b, m2.hex_s[0], m2.hex_e[0], &intr) &&
+        go_parse_hex32(b, m2.hex_s[1], m2.hex_e[1], &es) && go_atoi(b, m2.link_s, m2.link_e, &link) && code > 0 && code < GPUD_T_MAX_XID) {
+      h->kind = GPUD_KIND_XID; h->code = (int32_t)code; h->flags = GPUD_HIT_EXTENDED;
+      h->intrinfo = intr; h->error_status = es; h->link = link; h->sub_code = (int32_t)((intr >> 20) & 0x3F);
+      h->severity_fatal = m2.fatal; h->xc = m2.xc;
+      h->n_extra = 0;
+      for (int k = 2; k < m2.n_hex; ++k) {
+        uint32_t v;
+        if (go_parse_hex32(b, m2.hex_s[k], m2.hex_e[k], &v)) h->extra[h->n_extra++] = v;
+      }
+      h->unit_name_off = m2.unit_s; h->unit_name_len = (int32_t)(m2.unit_e - m2.unit_s);
+      h->pid_off = m2.pid_s; h->pid_len = (int32_t)(m2.pid_e - m2.pid_s);
+      h->pname_off = m2.name_s; h->pname_len = (int32_t)(m2.name_e - m2.name_s);
+      h->inj_off = m2.inj_s; h->inj_len = (int32_t)(m2.inj_e - m2.inj_s);
+      copy_span(b, m2.unit_s, m2.unit_e, h->unit_name, 40, nullptr);
+      if (h->unit_name_len >= 40) h->flags |= GPUD_HIT_DEV_TRUNCATED;   // inline copy cut; no catalog alias is that long
+      if (classify_extended(T, h)) {
+        h->dev_off = m2.dev_s; h->dev_len = (int32_t)(m2.dev_e - m2.dev_s);
+        copy_span(b, m2.dev_s, m2.dev_e, h->device, 40, "PCI:");      // kmsg.go:206-208
+        if (h->dev_len + 4 > 39) h->flags |= GPUD_HIT_DEV_TRUNCATED;
+        return true;
+      }
+      // base code unknown -> fall through to the combined regex, like Match does
+      h->flags = 0; h->n_extra = 0; h->sub_code = 0; h->intrinfo = h->error_status = 0; h->link = 0; h->unit_name[0] = 0;
+      h->unit_name_len = h->pid_len = h->pname_len = h->inj_len = 0; h->severity_fatal = h->xc = 0;
+    }
+  }
+  R1Match m1;
+  if (match_r1(b, s, e, &m1)) {                         // ExtractNVRMXidInfo (kmsg.go:73-80)
+    long long code;
+    if (go_atoi(b, m1.code_s, m1.code_e, &code) && code != 0) {
+      if (code < 0 || code >= GPUD_T_MAX_XID) return false;       // GetDetail miss => nil, no fall-through (kmsg.go:219-222)
+      h->kind = GPUD_KIND_XID; h->code = (int32_t)code; h->flags = 0;
+      if (!classify_plain_xid(T, h)) return false;
+      h->dev_off = m1.dev_s; h->dev_len = (int32_t)(m1.dev_e - m1.dev_s);
+      copy_span(b, m1.dev_s, m1.dev_e, h->device, 40, nullptr);
+      if (h->dev_len > 39) h->flags |= GPUD_HIT_DEV_TRUNCATED;
+      return true;
+    }
+  }
+  int64_t bs, be;
+  if (match_r4(b, s, e, &bs, &be) || match_r3(b, s, e, &bs, &be)) {   // extractFallenOffBusXidInfo (kmsg.go:247-257)
+    h->kind = GPUD_KIND_XID; h->code = 79; h->flags = GPUD_HIT_FALLEN_OFF_BUS;
+    if (!classify_plain_xid(T, h)) return false;
+    h->dev_off = bs; h->dev_len = (int32_t)(be - bs);
+    copy_span(b, bs, be, h->device, 40, (be - bs) == 5 ? "PCI:0000:" : "PCI:");   // normalizePCIBDF (kmsg.go:259-268)
+    return true;
+  }
+  return false;
+}
+
+__device__ bool sxid_match_unit(const ScanBuf& g, int64_t s, int64_t e, const gpud_tables* T, gpud_xid_hit* h) {   // sxid/kmsg.go:58-73
+  const ScanBuf b{g.p, e};
+  int64_t cs, ce;
+  if (!match_r5(b, s, e, &cs, &ce)) return false;
+  long long code;
+  if (!go_atoi(b, cs, ce, &code) || code <= 0 || code > 0x7fffffffll) return false;
+  h->kind = GPUD_KIND_SXID; h->code = (int32_t)code; h->flags = 0;
+  if (!classify_sxid(T, h)) return false;
+  int64_t ds, de;
+  h->device[0] = 0; h->dev_off = 0; h->dev_len = 0;
+  if (match_r6(b, s, e, &ds, &de)) {
+    h->dev_off = ds; h->dev_len = (int32_t)(de - ds);
+    copy_span(b, ds, de, h->device, 40, nullptr);
+    if (h->dev_len > 39) h->flags |= GPUD_HIT_DEV_TRUNCATED;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5c: one thread per candidate anchor
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool is_sep(const ScanBuf& b, int64_t i, int mode) {
+  if (ld8(b, i) != '\n') return false;
+  return mode == GPUD_SCAN_LINES || ld8(b, i + 1) != ' ';
+}
+
+__global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const unsigned long long* __restrict__ cands,
+                                                     const unsigned long long* __restrict__ n_cand, unsigned long long cand_cap,
+                                                     const unsigned long long* __restrict__ chunk_prefix, const gpud_tables* __restrict__ T,
+                                                     gpud_xid_hit* hits, unsigned long long hit_cap, unsigned long long* n_hits) {
+  const unsigned long long n = min(*n_cand, cand_cap);
+  for (unsigned long long ci = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long cv = cands[ci];
+    const unsigned long long fam = cv >> 60;
+    const int64_t a = (int64_t)(cv & ((1ull << 60) - 1));
+    // unit bounds
+    int64_t us = a;
+    while (us > 0 && !is_sep(b, us - 1, mode)) --us;
+    int64_t ue = a;
+    while (ue < b.len && !is_sep(b, ue, mode)) ++ue;
+    // message span
+    int64_t ms = us;
+    long long k_prio = 0, k_seq = 0, k_usec = 0;
+    if (mode == GPUD_SCAN_RAW_KMSG) {                    // parseLine (pkg/kmsg/watcher.go:292-332)
+      int64_t semi = us;
+      while (semi < ue && ld8(b, semi) != ';') ++semi;
+      if (semi >= ue) continue;                          // no ';' -> parse error -> record skipped (watcher.go:161-165)
+      int64_t f0 = us, fs[3], fe[3];
+      int nf = 0;
+      for (int64_t i = us; i <= semi; ++i) {
+        if (i == semi || ld8(b, i) == ',') {
+          if (nf < 3) { fs[nf] = f0; fe[nf] = i; }
+          ++nf;
+          f0 = i + 1;
+        }
+      }
+      if (nf < 3) continue;
+      if (!go_atoi(b, fs[0], fe[0], &k_prio) || !go_atoi(b, fs[1], fe[1], &k_seq) || !go_atoi(b, fs[2], fe[2], &k_usec)) continue;
+      ms = semi + 1;
+      if (a < ms) continue;
+    }
+    // only the first anchor of this family group in the unit does the work
+    bool first = true;
+    if (fam == kFamS) {
+      for (int64_t i = ms; i < a && first; ++i)
+        if (ld8(b, i) == 'S' && lit_at(b, i, ue, "SXid")) first = false;
+    } else {
+      for (int64_t i = ms; i < a && first; ++i)
+        if (ld8(b, i) == 'N' && lit_at(b, i, ue, "NVRM:") && nvrm_family(b, i, ue)) first = false;
+    }
+    if (!first) continue;
+    if (fam != kFamS && !nvrm_family(b, a, ue)) continue;   // the filter judged the context against the buffer end, not the unit end
+    gpud_xid_hit h;
+    memset(&h, 0, sizeof h);
+    const bool ok = (fam == kFamS) ? sxid_match_unit(b, ms, ue, T, &h) : xid_match_unit(b, ms, ue, T, &h);
+    if (!ok) continue;
+    // unit number = separators before `us`
+    const int64_t chunk = us / kChunk;
+    unsigned long long idx = chunk_prefix[chunk];
+    for (int64_t i = chunk * kChunk; i < us; ++i) idx += is_sep(b, i, mode) ? 1 : 0;
+    h.unit_index = (int64_t)idx;
+    h.unit_offset = us;
+    h.kmsg_priority = (int32_t)k_prio;
+    h.kmsg_seq = k_seq;
+    h.kmsg_usec = k_usec;
+    const unsigned long long slot = atomicAdd(n_hits, 1ull);
+    if (slot < hit_cap) hits[slot] = h;
+  }
+}
+
+__global__ void k_classify(const gpud_tables* __restrict__ T, gpud_xid_hit* hits, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  gpud_xid_hit h = hits[i];
+  h.unit_name[39] = 0;
+  bool ok;
+  if (h.kind == GPUD_KIND_SXID) ok = classify_sxid(T, &h);
+  else if (h.flags & GPUD_HIT_EXTENDED) { h.sub_code = (int32_t)((h.intrinfo >> 20) & 0x3F); ok = classify_extended(T, &h); }
+  else ok = classify_plain_xid(T, &h);
+  if (!ok) { h.event_type = GPUD_EVENT_UNKNOWN; h.n_actions = -1; h.rule_index = -1; h.detail_variant = 0; }
+  hits[i] = h;
+}
+
+}  // namespace
+
+// =================================================================================================
+// host side
+// =================================================================================================
+struct gpud_scan_state {
+  int dev = 0;
+  gpud_tables* d_tables = nullptr;
+  uint8_t* d_buf = nullptr; size_t buf_cap = 0;
+  uint32_t* d_chunk_sep = nullptr; unsigned long long* d_chunk_prefix = nullptr; size_t chunk_cap = 0;
+  unsigned long long* d_cands = nullptr; size_t cand_cap = 0;
+  gpud_xid_hit* d_hits = nullptr; size_t hit_cap = 0;
+  unsigned long long* d_counters = nullptr;   // [0] n_cand [1] n_hits [2] n_sep
+  unsigned long long* h_counters = nullptr;   // pinned
+  cudaStream_t stream = nullptr;
+};
+
+void gpud_scan_state_free(gpud_scan_state* s) {
+  if (!s) return;
+  cudaFree(s->d_tables); cudaFree(s->d_buf); cudaFree(s->d_chunk_sep); cudaFree(s->d_chunk_prefix); cudaFree(s->d_cands);
+  cudaFree(s->d_hits); cudaFree(s->d_counters);
+  if (s->h_counters) cudaFreeHost(s->h_counters);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+static int32_t scan_state_get(gpud_ctx* ctx, int dev, gpud_scan_state** out) {
+  const int slot = gpud_dev_slot(ctx, dev);
+  if (slot < 0) return gpud_fail(ctx, GPUD_E_INVALID, "device %d is not part of this ctx", dev);
+  GPUD_CUDA(ctx, cudaSetDevice(dev));
+  if (!ctx->scan[slot]) {
+    gpud_scan_state* s = new gpud_scan_state();
+    s->dev = dev;
+    ctx->scan[slot] = s;
+    GPUD_CUDA(ctx, cudaMalloc(&s->d_tables, sizeof(gpud_tables)));
+    GPUD_CUDA(ctx, cudaMemcpy(s->d_tables, gpud_host_tables(), sizeof(gpud_tables), cudaMemcpyHostToDevice));
+    GPUD_CUDA(ctx, cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
+    GPUD_CUDA(ctx, cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long)));
+    GPUD_CUDA(ctx, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  }
+  *out = ctx->scan[slot];
+  return GPUD_OK;
+}
+
+template <typename T>
+static cudaError_t grow(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return cudaSuccess;
+  cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc(p, need * sizeof(T));
+  if (e == cudaSuccess) *cap = need;
+  return e;
+}
+
+static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_buf, int64_t len, int32_t mode, int64_t hit_cap_req,
+                           cudaStream_t st) {
+  const int64_t n_chunks = std::max<int64_t>(1, (len + kChunk - 1) / kChunk);
+  size_t cc = s->chunk_cap;
+  GPUD_CUDA(ctx, grow(&s->d_chunk_sep, &cc, (size_t)n_chunks));
+  cc = s->chunk_cap;
+  GPUD_CUDA(ctx, grow(&s->d_chunk_prefix, &cc, (size_t)n_chunks));
+  s->chunk_cap = cc;
+  GPUD_CUDA(ctx, grow(&s->d_cands, &s->cand_cap, (size_t)(len / 4 + 1024)));
+  GPUD_CUDA(ctx, grow(&s->d_hits, &s->hit_cap, (size_t)std::max<int64_t>(hit_cap_req, 1024)));
+  GPUD_CUDA(ctx, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  if (len == 0) {
+    GPUD_CUDA(ctx, cudaMemsetAsync(s->d_chunk_sep, 0, sizeof(uint32_t), st));
+  }
+  ScanBuf b{d_buf, len};
+  const int grid_f = (int)std::min<int64_t>((n_chunks + 31) / 32, (int64_t)ctx->sm_count * 8);   // 8 warps x 4 chunks per block step
+  k_scan_filter<<<std::max(grid_f, 1), 256, 0, st>>>(b, mode, s->d_chunk_sep, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  k_scan_prefix<<<1, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_prefix, n_chunks, s->d_counters + 2);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  k_scan_match<<<ctx->sm_count * 4, 128, 0, st>>>(b, mode, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, s->d_chunk_prefix,
+                                                   s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  GPUD_CUDA(ctx, cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  return GPUD_OK;
+}
+
+static int32_t scan_collect(gpud_ctx* ctx, gpud_scan_state* s, gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units,
+                            cudaStream_t st) {
+  GPUD_CUDA(ctx, cudaStreamSynchronize(st));
+  const int64_t found = (int64_t)s->h_counters[1];
+  const int64_t have = std::min<int64_t>(found, (int64_t)s->hit_cap);
+  if (n_hits) *n_hits = found;
+  if (n_units) *n_units = (int64_t)s->h_counters[2] + 1;
+  if (s->h_counters[0] > s->cand_cap) return gpud_fail(ctx, GPUD_E_CAPACITY, "candidate list overflow (%llu)", s->h_counters[0]);
+  std::vector<gpud_xid_hit> tmp((size_t)have);
+  if (have) {
+    GPUD_CUDA(ctx, cudaMemcpyAsync(tmp.data(), s->d_hits, (size_t)have * sizeof(gpud_xid_hit), cudaMemcpyDeviceToHost, st));
+    GPUD_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  // device threads finish in arbitrary order: present hits in (unit, kind) order like the sequential reference loop
+  std::sort(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
+    return a.unit_index != b.unit_index ? a.unit_index < b.unit_index : a.kind < b.kind;
+  });
+  const int64_t n_copy = std::min<int64_t>(have, cap);
+  if (n_copy && hits) memcpy(hits, tmp.data(), (size_t)n_copy * sizeof(gpud_xid_hit));
+  if (found > cap || found > have) return gpud_fail(ctx, GPUD_E_CAPACITY, "%lld hits, caller capacity %lld", (long long)found, (long long)cap);
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8_t* dev_buf, int64_t len, int32_t mode, gpud_xid_hit* hits,
+                                         int64_t cap, int64_t* n_hits, int64_t* n_units, void* cuda_stream) {
+  if (!ctx || len < 0 || (len && !dev_buf) || cap < 0 || (mode != GPUD_SCAN_LINES && mode != GPUD_SCAN_RAW_KMSG)) return GPUD_E_INVALID;
+  gpud_scan_state* s;
+  int32_t rc = scan_state_get(ctx, dev, &s);
+  if (rc) return rc;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+  rc = scan_launch(ctx, s, dev_buf, len, mode, cap, st);
+  if (rc) return rc;
+  return scan_collect(ctx, s, hits, cap, n_hits, n_units, st);
+}
+
+extern "C" int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf, int64_t len, int32_t mode, gpud_xid_hit* hits, int64_t cap,
+                                  int64_t* n_hits, int64_t* n_units) {
+  if (!ctx || len < 0 || (len && !buf) || cap < 0 || (mode != GPUD_SCAN_LINES && mode != GPUD_SCAN_RAW_KMSG)) return GPUD_E_INVALID;
+  gpud_scan_state* s;
+  int32_t rc = scan_state_get(ctx, dev, &s);
+  if (rc) return rc;
+  GPUD_CUDA(ctx, grow(&s->d_buf, &s->buf_cap, (size_t)len + 64));
+  if (len) GPUD_CUDA(ctx, cudaMemcpyAsync(s->d_buf, buf, (size_t)len, cudaMemcpyHostToDevice, s->stream));
+  rc = scan_launch(ctx, s, s->d_buf, len, mode, cap, s->stream);
+  if (rc) return rc;
+  return scan_collect(ctx, s, hits, cap, n_hits, n_units, s->stream);
+}
+
+extern "C" int32_t gpud_xid_classify(gpud_ctx* ctx, int32_t dev, gpud_xid_hit* hits, int64_t n) {
+  if (!ctx || n < 0 || (n && !hits)) return GPUD_E_INVALID;
+  if (n == 0) return GPUD_OK;
+  gpud_scan_state* s;
+  int32_t rc = scan_state_get(ctx, dev, &s);
+  if (rc) return rc;
+  GPUD_CUDA(ctx, grow(&s->d_hits, &s->hit_cap, (size_t)std::max<int64_t>(n, 1024)));
+  GPUD_CUDA(ctx, cudaMemcpyAsync(s->d_hits, hits, (size_t)n * sizeof(gpud_xid_hit), cudaMemcpyHostToDevice, s->stream));
+  k_classify<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->d_tables, s->d_hits, n);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  GPUD_CUDA(ctx, cudaMemcpyAsync(hits, s->d_hits, (size_t)n * sizeof(gpud_xid_hit), cudaMemcpyDeviceToHost, s->stream));
+  GPUD_CUDA(ctx, cudaStreamSynchronize(s->stream));
+  return GPUD_OK;
+}

@@ -1,0 +1,268 @@
+/* gpud_b200.h — C ABI of libgpud_b200.so: the B200-native telemetry aggregation / Xid scan hot path of gpud.
+ *
+ * This is the drop-in boundary a thin cgo file in a gpud `components.Component` would bind
+ * (INTEGRATION.md shows the stub).  The reference has no FFI seam of its own (it is 100 % Go,
+ * SURVEY.md §0); each entry point names the reference function(s) whose work it replaces.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 = GPUD_OK, <0 = GPUD_E_*; gpud_last_error() copies the message.
+ *  - no exceptions, no callbacks, nothing retains caller memory after return (cgo pointer rule).
+ *  - the library owns device memory and pinned staging; the caller owns every buffer it passes.
+ *  - callable from any OS thread: each entry does cudaSetDevice itself.  Calls on the same ring / the
+ *    same (ctx, dev) scanner must be serialised by the caller (the Go side holds a mutex, like
+ *    `lastMu` in components/accelerator/nvidia/temperature/component.go:99-104).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry fails with GPUD_E_CUDA.
+ */
+#ifndef GPUD_B200_H
+#define GPUD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPUD_ABI_VERSION 1
+
+#define GPUD_OK 0
+#define GPUD_E_INVALID (-1)  /* bad argument                                   */
+#define GPUD_E_CUDA (-2)     /* CUDA runtime error (message has the cudaError)  */
+#define GPUD_E_NOMEM (-3)
+#define GPUD_E_CAPACITY (-4) /* caller's output buffer too small; *n_* = needed */
+#define GPUD_E_NCCL (-5)
+#define GPUD_E_STATE (-6)    /* call order (e.g. read before reduce)            */
+
+typedef struct gpud_ctx gpud_ctx;
+typedef struct gpud_ring gpud_ring;
+
+int32_t gpud_abi_version(void);
+/* sizeof of the ABI structs for binding layout checks: 0 gpud_xid_hit, 1 gpud_fabric_raw, 2 gpud_fabric_local,
+ * 3 gpud_fabric_verdict, 4 gpud_ring_cfg; -1 otherwise. */
+int32_t gpud_sizeof(int32_t which);
+
+/* One context per process; `cuda_devs[n]` are the CUDA ordinals this process drives (one per rank when
+ * launched one-process-per-GPU).  Replaces the per-process NVML instance wiring of
+ * pkg/nvidia/nvml/instance.go:110-273 for the compute side (NVML itself stays the data source). */
+int32_t gpud_ctx_create(const int32_t* cuda_devs, int32_t n, gpud_ctx** out);
+int32_t gpud_ctx_destroy(gpud_ctx* ctx);
+/* Thread-safe copy of the last error message recorded on this ctx (NUL-terminated, truncated to cap). */
+int32_t gpud_last_error(gpud_ctx* ctx, char* buf, int32_t cap);
+
+/* Pinned host memory for sample batches / log buffers a caller wants DMA'd without the staging copy. */
+int32_t gpud_host_alloc(int64_t bytes, void** out);
+int32_t gpud_host_free(void* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Counter-sample ring + windowed aggregates.
+ * Replaces: the gauge -> scrape -> SQLite row path of pkg/metrics (scraper/prometheus.go:28-81,
+ * syncer/syncer.go:36-82, store/sqlite.go:108-164) as the sample sink, and adds the windowed
+ * min/max/mean/EMA/p99/threshold-count the north star asks for.  The reference has NO implementation
+ * of those aggregates: definitions are oracle/SPEC.md ("parity unpinned").  The strict `>` of n_over
+ * mirrors components/accelerator/nvidia/temperature/component.go:228,240.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_fields;         /* F: gauges per GPU (api/v1/types.go:136-141 fixes the sample type: f64)   */
+  int32_t window;           /* W: tumbling window length in samples, 1..1024                            */
+  int64_t capacity;         /* CAP: samples kept per field (even, >= window)                            */
+  double ema_alpha;         /* 0 => 2/(W+1); otherwise in (0, 0.9999]                                   */
+  int32_t q_num, q_den;     /* order statistic, nearest rank ceil(m*q_num/q_den); 0/0 => 99/100         */
+  const double* thresholds; /* [F] or NULL (= +inf: nothing counts)                                     */
+} gpud_ring_cfg;
+
+enum { GPUD_OP_MIN = 0, GPUD_OP_MAX = 1, GPUD_OP_MEAN = 2, GPUD_OP_EMA = 3, GPUD_OP_P99 = 4, GPUD_OP_NOVER = 5, GPUD_N_OPS = 6 };
+
+int32_t gpud_ring_create(gpud_ctx* ctx, int32_t dev, const gpud_ring_cfg* cfg, gpud_ring** out);
+int32_t gpud_ring_destroy(gpud_ring* ring);
+/* Use an existing CUDA stream (cudaStream_t as void*) for every launch/copy of this ring; NULL = the ring's own. */
+int32_t gpud_ring_set_stream(gpud_ring* ring, void* cuda_stream);
+/* Append n_rows polls.  host_rows is [n_rows][F] row-major f64 in ordinary host memory (one row = one
+ * poll of all F gauges, the shape the poll loop produces, temperature/component.go:165-273).  The rows are
+ * staged through the library's pinned double buffers, copied with cudaMemcpyAsync and scattered into the
+ * field-major ring [F][CAP] by the append kernel.  Returns after the caller's buffer has been consumed. */
+int32_t gpud_ring_push(gpud_ring* ring, const double* host_rows, int64_t n_rows);
+/* Same, source already in device memory on the ring's device (append kernel only). */
+int32_t gpud_ring_push_device(gpud_ring* ring, const double* dev_rows, int64_t n_rows);
+int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
+/* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
+int32_t gpud_ring_reduce(gpud_ring* ring);
+int32_t gpud_ring_sync(gpud_ring* ring);
+/* Device time of the last reduce's two kernels (CUDA events recorded on the ring's stream around each launch). */
+int32_t gpud_ring_kernel_ms(gpud_ring* ring, float* reduce_ms, float* carry_ms);
+/* Copy one aggregate to host: [F][n_windows] row-major; f64 for MIN..P99, uint32 for NOVER.  Synchronises. */
+int32_t gpud_ring_read(gpud_ring* ring, int32_t op, void* out, int64_t out_bytes);
+/* Device pointer of an aggregate (same layout), valid until the next reduce/destroy. */
+int32_t gpud_ring_result_ptr(gpud_ring* ring, int32_t op, void** dev_ptr);
+
+/* Whole-range aggregates of the most recent `last_n` samples of every field (last_n = 0 => whole ring):
+ * exact order statistic by multi-pass radix select.  out_f64 is [5][F] (MIN,MAX,MEAN,EMA,P99), n_over [F]. */
+int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64, uint32_t* out_n_over);
+
+/* ------------------------------------------------------------------------------------------------
+ * kmsg Xid / SXid scan + classification.
+ * Replaces: xid.Match (components/accelerator/nvidia/xid/kmsg.go:202-245 with the regexes at :22,:29,:38,:43),
+ * sxid.Match (sxid/kmsg.go:58-73, regexes :17,:20), the catalog lookups GetDetail / detailFromNVLinkInfo
+ * (xid/xid.go:74-117, 2954-2995) applied per line of a buffer as in xid/kmsg_test.go:252-267 and
+ * xid/component.go:274-299.
+ * ---------------------------------------------------------------------------------------------- */
+enum { GPUD_SCAN_LINES = 0,   /* units are '\n'-separated lines (strings.Split(buf, "\n"))                  */
+       GPUD_SCAN_RAW_KMSG = 1 /* units are /dev/kmsg records "prio,seq,usec,flags;msg" (+ " KEY=val" lines);
+                                 Match runs on the message part (pkg/kmsg/watcher.go:292-332)               */ };
+enum { GPUD_KIND_XID = 1, GPUD_KIND_SXID = 2 };
+enum { GPUD_EVENT_UNKNOWN = 0, GPUD_EVENT_INFO = 1, GPUD_EVENT_WARNING = 2, GPUD_EVENT_CRITICAL = 3, GPUD_EVENT_FATAL = 4 };
+enum { GPUD_ACT_IGNORE_NO_ACTION_REQUIRED = 1, GPUD_ACT_REBOOT_SYSTEM = 2, GPUD_ACT_HARDWARE_INSPECTION = 3,
+       GPUD_ACT_CHECK_USER_APP_AND_GPU = 4 };
+#define GPUD_HIT_EXTENDED 0x1u      /* matched the NVLink5 extended format (kmsg.go:29)                       */
+#define GPUD_HIT_FALLEN_OFF_BUS 0x2u /* xid 79 implied by the fallen-off-the-bus fallbacks (kmsg.go:38,43)    */
+#define GPUD_HIT_DEV_TRUNCATED 0x4u /* device string longer than the inline copy; use dev_off/dev_len       */
+#define GPUD_HIT_HAS_RULE 0x8u      /* an NVLink decode rule matched (xid.go:3099-3114); rule_index is valid  */
+
+typedef struct {
+  int64_t unit_index;    /* 0-based line (LINES) or record (RAW_KMSG) number                               */
+  int64_t unit_offset;   /* byte offset of the line / record start in the scanned buffer                  */
+  int64_t dev_off;       /* byte offset and length of the device capture in the buffer                    */
+  int32_t dev_len;
+  int32_t kind;          /* GPUD_KIND_*                                                                    */
+  int32_t code;          /* Xid or SXid                                                                    */
+  uint32_t flags;        /* GPUD_HIT_*                                                                     */
+  /* extended (NVLink5) fields, zero unless GPUD_HIT_EXTENDED — ExtractedInfo, kmsg.go:84-98               */
+  int32_t sub_code;      /* (intrinfo >> 20) & 0x3F                                                        */
+  int32_t kmsg_priority; /* RAW_KMSG only: parseLine fields (pkg/kmsg/watcher.go:292-332), else 0                 */
+  int64_t kmsg_seq;
+  int64_t kmsg_usec;     /* microseconds since boot; event time = boot time + kmsg_usec                           */
+  int64_t link;          /* Atoi("-?\\d+"): Go int is 64-bit                                                      */
+  uint32_t intrinfo;
+  uint32_t error_status;
+  uint32_t extra[4];
+  int32_t n_extra;
+  int32_t severity_fatal; /* log says "Fatal" (1) / "Nonfatal" (0)                                         */
+  int32_t xc;             /* 0 / 1 from XC0 / XC1                                                          */
+  int64_t unit_name_off;  /* capture 5 (sub-code mnemonic): offset/len in the buffer                       */
+  int32_t unit_name_len;
+  int64_t pid_off;        /* optional captures 3,4; len 0 when absent                                      */
+  int32_t pid_len;
+  int64_t pname_off;
+  int32_t pname_len;
+  int64_t inj_off;        /* capture 8 ("i0")                                                              */
+  int32_t inj_len;
+  /* classification (Detail of xid.go:12-42 as ids; strings are rendered by gpud_hit_detail_json)          */
+  int32_t event_type;     /* GPUD_EVENT_*                                                                  */
+  int32_t n_actions;      /* -1 = SuggestedActionsByGPUd nil                                               */
+  int32_t actions[4];     /* GPUD_ACT_*, reference order                                                   */
+  int32_t rule_index;     /* index into the NVLink rule table, -1 if none                                  */
+  int32_t detail_variant; /* 0 base / sub-code table; 1, 2 = the 149.4 / 149.10 operational overrides       */
+  char device[40];        /* NUL-terminated device id as Match returns it ("PCI:0000:05:00", "0000:03:00") */
+  char unit_name[40];     /* NUL-terminated capture 5, truncated                                           */
+} gpud_xid_hit;
+
+/* Scan `len` bytes of host memory.  hits[cap] receives the hits in (unit_index, kind) order; *n_hits is the
+ * number found (may exceed cap -> GPUD_E_CAPACITY, first cap are valid); *n_units = number of lines/records. */
+int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf, int64_t len, int32_t mode,
+                       gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units);
+/* Device-resident variant: dev_buf on `dev`; kernels only, results copied to the caller's host arrays. */
+int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8_t* dev_buf, int64_t len, int32_t mode,
+                              gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units, void* cuda_stream);
+/* Classify already-extracted hits (fills event_type/actions/rule_index/detail_variant) with the device LUT
+ * kernel; `hits` is host memory, updated in place.  unit_name[] must hold capture 5 for extended hits. */
+int32_t gpud_xid_classify(gpud_ctx* ctx, int32_t dev, gpud_xid_hit* hits, int64_t n);
+/* Host-side rendering of the persisted payload (xidErrorEventDetail JSON, xid/health_state.go:284-315 and
+ * xid/component.go:503-554) for one hit; `buf_bytes` is the scanned buffer (for long captures) or NULL. */
+int32_t gpud_hit_detail_json(const gpud_xid_hit* hit, int64_t unix_seconds, char* out, int32_t cap);
+/* Catalog accessors (xid/xid.go:74, sxid/sxid.go:32): description / mnemonic / name strings, "" if unknown. */
+const char* gpud_xid_description(int32_t code, int32_t detail_variant);
+const char* gpud_xid_mnemonic(int32_t code);
+const char* gpud_sxid_name(int32_t code);
+const char* gpud_nvlink_rule_hint(int32_t rule_index);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-box NVLink / fabric view.
+ * Replaces: the single-process loops of nvlink.Check (nvlink/component.go:164-311),
+ * evaluateHealthStateWithThresholds (nvlink/evaluate_threshold.go:77-188) and collectFabricState /
+ * FabricState.GetIssues (fabric-manager/fabric_state.go:67-113, pkg/nvidia/nvml/device/fabric_state.go:115-177)
+ * with: per-GPU pack kernel -> allgather of one 128-byte record per GPU over NVLink -> replicated verdict kernel.
+ * ---------------------------------------------------------------------------------------------- */
+#define GPUD_MAX_LINKS 18 /* NVML_NVLINK_MAX_LINKS, nvml.h:389 */
+#define GPUD_MAX_GPUS 16
+#define GPUD_P2P_UNPROBED 0xFF
+
+typedef struct { /* what the host poller read from NVML for ONE GPU (nvlink/nvlink.go:93-168, p2p.go:21-50) */
+  uint32_t gpu_index;                     /* position in the sorted-UUID order (component.go:185-190)      */
+  uint32_t nvlink_supported;              /* NVLink.Supported                                              */
+  uint32_t system_expected_nvlink;        /* FabricManagerSupported() || FabricStateSupported()            */
+  uint32_t n_links;                       /* len(States)                                                   */
+  uint8_t link_feature_enabled[GPUD_MAX_LINKS];
+  uint8_t pad0[2];
+  uint64_t link_replay_errors[GPUD_MAX_LINKS];
+  uint64_t link_recovery_errors[GPUD_MAX_LINKS];
+  uint64_t link_crc_errors[GPUD_MAX_LINKS];
+  uint8_t p2p_status[GPUD_MAX_GPUS];      /* NVML P2P status vs peer j (0 OK .. 6 UNKNOWN), GPUD_P2P_UNPROBED */
+  uint32_t fabric_valid;                  /* fabric info was read                                          */
+  uint8_t fabric_state;                   /* nvml.h:3433-3436; 3 = COMPLETED                               */
+  uint8_t fabric_summary;                 /* 0 NOT_SUPPORTED 1 HEALTHY 2 UNHEALTHY 3 LIMITED_CAPACITY       */
+  uint8_t pad1[2];
+  int32_t fabric_status;                  /* nvml.Return, 0 = SUCCESS                                      */
+  uint32_t fabric_health_mask;            /* nvml.h:3453-3488                                              */
+  uint32_t clique_id;
+} gpud_fabric_raw;
+
+typedef struct { /* the 128-byte record each GPU contributes to the allgather */
+  uint32_t gpu_index;
+  uint32_t flags;              /* bit0 nvlink_supported, bit1 system_expected_nvlink, bit2 fabric_valid,
+                                  bit3 all-links-feature-enabled && n_links > 0 ("active", component.go:281) */
+  uint32_t n_links;
+  uint32_t links_enabled_mask;
+  uint64_t replay_errors, recovery_errors, crc_errors; /* NVLinkStates.Total*Errors, nvlink.go:44-68       */
+  uint8_t p2p_status[GPUD_MAX_GPUS];
+  uint8_t fabric_state, fabric_summary, fabric_issue_bits, pad0;
+  int32_t fabric_status;
+  uint32_t fabric_health_mask;
+  uint32_t clique_id;
+  uint8_t pad1[128 - 76];
+} gpud_fabric_local;
+
+enum { GPUD_NVLINK_NO_ISSUE = 0, GPUD_NVLINK_P2P_FAILURE = 1, GPUD_NVLINK_NO_ACTIVE_LINKS = 2,
+       GPUD_NVLINK_THRESHOLD_SATISFIED = 3, GPUD_NVLINK_THRESHOLD_VIOLATED = 4, GPUD_NVLINK_NO_THRESHOLD = 5,
+       GPUD_NVLINK_NO_DATA = 6, GPUD_NVLINK_P2P_INCOMPLETE_NO_THRESHOLD = 7 };
+/* fabric_issue_bits: */
+#define GPUD_FAB_STATE_NOT_COMPLETED 0x01u
+#define GPUD_FAB_STATUS_NOT_SUCCESS 0x02u
+#define GPUD_FAB_SUMMARY_UNHEALTHY 0x04u
+#define GPUD_FAB_SUMMARY_LIMITED 0x08u
+#define GPUD_FAB_BW_DEGRADED 0x10u
+#define GPUD_FAB_ROUTE_RECOVERY 0x20u
+#define GPUD_FAB_ROUTE_UNHEALTHY 0x40u
+#define GPUD_FAB_ACCESS_TIMEOUT 0x80u
+
+typedef struct {
+  int32_t n_gpus;
+  int32_t nvlink_health;  /* 0 Healthy, 2 Unhealthy (api/v1/types.go:20-25)                                 */
+  int32_t nvlink_reason;  /* GPUD_NVLINK_*                                                                  */
+  int32_t required, active, inactive, unsupported;
+  int32_t p2p_expected_pairs, p2p_probed_pairs, p2p_ok_pairs;
+  uint32_t p2p_ok_gpu_mask;       /* PeerNVLinkOKGPUUUIDs as a bit per gpu_index                            */
+  uint32_t p2p_observed_status_mask; /* bit s set if status code s was observed                             */
+  uint32_t active_mask, inactive_mask, unsupported_mask;
+  int32_t fabric_healthy;         /* report.Healthy, fabric_state.go:67-113                                 */
+  uint32_t fabric_unhealthy_gpu_mask;
+  uint8_t fabric_issue_bits[GPUD_MAX_GPUS];
+  uint64_t total_replay, total_recovery, total_crc;
+} gpud_fabric_verdict;
+
+/* Single-rank pieces (one process per GPU; the collective itself is done by the host plumbing, e.g.
+ * torch.distributed / ncclAllGather on `dev_send` -> `dev_all`): */
+int32_t gpud_fabric_pack(gpud_ctx* ctx, int32_t dev, const gpud_fabric_raw* raw, void* dev_send /*128 B*/, void* cuda_stream);
+int32_t gpud_fabric_verdict_device(gpud_ctx* ctx, int32_t dev, const void* dev_all /*[n]x128 B*/, int32_t n,
+                                   int32_t at_least_gpus_with_all_links, gpud_fabric_verdict* out, void* cuda_stream);
+/* All-in-one for a process that owns the communicator: NCCL is dlopen'ed (libnccl.so.2) on first use. */
+int32_t gpud_comm_unique_id(void* out128);
+int32_t gpud_comm_init(gpud_ctx* ctx, int32_t dev, int32_t n_ranks, int32_t rank, const void* unique_id128);
+int32_t gpud_fabric_gather(gpud_ctx* ctx, int32_t dev, const gpud_fabric_raw* raw, int32_t at_least_gpus_with_all_links,
+                           gpud_fabric_local* all_out /*[n_ranks] host*/, gpud_fabric_verdict* out);
+/* Single-process multi-GPU (the reference's own deployment shape): every device of the ctx packs its record and
+ * writes it straight into every peer's table over NVLink peer stores (no NCCL), then each evaluates the verdict. */
+int32_t gpud_fabric_gather_p2p(gpud_ctx* ctx, const gpud_fabric_raw* raws /*[n devs]*/, int32_t at_least_gpus_with_all_links,
+                               gpud_fabric_local* all_out /*[n] host*/, gpud_fabric_verdict* verdicts /*[n]*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUD_B200_H */

@@ -1,0 +1,39 @@
+"""ctypes loader for oracle/liboracle.so (the C restatement).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        p = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(p):
+            raise RuntimeError("oracle/liboracle.so missing: run `make -C oracle`")
+        _lib = C.CDLL(p)
+        _lib.orc_max_threads.restype = C.c_int32
+    return _lib
+
+
+def windows_fields(ring: np.ndarray, W: int, thr: np.ndarray, alpha: float = 0.0, q_num: int = 0, q_den: int = 0, threads: int = 0):
+    """ring: [F][n] f64 field-major.  Returns dict of [F][nw] arrays."""
+    L = lib()
+    ring = np.ascontiguousarray(ring, dtype=np.float64)
+    F, n = ring.shape
+    nw = (n + W - 1) // W
+    out = {k: np.empty((F, nw), dtype=np.float64) for k in ("min", "max", "mean", "ema", "p99")}
+    out["n_over"] = np.empty((F, nw), dtype=np.uint32)
+    thr = np.ascontiguousarray(thr, dtype=np.float64)
+    vp = C.c_void_p
+    L.orc_windows_fields(vp(ring.ctypes.data), C.c_int32(F), C.c_int64(n), C.c_int32(W), vp(thr.ctypes.data), C.c_double(alpha),
+                         C.c_int32(q_num), C.c_int32(q_den), C.c_int32(threads), vp(out["min"].ctypes.data), vp(out["max"].ctypes.data),
+                         vp(out["mean"].ctypes.data), vp(out["ema"].ctypes.data), vp(out["p99"].ctypes.data), vp(out["n_over"].ctypes.data))
+    return out
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())

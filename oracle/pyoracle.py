@@ -602,3 +602,75 @@ def window_aggregates(x: np.ndarray, W: int, thr: float, alpha: float = 0.0, q_n
 # whole-box NVLink / fabric verdict  (nvlink/evaluate_threshold.go:77-188 ; device/fabric_state.go:115-177)
 # implemented in oracle/fabric.py to keep this file focused on the scan path
 # --------------------------------------------------------------------------------------------
+
+
+def scan_raw_kmsg(buf: bytes):
+    """Buffer of concatenated /dev/kmsg records (a record continues on lines that start with ' ').  Each record goes
+    through parseLine (records that fail to parse are skipped, pkg/kmsg/watcher.go:161-165) and Match runs on the
+    message part (xid/component.go:274-299)."""
+    hits = []
+    off = 0
+    recs = re.split(rb"\n(?! )", buf)
+    for idx, rec in enumerate(recs):
+        try:
+            prio, seq, usec, msg = parse_kmsg_line(0, rec.decode("latin-1"))
+        except ValueError:
+            off += len(rec) + 1
+            continue
+        m = msg.encode("latin-1")
+        x = xid_match(m)
+        if x is not None:
+            hits.append({"line": idx, "offset": off, "kind": 1, "code": x.xid, "device": x.device,
+                         "event_type": x.detail.event_type, "actions": x.detail.actions or [], "kmsg": (prio, seq, usec),
+                         "extended": x.info is not None, "sub_code": x.detail.sub_code, "error_status": x.detail.error_status})
+        s = sxid_match(m)
+        if s is not None:
+            hits.append({"line": idx, "offset": off, "kind": 2, "code": s["sxid"], "device": s["device"],
+                         "event_type": s["detail"]["event_type"], "actions": s["detail"]["actions"], "kmsg": (prio, seq, usec),
+                         "extended": False, "sub_code": 0, "error_status": 0})
+        off += len(rec) + 1
+    return hits, len(recs)
+
+
+def xid_event_detail_json(x: "XidError", unix_seconds: int = 0) -> str:
+    """json.Marshal(xidErrorEventDetail) as built in xid/component.go:503-521 (struct at health_state.go:284-315)."""
+    import datetime
+    d = x.detail
+    parts = ['"time":' + ("null" if unix_seconds == 0 else json.dumps(
+        datetime.datetime.fromtimestamp(unix_seconds, datetime.timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ"))),
+        '"data_source":"kmsg"', '"device_uuid":' + _go_json_str(x.device), '"xid":%d' % x.xid]
+    if d.sub_code:
+        parts.append('"sub_code":%d' % d.sub_code)
+    if d.sub_code_description:
+        parts.append('"sub_code_description":' + _go_json_str(d.sub_code_description))
+    if d.error_status:
+        parts.append('"error_status":%d' % d.error_status)
+    if d.investigatory_hint:
+        parts.append('"investigatory_hint":' + _go_json_str(d.investigatory_hint))
+    if d.description:
+        parts.append('"description":' + _go_json_str(d.description))
+    if d.actions is not None:
+        parts.append('"suggested_actions_by_gpud":{"repair_actions":[' + ",".join('"%s"' % ACTION_WIRE[a] for a in d.actions) + "]}")
+    return "{" + ",".join(parts) + "}"
+
+
+def _go_json_str(s: str) -> str:
+    out = ['"']
+    for ch in s:
+        o = ord(ch)
+        if ch == '"':
+            out.append('\\"')
+        elif ch == "\\":
+            out.append("\\\\")
+        elif ch == "\n":
+            out.append("\\n")
+        elif ch == "\r":
+            out.append("\\r")
+        elif ch == "\t":
+            out.append("\\t")
+        elif ch in "<>&" or o < 0x20:
+            out.append("\\u%04x" % o)
+        else:
+            out.append(ch)
+    out.append('"')
+    return "".join(out)

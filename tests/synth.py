@@ -1,0 +1,142 @@
+"""Deterministic synthetic inputs shared by the tests, smoke() and bench.py (SURVEY.md §8d shapes)."""
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEED = 0x67707564   # "gpud"
+
+
+def golden(name):
+    with open(os.path.join(ROOT, "tests", "golden", name)) as f:
+        return json.load(f)
+
+
+def gauge_stream(n_fields: int, n: int, seed: int = SEED, dtype=np.float64) -> np.ndarray:
+    """[n, F] row-major polls.  Field k models a gauge base_k + A_k sin(2 pi t / P_k) + sigma_k N(0,1) with 0.1 % spikes;
+    every 8th field is a monotone counter, every 8th+1 an integer-valued gauge (ties)."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64)[:, None]
+    base = rng.uniform(30.0, 90.0, n_fields)[None, :]
+    amp = rng.uniform(1.0, 10.0, n_fields)[None, :]
+    per = rng.uniform(500.0, 50000.0, n_fields)[None, :]
+    sig = rng.uniform(0.1, 2.0, n_fields)[None, :]
+    x = base + amp * np.sin(2 * np.pi * t / per) + sig * rng.standard_normal((n, n_fields))
+    spikes = rng.random((n, n_fields)) < 0.001
+    x = np.where(spikes, x + 40.0, x)
+    for k in range(0, n_fields, 8):
+        x[:, k] = np.cumsum(rng.integers(0, 5, n)).astype(np.float64)
+    for k in range(1, n_fields, 8):
+        x[:, k] = np.round(x[:, k])
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+def thresholds_for(x: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(x.mean(axis=0) + 2.0 * x.std(axis=0))
+
+
+def hit_lines():
+    """Every Xid / SXid line the reference's tests exercise, plus the injectable messages for all catalog codes."""
+    g = golden("xid_kmsg.json")
+    s = golden("sxid_kmsg.json")
+    lines = []
+    for k in ("extract_xid", "extract_device", "match", "unknown_code"):
+        lines += [r["input"] for r in g[k]["rows"]]
+    for k in ("extended", "match_nvlink_examples"):
+        lines += [r["logLine"] for r in g[k]["rows"]]
+    lines += [r["line"] for r in g["nvlink_log_coverage"]["rows"]]
+    lines += [r["line"] for r in g["short_match"]["rows"]]
+    inj = g["inject_messages"]
+    for c in range(1, 175):
+        lines.append(inj["known"][str(c)]["message"] if str(c) in inj["known"] else inj["template"] % c)
+    for c in (99999, 11111, 0):
+        lines.append(inj["template"] % c)
+    for k in ("extract_sxid", "extract_device", "match"):
+        lines += [r["input"] for r in s[k]["rows"]]
+    return lines
+
+
+EDGE_LINES = [
+    "NVRM: Xid (PCI:0000:05:00): 79, first NVRM: Xid (PCI:0000:06:00): 31, second",     # two anchors, leftmost wins
+    "NVRM: Xid (invalid): x NVRM: Xid (PCI:0000:07:00): 13, later anchor is the match",
+    "NVRM: Xid (PCI:0000:05:00) no code here: abc, then : 48, lazy finds the first ': digits,'",
+    "NVRM: Xid (PCI:0000:05:00): 99999999999999999999, overflow then NVRM: GPU 0000:29:00.0: GPU has fallen off the bus.",
+    "NVRM: Xid (PCI:0000:05:00): 0079, leading zeros",
+    "NVRM: Xid (PCI:0000:05:00): 0, zero code NVRM: GPU 18:00.0: GPU has fallen off the bus",
+    "NVRM: Xid (PCI:0000:04:00): 145, RLW_REMAP Nonfatal XC0 i0 Link 00 (0x1ffffffff 0x00000001 0x0 0x0)",  # intrinfo > 32 bit -> plain
+    "NVRM: Xid (PCI:0000:04:00): 145, RLW_REMAP Nonfatal XC0 i0 Link 00 (0x00000004 0x00000001 0xfffffffff 0x5)",  # optional hex overflow skipped
+    "NVRM: Xid (PCI:0000:04:00): 146, TLW_RX/TLW_RX_PIPE0 Fatal XC0 i0 Link 00 (0x0000000a 0x00000004 0x0 0x0)",   # digit in unit -> not extended
+    "NVRM: Xid (PCI:0000:04:00): 149, NETIR_LINK_EVT/NETIR_LINK_DOWN Fatal XC1 i12 Link -1 (0x00a00011 0x00000000)",
+    "NVRM: Xid (PCI:0000:04:00): 149, NETIR_LINK_EVT\tFatal\t\tXC0 i0 Link 08 (0x004505c6 0x00000000",               # truncated but 2 hex words
+    "NVRM: Xid (PCI:0000:04:00): 200, pid=1, name=a, RLW_REMAP Nonfatal XC0 i0 Link 00 (0x00000004 0x00000001)",     # unknown base code
+    "NVRM: Xid (PCI:0000:04:00): 145, pid=12, name=we,ird, RLW_REMAP Nonfatal XC0 i0 Link 00 (0x00000004 0x00000001)",
+    "NVRM:   The NVIDIA GPU 0000:18:00.0 (PCI ID) has fallen off the bus and is not responding to commands.",
+    "NVRM: GPU abcd:ef:01.0:   GPU has fallen off the bus",
+    "NVRM: GPU 0000:29:00.1: GPU has fallen off the bus.",
+    "xNVRM: Xid (0000:03:00): 14, glued prefix",
+    "NVRM: Xid (PCI:): 14, empty device",
+    "NVRM: Xid (PCI:00g0): 14, bad device",
+    "nvidia-nvswitch0: SXid (PCI:0000:00:00.0): 20034, Fatal and NVRM: Xid (PCI:0000:01:00): 74, both on one line",
+    "SXid nothing: here SXid (PCI:0000:a9:00.0): 12028, second SXid anchor has the code",
+    "SXid (PCI:zz): 20034, device regex fails -> empty device",
+    "SXid: 999999999999999999999999, overflow",
+    "V X NV SX NVR NVRM SXi VRM: Xid",
+    "",
+    "NVRM: Xid (PCI:0000:05:00): 79",          # no trailing comma
+]
+
+
+def dmesg_buffer(n_bytes: int, seed: int = SEED, hit_every: int = 1000):
+    """~n_bytes of log text: the reference's fixture lines + noise + decoys, with one hit-line per ~hit_every lines."""
+    rng = np.random.default_rng(seed)
+    fix = [l for l in golden("xid_kmsg.json")["dmesg_xid_119"]["lines"] if l]
+    kfix = []
+    for rec in golden("pkg_kmsg.json")["fixture:kmsg.1.log"]["records"]:
+        if ";" in rec:
+            kfix.append(rec.split(";", 1)[1])
+    hits = hit_lines() + EDGE_LINES
+    decoys = ["Xid", "NVRM:", "SXid (invalid)", "NVRM: Xid", "VRM", "X", "V", "NV", "SX"]
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz0123456789 .:-_[]()=,/ABCDEFGHIJKLMNOPQRSTUVWXYZ", dtype=np.uint8)
+    out, size, i = [], 0, 0
+    while size < n_bytes:
+        r = i % 10
+        if i % hit_every == hit_every - 1:
+            line = hits[(i // hit_every) % len(hits)]
+        elif r < 3:
+            line = kfix[(i // 10) % len(kfix)]
+        elif r < 5:
+            line = fix[(i // 10) % len(fix)]
+        else:
+            ln = int(rng.integers(40, 200))
+            line = "[%12.6f] " % (i * 0.001) + alphabet[rng.integers(0, len(alphabet), ln)].tobytes().decode()
+            if rng.random() < 0.05:
+                line += " " + decoys[int(rng.integers(0, len(decoys)))]
+        b = line.encode("utf-8", "surrogateescape") if isinstance(line, str) else line
+        out.append(b)
+        size += len(b) + 1
+        i += 1
+    return b"\n".join(out) + b"\n"
+
+
+def raw_kmsg_buffer(n_records: int, seed: int = SEED):
+    """/dev/kmsg style records 'prio,seq,usec,-;msg' with continuation lines and a few malformed records."""
+    rng = np.random.default_rng(seed)
+    hits = hit_lines() + EDGE_LINES
+    recs = []
+    for i in range(n_records):
+        if i % 7 == 3:
+            msg = hits[(i // 7) % len(hits)].replace("\n", "\\x0a")
+        else:
+            msg = "usb 1-%d: new high-speed USB device number %d using xhci_hcd" % (i % 9, i)
+        meta = "%d,%d,%d,-" % (int(rng.integers(0, 8)), 1000 + i, 5000000 + 137 * i)
+        if i % 53 == 17:
+            meta = "x,%d,9,-" % i            # unparsable priority -> record skipped (watcher.go:161-165)
+        if i % 59 == 23:
+            rec = "no semicolon record %d" % i
+        else:
+            rec = meta + ";" + msg
+        if i % 5 == 0:
+            rec += "\n SUBSYSTEM=pci\n DEVICE=+pci:0000:%02x:00.0" % (i % 256)
+        recs.append(rec)
+    return ("\n".join(recs) + "\n").encode("utf-8", "surrogateescape")

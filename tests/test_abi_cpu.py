@@ -1,0 +1,57 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol the header declares, the binding
+layout matches, catalog accessors answer, and compute entry points fail loudly without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import gpud_b200 as g
+from gpud_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_exported():
+    hdr = open(os.path.join(ROOT, "include", "gpud_b200.h")).read()
+    declared = set(re.findall(r"\b(gpud_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    L = g.lib()
+    for s in declared:
+        assert hasattr(L, s), s
+
+
+def test_layout_and_version():
+    L = g.lib()
+    assert L.gpud_abi_version() == 1
+    assert L.gpud_sizeof(2) == 128 == C.sizeof(g.FabricLocal)
+    assert L.gpud_sizeof(99) == -1
+
+
+def test_catalog_accessors():
+    L = g.lib()
+    assert L.gpud_xid_description(79, 0) == b"GPU has fallen off the bus"
+    assert L.gpud_xid_mnemonic(79) == b"ROBUST_CHANNEL_GPU_HAS_FALLEN_OFF_THE_BUS"
+    assert L.gpud_xid_description(133, 0) == b"" and L.gpud_xid_description(99999, 0) == b""
+    assert b"cartridge" in L.gpud_xid_description(149, 1)
+    assert L.gpud_sxid_name(20034) != b"" and L.gpud_sxid_name(11111) == b""
+
+
+def test_hit_json_host_rendering():
+    from oracle import pyoracle as O
+    L = g.lib()
+    h = g.XidHit()
+    h.kind, h.code, h.n_actions = 1, 79, 2
+    h.actions[0], h.actions[1] = 2, 3
+    h.device = b"PCI:0000:05:00"
+    buf = C.create_string_buffer(2048)
+    assert L.gpud_hit_detail_json(C.byref(h), 1740327858, buf, 2048) == 0
+    x = O.xid_match(b"NVRM: Xid (PCI:0000:05:00): 79, GPU has fallen off the bus.")
+    assert buf.value.decode() == O.xid_event_detail_json(x, 1740327858)
+    assert L.gpud_hit_detail_json(C.byref(h), 0, buf, 8) == -4
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
+def test_no_cpu_fallback():
+    with pytest.raises(g.GpudError):
+        g.Context([0])

@@ -1,0 +1,111 @@
+"""CPU tests of the whole-box NVLink/fabric verdict oracle against the scenarios the reference's tests pin
+(nvlink/evaluate_threshold_test.go:12-490, pkg/nvidia/nvml/device/fabric_state_test.go) — restated as inputs of the
+per-GPU record form.  The GPU test (test_gpu_parity.py::test_fabric_pack_and_verdict) reuses SCENARIOS."""
+from oracle import fabric as OF
+
+
+def gpu(i, n, *, supported=1, expected=1, n_links=18, enabled=None, p2p=0, fabric=(1, 3, 1, 0, 0x00AA)):
+    """fabric = (valid, state, summary, status, health_mask); mask 0xAA = every 2-bit field FALSE(2)"""
+    en = [1] * 18 if enabled is None else list(enabled) + [0] * (18 - len(enabled))
+    p = [0xFF] * 16
+    for j in range(n):
+        if j != i:
+            p[j] = p2p if not isinstance(p2p, dict) else p2p.get((min(i, j), max(i, j)), 0)
+    return {"gpu_index": i, "nvlink_supported": supported, "system_expected_nvlink": expected, "n_links": n_links,
+            "link_feature_enabled": en, "link_replay_errors": [i + k for k in range(18)], "link_recovery_errors": [k % 3 for k in range(18)],
+            "link_crc_errors": [(i * 7 + k) % 5 for k in range(18)], "p2p_status": p, "fabric_valid": fabric[0], "fabric_state": fabric[1],
+            "fabric_summary": fabric[2], "fabric_status": fabric[3], "fabric_health_mask": fabric[4], "clique_id": 1}
+
+
+def scenario(name, n=8):
+    if name == "all_healthy":                       # Satisfied (evaluate_threshold_test.go:40)
+        return [gpu(i, n) for i in range(n)], n
+    if name == "gpu3_link7_down_threshold":         # PartialDegradationFailsWhenThresholdConfigured (:461)
+        gs = [gpu(i, n) for i in range(n)]
+        gs[3]["link_feature_enabled"][7] = 0
+        return gs, n
+    if name == "gpu3_link7_down_no_threshold":      # ImplicitFallbackDoesNotFailPartialDegradation (:430)
+        gs = [gpu(i, n) for i in range(n)]
+        gs[3]["link_feature_enabled"][7] = 0
+        return gs, 0
+    if name == "all_pairs_ns":                      # ImplicitFailureWhenPeerNVLinkP2PReportsNoOKPairs (:253)
+        return [gpu(i, n, p2p=5) for i in range(n)], 0
+    if name == "all_pairs_ns_with_threshold":       # ConfiguredThresholdStillFailsOnPeerNVLinkP2PFailure (:329)
+        return [gpu(i, n, p2p=5) for i in range(n)], 1
+    if name == "partial_probe_coverage":            # ImplicitPeerFailureSkippedWhenProbeCoverageIsPartial (:287)
+        gs = [gpu(i, n, p2p=5) for i in range(n)]
+        for j in range(2, n):
+            gs[0]["p2p_status"][j] = 0xFF
+        return gs, 0
+    if name == "zero_active_no_threshold":          # ImplicitFailureWhenSystemExpectedNVLink (:229)
+        return [gpu(i, n, enabled=[0] * 18, p2p=0xFF) for i in range(n)], 0
+    if name == "zero_active_but_p2p_ok":            # ImplicitFallbackStaysHealthyWhenPeerP2POK (:397)
+        return [gpu(i, n, enabled=[0] * 18, p2p=0) for i in range(n)], 0
+    if name == "unsupported_violation":             # ViolationUnsupported (:89) / MixedInactiveAndUnsupported (:129)
+        gs = [gpu(i, n) for i in range(n)]
+        gs[1]["nvlink_supported"] = 0
+        gs[2]["link_feature_enabled"] = [0] * 18
+        return gs, n
+    if name == "empty_states":                      # EmptyStates (:109): supported, zero links discovered -> inactive
+        gs = [gpu(i, n) for i in range(n)]
+        gs[0]["n_links"] = 0
+        return gs, n
+    if name == "fabric_summary_unhealthy":          # FailureInjector.GPUUUIDsWithFabricStateHealthSummaryUnhealthy (registry.go:58)
+        gs = [gpu(i, n) for i in range(n)]
+        gs[5] = gpu(5, n, fabric=(1, 3, 2, 0, 0x00AA))
+        return gs, 0
+    if name == "fabric_mask_and_state":             # GetIssues: state IN_PROGRESS, status error, bw degraded + route unhealthy
+        gs = [gpu(i, n) for i in range(n)]
+        gs[2] = gpu(2, n, fabric=(1, 2, 3, 9, (1 << 0) | (2 << 2) | (1 << 4) | (2 << 6)))
+        gs[6] = gpu(6, n, fabric=(0, 0, 0, 0, 0))
+        return gs, 0
+    if name == "not_expected_single_domain":        # system without fabric support: nothing is implied
+        return [gpu(i, n, expected=0, enabled=[0] * 18, p2p=5) for i in range(n)], 0
+    raise KeyError(name)
+
+
+SCENARIOS = ["all_healthy", "gpu3_link7_down_threshold", "gpu3_link7_down_no_threshold", "all_pairs_ns", "all_pairs_ns_with_threshold",
+             "partial_probe_coverage", "zero_active_no_threshold", "zero_active_but_p2p_ok", "unsupported_violation", "empty_states",
+             "fabric_summary_unhealthy", "fabric_mask_and_state", "not_expected_single_domain"]
+
+# (health, reason) the Go tests assert for each scenario: 0 Healthy / 2 Unhealthy ; reason ids as GPUD_NVLINK_*
+EXPECT = {"all_healthy": (0, 3), "gpu3_link7_down_threshold": (2, 4), "gpu3_link7_down_no_threshold": (0, 0), "all_pairs_ns": (2, 1),
+          "all_pairs_ns_with_threshold": (2, 1), "partial_probe_coverage": (0, 0), "zero_active_no_threshold": (2, 2),
+          "zero_active_but_p2p_ok": (0, 0), "unsupported_violation": (2, 4), "empty_states": (2, 4), "fabric_summary_unhealthy": (0, 0),
+          "fabric_mask_and_state": (0, 0), "not_expected_single_domain": (0, 0)}
+
+
+def test_nvlink_verdicts():
+    for name in SCENARIOS:
+        gpus, at_least = scenario(name)
+        v = OF.verdict(gpus, at_least)
+        assert (v["nvlink_health"], v["nvlink_reason"]) == EXPECT[name], name
+
+
+def test_counts_and_masks():
+    gpus, at_least = scenario("unsupported_violation")
+    v = OF.verdict(gpus, at_least)
+    assert (v["active"], v["inactive"], v["unsupported"]) == (6, 1, 1)
+    assert v["unsupported_mask"] == 0b10 and v["inactive_mask"] == 0b100
+    assert v["p2p_expected_pairs"] == 28 == v["p2p_probed_pairs"] == v["p2p_ok_pairs"]
+    assert v["total_replay"] == sum(sum(g["link_replay_errors"]) for g in gpus)
+
+
+def test_fabric_issues():
+    # GetIssues (pkg/nvidia/nvml/device/fabric_state.go:115-177)
+    gpus, _ = scenario("fabric_summary_unhealthy")
+    v = OF.verdict(gpus, 0)
+    assert v["fabric_healthy"] == 0 and v["fabric_unhealthy_gpu_mask"] == 1 << 5 and v["fabric_issue_bits"][5] == 0x04
+    gpus, _ = scenario("fabric_mask_and_state")
+    v = OF.verdict(gpus, 0)
+    assert v["fabric_issue_bits"][2] == 0x01 | 0x02 | 0x08 | 0x10 | 0x40
+    assert v["fabric_issue_bits"][6] == 0 and v["fabric_unhealthy_gpu_mask"] == 1 << 2
+    gpus, _ = scenario("all_healthy")
+    assert OF.verdict(gpus, 8)["fabric_healthy"] == 1
+
+
+def test_single_gpu_is_left_alone():
+    # 1-GPU hosts never expect NVLink (component.go:166-184)
+    g = [gpu(0, 1, enabled=[0] * 18)]
+    v = OF.verdict(g, 0)
+    assert (v["nvlink_health"], v["p2p_expected_pairs"]) == (0, 0)

@@ -1,0 +1,338 @@
+"""GPU parity: the CUDA path behind the C ABI vs the oracle on the same inputs.  Run on the B200 box: pytest -m gpu.
+Integer / byte / selection outputs are compared bit-exactly; mean and EMA at 1e-6 relative (oracle/SPEC.md)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import fabric as OF
+from oracle import pyoracle as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+g = None
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    global g
+    import gpud_b200 as _g
+    g = _g
+    c = g.Context([0])
+    yield c
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------ scan
+def _cmp_hits(got, want, extended=True):
+    gd = [h.as_dict() for h in got]
+    assert [(h["line"], h["kind"], h["code"]) for h in gd] == [(h["line"], h["kind"], h["code"]) for h in want]
+    for a, b in zip(gd, want):
+        assert a["device"] == b["device"], (a, b)
+        assert a["offset"] == b["offset"], (a, b)
+        assert a["event_type"] == b["event_type"], (a, b)
+        assert a["actions"] == list(b["actions"]), (a, b)
+        assert a["extended"] == b["extended"], (a, b)
+        if b["extended"]:
+            assert a["sub_code"] == b["sub_code"] and a["error_status"] == b["error_status"], (a, b)
+            if "intrinfo" in b:
+                assert a["intrinfo"] == b["intrinfo"] and a["link"] == b["link"] and a["unit"] == b["unit"][:39], (a, b)
+
+
+def test_scan_golden_lines(ctx):
+    lines = synth.hit_lines() + synth.EDGE_LINES
+    buf = "\n".join(lines).encode()
+    hits, n_units = ctx.kmsg_scan(buf)
+    want = O.scan_lines(buf)
+    assert n_units == buf.count(b"\n") + 1
+    assert len(want) > 250
+    _cmp_hits(hits, want)
+
+
+def test_scan_each_golden_vector(ctx):
+    """every reference test vector scanned as its own buffer (kmsg_test.go TestMatch etc.), incl. multi-line inputs"""
+    G = synth.golden("xid_kmsg.json")
+    for r in G["match"]["rows"]:
+        buf = r["input"].encode()
+        hits, _ = ctx.kmsg_scan(buf)
+        want = O.scan_lines(buf)          # LINES semantics: a multi-line input is split, exactly like the oracle does
+        _cmp_hits(hits, want)
+    # the dmesg fixture: exactly 5 x (119, PCI:0000:9b:00)   kmsg_test.go:248-287
+    buf = "\n".join(G["dmesg_xid_119"]["lines"]).encode()
+    hits, _ = ctx.kmsg_scan(buf)
+    assert [(h.code, h.device.decode()) for h in hits] == [(119, "PCI:0000:9b:00")] * 5
+
+
+def test_scan_multiline_record_raw_mode(ctx):
+    """the multiline fallen-off-the-bus vector only matches when the record is one unit (RAW_KMSG continuation lines)"""
+    rec = b"4,1,5,-;NVRM: The NVIDIA GPU 0000:18:00.0\n NVRM: (PCI ID: 10de:2901) installed in this system has\n NVRM: fallen off the bus and is not responding to commands.\n"
+    hits, n = ctx.kmsg_scan(rec, mode=g.SCAN_RAW_KMSG)
+    want, wn = O.scan_raw_kmsg(rec)
+    assert n == wn
+    assert [(h.code, h.device.decode()) for h in hits] == [(w["code"], w["device"]) for w in want] == [(79, "PCI:0000:18:00")]
+
+
+def test_scan_synthetic_buffer(ctx):
+    buf = synth.dmesg_buffer(3 << 20, hit_every=200)
+    hits, n_units = ctx.kmsg_scan(buf)
+    want = O.scan_lines(buf)
+    assert n_units == buf.count(b"\n") + 1
+    assert len(want) > 50
+    _cmp_hits(hits, want)
+
+
+def test_scan_raw_kmsg(ctx):
+    buf = synth.raw_kmsg_buffer(4000)
+    hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_RAW_KMSG)
+    want, wn = O.scan_raw_kmsg(buf)
+    assert n_units == wn
+    assert len(want) > 100
+    gd = [h.as_dict() for h in hits]
+    assert [(h["line"], h["kind"], h["code"], h["device"], h["offset"]) for h in gd] == \
+           [(h["line"], h["kind"], h["code"], h["device"], h["offset"]) for h in want]
+    assert [h["kmsg"] for h in gd] == [h["kmsg"] for h in want]
+    assert [h["event_type"] for h in gd] == [h["event_type"] for h in want]
+
+
+@pytest.mark.parametrize("buf", [b"", b"\n", b"\n\n\n", b"x", b"NVRM: Xid (PCI:0000:05:00): 79, a",
+                                 b"NVRM: Xid (PCI:0000:05:00): 79, a\n", b"\nNVRM: Xid (PCI:0000:05:00): 79, a"])
+def test_scan_edges(ctx, buf):
+    hits, n_units = ctx.kmsg_scan(buf)
+    want = O.scan_lines(buf)
+    assert n_units == buf.count(b"\n") + 1
+    _cmp_hits(hits, want)
+
+
+def test_scan_ragged_offsets(ctx):
+    """hit lines at every alignment relative to the 16-byte / 512-byte / 2048-byte load boundaries"""
+    line = b"NVRM: Xid (PCI:0000:05:00): 79, GPU has fallen off the bus.\n"
+    for pad in list(range(0, 40)) + [495, 500, 511, 512, 513, 2040, 2047, 2048, 2049]:
+        buf = b"a" * pad + b"\n" + line + b"tail without newline"
+        hits, n_units = ctx.kmsg_scan(buf)
+        assert n_units == 3
+        assert [(h.unit_index, h.code, h.unit_offset) for h in hits] == [(1, 79, pad + 1)], pad
+
+
+def test_hit_json_matches_oracle(ctx):
+    lines = synth.hit_lines()
+    buf = "\n".join(lines).encode()
+    hits, _ = ctx.kmsg_scan(buf)
+    n = 0
+    for h in hits:
+        if h.kind != 1:
+            assert ctx.hit_json(h) == str(h.code)
+            continue
+        line = buf[h.unit_offset:].split(b"\n", 1)[0]
+        x = O.xid_match(line)
+        assert ctx.hit_json(h, 1740327858) == O.xid_event_detail_json(x, 1740327858), line
+        n += 1
+    assert n > 200
+
+
+def test_classify_entry(ctx):
+    """gpud_xid_classify on hand-built hits: the status-specific vectors of xid/xid_test.go:13-55"""
+    for r in synth.golden("xid_kmsg.json")["status_specific"]["rows"]:
+        h = g.XidHit()
+        h.kind, h.code, h.flags = 1, r["xid"], 1
+        h.intrinfo, h.error_status, h.severity_fatal = r["intrinfo"], r["error_status"], 0
+        h.unit_name = r["unit"].encode()
+        out = ctx.classify([h])[0]
+        assert g.EVENT_NAMES[out.event_type] == r["event"]
+        for a in r.get("actions_contain", []):
+            assert {"RebootSystem": 2}[a] in list(out.actions)[:out.n_actions]
+    # plain codes: every catalog entry
+    hs = []
+    for code in sorted(O.XID_DETAILS):
+        h = g.XidHit()
+        h.kind, h.code = 1, code
+        hs.append(h)
+    for s in sorted(O.SXID_DETAILS):
+        h = g.XidHit()
+        h.kind, h.code = 2, s
+        hs.append(h)
+    out = ctx.classify(hs)
+    for h in out:
+        if h.kind == 1:
+            d = O.XID_DETAILS[h.code]
+            assert h.event_type == d.event_type and (list(h.actions)[:max(h.n_actions, 0)] == (d.actions or []))
+            assert (h.n_actions < 0) == (d.actions is None)
+        else:
+            d = O.SXID_DETAILS[h.code]
+            assert h.event_type == d["event_type"] and list(h.actions)[:max(h.n_actions, 0)] == d["actions"]
+
+
+# ------------------------------------------------------------------------------------------------ ring
+def _check_windows(got, x, W, thr, alpha=0.0, qn=99, qd=100):
+    F = x.shape[1]
+    for f in range(F):
+        want = O.window_aggregates(x[:, f], W, thr[f], alpha, qn, qd)
+        for k in ("min", "max", "p99"):
+            assert np.array_equal(got[k][f].view(np.uint64), want[k].view(np.uint64)), (k, f)
+        assert np.array_equal(got["n_over"][f].astype(np.uint64), want["n_over"]), f
+        scale = max(1e-300, float(np.max(np.abs(x[:, f]))))
+        for k in ("mean", "ema"):
+            err = np.abs(got[k][f] - want[k])
+            tol = 1e-6 * np.maximum(np.abs(want[k]), scale)
+            assert np.all(err <= tol), (k, f, float(err.max()))
+
+
+@pytest.mark.parametrize("F,n,W,cap", [(8, 4000, 1000, 4096), (5, 4096, 1000, 4096), (3, 2777, 1024, 4096), (4, 600, 7, 1024),
+                                        (2, 100, 1, 128), (6, 3000, 333, 4096), (64, 10000, 1000, 10000)])
+def test_ring_windows(ctx, F, n, W, cap):
+    x = synth.gauge_stream(F, n, seed=F * 1000 + W)
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    r.push(x)
+    got = r.reduce_all()
+    assert r.counts() == (n, n, (n + W - 1) // W)
+    _check_windows(got, x, W, thr)
+    r.close()
+
+
+def test_ring_wrap_and_odd_start(ctx):
+    F, cap, W = 4, 2048, 500
+    x = synth.gauge_stream(F, 5001, seed=7)
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    for a, b in ((0, 1500), (1500, 1501), (1501, 3999), (3999, 5001)):   # uneven batches; the ring wraps, start becomes odd
+        r.push(x[a:b])
+    total, count, nw = r.counts()
+    assert (total, count) == (5001, cap)
+    got = r.reduce_all()
+    _check_windows(got, x[-cap:], W, thr)
+    r.close()
+
+
+def test_ring_push_larger_than_capacity(ctx):
+    F, cap, W = 3, 1024, 100
+    x = synth.gauge_stream(F, 5000, seed=9)
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    r.push(x)
+    got = r.reduce_all()
+    _check_windows(got, x[-cap:], W, thr)
+    r.close()
+
+
+def test_ring_special_values(ctx):
+    """ties, constants, monotone runs, infinities, signed zeros, a NaN: selection ops follow totalOrder bit-exactly"""
+    W, cap = 1000, 4000
+    n = 4000
+    rng = np.random.default_rng(3)
+    cols = [np.full(n, 65.0), np.arange(n, dtype=np.float64), -np.arange(n, dtype=np.float64),
+            rng.integers(60, 64, n).astype(np.float64), np.where(rng.random(n) < 0.5, 0.0, -0.0),
+            np.concatenate([np.full(n - 3, 1.0), [np.inf, -np.inf, 5.0]]), rng.standard_normal(n) * 1e300,
+            np.where(np.arange(n) % 1000 < 15, 1e6 + np.arange(n), rng.standard_normal(n)),     # top-k concentrated at a window start
+            rng.integers(0, 2, n).astype(np.float64)]
+    x = np.ascontiguousarray(np.stack(cols, axis=1))
+    thr = np.zeros(x.shape[1])
+    r = g.Ring(ctx, x.shape[1], cap, W, thresholds=thr)
+    r.push(x)
+    got = r.reduce_all()
+    _check_windows(got, x, W, thr)
+    r.close()
+
+
+@pytest.mark.parametrize("qn,qd,alpha", [(50, 100, 0.1), (0, 1, 0.5), (1, 1, 0.9), (999, 1000, 0.01), (90, 100, 0.0)])
+def test_ring_quantiles_and_alpha(ctx, qn, qd, alpha):
+    F, n, W, cap = 3, 2500, 1000, 4096
+    x = synth.gauge_stream(F, n, seed=qn + 1)
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr, ema_alpha=alpha, q_num=qn, q_den=qd)
+    r.push(x)
+    got = r.reduce_all()
+    _check_windows(got, x, W, thr, alpha, qn if (qn or qd) else 99, qd if (qn or qd) else 100)
+    r.close()
+
+
+@pytest.mark.parametrize("last_n", [0, 1, 999, 3000, 5000])
+def test_ring_reduce_range(ctx, last_n):
+    F, cap, W = 6, 8192, 1000
+    x = synth.gauge_stream(F, 10000, seed=11)
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    r.push(x)
+    got = r.reduce_range(last_n)
+    n = cap if last_n == 0 else min(last_n, cap)
+    seg = x[-n:]
+    for f in range(F):
+        want = O.window_aggregates(seg[:, f], n, thr[f], 2.0 / (W + 1.0))
+        for k in ("min", "max", "p99"):
+            assert got[k][f:f + 1].view(np.uint64)[0] == want[k].view(np.uint64)[0], (k, f)
+        assert int(got["n_over"][f]) == int(want["n_over"][0])
+        scale = float(np.max(np.abs(seg[:, f])))
+        for k in ("mean", "ema"):
+            assert abs(got[k][f] - want[k][0]) <= 1e-6 * max(abs(want[k][0]), scale), (k, f)
+    r.close()
+
+
+def test_ring_full_size_properties(ctx):
+    """BASELINE configs[3] shape on one GPU (512 fields x 1 Mi samples = 4 GiB): size-independent properties."""
+    import torch
+    F, cap, W = 512, 1 << 20, 1000
+    thr = np.full(F, 0.5)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    chunk = 1 << 16
+    xs = []
+    for i in range(cap // chunk):
+        t = torch.rand((chunk, F), dtype=torch.float64, device="cuda", generator=gen)
+        if i == 3:
+            xs.append(t[:, :4].cpu().numpy())
+        r.push_device(t.data_ptr(), chunk)
+        r.sync()
+    r.reduce()
+    mn, mx, mean, p99, nov = (r.read(k) for k in ("min", "max", "mean", "p99", "n_over"))
+    nw = (cap + W - 1) // W
+    assert mn.shape == (F, nw)
+    assert np.all(mn <= mean + 1e-12) and np.all(mean <= mx + 1e-12) and np.all(p99 <= mx) and np.all(mn <= p99)
+    m_last = cap - (nw - 1) * W
+    assert int(nov.sum()) > 0 and np.all(nov[:, :-1] <= W) and np.all(nov[:, -1] <= m_last)
+    # sampled exact check: chunk 3 covers chronological samples [196608, 262144)
+    x = xs[0]
+    w0 = (3 * chunk + W - 1) // W
+    for f in range(4):
+        for w in (w0, w0 + 7, w0 + 40):
+            seg = x[w * W - 3 * chunk:(w + 1) * W - 3 * chunk, f]
+            assert mn[f, w] == seg.min() and mx[f, w] == seg.max()
+            assert p99[f, w] == np.sort(seg)[989]
+            assert nov[f, w] == np.count_nonzero(seg > 0.5)
+            assert abs(mean[f, w] - seg.mean()) < 1e-12
+    # the range view agrees with a fold of the windows
+    rr = r.reduce_range(0)
+    assert np.array_equal(rr["min"], mn.min(axis=1)) and np.array_equal(rr["max"], mx.max(axis=1))
+    assert np.array_equal(rr["n_over"].astype(np.int64), nov.astype(np.int64).sum(axis=1))
+    assert np.all(rr["p99"] >= np.percentile(p99, 1, axis=1) - 0.05) and np.all(rr["p99"] <= mx.max(axis=1))
+    r.close()
+
+
+# ------------------------------------------------------------------------------------------------ fabric
+def _raw(d):
+    r = g.FabricRaw()
+    r.gpu_index, r.nvlink_supported, r.system_expected_nvlink, r.n_links = d["gpu_index"], d["nvlink_supported"], d["system_expected_nvlink"], d["n_links"]
+    for i in range(18):
+        r.link_feature_enabled[i] = d["link_feature_enabled"][i]
+        r.link_replay_errors[i] = d["link_replay_errors"][i]
+        r.link_recovery_errors[i] = d["link_recovery_errors"][i]
+        r.link_crc_errors[i] = d["link_crc_errors"][i]
+    for j in range(16):
+        r.p2p_status[j] = d["p2p_status"][j]
+    r.fabric_valid, r.fabric_state, r.fabric_summary = d["fabric_valid"], d["fabric_state"], d["fabric_summary"]
+    r.fabric_status, r.fabric_health_mask, r.clique_id = d["fabric_status"], d["fabric_health_mask"], d.get("clique_id", 1)
+    return r
+
+
+def test_fabric_pack_and_verdict(ctx):
+    import torch
+    from test_fabric_host import SCENARIOS, scenario
+    for name in SCENARIOS:
+        gpus, at_least = scenario(name, 8)
+        table = torch.zeros(8 * 128, dtype=torch.uint8, device="cuda")
+        for d in gpus:
+            ctx.fabric_pack(_raw(d), table.data_ptr() + 128 * d["gpu_index"])
+        torch.cuda.synchronize()
+        v = ctx.fabric_verdict(table.data_ptr(), 8, at_least).as_dict()
+        want = OF.verdict(gpus, at_least)
+        for k, val in want.items():
+            assert v[k] == val, (name, k, v[k], val)
