@@ -144,8 +144,10 @@ def main():
     ctx = g.Context([local])
     thr = np.full(F, 88.0)
     ring = g.Ring(ctx, F, CAP, W, thresholds=thr, dev=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)            # a real (non-NULL) stream: the library launches on it and torch events time it
+    torch.cuda.set_stream(stream)
     ring.set_stream(stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
     # ---- synthetic resident data: gauge-like values generated on the device, appended through the real append kernel ----
     gen = torch.Generator(device=dev).manual_seed(0x67707564 + rank)

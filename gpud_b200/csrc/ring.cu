@@ -41,8 +41,11 @@ struct WinParams {
   double* out_mean;
   double* out_p99;
   uint32_t* out_nover;
-  double* part;        // [nw][F]
+  double* part;        // [F][nw] per-window EMA partial sums
   int do_select;       // 0: skip the order statistic (range reduce uses the radix select instead)
+  int n_list;          // > 0: process only windows w_list[0..n_list) of every field (generic instantiation)
+  int w_list[2];
+  int w_skip[2];       // windows the specialised launch leaves to the generic one (-1 = none)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -78,235 +81,333 @@ __global__ void __launch_bounds__(256) k_ring_append(const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// warp primitives on 64-bit keys
+// warp primitives.  Keys are kept as (hi, lo) 32-bit halves so every compare / select is one 32-bit instruction.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+struct K64 { unsigned hi, lo; };
+__device__ __forceinline__ bool k_gt(unsigned ah, unsigned al, unsigned bh, unsigned bl) { return ah > bh || (ah == bh && al > bl); }
+
+__device__ __forceinline__ K64 warp_max_k64(unsigned hi, unsigned lo) {
   // two REDUX passes instead of ten shuffles: max of the high words, then max of the low words among the winners
-  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
-  const unsigned mh = __reduce_max_sync(kFull, hi);
-  const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
-  return ((unsigned long long)mh << 32) | ml;
+  K64 r;
+  r.hi = __reduce_max_sync(kFull, hi);
+  r.lo = __reduce_max_sync(kFull, hi == r.hi ? lo : 0u);
+  return r;
 }
-__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
-  const unsigned mh = __reduce_min_sync(kFull, hi);
-  const unsigned ml = __reduce_min_sync(kFull, hi == mh ? lo : 0xffffffffu);
-  return ((unsigned long long)mh << 32) | ml;
+__device__ __forceinline__ K64 warp_min_k64(unsigned hi, unsigned lo) {
+  K64 r;
+  r.hi = __reduce_min_sync(kFull, hi);
+  r.lo = __reduce_min_sync(kFull, hi == r.hi ? lo : 0xffffffffu);
+  return r;
 }
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
-// bitonic sort across the 32 lanes, descending: afterwards lane i holds the i-th largest value
-__device__ __forceinline__ unsigned long long warp_sort_desc_u64(unsigned long long v, int lane) {
+__device__ __forceinline__ double k64_to_f64(K64 k) {
+  const unsigned m = (k.hi & 0x80000000u) ? 0x80000000u : 0xffffffffu;   // inverse of the totalOrder key map
+  const unsigned lo = (k.hi & 0x80000000u) ? k.lo : ~k.lo;
+  return __hiloint2double((int)(k.hi ^ m), (int)lo);
+}
+// k-th largest (1-based, k <= 32) of one 32-bit value per lane, counting multiplicity: 32-bit bitonic sort, straight-line
+__device__ __forceinline__ unsigned warp_kth_largest_u32(unsigned v, int k, int lane) {
+#pragma unroll
+  for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const unsigned o = __shfl_xor_sync(kFull, v, j);
+      const bool keep_max = (((lane & kk) == 0) == ((lane & j) == 0));
+      v = keep_max ? max(v, o) : min(v, o);
+    }
+  }
+  return __shfl_sync(kFull, v, k - 1);
+}
+// bitonic sort across the 32 lanes, descending, on (hi, lo)
+__device__ __forceinline__ void warp_sort_desc_k64(unsigned& hi, unsigned& lo, int lane) {
 #pragma unroll
   for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(kFull, v, j);
+      const unsigned oh = __shfl_xor_sync(kFull, hi, j), ol = __shfl_xor_sync(kFull, lo, j);
       const bool keep_max = (((lane & k) == 0) == ((lane & j) == 0));
-      const bool o_gt = o > v;
-      v = (keep_max == o_gt) ? o : v;
+      const bool take = keep_max == k_gt(oh, ol, hi, lo);
+      hi = take ? oh : hi;
+      lo = take ? ol : lo;
     }
   }
-  return v;
 }
 
-// exact k-th largest of the 32x32 register-resident keys by MSB-first bit search (always correct, slow path)
-__device__ __noinline__ unsigned long long warp_select_bits(const unsigned long long (&key)[32], int kk) {
-  unsigned long long pref = 0;
-  for (int b = 63; b >= 0; --b) {
-    const unsigned long long trial = pref | (1ull << b);
-    const unsigned long long himask = ~((1ull << b) - 1ull);
-    unsigned c = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) c += ((key[i] & himask) == trial) ? 1u : 0u;
-    c = __reduce_add_sync(kFull, c);
-    if ((int)c >= kk) pref = trial; else kk -= (int)c;
+// Candidates sit in shared memory s[0..cnt), cnt <= 32.  Returns the k-th largest (k <= cnt) and the maximum.
+// rank_i = #{j : c_j > c_i};  the k-th largest is the smallest candidate whose rank is < k.
+__device__ __forceinline__ K64 select_from_candidates(const uint2* s, int cnt, int k, int lane, K64* mx) {
+  const bool mine = lane < cnt;
+  const uint2 c = mine ? s[lane] : make_uint2(0u, 0u);      // .x = lo, .y = hi
+  int rank = 0;
+#pragma unroll 1
+  for (int j = 0; j < cnt; ++j) {
+    const uint2 o = s[j];                                    // broadcast LDS.64
+    rank += k_gt(o.y, o.x, c.y, c.x) ? 1 : 0;
   }
-  return pref;
+  *mx = warp_max_k64(mine ? c.y : 0u, mine ? c.x : 0u);
+  const bool in = mine && rank < k;
+  return warp_min_k64(in ? c.y : 0xffffffffu, in ? c.x : 0xffffffffu);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K2+K4 (+ the per-window part of K3): one warp per (field, window).
 //   lane l, register pair j holds chronological elements t = 64 j + 2 l + {0,1} of the window.
+// ALIGNED: the window is one 16-byte aligned run (no wrap) -> 128-bit loads; otherwise 64-bit loads with wrap.
 // ---------------------------------------------------------------------------------------------
+// JF >= 0: compile-time number of fully valid register pairs (= W >> 6); such an instantiation only sees full windows
+// (m == W), so the pair loop is straight-line code.  JF = -1: everything is decided at run time (any W, partial windows).
+template <bool ALIGNED, int JF>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const WinParams p) {
-  __shared__ unsigned long long s_cand[kWarpsPerBlock][kCandMax];
+  __shared__ uint2 s_cand[kWarpsPerBlock][kCandMax];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int64_t n_units = (int64_t)p.F * p.nw;
+  const int64_t n_units = p.n_list > 0 ? (int64_t)p.F * p.n_list : (int64_t)p.F * p.nw;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   for (int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp; u < n_units; u += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int f = (int)(u / p.nw);
-    const int w = (int)(u - (int64_t)f * p.nw);
+    int f, w;
+    if (p.n_list > 0) { f = (int)(u / p.n_list); w = p.w_list[(int)(u - (int64_t)f * p.n_list)]; }
+    else { f = (int)(u / p.nw); w = (int)(u - (int64_t)f * p.nw); if (w == p.w_skip[0] || w == p.w_skip[1]) continue; }
     const int64_t c0 = (int64_t)w * p.W;
-    const int m = (int)min((int64_t)p.W, p.count - c0);
+    const int m = JF >= 0 ? p.W : (int)min((int64_t)p.W, p.count - c0);
     int64_t p0 = p.start + c0;
     if (p0 >= p.cap) p0 -= p.cap;
     const double* __restrict__ base = p.ring + (int64_t)f * p.cap;
-    const bool fast = (p0 + m <= p.cap) && ((p0 & 1) == 0);
-    const int J = (m + 63) >> 6;       // register pairs that hold at least one valid element
-    const int Jfull = m >> 6;          // register pairs in which every lane's two elements are valid
+    const int J = (m + 63) >> 6;                     // register pairs that hold at least one valid element
+    const int Jfull = JF >= 0 ? JF : (m >> 6);       // register pairs in which every lane's two elements are valid
     const double thr = __ldg(p.thr + f);
 
     // ---- issue every load of the window before touching any of them (8 KB in flight per warp) ----
     double2 v[16];
-    if (fast) {
-      const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + p0);
+    if (ALIGNED) {
+      const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + p0) + lane;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const int t0 = 64 * j + 2 * lane;
+        if (JF >= 0 && j < JF) { v[j] = __ldcs(b2 + 32 * j); continue; }
         v[j] = make_double2(0.0, 0.0);
-        if (t0 < m) v[j] = __ldcs(b2 + (t0 >> 1));   // 16 B aligned; element t0+1 == m is masked below (ring has slack)
+        if (64 * j + 2 * lane < m) v[j] = __ldcs(b2 + 32 * j);   // element t0+1 == m is masked below (the ring has slack)
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int t0 = 64 * j + 2 * lane;
         v[j] = make_double2(0.0, 0.0);
-        if (t0 < m) {
-          int64_t a = p0 + t0;
-          if (a >= p.cap) a -= p.cap;
-          v[j].x = __ldcs(base + a);
-        }
-        if (t0 + 1 < m) {
-          int64_t a = p0 + t0 + 1;
-          if (a >= p.cap) a -= p.cap;
-          v[j].y = __ldcs(base + a);
-        }
+        if (t0 < m) { int64_t a = p0 + t0; if (a >= p.cap) a -= p.cap; v[j].x = __ldcs(base + a); }
+        if (t0 + 1 < m) { int64_t a = p0 + t0 + 1; if (a >= p.cap) a -= p.cap; v[j].y = __ldcs(base + a); }
       }
     }
 
-    unsigned long long key[32];
-    double sum = 0.0, es0 = 0.0, es1 = 0.0;
+    // keys replace the loaded doubles in place (same register pairs): K[i] = totalOrder key of element i of this lane
+    unsigned long long K[32];
+    double sum0 = 0.0, sum1 = 0.0, es0 = 0.0, es1 = 0.0;
     unsigned nov = 0;
-    unsigned long long kmin = ~0ull, kmax = 0ull;
+    unsigned mh = 0u, nh = 0xffffffffu;    // lane max / min of the key high words
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      if (j < Jfull) {                       // warp-uniform: whole register pair valid
+      if (JF >= 0 ? (j < JF) : (j < Jfull)) {  // whole register pair valid (compile-time when JF >= 0, else warp-uniform)
         const double x0 = v[j].x, x1 = v[j].y;
         const unsigned long long k0 = gpud_f64_key((unsigned long long)__double_as_longlong(x0));
         const unsigned long long k1 = gpud_f64_key((unsigned long long)__double_as_longlong(x1));
-        key[2 * j] = k0;
-        key[2 * j + 1] = k1;
-        sum += x0 + x1;
-        es0 = fma(es0, p.q64, x0);
-        es1 = fma(es1, p.q64, x1);
-        nov += (x0 > thr) ? 1u : 0u;
-        nov += (x1 > thr) ? 1u : 0u;
-        kmax = max(kmax, max(k0, k1));
-        kmin = min(kmin, min(k0, k1));
-      } else if (j < J) {                    // the one partially valid pair
+        sum0 += x0; sum1 += x1;
+        es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
+        if (x0 > thr) ++nov;
+        if (x1 > thr) ++nov;
+        K[2 * j] = k0; K[2 * j + 1] = k1;
+        const unsigned a0 = (unsigned)(k0 >> 32), a1 = (unsigned)(k1 >> 32);
+        mh = max(mh, max(a0, a1));
+        nh = min(nh, min(a0, a1));
+      } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
         const int t0 = 64 * j + 2 * lane;
-        const bool a0 = t0 < m, a1 = t0 + 1 < m;
-        const double x0 = a0 ? v[j].x : 0.0, x1 = a1 ? v[j].y : 0.0;
-        const unsigned long long k0 = a0 ? gpud_f64_key((unsigned long long)__double_as_longlong(x0)) : 0ull;
-        const unsigned long long k1 = a1 ? gpud_f64_key((unsigned long long)__double_as_longlong(x1)) : 0ull;
-        key[2 * j] = k0;
-        key[2 * j + 1] = k1;
-        sum += x0 + x1;
-        es0 = fma(es0, p.q64, x0);
-        es1 = fma(es1, p.q64, x1);
-        nov += (a0 && x0 > thr) ? 1u : 0u;
-        nov += (a1 && x1 > thr) ? 1u : 0u;
-        kmax = max(kmax, max(k0, k1));
-        if (a0) kmin = min(kmin, k0);
-        if (a1) kmin = min(kmin, k1);
+        const bool q0 = t0 < m, q1 = t0 + 1 < m;
+        const double x0 = q0 ? v[j].x : 0.0, x1 = q1 ? v[j].y : 0.0;
+        const unsigned long long k0 = q0 ? gpud_f64_key((unsigned long long)__double_as_longlong(x0)) : 0ull;
+        const unsigned long long k1 = q1 ? gpud_f64_key((unsigned long long)__double_as_longlong(x1)) : 0ull;
+        sum0 += x0; sum1 += x1;
+        es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
+        if (q0 && x0 > thr) ++nov;
+        if (q1 && x1 > thr) ++nov;
+        K[2 * j] = k0; K[2 * j + 1] = k1;
+        const unsigned a0 = (unsigned)(k0 >> 32), a1 = (unsigned)(k1 >> 32);
+        mh = max(mh, max(a0, a1));
+        if (q0) nh = min(nh, a0);
+        if (q1) nh = min(nh, a1);
       } else {
-        key[2 * j] = 0ull;
-        key[2 * j + 1] = 0ull;
+        K[2 * j] = K[2 * j + 1] = 0ull;   // padding: the smallest key
       }
     }
+#define KH(i) ((unsigned)(K[i] >> 32))
+#define KL(i) ((unsigned)K[i])
 
-    // ---- warp-level combines ----
-    const unsigned long long wmax = warp_max_u64(kmax);
-    const unsigned long long wmin = warp_min_u64(kmin);
-    sum = warp_sum_f64(sum);
+    // ---- sums ----
+    const double sum = warp_sum_f64(sum0 + sum1);
     nov = __reduce_add_sync(kFull, nov);
     // EMA partial: sum_t alpha (1-alpha)^(m-1-t) x_t with t = 64 j + 2 lane + h; Horner above ran over j < J with q64
     const int eb = m - 1 - 64 * (J - 1) - 2 * lane;          // exponent of this lane's h=0 element in pair J-1, in [-62, 63]
     double ep = es0 * __ldg(p.pw + (eb + 63)) + es1 * __ldg(p.pw + (eb - 1 + 63));
     ep = warp_sum_f64(ep) * p.alpha;
 
-    // ---- exact order statistic: k-th largest, k = m - ceil(m q) + 1 ----
+    // ---- exact minimum: global min of the high words, then min of the low words among the holders ----
+    K64 wmin;
+    wmin.hi = __reduce_min_sync(kFull, nh);
+    {
+      unsigned nl = 0xffffffffu;
+      if (wmin.hi != 0u) {                   // padding keys have hi == 0: they cannot collide unless the minimum's hi is 0
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (KH(i) == wmin.hi) nl = min(nl, KL(i));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (KH(i) == 0u && 64 * (i >> 1) + 2 * lane + (i & 1) < m) nl = min(nl, KL(i));
+      }
+      wmin.lo = __reduce_min_sync(kFull, nl);
+    }
+
+    // ---- exact order statistic: k-th largest, k = m - ceil(m q) + 1; the maximum falls out of the same candidate set ----
     long long r = ((long long)m * p.q_num + p.q_den - 1) / p.q_den;
     r = r < 1 ? 1 : (r > m ? m : r);
     const int k = m - (int)r + 1;
-    unsigned long long ans = 0ull;
-    if (!p.do_select) {
-    } else if (k <= 32) {
-      // lower bound L = k-th largest lane maximum: at least k elements are >= L, so the answer is >= L
-      const unsigned long long sorted = warp_sort_desc_u64(kmax, lane);
-      const unsigned long long L = __shfl_sync(kFull, sorted, k - 1);
-      int cnt = 0;                                            // elements strictly above L, compacted to shared memory
+    K64 ans, wmax;
+    ans.hi = ans.lo = 0u;
+    bool done = false;
+    uint2* cand = s_cand[warp];
+    if (k <= 32) {
+      // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L'.
+      const unsigned Lh = warp_kth_largest_u32(mh, k, lane);
+      int cnt = 0;                           // keys strictly above L', compacted to shared memory
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const bool pr = key[i] > L;
-        const unsigned b = __ballot_sync(kFull, pr);
-        if (b) {
-          if (pr) {
-            const int pos = cnt + __popc(b & lt_mask);
-            if (pos < kCandMax) s_cand[warp][pos] = key[i];
+      for (int g = 0; g < 8; ++g) {
+        bool pr[4];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { pr[q] = k_gt(KH(4 * g + q), KL(4 * g + q), Lh, 0u); any = any || pr[q]; }
+        if (__any_sync(kFull, any)) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const unsigned b = __ballot_sync(kFull, pr[q]);
+            if (pr[q]) { const int pos = cnt + __popc(b & lt_mask); if (pos < kCandMax) cand[pos] = make_uint2(KL(4 * g + q), KH(4 * g + q)); }
+            cnt += __popc(b);
           }
-          cnt += __popc(b);
         }
       }
-      if (cnt < k) {
-        ans = L;                                              // fewer than k above L and >= k at-or-above L  =>  answer is L
-      } else if (cnt <= 32) {
-        __syncwarp();
-        const unsigned long long c = lane < cnt ? s_cand[warp][lane] : 0ull;
-        const unsigned long long cs = warp_sort_desc_u64(c, lane);
-        ans = __shfl_sync(kFull, cs, k - 1);
-        __syncwarp();
-      } else {
-        ans = warp_select_bits(key, k);
+      __syncwarp();
+      if (cnt <= 32) {
+        if (cnt == 0) { ans.hi = Lh; ans.lo = 0u; wmax = ans; }
+        else {
+          const K64 sel = select_from_candidates(cand, cnt, min(k, cnt), lane, &wmax);
+          if (cnt < k) { ans.hi = Lh; ans.lo = 0u; } else ans = sel;     // fewer than k above L' and >= k at-or-above  =>  L'
+        }
+        done = true;
       }
-    } else {
-      ans = warp_select_bits(key, k);
+      __syncwarp();
+    }
+    if (!done) {
+      // exact lane maximum (low words among the lane's top high word), needed by both slower paths
+      unsigned ml = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) if (KH(i) == mh) ml = max(ml, KL(i));
+      wmax = warp_max_k64(mh, ml);
+      bool solved = false;
+      if (k <= 32) {
+        // medium path: exact 64-bit bound L = k-th largest lane maximum; ties collapse here (constant gauges)
+        unsigned sh = mh, sl = ml;
+        warp_sort_desc_k64(sh, sl, lane);
+        const unsigned Lh = __shfl_sync(kFull, sh, k - 1), Ll = __shfl_sync(kFull, sl, k - 1);
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool pr = k_gt(KH(i), KL(i), Lh, Ll);
+          const unsigned b = __ballot_sync(kFull, pr);
+          if (b) {
+            if (pr) { const int pos = cnt + __popc(b & lt_mask); if (pos < kCandMax) cand[pos] = make_uint2(KL(i), KH(i)); }
+            cnt += __popc(b);
+          }
+        }
+        __syncwarp();
+        if (cnt < k) { ans.hi = Lh; ans.lo = Ll; solved = true; }
+        else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); solved = true; }
+        __syncwarp();
+      }
+      if (!solved) {
+        // always-correct slow path: MSB-first bit search over the register-resident keys
+        unsigned long long pref = 0ull;
+        int kk = k;
+#pragma unroll 1
+        for (int b = 63; b >= 0; --b) {
+          const unsigned long long trial = pref | (1ull << b);
+          const unsigned long long himask = ~((1ull << b) - 1ull);
+          const unsigned th = (unsigned)(trial >> 32), tl = (unsigned)trial, hh = (unsigned)(himask >> 32), hl = (unsigned)himask;
+          unsigned c = 0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) c += ((KH(i) & hh) == th && (KL(i) & hl) == tl) ? 1u : 0u;
+          c = __reduce_add_sync(kFull, c);
+          if ((int)c >= kk) pref = trial; else kk -= (int)c;
+        }
+        ans.hi = (unsigned)(pref >> 32);
+        ans.lo = (unsigned)pref;
+      }
     }
 
     if (lane == 0) {
       const int64_t o = (int64_t)f * p.nw + w;
-      p.out_min[o] = __longlong_as_double((long long)gpud_key_f64bits(wmin));
-      p.out_max[o] = __longlong_as_double((long long)gpud_key_f64bits(wmax));
+      p.out_min[o] = k64_to_f64(wmin);
+      p.out_max[o] = k64_to_f64(wmax);
       p.out_mean[o] = sum / (double)m;
-      p.out_p99[o] = __longlong_as_double((long long)gpud_key_f64bits(ans));
+      if (p.do_select) p.out_p99[o] = k64_to_f64(ans);
       p.out_nover[o] = nov;
-      p.part[(int64_t)w * p.F + f] = ep;
+      p.part[o] = ep;
     }
   }
+#undef KH
+#undef KL
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 carry: E_w = (1-alpha)^{m_w} E_{w-1} + P_w, E_{-1} = x[0] (oldest sample).  One thread per field; the
-// partials are stored [nw][F] so the loads are coalesced and independent of the FMA chain.
+// K3 carry: E_w = (1-alpha)^{m_w} E_{w-1} + P_w, E_{-1} = x[0] (oldest sample).  One 128-thread CTA per field:
+// rows of 128 consecutive windows are scanned with a decayed Kogge-Stone prefix (S_t += d^off S_{t-off}), the carry
+// crosses rows through shared memory; only the last window can have a different decay.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_ema_carry(const double* __restrict__ part, const double* __restrict__ ring, int64_t cap,
                                                     int64_t start, int F, int nw, double d_full, double d_last,
                                                     double* __restrict__ out_ema) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-  double e = ring[(int64_t)f * cap + start];
-  int w = 0;
-  for (; w + 8 <= nw - 1; w += 8) {
-    double pv[8];
+  __shared__ double s_warp[4];
+  __shared__ double s_carry;
+  const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const double* __restrict__ P = part + (int64_t)f * nw;
+  double* __restrict__ O = out_ema + (int64_t)f * nw;
+  double dp[6];                              // d^1, d^2, d^4, d^8, d^16, d^32
+  dp[0] = d_full;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) pv[i] = __ldg(part + (int64_t)(w + i) * F + f);
+  for (int i = 1; i < 6; ++i) dp[i] = dp[i - 1] * dp[i - 1];
+  const double my_pow = pow(d_full, (double)(t + 1));        // d^(t+1): weight of the incoming carry at position t of a row
+  const double lane_pow = pow(d_full, (double)(lane + 1));
+  if (t == 0) s_carry = ring[(int64_t)f * cap + start];
+  __syncthreads();
+  const int n_main = nw - 1;                 // windows with the full decay; the last window is folded in afterwards
+  for (int row = 0; row * 128 < n_main; ++row) {
+    const int w = row * 128 + t;
+    double sacc = w < n_main ? __ldg(P + w) : 0.0;
+    // inclusive decayed scan inside the warp
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      e = fma(d_full, e, pv[i]);
-      out_ema[(int64_t)f * nw + w + i] = e;
+    for (int i = 0; i < 5; ++i) {
+      const double o = __shfl_up_sync(kFull, sacc, 1 << i);
+      if (lane >= (1 << i)) sacc = fma(dp[i], o, sacc);
     }
+    if (lane == 31) s_warp[wid] = sacc;
+    __syncthreads();
+    // carry of the preceding warps of this row: sum_{v < wid} d^(32 (wid-1-v)) * s_warp[v], applied with d^(lane+1)
+    double pre = 0.0;
+    for (int v2 = 0; v2 < wid; ++v2) pre = fma(pre, dp[5], s_warp[v2]);
+    sacc = fma(lane_pow, pre, sacc);
+    const double e = fma(my_pow, s_carry, sacc);
+    if (w < n_main) O[w] = e;
+    __syncthreads();
+    if (w == min(n_main, (row + 1) * 128) - 1) s_carry = e;   // the row's last valid window carries into the next row
+    __syncthreads();
   }
-  for (; w < nw; ++w) {
-    const double d = (w == nw - 1) ? d_last : d_full;
-    e = fma(d, e, __ldg(part + (int64_t)w * F + f));
-    out_ema[(int64_t)f * nw + w] = e;
-  }
+  if (t == 0) O[nw - 1] = fma(d_last, s_carry, __ldg(P + nw - 1));
 }
 
 }  // namespace
@@ -350,7 +451,7 @@ extern "C" int32_t gpud_ring_create(gpud_ctx* ctx, int32_t dev, const gpud_ring_
   if (gpud_dev_slot(ctx, dev) < 0) return gpud_fail(ctx, GPUD_E_INVALID, "device %d is not part of this ctx", dev);
   if (cfg->n_fields < 1 || cfg->window < 1 || cfg->window > kMaxWindow || cfg->capacity < cfg->window || (cfg->capacity & 1))
     return gpud_fail(ctx, GPUD_E_INVALID, "ring cfg: need n_fields>=1, 1<=window<=%d, capacity even and >= window", kMaxWindow);
-  double alpha = cfg->ema_alpha > 0 ? cfg->ema_alpha : 2.0 / (cfg->window + 1.0);
+  double alpha = cfg->ema_alpha > 0 ? cfg->ema_alpha : std::min(2.0 / (cfg->window + 1.0), 0.9999);   // SPEC.md: default clamped
   if (!(alpha > 0.0) || alpha > 0.9999) return gpud_fail(ctx, GPUD_E_INVALID, "ema_alpha must be in (0, 0.9999]");
   int qn = cfg->q_num, qd = cfg->q_den;
   if (qn == 0 && qd == 0) { qn = 99; qd = 100; }
@@ -487,6 +588,48 @@ extern "C" int32_t gpud_ring_counts(gpud_ring* r, int64_t* total, int64_t* count
   return GPUD_OK;
 }
 
+
+// Launch the window kernel(s).  The bulk goes to the aligned 128-bit instantiation (specialised for the window shape when
+// W >> 6 is 15 or 16, i.e. W in 960..1024); the window that wraps the physical end of the ring and a trailing partial
+// window go to the generic run-time instantiation, which also serves rings whose start is odd.
+template <bool ALIGNED, int JF>
+static cudaError_t launch_one(gpud_ring* r, const WinParams& p, int64_t units) {
+  // persistent grid: 2 CTAs of 8 warps per SM, a whole number of waves (148 SMs)
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 2));
+  k_window_reduce<ALIGNED, JF><<<grid, kWarpsPerBlock * 32, 0, r->stream>>>(p);
+  return cudaGetLastError();
+}
+
+static int32_t launch_windows(gpud_ring* r, WinParams p) {
+  p.n_list = 0;
+  p.w_list[0] = p.w_list[1] = -1;
+  p.w_skip[0] = p.w_skip[1] = -1;
+  const int64_t units = (int64_t)p.F * p.nw;
+  if ((p.start & 1) || ((p.W & 1) && p.nw > 1)) {          // some window would start on an odd element: 64-bit loads everywhere
+    GPUD_CUDA(r->ctx, (launch_one<false, -1>(r, p, units)));
+    return GPUD_OK;
+  }
+  int n_skip = 0;
+  const int64_t c_wrap = p.cap - p.start;                 // chronological index of the sample stored at physical column 0
+  if (p.start > 0 && c_wrap < p.count && (c_wrap % p.W) != 0) p.w_skip[n_skip++] = (int)(c_wrap / p.W);
+  const int jf = p.W >> 6;
+  const bool special = (jf == 15 || jf == 16) && p.nw > 1;
+  if (special && (p.count % p.W) != 0 && (n_skip == 0 || p.w_skip[0] != p.nw - 1)) p.w_skip[n_skip++] = p.nw - 1;   // trailing partial window
+  cudaError_t e;
+  if (special && jf == 15) e = launch_one<true, 15>(r, p, units);
+  else if (special && jf == 16) e = launch_one<true, 16>(r, p, units);
+  else e = launch_one<true, -1>(r, p, units);
+  GPUD_CUDA(r->ctx, e);
+  if (n_skip > 0) {
+    p.n_list = n_skip;
+    p.w_list[0] = p.w_skip[0];
+    p.w_list[1] = p.w_skip[1];
+    p.w_skip[0] = p.w_skip[1] = -1;
+    GPUD_CUDA(r->ctx, (launch_one<false, -1>(r, p, (int64_t)p.F * n_skip)));
+  }
+  return GPUD_OK;
+}
+
 extern "C" int32_t gpud_ring_reduce(gpud_ring* r) {
   if (!r) return GPUD_E_INVALID;
   const int64_t count = ring_count(r);
@@ -499,15 +642,11 @@ extern "C" int32_t gpud_ring_reduce(gpud_ring* r) {
   p.q64 = pow(1.0 - r->alpha, 64.0); p.alpha = r->alpha;
   p.out_min = r->d_res[GPUD_OP_MIN]; p.out_max = r->d_res[GPUD_OP_MAX]; p.out_mean = r->d_res[GPUD_OP_MEAN];
   p.out_p99 = r->d_res[GPUD_OP_P99]; p.out_nover = r->d_nover; p.part = r->d_part; p.do_select = 1;
-  const int64_t units = (int64_t)p.F * p.nw;
-  // persistent grid: 2 CTAs of 8 warps per SM, a whole number of waves (148 SMs)
-  const int grid = (int)std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 2);
   cudaEventRecord(r->ev_k[0], r->stream);
-  k_window_reduce<<<grid, kWarpsPerBlock * 32, 0, r->stream>>>(p);
-  GPUD_CUDA(r->ctx, cudaGetLastError());
+  { int32_t rc = launch_windows(r, p); if (rc) return rc; }
   cudaEventRecord(r->ev_k[1], r->stream);
   const int m_last = (int)(count - (int64_t)(p.nw - 1) * r->W);
-  k_ema_carry<<<(r->F + 127) / 128, 128, 0, r->stream>>>(r->d_part, r->d_ring, r->cap, p.start, r->F, p.nw,
+  k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_part, r->d_ring, r->cap, p.start, r->F, p.nw,
                                                         pow(1.0 - r->alpha, (double)r->W), pow(1.0 - r->alpha, (double)m_last),
                                                         r->d_res[GPUD_OP_EMA]);
   GPUD_CUDA(r->ctx, cudaGetLastError());
@@ -575,12 +714,9 @@ int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v) {
   p.q_num = r->q_num; p.q_den = r->q_den; p.thr = r->d_thr; p.pw = r->d_pw; p.q64 = pow(1.0 - r->alpha, 64.0); p.alpha = r->alpha;
   p.out_min = r->d_rng[0]; p.out_max = r->d_rng[1]; p.out_mean = r->d_rng[2]; p.out_p99 = r->d_rng[3]; p.out_nover = r->d_rng_nover;
   p.part = r->d_rng[4]; p.do_select = 0;
-  const int64_t units = (int64_t)p.F * p.nw;
-  const int grid = (int)std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 2);
-  k_window_reduce<<<grid, kWarpsPerBlock * 32, 0, r->stream>>>(p);
-  GPUD_CUDA(r->ctx, cudaGetLastError());
+  { int32_t rc = launch_windows(r, p); if (rc) return rc; }
   const int m_last = (int)(n - (int64_t)(nw - 1) * Wp);
-  k_ema_carry<<<(r->F + 127) / 128, 128, 0, r->stream>>>(r->d_rng[4], r->d_ring, r->cap, start, r->F, nw, pow(1.0 - r->alpha, (double)Wp),
+  k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_rng[4], r->d_ring, r->cap, start, r->F, nw, pow(1.0 - r->alpha, (double)Wp),
                                                         pow(1.0 - r->alpha, (double)m_last), r->d_rng[3]);
   GPUD_CUDA(r->ctx, cudaGetLastError());
   v->ring = r->d_ring; v->F = r->F; v->cap = r->cap; v->start = start; v->n = n; v->Wp = Wp; v->nw = nw;

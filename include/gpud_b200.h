@@ -64,7 +64,7 @@ typedef struct {
   int32_t n_fields;         /* F: gauges per GPU (api/v1/types.go:136-141 fixes the sample type: f64)   */
   int32_t window;           /* W: tumbling window length in samples, 1..1024                            */
   int64_t capacity;         /* CAP: samples kept per field (even, >= window)                            */
-  double ema_alpha;         /* 0 => 2/(W+1); otherwise in (0, 0.9999]                                   */
+  double ema_alpha;         /* 0 => min(2/(W+1), 0.9999); otherwise in (0, 0.9999]                    */
   int32_t q_num, q_den;     /* order statistic, nearest rank ceil(m*q_num/q_den); 0/0 => 99/100         */
   const double* thresholds; /* [F] or NULL (= +inf: nothing counts)                                     */
 } gpud_ring_cfg;

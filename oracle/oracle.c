@@ -49,7 +49,7 @@ static uint64_t select_kth(uint64_t* a, int n, int k) {
 /* One field: x[0..n) chronological.  Outputs are arrays of ceil(n/W).  `e_io` carries the EMA (in: e_{-1}). */
 void orc_window_aggregates(const double* x, int64_t n, int32_t W, double thr, double alpha, int32_t q_num, int32_t q_den,
                            double* o_min, double* o_max, double* o_mean, double* o_ema, double* o_p99, uint32_t* o_nover) {
-  if (alpha <= 0.0) alpha = 2.0 / (W + 1.0);
+  if (alpha <= 0.0) { alpha = 2.0 / (W + 1.0); if (alpha > 0.9999) alpha = 0.9999; }
   if (q_num == 0 && q_den == 0) { q_num = 99; q_den = 100; }
   uint64_t* scratch = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)W);
   double e = n > 0 ? x[0] : 0.0;

@@ -579,7 +579,7 @@ def window_aggregates(x: np.ndarray, W: int, thr: float, alpha: float = 0.0, q_n
     n = x.shape[0]
     nw = (n + W - 1) // W
     if alpha <= 0.0:
-        alpha = 2.0 / (W + 1.0)
+        alpha = min(2.0 / (W + 1.0), 0.9999)
     out = {k: np.zeros(nw, dtype=np.float64) for k in ("min", "max", "mean", "ema", "p99")}
     out["n_over"] = np.zeros(nw, dtype=np.uint64)
     e = float(x[0]) if n else 0.0
