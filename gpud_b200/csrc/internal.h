@@ -55,7 +55,9 @@ inline int gpud_dev_slot(gpud_ctx* ctx, int dev) {
 #ifdef __CUDACC__
 // IEEE-754 totalOrder key (oracle/SPEC.md): unsigned compare of the key == totalOrder of the doubles.
 __host__ __device__ __forceinline__ unsigned long long gpud_f64_key(unsigned long long bits) {
-  return bits ^ ((bits >> 63) ? ~0ull : 0x8000000000000000ull);
+  // branch-free: m = all-ones for negatives (arithmetic shift of the sign), then flip everything / only the sign bit
+  const unsigned long long m = (unsigned long long)((long long)bits >> 63);
+  return bits ^ (m | 0x8000000000000000ull);
 }
 __host__ __device__ __forceinline__ unsigned long long gpud_key_f64bits(unsigned long long key) {
   return key ^ ((key >> 63) ? 0x8000000000000000ull : ~0ull);

@@ -43,6 +43,8 @@ struct WinParams {
   uint32_t* out_nover;
   double* part;        // [F][nw] per-window EMA partial sums
   int do_select;       // 0: skip the order statistic (range reduce uses the radix select instead)
+  int k_full;          // k-th largest rank of a full window (m == W), precomputed on the host
+  double inv_w;        // 1.0 / W
   int n_list;          // > 0: process only windows w_list[0..n_list) of every field (generic instantiation)
   int w_list[2];
   int w_skip[2];       // windows the specialised launch leaves to the generic one (-1 = none)
@@ -155,23 +157,60 @@ __device__ __forceinline__ K64 select_from_candidates(const uint2* s, int cnt, i
 
 // ---------------------------------------------------------------------------------------------
 // K2+K4 (+ the per-window part of K3): one warp per (field, window).
-//   lane l, register pair j holds chronological elements t = 64 j + 2 l + {0,1} of the window.
+//   lane l, register pair j holds chronological elements t = 64 j + 2 l + {0,1} of the window (128-bit coalesced loads).
+//   Pass 1 streams the loaded values once: sum, EMA Horner, threshold count, min/max of the key high words, and parks the
+//   totalOrder keys in shared memory, row = lane (272-byte rows: conflict-free 128-bit stores and 64-bit row reads).
+//   Everything after that is warp-cooperative over ROWS: only the ~k lanes whose maximum can reach the order statistic
+//   are revisited, 32 keys per LDS, instead of every lane scanning its 32 registers.
 // ALIGNED: the window is one 16-byte aligned run (no wrap) -> 128-bit loads; otherwise 64-bit loads with wrap.
-// ---------------------------------------------------------------------------------------------
 // JF >= 0: compile-time number of fully valid register pairs (= W >> 6); such an instantiation only sees full windows
 // (m == W), so the pair loop is straight-line code.  JF = -1: everything is decided at run time (any W, partial windows).
+// ---------------------------------------------------------------------------------------------
+constexpr int kRowU64 = 34;                                   // 32 keys + 2 pad -> 272-byte rows
+constexpr int kWarpSmemBytes = 32 * kRowU64 * 8 + kCandMax * 8;
+constexpr int kBlockSmemBytes = kWarpsPerBlock * kWarpSmemBytes;
+
+__device__ __forceinline__ int elem_index(int row, int col) { return 64 * (col >> 1) + 2 * row + (col & 1); }   // chronological t
+
+// compact the keys of the flagged rows that are > (Lh, Ll) into cand[]; returns how many there are (may exceed kCandMax)
+__device__ __forceinline__ int gather_above(const unsigned long long* sk, unsigned rows, unsigned Lh, unsigned Ll, uint2* cand, int lane,
+                                            unsigned lt_mask) {
+  int cnt = 0;
+  while (rows) {
+    const int row = __ffs(rows) - 1;
+    rows &= rows - 1;
+    const unsigned long long kv = sk[row * kRowU64 + lane];
+    const unsigned h = (unsigned)(kv >> 32), l = (unsigned)kv;
+    const bool pr = k_gt(h, l, Lh, Ll);
+    const unsigned b = __ballot_sync(kFull, pr);
+    if (pr) { const int pos = cnt + __popc(b & lt_mask); if (pos < kCandMax) cand[pos] = make_uint2(l, h); }
+    cnt += __popc(b);
+  }
+  __syncwarp();
+  return cnt;
+}
+
 template <bool ALIGNED, int JF>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const WinParams p) {
-  __shared__ uint2 s_cand[kWarpsPerBlock][kCandMax];
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_window_reduce(const WinParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)warp * kWarpSmemBytes);   // [32][kRowU64]
+  uint2* cand = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * kWarpSmemBytes + 32 * kRowU64 * 8);
+  ulonglong2* my_row2 = reinterpret_cast<ulonglong2*>(sk + lane * kRowU64);
   const int64_t n_units = p.n_list > 0 ? (int64_t)p.F * p.n_list : (int64_t)p.F * p.nw;
   const unsigned lt_mask = (1u << lane) - 1u;
 
-  for (int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp; u < n_units; u += (int64_t)gridDim.x * kWarpsPerBlock) {
-    int f, w;
-    if (p.n_list > 0) { f = (int)(u / p.n_list); w = p.w_list[(int)(u - (int64_t)f * p.n_list)]; }
-    else { f = (int)(u / p.nw); w = (int)(u - (int64_t)f * p.nw); if (w == p.w_skip[0] || w == p.w_skip[1]) continue; }
+  // (field, slot) advance incrementally: one division per kernel instead of one per window
+  const int per_f = p.n_list > 0 ? p.n_list : p.nw;
+  const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
+  const int df = (int)(stride / per_f), ds = (int)(stride - (int64_t)df * per_f);
+  const int64_t u0 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  int f = (int)(u0 / per_f), slot = (int)(u0 - (int64_t)f * per_f);
+  for (int64_t u = u0; u < n_units; u += stride, f += df, slot += ds) {
+    if (slot >= per_f) { slot -= per_f; ++f; }
+    const int w = p.n_list > 0 ? p.w_list[slot] : slot;
+    if (p.n_list == 0 && (w == p.w_skip[0] || w == p.w_skip[1])) continue;
     const int64_t c0 = (int64_t)w * p.W;
     const int m = JF >= 0 ? p.W : (int)min((int64_t)p.W, p.count - c0);
     int64_t p0 = p.start + c0;
@@ -201,46 +240,44 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
       }
     }
 
-    // keys replace the loaded doubles in place (same register pairs): K[i] = totalOrder key of element i of this lane
-    unsigned long long K[32];
+    // ---- pass 1 ----
     double sum0 = 0.0, sum1 = 0.0, es0 = 0.0, es1 = 0.0;
     unsigned nov = 0;
     unsigned mh = 0u, nh = 0xffffffffu;    // lane max / min of the key high words
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
+      ulonglong2 kk;
       if (JF >= 0 ? (j < JF) : (j < Jfull)) {  // whole register pair valid (compile-time when JF >= 0, else warp-uniform)
         const double x0 = v[j].x, x1 = v[j].y;
-        const unsigned long long k0 = gpud_f64_key((unsigned long long)__double_as_longlong(x0));
-        const unsigned long long k1 = gpud_f64_key((unsigned long long)__double_as_longlong(x1));
+        kk.x = gpud_f64_key((unsigned long long)__double_as_longlong(x0));
+        kk.y = gpud_f64_key((unsigned long long)__double_as_longlong(x1));
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (x0 > thr) ++nov;
         if (x1 > thr) ++nov;
-        K[2 * j] = k0; K[2 * j + 1] = k1;
-        const unsigned a0 = (unsigned)(k0 >> 32), a1 = (unsigned)(k1 >> 32);
+        const unsigned a0 = (unsigned)(kk.x >> 32), a1 = (unsigned)(kk.y >> 32);
         mh = max(mh, max(a0, a1));
         nh = min(nh, min(a0, a1));
       } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
         const int t0 = 64 * j + 2 * lane;
         const bool q0 = t0 < m, q1 = t0 + 1 < m;
         const double x0 = q0 ? v[j].x : 0.0, x1 = q1 ? v[j].y : 0.0;
-        const unsigned long long k0 = q0 ? gpud_f64_key((unsigned long long)__double_as_longlong(x0)) : 0ull;
-        const unsigned long long k1 = q1 ? gpud_f64_key((unsigned long long)__double_as_longlong(x1)) : 0ull;
+        kk.x = q0 ? gpud_f64_key((unsigned long long)__double_as_longlong(x0)) : 0ull;
+        kk.y = q1 ? gpud_f64_key((unsigned long long)__double_as_longlong(x1)) : 0ull;
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (q0 && x0 > thr) ++nov;
         if (q1 && x1 > thr) ++nov;
-        K[2 * j] = k0; K[2 * j + 1] = k1;
-        const unsigned a0 = (unsigned)(k0 >> 32), a1 = (unsigned)(k1 >> 32);
+        const unsigned a0 = (unsigned)(kk.x >> 32), a1 = (unsigned)(kk.y >> 32);
         mh = max(mh, max(a0, a1));
         if (q0) nh = min(nh, a0);
         if (q1) nh = min(nh, a1);
       } else {
-        K[2 * j] = K[2 * j + 1] = 0ull;   // padding: the smallest key
+        kk.x = kk.y = 0ull;                  // padding: the smallest key
       }
+      my_row2[j] = kk;                       // STS.128, conflict-free (272-byte row stride)
     }
-#define KH(i) ((unsigned)(K[i] >> 32))
-#define KL(i) ((unsigned)K[i])
+    __syncwarp();
 
     // ---- sums ----
     const double sum = warp_sum_f64(sum0 + sum1);
@@ -250,49 +287,36 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
     double ep = es0 * __ldg(p.pw + (eb + 63)) + es1 * __ldg(p.pw + (eb - 1 + 63));
     ep = warp_sum_f64(ep) * p.alpha;
 
-    // ---- exact minimum: global min of the high words, then min of the low words among the holders ----
+    // ---- exact minimum: global min of the high words, then the low words of the rows that hold it ----
     K64 wmin;
     wmin.hi = __reduce_min_sync(kFull, nh);
     {
+      unsigned rows = __ballot_sync(kFull, nh == wmin.hi);
       unsigned nl = 0xffffffffu;
-      if (wmin.hi != 0u) {                   // padding keys have hi == 0: they cannot collide unless the minimum's hi is 0
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (KH(i) == wmin.hi) nl = min(nl, KL(i));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) if (KH(i) == 0u && 64 * (i >> 1) + 2 * lane + (i & 1) < m) nl = min(nl, KL(i));
+      while (rows) {
+        const int row = __ffs(rows) - 1;
+        rows &= rows - 1;
+        const unsigned long long kv = sk[row * kRowU64 + lane];
+        if ((unsigned)(kv >> 32) == wmin.hi && elem_index(row, lane) < m) nl = min(nl, (unsigned)kv);   // the index test screens padding
       }
       wmin.lo = __reduce_min_sync(kFull, nl);
     }
 
     // ---- exact order statistic: k-th largest, k = m - ceil(m q) + 1; the maximum falls out of the same candidate set ----
-    long long r = ((long long)m * p.q_num + p.q_den - 1) / p.q_den;
-    r = r < 1 ? 1 : (r > m ? m : r);
-    const int k = m - (int)r + 1;
+    int k = p.k_full;
+    if (JF < 0 && m != p.W) {
+      long long r = ((long long)m * p.q_num + p.q_den - 1) / p.q_den;
+      r = r < 1 ? 1 : (r > m ? m : r);
+      k = m - (int)r + 1;
+    }
     K64 ans, wmax;
     ans.hi = ans.lo = 0u;
     bool done = false;
-    uint2* cand = s_cand[warp];
     if (k <= 32) {
-      // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L'.
+      // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L', so the answer is too.
+      // Only rows whose maximum reaches L' can hold keys above it.
       const unsigned Lh = warp_kth_largest_u32(mh, k, lane);
-      int cnt = 0;                           // keys strictly above L', compacted to shared memory
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        bool pr[4];
-        bool any = false;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { pr[q] = k_gt(KH(4 * g + q), KL(4 * g + q), Lh, 0u); any = any || pr[q]; }
-        if (__any_sync(kFull, any)) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const unsigned b = __ballot_sync(kFull, pr[q]);
-            if (pr[q]) { const int pos = cnt + __popc(b & lt_mask); if (pos < kCandMax) cand[pos] = make_uint2(KL(4 * g + q), KH(4 * g + q)); }
-            cnt += __popc(b);
-          }
-        }
-      }
-      __syncwarp();
+      const int cnt = gather_above(sk, __ballot_sync(kFull, mh >= Lh), Lh, 0u, cand, lane, lt_mask);
       if (cnt <= 32) {
         if (cnt == 0) { ans.hi = Lh; ans.lo = 0u; wmax = ans; }
         else {
@@ -304,10 +328,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
       __syncwarp();
     }
     if (!done) {
-      // exact lane maximum (low words among the lane's top high word), needed by both slower paths
+      // exact lane maximum: low words among this lane's own row entries that carry its top high word
       unsigned ml = 0u;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) if (KH(i) == mh) ml = max(ml, KL(i));
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const unsigned long long kv = sk[lane * kRowU64 + i];
+        if ((unsigned)(kv >> 32) == mh) ml = max(ml, (unsigned)kv);
+      }
       wmax = warp_max_k64(mh, ml);
       bool solved = false;
       if (k <= 32) {
@@ -315,53 +342,41 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
         unsigned sh = mh, sl = ml;
         warp_sort_desc_k64(sh, sl, lane);
         const unsigned Lh = __shfl_sync(kFull, sh, k - 1), Ll = __shfl_sync(kFull, sl, k - 1);
-        int cnt = 0;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool pr = k_gt(KH(i), KL(i), Lh, Ll);
-          const unsigned b = __ballot_sync(kFull, pr);
-          if (b) {
-            if (pr) { const int pos = cnt + __popc(b & lt_mask); if (pos < kCandMax) cand[pos] = make_uint2(KL(i), KH(i)); }
-            cnt += __popc(b);
-          }
-        }
-        __syncwarp();
+        const int cnt = gather_above(sk, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, cand, lane, lt_mask);
         if (cnt < k) { ans.hi = Lh; ans.lo = Ll; solved = true; }
         else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); solved = true; }
         __syncwarp();
       }
       if (!solved) {
-        // always-correct slow path: MSB-first bit search over the register-resident keys
+        // always-correct slow path: MSB-first bit search over the keys of this lane's row
         unsigned long long pref = 0ull;
-        int kk = k;
+        int kk2 = k;
 #pragma unroll 1
         for (int b = 63; b >= 0; --b) {
           const unsigned long long trial = pref | (1ull << b);
           const unsigned long long himask = ~((1ull << b) - 1ull);
-          const unsigned th = (unsigned)(trial >> 32), tl = (unsigned)trial, hh = (unsigned)(himask >> 32), hl = (unsigned)himask;
           unsigned c = 0;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) c += ((KH(i) & hh) == th && (KL(i) & hl) == tl) ? 1u : 0u;
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) c += ((sk[lane * kRowU64 + i] & himask) == trial) ? 1u : 0u;
           c = __reduce_add_sync(kFull, c);
-          if ((int)c >= kk) pref = trial; else kk -= (int)c;
+          if ((int)c >= kk2) pref = trial; else kk2 -= (int)c;
         }
         ans.hi = (unsigned)(pref >> 32);
         ans.lo = (unsigned)pref;
       }
     }
+    __syncwarp();                            // every lane is done with this window's rows before the next window overwrites them
 
     if (lane == 0) {
       const int64_t o = (int64_t)f * p.nw + w;
       p.out_min[o] = k64_to_f64(wmin);
       p.out_max[o] = k64_to_f64(wmax);
-      p.out_mean[o] = sum / (double)m;
+      p.out_mean[o] = (JF >= 0 || m == p.W) ? sum * p.inv_w : sum / (double)m;
       if (p.do_select) p.out_p99[o] = k64_to_f64(ans);
       p.out_nover[o] = nov;
       p.part[o] = ep;
     }
   }
-#undef KH
-#undef KL
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -595,12 +610,21 @@ extern "C" int32_t gpud_ring_counts(gpud_ring* r, int64_t* total, int64_t* count
 template <bool ALIGNED, int JF>
 static cudaError_t launch_one(gpud_ring* r, const WinParams& p, int64_t units) {
   // persistent grid: 2 CTAs of 8 warps per SM, a whole number of waves (148 SMs)
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 2));
-  k_window_reduce<ALIGNED, JF><<<grid, kWarpsPerBlock * 32, 0, r->stream>>>(p);
+  // 72 KB of dynamic shared memory per CTA (8 warps x (32 x 272 B key rows + candidate list)): opt in above 48 KB
+  cudaError_t e = cudaFuncSetAttribute(k_window_reduce<ALIGNED, JF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmemBytes);
+  if (e != cudaSuccess) return e;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 3));
+  k_window_reduce<ALIGNED, JF><<<grid, kWarpsPerBlock * 32, kBlockSmemBytes, r->stream>>>(p);
   return cudaGetLastError();
 }
 
 static int32_t launch_windows(gpud_ring* r, WinParams p) {
+  {
+    long long rr = ((long long)p.W * p.q_num + p.q_den - 1) / p.q_den;
+    rr = rr < 1 ? 1 : (rr > p.W ? p.W : rr);
+    p.k_full = p.W - (int)rr + 1;
+    p.inv_w = 1.0 / (double)p.W;
+  }
   p.n_list = 0;
   p.w_list[0] = p.w_list[1] = -1;
   p.w_skip[0] = p.w_skip[1] = -1;

@@ -10,6 +10,7 @@
  *   (components/accelerator/nvidia/xid/kmsg.go:22-43,202-268 ; sxid/kmsg.go:17-73) with the catalog lookups of
  *   xid/xid.go:74-117,2954-3305.  Pinned by tests/golden/ (tests/test_oracle_c.py).
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -122,4 +123,190 @@ void orc_windows_fields(const double* ring, int32_t F, int64_t n, int32_t W, con
                         int32_t threads, double* o_min, double* o_max, double* o_mean, double* o_ema, double* o_p99, uint32_t* o_nover) {
   orc_win_job j = {ring, n, (n + W - 1) / W, W, thr, alpha, q_num, q_den, o_min, o_max, o_mean, o_ema, o_p99, o_nover};
   orc_parallel_for(orc_win_one, &j, F, threads);
+}
+
+/* =====================================================================================================================
+ * Part 2: xid.Match / sxid.Match over the reference's verbatim regex strings (engine: regex_bt.c).
+ * ===================================================================================================================== */
+#include "regex_bt.h"
+
+#include <stdio.h>
+
+#include "../gpud_b200/csrc/catalog.h"
+#include "../gpud_b200/csrc/catalog_data.inc"   /* DATA ONLY: generated tables (tools/gen_catalog.py) */
+
+/* components/accelerator/nvidia/xid/kmsg.go:22,29,38,43 ; sxid/kmsg.go:17,20 — verbatim */
+static const char* RX[6] = {
+    "NVRM: Xid \\(((?:PCI:)?[0-9a-fA-F:]+)\\).*?: (\\d+),",
+    "NVRM: Xid \\(PCI:([0-9a-fA-F:]+)\\): (\\d+)(?:, pid=(\\d+), name=([^,]+))?, ([A-Z_]+(?:/[A-Z_]+)?)\\s+(Nonfatal|Fatal)\\s+(XC[01])\\s+(i\\d+)\\s+Link\\s+(-?\\d+)\\s+\\((0x[0-9a-fA-F]+)\\s+(0x[0-9a-fA-F]+)(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?",
+    "(?s)NVRM:\\s+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\\.0.*?fallen off the bus and is not responding to commands\\.",
+    "NVRM:\\s+GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\\.0:\\s+GPU has fallen off the bus\\.?",
+    "SXid.*?: (\\d+),",
+    "SXid \\((PCI:[0-9a-fA-F:\\.]+)\\)"};
+static orx_prog* PR[6];
+static pthread_once_t rx_once = PTHREAD_ONCE_INIT;
+static void rx_init(void) { for (int i = 0; i < 6; ++i) PR[i] = orx_compile(RX[i]); }
+int32_t orc_regex_ok(void) {
+  pthread_once(&rx_once, rx_init);
+  for (int i = 0; i < 6; ++i) if (!PR[i]) return 0;
+  return 1;
+}
+
+typedef struct {
+  int64_t line, offset;
+  int32_t kind, code, extended, sub_code, severity_fatal;
+  int64_t link;
+  uint32_t intrinfo, error_status;
+  char device[64];
+  char unit[64];
+} orc_hit;
+
+/* strconv.Atoi: 1 ok / 0 range or syntax error */
+static int go_atoi(const char* s, int n, long long* out) {
+  int i = 0, neg = 0;
+  if (n > 0 && (s[0] == '-' || s[0] == '+')) { neg = s[0] == '-'; i = 1; }
+  if (i >= n) return 0;
+  unsigned long long v = 0, lim = neg ? 0x8000000000000000ull : 0x7fffffffffffffffull;
+  for (; i < n; ++i) {
+    if (s[i] < '0' || s[i] > '9') return 0;
+    unsigned d = (unsigned)(s[i] - '0');
+    if (v > (lim - d) / 10ull) return 0;
+    v = v * 10ull + d;
+  }
+  *out = neg ? (long long)(0ull - v) : (long long)v;
+  return 1;
+}
+static int go_hex32(const char* s, int n, uint32_t* out) {   /* ParseUint("0x..", 0, 32) */
+  unsigned long long v = 0;
+  for (int i = 2; i < n; ++i) {
+    int c = s[i];
+    unsigned d = (c >= '0' && c <= '9') ? c - '0' : (c | 0x20) - 'a' + 10;
+    v = v * 16ull + d;
+    if (v > 0xffffffffull) return 0;
+  }
+  *out = (uint32_t)v;
+  return 1;
+}
+static int xid_known(long long code) {
+  for (int i = 0; i < GPUD_CAT_N_XID; ++i) if (GPUD_CAT_XID[i].code == code) return 1;
+  return 0;
+}
+static int sxid_known(long long code) {
+  for (int i = 0; i < GPUD_CAT_N_SXID; ++i) if (GPUD_CAT_SXID[i].sxid == code) return 1;
+  return 0;
+}
+static void cpy(char* dst, int cap, const char* pre, const char* s, int n) {
+  int k = 0;
+  for (; pre && pre[k] && k < cap - 1; ++k) dst[k] = pre[k];
+  for (int i = 0; i < n && k < cap - 1; ++i) dst[k++] = s[i];
+  dst[k] = 0;
+}
+
+/* xid.Match (kmsg.go:202-245).  Returns 1 and fills h on a hit. */
+int32_t orc_xid_match(const char* s, int32_t n, orc_hit* h) {
+  pthread_once(&rx_once, rx_init);
+  int c[40];
+  memset(h, 0, sizeof *h);
+  h->kind = 1;
+  if (orx_search(PR[1], s, n, c)) {   /* ExtractNVRMXidInfoExtended (kmsg.go:116-183) */
+    long long code, link;
+    uint32_t intr, es;
+    if (go_atoi(s + c[4], c[5] - c[4], &code) && go_hex32(s + c[20], c[21] - c[20], &intr) && go_hex32(s + c[22], c[23] - c[22], &es) &&
+        go_atoi(s + c[18], c[19] - c[18], &link) && xid_known(code)) {   /* detailFromNVLinkInfo needs the base code (xid.go:2955-2958) */
+      h->code = (int32_t)code; h->extended = 1; h->intrinfo = intr; h->error_status = es; h->link = link;
+      h->sub_code = (int32_t)((intr >> 20) & 0x3F);
+      h->severity_fatal = (c[13] - c[12]) == 5;   /* "Fatal" vs "Nonfatal" */
+      cpy(h->unit, 64, NULL, s + c[10], c[11] - c[10]);
+      cpy(h->device, 64, "PCI:", s + c[2], c[3] - c[2]);
+      return 1;
+    }
+  }
+  if (orx_search(PR[0], s, n, c)) {   /* ExtractNVRMXidInfo (kmsg.go:73-80) */
+    long long code;
+    if (go_atoi(s + c[4], c[5] - c[4], &code) && code != 0) {
+      if (!xid_known(code)) return 0;
+      h->code = (int32_t)code;
+      cpy(h->device, 64, NULL, s + c[2], c[3] - c[2]);
+      return 1;
+    }
+  }
+  int ok = orx_search(PR[3], s, n, c);   /* extractFallenOffBusXidInfo (kmsg.go:247-257): single-line first */
+  if (!ok) ok = orx_search(PR[2], s, n, c);
+  if (ok) {
+    if (!xid_known(79)) return 0;
+    h->code = 79;
+    int colons = 0;
+    for (int i = c[2]; i < c[3]; ++i) colons += s[i] == ':';
+    cpy(h->device, 64, colons == 1 ? "PCI:0000:" : "PCI:", s + c[2], c[3] - c[2]);   /* normalizePCIBDF (kmsg.go:259-268) */
+    return 1;
+  }
+  return 0;
+}
+
+/* sxid.Match (sxid/kmsg.go:58-73) */
+int32_t orc_sxid_match(const char* s, int32_t n, orc_hit* h) {
+  pthread_once(&rx_once, rx_init);
+  int c[8];
+  memset(h, 0, sizeof *h);
+  h->kind = 2;
+  if (!orx_search(PR[4], s, n, c)) return 0;
+  long long code;
+  if (!go_atoi(s + c[2], c[3] - c[2], &code) || code == 0 || !sxid_known(code)) return 0;
+  h->code = (int32_t)code;
+  if (orx_search(PR[5], s, n, c)) cpy(h->device, 64, NULL, s + c[2], c[3] - c[2]);
+  return 1;
+}
+
+/* The reference's buffer-scan form: split on '\n', Match each line (xid/kmsg_test.go:252-267), parallel over byte ranges
+ * cut at line boundaries.  Returns the number of hits (may exceed cap; only the first cap are stored, in line order). */
+typedef struct { const char* buf; int64_t b, e; orc_hit* hits; int64_t n, cap, lines; } orc_scan_part;
+static void orc_scan_one(void* a, int64_t idx) {
+  orc_scan_part* P = (orc_scan_part*)a + idx;
+  int64_t ls = P->b, line = 0;
+  for (int64_t i = P->b; i <= P->e; ++i) {
+    if (i == P->e || P->buf[i] == '\n') {
+      const int32_t n = (int32_t)(i - ls);
+      /* cheap prefilter: every pattern needs "NVRM:" or "SXid" (Go's regexp does the same literal-prefix skip) */
+      if (n >= 4 && (memmem(P->buf + ls, (size_t)n, "NVRM:", 5) || memmem(P->buf + ls, (size_t)n, "SXid", 4))) {
+        orc_hit h;
+        if (orc_xid_match(P->buf + ls, n, &h)) { h.line = line; h.offset = ls; if (P->n < P->cap) P->hits[P->n] = h; ++P->n; }
+        if (orc_sxid_match(P->buf + ls, n, &h)) { h.line = line; h.offset = ls; if (P->n < P->cap) P->hits[P->n] = h; ++P->n; }
+      }
+      ls = i + 1;
+      if (i < P->e) ++line;
+    }
+  }
+  P->lines = line;   /* newlines inside [b, e) */
+}
+
+int64_t orc_scan_lines(const char* buf, int64_t len, orc_hit* hits, int64_t cap, int64_t* n_lines, int32_t threads) {
+  if (threads <= 0) threads = orc_max_threads();
+  int parts = threads * 4;
+  if (parts > 1024) parts = 1024;
+  if ((int64_t)parts > len / 4096 + 1) parts = (int)(len / 4096 + 1);
+  orc_scan_part* P = (orc_scan_part*)calloc((size_t)parts, sizeof(orc_scan_part));
+  int64_t b = 0;
+  for (int i = 0; i < parts; ++i) {
+    int64_t e = (i == parts - 1) ? len : (len * (i + 1)) / parts;
+    if (e < b) e = b;
+    while (e < len && buf[e] != '\n') ++e;       /* cut at a newline: the part is [b, e], the newline at e belongs to it */
+    if (e < len && i != parts - 1) ++e;
+    P[i].buf = buf; P[i].b = b; P[i].e = e; P[i].cap = cap;
+    P[i].hits = (orc_hit*)malloc((size_t)(cap > 0 ? cap : 1) * sizeof(orc_hit));
+    b = e;
+  }
+  orc_parallel_for(orc_scan_one, P, parts, threads);
+  int64_t total = 0, line0 = 0;
+  for (int i = 0; i < parts; ++i) {
+    for (int64_t k = 0; k < P[i].n && k < P[i].cap; ++k) {
+      if (total < cap) { hits[total] = P[i].hits[k]; hits[total].line += line0; }
+      ++total;
+    }
+    if (P[i].n > P[i].cap) total += P[i].n - P[i].cap;
+    line0 += P[i].lines;
+    free(P[i].hits);
+  }
+  if (n_lines) *n_lines = line0 + 1;
+  free(P);
+  return total;
 }
