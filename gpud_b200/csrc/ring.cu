@@ -146,9 +146,12 @@ __device__ __forceinline__ K64 select_from_candidates(const uint2* s, int cnt, i
   const uint2 c = mine ? s[lane] : make_uint2(0u, 0u);      // .x = lo, .y = hi
   int rank = 0;
 #pragma unroll 1
-  for (int j = 0; j < cnt; ++j) {
-    const uint2 o = s[j];                                    // broadcast LDS.64
-    rank += k_gt(o.y, o.x, c.y, c.x) ? 1 : 0;
+  for (int j = 0; j < cnt; j += 4) {                         // the list is zero-padded to a multiple of 4; a zero never outranks
+    const uint4 o01 = *reinterpret_cast<const uint4*>(s + j), o23 = *reinterpret_cast<const uint4*>(s + j + 2);   // broadcast LDS.128
+    rank += k_gt(o01.y, o01.x, c.y, c.x) ? 1 : 0;
+    rank += k_gt(o01.w, o01.z, c.y, c.x) ? 1 : 0;
+    rank += k_gt(o23.y, o23.x, c.y, c.x) ? 1 : 0;
+    rank += k_gt(o23.w, o23.z, c.y, c.x) ? 1 : 0;
   }
   *mx = warp_max_k64(mine ? c.y : 0u, mine ? c.x : 0u);
   const bool in = mine && rank < k;
@@ -167,37 +170,73 @@ __device__ __forceinline__ K64 select_from_candidates(const uint2* s, int cnt, i
 // (m == W), so the pair loop is straight-line code.  JF = -1: everything is decided at run time (any W, partial windows).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowU64 = 34;                                   // 32 keys + 2 pad -> 272-byte rows
-constexpr int kWarpSmemBytes = 32 * kRowU64 * 8 + kCandMax * 8;
+constexpr int kWarpSmemBytes = 32 * kRowU64 * 8 + (kCandMax + 4) * 8 + 32 + 16;   // key rows, candidates (+pad), row list, counter
 constexpr int kBlockSmemBytes = kWarpsPerBlock * kWarpSmemBytes;
 
 __device__ __forceinline__ int elem_index(int row, int col) { return 64 * (col >> 1) + 2 * row + (col & 1); }   // chronological t
 
-// compact the keys of the flagged rows that are > (Lh, Ll) into cand[]; returns how many there are (may exceed kCandMax)
-__device__ __forceinline__ int gather_above(const unsigned long long* sk, unsigned rows, unsigned Lh, unsigned Ll, uint2* cand, int lane,
-                                            unsigned lt_mask) {
-  int cnt = 0;
-  while (rows) {
-    const int row = __ffs(rows) - 1;
-    rows &= rows - 1;
-    const unsigned long long kv = sk[row * kRowU64 + lane];
-    const unsigned h = (unsigned)(kv >> 32), l = (unsigned)kv;
-    const bool pr = k_gt(h, l, Lh, Ll);
-    const unsigned b = __ballot_sync(kFull, pr);
-    if (pr) { const int pos = cnt + __popc(b & lt_mask); if (pos < kCandMax) cand[pos] = make_uint2(l, h); }
-    cnt += __popc(b);
+// Append the keys of the flagged rows that are > (Lh, Ll) to cand[] (any order).  The flagged row ids are first packed
+// into cand's tail; then one LDS per row gives every lane one key of that row, and the few lanes that hold a hit claim a
+// slot with a shared-memory atomic.  Returns the number of hits (may exceed kCandMax; only the first kCandMax are stored).
+__device__ __forceinline__ int gather_above(const unsigned long long* sk, unsigned rows, unsigned Lh, unsigned Ll, uint2* cand, int* s_cnt,
+                                            int lane, unsigned lt_mask) {
+  const int n_rows = __popc(rows);
+  unsigned char* row_list = reinterpret_cast<unsigned char*>(cand + kCandMax + 4);   // 32 bytes after the candidate slots
+  if ((rows >> lane) & 1u) row_list[__popc(rows & lt_mask)] = (unsigned char)lane;
+  if (lane == 0) *s_cnt = 0;
+  __syncwarp();
+#pragma unroll 1
+  for (int i = 0; i < n_rows; i += 4) {                      // four rows per trip: their LDS are independent and overlap
+    const unsigned r4 = *reinterpret_cast<const unsigned*>(row_list + i);
+    unsigned long long kv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) kv[q] = (i + q < n_rows) ? sk[((r4 >> (8 * q)) & 31u) * kRowU64 + lane] : 0ull;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned h = (unsigned)(kv[q] >> 32), l = (unsigned)kv[q];
+      if (h >= Lh && k_gt(h, l, Lh, Ll)) {                   // a zero (absent row) is never above the bound
+        const int pos = atomicAdd(s_cnt, 1);
+        if (pos < kCandMax) cand[pos] = make_uint2(l, h);
+      }
+    }
   }
+  __syncwarp();
+  const int cnt = *s_cnt;
+  // zero-pad to a multiple of 4 so the rank loop can run unrolled without a tail
+  if (lane < 4 && cnt <= kCandMax) cand[cnt + lane] = make_uint2(0u, 0u);
   __syncwarp();
   return cnt;
 }
 
+// k-th largest (1-based, k <= 32) of one 32-bit value per lane, counting multiplicity, through shared memory:
+// rank_i = #{j : v_j > v_i};  the answer is the smallest value whose rank is < k.  One STS, eight broadcast LDS.128 and
+// 32 independent compares per lane: the same instruction count as a 32-bit bitonic sort without its 15-deep shuffle chain.
+__device__ __forceinline__ unsigned warp_kth_largest_smem(unsigned v, int k, unsigned* s32, int lane) {
+  s32[lane] = v;
+  __syncwarp();
+  int rank = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint4 o = reinterpret_cast<const uint4*>(s32)[q];
+    rank += (o.x > v) + (o.y > v) + (o.z > v) + (o.w > v);
+  }
+  __syncwarp();
+  return __reduce_min_sync(kFull, rank < k ? v : 0xffffffffu);
+}
+
+struct WinUnit { int f, w, m; int64_t p0; };
+
 template <bool ALIGNED, int JF>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_window_reduce(const WinParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const WinParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)warp * kWarpSmemBytes);   // [32][kRowU64]
-  uint2* cand = reinterpret_cast<uint2*>(smem_raw + (size_t)warp * kWarpSmemBytes + 32 * kRowU64 * 8);
-  ulonglong2* my_row2 = reinterpret_cast<ulonglong2*>(sk + lane * kRowU64);
+  unsigned char* wbase = smem_raw + (size_t)warp * kWarpSmemBytes;
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(wbase);                        // [32][kRowU64] key rows
+  uint2* cand = reinterpret_cast<uint2*>(wbase + 32 * kRowU64 * 8);                             // [kCandMax + 4]
+  int* s_cnt = reinterpret_cast<int*>(wbase + 32 * kRowU64 * 8 + (kCandMax + 4) * 8 + 32);
+  unsigned* s32 = reinterpret_cast<unsigned*>(cand);                                            // 128 B scratch, reused before the gather
+  uint4* my_row4 = reinterpret_cast<uint4*>(sk + lane * kRowU64);   // one uint4 = two keys {lo0, hi0, lo1, hi1}
   const int64_t n_units = p.n_list > 0 ? (int64_t)p.F * p.n_list : (int64_t)p.F * p.nw;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -205,87 +244,110 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_wind
   const int per_f = p.n_list > 0 ? p.n_list : p.nw;
   const int64_t stride = (int64_t)gridDim.x * kWarpsPerBlock;
   const int df = (int)(stride / per_f), ds = (int)(stride - (int64_t)df * per_f);
-  const int64_t u0 = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  int f = (int)(u0 / per_f), slot = (int)(u0 - (int64_t)f * per_f);
-  for (int64_t u = u0; u < n_units; u += stride, f += df, slot += ds) {
-    if (slot >= per_f) { slot -= per_f; ++f; }
-    const int w = p.n_list > 0 ? p.w_list[slot] : slot;
-    if (p.n_list == 0 && (w == p.w_skip[0] || w == p.w_skip[1])) continue;
-    const int64_t c0 = (int64_t)w * p.W;
-    const int m = JF >= 0 ? p.W : (int)min((int64_t)p.W, p.count - c0);
-    int64_t p0 = p.start + c0;
-    if (p0 >= p.cap) p0 -= p.cap;
-    const double* __restrict__ base = p.ring + (int64_t)f * p.cap;
-    const int J = (m + 63) >> 6;                     // register pairs that hold at least one valid element
-    const int Jfull = JF >= 0 ? JF : (m >> 6);       // register pairs in which every lane's two elements are valid
-    const double thr = __ldg(p.thr + f);
+  int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  int uf = (int)(u / per_f), uslot = (int)(u - (int64_t)uf * per_f);
 
-    // ---- issue every load of the window before touching any of them (8 KB in flight per warp) ----
-    double2 v[16];
+  double2 v[16];                 // the window in flight: loaded for the NEXT unit while the current one is post-processed
+  double thr_next = 0.0;
+  // fetch the next non-skipped unit of this warp (if any) and issue all of its loads
+  auto fetch = [&](WinUnit& q) -> bool {
+    for (;;) {
+      if (u >= n_units) return false;
+      q.f = uf;
+      q.w = p.n_list > 0 ? p.w_list[uslot] : uslot;
+      u += stride; uf += df; uslot += ds;
+      if (uslot >= per_f) { uslot -= per_f; ++uf; }
+      if (p.n_list > 0 || (q.w != p.w_skip[0] && q.w != p.w_skip[1])) break;
+    }
+    const int64_t c0 = (int64_t)q.w * p.W;
+    q.m = JF >= 0 ? p.W : (int)min((int64_t)p.W, p.count - c0);
+    q.p0 = p.start + c0;
+    if (q.p0 >= p.cap) q.p0 -= p.cap;
+    const double* __restrict__ base = p.ring + (int64_t)q.f * p.cap;
+    thr_next = __ldg(p.thr + q.f);
     if (ALIGNED) {
-      const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + p0) + lane;
+      const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + q.p0) + lane;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         if (JF >= 0 && j < JF) { v[j] = __ldcs(b2 + 32 * j); continue; }
         v[j] = make_double2(0.0, 0.0);
-        if (64 * j + 2 * lane < m) v[j] = __ldcs(b2 + 32 * j);   // element t0+1 == m is masked below (the ring has slack)
+        if (64 * j + 2 * lane < q.m) v[j] = __ldcs(b2 + 32 * j);   // element t0+1 == m is masked in pass 1 (the ring has slack)
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int t0 = 64 * j + 2 * lane;
         v[j] = make_double2(0.0, 0.0);
-        if (t0 < m) { int64_t a = p0 + t0; if (a >= p.cap) a -= p.cap; v[j].x = __ldcs(base + a); }
-        if (t0 + 1 < m) { int64_t a = p0 + t0 + 1; if (a >= p.cap) a -= p.cap; v[j].y = __ldcs(base + a); }
+        if (t0 < q.m) { int64_t a = q.p0 + t0; if (a >= p.cap) a -= p.cap; v[j].x = __ldcs(base + a); }
+        if (t0 + 1 < q.m) { int64_t a = q.p0 + t0 + 1; if (a >= p.cap) a -= p.cap; v[j].y = __ldcs(base + a); }
       }
     }
+    return true;
+  };
 
-    // ---- pass 1 ----
+  WinUnit cur, nxt;
+  bool have = fetch(cur);
+  while (have) {
+    const int f = cur.f, w = cur.w, m = cur.m;
+    const int J = (m + 63) >> 6;                     // register pairs that hold at least one valid element
+    const int Jfull = JF >= 0 ? JF : (m >> 6);       // register pairs in which every lane's two elements are valid
+    const double thr = thr_next;
+
+    // ---- pass 1: consume the loaded registers once ----
     double sum0 = 0.0, sum1 = 0.0, es0 = 0.0, es1 = 0.0;
     unsigned nov = 0;
     unsigned mh = 0u, nh = 0xffffffffu;    // lane max / min of the key high words
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      ulonglong2 kk;
+      uint4 kk;                              // {lo0, hi0, lo1, hi1}: totalOrder keys of the pair, 3 integer ops per element
       if (JF >= 0 ? (j < JF) : (j < Jfull)) {  // whole register pair valid (compile-time when JF >= 0, else warp-uniform)
         const double x0 = v[j].x, x1 = v[j].y;
-        kk.x = gpud_f64_key((unsigned long long)__double_as_longlong(x0));
-        kk.y = gpud_f64_key((unsigned long long)__double_as_longlong(x1));
+        const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
+        const unsigned m0 = (unsigned)(h0 >> 31), m1 = (unsigned)(h1 >> 31);
+        kk.x = (unsigned)__double2loint(x0) ^ m0; kk.y = (unsigned)h0 ^ (m0 | 0x80000000u);
+        kk.z = (unsigned)__double2loint(x1) ^ m1; kk.w = (unsigned)h1 ^ (m1 | 0x80000000u);
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (x0 > thr) ++nov;
         if (x1 > thr) ++nov;
-        const unsigned a0 = (unsigned)(kk.x >> 32), a1 = (unsigned)(kk.y >> 32);
-        mh = max(mh, max(a0, a1));
-        nh = min(nh, min(a0, a1));
+        mh = max(mh, max(kk.y, kk.w));
+        nh = min(nh, min(kk.y, kk.w));
       } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
         const int t0 = 64 * j + 2 * lane;
         const bool q0 = t0 < m, q1 = t0 + 1 < m;
         const double x0 = q0 ? v[j].x : 0.0, x1 = q1 ? v[j].y : 0.0;
-        kk.x = q0 ? gpud_f64_key((unsigned long long)__double_as_longlong(x0)) : 0ull;
-        kk.y = q1 ? gpud_f64_key((unsigned long long)__double_as_longlong(x1)) : 0ull;
+        const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
+        const unsigned m0 = (unsigned)(h0 >> 31), m1 = (unsigned)(h1 >> 31);
+        kk.x = q0 ? (unsigned)__double2loint(x0) ^ m0 : 0u; kk.y = q0 ? (unsigned)h0 ^ (m0 | 0x80000000u) : 0u;
+        kk.z = q1 ? (unsigned)__double2loint(x1) ^ m1 : 0u; kk.w = q1 ? (unsigned)h1 ^ (m1 | 0x80000000u) : 0u;
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (q0 && x0 > thr) ++nov;
         if (q1 && x1 > thr) ++nov;
-        const unsigned a0 = (unsigned)(kk.x >> 32), a1 = (unsigned)(kk.y >> 32);
-        mh = max(mh, max(a0, a1));
-        if (q0) nh = min(nh, a0);
-        if (q1) nh = min(nh, a1);
+        mh = max(mh, max(kk.y, kk.w));
+        if (q0) nh = min(nh, kk.y);
+        if (q1) nh = min(nh, kk.w);
       } else {
-        kk.x = kk.y = 0ull;                  // padding: the smallest key
+        kk = make_uint4(0u, 0u, 0u, 0u);     // padding: the smallest key
       }
-      my_row2[j] = kk;                       // STS.128, conflict-free (272-byte row stride)
+      my_row4[j] = kk;                       // STS.128, conflict-free (272-byte row stride)
     }
     __syncwarp();
 
-    // ---- sums ----
-    const double sum = warp_sum_f64(sum0 + sum1);
-    nov = __reduce_add_sync(kFull, nov);
-    // EMA partial: sum_t alpha (1-alpha)^(m-1-t) x_t with t = 64 j + 2 lane + h; Horner above ran over j < J with q64
+    // ---- the registers are free again: put the next window's loads in flight under the post-processing below ----
+    have = fetch(nxt);
+
+    // ---- sums (the two shuffle trees are interleaved) ----
     const int eb = m - 1 - 64 * (J - 1) - 2 * lane;          // exponent of this lane's h=0 element in pair J-1, in [-62, 63]
-    double ep = es0 * __ldg(p.pw + (eb + 63)) + es1 * __ldg(p.pw + (eb - 1 + 63));
-    ep = warp_sum_f64(ep) * p.alpha;
+    double ep = es0 * __ldg(p.pw + (eb + 63)) + es1 * __ldg(p.pw + (eb - 1 + 63));   // EMA partial, weights alpha (1-alpha)^(m-1-t)
+    double sum = sum0 + sum1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(kFull, sum, o);
+      ep += __shfl_xor_sync(kFull, ep, o);
+    }
+    ep *= p.alpha;
+    nov = __reduce_add_sync(kFull, nov);
 
     // ---- exact minimum: global min of the high words, then the low words of the rows that hold it ----
     K64 wmin;
@@ -315,8 +377,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_wind
     if (k <= 32) {
       // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L', so the answer is too.
       // Only rows whose maximum reaches L' can hold keys above it.
-      const unsigned Lh = warp_kth_largest_u32(mh, k, lane);
-      const int cnt = gather_above(sk, __ballot_sync(kFull, mh >= Lh), Lh, 0u, cand, lane, lt_mask);
+      const unsigned Lh = warp_kth_largest_smem(mh, k, s32, lane);
+      const int cnt = gather_above(sk, __ballot_sync(kFull, mh >= Lh), Lh, 0u, cand, s_cnt, lane, lt_mask);
       if (cnt <= 32) {
         if (cnt == 0) { ans.hi = Lh; ans.lo = 0u; wmax = ans; }
         else {
@@ -342,7 +404,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_wind
         unsigned sh = mh, sl = ml;
         warp_sort_desc_k64(sh, sl, lane);
         const unsigned Lh = __shfl_sync(kFull, sh, k - 1), Ll = __shfl_sync(kFull, sl, k - 1);
-        const int cnt = gather_above(sk, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, cand, lane, lt_mask);
+        const int cnt = gather_above(sk, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, cand, s_cnt, lane, lt_mask);
         if (cnt < k) { ans.hi = Lh; ans.lo = Ll; solved = true; }
         else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); solved = true; }
         __syncwarp();
@@ -365,7 +427,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_wind
         ans.lo = (unsigned)pref;
       }
     }
-    __syncwarp();                            // every lane is done with this window's rows before the next window overwrites them
+    __syncwarp();                            // every lane is done with this window's rows before pass 1 of the next overwrites them
 
     if (lane == 0) {
       const int64_t o = (int64_t)f * p.nw + w;
@@ -376,6 +438,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (JF >= 0) ? 3 : 2) k_wind
       p.out_nover[o] = nov;
       p.part[o] = ep;
     }
+    cur = nxt;
   }
 }
 
@@ -613,7 +676,7 @@ static cudaError_t launch_one(gpud_ring* r, const WinParams& p, int64_t units) {
   // 72 KB of dynamic shared memory per CTA (8 warps x (32 x 272 B key rows + candidate list)): opt in above 48 KB
   cudaError_t e = cudaFuncSetAttribute(k_window_reduce<ALIGNED, JF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmemBytes);
   if (e != cudaSuccess) return e;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 3));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 2));
   k_window_reduce<ALIGNED, JF><<<grid, kWarpsPerBlock * 32, kBlockSmemBytes, r->stream>>>(p);
   return cudaGetLastError();
 }
