@@ -62,65 +62,95 @@ __device__ unsigned long long nvrm_family(const ScanBuf& b, int64_t a, int64_t e
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5a filter
+// K5a filter.  Every thread owns 16 bytes (one 128-bit load) plus a 4-byte look-ahead from its right neighbour, and
+// tests all 16 four-byte windows against the two anchor words "NVRM" / "SXid" exactly (funnel shifts + chained integer
+// compares): no false positives, so the verification path below only runs where an anchor really starts.  Separators
+// are counted with an exact zero-byte bit trick.  About 5 integer instructions per byte, no shared memory.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void filter_rare(const ScanBuf& b, int64_t off, const uint4& w, unsigned mv, int mode, unsigned& sep,
-                                            unsigned long long* cands, unsigned long long* n_cand, unsigned long long cand_cap) {
-  const unsigned words[4] = {w.x, w.y, w.z, w.w};
-  for (int k = 0; k < 16; ++k) {
-    const int c = (words[k >> 2] >> ((k & 3) * 8)) & 0xff;
-    const int64_t i = off + k;
-    if (i >= b.len) break;
-    if (mode == GPUD_SCAN_RAW_KMSG && c == '\n') {
-      if (ld8(b, i + 1) == ' ') --sep;            // continuation line of the same record: not a separator
-    }
-    if (!mv) continue;
-    unsigned long long fam = 0;
-    if (c == 'V') {
-      if (ld8(b, i - 1) == 'N' && ld8(b, i + 1) == 'R' && ld8(b, i + 2) == 'M' && ld8(b, i + 3) == ':') fam = nvrm_family(b, i - 1, b.len);
-    } else if (c == 'X') {
-      if (ld8(b, i - 1) == 'S' && ld8(b, i + 1) == 'i' && ld8(b, i + 2) == 'd') fam = kFamS;
-    }
-    if (fam) {
-      const unsigned long long slot = atomicAdd(n_cand, 1ull);
-      if (slot < cand_cap) cands[slot] = (unsigned long long)(i - 1) | (fam << 60);
-    }
+constexpr unsigned kNVRM = 0x4d52564eu;   // "NVRM" little-endian
+constexpr unsigned kSXid = 0x64695853u;   // "SXid"
+
+// bit 7 of every byte of the result is set exactly where the byte of x is zero
+__device__ __forceinline__ unsigned zero_bytes(unsigned x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
+
+// Verify one anchor position and append it to the candidate list.  The seven bytes after "NVRM" are fetched with
+// independent loads (one round trip) before any of them is compared.
+__device__ __noinline__ void filter_verify(const ScanBuf& b, int64_t a, bool is_nvrm, unsigned long long* cands, unsigned long long* n_cand,
+                                           unsigned long long cand_cap) {
+  unsigned long long fam = kFamS;
+  if (is_nvrm) {
+    int c[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) c[k] = ld8(b, a + 4 + k);
+    if (c[0] != ':') return;
+    if (c[1] == ' ' && c[2] == 'X' && c[3] == 'i' && c[4] == 'd' && c[5] == ' ' && c[6] == '(') fam = kFamX;
+    else if (!is_ws(c[1])) return;
+    else fam = nvrm_family(b, a, b.len);
+    if (!fam) return;
   }
+  const unsigned long long slot = atomicAdd(n_cand, 1ull);
+  if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << 60);
 }
 
-__global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, int mode, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
+template <int MODE>
+__global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
                                                       unsigned long long* n_cand, unsigned long long cand_cap) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t n_chunks = (b.len + kChunk - 1) / kChunk;
   const bool aligned = ((uintptr_t)b.p & 15) == 0;
-  // each warp takes 4 consecutive chunks per step: four independent 128-bit loads in flight per lane
+  // each warp takes 4 consecutive chunks (2 KB) per step: four independent 128-bit loads in flight per lane
   for (int64_t c0 = warp_g * 4; c0 < n_chunks; c0 += n_warps * 4) {
-    uint4 w[4];
+    uint4 q[4];
+    unsigned tail = 0;                        // first word after the 2 KB run (lane 31 of the last chunk needs it)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t off = (c0 + u) * kChunk + lane * 16;
-      w[u] = make_uint4(0, 0, 0, 0);
+      q[u] = make_uint4(0, 0, 0, 0);
       if (aligned && off + 16 <= b.len) {
-        w[u] = __ldcs(reinterpret_cast<const uint4*>(b.p + off));
+        q[u] = __ldcs(reinterpret_cast<const uint4*>(b.p + off));
       } else if (off < b.len) {                  // ragged tail / unaligned caller buffer: bytewise
         unsigned t[4] = {0, 0, 0, 0};
         for (int k = 0; k < 16 && off + k < b.len; ++k) t[k >> 2] |= (unsigned)__ldg(b.p + off + k) << ((k & 3) * 8);
-        w[u] = make_uint4(t[0], t[1], t[2], t[3]);
+        q[u] = make_uint4(t[0], t[1], t[2], t[3]);
       }
+    }
+    if (lane == 31) {
+      const int64_t off = (c0 + 4) * kChunk;
+      for (int k = 0; k < 4 && off + k < b.len; ++k) tail |= (unsigned)__ldg(b.p + off + k) << (k * 8);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t chunk = c0 + u;
       if (chunk >= n_chunks) break;              // warp-uniform
-      const int64_t off = chunk * kChunk + lane * 16;
-      const unsigned nl = (__vcmpeq4(w[u].x, 0x0a0a0a0au) & 0x01010101u) + (__vcmpeq4(w[u].y, 0x0a0a0a0au) & 0x01010101u) +
-                          (__vcmpeq4(w[u].z, 0x0a0a0a0au) & 0x01010101u) + (__vcmpeq4(w[u].w, 0x0a0a0a0au) & 0x01010101u);
-      unsigned sep = (nl * 0x01010101u) >> 24;   // horizontal byte sum (each byte <= 4)
-      const unsigned mv = (__vcmpeq4(w[u].x, 0x56565656u) | __vcmpeq4(w[u].x, 0x58585858u)) | (__vcmpeq4(w[u].y, 0x56565656u) | __vcmpeq4(w[u].y, 0x58585858u)) |
-                          (__vcmpeq4(w[u].z, 0x56565656u) | __vcmpeq4(w[u].z, 0x58585858u)) | (__vcmpeq4(w[u].w, 0x56565656u) | __vcmpeq4(w[u].w, 0x58585858u));
-      if (mv || (mode == GPUD_SCAN_RAW_KMSG && nl)) filter_rare(b, off, w[u], mv, mode, sep, cands, n_cand, cand_cap);
+      // look-ahead word: right neighbour's first word; lane 31 takes lane 0 of the next chunk (or the tail word)
+      unsigned nx = __shfl_down_sync(kFull, q[u].x, 1);
+      const unsigned nx_chunk = __shfl_sync(kFull, u < 3 ? q[u < 3 ? u + 1 : 3].x : 0u, 0);
+      if (lane == 31) nx = u < 3 ? nx_chunk : tail;
+      const unsigned w[5] = {q[u].x, q[u].y, q[u].z, q[u].w, nx};
+      bool hit = false;
+      unsigned sepbits = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned x1 = __funnelshift_r(w[k], w[k + 1], 8), x2 = __funnelshift_r(w[k], w[k + 1], 16), x3 = __funnelshift_r(w[k], w[k + 1], 24);
+        hit = hit || w[k] == kNVRM || w[k] == kSXid || x1 == kNVRM || x1 == kSXid || x2 == kNVRM || x2 == kSXid || x3 == kNVRM || x3 == kSXid;
+        unsigned z = zero_bytes(w[k] ^ 0x0a0a0a0au);                           // '\n'
+        if (MODE == GPUD_SCAN_RAW_KMSG) z &= ~zero_bytes(x1 ^ 0x20202020u);     // ... not followed by ' ' (continuation line)
+        sepbits |= z >> (k + 4);                                                // bit 7 of each byte -> bit 3-k: four words share one POPC
+      }
+      unsigned sep = (unsigned)__popc(sepbits);
+      if (MODE == GPUD_SCAN_RAW_KMSG) {
+        // a '\n' in the last byte of the buffer has no follower: it is a separator (x1's byte there is 0, not ' ') - nothing to fix
+      }
+      if (hit) {                                   // unrolled: two compares per position, the call only where an anchor word sits
+        const int64_t off = chunk * kChunk + lane * 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const unsigned x = (k & 3) ? __funnelshift_r(w[k >> 2], w[(k >> 2) + 1], 8 * (k & 3)) : w[k >> 2];
+          if (x == kNVRM || x == kSXid) filter_verify(b, off + k, x == kNVRM, cands, n_cand, cand_cap);
+        }
+      }
       sep = __reduce_add_sync(kFull, sep);
       if (lane == 0) chunk_sep[chunk] = sep;
     }
@@ -128,16 +158,39 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, int mode, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5b exclusive scan of chunk separator counts (single block; n is len/512)
+// K5b exclusive scan of the per-chunk separator counts, two levels, coalesced: every 1024-entry tile is scanned by one
+// CTA (tile-local exclusive prefix + tile total), then one CTA scans the tile totals.  The match kernel adds the two.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan_prefix(const uint32_t* __restrict__ in, unsigned long long* __restrict__ out, int64_t n,
-                                                       unsigned long long* total) {
+__global__ void __launch_bounds__(1024) k_scan_prefix_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ local, int64_t n,
+                                                             unsigned long long* __restrict__ tile_total) {
+  __shared__ unsigned s_w[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 1024 + t;
+  const unsigned v = i < n ? in[i] : 0u;
+  unsigned x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(kFull, x, o); if (lane >= o) x += y; }
+  if (lane == 31) s_w[wid] = x;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned y = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned z = __shfl_up_sync(kFull, y, o); if (lane >= o) y += z; }
+    s_w[lane] = y;
+  }
+  __syncthreads();
+  const unsigned incl = x + (wid ? s_w[wid - 1] : 0u);
+  if (i < n) local[i] = incl - v;
+  if (t == 1023) tile_total[blockIdx.x] = incl;
+}
+__global__ void __launch_bounds__(1024) k_scan_prefix_top(unsigned long long* __restrict__ tile_total, int64_t n_tiles, unsigned long long* total) {
+  // n_tiles = len / 512 KiB: a few hundred for 100 MB; serial chunks per thread + one block scan
   __shared__ unsigned long long s[1024];
   const int t = threadIdx.x;
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t b = t * per, e = min(n, b + per);
+  const int64_t per = (n_tiles + 1023) / 1024;
+  const int64_t b0 = t * per, e0 = min(n_tiles, b0 + per);
   unsigned long long acc = 0;
-  for (int64_t i = b; i < e; ++i) acc += in[i];
+  for (int64_t i = b0; i < e0; ++i) acc += tile_total[i];
   s[t] = acc;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {
@@ -147,10 +200,7 @@ __global__ void __launch_bounds__(1024) k_scan_prefix(const uint32_t* __restrict
     __syncthreads();
   }
   unsigned long long run = s[t] - acc;
-  for (int64_t i = b; i < e; ++i) {
-    out[i] = run;
-    run += in[i];
-  }
+  for (int64_t i = b0; i < e0; ++i) { const unsigned long long v = tile_total[i]; tile_total[i] = run; run += v; }
   if (t == 1023) *total = s[1023];
 }
 
@@ -583,9 +633,36 @@ __device__ __forceinline__ bool is_sep(const ScanBuf& b, int64_t i, int mode) {
   return mode == GPUD_SCAN_LINES || ld8(b, i + 1) != ' ';
 }
 
+// separators in [from, to): bytes until the address is 4-byte aligned, then whole words with the zero-byte trick
+__device__ unsigned count_seps(const ScanBuf& b, int64_t from, int64_t to, int mode) {
+  unsigned n = 0;
+  int64_t i = from;
+  while (i < to && (((uintptr_t)(b.p + i)) & 3)) { n += is_sep(b, i, mode) ? 1 : 0; ++i; }
+  if (i + 4 <= to) {
+    unsigned w = __ldg(reinterpret_cast<const unsigned*>(b.p + i));
+    for (; i + 4 <= to; i += 4) {
+      const unsigned nxt = (i + 8 <= b.len) ? __ldg(reinterpret_cast<const unsigned*>(b.p + i + 4)) : 0u;
+      unsigned z = zero_bytes(w ^ 0x0a0a0a0au);
+      if (mode == GPUD_SCAN_RAW_KMSG) {
+        unsigned x1 = __funnelshift_r(w, nxt, 8);
+        if (i + 8 > b.len) {                                   // ragged end: fetch the follower bytes one by one
+          x1 = w >> 8;
+          if (i + 4 < b.len) x1 |= (unsigned)__ldg(b.p + i + 4) << 24;
+        }
+        z &= ~zero_bytes(x1 ^ 0x20202020u);
+      }
+      n += __popc(z);
+      w = nxt;
+      if (i + 8 > b.len) { i += 4; break; }
+    }
+  }
+  for (; i < to; ++i) n += is_sep(b, i, mode) ? 1 : 0;
+  return n;
+}
+
 __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const unsigned long long* __restrict__ cands,
                                                      const unsigned long long* __restrict__ n_cand, unsigned long long cand_cap,
-                                                     const unsigned long long* __restrict__ chunk_prefix, const gpud_tables* __restrict__ T,
+                                                     const uint32_t* __restrict__ chunk_local, const unsigned long long* __restrict__ tile_base, const gpud_tables* __restrict__ T,
                                                      gpud_xid_hit* hits, unsigned long long hit_cap, unsigned long long* n_hits) {
   const unsigned long long n = min(*n_cand, cand_cap);
   for (unsigned long long ci = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (unsigned long long)gridDim.x * blockDim.x) {
@@ -631,12 +708,13 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
     if (fam != kFamS && !nvrm_family(b, a, ue)) continue;   // the filter judged the context against the buffer end, not the unit end
     gpud_xid_hit h;
     memset(&h, 0, sizeof h);
-    const bool ok = (fam == kFamS) ? sxid_match_unit(b, ms, ue, T, &h) : xid_match_unit(b, ms, ue, T, &h);
+    // every pattern starts with this family's anchor literal and `a` is the unit's first such anchor: start there
+    const bool ok = (fam == kFamS) ? sxid_match_unit(b, a, ue, T, &h) : xid_match_unit(b, a, ue, T, &h);
     if (!ok) continue;
     // unit number = separators before `us`
     const int64_t chunk = us / kChunk;
-    unsigned long long idx = chunk_prefix[chunk];
-    for (int64_t i = chunk * kChunk; i < us; ++i) idx += is_sep(b, i, mode) ? 1 : 0;
+    unsigned long long idx = tile_base[chunk >> 10] + chunk_local[chunk];
+    idx += count_seps(b, chunk * kChunk, us, mode);
     h.unit_index = (int64_t)idx;
     h.unit_offset = us;
     h.kmsg_priority = (int32_t)k_prio;
@@ -669,19 +747,21 @@ struct gpud_scan_state {
   int dev = 0;
   gpud_tables* d_tables = nullptr;
   uint8_t* d_buf = nullptr; size_t buf_cap = 0;
-  uint32_t* d_chunk_sep = nullptr; unsigned long long* d_chunk_prefix = nullptr; size_t chunk_cap = 0;
+  uint32_t* d_chunk_sep = nullptr; uint32_t* d_chunk_local = nullptr; unsigned long long* d_tile_base = nullptr; size_t chunk_cap = 0;
   unsigned long long* d_cands = nullptr; size_t cand_cap = 0;
   gpud_xid_hit* d_hits = nullptr; size_t hit_cap = 0;
   unsigned long long* d_counters = nullptr;   // [0] n_cand [1] n_hits [2] n_sep
   unsigned long long* h_counters = nullptr;   // pinned
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around filter / prefix / match of the last scan
 };
 
 void gpud_scan_state_free(gpud_scan_state* s) {
   if (!s) return;
-  cudaFree(s->d_tables); cudaFree(s->d_buf); cudaFree(s->d_chunk_sep); cudaFree(s->d_chunk_prefix); cudaFree(s->d_cands);
+  cudaFree(s->d_tables); cudaFree(s->d_buf); cudaFree(s->d_chunk_sep); cudaFree(s->d_chunk_local); cudaFree(s->d_tile_base); cudaFree(s->d_cands);
   cudaFree(s->d_hits); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
+  for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -699,6 +779,7 @@ static int32_t scan_state_get(gpud_ctx* ctx, int dev, gpud_scan_state** out) {
     GPUD_CUDA(ctx, cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
     GPUD_CUDA(ctx, cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long)));
     GPUD_CUDA(ctx, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) GPUD_CUDA(ctx, cudaEventCreate(&e));
   }
   *out = ctx->scan[slot];
   return GPUD_OK;
@@ -718,10 +799,13 @@ static cudaError_t grow(T** p, size_t* cap, size_t need) {
 static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_buf, int64_t len, int32_t mode, int64_t hit_cap_req,
                            cudaStream_t st) {
   const int64_t n_chunks = std::max<int64_t>(1, (len + kChunk - 1) / kChunk);
+  const int64_t n_tiles = (n_chunks + 1023) / 1024;
   size_t cc = s->chunk_cap;
   GPUD_CUDA(ctx, grow(&s->d_chunk_sep, &cc, (size_t)n_chunks));
   cc = s->chunk_cap;
-  GPUD_CUDA(ctx, grow(&s->d_chunk_prefix, &cc, (size_t)n_chunks));
+  GPUD_CUDA(ctx, grow(&s->d_chunk_local, &cc, (size_t)n_chunks));
+  cc = s->chunk_cap;
+  GPUD_CUDA(ctx, grow(&s->d_tile_base, &cc, (size_t)n_chunks / 1024 + 2));
   s->chunk_cap = cc;
   GPUD_CUDA(ctx, grow(&s->d_cands, &s->cand_cap, (size_t)(len / 4 + 1024)));
   GPUD_CUDA(ctx, grow(&s->d_hits, &s->hit_cap, (size_t)std::max<int64_t>(hit_cap_req, 1024)));
@@ -731,13 +815,22 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   }
   ScanBuf b{d_buf, len};
   const int grid_f = (int)std::min<int64_t>((n_chunks + 31) / 32, (int64_t)ctx->sm_count * 8);   // 8 warps x 4 chunks per block step
-  k_scan_filter<<<std::max(grid_f, 1), 256, 0, st>>>(b, mode, s->d_chunk_sep, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap);
+  cudaEventRecord(s->ev[0], st);
+  if (mode == GPUD_SCAN_LINES)
+    k_scan_filter<GPUD_SCAN_LINES><<<std::max(grid_f, 1), 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap);
+  else
+    k_scan_filter<GPUD_SCAN_RAW_KMSG><<<std::max(grid_f, 1), 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
-  k_scan_prefix<<<1, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_prefix, n_chunks, s->d_counters + 2);
+  cudaEventRecord(s->ev[1], st);
+  k_scan_prefix_tiles<<<(unsigned)n_tiles, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_local, n_chunks, s->d_tile_base);
   GPUD_CUDA(ctx, cudaGetLastError());
-  k_scan_match<<<ctx->sm_count * 4, 128, 0, st>>>(b, mode, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, s->d_chunk_prefix,
+  k_scan_prefix_top<<<1, 1024, 0, st>>>(s->d_tile_base, n_tiles, s->d_counters + 2);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  cudaEventRecord(s->ev[2], st);
+  k_scan_match<<<ctx->sm_count * 4, 128, 0, st>>>(b, mode, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, s->d_chunk_local, s->d_tile_base,
                                                    s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
   GPUD_CUDA(ctx, cudaGetLastError());
+  cudaEventRecord(s->ev[3], st);
   GPUD_CUDA(ctx, cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   return GPUD_OK;
 }
@@ -802,5 +895,15 @@ extern "C" int32_t gpud_xid_classify(gpud_ctx* ctx, int32_t dev, gpud_xid_hit* h
   GPUD_CUDA(ctx, cudaGetLastError());
   GPUD_CUDA(ctx, cudaMemcpyAsync(hits, s->d_hits, (size_t)n * sizeof(gpud_xid_hit), cudaMemcpyDeviceToHost, s->stream));
   GPUD_CUDA(ctx, cudaStreamSynchronize(s->stream));
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_kmsg_scan_kernel_ms(gpud_ctx* ctx, int32_t dev, float* ms3) {
+  if (!ctx || !ms3) return GPUD_E_INVALID;
+  gpud_scan_state* s;
+  int32_t rc = scan_state_get(ctx, dev, &s);
+  if (rc) return rc;
+  GPUD_CUDA(ctx, cudaEventSynchronize(s->ev[3]));
+  for (int i = 0; i < 3; ++i) GPUD_CUDA(ctx, cudaEventElapsedTime(&ms3[i], s->ev[i], s->ev[i + 1]));
   return GPUD_OK;
 }

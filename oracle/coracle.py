@@ -37,3 +37,34 @@ def windows_fields(ring: np.ndarray, W: int, thr: np.ndarray, alpha: float = 0.0
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+class OrcHit(C.Structure):
+    _fields_ = [("line", C.c_int64), ("offset", C.c_int64), ("kind", C.c_int32), ("code", C.c_int32), ("extended", C.c_int32),
+                ("sub_code", C.c_int32), ("severity_fatal", C.c_int32), ("link", C.c_int64), ("intrinfo", C.c_uint32),
+                ("error_status", C.c_uint32), ("device", C.c_char * 64), ("unit", C.c_char * 64)]
+
+
+def xid_match(line: bytes):
+    L = lib()
+    assert L.orc_regex_ok() == 1
+    h = OrcHit()
+    L.orc_xid_match.restype = C.c_int32
+    return h if L.orc_xid_match(line, C.c_int32(len(line)), C.byref(h)) else None
+
+
+def sxid_match(line: bytes):
+    L = lib()
+    h = OrcHit()
+    L.orc_sxid_match.restype = C.c_int32
+    return h if L.orc_sxid_match(line, C.c_int32(len(line)), C.byref(h)) else None
+
+
+def scan_lines(buf: bytes, threads: int = 0, cap: int = 1 << 20):
+    """Returns (hits list of OrcHit, n_lines) for the reference's split-on-newline scan form."""
+    L = lib()
+    L.orc_scan_lines.restype = C.c_int64
+    hits = (OrcHit * cap)()
+    nl = C.c_int64()
+    n = L.orc_scan_lines(buf, C.c_int64(len(buf)), hits, C.c_int64(cap), C.byref(nl), C.c_int32(threads))
+    return [hits[i] for i in range(min(n, cap))], nl.value

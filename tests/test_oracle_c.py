@@ -1,0 +1,93 @@
+"""Pin the C restatement (oracle/oracle.c + oracle/regex_bt.c: own backtracking engine over the reference's verbatim regex
+strings) against the reference's golden vectors and against the independent Python `re` restatement."""
+import numpy as np
+import pytest
+
+import synth
+from oracle import coracle as CO
+from oracle import pyoracle as O
+
+
+def test_engine_compiles_all_six_patterns():
+    assert CO.lib().orc_regex_ok() == 1
+
+
+def _same(c, p):
+    if p is None:
+        assert c is None
+        return
+    assert c is not None and c.code == p.xid and c.device.decode() == p.device
+    assert bool(c.extended) == (p.info is not None)
+    if p.info is not None:
+        assert (c.sub_code, c.intrinfo, c.error_status, c.link, c.unit.decode()) == \
+               (p.info.sub_code, p.info.intrinfo, p.info.error_status, p.info.link, p.info.unit)
+        assert bool(c.severity_fatal) == (p.info.severity == "Fatal")
+
+
+def test_golden_match_vectors(golden):            # xid/kmsg_test.go:105-246, :289
+    g = golden("xid_kmsg.json")
+    for r in g["match"]["rows"] + g["unknown_code"]["rows"]:
+        c = CO.xid_match(r["input"].encode())
+        if r.get("expectNil"):
+            assert c is None, r["name"]
+        else:
+            assert c is not None and c.code == r["expectedXid"] and c.device.decode() == r["expectedDevice"], r["name"]
+
+
+def test_golden_extended_vectors(golden):         # xid/kmsg_extended_test.go:15-326
+    for r in golden("xid_kmsg.json")["extended"]["rows"]:
+        c = CO.xid_match(r["logLine"].encode())
+        assert c is not None and c.extended == 1, r["name"]
+        assert c.code == r["expectedXid"] and c.device.decode() == "PCI:" + r["expectedDeviceUUID"]
+        assert (c.sub_code, c.unit.decode(), c.link, c.intrinfo, c.error_status) == \
+               (r["expectedSubCode"], r["expectedSubCodeName"], r["expectedLink"], r["expectedIntrinfo"], r["expectedErrorStatus"])
+
+
+def test_golden_sxid_vectors(golden):             # sxid/kmsg_test.go:102-170
+    for r in golden("sxid_kmsg.json")["match"]["rows"]:
+        c = CO.sxid_match(r["input"].encode())
+        if r.get("expectNil"):
+            assert c is None, r["name"]
+        else:
+            assert c.code == r["expectedSXid"] and c.device.decode() == r["expectedDevice"], r["name"]
+
+
+def test_dmesg_fixture(golden):                   # xid/kmsg_test.go:248-287
+    buf = "\n".join(golden("xid_kmsg.json")["dmesg_xid_119"]["lines"]).encode()
+    hits, n_lines = CO.scan_lines(buf, threads=3)
+    assert [(h.code, h.device.decode()) for h in hits] == [(119, "PCI:0000:9b:00")] * 5
+    assert n_lines == buf.count(b"\n") + 1
+
+
+def test_c_engine_equals_python_re_on_every_line():
+    for line in synth.hit_lines() + synth.EDGE_LINES:
+        b = line.encode()
+        _same(CO.xid_match(b), O.xid_match(b))
+        s = O.sxid_match(b)
+        c = CO.sxid_match(b)
+        assert (c is None) == (s is None)
+        if s:
+            assert (c.code, c.device.decode()) == (s["sxid"], s["device"])
+
+
+def test_c_scan_equals_python_scan_on_synthetic_buffer():
+    buf = synth.dmesg_buffer(1 << 20, hit_every=100)
+    hits, n_lines = CO.scan_lines(buf, threads=4)
+    want = O.scan_lines(buf)
+    assert n_lines == buf.count(b"\n") + 1
+    assert [(h.line, h.offset, h.kind, h.code, h.device.decode()) for h in hits] == \
+           [(w["line"], w["offset"], w["kind"], w["code"], w["device"]) for w in want]
+    assert len(want) > 80
+
+
+def test_windows_c_equals_python():
+    x = synth.gauge_stream(5, 2777, seed=21)
+    thr = synth.thresholds_for(x)
+    for W, a, qn, qd in ((1000, 0.0, 0, 0), (7, 0.3, 50, 100), (1024, 0.0, 999, 1000), (1, 0.0, 1, 1)):
+        c = CO.windows_fields(np.ascontiguousarray(x.T), W, thr, a, qn, qd, threads=2)
+        for f in range(x.shape[1]):
+            w = O.window_aggregates(x[:, f], W, thr[f], a, qn or 99, qd or 100)
+            for k in ("min", "max", "p99"):
+                assert np.array_equal(c[k][f].view(np.uint64), w[k].view(np.uint64)), (W, k, f)
+            assert np.array_equal(c["n_over"][f].astype(np.uint64), w["n_over"])
+            assert np.allclose(c["mean"][f], w["mean"], rtol=1e-12, atol=0) and np.allclose(c["ema"][f], w["ema"], rtol=1e-9, atol=0)

@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""Driver for the kmsg-scan measurements (BASELINE configs[2]: 100 MB synthetic dmesg buffer) and its ncu captures."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import torch
+
+import gpud_b200 as g
+import synth
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+cpu = len(sys.argv) > 2 and sys.argv[2] == "cpu"
+unit = synth.dmesg_buffer(4 << 20, hit_every=1000)
+buf = unit * 25                                             # 100 MiB of lines; every tile starts on a line boundary
+ctx = g.Context([0])
+d = torch.frombuffer(bytearray(buf), dtype=torch.uint8).cuda()
+torch.cuda.synchronize()
+ms = []
+for _ in range(reps):
+    hits, n_units = ctx.kmsg_scan_device(d.data_ptr(), len(buf), cap=1 << 20)
+    ms.append(ctx.scan_kernel_ms())
+ms = np.array(ms[1:] if reps > 1 else ms)
+filt, pre, mat = ms.mean(axis=0)
+t0 = time.perf_counter()
+hits2, _ = ctx.kmsg_scan(buf, cap=1 << 20)
+e2e = time.perf_counter() - t0
+out = {"bytes": len(buf), "lines": n_units, "hits": len(hits), "filter_ms": float(filt), "prefix_ms": float(pre), "match_ms": float(mat),
+       "device_total_ms": float(filt + pre + mat), "filter_GBps": len(buf) / filt / 1e6, "total_GBps": len(buf) / (filt + pre + mat) / 1e6,
+       "e2e_host_ms": e2e * 1e3, "e2e_GBps": len(buf) / e2e / 1e9}
+if cpu:
+    from oracle import coracle
+    t0 = time.perf_counter()
+    ch, nl = coracle.scan_lines(buf)
+    dt = time.perf_counter() - t0
+    assert [(h.line, h.kind, h.code) for h in ch] == [(h.unit_index, h.kind, h.code) for h in hits]
+    out.update(cpu_threads=coracle.max_threads(), cpu_ms=dt * 1e3, cpu_GBps=len(buf) / dt / 1e9, cpu_hits_equal=True)
+print(json.dumps(out))
