@@ -1,0 +1,399 @@
+// host_component.cpp — see host_component.h.  Every function cites the reference code it mirrors.
+#include "host_component.h"
+
+#include <string.h>
+
+#include <algorithm>
+
+namespace gpud {
+
+const char* health_string(Health h) {            // api/v1/types.go:20-25
+  switch (h) {
+    case Health::Healthy: return "Healthy";
+    case Health::Degraded: return "Degraded";
+    case Health::Unhealthy: return "Unhealthy";
+    case Health::Initializing: return "Initializing";
+  }
+  return "Healthy";
+}
+const char* event_type_string(int32_t t) {       // api/v1/types.go:222-244
+  static const char* n[] = {"Unknown", "Info", "Warning", "Critical", "Fatal"};
+  return (t >= 0 && t <= 4) ? n[t] : "Unknown";
+}
+const char* repair_action_string(int32_t a) {    // api/v1/types.go:183-203
+  switch (a) {
+    case GPUD_ACT_IGNORE_NO_ACTION_REQUIRED: return "IGNORE_NO_ACTION_REQUIRED";
+    case GPUD_ACT_REBOOT_SYSTEM: return "REBOOT_SYSTEM";
+    case GPUD_ACT_HARDWARE_INSPECTION: return "HARDWARE_INSPECTION";
+    case GPUD_ACT_CHECK_USER_APP_AND_GPU: return "CHECK_USER_APP_AND_GPU";
+  }
+  return "";
+}
+
+static void jstr(std::string& o, const std::string& s) {
+  o.push_back('"');
+  for (unsigned char c : s) {
+    if (c == '"') o += "\\\"";
+    else if (c == '\\') o += "\\\\";
+    else if (c == '\n') o += "\\n";
+    else if (c < 0x20 || c == '<' || c == '>' || c == '&') { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o.push_back((char)c);
+  }
+  o.push_back('"');
+}
+
+std::string HealthState::to_json() const {       // api/v1/types.go:50-94 (omitempty fields)
+  std::string o = "{";
+  bool first = true;
+  auto key = [&](const char* k) { if (!first) o += ","; first = false; o += "\""; o += k; o += "\":"; };
+  if (!component.empty()) { key("component"); jstr(o, component); }
+  if (!name.empty()) { key("name"); jstr(o, name); }
+  key("health"); jstr(o, health_string(health));
+  if (!reason.empty()) { key("reason"); jstr(o, reason); }
+  if (!error.empty()) { key("error"); jstr(o, error); }
+  if (has_actions) {
+    key("suggested_actions");
+    o += "{\"repair_actions\":[";
+    for (size_t i = 0; i < actions.repair_actions.size(); ++i) { if (i) o += ","; jstr(o, repair_action_string(actions.repair_actions[i])); }
+    o += "]}";
+  }
+  o += "}";
+  return o;
+}
+
+// ---- pkg/kmsg ----
+static bool go_atoi64(const std::string& s, int64_t* out) {   // strconv.Atoi / ParseInt(s, 10, 64)
+  size_t i = 0;
+  bool neg = false;
+  if (!s.empty() && (s[0] == '+' || s[0] == '-')) { neg = s[0] == '-'; i = 1; }
+  if (i >= s.size()) return false;
+  unsigned long long v = 0;
+  const unsigned long long lim = neg ? 0x8000000000000000ull : 0x7fffffffffffffffull;
+  for (; i < s.size(); ++i) {
+    if (s[i] < '0' || s[i] > '9') return false;
+    const unsigned d = (unsigned)(s[i] - '0');
+    if (v > (lim - d) / 10ull) return false;
+    v = v * 10ull + d;
+  }
+  *out = neg ? (int64_t)(0ull - v) : (int64_t)v;
+  return true;
+}
+
+bool parse_kmsg_line(const std::string& line, KmsgMessage* out, std::string* err) {   // watcher.go:292-332
+  const size_t semi = line.find(';');
+  if (semi == std::string::npos) { if (err) *err = "invalid kmsg; must contain a ';'"; return false; }
+  const std::string meta = line.substr(0, semi);
+  std::vector<std::string> parts;
+  size_t b = 0;
+  for (;;) {
+    const size_t c = meta.find(',', b);
+    parts.push_back(meta.substr(b, c == std::string::npos ? std::string::npos : c - b));
+    if (c == std::string::npos) break;
+    b = c + 1;
+  }
+  if (parts.size() < 3) { if (err) *err = "invalid kmsg: must contain at least 3 ',' separated pieces at the start"; return false; }
+  int64_t prio, seq, usec;
+  if (!go_atoi64(parts[0], &prio)) { if (err) *err = "could not parse priority"; return false; }
+  if (!go_atoi64(parts[1], &seq)) { if (err) *err = "could not parse sequence number"; return false; }
+  if (!go_atoi64(parts[2], &usec)) { if (err) *err = "could not parse timestamp"; return false; }
+  out->priority = (int)prio; out->sequence = seq; out->usec_since_boot = usec;
+  out->message = line.substr(semi + 1);            // unmodified: continuation lines and extra ';' stay (watcher_test.go:113-133)
+  return true;
+}
+
+std::string dedup_key(int64_t unix_seconds, const std::string& message, int truncate_seconds) {   // deduper.go:63-74
+  if (truncate_seconds <= 0) truncate_seconds = 60;
+  const int64_t t = unix_seconds - (unix_seconds % truncate_seconds);
+  return std::to_string(t) + "-" + message;
+}
+
+int Deduper::add(int64_t now_unix, int64_t msg_unix, const std::string& message) {      // deduper.go:111-125
+  const std::string k = dedup_key(msg_unix, message, trunc_);
+  auto it = cache_.find(k);
+  int freq = 1;
+  if (it != cache_.end() && it->second.expires > now_unix) freq = it->second.count + 1;
+  cache_[k] = Entry{freq, now_unix + ttl_};
+  return freq;
+}
+
+// ---- eventstore ----
+static bool same_event(const Event& a, const Event& b) {       // findEvent's WHERE + compareEvent (database.go:278-324, 459-469)
+  if (a.time_unix != b.time_unix || a.name != b.name || a.type != b.type) return false;
+  if (!b.message.empty() && a.message != b.message) return false;
+  return a.extra_info == b.extra_info;
+}
+bool EventBucket::insert(const Event& ev) { events_.push_back(ev); return true; }
+const Event* EventBucket::find(const Event& ev) const {
+  for (const Event& e : events_) if (same_event(e, ev)) return &e;
+  return nullptr;
+}
+std::vector<Event> EventBucket::get(int64_t since_unix) const {
+  std::vector<Event> out;
+  for (const Event& e : events_) if (e.time_unix >= since_unix) out.push_back(e);
+  std::stable_sort(out.begin(), out.end(), [](const Event& a, const Event& b) { return a.time_unix > b.time_unix; });
+  return out;
+}
+int EventBucket::purge(int64_t before_unix) {
+  const size_t n0 = events_.size();
+  events_.erase(std::remove_if(events_.begin(), events_.end(), [&](const Event& e) { return e.time_unix < before_unix; }), events_.end());
+  return (int)(n0 - events_.size());
+}
+
+// ---- health evolution ----
+EvolveResult evolve_healthy_state(const std::vector<XidEventView>& ev, int reboot_threshold) {   // health_state.go:57-128
+  EvolveResult r;
+  int last_health = 0;
+  std::map<uint64_t, int> reboot_map;
+  for (auto it = ev.rbegin(); it != ev.rend(); ++it) {          // oldest -> newest
+    if (it->name == "error_xid") {
+      int cur = 0;
+      if (it->type == "Critical") cur = 1;
+      else if (it->type == "Fatal") cur = 2;
+      if (cur < last_health) continue;
+      last_health = cur;
+      r.has_xid = true;
+      r.xid = it->xid;
+      if (it->has_actions && !it->actions.empty()) {
+        std::vector<int32_t> acts = it->actions;
+        if (acts[0] == GPUD_ACT_REBOOT_SYSTEM) {
+          auto f = reboot_map.find(it->xid);
+          if (f == reboot_map.end()) reboot_map[it->xid] = 0;
+          else if (f->second >= reboot_threshold) acts[0] = GPUD_ACT_HARDWARE_INSPECTION;
+        }
+        acts.resize(1);
+        r.has_actions = true;
+        r.actions = acts;
+      }
+    } else if (it->name == "reboot") {
+      if (r.has_actions && !r.actions.empty() && (r.actions[0] == GPUD_ACT_REBOOT_SYSTEM || r.actions[0] == GPUD_ACT_CHECK_USER_APP_AND_GPU)) {
+        last_health = 0;
+        r.has_actions = false;
+        r.actions.clear();
+        r.has_xid = false;
+        r.xid = 0;
+      }
+      for (auto& kv : reboot_map) kv.second += 1;
+    }
+  }
+  r.health = last_health == 2 ? Health::Unhealthy : (last_health == 1 ? Health::Degraded : Health::Healthy);
+  return r;
+}
+
+std::vector<Event> trim_events_after_set_healthy(const std::vector<Event>& e) {   // component.go:630-642
+  for (size_t i = 0; i < e.size(); ++i)
+    if (e[i].name == "SetHealthy") return std::vector<Event>(e.begin(), e.begin() + i);
+  return e;
+}
+std::vector<Event> merge_events(const std::vector<Event>& a, const std::vector<Event>& b) {   // component.go:614-628
+  std::vector<Event> r(a);
+  r.insert(r.end(), b.begin(), b.end());
+  std::stable_sort(r.begin(), r.end(), [](const Event& x, const Event& y) { return x.time_unix > y.time_unix; });
+  return r;
+}
+
+// ---- the component ----
+XidComponent::XidComponent(gpud_ctx* ctx, int32_t dev, bool row_remap, int reboot_threshold)
+    : ctx_(ctx), dev_(dev), row_remap_(row_remap), reboot_threshold_(reboot_threshold) {
+  cur_.name = "error_xid";                         // StateNameErrorXid, component.go:39
+  cur_.component = kName;
+  cur_.health = Health::Healthy;
+  cur_.reason = "XIDComponent is healthy";
+}
+void XidComponent::AddRebootEvent(int64_t t) {
+  Event e;
+  e.time_unix = t;
+  e.name = "reboot";
+  std::lock_guard<std::mutex> g(mu_);
+  reboots_.insert(e);
+}
+int32_t XidComponent::Start() {
+  std::lock_guard<std::mutex> g(mu_);
+  update_state();
+  return 0;
+}
+
+static bool keep_hit(const gpud_xid_hit& h, bool row_remap) {
+  // Xid 63/64 are left to the remapped-rows component when the product supports row remapping (component.go:290, 484)
+  return !(h.kind == GPUD_KIND_XID && row_remap && (h.code == 63 || h.code == 64));
+}
+
+CheckResult XidComponent::Check() {               // component.go:255-311
+  CheckResult cr;
+  cr.component = kName;
+  std::vector<gpud_xid_hit> hits(4096);
+  int64_t n_hits = 0, n_units = 0;
+  for (;;) {
+    const int32_t rc = gpud_kmsg_scan(ctx_, dev_, reinterpret_cast<const uint8_t*>(buf_.data()), (int64_t)buf_.size(),
+                                      raw_ ? GPUD_SCAN_RAW_KMSG : GPUD_SCAN_LINES, hits.data(), (int64_t)hits.size(), &n_hits, &n_units);
+    if (rc == GPUD_E_CAPACITY && n_hits > (int64_t)hits.size()) { hits.resize((size_t)n_hits); continue; }
+    if (rc != GPUD_OK) {
+      char msg[512] = {0};
+      gpud_last_error(ctx_, msg, sizeof msg);
+      cr.health = Health::Unhealthy;              // errors are embedded in the result, Check never throws (types.go:48-53)
+      cr.summary = "failed to read kmsg";
+      HealthState s = cur_;
+      s.health = Health::Unhealthy; s.reason = cr.summary; s.error = msg;
+      cr.states.push_back(s);
+      return cr;
+    }
+    break;
+  }
+  for (int64_t i = 0; i < n_hits; ++i)
+    if (hits[i].kind == GPUD_KIND_XID && keep_hit(hits[i], row_remap_)) cr.found.push_back(hits[i]);
+  cr.summary = "matched " + std::to_string(cr.found.size()) + " xid errors from " + std::to_string(n_units) + " kmsg(s)";
+  cr.health = Health::Healthy;
+  for (const auto& h : cr.found)
+    if (h.event_type == GPUD_EVENT_CRITICAL || h.event_type == GPUD_EVENT_FATAL) { cr.health = Health::Unhealthy; break; }
+  HealthState s;
+  s.name = "error_xid"; s.component = kName; s.health = cr.health; s.reason = cr.summary;
+  cr.states.push_back(s);
+  cr.text = cr.found.empty() ? "no xid error found" : cr.summary;
+  std::lock_guard<std::mutex> g(mu_);
+  checked_ = true;
+  return cr;
+}
+
+int32_t XidComponent::IngestHits(const std::vector<gpud_xid_hit>& hits, int64_t fallback_unix) {   // component.go:468-577
+  std::lock_guard<std::mutex> g(mu_);
+  int inserted = 0;
+  for (const auto& h : hits) {
+    if (h.kind != GPUD_KIND_XID || !keep_hit(h, row_remap_)) continue;
+    const int64_t t = raw_ ? boot_unix_ + h.kmsg_usec / 1000000 : fallback_unix;
+    char payload[4096];
+    if (gpud_hit_detail_json(&h, t, payload, sizeof payload) != GPUD_OK) continue;
+    Event ev;
+    ev.time_unix = t;
+    ev.name = "error_xid";
+    ev.type = event_type_string(h.event_type);
+    ev.extra_info["device_uuid"] = h.device;
+    ev.extra_info["data"] = payload;
+    if (bucket_.find(ev)) continue;                // "find the same event, skip inserting it"
+    bucket_.insert(ev);
+    ++inserted;
+  }
+  if (inserted) update_state();
+  return inserted;
+}
+
+void XidComponent::update_state() {                // component.go:581-611
+  std::vector<Event> local = trim_events_after_set_healthy(bucket_.get(0));
+  std::vector<Event> all = merge_events(reboots_.get(0), local);
+  std::vector<XidEventView> views;
+  for (const Event& e : all) {
+    XidEventView v;
+    v.name = e.name;
+    v.type = e.type;
+    auto it = e.extra_info.find("data");
+    if (it != e.extra_info.end()) {
+      // the payload is our own rendering: pull xid and the first-listed actions back out
+      const std::string& d = it->second;
+      const size_t px = d.find("\"xid\":");
+      if (px != std::string::npos) v.xid = strtoull(d.c_str() + px + 6, nullptr, 10);
+      size_t pa = d.find("\"repair_actions\":[");
+      if (pa != std::string::npos) {
+        v.has_actions = true;
+        pa += 18;
+        while (pa < d.size() && d[pa] != ']') {
+          if (d[pa] == '"') {
+            const size_t e2 = d.find('"', pa + 1);
+            const std::string a = d.substr(pa + 1, e2 - pa - 1);
+            for (int id = 1; id <= 4; ++id) if (a == repair_action_string(id)) v.actions.push_back(id);
+            pa = e2 + 1;
+          } else ++pa;
+        }
+      }
+    }
+    views.push_back(v);
+  }
+  const EvolveResult r = evolve_healthy_state(views, reboot_threshold_);
+  cur_.health = r.health;
+  cur_.has_actions = r.has_actions;
+  cur_.actions.repair_actions = r.actions;
+  cur_.reason = r.has_xid ? ("XID " + std::to_string(r.xid) + " detected") : "XIDComponent is healthy";
+}
+
+std::vector<HealthState> XidComponent::LastHealthStates() {     // types.go:55-58
+  std::lock_guard<std::mutex> g(mu_);
+  return {cur_};
+}
+std::vector<Event> XidComponent::Events(int64_t since) {
+  std::lock_guard<std::mutex> g(mu_);
+  return bucket_.get(since);
+}
+int32_t XidComponent::SetHealthy(int64_t now_unix) {            // set_healthy.go:14-35
+  std::lock_guard<std::mutex> g(mu_);
+  Event e;
+  e.time_unix = now_unix;
+  e.name = "SetHealthy";
+  bucket_.insert(e);
+  update_state();
+  return 0;
+}
+
+}  // namespace gpud
+
+// ---- flat C entry points so the host mirror is testable through ctypes (not part of gpud_b200.h) ----
+extern "C" {
+
+int32_t gpudh_parse_kmsg_line(const char* line, int32_t* prio, int64_t* seq, int64_t* usec, char* msg, int32_t cap) {
+  gpud::KmsgMessage m;
+  std::string err;
+  if (!gpud::parse_kmsg_line(line, &m, &err)) return -1;
+  *prio = m.priority; *seq = m.sequence; *usec = m.usec_since_boot;
+  snprintf(msg, (size_t)cap, "%s", m.message.c_str());
+  return 0;
+}
+int32_t gpudh_dedup_key(int64_t unix_s, const char* msg, char* out, int32_t cap) {
+  snprintf(out, (size_t)cap, "%s", gpud::dedup_key(unix_s, msg).c_str());
+  return 0;
+}
+void* gpudh_deduper_new(int64_t ttl) { return new gpud::Deduper(ttl); }
+int32_t gpudh_deduper_add(void* d, int64_t now, int64_t t, const char* msg) { return static_cast<gpud::Deduper*>(d)->add(now, t, msg); }
+void gpudh_deduper_free(void* d) { delete static_cast<gpud::Deduper*>(d); }
+
+// events: n records of {kind 0 xid / 1 reboot / 2 SetHealthy(ignored here), event_type, xid, n_actions(-1 nil), actions[4]} newest first
+typedef struct { int32_t kind, event_type; uint64_t xid; int32_t n_actions; int32_t actions[4]; } gpudh_event;
+int32_t gpudh_evolve(const gpudh_event* ev, int32_t n, int32_t reboot_threshold, int32_t* health, int32_t* action, uint64_t* xid) {
+  std::vector<gpud::XidEventView> v;
+  for (int i = 0; i < n; ++i) {
+    gpud::XidEventView e;
+    e.name = ev[i].kind == 0 ? "error_xid" : (ev[i].kind == 1 ? "reboot" : "SetHealthy");
+    e.type = gpud::event_type_string(ev[i].event_type);
+    e.xid = ev[i].xid;
+    e.has_actions = ev[i].n_actions >= 0;
+    for (int k = 0; k < ev[i].n_actions && k < 4; ++k) e.actions.push_back(ev[i].actions[k]);
+    v.push_back(e);
+  }
+  const gpud::EvolveResult r = gpud::evolve_healthy_state(v, reboot_threshold);
+  *health = (int32_t)r.health;
+  *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
+  *xid = r.has_xid ? r.xid : 0;
+  return 0;
+}
+
+void* gpudh_xid_component_new(gpud_ctx* ctx, int32_t dev, int32_t row_remap, int32_t reboot_threshold) {
+  return new gpud::XidComponent(ctx, dev, row_remap != 0, reboot_threshold);
+}
+void gpudh_xid_component_free(void* c) { delete static_cast<gpud::XidComponent*>(c); }
+void gpudh_xid_component_set_source(void* c, const char* buf, int64_t len, int32_t raw, int64_t boot_unix) {
+  static_cast<gpud::XidComponent*>(c)->SetKmsgSource(std::string(buf, (size_t)len), raw != 0, boot_unix);
+}
+// Check(): returns the number of found errors, health (0/1/2) and the summary string
+int32_t gpudh_xid_component_check(void* c, int32_t* health, char* summary, int32_t cap, int32_t ingest, int64_t now_unix) {
+  auto* x = static_cast<gpud::XidComponent*>(c);
+  gpud::CheckResult cr = x->Check();
+  *health = (int32_t)cr.health;
+  snprintf(summary, (size_t)cap, "%s", cr.summary.c_str());
+  if (ingest) x->IngestHits(cr.found, now_unix);
+  return (int32_t)cr.found.size();
+}
+int32_t gpudh_xid_component_state_json(void* c, char* out, int32_t cap) {
+  auto s = static_cast<gpud::XidComponent*>(c)->LastHealthStates();
+  snprintf(out, (size_t)cap, "%s", s[0].to_json().c_str());
+  return 0;
+}
+int32_t gpudh_xid_component_reboot(void* c, int64_t t) { static_cast<gpud::XidComponent*>(c)->AddRebootEvent(t); static_cast<gpud::XidComponent*>(c)->Start(); return 0; }
+int32_t gpudh_xid_component_set_healthy(void* c, int64_t t) { return static_cast<gpud::XidComponent*>(c)->SetHealthy(t); }
+int32_t gpudh_xid_component_n_events(void* c) { return (int32_t)static_cast<gpud::XidComponent*>(c)->Events(0).size(); }
+const char* gpudh_xid_component_name(void) { return gpud::XidComponent::kName; }
+}

@@ -339,3 +339,36 @@ def test_fabric_pack_and_verdict(ctx):
         want = OF.verdict(gpus, at_least)
         for k, val in want.items():
             assert v[k] == val, (name, k, v[k], val)
+
+
+# ------------------------------------------------------------------------------------------------ host-side component mirror
+def test_xid_component_check_and_state(ctx):
+    """C++ mirror of the xid component (csrc/host_component.cpp): Check() scans on the GPU (xid/component.go:255-311), streaming
+    ingestion + evolveHealthyState (component.go:468-611, health_state.go:57-128), reboot clears, SetHealthy trims."""
+    import json
+    L = g.lib()
+    L.gpudh_xid_component_new.restype = C.c_void_p
+    G = synth.golden("xid_kmsg.json")
+    lines = G["dmesg_xid_119"]["lines"] + [G["inject_messages"]["known"]["63"]["message"], "NVRM: Xid (PCI:0000:04:00): 31, pid=1, name=a, mmu fault"]
+    buf = "\n".join(lines).encode()
+    for row_remap, want_n in ((1, 6), (0, 7)):      # Xid 63 is discarded when row remapping is supported (component.go:290)
+        comp = C.c_void_p(L.gpudh_xid_component_new(ctx._h, 0, row_remap, 2))
+        L.gpudh_xid_component_set_source(comp, buf, C.c_int64(len(buf)), 0, C.c_int64(0))
+        health, summary = C.c_int32(), C.create_string_buffer(256)
+        n = L.gpudh_xid_component_check(comp, C.byref(health), summary, 256, 1, C.c_int64(1740327858))
+        assert n == want_n
+        assert summary.value.decode() == "matched %d xid errors from %d kmsg(s)" % (want_n, len(lines))
+        assert health.value == 2                      # Xid 119 is Fatal -> Unhealthy
+        out = C.create_string_buffer(2048)
+        L.gpudh_xid_component_state_json(comp, out, 2048)
+        st = json.loads(out.value)
+        assert st["health"] == "Unhealthy" and st["name"] == "error_xid" and st["suggested_actions"]["repair_actions"] == ["REBOOT_SYSTEM"]
+        # the identical events are not inserted twice (eventBucket.Find, component.go:555-563)
+        n_ev = L.gpudh_xid_component_n_events(comp)
+        L.gpudh_xid_component_check(comp, C.byref(health), summary, 256, 1, C.c_int64(1740327858))
+        assert L.gpudh_xid_component_n_events(comp) == n_ev
+        # a reboot after the errors clears a REBOOT_SYSTEM state
+        L.gpudh_xid_component_reboot(comp, C.c_int64(1740327900))
+        L.gpudh_xid_component_state_json(comp, out, 2048)
+        assert json.loads(out.value)["health"] == "Healthy"
+        L.gpudh_xid_component_free(comp)

@@ -1,0 +1,104 @@
+"""The C++ host-side mirror of the reference's operator interface (gpud_b200/csrc/host_component.cpp), exercised through its
+flat test entry points, against the reference's vectors and the Python oracle.  CPU only (no compute calls)."""
+import ctypes as C
+
+import pytest
+
+import gpud_b200 as g
+from oracle import pyoracle as O
+
+ACT = {"IGNORE_NO_ACTION_REQUIRED": 1, "REBOOT_SYSTEM": 2, "HARDWARE_INSPECTION": 3, "CHECK_USER_APP_AND_GPU": 4}
+EV = {"Unknown": 0, "Info": 1, "Warning": 2, "Critical": 3, "Fatal": 4}
+HEALTH = ["Healthy", "Degraded", "Unhealthy"]
+
+
+class HEvent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("event_type", C.c_int32), ("xid", C.c_uint64), ("n_actions", C.c_int32), ("actions", C.c_int32 * 4)]
+
+
+def test_parse_kmsg_line_matches_reference_vectors(golden):          # pkg/kmsg/watcher_test.go (Test_parseLineComprehensive)
+    L = g.lib()
+    rows = golden("pkg_kmsg.json")["Test_parseLineComprehensive"]["rows"]
+    for r in rows:
+        prio, seq, usec = C.c_int32(), C.c_int64(), C.c_int64()
+        msg = C.create_string_buffer(8192)
+        rc = L.gpudh_parse_kmsg_line(r["input"].encode(), C.byref(prio), C.byref(seq), C.byref(usec), msg, 8192)
+        if r.get("expectError"):
+            assert rc != 0, r["name"]
+            with pytest.raises(ValueError):
+                O.parse_kmsg_line(0, r["input"])
+            continue
+        assert rc == 0, r["name"]
+        want = O.parse_kmsg_line(0, r["input"])
+        assert (prio.value, seq.value, usec.value, msg.value.decode()) == want, r["name"]
+        assert (prio.value, seq.value, msg.value.decode()) == (r["expected"]["Priority"], r["expected"]["SequenceNumber"], r["expected"]["Message"])
+
+
+def test_parse_fixture_records(golden):                               # pkg/kmsg/testdata/kmsg.1.log
+    L = g.lib()
+    n = 0
+    for rec in golden("pkg_kmsg.json")["fixture:kmsg.1.log"]["records"]:
+        if not rec:
+            continue
+        prio, seq, usec = C.c_int32(), C.c_int64(), C.c_int64()
+        msg = C.create_string_buffer(8192)
+        rc = L.gpudh_parse_kmsg_line(rec.encode("utf-8", "surrogateescape"), C.byref(prio), C.byref(seq), C.byref(usec), msg, 8192)
+        try:
+            want = O.parse_kmsg_line(0, rec)
+        except ValueError:
+            assert rc != 0
+            continue
+        assert rc == 0 and (prio.value, seq.value, usec.value) == want[:3]
+        n += 1
+    assert n >= 40
+
+
+def test_dedup_key_and_counts():                                      # pkg/kmsg/deduper.go:63-125, deduper_test.go
+    L = g.lib()
+    out = C.create_string_buffer(512)
+    for t, m in ((1700000123, "hello"), (59, "x"), (60, "x"), (1700000160, "NVRM: Xid (PCI:0000:05:00): 79, a")):
+        L.gpudh_dedup_key(C.c_int64(t), m.encode(), out, 512)
+        assert out.value.decode() == O.dedup_key(t, m)
+    L.gpudh_deduper_new.restype = C.c_void_p
+    d = C.c_void_p(L.gpudh_deduper_new(C.c_int64(900)))
+    add = lambda now, t, m: L.gpudh_deduper_add(d, C.c_int64(now), C.c_int64(t), m.encode())
+    assert add(1000, 1000, "a") == 1 and add(1001, 1010, "a") == 2          # same minute bucket: second occurrence is dropped (>1)
+    assert add(1002, 1070, "a") == 1                                         # next minute: new key
+    assert add(1003, 1000, "b") == 1
+    assert add(1000 + 901, 1000, "a") == 1                                   # TTL (15 min) expired
+    L.gpudh_deduper_free(d)
+
+
+def _evolve(events, threshold=2):
+    L = g.lib()
+    arr = (HEvent * max(1, len(events)))()
+    for i, e in enumerate(events):
+        if e["k"] == "xid":
+            arr[i].kind, arr[i].event_type, arr[i].xid = 0, EV[e["type"]], e["xid"]
+            acts = e.get("actions")
+            arr[i].n_actions = -1 if acts is None else len(acts)
+            for j, a in enumerate(acts or []):
+                arr[i].actions[j] = ACT[a]
+        else:
+            arr[i].kind = 1 if e["k"] == "reboot" else 2
+    h, a, x = C.c_int32(), C.c_int32(), C.c_uint64()
+    L.gpudh_evolve(arr, len(events), threshold, C.byref(h), C.byref(a), C.byref(x))
+    return HEALTH[h.value], a.value, x.value
+
+
+def test_evolve_healthy_state_reference_scenarios(golden):            # xid/health_state_test.go:78-246
+    for r in golden("xid_health.json")["rows"]:
+        health, action, _ = _evolve(r["events"])
+        assert health == r["health"], r["name"]
+        assert action == (ACT[r["action"]] if r["action"] else 0), r["name"]
+        # the Python oracle agrees
+        ev = [{"name": "error_xid", "type": e["type"], "xid": e["xid"], "actions": None if e.get("actions") is None else [ACT[a] for a in e["actions"]]}
+              if e["k"] == "xid" else {"name": "reboot"} for e in r["events"]]
+        o = O.evolve_healthy_state(ev, 2)
+        assert o["health"] == r["health"] and (o["actions"][0] if o["actions"] else 0) == action, r["name"]
+
+
+def test_component_name_matches_reference():
+    L = g.lib()
+    L.gpudh_xid_component_name.restype = C.c_char_p
+    assert L.gpudh_xid_component_name() == b"accelerator-nvidia-error-xid"        # xid/component.go:35
