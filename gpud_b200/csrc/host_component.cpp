@@ -191,6 +191,39 @@ std::vector<Event> merge_events(const std::vector<Event>& a, const std::vector<E
   return r;
 }
 
+// ---- threshold rules ----
+SlowdownVerdict evaluate_hw_slowdown(const std::vector<int64_t>& ev, int64_t now, int64_t window_s, double thr) {   // hw-slowdown/component.go:352-407
+  SlowdownVerdict v;
+  if (window_s == 0) { v.reason = "no time window to evaluate states"; return v; }
+  const int64_t since = now - window_s;
+  std::vector<int64_t> minutes;
+  for (int64_t t : ev) if (t >= since) minutes.push_back(t / 60);        // eventBucket.Get(since) then Unix()/60
+  if (minutes.empty()) { v.reason = "no clock events found"; return v; }
+  std::sort(minutes.begin(), minutes.end());
+  minutes.erase(std::unique(minutes.begin(), minutes.end()), minutes.end());
+  v.distinct_minutes = (int)minutes.size();
+  v.freq_per_min = (double)v.distinct_minutes / ((double)window_s / 60.0);
+  char buf[256];
+  if (v.freq_per_min < thr) {
+    snprintf(buf, sizeof buf, "hw slowdown events frequency per minute %.2f (total events per minute count %d) is less than threshold %.2f", v.freq_per_min, v.distinct_minutes, thr);
+    v.reason = buf;
+    return v;
+  }
+  v.health = Health::Unhealthy;
+  v.inspect = true;
+  snprintf(buf, sizeof buf, "hw slowdown events frequency per minute %.2f (total events per minute count %d) exceeded threshold %.2f", v.freq_per_min, v.distinct_minutes, thr);
+  v.reason = buf;
+  return v;
+}
+
+int evaluate_temperature(uint32_t cur, uint32_t gpu_max, uint32_t hbm, uint32_t mem_max, int32_t margin, int32_t margin_thr) {   // temperature/component.go:206-248
+  int m = 0;
+  if (gpu_max > 0 && cur > gpu_max) m |= 1;          // strict '>' like the reference (the same compare n_over uses)
+  if (mem_max > 0 && hbm > mem_max) m |= 2;
+  if (margin_thr > 0 && margin <= margin_thr) m |= 4;
+  return m;
+}
+
 // ---- the component ----
 XidComponent::XidComponent(gpud_ctx* ctx, int32_t dev, bool row_remap, int reboot_threshold)
     : ctx_(ctx), dev_(dev), row_remap_(row_remap), reboot_threshold_(reboot_threshold) {
@@ -396,4 +429,10 @@ int32_t gpudh_xid_component_reboot(void* c, int64_t t) { static_cast<gpud::XidCo
 int32_t gpudh_xid_component_set_healthy(void* c, int64_t t) { return static_cast<gpud::XidComponent*>(c)->SetHealthy(t); }
 int32_t gpudh_xid_component_n_events(void* c) { return (int32_t)static_cast<gpud::XidComponent*>(c)->Events(0).size(); }
 const char* gpudh_xid_component_name(void) { return gpud::XidComponent::kName; }
+int32_t gpudh_hw_slowdown(const int64_t* ev, int32_t n, int64_t now, int64_t window_s, double thr, double* freq, int32_t* distinct) {
+  const gpud::SlowdownVerdict v = gpud::evaluate_hw_slowdown(std::vector<int64_t>(ev, ev + n), now, window_s, thr);
+  *freq = v.freq_per_min; *distinct = v.distinct_minutes;
+  return (int32_t)v.health;
+}
+int32_t gpudh_temperature(uint32_t cur, uint32_t gmax, uint32_t hbm, uint32_t mmax, int32_t margin, int32_t mthr) { return gpud::evaluate_temperature(cur, gmax, hbm, mmax, margin, mthr); }
 }

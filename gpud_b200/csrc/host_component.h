@@ -73,6 +73,15 @@ EvolveResult evolve_healthy_state(const std::vector<XidEventView>& events_newest
 std::vector<Event> trim_events_after_set_healthy(const std::vector<Event>& events_newest_first);     // component.go:630-642
 std::vector<Event> merge_events(const std::vector<Event>& a, const std::vector<Event>& b);           // component.go:614-628
 
+// ---- windowed threshold rules with reference code ----
+// hw-slowdown: distinct event-minutes in the evaluation window / window minutes >= threshold -> Unhealthy + HARDWARE_INSPECTION
+// (components/accelerator/nvidia/hw-slowdown/component.go:352-407; defaults 10 min / 0.6 at :29-35)
+struct SlowdownVerdict { Health health = Health::Healthy; double freq_per_min = 0.0; int distinct_minutes = 0; bool inspect = false; std::string reason; };
+SlowdownVerdict evaluate_hw_slowdown(const std::vector<int64_t>& event_unix_seconds, int64_t now_unix, int64_t window_seconds, double threshold_per_min);
+// temperature: current > max-operating, HBM > max-memory, margin <= configured threshold -> Degraded-class reasons
+// (components/accelerator/nvidia/temperature/component.go:206-248); returns a bit mask 1 gpu, 2 hbm, 4 margin
+int evaluate_temperature(uint32_t cur_c, uint32_t gpu_max_c, uint32_t hbm_c, uint32_t mem_max_c, int32_t margin_c, int32_t margin_threshold_c);
+
 // ---- components.Component (types.go:20-66) ----
 struct CheckResult {
   std::string component, summary, text;

@@ -543,13 +543,15 @@ def evolve_healthy_state(events, reboot_threshold: int = 2):
 # --------------------------------------------------------------------------------------------
 # threshold rules
 # --------------------------------------------------------------------------------------------
-def hw_slowdown_state(event_unix_s: List[int], window_minutes: int, threshold_freq_per_min: float):
-    """hw-slowdown/component.go:383-407: distinct event-minutes / window minutes >= threshold -> Unhealthy."""
-    if window_minutes <= 0:
-        return "Healthy", 0.0
-    mins = {t // 60 for t in event_unix_s}
-    freq = len(mins) / float(window_minutes)
-    return ("Unhealthy" if freq >= threshold_freq_per_min and len(mins) > 0 else "Healthy"), freq
+def hw_slowdown_state(event_unix_s: List[int], now_unix: int, window_seconds: int, threshold_freq_per_min: float):
+    """hw-slowdown/component.go:352-407: distinct event-minutes since (now - window) / window minutes >= threshold -> Unhealthy."""
+    if window_seconds == 0:
+        return "Healthy", 0.0, 0
+    mins = {t // 60 for t in event_unix_s if t >= now_unix - window_seconds}
+    if not mins:
+        return "Healthy", 0.0, 0
+    freq = len(mins) / (window_seconds / 60.0)
+    return ("Healthy" if freq < threshold_freq_per_min else "Unhealthy"), freq, len(mins)
 
 
 # --------------------------------------------------------------------------------------------

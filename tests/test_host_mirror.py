@@ -102,3 +102,28 @@ def test_component_name_matches_reference():
     L = g.lib()
     L.gpudh_xid_component_name.restype = C.c_char_p
     assert L.gpudh_xid_component_name() == b"accelerator-nvidia-error-xid"        # xid/component.go:35
+
+
+def test_hw_slowdown_window_rule():               # hw-slowdown/component.go:352-407 (defaults 10 min / 0.6 per minute, :29-35)
+    L = g.lib()
+    now = 1_700_000_000
+    cases = [([now - 60 * i for i in range(1, 7)], 600, 0.6, "Unhealthy"),          # 6 distinct minutes / 10 = 0.6 >= 0.6
+             ([now - 60 * i for i in range(1, 6)], 600, 0.6, "Healthy"),            # 5 / 10 < 0.6
+             ([now - 61, now - 62, now - 63, now - 119], 600, 0.6, "Healthy"),      # same minute counts once
+             ([now - 700], 600, 0.6, "Healthy"),                                    # outside the window
+             ([now - 5], 0, 0.6, "Healthy"),                                        # no evaluation window
+             ([now - 30 * i for i in range(1, 21)], 600, 0.6, "Unhealthy")]
+    for ev, win, thr, want in cases:
+        arr = (C.c_int64 * max(1, len(ev)))(*ev)
+        freq, distinct = C.c_double(), C.c_int32()
+        h = L.gpudh_hw_slowdown(arr, len(ev), C.c_int64(now), C.c_int64(win), C.c_double(thr), C.byref(freq), C.byref(distinct))
+        oh, ofreq, on = O.hw_slowdown_state(ev, now, win, thr)
+        assert HEALTH[h] == want == oh and distinct.value == on and abs(freq.value - ofreq) < 1e-12
+
+
+def test_temperature_rule():                      # temperature/component.go:206-248: strict '>' on limits, '<=' on the margin
+    L = g.lib()
+    assert L.gpudh_temperature(90, 89, 70, 95, 20, 10) == 1
+    assert L.gpudh_temperature(89, 89, 96, 95, 20, 10) == 2
+    assert L.gpudh_temperature(80, 89, 70, 95, 10, 10) == 4
+    assert L.gpudh_temperature(80, 0, 70, 0, 5, 0) == 0
