@@ -86,6 +86,15 @@ __global__ void __launch_bounds__(256) k_ring_append(const double* __restrict__ 
 // warp primitives.  Keys are kept as (hi, lo) 32-bit halves so every compare / select is one 32-bit instruction.
 // ---------------------------------------------------------------------------------------------
 struct K64 { unsigned hi, lo; };
+// acc += (a > b) for IEEE doubles: DSETP and one predicated integer add
+__device__ __forceinline__ void count_gt_f64(unsigned& acc, double a, double b) {
+  asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(acc) : "d"(a), "d"(b));   // DSETP + predicated add
+}
+// acc -= (o > v) for unsigned words through the borrow flag (sub.cc / subc pair): two integer instructions, no predicate
+__device__ __forceinline__ void count_gt_u32_neg(unsigned& acc, unsigned o, unsigned v) {
+  unsigned t;
+  asm("sub.cc.u32 %1, %2, %3;\n\tsubc.u32 %0, %0, 0;" : "+r"(acc), "=r"(t) : "r"(v), "r"(o));
+}
 __device__ __forceinline__ bool k_gt(unsigned ah, unsigned al, unsigned bh, unsigned bl) { return ah > bh || (ah == bh && al > bl); }
 
 __device__ __forceinline__ K64 warp_max_k64(unsigned hi, unsigned lo) {
@@ -214,14 +223,14 @@ __device__ __forceinline__ int gather_above(const unsigned long long* sk, unsign
 __device__ __forceinline__ unsigned warp_kth_largest_smem(unsigned v, int k, unsigned* s32, int lane) {
   s32[lane] = v;
   __syncwarp();
-  int rank = 0;
+  unsigned neg_rank = 0;                      // minus the number of lanes holding a larger value
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const uint4 o = reinterpret_cast<const uint4*>(s32)[q];
-    rank += (o.x > v) + (o.y > v) + (o.z > v) + (o.w > v);
+    count_gt_u32_neg(neg_rank, o.x, v); count_gt_u32_neg(neg_rank, o.y, v); count_gt_u32_neg(neg_rank, o.z, v); count_gt_u32_neg(neg_rank, o.w, v);
   }
   __syncwarp();
-  return __reduce_min_sync(kFull, rank < k ? v : 0xffffffffu);
+  return __reduce_min_sync(kFull, (int)(0u - neg_rank) < k ? v : 0xffffffffu);
 }
 
 struct WinUnit { int f, w, m; int64_t p0; };
@@ -308,8 +317,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
         kk.z = (unsigned)__double2loint(x1) ^ m1; kk.w = (unsigned)h1 ^ (m1 | 0x80000000u);
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
-        if (x0 > thr) ++nov;
-        if (x1 > thr) ++nov;
+        count_gt_f64(nov, x0, thr);
+        count_gt_f64(nov, x1, thr);
         mh = max(mh, max(kk.y, kk.w));
         nh = min(nh, min(kk.y, kk.w));
       } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
