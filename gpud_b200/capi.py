@@ -87,7 +87,7 @@ class FabricVerdict(C.Structure):
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
            "gpud_ring_push_device", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
-           "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_xid_classify",
+           "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint",
            "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
         "gpud_kmsg_scan": (i32, [vp, i32, vp, i64, i32, C.POINTER(XidHit), i64, C.POINTER(i64), C.POINTER(i64)]),
         "gpud_kmsg_scan_device": (i32, [vp, i32, vp, i64, i32, C.POINTER(XidHit), i64, C.POINTER(i64), C.POINTER(i64), vp]),
         "gpud_kmsg_scan_kernel_ms": (i32, [vp, i32, C.POINTER(C.c_float)]),
+        "gpud_kmsg_scan_stats": (i32, [vp, i32, C.POINTER(i64)]),
         "gpud_xid_classify": (i32, [vp, i32, C.POINTER(XidHit), i64]),
         "gpud_hit_detail_json": (i32, [C.POINTER(XidHit), i64, C.c_char_p, i32]),
         "gpud_xid_description": (C.c_char_p, [i32, i32]), "gpud_xid_mnemonic": (C.c_char_p, [i32]),
@@ -193,6 +194,12 @@ class Context:
         ms = (C.c_float * 3)()
         self._check(self._L.gpud_kmsg_scan_kernel_ms(self._h, dev, ms))
         return list(ms)
+
+    def scan_stats(self, dev: Optional[int] = None):
+        dev = self.devices[0] if dev is None else dev
+        out = (C.c_int64 * 3)()
+        self._check(self._L.gpud_kmsg_scan_stats(self._h, dev, out))
+        return {"candidates": out[0], "hits": out[1], "separators": out[2]}
 
     def classify(self, hits: List[XidHit], dev: Optional[int] = None) -> List[XidHit]:
         dev = self.devices[0] if dev is None else dev

@@ -28,6 +28,7 @@ constexpr int kChunk = 512;                 // bytes per warp step
 constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid ("
 constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVIDIA GPU "
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
+constexpr unsigned kMatchLanes = 16;        // candidates per warp in k_scan_match
 
 struct ScanBuf {
   const uint8_t* p;
@@ -72,6 +73,31 @@ constexpr unsigned kSXid = 0x64695853u;   // "SXid"
 
 // bit 7 of every byte of the result is set exactly where the byte of x is zero
 __device__ __forceinline__ unsigned zero_bytes(unsigned x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
+
+// first index in [from, to) holding byte `c`, else `to`: bytes up to 4-byte alignment, then one aligned word per step
+__device__ int64_t find_byte(const ScanBuf& b, int64_t from, int64_t to, unsigned c) {
+  int64_t i = from;
+  const unsigned pat = c * 0x01010101u;
+  while (i < to && (((uintptr_t)(b.p + i)) & 3)) { if (__ldg(b.p + i) == c) return i; ++i; }
+  for (; i + 4 <= to; i += 4) {
+    const unsigned z = zero_bytes(__ldg(reinterpret_cast<const unsigned*>(b.p + i)) ^ pat);
+    if (z) return i + ((__ffs(z) - 1) >> 3);
+  }
+  for (; i < to; ++i) if (__ldg(b.p + i) == c) return i;
+  return to;
+}
+// last index in [lo, from) holding byte `c`, else lo - 1
+__device__ int64_t rfind_byte(const ScanBuf& b, int64_t lo, int64_t from, unsigned c) {
+  int64_t i = from;                              // exclusive
+  const unsigned pat = c * 0x01010101u;
+  while (i > lo && (((uintptr_t)(b.p + i)) & 3)) { --i; if (__ldg(b.p + i) == c) return i; }
+  for (; i - 4 >= lo; i -= 4) {
+    const unsigned z = zero_bytes(__ldg(reinterpret_cast<const unsigned*>(b.p + i - 4)) ^ pat);
+    if (z) return i - 4 + ((31 - __clz(z)) >> 3);
+  }
+  while (i > lo) { --i; if (__ldg(b.p + i) == c) return i; }
+  return lo - 1;
+}
 
 // Verify one anchor position and append it to the candidate list.  The seven bytes after "NVRM" are fetched with
 // independent loads (one round trip) before any of them is compared.
@@ -247,7 +273,7 @@ struct R1Match { int64_t dev_s, dev_e, code_s, code_e; };
 //  - the class run is maximal and must be followed by ')' (a shorter run would be followed by a class byte);
 //  - `.*?` stops at the first ": " digits+ "," and cannot cross '\n'.
 __device__ bool match_r1(const ScanBuf& b, int64_t s, int64_t e, R1Match* m) {
-  for (int64_t a = s; a + 11 <= e; ++a) {
+  for (int64_t a = find_byte(b, s, e, 'N'); a + 11 <= e; a = find_byte(b, a + 1, e, 'N')) {
     if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM: Xid (")) continue;
     int64_t p = a + 11, q = p;
     if (lit_at(b, q, e, "PCI:")) q += 4;
@@ -291,7 +317,7 @@ __device__ __forceinline__ bool take_hexword(const ScanBuf& b, int64_t& i, int64
 // R2 (kmsg.go:29).  Deterministic given the anchor: every greedy run is maximal and followed by a byte outside its class;
 // the optional ", pid=…, name=…" group is exclusive with the bare ", " continuation ('p' is not in [A-Z_]).
 __device__ bool match_r2(const ScanBuf& b, int64_t s, int64_t e, R2Match* m) {
-  for (int64_t a = s; a + 15 <= e; ++a) {
+  for (int64_t a = find_byte(b, s, e, 'N'); a + 15 <= e; a = find_byte(b, a + 1, e, 'N')) {
     if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM: Xid (PCI:")) continue;
     int64_t i = a + 15;
     m->dev_s = i;
@@ -385,7 +411,7 @@ __device__ bool take_bdf(const ScanBuf& b, int64_t i, int64_t e, int64_t* bs, in
 }
 // R4  NVRM:\s+GPU (BDF)\.0:\s+GPU has fallen off the bus\.?
 __device__ bool match_r4(const ScanBuf& b, int64_t s, int64_t e, int64_t* bs, int64_t* be) {
-  for (int64_t a = s; a + 5 <= e; ++a) {
+  for (int64_t a = find_byte(b, s, e, 'N'); a + 5 <= e; a = find_byte(b, a + 1, e, 'N')) {
     if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM:")) continue;
     int64_t i = a + 5;
     if (!skip_ws1(b, i, e)) continue;
@@ -403,7 +429,7 @@ __device__ bool match_r4(const ScanBuf& b, int64_t s, int64_t e, int64_t* bs, in
 }
 // R3  (?s)NVRM:\s+The NVIDIA GPU (BDF)\.0.*?fallen off the bus and is not responding to commands\.
 __device__ bool match_r3(const ScanBuf& b, int64_t s, int64_t e, int64_t* bs, int64_t* be) {
-  for (int64_t a = s; a + 5 <= e; ++a) {
+  for (int64_t a = find_byte(b, s, e, 'N'); a + 5 <= e; a = find_byte(b, a + 1, e, 'N')) {
     if (ld8(b, a) != 'N' || !lit_at(b, a, e, "NVRM:")) continue;
     int64_t i = a + 5;
     if (!skip_ws1(b, i, e)) continue;
@@ -420,7 +446,7 @@ __device__ bool match_r3(const ScanBuf& b, int64_t s, int64_t e, int64_t* bs, in
 }
 // R5  SXid.*?: (\d+),
 __device__ bool match_r5(const ScanBuf& b, int64_t s, int64_t e, int64_t* cs, int64_t* ce) {
-  for (int64_t a = s; a + 4 <= e; ++a) {
+  for (int64_t a = find_byte(b, s, e, 'S'); a + 4 <= e; a = find_byte(b, a + 1, e, 'S')) {
     if (ld8(b, a) != 'S' || !lit_at(b, a, e, "SXid")) continue;
     for (int64_t i = a + 4; i < e; ++i) {
       const int c = ld8(b, i);
@@ -436,7 +462,7 @@ __device__ bool match_r5(const ScanBuf& b, int64_t s, int64_t e, int64_t* cs, in
 }
 // R6  SXid \((PCI:[0-9a-fA-F:\.]+)\)
 __device__ bool match_r6(const ScanBuf& b, int64_t s, int64_t e, int64_t* ds, int64_t* de) {
-  for (int64_t a = s; a + 10 <= e; ++a) {
+  for (int64_t a = find_byte(b, s, e, 'S'); a + 10 <= e; a = find_byte(b, a + 1, e, 'S')) {
     if (ld8(b, a) != 'S' || !lit_at(b, a, e, "SXid (PCI:")) continue;
     int64_t i = a + 10;
     while (i < e && (is_hex(ld8(b, i)) || ld8(b, i) == ':' || ld8(b, i) == '.')) ++i;
@@ -665,15 +691,30 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
                                                      const uint32_t* __restrict__ chunk_local, const unsigned long long* __restrict__ tile_base, const gpud_tables* __restrict__ T,
                                                      gpud_xid_hit* hits, unsigned long long hit_cap, unsigned long long* n_hits) {
   const unsigned long long n = min(*n_cand, cand_cap);
-  for (unsigned long long ci = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (unsigned long long)gridDim.x * blockDim.x) {
+  // Every candidate runs its own data-dependent automaton, so lanes of a warp serialise on divergent paths.  Only
+  // kMatchLanes lanes per warp take a candidate: the same work spreads over 32 / kMatchLanes times more warps, which the
+  // schedulers overlap (measured: the kernel is latency-bound, not issue-bound).
+  const unsigned lane = threadIdx.x & 31;
+  if (lane >= kMatchLanes) return;
+  const unsigned long long slot0 = (((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kMatchLanes + lane;
+  const unsigned long long slots = (((unsigned long long)gridDim.x * blockDim.x) >> 5) * kMatchLanes;
+  for (unsigned long long ci = slot0; ci < n; ci += slots) {
     const unsigned long long cv = cands[ci];
     const unsigned long long fam = cv >> 60;
     const int64_t a = (int64_t)(cv & ((1ull << 60) - 1));
     // unit bounds
-    int64_t us = a;
-    while (us > 0 && !is_sep(b, us - 1, mode)) --us;
-    int64_t ue = a;
-    while (ue < b.len && !is_sep(b, ue, mode)) ++ue;
+    int64_t us = a, ue = a;
+    for (;;) {                                             // previous separator: a '\n' (in RAW mode one not followed by ' ')
+      const int64_t nl = rfind_byte(b, 0, us, '\n');
+      us = nl + 1;
+      if (nl < 0 || is_sep(b, nl, mode)) break;
+      us = nl;                                             // a continuation line: keep walking back
+    }
+    for (;;) {
+      ue = find_byte(b, ue, b.len, '\n');
+      if (ue >= b.len || is_sep(b, ue, mode)) break;
+      ++ue;
+    }
     // message span
     int64_t ms = us;
     long long k_prio = 0, k_seq = 0, k_usec = 0;
@@ -698,11 +739,11 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
     // only the first anchor of this family group in the unit does the work
     bool first = true;
     if (fam == kFamS) {
-      for (int64_t i = ms; i < a && first; ++i)
-        if (ld8(b, i) == 'S' && lit_at(b, i, ue, "SXid")) first = false;
+      for (int64_t i = find_byte(b, ms, a, 'S'); i < a && first; i = find_byte(b, i + 1, a, 'S'))
+        if (lit_at(b, i, ue, "SXid")) first = false;
     } else {
-      for (int64_t i = ms; i < a && first; ++i)
-        if (ld8(b, i) == 'N' && lit_at(b, i, ue, "NVRM:") && nvrm_family(b, i, ue)) first = false;
+      for (int64_t i = find_byte(b, ms, a, 'N'); i < a && first; i = find_byte(b, i + 1, a, 'N'))
+        if (lit_at(b, i, ue, "NVRM:") && nvrm_family(b, i, ue)) first = false;
     }
     if (!first) continue;
     if (fam != kFamS && !nvrm_family(b, a, ue)) continue;   // the filter judged the context against the buffer end, not the unit end
@@ -711,17 +752,33 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
     // every pattern starts with this family's anchor literal and `a` is the unit's first such anchor: start there
     const bool ok = (fam == kFamS) ? sxid_match_unit(b, a, ue, T, &h) : xid_match_unit(b, a, ue, T, &h);
     if (!ok) continue;
-    // unit number = separators before `us`
-    const int64_t chunk = us / kChunk;
-    unsigned long long idx = tile_base[chunk >> 10] + chunk_local[chunk];
-    idx += count_seps(b, chunk * kChunk, us, mode);
-    h.unit_index = (int64_t)idx;
+    h.unit_index = 0;                              // filled by k_scan_unit_index (one warp per hit, cooperative count)
     h.unit_offset = us;
     h.kmsg_priority = (int32_t)k_prio;
     h.kmsg_seq = k_seq;
     h.kmsg_usec = k_usec;
     const unsigned long long slot = atomicAdd(n_hits, 1ull);
     if (slot < hit_cap) hits[slot] = h;
+  }
+}
+
+// Unit number of every hit = separators before its unit start = tile base + chunk-local prefix + separators between the
+// chunk start and the unit start.  One warp per hit: each lane counts 16 bytes of the (at most 512-byte) run.
+__global__ void __launch_bounds__(256) k_scan_unit_index(ScanBuf b, int mode, const uint32_t* __restrict__ chunk_local,
+                                                          const unsigned long long* __restrict__ tile_base, gpud_xid_hit* hits,
+                                                          const unsigned long long* __restrict__ n_hits, unsigned long long hit_cap) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long n = min(*n_hits, hit_cap);
+  const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long hi = warp_g; hi < n; hi += n_warps) {
+    const int64_t us = hits[hi].unit_offset;
+    const int64_t chunk = us / kChunk, c0 = chunk * kChunk;
+    unsigned cnt = 0;
+    const int64_t lo = c0 + lane * 16;
+    for (int64_t i = lo; i < lo + 16 && i < us; ++i) cnt += is_sep(b, i, mode) ? 1u : 0u;
+    cnt = __reduce_add_sync(kFull, cnt);
+    if (lane == 0) hits[hi].unit_index = (int64_t)(tile_base[chunk >> 10] + chunk_local[chunk] + cnt);
   }
 }
 
@@ -827,8 +884,10 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   k_scan_prefix_top<<<1, 1024, 0, st>>>(s->d_tile_base, n_tiles, s->d_counters + 2);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[2], st);
-  k_scan_match<<<ctx->sm_count * 4, 128, 0, st>>>(b, mode, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, s->d_chunk_local, s->d_tile_base,
+  k_scan_match<<<ctx->sm_count * 16, 128, 0, st>>>(b, mode, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, s->d_chunk_local, s->d_tile_base,
                                                    s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  k_scan_unit_index<<<ctx->sm_count * 2, 256, 0, st>>>(b, mode, s->d_chunk_local, s->d_tile_base, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[3], st);
   GPUD_CUDA(ctx, cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -905,5 +964,16 @@ extern "C" int32_t gpud_kmsg_scan_kernel_ms(gpud_ctx* ctx, int32_t dev, float* m
   if (rc) return rc;
   GPUD_CUDA(ctx, cudaEventSynchronize(s->ev[3]));
   for (int i = 0; i < 3; ++i) GPUD_CUDA(ctx, cudaEventElapsedTime(&ms3[i], s->ev[i], s->ev[i + 1]));
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_kmsg_scan_stats(gpud_ctx* ctx, int32_t dev, int64_t* out3) {
+  if (!ctx || !out3) return GPUD_E_INVALID;
+  gpud_scan_state* s;
+  int32_t rc = scan_state_get(ctx, dev, &s);
+  if (rc) return rc;
+  out3[0] = (int64_t)s->h_counters[0];   // verified anchors (candidates)
+  out3[1] = (int64_t)s->h_counters[1];   // hits
+  out3[2] = (int64_t)s->h_counters[2];   // separators
   return GPUD_OK;
 }

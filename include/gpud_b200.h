@@ -163,6 +163,8 @@ int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8_t* dev_buf
                               gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units, void* cuda_stream);
 /* Device time (ms) of the three kernels of the last scan on `dev`: [0] anchor filter, [1] separator prefix, [2] match. */
 int32_t gpud_kmsg_scan_kernel_ms(gpud_ctx* ctx, int32_t dev, float* ms3);
+/* Counters of the last scan on `dev`: [0] verified anchors, [1] hits, [2] unit separators. */
+int32_t gpud_kmsg_scan_stats(gpud_ctx* ctx, int32_t dev, int64_t* out3);
 /* Classify already-extracted hits (fills event_type/actions/rule_index/detail_variant) with the device LUT
  * kernel; `hits` is host memory, updated in place.  unit_name[] must hold capture 5 for extended hits. */
 int32_t gpud_xid_classify(gpud_ctx* ctx, int32_t dev, gpud_xid_hit* hits, int64_t n);

@@ -32,7 +32,7 @@ hits2, _ = ctx.kmsg_scan(buf, cap=1 << 20)
 e2e = time.perf_counter() - t0
 out = {"bytes": len(buf), "lines": n_units, "hits": len(hits), "filter_ms": float(filt), "prefix_ms": float(pre), "match_ms": float(mat),
        "device_total_ms": float(filt + pre + mat), "filter_GBps": len(buf) / filt / 1e6, "total_GBps": len(buf) / (filt + pre + mat) / 1e6,
-       "e2e_host_ms": e2e * 1e3, "e2e_GBps": len(buf) / e2e / 1e9}
+       "e2e_host_ms": e2e * 1e3, "e2e_GBps": len(buf) / e2e / 1e9, "stats": ctx.scan_stats()}
 if cpu:
     from oracle import coracle
     t0 = time.perf_counter()
