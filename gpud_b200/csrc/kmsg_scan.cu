@@ -169,12 +169,42 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
       if (MODE == GPUD_SCAN_RAW_KMSG) {
         // a '\n' in the last byte of the buffer has no follower: it is a separator (x1's byte there is 0, not ' ') - nothing to fix
       }
-      if (hit) {                                   // unrolled: two compares per position, the call only where an anchor word sits
-        const int64_t off = chunk * kChunk + lane * 16;
+      // ---- anchors (rare): handled by the whole warp, one flagged lane at a time, so no lane works alone ----
+      unsigned hit_lanes = __ballot_sync(kFull, hit);
+      while (hit_lanes) {
+        const int src = __ffs(hit_lanes) - 1;
+        hit_lanes &= hit_lanes - 1;
+        // broadcast the flagged lane's five words; lane k < 16 re-tests window k of its 16 bytes
+        unsigned bw[5];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const unsigned x = (k & 3) ? __funnelshift_r(w[k >> 2], w[(k >> 2) + 1], 8 * (k & 3)) : w[k >> 2];
-          if (x == kNVRM || x == kSXid) filter_verify(b, off + k, x == kNVRM, cands, n_cand, cand_cap);
+        for (int k = 0; k < 5; ++k) bw[k] = __shfl_sync(kFull, w[k], src);
+        const int k16 = lane & 15;
+        const unsigned lo = k16 < 4 ? bw[0] : (k16 < 8 ? bw[1] : (k16 < 12 ? bw[2] : bw[3]));
+        const unsigned hi = k16 < 4 ? bw[1] : (k16 < 8 ? bw[2] : (k16 < 12 ? bw[3] : bw[4]));
+        const unsigned x = __funnelshift_r(lo, hi, 8 * (k16 & 3));
+        const unsigned is_nv = __ballot_sync(kFull, lane < 16 && x == kNVRM);
+        unsigned anchors = is_nv | __ballot_sync(kFull, lane < 16 && x == kSXid);
+        const int64_t off0 = chunk * kChunk + (int64_t)src * 16;
+        while (anchors) {
+          const int k = __ffs(anchors) - 1;
+          anchors &= anchors - 1;
+          const int64_t a = off0 + k;
+          unsigned long long fam = kFamS;
+          if ((is_nv >> k) & 1u) {
+            // ": Xid (" must follow "NVRM": lanes 0..6 fetch one byte each (one 32-byte sector) and vote
+            const int cb = lane < 7 ? ld8(b, a + 4 + lane) : 0;
+            const unsigned long long pat = 0x2820646958203aull;            // bytes ':',' ','X','i','d',' ','(' little-endian
+            const int want = (int)((pat >> (8 * (lane < 7 ? lane : 0))) & 0xff);
+            const unsigned bad = __ballot_sync(kFull, lane < 7 && cb != want);
+            if (bad == 0u) fam = kFamX;
+            else if (bad & 1u) fam = 0;                                    // not even "NVRM:"
+            else if (!is_ws(__shfl_sync(kFull, cb, 1))) fam = 0;          // R3/R4 need \s+ right after the colon
+            else fam = nvrm_family(b, a, b.len);                          // rare: whitespace run, then "GPU " / "The NVIDIA GPU "
+          }
+          if (fam && lane == 0) {
+            const unsigned long long slot = atomicAdd(n_cand, 1ull);
+            if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << 60);
+          }
         }
       }
       sep = __reduce_add_sync(kFull, sep);
