@@ -168,7 +168,7 @@ class Context:
         """Scan host bytes; returns (hits: List[XidHit], n_units)."""
         dev = self.devices[0] if dev is None else dev
         n = len(buf)
-        src = (C.c_char * max(n, 1)).from_buffer_copy(buf if n else b"\0")
+        src = C.c_char_p(buf)                     # no copy: the library only reads the bytes during the call
         while True:
             hits = (XidHit * cap)()
             nh, nu = C.c_int64(), C.c_int64()
@@ -177,7 +177,15 @@ class Context:
                 cap = int(nh.value)
                 continue
             self._check(rc)
+            self.last_scan_raw = (hits, nh.value)
             return [hits[i] for i in range(nh.value)], nu.value
+
+    def kmsg_scan_c(self, buf: bytes, hits, cap: int, mode: int = SCAN_LINES, dev: Optional[int] = None):
+        """The bare C call (preallocated XidHit array): what a cgo caller pays.  Returns (n_hits, n_units)."""
+        dev = self.devices[0] if dev is None else dev
+        nh, nu = C.c_int64(), C.c_int64()
+        self._check(self._L.gpud_kmsg_scan(self._h, dev, C.cast(C.c_char_p(buf), C.c_void_p), len(buf), mode, hits, cap, C.byref(nh), C.byref(nu)))
+        return nh.value, nu.value
 
     def kmsg_scan_device(self, dev_ptr: int, length: int, mode: int = SCAN_LINES, dev: Optional[int] = None, cap: int = 1 << 16,
                          stream: int = 0):

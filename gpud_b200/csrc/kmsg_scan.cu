@@ -118,6 +118,23 @@ __device__ __noinline__ void filter_verify(const ScanBuf& b, int64_t a, bool is_
   if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << 60);
 }
 
+// nvrm_family for the R3/R4 shapes, by the whole warp: the 32 bytes after "NVRM:" are fetched one per lane, the
+// whitespace run ends at the first non-\s ballot bit, and the two literals are compared lane-wise against it.
+__device__ const char kLitGPU[] = "GPU ";
+__device__ const char kLitTheGPU[] = "The NVIDIA GPU ";
+__device__ __forceinline__ unsigned long long nvrm_family_coop(const ScanBuf& b, int64_t a, int lane) {
+  const int cb = ld8(b, a + 5 + lane);
+  const unsigned nws = __ballot_sync(kFull, !is_ws(cb));
+  if (nws == 0u) return nvrm_family(b, a, b.len);            // more than 32 whitespace bytes: sequential path
+  const int q = __ffs(nws) - 1;
+  if (q == 0) return 0;                                       // \s+ needs at least one
+  if (q + 15 > 32) return nvrm_family(b, a, b.len);
+  const int k = lane - q;
+  const unsigned bad1 = __ballot_sync(kFull, k >= 0 && k < 4 && cb != (int)(unsigned char)__ldg(kLitGPU + (k < 0 ? 0 : (k > 3 ? 3 : k))));
+  const unsigned bad2 = __ballot_sync(kFull, k >= 0 && k < 15 && cb != (int)(unsigned char)__ldg(kLitTheGPU + (k < 0 ? 0 : (k > 14 ? 14 : k))));
+  return (bad1 == 0u || bad2 == 0u) ? kFamB : 0ull;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
                                                       unsigned long long* n_cand, unsigned long long cand_cap) {
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
             if (bad == 0u) fam = kFamX;
             else if (bad & 1u) fam = 0;                                    // not even "NVRM:"
             else if (!is_ws(__shfl_sync(kFull, cb, 1))) fam = 0;          // R3/R4 need \s+ right after the colon
-            else fam = nvrm_family(b, a, b.len);                          // rare: whitespace run, then "GPU " / "The NVIDIA GPU "
+            else fam = nvrm_family_coop(b, a, lane);                      // whitespace run, then "GPU " / "The NVIDIA GPU "
           }
           if (fam && lane == 0) {
             const unsigned long long slot = atomicAdd(n_cand, 1ull);
@@ -841,6 +858,8 @@ struct gpud_scan_state {
   unsigned long long* h_counters = nullptr;   // pinned
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around filter / prefix / match of the last scan
+  uint8_t* h_stage[2] = {nullptr, nullptr};                    // pinned staging for pageable caller buffers
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 };
 
 void gpud_scan_state_free(gpud_scan_state* s) {
@@ -849,6 +868,7 @@ void gpud_scan_state_free(gpud_scan_state* s) {
   cudaFree(s->d_hits); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) { if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]); if (s->ev_stage[i]) cudaEventDestroy(s->ev_stage[i]); }
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -966,7 +986,31 @@ extern "C" int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf
   int32_t rc = scan_state_get(ctx, dev, &s);
   if (rc) return rc;
   GPUD_CUDA(ctx, grow(&s->d_buf, &s->buf_cap, (size_t)len + 64));
-  if (len) GPUD_CUDA(ctx, cudaMemcpyAsync(s->d_buf, buf, (size_t)len, cudaMemcpyHostToDevice, s->stream));
+  if (len) {
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, buf) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    if (pinned) {
+      GPUD_CUDA(ctx, cudaMemcpyAsync(s->d_buf, buf, (size_t)len, cudaMemcpyHostToDevice, s->stream));
+    } else {
+      // pageable caller memory (a Go []byte): stage through two pinned buffers so the CPU copy of piece k+1 overlaps the DMA of piece k
+      const size_t piece = 8u << 20;
+      for (int i = 0; i < 2; ++i)
+        if (!s->h_stage[i]) {
+          GPUD_CUDA(ctx, cudaMallocHost(&s->h_stage[i], piece));
+          GPUD_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_stage[i], cudaEventDisableTiming));
+        }
+      int k = 0;
+      for (size_t off = 0; off < (size_t)len; off += piece, k ^= 1) {
+        const size_t n = std::min(piece, (size_t)len - off);
+        GPUD_CUDA(ctx, cudaEventSynchronize(s->ev_stage[k]));
+        memcpy(s->h_stage[k], buf + off, n);
+        GPUD_CUDA(ctx, cudaMemcpyAsync(s->d_buf + off, s->h_stage[k], n, cudaMemcpyHostToDevice, s->stream));
+        GPUD_CUDA(ctx, cudaEventRecord(s->ev_stage[k], s->stream));
+      }
+    }
+  }
   rc = scan_launch(ctx, s, s->d_buf, len, mode, cap, s->stream);
   if (rc) return rc;
   return scan_collect(ctx, s, hits, cap, n_hits, n_units, s->stream);
