@@ -113,6 +113,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-fields", type=int, default=0, help="fields in the CPU sample (0 = auto, about 10-30 s of CPU work)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scan", action="store_true")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,6 +267,38 @@ def main():
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                "sample": "%d of 512 fields x 1Mi samples, one pass (C oracle oracle/oracle.c, pthreads over fields)" % fields}
 
+    # ---- secondary workload (BASELINE configs[2]): Xid/SXid scan of a 100 MiB synthetic dmesg buffer, rank 0 at N=1 only ----
+    scan = None
+    if rank == 0 and world == 1 and not a.no_scan:
+        try:
+            unit = synth.dmesg_buffer(4 << 20, hit_every=1000)
+            buf = unit * 25
+            d = torch.frombuffer(bytearray(buf), dtype=torch.uint8).to(dev)
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(4):
+                hits, n_units = ctx.kmsg_scan_device(d.data_ptr(), len(buf), cap=1 << 17, dev=local)
+                ms.append(ctx.scan_kernel_ms(dev=local))
+            filt, pre, mat = np.array(ms[1:]).mean(axis=0)
+            harr = (g.XidHit * (1 << 17))()
+            ctx.kmsg_scan_c(buf, harr, 1 << 17, dev=local)
+            t0 = time.perf_counter()
+            nh2, _ = ctx.kmsg_scan_c(buf, harr, 1 << 17, dev=local)
+            e2e_s = time.perf_counter() - t0
+            from oracle import coracle
+            t0 = time.perf_counter()
+            ch, _nl = coracle.scan_lines(buf)
+            cpu_s = time.perf_counter() - t0
+            same = [(h.line, h.kind, h.code) for h in ch] == [(h.unit_index, h.kind, h.code) for h in hits]
+            scan = {"workload": "100 MiB synthetic dmesg (reference fixtures + noise + injected Xid/SXid lines)", "bytes": len(buf), "lines": n_units,
+                    "hits": len(hits), "device_ms": float(filt + pre + mat), "device_GBps": len(buf) / float(filt + pre + mat) / 1e6,
+                    "filter_kernel_ms": float(filt), "filter_frac_of_hbm_peak": len(buf) / float(filt) / 1e6 / peaks()[0],
+                    "e2e_host_ms": e2e_s * 1e3, "e2e_GBps": len(buf) / e2e_s / 1e9, "cpu_oracle_ms": cpu_s * 1e3, "cpu_oracle_GBps": len(buf) / cpu_s / 1e9,
+                    "cpu_threads": coracle.max_threads(), "hits_identical_to_oracle": bool(same and nh2 == len(hits))}
+            del d
+        except Exception as ex:   # the scan leg must never cost the headline line
+            scan = {"error": repr(ex)}
+
     ring.close()
     ctx.close()
     if rank == 0:
@@ -276,7 +309,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "kernel": "k_window_reduce", "kernel_ms": k_reduce, "carry_kernel_ms": k_carry, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"
                              if how == "measured" else "fallback 6650 GB/s (B200_PROFILING.md)", "algorithmic_bytes_per_launch": F * CAP * 8},
-                "cpu_baseline": cpu}
+                "cpu_baseline": cpu, "scan": scan}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -234,9 +234,14 @@ __device__ __forceinline__ unsigned warp_kth_largest_smem(unsigned v, int k, uns
 }
 
 struct WinUnit { int f, w, m; int64_t p0; };
+#ifndef GPUD_PREFETCH_PAIRS
+#define GPUD_PREFETCH_PAIRS 16   /* measured: 8 pairs + 3 CTAs/SM = 63 % of roofline, 16 pairs + 2 CTAs/SM = 82 % */
+#endif
+constexpr int kPrefetchPairs = GPUD_PREFETCH_PAIRS;      // register pairs of the NEXT window loaded under the current post-processing
+constexpr int kHotCtasPerSM = kPrefetchPairs < 16 ? 3 : 2;  // 8 pairs in flight fit 80 registers (3 CTAs/SM); all 16 need 128 (2 CTAs/SM)
 
 template <bool ALIGNED, int JF>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const WinParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kHotCtasPerSM : 2) k_window_reduce(const WinParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
   int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   int uf = (int)(u / per_f), uslot = (int)(u - (int64_t)uf * per_f);
 
+  constexpr int PF = (ALIGNED && JF >= 0) ? kPrefetchPairs : 16;
   double2 v[16];                 // the window in flight: loaded for the NEXT unit while the current one is post-processed
   double thr_next = 0.0;
   // fetch the next non-skipped unit of this warp (if any) and issue all of its loads
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
       const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + q.p0) + lane;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
+        if (j >= PF) continue;                                     // the rest is loaded by fetch_rest() at the top of the next trip
         if (JF >= 0 && j < JF) { v[j] = __ldcs(b2 + 32 * j); continue; }
         v[j] = make_double2(0.0, 0.0);
         if (64 * j + 2 * lane < q.m) v[j] = __ldcs(b2 + 32 * j);   // element t0+1 == m is masked in pass 1 (the ring has slack)
@@ -294,9 +301,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) k_window_reduce(const 
     return true;
   };
 
+  auto fetch_rest = [&](const WinUnit& q) {
+    if (PF >= 16) return;
+    const double2* __restrict__ b2 = reinterpret_cast<const double2*>(p.ring + (int64_t)q.f * p.cap + q.p0) + lane;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < PF) continue;
+      if (JF >= 0 && j < JF) { v[j] = __ldcs(b2 + 32 * j); continue; }
+      v[j] = make_double2(0.0, 0.0);
+      if (64 * j + 2 * lane < q.m) v[j] = __ldcs(b2 + 32 * j);
+    }
+  };
+
   WinUnit cur, nxt;
   bool have = fetch(cur);
   while (have) {
+    fetch_rest(cur);
     const int f = cur.f, w = cur.w, m = cur.m;
     const int J = (m + 63) >> 6;                     // register pairs that hold at least one valid element
     const int Jfull = JF >= 0 ? JF : (m >> 6);       // register pairs in which every lane's two elements are valid
@@ -685,7 +705,7 @@ static cudaError_t launch_one(gpud_ring* r, const WinParams& p, int64_t units) {
   // 72 KB of dynamic shared memory per CTA (8 warps x (32 x 272 B key rows + candidate list)): opt in above 48 KB
   cudaError_t e = cudaFuncSetAttribute(k_window_reduce<ALIGNED, JF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmemBytes);
   if (e != cudaSuccess) return e;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * 2));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * ((ALIGNED && JF >= 0) ? kHotCtasPerSM : 2)));
   k_window_reduce<ALIGNED, JF><<<grid, kWarpsPerBlock * 32, kBlockSmemBytes, r->stream>>>(p);
   return cudaGetLastError();
 }
