@@ -194,18 +194,19 @@ __device__ __forceinline__ int gather_above(const unsigned long long* sk, unsign
   if ((rows >> lane) & 1u) row_list[__popc(rows & lt_mask)] = (unsigned char)lane;
   if (lane == 0) *s_cnt = 0;
   __syncwarp();
+  const unsigned long long Lp = ((unsigned long long)Lh << 32) | Ll;
+  const unsigned long long* my_col = sk + lane;              // this lane's column; a row is kRowU64 entries further
 #pragma unroll 1
   for (int i = 0; i < n_rows; i += 4) {                      // four rows per trip: their LDS are independent and overlap
     const unsigned r4 = *reinterpret_cast<const unsigned*>(row_list + i);
     unsigned long long kv[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) kv[q] = (i + q < n_rows) ? sk[((r4 >> (8 * q)) & 31u) * kRowU64 + lane] : 0ull;
+    for (int q = 0; q < 4; ++q) kv[q] = (i + q < n_rows) ? my_col[((r4 >> (8 * q)) & 31u) * kRowU64] : 0ull;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const unsigned h = (unsigned)(kv[q] >> 32), l = (unsigned)kv[q];
-      if (h >= Lh && k_gt(h, l, Lh, Ll)) {                   // a zero (absent row) is never above the bound
+      if (kv[q] > Lp) {                                      // a zero (absent row) is never above the bound
         const int pos = atomicAdd(s_cnt, 1);
-        if (pos < kCandMax) cand[pos] = make_uint2(l, h);
+        if (pos < kCandMax) cand[pos] = make_uint2((unsigned)kv[q], (unsigned)(kv[q] >> 32));
       }
     }
   }
