@@ -1,7 +1,15 @@
-// select.cu — whole-range aggregates of the newest n samples of every field: exact order statistic by MSB-first radix
-// select (6 passes of 11/11/11/11/11/9 key bits), the other aggregates folded from the per-window pass of ring.cu.
+// select.cu — whole-range aggregates of the newest n samples of every field (gpud_ring_reduce_range).
+//
+// min / max / mean / EMA / n_over are folded from the per-window pass of ring.cu (W' = 1024 windows over the range).
+// The exact order statistic is an MSB-first radix select on the IEEE totalOrder keys that spends HBM passes only where
+// they narrow the candidate set:
+//   1. the bits on which the field's min and max keys agree are skipped (they are common to every key);
+//   2. one 11-bit histogram pass over the first varying digit usually leaves <= kCollectMax keys in the bin that holds the
+//      rank; further histogram passes run only for fields that still have more (heavy ties);
+//   3. one collect pass compacts the surviving keys of every field, and a final per-field kernel selects among them
+//      bit by bit in registers.
+// Typical cost: 3 reads of the range (window pass, histogram, collect) instead of the 7 of a plain 6-digit radix select.
 // Definitions: oracle/SPEC.md (parity unpinned: the reference has no such aggregate).
-// Algorithmic bytes: 8 B/sample; this first version re-reads the range once per radix pass (7 reads in total).
 #include <stdarg.h>
 
 #include <algorithm>
@@ -11,62 +19,56 @@
 namespace {
 
 constexpr int kBins = 2048;
-__constant__ int c_shift[6] = {53, 42, 31, 20, 9, 0};
-__constant__ int c_bits[6] = {11, 11, 11, 11, 11, 9};
+constexpr int kDigit = 11;
+constexpr int kCollectMax = 8192;      // candidates the final kernel keeps in registers: 256 threads x 32 keys
+constexpr int kMaxHistPasses = 6;      // 64 bits / 11
 
-// grid (blocks_per_field, F); each block histograms its slice of the field's range for the current digit
-__global__ void __launch_bounds__(256) k_sel_hist(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, int pass,
-                                                   const unsigned long long* __restrict__ prefix, unsigned* __restrict__ hist) {
-  __shared__ unsigned s_hist[kBins];
-  const int f = blockIdx.y;
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_hist[i] = 0;
-  __syncthreads();
-  const int shift = c_shift[pass], bits = c_bits[pass];
-  const unsigned long long want = pass ? prefix[f] : 0ull;
-  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
-  const int64_t b = (int64_t)blockIdx.x * per, e = min(n, b + per);
-  const double* __restrict__ base = ring + (int64_t)f * cap;
+struct SelState {                      // one per field, device resident
+  unsigned long long prefix;           // the key bits fixed so far, right-aligned
+  unsigned long long kk;               // rank (1-based, from the top) among the keys that match the prefix
+  unsigned long long cnt;              // how many keys match the prefix
+  unsigned long long ans;              // valid when done
+  int nbits;                           // number of fixed bits, from the MSB
+  int done;
+  unsigned collected;                  // fill counter of the candidate list
+  int pad;
+};
+
+__device__ __forceinline__ bool key_matches(unsigned long long key, const SelState& s) {
+  return s.nbits == 0 || (key >> (64 - s.nbits)) == s.prefix;
+}
+
+// Stream the keys of chronological positions [b, e) of one field through `fn(key)`.  When the slice is one aligned,
+// non-wrapping run every thread keeps four 128-bit loads in flight (8 keys); otherwise 64-bit loads with the ring wrap.
+template <typename Fn>
+__device__ __forceinline__ void for_each_key(const double* __restrict__ base, int64_t cap, int64_t start, int64_t b, int64_t e, Fn fn) {
+  int64_t p0 = start + b;
+  if (p0 >= cap) p0 -= cap;
+  const int64_t len = e - b;
+  auto K = [](double x) { return gpud_f64_key((unsigned long long)__double_as_longlong(x)); };
+  if (len > 0 && p0 + len <= cap && (p0 & 1) == 0) {
+    const double2* __restrict__ v2 = reinterpret_cast<const double2*>(base + p0);
+    const int64_t n2 = len >> 1;                            // whole pairs
+    int64_t i = threadIdx.x;
+    for (; i + 3 * (int64_t)blockDim.x < n2; i += 4 * (int64_t)blockDim.x) {
+      const double2 a0 = __ldcs(v2 + i), a1 = __ldcs(v2 + i + blockDim.x), a2 = __ldcs(v2 + i + 2 * blockDim.x), a3 = __ldcs(v2 + i + 3 * blockDim.x);
+      fn(K(a0.x)); fn(K(a0.y)); fn(K(a1.x)); fn(K(a1.y)); fn(K(a2.x)); fn(K(a2.y)); fn(K(a3.x)); fn(K(a3.y));
+    }
+    for (; i < n2; i += blockDim.x) { const double2 a0 = __ldcs(v2 + i); fn(K(a0.x)); fn(K(a0.y)); }
+    if ((len & 1) && threadIdx.x == 0) fn(K(__ldcs(base + p0 + len - 1)));
+    return;
+  }
   for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
     int64_t a = start + i;
     if (a >= cap) a -= cap;
-    const unsigned long long key = gpud_f64_key((unsigned long long)__double_as_longlong(__ldcs(base + a)));
-    if (pass == 0 || (key >> (shift + bits)) == want) atomicAdd(&s_hist[(unsigned)(key >> shift) & ((1u << bits) - 1u)], 1u);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x)
-    if (s_hist[i]) atomicAdd(&hist[(int64_t)f * kBins + i], s_hist[i]);
-}
-
-// one block per field: walk the digit histogram from the top, fix the next digit of the k-th largest key
-__global__ void __launch_bounds__(256) k_sel_pick(unsigned* __restrict__ hist, int pass, unsigned long long* __restrict__ prefix,
-                                                   unsigned long long* __restrict__ kk) {
-  __shared__ unsigned s[kBins];
-  __shared__ unsigned s_sum[256];
-  const int f = blockIdx.x, t = threadIdx.x;
-  const int bits = c_bits[pass], nb = 1 << bits;
-  for (int i = t; i < kBins; i += 256) { s[i] = i < nb ? hist[(int64_t)f * kBins + i] : 0; hist[(int64_t)f * kBins + i] = 0; }
-  __syncthreads();
-  // thread t owns bins [8t, 8t+8) counted from the TOP: bin index nb-1-j
-  unsigned loc = 0;
-  for (int j = 8 * t; j < 8 * t + 8; ++j) if (j < nb) loc += s[nb - 1 - j];
-  s_sum[t] = loc;
-  __syncthreads();
-  if (t == 0) {
-    unsigned long long want = kk[f], acc = 0;
-    int g = 0;
-    while (g < 255 && acc + s_sum[g] < want) { acc += s_sum[g]; ++g; }
-    int j = 8 * g;
-    while (j < nb - 1 && acc + s[nb - 1 - j] < want) { acc += s[nb - 1 - j]; ++j; }
-    prefix[f] = ((pass ? prefix[f] : 0ull) << bits) | (unsigned long long)(nb - 1 - j);
-    kk[f] = want - acc;
+    fn(K(__ldcs(base + a)));
   }
 }
 
-// fold the per-window partials into per-field results; init the select rank
+// fold the per-window partials into per-field results; initialise the select state
 __global__ void k_range_fold(int F, int nw, int Wp, int64_t n, const double* __restrict__ w_min, const double* __restrict__ w_max,
                              const double* __restrict__ w_mean, const double* __restrict__ w_ema, const uint32_t* __restrict__ w_nover,
-                             int q_num, int q_den, double* __restrict__ out /*[5][F]*/, uint32_t* __restrict__ out_nover,
-                             unsigned long long* __restrict__ kk) {
+                             int q_num, int q_den, double* __restrict__ out /*[5][F]*/, uint32_t* __restrict__ out_nover, SelState* __restrict__ st) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   unsigned long long kmin = ~0ull, kmax = 0ull;
@@ -87,12 +89,129 @@ __global__ void k_range_fold(int F, int nw, int Wp, int64_t n, const double* __r
   out_nover[f] = nov;
   long long r = (n * q_num + q_den - 1) / q_den;
   r = r < 1 ? 1 : (r > n ? n : r);
-  kk[f] = (unsigned long long)(n - r + 1);
+  SelState s;
+  s.kk = (unsigned long long)(n - r + 1);
+  s.cnt = (unsigned long long)n;
+  s.collected = 0;
+  s.pad = 0;
+  const unsigned long long diff = kmin ^ kmax;
+  if (diff == 0ull) {                  // a constant field: every key is the answer
+    s.prefix = kmax; s.nbits = 64; s.done = 1; s.ans = kmax;
+  } else {
+    const int cp = __clzll((long long)diff);   // leading bits common to all keys of the field
+    s.nbits = cp;
+    s.prefix = cp ? (kmax >> (64 - cp)) : 0ull;
+    s.done = 0;
+    s.ans = 0ull;
+  }
+  st[f] = s;
 }
 
-__global__ void k_sel_finish(int F, const unsigned long long* __restrict__ prefix, double* __restrict__ out) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f < F) out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(prefix[f]));
+// grid (blocks_per_field, F): histogram of the next digit over the keys that match the field's prefix
+__global__ void __launch_bounds__(256) k_sel_hist(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n,
+                                                   const SelState* __restrict__ st, unsigned* __restrict__ hist) {
+  __shared__ unsigned s_hist[kBins];
+  const int f = blockIdx.y;
+  const SelState s = st[f];
+  if (s.done || s.cnt <= (unsigned long long)kCollectMax) return;   // block-uniform: nothing left to narrow for this field
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int d = min(kDigit, 64 - s.nbits), shift = 64 - s.nbits - d;
+  const unsigned mask = (1u << d) - 1u;
+  const int64_t per = (((n + gridDim.x - 1) / gridDim.x) + 1) & ~(int64_t)1;   // even, so aligned slices stay aligned
+  const int64_t b = min(n, (int64_t)blockIdx.x * per), e = min(n, b + per);
+  const double* __restrict__ base = ring + (int64_t)f * cap;
+  for_each_key(base, cap, start, b, e, [&](unsigned long long key) {
+    if (key_matches(key, s)) atomicAdd(&s_hist[(unsigned)(key >> shift) & mask], 1u);
+  });
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[(int64_t)f * kBins + i], s_hist[i]);
+}
+
+// one block per field: walk the digit histogram from the top, fix the next digit of the k-th largest key
+__global__ void __launch_bounds__(256) k_sel_pick(unsigned* __restrict__ hist, SelState* __restrict__ st) {
+  __shared__ unsigned s[kBins];
+  __shared__ unsigned s_sum[256];
+  const int f = blockIdx.x, t = threadIdx.x;
+  SelState cur = st[f];
+  if (cur.done || cur.cnt <= (unsigned long long)kCollectMax) return;
+  const int d = min(kDigit, 64 - cur.nbits), nb = 1 << d;
+  for (int i = t; i < kBins; i += 256) { s[i] = i < nb ? hist[(int64_t)f * kBins + i] : 0; hist[(int64_t)f * kBins + i] = 0; }
+  __syncthreads();
+  unsigned loc = 0;                    // thread t owns bins [8t, 8t+8) counted from the TOP
+  for (int j = 8 * t; j < 8 * t + 8; ++j) if (j < nb) loc += s[nb - 1 - j];
+  s_sum[t] = loc;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long acc = 0;
+    int g = 0;
+    while (g < 255 && acc + s_sum[g] < cur.kk) { acc += s_sum[g]; ++g; }
+    int j = 8 * g;
+    while (j < nb - 1 && acc + s[nb - 1 - j] < cur.kk) { acc += s[nb - 1 - j]; ++j; }
+    const unsigned bin = (unsigned)(nb - 1 - j);
+    cur.prefix = (cur.nbits ? (cur.prefix << d) : 0ull) | bin;
+    cur.nbits += d;
+    cur.kk -= acc;
+    cur.cnt = s[bin];
+    if (cur.nbits >= 64) { cur.done = 1; cur.ans = cur.prefix; }
+    st[f] = cur;
+  }
+}
+
+// grid (blocks_per_field, F): compact the keys that still match into the field's candidate list (<= kCollectMax of them)
+__global__ void __launch_bounds__(256) k_sel_collect(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n,
+                                                      SelState* __restrict__ st, unsigned long long* __restrict__ lists) {
+  const int f = blockIdx.y;
+  const SelState s = st[f];
+  if (s.done) return;
+  const int64_t per = (((n + gridDim.x - 1) / gridDim.x) + 1) & ~(int64_t)1;
+  const int64_t b = min(n, (int64_t)blockIdx.x * per), e = min(n, b + per);
+  const double* __restrict__ base = ring + (int64_t)f * cap;
+  unsigned long long* __restrict__ list = lists + (int64_t)f * kCollectMax;
+  unsigned* fill = &st[f].collected;
+  for_each_key(base, cap, start, b, e, [&](unsigned long long key) {
+    if (key_matches(key, s)) {
+      const unsigned pos = atomicAdd(fill, 1u);
+      if (pos < (unsigned)kCollectMax) list[pos] = key;
+    }
+  });
+}
+
+// one block per field: k-th largest of the (<= kCollectMax) collected keys, remaining bits fixed one at a time;
+// every thread keeps its 32 keys in registers, the per-bit counts meet in shared memory
+__global__ void __launch_bounds__(256) k_sel_final(const SelState* __restrict__ st, const unsigned long long* __restrict__ lists, int F,
+                                                    double* __restrict__ out) {
+  __shared__ unsigned s_cnt[8];
+  const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const SelState s = st[f];
+  unsigned long long ans = s.ans;
+  if (!s.done) {
+    const unsigned n = (unsigned)min((unsigned long long)kCollectMax, (unsigned long long)s.collected);
+    const unsigned long long* __restrict__ list = lists + (int64_t)f * kCollectMax;
+    unsigned long long key[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const unsigned idx = (unsigned)i * 256u + (unsigned)t; key[i] = idx < n ? list[idx] : 0ull; }   // 0 never matches a set bit
+    unsigned long long pref = s.nbits ? (s.prefix << (64 - s.nbits)) : 0ull;
+    unsigned long long kk = s.kk;
+    for (int b = 63 - s.nbits; b >= 0; --b) {
+      const unsigned long long trial = pref | (1ull << b);
+      const unsigned long long himask = ~((1ull << b) - 1ull);
+      unsigned c = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) c += ((key[i] & himask) == trial) ? 1u : 0u;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0) s_cnt[wid] = c;
+      __syncthreads();
+      unsigned tot = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += s_cnt[w];
+      __syncthreads();
+      if ((unsigned long long)tot >= kk) pref = trial; else kk -= tot;
+    }
+    ans = pref;
+  }
+  if (t == 0) out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(ans));
 }
 
 }  // namespace
@@ -102,7 +221,6 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   gpud_range_view v;
   int64_t total = 0, count = 0, nwin = 0;
   gpud_ring_counts(ring, &total, &count, &nwin);
-  // ctx is reachable only after the view is built; validate emptiness through counts first
   if (count == 0) return GPUD_E_STATE;
   int32_t rc = gpud_ring_range_partials(ring, last_n, &v);
   if (rc) return rc;
@@ -111,29 +229,33 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   double* d_out = nullptr;
   uint32_t* d_nover = nullptr;
   unsigned* d_hist = nullptr;
-  unsigned long long *d_prefix = nullptr, *d_kk = nullptr;
+  SelState* d_st = nullptr;
+  unsigned long long* d_lists = nullptr;
   cudaError_t e = cudaMallocAsync(&d_out, 5 * v.F * sizeof(double), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nover, v.F * sizeof(uint32_t), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_hist, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_prefix, v.F * sizeof(unsigned long long), v.stream);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_kk, v.F * sizeof(unsigned long long), v.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_st, v.F * sizeof(SelState), v.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_lists, (size_t)v.F * kCollectMax * sizeof(unsigned long long), v.stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_hist, 0, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_prefix, 0, v.F * sizeof(unsigned long long), v.stream);
   if (e == cudaSuccess) {
     k_range_fold<<<(v.F + 127) / 128, 128, 0, v.stream>>>(v.F, v.nw, v.Wp, v.n, v.w_min, v.w_max, v.w_mean, v.w_ema, v.w_nover, v.q_num, v.q_den,
-                                                         d_out, d_nover, d_kk);
-    const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 4 * v.sm_count / v.F + 1)));
-    for (int pass = 0; pass < 6; ++pass) {
-      k_sel_hist<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, pass, d_prefix, d_hist);
-      k_sel_pick<<<v.F, 256, 0, v.stream>>>(d_hist, pass, d_prefix, d_kk);
+                                                         d_out, d_nover, d_st);
+    // blocks per field: enough CTAs to fill the machine a few times over, each streaming >= 16 Ki keys
+    const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 8 * v.sm_count / v.F + 1)));
+    if (v.n > kCollectMax) {
+      for (int pass = 0; pass < kMaxHistPasses; ++pass) {          // later passes exit at once for fields that are already narrow
+        k_sel_hist<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_hist);
+        k_sel_pick<<<v.F, 256, 0, v.stream>>>(d_hist, d_st);
+      }
     }
-    k_sel_finish<<<(v.F + 127) / 128, 128, 0, v.stream>>>(v.F, d_prefix, d_out);
+    k_sel_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_lists);
+    k_sel_final<<<v.F, 256, 0, v.stream>>>(d_st, d_lists, v.F, d_out);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
   cudaFreeAsync(d_out, v.stream); cudaFreeAsync(d_nover, v.stream); cudaFreeAsync(d_hist, v.stream);
-  cudaFreeAsync(d_prefix, v.stream); cudaFreeAsync(d_kk, v.stream);
+  cudaFreeAsync(d_st, v.stream); cudaFreeAsync(d_lists, v.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
   if (e != cudaSuccess) return gpud_fail(ctx, GPUD_E_CUDA, "reduce_range: %s", cudaGetErrorString(e));
   return GPUD_OK;
