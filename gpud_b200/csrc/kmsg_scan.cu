@@ -706,33 +706,6 @@ __device__ __forceinline__ bool is_sep(const ScanBuf& b, int64_t i, int mode) {
   return mode == GPUD_SCAN_LINES || ld8(b, i + 1) != ' ';
 }
 
-// separators in [from, to): bytes until the address is 4-byte aligned, then whole words with the zero-byte trick
-__device__ unsigned count_seps(const ScanBuf& b, int64_t from, int64_t to, int mode) {
-  unsigned n = 0;
-  int64_t i = from;
-  while (i < to && (((uintptr_t)(b.p + i)) & 3)) { n += is_sep(b, i, mode) ? 1 : 0; ++i; }
-  if (i + 4 <= to) {
-    unsigned w = __ldg(reinterpret_cast<const unsigned*>(b.p + i));
-    for (; i + 4 <= to; i += 4) {
-      const unsigned nxt = (i + 8 <= b.len) ? __ldg(reinterpret_cast<const unsigned*>(b.p + i + 4)) : 0u;
-      unsigned z = zero_bytes(w ^ 0x0a0a0a0au);
-      if (mode == GPUD_SCAN_RAW_KMSG) {
-        unsigned x1 = __funnelshift_r(w, nxt, 8);
-        if (i + 8 > b.len) {                                   // ragged end: fetch the follower bytes one by one
-          x1 = w >> 8;
-          if (i + 4 < b.len) x1 |= (unsigned)__ldg(b.p + i + 4) << 24;
-        }
-        z &= ~zero_bytes(x1 ^ 0x20202020u);
-      }
-      n += __popc(z);
-      w = nxt;
-      if (i + 8 > b.len) { i += 4; break; }
-    }
-  }
-  for (; i < to; ++i) n += is_sep(b, i, mode) ? 1 : 0;
-  return n;
-}
-
 __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const unsigned long long* __restrict__ cands,
                                                      const unsigned long long* __restrict__ n_cand, unsigned long long cand_cap,
                                                      const uint32_t* __restrict__ chunk_local, const unsigned long long* __restrict__ tile_base, const gpud_tables* __restrict__ T,
