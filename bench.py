@@ -295,6 +295,19 @@ def main():
                     "filter_kernel_ms": float(filt), "filter_frac_of_hbm_peak": len(buf) / float(filt) / 1e6 / peaks()[0],
                     "e2e_host_ms": e2e_s * 1e3, "e2e_GBps": len(buf) / e2e_s / 1e9, "cpu_oracle_ms": cpu_s * 1e3, "cpu_oracle_GBps": len(buf) / cpu_s / 1e9,
                     "cpu_threads": coracle.max_threads(), "hits_identical_to_oracle": bool(same and nh2 == len(hits))}
+            # same buffer with the nccl / peermem matchers switched on: four anchor words instead of two in the filter
+            ebuf = synth.ext_buffer(4 << 20, hit_every=1000) * 25
+            d2 = torch.frombuffer(bytearray(ebuf), dtype=torch.uint8).to(dev)
+            ems = []
+            for _ in range(4):
+                ehits, _eu = ctx.kmsg_scan_device(d2.data_ptr(), len(ebuf), mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS, cap=1 << 18, dev=local)
+                ems.append(ctx.scan_kernel_ms(dev=local))
+            ech, _ = coracle.scan_lines(ebuf, ext=True)
+            ef, ep, em = np.array(ems[1:]).mean(axis=0)
+            scan["ext_matchers"] = {"bytes": len(ebuf), "hits": len(ehits), "nccl_hits": sum(h.kind == 3 for h in ehits),
+                                    "peermem_hits": sum(h.kind == 4 for h in ehits), "device_ms": float(ef + ep + em), "filter_kernel_ms": float(ef),
+                                    "hits_identical_to_oracle": [(h.line, h.kind, h.code) for h in ech] == [(h.unit_index, h.kind, h.code) for h in ehits]}
+            del d2
             del d
         except Exception as ex:   # the scan leg must never cost the headline line
             scan = {"error": repr(ex)}

@@ -288,6 +288,17 @@ extern "C" const char* gpud_nvlink_rule_hint(int32_t idx) {
   return h;
 }
 
+extern "C" const char* gpud_kmsg_event_name(int32_t kind) {          // nccl/kmsg_matcher.go:11, peermem/kmsg_matcher.go:13
+  if (kind == GPUD_KIND_NCCL_SEGFAULT) return "nvidia_nccl_segfault_in_libnccl";
+  if (kind == GPUD_KIND_PEERMEM_INVALID_CONTEXT) return "nvidia_peermem_invalid_context";
+  return "";
+}
+extern "C" const char* gpud_kmsg_event_message(int32_t kind) {       // nccl/kmsg_matcher.go:13, peermem/kmsg_matcher.go:15
+  if (kind == GPUD_KIND_NCCL_SEGFAULT) return "NCCL communication error (segfault in libnccl.so)";
+  if (kind == GPUD_KIND_PEERMEM_INVALID_CONTEXT) return "peermem error detected (possible GPU communication issue)";
+  return "";
+}
+
 // xidErrorEventDetail JSON (xid/health_state.go:284-315), field order and omitempty as encoding/json emits them;
 // time is RFC3339 UTC seconds like metav1.Time.
 extern "C" int32_t gpud_hit_detail_json(const gpud_xid_hit* h, int64_t unix_seconds, char* out, int32_t cap) {

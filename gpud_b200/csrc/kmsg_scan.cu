@@ -28,6 +28,9 @@ constexpr int kChunk = 512;                 // bytes per warp step
 constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid ("
 constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVIDIA GPU "
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
+constexpr unsigned long long kFamN = 4ull;  // "segfault at"      (GPUD_SCAN_EXT_MATCHERS: nccl/kmsg_matcher.go:12)
+constexpr unsigned long long kFamP = 5ull;  // "ERROR detected invalid context, skipping further processing"   (peermem/kmsg_matcher.go:14)
+constexpr int kModeMask = 0xff;
 constexpr unsigned kMatchLanes = 16;        // candidates per warp in k_scan_match
 
 struct ScanBuf {
@@ -135,7 +138,33 @@ __device__ __forceinline__ unsigned long long nvrm_family_coop(const ScanBuf& b,
   return (bad1 == 0u || bad2 == 0u) ? kFamB : 0ull;
 }
 
-template <int MODE>
+// extra matchers (GPUD_SCAN_EXT_MATCHERS): four-byte anchor words and the literals the warp verifies behind them
+constexpr unsigned kSegf = 0x66676573u;   // "segf"
+constexpr unsigned kERRO = 0x4f525245u;   // "ERRO"
+__device__ const char kLitSegfault[] = "segfault at";
+__device__ const char kLitLibnccl[] = "in libnccl.so";
+__device__ const char kLitPeermem[] = "ERROR detected invalid context, skipping further processing";
+constexpr int kLenSegfault = 11, kLenLibnccl = 13, kLenPeermem = 59;
+
+// whole warp: does the n-byte literal start at a?  One byte per lane and round.
+__device__ __forceinline__ bool coop_lit(const ScanBuf& b, int64_t a, const char* lit, int n, int lane) {
+  unsigned bad = 0;
+  for (int off = 0; off < n; off += 32) {
+    const int i = off + lane;
+    const int cb = i < n ? ld8(b, a + i) : 0;
+    bad |= __ballot_sync(kFull, i < n && cb != (int)(unsigned char)__ldg(lit + (i < n ? i : 0)));
+  }
+  return bad == 0u;
+}
+// one thread: literal of n bytes at i inside [.., e)
+__device__ __forceinline__ bool lit_at_n(const ScanBuf& b, int64_t i, int64_t e, const char* lit, int n) {
+  if (i + n > e) return false;
+  for (int k = 0; k < n; ++k)
+    if (__ldg(b.p + i + k) != (uint8_t)__ldg(lit + k)) return false;
+  return true;
+}
+
+template <int MODE, bool EXT>
 __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
                                                       unsigned long long* n_cand, unsigned long long cand_cap) {
   const int lane = threadIdx.x & 31;
@@ -178,6 +207,7 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
       for (int k = 0; k < 4; ++k) {
         const unsigned x1 = __funnelshift_r(w[k], w[k + 1], 8), x2 = __funnelshift_r(w[k], w[k + 1], 16), x3 = __funnelshift_r(w[k], w[k + 1], 24);
         hit = hit || w[k] == kNVRM || w[k] == kSXid || x1 == kNVRM || x1 == kSXid || x2 == kNVRM || x2 == kSXid || x3 == kNVRM || x3 == kSXid;
+        if (EXT) hit = hit || w[k] == kSegf || w[k] == kERRO || x1 == kSegf || x1 == kERRO || x2 == kSegf || x2 == kERRO || x3 == kSegf || x3 == kERRO;
         unsigned z = zero_bytes(w[k] ^ 0x0a0a0a0au);                           // '\n'
         if (MODE == GPUD_SCAN_RAW_KMSG) z &= ~zero_bytes(x1 ^ 0x20202020u);     // ... not followed by ' ' (continuation line)
         sepbits |= z >> (k + 4);                                                // bit 7 of each byte -> bit 3-k: four words share one POPC
@@ -201,6 +231,12 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
         const unsigned x = __funnelshift_r(lo, hi, 8 * (k16 & 3));
         const unsigned is_nv = __ballot_sync(kFull, lane < 16 && x == kNVRM);
         unsigned anchors = is_nv | __ballot_sync(kFull, lane < 16 && x == kSXid);
+        unsigned is_sg = 0, is_er = 0;
+        if (EXT) {
+          is_sg = __ballot_sync(kFull, lane < 16 && x == kSegf);
+          is_er = __ballot_sync(kFull, lane < 16 && x == kERRO);
+          anchors |= is_sg | is_er;
+        }
         const int64_t off0 = chunk * kChunk + (int64_t)src * 16;
         while (anchors) {
           const int k = __ffs(anchors) - 1;
@@ -217,6 +253,10 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
             else if (bad & 1u) fam = 0;                                    // not even "NVRM:"
             else if (!is_ws(__shfl_sync(kFull, cb, 1))) fam = 0;          // R3/R4 need \s+ right after the colon
             else fam = nvrm_family_coop(b, a, lane);                      // whitespace run, then "GPU " / "The NVIDIA GPU "
+          } else if (EXT && ((is_sg >> k) & 1u)) {
+            fam = coop_lit(b, a, kLitSegfault, kLenSegfault, lane) ? kFamN : 0ull;
+          } else if (EXT && ((is_er >> k) & 1u)) {
+            fam = coop_lit(b, a, kLitPeermem, kLenPeermem, lane) ? kFamP : 0ull;
           }
           if (fam && lane == 0) {
             const unsigned long long slot = atomicAdd(n_cand, 1ull);
@@ -756,6 +796,47 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
       ms = semi + 1;
       if (a < ms) continue;
     }
+    if (fam == kFamN || fam == kFamP) {                  // extra matchers: literal-only patterns, `.` never crosses '\n'
+      const bool is_n = fam == kFamN;
+      const char* lit = is_n ? kLitSegfault : kLitPeermem;
+      const int ln = is_n ? kLenSegfault : kLenPeermem;
+      const unsigned c0 = is_n ? 's' : 'E';
+      bool first_ext = true;                               // one hit per unit: its first anchor looks at every later one
+      for (int64_t i = find_byte(b, ms, a, c0); i < a && first_ext; i = find_byte(b, i + 1, a, c0))
+        if (lit_at_n(b, i, ue, lit, ln)) first_ext = false;
+      if (!first_ext) continue;
+      bool ok_ext = !is_n;
+      if (is_n) {
+        // `.*segfault at.*in libnccl\.so.*`: both literals inside one '\n'-free segment, the second starting after the first ends
+        int64_t p = a;
+        while (p < ue && !ok_ext) {
+          const int64_t seg_e = find_byte(b, p, ue, '\n');
+          for (int64_t j = find_byte(b, p + kLenSegfault, seg_e, 'i'); j < seg_e && !ok_ext; j = find_byte(b, j + 1, seg_e, 'i'))
+            if (lit_at_n(b, j, seg_e, kLitLibnccl, kLenLibnccl)) ok_ext = true;
+          if (ok_ext) break;
+          p = seg_e + 1;                                   // next segment of the record: its first "segfault at"
+          for (;;) {
+            p = find_byte(b, p, ue, 's');
+            if (p >= ue || lit_at_n(b, p, ue, kLitSegfault, kLenSegfault)) break;
+            ++p;
+          }
+        }
+      }
+      if (!ok_ext) continue;
+      gpud_xid_hit h;
+      memset(&h, 0, sizeof h);
+      h.kind = is_n ? GPUD_KIND_NCCL_SEGFAULT : GPUD_KIND_PEERMEM_INVALID_CONTEXT;
+      h.event_type = GPUD_EVENT_WARNING;                   // pkg/kmsg/syncer.go:94
+      h.n_actions = -1;
+      h.rule_index = -1;
+      h.unit_offset = us;
+      h.kmsg_priority = (int32_t)k_prio;
+      h.kmsg_seq = k_seq;
+      h.kmsg_usec = k_usec;
+      const unsigned long long slot = atomicAdd(n_hits, 1ull);
+      if (slot < hit_cap) hits[slot] = h;
+      continue;
+    }
     // only the first anchor of this family group in the unit does the work
     bool first = true;
     if (fam == kFamS) {
@@ -806,6 +887,7 @@ __global__ void k_classify(const gpud_tables* __restrict__ T, gpud_xid_hit* hits
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   gpud_xid_hit h = hits[i];
+  if (h.kind != GPUD_KIND_XID && h.kind != GPUD_KIND_SXID) return;   // the extra matchers carry no catalog detail
   h.unit_name[39] = 0;
   bool ok;
   if (h.kind == GPUD_KIND_SXID) ok = classify_sxid(T, &h);
@@ -876,6 +958,11 @@ static cudaError_t grow(T** p, size_t* cap, size_t need) {
   return e;
 }
 
+static bool scan_mode_ok(int32_t mode) {
+  const int32_t base = mode & ~GPUD_SCAN_EXT_MATCHERS;
+  return base == GPUD_SCAN_LINES || base == GPUD_SCAN_RAW_KMSG;
+}
+
 static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_buf, int64_t len, int32_t mode, int64_t hit_cap_req,
                            cudaStream_t st) {
   const int64_t n_chunks = std::max<int64_t>(1, (len + kChunk - 1) / kChunk);
@@ -896,10 +983,14 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   ScanBuf b{d_buf, len};
   const int grid_f = (int)std::min<int64_t>((n_chunks + 31) / 32, (int64_t)ctx->sm_count * 8);   // 8 warps x 4 chunks per block step
   cudaEventRecord(s->ev[0], st);
-  if (mode == GPUD_SCAN_LINES)
-    k_scan_filter<GPUD_SCAN_LINES><<<std::max(grid_f, 1), 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap);
-  else
-    k_scan_filter<GPUD_SCAN_RAW_KMSG><<<std::max(grid_f, 1), 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap);
+  const bool ext = (mode & GPUD_SCAN_EXT_MATCHERS) != 0;
+  mode &= kModeMask;
+  const int grid = std::max(grid_f, 1);
+  const unsigned long long ccap = (unsigned long long)s->cand_cap;
+  if (mode == GPUD_SCAN_LINES && !ext) k_scan_filter<GPUD_SCAN_LINES, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
+  else if (mode == GPUD_SCAN_LINES) k_scan_filter<GPUD_SCAN_LINES, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
+  else if (!ext) k_scan_filter<GPUD_SCAN_RAW_KMSG, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
+  else k_scan_filter<GPUD_SCAN_RAW_KMSG, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[1], st);
   k_scan_prefix_tiles<<<(unsigned)n_tiles, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_local, n_chunks, s->d_tile_base);
@@ -942,7 +1033,7 @@ static int32_t scan_collect(gpud_ctx* ctx, gpud_scan_state* s, gpud_xid_hit* hit
 
 extern "C" int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8_t* dev_buf, int64_t len, int32_t mode, gpud_xid_hit* hits,
                                          int64_t cap, int64_t* n_hits, int64_t* n_units, void* cuda_stream) {
-  if (!ctx || len < 0 || (len && !dev_buf) || cap < 0 || (mode != GPUD_SCAN_LINES && mode != GPUD_SCAN_RAW_KMSG)) return GPUD_E_INVALID;
+  if (!ctx || len < 0 || (len && !dev_buf) || cap < 0 || !scan_mode_ok(mode)) return GPUD_E_INVALID;
   gpud_scan_state* s;
   int32_t rc = scan_state_get(ctx, dev, &s);
   if (rc) return rc;
@@ -954,7 +1045,7 @@ extern "C" int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8
 
 extern "C" int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf, int64_t len, int32_t mode, gpud_xid_hit* hits, int64_t cap,
                                   int64_t* n_hits, int64_t* n_units) {
-  if (!ctx || len < 0 || (len && !buf) || cap < 0 || (mode != GPUD_SCAN_LINES && mode != GPUD_SCAN_RAW_KMSG)) return GPUD_E_INVALID;
+  if (!ctx || len < 0 || (len && !buf) || cap < 0 || !scan_mode_ok(mode)) return GPUD_E_INVALID;
   gpud_scan_state* s;
   int32_t rc = scan_state_get(ctx, dev, &s);
   if (rc) return rc;

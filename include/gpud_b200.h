@@ -107,7 +107,11 @@ int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64,
 enum { GPUD_SCAN_LINES = 0,   /* units are '\n'-separated lines (strings.Split(buf, "\n"))                  */
        GPUD_SCAN_RAW_KMSG = 1 /* units are /dev/kmsg records "prio,seq,usec,flags;msg" (+ " KEY=val" lines);
                                  Match runs on the message part (pkg/kmsg/watcher.go:292-332)               */ };
-enum { GPUD_KIND_XID = 1, GPUD_KIND_SXID = 2 };
+/* OR into `mode`: also run the next kmsg matchers of the reference on every unit:
+ *   nccl     `.*segfault at.*in libnccl\.so.*`            components/accelerator/nvidia/nccl/kmsg_matcher.go:12
+ *   peermem  `.*ERROR detected invalid context, skipping further processing`   .../peermem/kmsg_matcher.go:14 */
+#define GPUD_SCAN_EXT_MATCHERS 0x100
+enum { GPUD_KIND_XID = 1, GPUD_KIND_SXID = 2, GPUD_KIND_NCCL_SEGFAULT = 3, GPUD_KIND_PEERMEM_INVALID_CONTEXT = 4 };
 enum { GPUD_EVENT_UNKNOWN = 0, GPUD_EVENT_INFO = 1, GPUD_EVENT_WARNING = 2, GPUD_EVENT_CRITICAL = 3, GPUD_EVENT_FATAL = 4 };
 enum { GPUD_ACT_IGNORE_NO_ACTION_REQUIRED = 1, GPUD_ACT_REBOOT_SYSTEM = 2, GPUD_ACT_HARDWARE_INSPECTION = 3,
        GPUD_ACT_CHECK_USER_APP_AND_GPU = 4 };
@@ -176,6 +180,9 @@ const char* gpud_xid_description(int32_t code, int32_t detail_variant);
 const char* gpud_xid_mnemonic(int32_t code);
 const char* gpud_sxid_name(int32_t code);
 const char* gpud_nvlink_rule_hint(int32_t rule_index);
+/* kmsg.MatchFunc results (eventName, message) of the extra matchers, by hit kind; "" for xid / sxid kinds. */
+const char* gpud_kmsg_event_name(int32_t kind);
+const char* gpud_kmsg_event_message(int32_t kind);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-box NVLink / fabric view.

@@ -60,11 +60,18 @@ def sxid_match(line: bytes):
     return h if L.orc_sxid_match(line, C.c_int32(len(line)), C.byref(h)) else None
 
 
-def scan_lines(buf: bytes, threads: int = 0, cap: int = 1 << 20):
+def ext_match(line: bytes) -> int:
+    """bit 0 = nccl segfault-in-libnccl matcher, bit 1 = peermem invalid-context matcher."""
+    L = lib()
+    L.orc_ext_match.restype = C.c_int32
+    return L.orc_ext_match(line, C.c_int32(len(line)))
+
+
+def scan_lines(buf: bytes, threads: int = 0, cap: int = 1 << 20, ext: bool = False):
     """Returns (hits list of OrcHit, n_lines) for the reference's split-on-newline scan form."""
     L = lib()
-    L.orc_scan_lines.restype = C.c_int64
+    L.orc_scan_lines_ext.restype = C.c_int64
     hits = (OrcHit * cap)()
     nl = C.c_int64()
-    n = L.orc_scan_lines(buf, C.c_int64(len(buf)), hits, C.c_int64(cap), C.byref(nl), C.c_int32(threads))
+    n = L.orc_scan_lines_ext(buf, C.c_int64(len(buf)), hits, C.c_int64(cap), C.byref(nl), C.c_int32(threads), C.c_int32(1 if ext else 0))
     return [hits[i] for i in range(min(n, cap))], nl.value

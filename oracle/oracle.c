@@ -136,16 +136,19 @@ void orc_windows_fields(const double* ring, int32_t F, int64_t n, int32_t W, con
 #include "../gpud_b200/csrc/catalog_data.inc"   /* DATA ONLY: generated tables (tools/gen_catalog.py) */
 
 /* components/accelerator/nvidia/xid/kmsg.go:22,29,38,43 ; sxid/kmsg.go:17,20 — verbatim */
-static const char* RX[6] = {
+static const char* RX[8] = {
     "NVRM: Xid \\(((?:PCI:)?[0-9a-fA-F:]+)\\).*?: (\\d+),",
     "NVRM: Xid \\(PCI:([0-9a-fA-F:]+)\\): (\\d+)(?:, pid=(\\d+), name=([^,]+))?, ([A-Z_]+(?:/[A-Z_]+)?)\\s+(Nonfatal|Fatal)\\s+(XC[01])\\s+(i\\d+)\\s+Link\\s+(-?\\d+)\\s+\\((0x[0-9a-fA-F]+)\\s+(0x[0-9a-fA-F]+)(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?",
     "(?s)NVRM:\\s+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\\.0.*?fallen off the bus and is not responding to commands\\.",
     "NVRM:\\s+GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\\.0:\\s+GPU has fallen off the bus\\.?",
     "SXid.*?: (\\d+),",
-    "SXid \\((PCI:[0-9a-fA-F:\\.]+)\\)"};
-static orx_prog* PR[6];
+    "SXid \\((PCI:[0-9a-fA-F:\\.]+)\\)",
+    /* next matchers on the same scanner: nccl/kmsg_matcher.go:12 ; peermem/kmsg_matcher.go:14 — verbatim */
+    ".*segfault at.*in libnccl\\.so.*",
+    ".*ERROR detected invalid context, skipping further processing"};
+static orx_prog* PR[8];
 static pthread_once_t rx_once = PTHREAD_ONCE_INIT;
-static void rx_init(void) { for (int i = 0; i < 6; ++i) PR[i] = orx_compile(RX[i]); }
+static void rx_init(void) { for (int i = 0; i < 8; ++i) PR[i] = orx_compile(RX[i]); }
 int32_t orc_regex_ok(void) {
   pthread_once(&rx_once, rx_init);
   for (int i = 0; i < 6; ++i) if (!PR[i]) return 0;
@@ -257,9 +260,20 @@ int32_t orc_sxid_match(const char* s, int32_t n, orc_hit* h) {
   return 1;
 }
 
+/* HasNCCLSegfaultInLibnccl / HasPeermemInvalidContext (nccl/kmsg_matcher.go:20-25, peermem/kmsg_matcher.go:22-27):
+ * bit 0 = nccl segfault, bit 1 = peermem invalid context. */
+int32_t orc_ext_match(const char* s, int32_t n) {
+  pthread_once(&rx_once, rx_init);
+  int c[4];
+  int32_t m = 0;
+  if (orx_search(PR[6], s, n, c)) m |= 1;
+  if (orx_search(PR[7], s, n, c)) m |= 2;
+  return m;
+}
+
 /* The reference's buffer-scan form: split on '\n', Match each line (xid/kmsg_test.go:252-267), parallel over byte ranges
  * cut at line boundaries.  Returns the number of hits (may exceed cap; only the first cap are stored, in line order). */
-typedef struct { const char* buf; int64_t b, e; orc_hit* hits; int64_t n, cap, lines; } orc_scan_part;
+typedef struct { const char* buf; int64_t b, e; orc_hit* hits; int64_t n, cap, lines; int32_t ext; } orc_scan_part;
 static void orc_scan_one(void* a, int64_t idx) {
   orc_scan_part* P = (orc_scan_part*)a + idx;
   int64_t ls = P->b, line = 0;
@@ -272,6 +286,17 @@ static void orc_scan_one(void* a, int64_t idx) {
         if (orc_xid_match(P->buf + ls, n, &h)) { h.line = line; h.offset = ls; if (P->n < P->cap) P->hits[P->n] = h; ++P->n; }
         if (orc_sxid_match(P->buf + ls, n, &h)) { h.line = line; h.offset = ls; if (P->n < P->cap) P->hits[P->n] = h; ++P->n; }
       }
+      if (P->ext && n >= 11 && (memmem(P->buf + ls, (size_t)n, "segfault at", 11) || memmem(P->buf + ls, (size_t)n, "ERROR detected", 14))) {
+        const int32_t m = orc_ext_match(P->buf + ls, n);
+        for (int k = 0; k < 2; ++k)
+          if (m & (1 << k)) {
+            orc_hit h;
+            memset(&h, 0, sizeof h);
+            h.kind = 3 + k; h.line = line; h.offset = ls;   /* event type Warning is fixed by pkg/kmsg/syncer.go:94 */
+            if (P->n < P->cap) P->hits[P->n] = h;
+            ++P->n;
+          }
+      }
       ls = i + 1;
       if (i < P->e) ++line;
     }
@@ -279,7 +304,11 @@ static void orc_scan_one(void* a, int64_t idx) {
   P->lines = line;   /* newlines inside [b, e) */
 }
 
+int64_t orc_scan_lines_ext(const char* buf, int64_t len, orc_hit* hits, int64_t cap, int64_t* n_lines, int32_t threads, int32_t ext);
 int64_t orc_scan_lines(const char* buf, int64_t len, orc_hit* hits, int64_t cap, int64_t* n_lines, int32_t threads) {
+  return orc_scan_lines_ext(buf, len, hits, cap, n_lines, threads, 0);
+}
+int64_t orc_scan_lines_ext(const char* buf, int64_t len, orc_hit* hits, int64_t cap, int64_t* n_lines, int32_t threads, int32_t ext) {
   if (threads <= 0) threads = orc_max_threads();
   int parts = threads * 4;
   if (parts > 1024) parts = 1024;
@@ -291,7 +320,7 @@ int64_t orc_scan_lines(const char* buf, int64_t len, orc_hit* hits, int64_t cap,
     if (e < b) e = b;
     while (e < len && buf[e] != '\n') ++e;       /* cut at a newline: the part is [b, e], the newline at e belongs to it */
     if (e < len && i != parts - 1) ++e;
-    P[i].buf = buf; P[i].b = b; P[i].e = e; P[i].cap = cap;
+    P[i].buf = buf; P[i].b = b; P[i].e = e; P[i].cap = cap; P[i].ext = ext;
     P[i].hits = (orc_hit*)malloc((size_t)(cap > 0 ? cap : 1) * sizeof(orc_hit));
     b = e;
   }

@@ -39,6 +39,9 @@ R3 = re.compile(rb"(?s)NVRM:[\t\n\f\r ]+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9
 R4 = re.compile(rb"NVRM:[\t\n\f\r ]+GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\.0:[\t\n\f\r ]+GPU has fallen off the bus\.?")
 R5 = re.compile(rb"SXid.*?: (\d+),")
 R6 = re.compile(rb"SXid \((PCI:[0-9a-fA-F:\.]+)\)")
+# next matchers riding the same scanner: nccl/kmsg_matcher.go:12, peermem/kmsg_matcher.go:14 (verbatim)
+R_NCCL = re.compile(rb".*segfault at.*in libnccl\.so.*")
+R_PEERMEM = re.compile(rb".*ERROR detected invalid context, skipping further processing")
 # NOTE: Go/RE2 `\s` is [\t\n\f\r ] (no \v); Python bytes `\s` also matches \v, hence the explicit class.
 
 INT64_MAX = (1 << 63) - 1
@@ -448,7 +451,18 @@ def sxid_match(line: bytes):                                          # sxid/kms
     return {"sxid": code, "device": extract_sxid_device(line), "detail": d}
 
 
-def scan_lines(buf: bytes):
+def ext_match(line: bytes):
+    """kinds of the extra matchers that fire on this line: 3 = nccl segfault, 4 = peermem invalid context
+    (nccl/kmsg_matcher.go:20-35, peermem/kmsg_matcher.go:22-37: FindStringSubmatch != nil)."""
+    out = []
+    if R_NCCL.search(line):
+        out.append(3)
+    if R_PEERMEM.search(line):
+        out.append(4)
+    return out
+
+
+def scan_lines(buf: bytes, ext: bool = False):
     """The reference's buffer-scan form: split on '\\n', Match each line (xid/kmsg_test.go:252-267).
     Returns hit dicts in (line, kind) order; kind 1 = xid, 2 = sxid."""
     hits = []
@@ -469,6 +483,10 @@ def scan_lines(buf: bytes):
                          "event_type": s["detail"]["event_type"], "actions": s["detail"]["actions"],
                          "extended": False, "sub_code": 0, "unit": "", "error_status": 0, "intrinfo": 0, "link": 0,
                          "hint": "", "description": ""})
+        if ext:
+            for kind in ext_match(line):
+                hits.append({"line": ln, "offset": off, "kind": kind, "code": 0, "device": "", "event_type": EV_WARNING, "actions": [],
+                             "extended": False, "sub_code": 0, "unit": "", "error_status": 0, "intrinfo": 0, "link": 0, "hint": "", "description": ""})
         off += len(line) + 1
     return hits
 
@@ -606,7 +624,7 @@ def window_aggregates(x: np.ndarray, W: int, thr: float, alpha: float = 0.0, q_n
 # --------------------------------------------------------------------------------------------
 
 
-def scan_raw_kmsg(buf: bytes):
+def scan_raw_kmsg(buf: bytes, ext: bool = False):
     """Buffer of concatenated /dev/kmsg records (a record continues on lines that start with ' ').  Each record goes
     through parseLine (records that fail to parse are skipped, pkg/kmsg/watcher.go:161-165) and Match runs on the
     message part (xid/component.go:274-299)."""
@@ -630,6 +648,10 @@ def scan_raw_kmsg(buf: bytes):
             hits.append({"line": idx, "offset": off, "kind": 2, "code": s["sxid"], "device": s["device"],
                          "event_type": s["detail"]["event_type"], "actions": s["detail"]["actions"], "kmsg": (prio, seq, usec),
                          "extended": False, "sub_code": 0, "error_status": 0})
+        if ext:
+            for kind in ext_match(m):
+                hits.append({"line": idx, "offset": off, "kind": kind, "code": 0, "device": "", "event_type": EV_WARNING, "actions": [],
+                             "kmsg": (prio, seq, usec), "extended": False, "sub_code": 0, "error_status": 0})
         off += len(rec) + 1
     return hits, len(recs)
 

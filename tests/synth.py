@@ -87,6 +87,46 @@ EDGE_LINES = [
 ]
 
 
+def ext_lines():
+    """every line of the nccl / peermem matcher tables of the reference (tests/golden/ext_kmsg.json)"""
+    G = golden("ext_kmsg.json")
+    out = []
+    for k in ("nccl_has", "nccl_match", "peermem_has", "peermem_match"):
+        out += [r["line"] for r in G[k]["rows"]]
+    return out
+
+
+PEERMEM_LIT = "ERROR detected invalid context, skipping further processing"
+EXT_EDGE_LINES = [
+    "segfault atin libnccl.so",                                   # `.*` may be empty
+    "segfault at in libnccl.s",                                   # literal cut short
+    "segfault at 0 in libnccl_so",                                # `\.` is a literal dot
+    "in libnccl.so then segfault at 0",                           # wrong order
+    "in libnccl.so segfault at 0 ip 1 in libnccl.so.2",           # second library mention counts
+    "segfault at 1 in libcuda.so segfault at 2 in libnccl.so",    # two anchors, one line
+    "segfault a", "segf", "segfault", "xsegfault at y in libnccl.so.",
+    "ERROR detected invalid context, skipping further processin",
+    "ERRO", "ERROR detected", "ERROR detected invalid context, skipping further processing and more text",
+    PEERMEM_LIT + " " + PEERMEM_LIT,
+    "NVRM: Xid (PCI:0000:05:00): 79, pid=1, GPU has fallen off the bus. segfault at 0 in libnccl.so " + PEERMEM_LIT,
+    "nvswitch0: SXid (PCI:0000:c1:00.0): 12028, Non-fatal, " + PEERMEM_LIT,
+    "segfault at" + " " * 300 + "in libnccl.so",                  # literals more than one chunk row apart
+    "s" * 40 + "egfault at in libnccl.so",
+]
+
+
+def ext_buffer(n_bytes: int, seed: int = SEED, hit_every: int = 50):
+    """dmesg_buffer with the extra matchers' lines and decoys mixed in"""
+    base = dmesg_buffer(n_bytes, seed, hit_every).split(b"\n")
+    ext = [l.encode() for l in ext_lines() + EXT_EDGE_LINES]
+    out = []
+    for i, l in enumerate(base):
+        out.append(l)
+        if i % 37 == 5:
+            out.append(ext[(i // 37) % len(ext)])
+    return b"\n".join(out)
+
+
 def dmesg_buffer(n_bytes: int, seed: int = SEED, hit_every: int = 1000):
     """~n_bytes of log text: the reference's fixture lines + noise + decoys, with one hit-line per ~hit_every lines."""
     rng = np.random.default_rng(seed)

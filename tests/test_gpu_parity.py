@@ -104,6 +104,45 @@ def test_scan_edges(ctx, buf):
     _cmp_hits(hits, want)
 
 
+def test_scan_ext_matchers(ctx):
+    """GPUD_SCAN_EXT_MATCHERS: nccl / peermem matchers ride the same scan; default mode is unaffected"""
+    lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:40]
+    for buf in ("\n".join(lines).encode(), synth.ext_buffer(2_000_000, hit_every=60)):
+        hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS)
+        want = O.scan_lines(buf, ext=True)
+        assert n_units == buf.count(b"\n") + 1
+        assert sum(h["kind"] == 3 for h in want) >= 8 and sum(h["kind"] == 4 for h in want) >= 8
+        _cmp_hits(hits, want)
+        _cmp_hits(ctx.kmsg_scan(buf)[0], O.scan_lines(buf))
+    for l in lines:                                   # every vector as its own buffer
+        _cmp_hits(ctx.kmsg_scan(l.encode(), mode=g.SCAN_EXT_MATCHERS)[0], O.scan_lines(l.encode(), ext=True))
+    import gpud_b200.capi as capi
+    L = capi.lib()
+    G = synth.golden("ext_kmsg.json")["constants"]
+    assert L.gpud_kmsg_event_name(3).decode() == G["nccl"]["event"] and L.gpud_kmsg_event_message(3).decode() == G["nccl"]["message"]
+    assert L.gpud_kmsg_event_name(4).decode() == G["peermem"]["event"] and L.gpud_kmsg_event_message(4).decode() == G["peermem"]["message"]
+
+
+def test_scan_ext_matchers_raw_mode(ctx):
+    recs = []
+    ext = synth.ext_lines() + synth.EXT_EDGE_LINES
+    for i, l in enumerate(ext):
+        recs.append("%d,%d,%d,-;%s" % (i % 8, 100 + i, 1000 * i, l))
+        if i % 3 == 0:
+            recs.append(" SUBSYSTEM=pci\n DEVICE=+pci:0000:05:00.0")
+        if i % 5 == 0:                                   # the two nccl literals split over a continuation line: `.` stops at \n
+            recs.append("4,%d,%d,-;x segfault at 0\n in libnccl.so" % (900 + i, i))
+            recs.append("4,%d,%d,-;y segfault at 0\n segfault at 1 in libnccl.so" % (950 + i, i))
+    buf = "\n".join(recs).encode()
+    hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_RAW_KMSG | g.SCAN_EXT_MATCHERS)
+    want, n_rec = O.scan_raw_kmsg(buf, ext=True)
+    assert n_units == n_rec
+    assert sum(h["kind"] == 3 for h in want) >= 8 and sum(h["kind"] == 4 for h in want) >= 8
+    _cmp_hits(hits, want)
+    for a, b in zip(hits, want):
+        assert (a.kmsg_priority, a.kmsg_seq, a.kmsg_usec) == b["kmsg"]
+
+
 def test_scan_ragged_offsets(ctx):
     """hit lines at every alignment relative to the 16-byte / 512-byte / 2048-byte load boundaries"""
     line = b"NVRM: Xid (PCI:0000:05:00): 79, GPU has fallen off the bus.\n"

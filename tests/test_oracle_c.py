@@ -91,3 +91,26 @@ def test_windows_c_equals_python():
                 assert np.array_equal(c[k][f].view(np.uint64), w[k].view(np.uint64)), (W, k, f)
             assert np.array_equal(c["n_over"][f].astype(np.uint64), w["n_over"])
             assert np.allclose(c["mean"][f], w["mean"], rtol=1e-12, atol=0) and np.allclose(c["ema"][f], w["ema"], rtol=1e-9, atol=0)
+
+
+def test_ext_matchers_golden_and_python(golden):   # nccl/kmsg_matcher_test.go:5,67 ; peermem/kmsg_matcher_test.go:5,62
+    G = golden("ext_kmsg.json")
+    for r in G["nccl_has"]["rows"]:
+        assert bool(CO.ext_match(r["line"].encode()) & 1) == r["want"], r
+    for r in G["peermem_has"]["rows"]:
+        assert bool(CO.ext_match(r["line"].encode()) & 2) == r["want"], r
+    for l in synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:50]:
+        b = l.encode()
+        want = sum(1 << (k - 3) for k in O.ext_match(b))
+        assert CO.ext_match(b) == want, l
+
+
+def test_c_ext_scan_equals_python_scan():
+    buf = synth.ext_buffer(300_000, hit_every=40)
+    ch, nl = CO.scan_lines(buf, ext=True)
+    ph = O.scan_lines(buf, ext=True)
+    assert nl == buf.count(b"\n") + 1
+    assert [(h.line, h.kind, h.code, h.offset) for h in ch] == [(h["line"], h["kind"], h["code"], h["offset"]) for h in ph]
+    assert sum(h.kind == 3 for h in ch) >= 10 and sum(h.kind == 4 for h in ch) >= 10
+    # the default scan is unchanged by the extra lines
+    assert [(h.line, h.kind) for h in CO.scan_lines(buf)[0]] == [(h["line"], h["kind"]) for h in O.scan_lines(buf)]

@@ -152,3 +152,15 @@ def test_parse_kmsg_line(golden):                  # pkg/kmsg/watcher_test.go (T
         assert (prio, seq, msg) == (e["Priority"], e["SequenceNumber"], e["Message"]), r["name"]
         m = re.search(r"bootTime\.Add\((\d+)\*time\.Microsecond", e["Timestamp"]["$call"])
         assert ts == (int(m.group(1)) if m else 0), r["name"]          # metav1.NewTime(bootTime) == +0us
+
+
+def test_ext_matchers(golden):                     # nccl/kmsg_matcher_test.go:5,67 ; peermem/kmsg_matcher_test.go:5,62
+    G = golden("ext_kmsg.json")
+    for r in G["nccl_has"]["rows"]:
+        assert (3 in O.ext_match(r["line"].encode())) == r["want"], r
+    for r in G["nccl_match"]["rows"]:
+        assert (3 in O.ext_match(r["line"].encode())) == bool(r["wantName"]), r
+    for r in G["peermem_has"]["rows"]:
+        assert (4 in O.ext_match(r["line"].encode())) == r["want"], r
+    for r in G["peermem_match"]["rows"]:
+        assert (4 in O.ext_match(r["line"].encode())) == bool(r["wantName"]), r

@@ -298,6 +298,20 @@ def main():
             k["fixture:" + fx] = {"src": K + "testdata/" + fx, "rows": [],
                                   "records": open(p, encoding="utf-8", errors="surrogateescape").read().split("\n")}
     dump("pkg_kmsg.json", k)
+
+    # the next kmsg matchers that ride the same scanner
+    N = "components/accelerator/nvidia/"
+    ext = {}
+    for key, path, fn in [("nccl_has", N + "nccl/kmsg_matcher_test.go", "TestHasNCCLSegfaultInLibnccl"),
+                          ("nccl_match", N + "nccl/kmsg_matcher_test.go", "TestMatch"),
+                          ("peermem_has", N + "peermem/kmsg_matcher_test.go", "TestHasPeermemInvalidContext"),
+                          ("peermem_match", N + "peermem/kmsg_matcher_test.go", "TestMatch")]:
+        rows, src = table(path, fn)
+        ext[key] = {"src": src, "rows": ident(rows)}
+    ext["constants"] = {"src": N + "nccl/kmsg_matcher.go:11-13 ; " + N + "peermem/kmsg_matcher.go:13-15", "rows": [],
+                        "nccl": {"event": "nvidia_nccl_segfault_in_libnccl", "message": "NCCL communication error (segfault in libnccl.so)"},
+                        "peermem": {"event": "nvidia_peermem_invalid_context", "message": "peermem error detected (possible GPU communication issue)"}}
+    dump("ext_kmsg.json", ext)
     return 0
 
 
