@@ -148,22 +148,39 @@ __device__ __forceinline__ void warp_sort_desc_k64(unsigned& hi, unsigned& lo, i
   }
 }
 
-// Candidates sit in shared memory s[0..cnt), cnt <= 32.  Returns the k-th largest (k <= cnt) and the maximum.
+// rank -= (o > c) for 64-bit keys given as (hi, lo) halves: one borrow chain, no predicates
+__device__ __forceinline__ void count_gt_k64_neg(unsigned& acc, unsigned oh, unsigned ol, unsigned ch, unsigned cl) {
+  unsigned t;
+  asm("sub.cc.u32 %1, %2, %3;\n\tsubc.cc.u32 %1, %4, %5;\n\tsubc.u32 %0, %0, 0;" : "+r"(acc), "=r"(t) : "r"(cl), "r"(ol), "r"(ch), "r"(oh));
+}
+// Keys are parked with the RAW low word (pass 1 transforms only the high word): true low word = lo ^ ~sign-extension of
+// key-hi bit 31 (set for non-negative doubles, whose totalOrder key keeps the low word as is).
+__device__ __forceinline__ unsigned true_lo(unsigned key_hi, unsigned raw_lo) { return raw_lo ^ ~(unsigned)((int)key_hi >> 31); }
+__device__ __forceinline__ unsigned long long true_key(unsigned long long stored) {
+  const unsigned hi = (unsigned)(stored >> 32);
+  return ((unsigned long long)hi << 32) | true_lo(hi, (unsigned)stored);
+}
+constexpr unsigned long long kPadStored = 0x00000000ffffffffull;   // stored form of the smallest key 0 (hi 0, raw lo ~0)
+
+// Candidates sit in shared memory s[0..cnt), cnt <= 32, in STORED form.  Returns the k-th largest (k <= cnt) and the maximum.
 // rank_i = #{j : c_j > c_i};  the k-th largest is the smallest candidate whose rank is < k.
-__device__ __forceinline__ K64 select_from_candidates(const uint2* s, int cnt, int k, int lane, K64* mx) {
+__device__ __forceinline__ K64 select_from_candidates(uint2* s, int cnt, int k, int lane, K64* mx) {
   const bool mine = lane < cnt;
-  const uint2 c = mine ? s[lane] : make_uint2(0u, 0u);      // .x = lo, .y = hi
-  int rank = 0;
+  uint2 c = mine ? s[lane] : make_uint2(0u, 0u);            // .x = lo, .y = hi
+  c.x = true_lo(c.y, c.x);
+  if (mine) s[lane] = c;                                     // the broadcast reads below see true keys
+  __syncwarp();
+  unsigned neg_rank = 0;
 #pragma unroll 1
   for (int j = 0; j < cnt; j += 4) {                         // the list is zero-padded to a multiple of 4; a zero never outranks
     const uint4 o01 = *reinterpret_cast<const uint4*>(s + j), o23 = *reinterpret_cast<const uint4*>(s + j + 2);   // broadcast LDS.128
-    rank += k_gt(o01.y, o01.x, c.y, c.x) ? 1 : 0;
-    rank += k_gt(o01.w, o01.z, c.y, c.x) ? 1 : 0;
-    rank += k_gt(o23.y, o23.x, c.y, c.x) ? 1 : 0;
-    rank += k_gt(o23.w, o23.z, c.y, c.x) ? 1 : 0;
+    count_gt_k64_neg(neg_rank, o01.y, o01.x, c.y, c.x);
+    count_gt_k64_neg(neg_rank, o01.w, o01.z, c.y, c.x);
+    count_gt_k64_neg(neg_rank, o23.y, o23.x, c.y, c.x);
+    count_gt_k64_neg(neg_rank, o23.w, o23.z, c.y, c.x);
   }
   *mx = warp_max_k64(mine ? c.y : 0u, mine ? c.x : 0u);
-  const bool in = mine && rank < k;
+  const bool in = mine && (int)(0u - neg_rank) < k;
   return warp_min_k64(in ? c.y : 0xffffffffu, in ? c.x : 0xffffffffu);
 }
 
@@ -179,40 +196,62 @@ __device__ __forceinline__ K64 select_from_candidates(const uint2* s, int cnt, i
 // (m == W), so the pair loop is straight-line code.  JF = -1: everything is decided at run time (any W, partial windows).
 // ---------------------------------------------------------------------------------------------
 constexpr int kRowU64 = 34;                                   // 32 keys + 2 pad -> 272-byte rows
-constexpr int kWarpSmemBytes = 32 * kRowU64 * 8 + (kCandMax + 4) * 8 + 32 + 16;   // key rows, candidates (+pad), row list, counter
+constexpr int kKeyBytes = 32 * kRowU64 * 8;                   // key rows
+constexpr int kPadRowOff = kKeyBytes;                         // 256 B of kPadStored: the row the padded tail of the row list points at
+constexpr int kCandOff = kPadRowOff + 256;                    // candidates (+4 pad slots)
+constexpr int kRowListOff = kCandOff + (kCandMax + 4) * 8;    // byte offsets of the flagged rows, 32 + 4 pad entries
+constexpr int kCntOff = kRowListOff + 36 * 4;
+constexpr int kWarpSmemBytes = kCntOff + 16;
 constexpr int kBlockSmemBytes = kWarpsPerBlock * kWarpSmemBytes;
 
 __device__ __forceinline__ int elem_index(int row, int col) { return 64 * (col >> 1) + 2 * row + (col & 1); }   // chronological t
 
-// Append the keys of the flagged rows that are > (Lh, Ll) to cand[] (any order).  The flagged row ids are first packed
-// into cand's tail; then one LDS per row gives every lane one key of that row, and the few lanes that hold a hit claim a
-// slot with a shared-memory atomic.  Returns the number of hits (may exceed kCandMax; only the first kCandMax are stored).
-__device__ __forceinline__ int gather_above(const unsigned long long* sk, unsigned rows, unsigned Lh, unsigned Ll, uint2* cand, int* s_cnt,
-                                            int lane, unsigned lt_mask) {
+// Append the keys of the flagged rows that pass the bound to cand[] (any order, STORED form).  HI_ONLY: keys whose high
+// word is >= Lh (one compare; the fast path's bound is (Lh, 0), inclusive).  Otherwise: true keys > (Lh, Ll).
+// The flagged rows' byte offsets are packed into a list first (padded to a multiple of four with the pad row); then one LDS
+// per row gives every lane one key of that row and the few lanes that hold a hit claim a slot with a predicated
+// shared-memory atomic - straight-line code, four rows in flight per trip.
+// Returns the number of hits (may exceed kCandMax; only the first kCandMax are stored).
+template <bool HI_ONLY>
+__device__ __forceinline__ int gather_rows(unsigned char* wbase, unsigned rows, unsigned Lh, unsigned Ll, int lane, unsigned lt_mask) {
   const int n_rows = __popc(rows);
-  unsigned char* row_list = reinterpret_cast<unsigned char*>(cand + kCandMax + 4);   // 32 bytes after the candidate slots
-  if ((rows >> lane) & 1u) row_list[__popc(rows & lt_mask)] = (unsigned char)lane;
+  unsigned* row_off = reinterpret_cast<unsigned*>(wbase + kRowListOff);
+  int* s_cnt = reinterpret_cast<int*>(wbase + kCntOff);
+  if ((rows >> lane) & 1u) row_off[__popc(rows & lt_mask)] = (unsigned)lane * (kRowU64 * 8);
+  if (lane < 4) row_off[n_rows + lane] = kPadRowOff;
   if (lane == 0) *s_cnt = 0;
   __syncwarp();
+  const unsigned col = (unsigned)__cvta_generic_to_shared(wbase) + lane * 8;        // this lane's column of every row
+  const unsigned cand_a = (unsigned)__cvta_generic_to_shared(wbase + kCandOff);
+  const unsigned cnt_a = (unsigned)__cvta_generic_to_shared(s_cnt);
   const unsigned long long Lp = ((unsigned long long)Lh << 32) | Ll;
-  const unsigned long long* my_col = sk + lane;              // this lane's column; a row is kRowU64 entries further
 #pragma unroll 1
-  for (int i = 0; i < n_rows; i += 4) {                      // four rows per trip: their LDS are independent and overlap
-    const unsigned r4 = *reinterpret_cast<const unsigned*>(row_list + i);
-    unsigned long long kv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) kv[q] = (i + q < n_rows) ? my_col[((r4 >> (8 * q)) & 31u) * kRowU64] : 0ull;
+  for (int i = 0; i < n_rows; i += 4) {
+    const uint4 o4 = *reinterpret_cast<const uint4*>(row_off + i);                   // broadcast
+    unsigned lo[4], hi[4];
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[0]), "=r"(hi[0]) : "r"(col + o4.x));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[1]), "=r"(hi[1]) : "r"(col + o4.y));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[2]), "=r"(hi[2]) : "r"(col + o4.z));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[3]), "=r"(hi[3]) : "r"(col + o4.w));
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      if (kv[q] > Lp) {                                      // a zero (absent row) is never above the bound
-        const int pos = atomicAdd(s_cnt, 1);
-        if (pos < kCandMax) cand[pos] = make_uint2((unsigned)kv[q], (unsigned)(kv[q] >> 32));
-      }
+      unsigned hit;
+      if (HI_ONLY) hit = hi[q] >= Lh ? 1u : 0u;
+      else hit = ((((unsigned long long)hi[q] << 32) | true_lo(hi[q], lo[q])) > Lp) ? 1u : 0u;
+      asm volatile(
+          "{\n\t.reg .pred p, q;\n\t.reg .u32 pos, a;\n\t"
+          "setp.ne.u32 p, %0, 0;\n\t"
+          "@p atom.shared.add.u32 pos, [%1], 1;\n\t"
+          "setp.lt.and.u32 q, pos, %2, p;\n\t"
+          "mad.lo.u32 a, pos, 8, %3;\n\t"
+          "@q st.shared.v2.u32 [a], {%4, %5};\n\t}"
+          :: "r"(hit), "r"(cnt_a), "n"(kCandMax), "r"(cand_a), "r"(lo[q]), "r"(hi[q]) : "memory");
     }
   }
   __syncwarp();
   const int cnt = *s_cnt;
   // zero-pad to a multiple of 4 so the rank loop can run unrolled without a tail
+  uint2* cand = reinterpret_cast<uint2*>(wbase + kCandOff);
   if (lane < 4 && cnt <= kCandMax) cand[cnt + lane] = make_uint2(0u, 0u);
   __syncwarp();
   return cnt;
@@ -248,9 +287,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
   const int warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * kWarpSmemBytes;
   unsigned long long* sk = reinterpret_cast<unsigned long long*>(wbase);                        // [32][kRowU64] key rows
-  uint2* cand = reinterpret_cast<uint2*>(wbase + 32 * kRowU64 * 8);                             // [kCandMax + 4]
-  int* s_cnt = reinterpret_cast<int*>(wbase + 32 * kRowU64 * 8 + (kCandMax + 4) * 8 + 32);
+  uint2* cand = reinterpret_cast<uint2*>(wbase + kCandOff);                                     // [kCandMax + 4]
   unsigned* s32 = reinterpret_cast<unsigned*>(cand);                                            // 128 B scratch, reused before the gather
+  reinterpret_cast<unsigned long long*>(wbase + kPadRowOff)[lane] = kPadStored;                 // the pad row, written once
   uint4* my_row4 = reinterpret_cast<uint4*>(sk + lane * kRowU64);   // one uint4 = two keys {lo0, hi0, lo1, hi1}
   const int64_t n_units = p.n_list > 0 ? (int64_t)p.F * p.n_list : (int64_t)p.F * p.nw;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -334,8 +373,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         const double x0 = v[j].x, x1 = v[j].y;
         const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
         const unsigned m0 = (unsigned)(h0 >> 31), m1 = (unsigned)(h1 >> 31);
-        kk.x = (unsigned)__double2loint(x0) ^ m0; kk.y = (unsigned)h0 ^ (m0 | 0x80000000u);
-        kk.z = (unsigned)__double2loint(x1) ^ m1; kk.w = (unsigned)h1 ^ (m1 | 0x80000000u);
+        kk.x = (unsigned)__double2loint(x0); kk.y = (unsigned)h0 ^ (m0 | 0x80000000u);     // low words stay raw (true_lo() on use)
+        kk.z = (unsigned)__double2loint(x1); kk.w = (unsigned)h1 ^ (m1 | 0x80000000u);
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         count_gt_f64(nov, x0, thr);
@@ -348,8 +387,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         const double x0 = q0 ? v[j].x : 0.0, x1 = q1 ? v[j].y : 0.0;
         const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
         const unsigned m0 = (unsigned)(h0 >> 31), m1 = (unsigned)(h1 >> 31);
-        kk.x = q0 ? (unsigned)__double2loint(x0) ^ m0 : 0u; kk.y = q0 ? (unsigned)h0 ^ (m0 | 0x80000000u) : 0u;
-        kk.z = q1 ? (unsigned)__double2loint(x1) ^ m1 : 0u; kk.w = q1 ? (unsigned)h1 ^ (m1 | 0x80000000u) : 0u;
+        kk.x = q0 ? (unsigned)__double2loint(x0) : 0xffffffffu; kk.y = q0 ? (unsigned)h0 ^ (m0 | 0x80000000u) : 0u;   // padding = kPadStored
+        kk.z = q1 ? (unsigned)__double2loint(x1) : 0xffffffffu; kk.w = q1 ? (unsigned)h1 ^ (m1 | 0x80000000u) : 0u;
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (q0 && x0 > thr) ++nov;
@@ -358,7 +397,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         if (q0) nh = min(nh, kk.y);
         if (q1) nh = min(nh, kk.w);
       } else {
-        kk = make_uint4(0u, 0u, 0u, 0u);     // padding: the smallest key
+        kk = make_uint4(0xffffffffu, 0u, 0xffffffffu, 0u);     // padding: the smallest key (kPadStored)
       }
       my_row4[j] = kk;                       // STS.128, conflict-free (272-byte row stride)
     }
@@ -389,7 +428,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         const int row = __ffs(rows) - 1;
         rows &= rows - 1;
         const unsigned long long kv = sk[row * kRowU64 + lane];
-        if ((unsigned)(kv >> 32) == wmin.hi && elem_index(row, lane) < m) nl = min(nl, (unsigned)kv);   // the index test screens padding
+        if ((unsigned)(kv >> 32) == wmin.hi && elem_index(row, lane) < m) nl = min(nl, true_lo(wmin.hi, (unsigned)kv));   // the index test screens padding
       }
       wmin.lo = __reduce_min_sync(kFull, nl);
     }
@@ -408,13 +447,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L', so the answer is too.
       // Only rows whose maximum reaches L' can hold keys above it.
       const unsigned Lh = warp_kth_largest_smem(mh, k, s32, lane);
-      const int cnt = gather_above(sk, __ballot_sync(kFull, mh >= Lh), Lh, 0u, cand, s_cnt, lane, lt_mask);
+      // at least k lane maxima reach Lh, so at least k keys pass: the k-th largest of the gathered set is the answer
+      const int cnt = gather_rows<true>(wbase, __ballot_sync(kFull, mh >= Lh), Lh, 0u, lane, lt_mask);
       if (cnt <= 32) {
-        if (cnt == 0) { ans.hi = Lh; ans.lo = 0u; wmax = ans; }
-        else {
-          const K64 sel = select_from_candidates(cand, cnt, min(k, cnt), lane, &wmax);
-          if (cnt < k) { ans.hi = Lh; ans.lo = 0u; } else ans = sel;     // fewer than k above L' and >= k at-or-above  =>  L'
-        }
+        ans = select_from_candidates(cand, cnt, k, lane, &wmax);
         done = true;
       }
       __syncwarp();
@@ -425,7 +461,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
 #pragma unroll 4
       for (int i = 0; i < 32; ++i) {
         const unsigned long long kv = sk[lane * kRowU64 + i];
-        if ((unsigned)(kv >> 32) == mh) ml = max(ml, (unsigned)kv);
+        if ((unsigned)(kv >> 32) == mh) ml = max(ml, true_lo(mh, (unsigned)kv));
       }
       wmax = warp_max_k64(mh, ml);
       bool solved = false;
@@ -434,7 +470,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         unsigned sh = mh, sl = ml;
         warp_sort_desc_k64(sh, sl, lane);
         const unsigned Lh = __shfl_sync(kFull, sh, k - 1), Ll = __shfl_sync(kFull, sl, k - 1);
-        const int cnt = gather_above(sk, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, cand, s_cnt, lane, lt_mask);
+        const int cnt = gather_rows<false>(wbase, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, lane, lt_mask);
         if (cnt < k) { ans.hi = Lh; ans.lo = Ll; solved = true; }
         else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); solved = true; }
         __syncwarp();
@@ -449,7 +485,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
           const unsigned long long himask = ~((1ull << b) - 1ull);
           unsigned c = 0;
 #pragma unroll 4
-          for (int i = 0; i < 32; ++i) c += ((sk[lane * kRowU64 + i] & himask) == trial) ? 1u : 0u;
+          for (int i = 0; i < 32; ++i) c += ((true_key(sk[lane * kRowU64 + i]) & himask) == trial) ? 1u : 0u;
           c = __reduce_add_sync(kFull, c);
           if ((int)c >= kk2) pref = trial; else kk2 -= (int)c;
         }
