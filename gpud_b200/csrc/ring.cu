@@ -22,7 +22,10 @@
 namespace {
 
 constexpr int kMaxWindow = 1024;      // 32 lanes x 32 elements held in registers
-constexpr int kWarpsPerBlock = 8;
+#ifndef GPUD_WARPS_PER_BLOCK
+#define GPUD_WARPS_PER_BLOCK 8
+#endif
+constexpr int kWarpsPerBlock = GPUD_WARPS_PER_BLOCK;
 constexpr int kCandMax = 64;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr size_t kStageBytes = 32u << 20;   // pinned staging buffers (x2)
@@ -153,32 +156,36 @@ __device__ __forceinline__ void count_gt_k64_neg(unsigned& acc, unsigned oh, uns
   unsigned t;
   asm("sub.cc.u32 %1, %2, %3;\n\tsubc.cc.u32 %1, %4, %5;\n\tsubc.u32 %0, %0, 0;" : "+r"(acc), "=r"(t) : "r"(cl), "r"(ol), "r"(ch), "r"(oh));
 }
-// Keys are parked with the RAW low word (pass 1 transforms only the high word): true low word = lo ^ ~sign-extension of
-// key-hi bit 31 (set for non-negative doubles, whose totalOrder key keeps the low word as is).
+// The window is parked in shared memory as RAW doubles (pass 1 spends no ALU on keys).  totalOrder key of raw (h, l):
+//   key_hi = h ^ ((h >> 31) | 0x80000000)   (bijection on the high word),   key_lo = l ^ ~sign-extension of key_hi bit 31.
+__device__ __forceinline__ unsigned key_hi_of(unsigned raw_hi) { return raw_hi ^ ((unsigned)((int)raw_hi >> 31) | 0x80000000u); }
+__device__ __forceinline__ unsigned raw_hi_of(unsigned key_hi) { return key_hi ^ ((key_hi & 0x80000000u) ? 0x80000000u : 0xffffffffu); }
 __device__ __forceinline__ unsigned true_lo(unsigned key_hi, unsigned raw_lo) { return raw_lo ^ ~(unsigned)((int)key_hi >> 31); }
-__device__ __forceinline__ unsigned long long true_key(unsigned long long stored) {
-  const unsigned hi = (unsigned)(stored >> 32);
-  return ((unsigned long long)hi << 32) | true_lo(hi, (unsigned)stored);
+__device__ __forceinline__ unsigned long long true_key(unsigned long long raw) {
+  const unsigned hi = key_hi_of((unsigned)(raw >> 32));
+  return ((unsigned long long)hi << 32) | true_lo(hi, (unsigned)raw);
 }
-constexpr unsigned long long kPadStored = 0x00000000ffffffffull;   // stored form of the smallest key 0 (hi 0, raw lo ~0)
+constexpr unsigned long long kPadStored = 0xffffffffffffffffull;   // raw form of the smallest key 0 (-NaN, all ones)
 
-// Candidates sit in shared memory s[0..cnt), cnt <= 32, in STORED form.  Returns the k-th largest (k <= cnt) and the maximum.
+// Candidates sit in shared memory s[0..cnt), cnt <= 32, as RAW doubles.  Returns the k-th largest (k <= cnt) and the maximum.
 // rank_i = #{j : c_j > c_i};  the k-th largest is the smallest candidate whose rank is < k.
 __device__ __forceinline__ K64 select_from_candidates(uint2* s, int cnt, int k, int lane, K64* mx) {
   const bool mine = lane < cnt;
-  uint2 c = mine ? s[lane] : make_uint2(0u, 0u);            // .x = lo, .y = hi
+  uint2 c = mine ? s[lane] : make_uint2(0xffffffffu, 0xffffffffu);   // .x = lo, .y = hi (raw)
+  c.y = key_hi_of(c.y);
   c.x = true_lo(c.y, c.x);
   if (mine) s[lane] = c;                                     // the broadcast reads below see true keys
   __syncwarp();
-  unsigned neg_rank = 0;
+  unsigned nr0 = 0, nr1 = 0, nr2 = 0, nr3 = 0;               // four independent borrow chains
 #pragma unroll 1
   for (int j = 0; j < cnt; j += 4) {                         // the list is zero-padded to a multiple of 4; a zero never outranks
     const uint4 o01 = *reinterpret_cast<const uint4*>(s + j), o23 = *reinterpret_cast<const uint4*>(s + j + 2);   // broadcast LDS.128
-    count_gt_k64_neg(neg_rank, o01.y, o01.x, c.y, c.x);
-    count_gt_k64_neg(neg_rank, o01.w, o01.z, c.y, c.x);
-    count_gt_k64_neg(neg_rank, o23.y, o23.x, c.y, c.x);
-    count_gt_k64_neg(neg_rank, o23.w, o23.z, c.y, c.x);
+    count_gt_k64_neg(nr0, o01.y, o01.x, c.y, c.x);
+    count_gt_k64_neg(nr1, o01.w, o01.z, c.y, c.x);
+    count_gt_k64_neg(nr2, o23.y, o23.x, c.y, c.x);
+    count_gt_k64_neg(nr3, o23.w, o23.z, c.y, c.x);
   }
+  const unsigned neg_rank = (nr0 + nr1) + (nr2 + nr3);
   *mx = warp_max_k64(mine ? c.y : 0u, mine ? c.x : 0u);
   const bool in = mine && (int)(0u - neg_rank) < k;
   return warp_min_k64(in ? c.y : 0xffffffffu, in ? c.x : 0xffffffffu);
@@ -206,8 +213,10 @@ constexpr int kBlockSmemBytes = kWarpsPerBlock * kWarpSmemBytes;
 
 __device__ __forceinline__ int elem_index(int row, int col) { return 64 * (col >> 1) + 2 * row + (col & 1); }   // chronological t
 
-// Append the keys of the flagged rows that pass the bound to cand[] (any order, STORED form).  HI_ONLY: keys whose high
-// word is >= Lh (one compare; the fast path's bound is (Lh, 0), inclusive).  Otherwise: true keys > (Lh, Ll).
+// Append the entries of the flagged rows that pass the bound to cand[] (any order, RAW form).  HI_ONLY: keys whose high
+// word is >= Lh (the fast path's bound is (Lh, 0), inclusive), tested on the raw word: key_hi >= Lh  <=>
+// (int)(raw ^ X) >= (int)(Lh ^ 0x80000000) with X = 0 for a non-negative bound and 0x7fffffff for a negative one.
+// Otherwise: true keys > (Lh, Ll).
 // The flagged rows' byte offsets are packed into a list first (padded to a multiple of four with the pad row); then one LDS
 // per row gives every lane one key of that row and the few lanes that hold a hit claim a slot with a predicated
 // shared-memory atomic - straight-line code, four rows in flight per trip.
@@ -225,6 +234,8 @@ __device__ __forceinline__ int gather_rows(unsigned char* wbase, unsigned rows, 
   const unsigned cand_a = (unsigned)__cvta_generic_to_shared(wbase + kCandOff);
   const unsigned cnt_a = (unsigned)__cvta_generic_to_shared(s_cnt);
   const unsigned long long Lp = ((unsigned long long)Lh << 32) | Ll;
+  const unsigned X = (Lh & 0x80000000u) ? 0u : 0x7fffffffu;
+  const int Y = (int)(Lh ^ 0x80000000u);
 #pragma unroll 1
   for (int i = 0; i < n_rows; i += 4) {
     const uint4 o4 = *reinterpret_cast<const uint4*>(row_off + i);                   // broadcast
@@ -236,8 +247,8 @@ __device__ __forceinline__ int gather_rows(unsigned char* wbase, unsigned rows, 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       unsigned hit;
-      if (HI_ONLY) hit = hi[q] >= Lh ? 1u : 0u;
-      else hit = ((((unsigned long long)hi[q] << 32) | true_lo(hi[q], lo[q])) > Lp) ? 1u : 0u;
+      if (HI_ONLY) hit = (int)(hi[q] ^ X) >= Y ? 1u : 0u;
+      else hit = (true_key(((unsigned long long)hi[q] << 32) | lo[q]) > Lp) ? 1u : 0u;
       asm volatile(
           "{\n\t.reg .pred p, q;\n\t.reg .u32 pos, a;\n\t"
           "setp.ne.u32 p, %0, 0;\n\t"
@@ -263,17 +274,24 @@ __device__ __forceinline__ int gather_rows(unsigned char* wbase, unsigned rows, 
 __device__ __forceinline__ unsigned warp_kth_largest_smem(unsigned v, int k, unsigned* s32, int lane) {
   s32[lane] = v;
   __syncwarp();
-  unsigned neg_rank = 0;                      // minus the number of lanes holding a larger value
+  unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;    // minus the number of lanes holding a larger value, four independent chains
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const uint4 o = reinterpret_cast<const uint4*>(s32)[q];
-    count_gt_u32_neg(neg_rank, o.x, v); count_gt_u32_neg(neg_rank, o.y, v); count_gt_u32_neg(neg_rank, o.z, v); count_gt_u32_neg(neg_rank, o.w, v);
+    count_gt_u32_neg(n0, o.x, v); count_gt_u32_neg(n1, o.y, v); count_gt_u32_neg(n2, o.z, v); count_gt_u32_neg(n3, o.w, v);
   }
+  const unsigned neg_rank = (n0 + n1) + (n2 + n3);
   __syncwarp();
   return __reduce_min_sync(kFull, (int)(0u - neg_rank) < k ? v : 0xffffffffu);
 }
 
 struct WinUnit { int f, w, m; int64_t p0; };
+// streaming 128-bit load: read-only path, no L1 allocation, 256-byte L2 sector promotion (measured best of the hints on B200)
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
 #ifndef GPUD_PREFETCH_PAIRS
 #define GPUD_PREFETCH_PAIRS 16   /* measured: 8 pairs + 3 CTAs/SM = 63 % of roofline, 16 pairs + 2 CTAs/SM = 82 % */
 #endif
@@ -325,9 +343,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         if (j >= PF) continue;                                     // the rest is loaded by fetch_rest() at the top of the next trip
-        if (JF >= 0 && j < JF) { v[j] = __ldcs(b2 + 32 * j); continue; }
+        if (JF >= 0 && j < JF) { v[j] = ld_stream(b2 + 32 * j); continue; }
         v[j] = make_double2(0.0, 0.0);
-        if (64 * j + 2 * lane < q.m) v[j] = __ldcs(b2 + 32 * j);   // element t0+1 == m is masked in pass 1 (the ring has slack)
+        if (64 * j + 2 * lane < q.m) v[j] = ld_stream(b2 + 32 * j);   // element t0+1 == m is masked in pass 1 (the ring has slack)
       }
     } else {
 #pragma unroll
@@ -347,9 +365,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < PF) continue;
-      if (JF >= 0 && j < JF) { v[j] = __ldcs(b2 + 32 * j); continue; }
+      if (JF >= 0 && j < JF) { v[j] = ld_stream(b2 + 32 * j); continue; }
       v[j] = make_double2(0.0, 0.0);
-      if (64 * j + 2 * lane < q.m) v[j] = __ldcs(b2 + 32 * j);
+      if (64 * j + 2 * lane < q.m) v[j] = ld_stream(b2 + 32 * j);
     }
   };
 
@@ -365,42 +383,46 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     // ---- pass 1: consume the loaded registers once ----
     double sum0 = 0.0, sum1 = 0.0, es0 = 0.0, es1 = 0.0;
     unsigned nov = 0;
-    unsigned mh = 0u, nh = 0xffffffffu;    // lane max / min of the key high words
+    // lane extremes of the RAW high words, three running values and no per-element transform: sign-magnitude order means
+    //   the largest key is smax(h) when any element is non-negative (smax >= 0), else umin(h);
+    //   the smallest key is umax(h) when any element is negative (umax >= 2^31), else umin(h).
+    int a_smax = (int)0x80000000;
+    unsigned b_umin = 0xffffffffu, c_umax = 0u;
+    double2* my_row2 = reinterpret_cast<double2*>(my_row4);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      uint4 kk;                              // {lo0, hi0, lo1, hi1}: totalOrder keys of the pair, 3 integer ops per element
       if (JF >= 0 ? (j < JF) : (j < Jfull)) {  // whole register pair valid (compile-time when JF >= 0, else warp-uniform)
         const double x0 = v[j].x, x1 = v[j].y;
         const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
-        const unsigned m0 = (unsigned)(h0 >> 31), m1 = (unsigned)(h1 >> 31);
-        kk.x = (unsigned)__double2loint(x0); kk.y = (unsigned)h0 ^ (m0 | 0x80000000u);     // low words stay raw (true_lo() on use)
-        kk.z = (unsigned)__double2loint(x1); kk.w = (unsigned)h1 ^ (m1 | 0x80000000u);
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         count_gt_f64(nov, x0, thr);
         count_gt_f64(nov, x1, thr);
-        mh = max(mh, max(kk.y, kk.w));
-        nh = min(nh, min(kk.y, kk.w));
+        a_smax = max(a_smax, max(h0, h1));
+        b_umin = min(b_umin, min((unsigned)h0, (unsigned)h1));
+        c_umax = max(c_umax, max((unsigned)h0, (unsigned)h1));
+        my_row2[j] = v[j];                     // STS.128 of the loaded registers, conflict-free (272-byte row stride)
       } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
         const int t0 = 64 * j + 2 * lane;
         const bool q0 = t0 < m, q1 = t0 + 1 < m;
         const double x0 = q0 ? v[j].x : 0.0, x1 = q1 ? v[j].y : 0.0;
-        const int h0 = __double2hiint(x0), h1 = __double2hiint(x1);
-        const unsigned m0 = (unsigned)(h0 >> 31), m1 = (unsigned)(h1 >> 31);
-        kk.x = q0 ? (unsigned)__double2loint(x0) : 0xffffffffu; kk.y = q0 ? (unsigned)h0 ^ (m0 | 0x80000000u) : 0u;   // padding = kPadStored
-        kk.z = q1 ? (unsigned)__double2loint(x1) : 0xffffffffu; kk.w = q1 ? (unsigned)h1 ^ (m1 | 0x80000000u) : 0u;
+        const unsigned h0 = q0 ? (unsigned)__double2hiint(x0) : 0xffffffffu, h1 = q1 ? (unsigned)__double2hiint(x1) : 0xffffffffu;   // padding = kPadStored
         sum0 += x0; sum1 += x1;
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (q0 && x0 > thr) ++nov;
         if (q1 && x1 > thr) ++nov;
-        mh = max(mh, max(kk.y, kk.w));
-        if (q0) nh = min(nh, kk.y);
-        if (q1) nh = min(nh, kk.w);
+        a_smax = max(a_smax, max((int)h0, (int)h1));                       // all-ones is -1: neutral unless every element is negative, and then unused
+        b_umin = min(b_umin, min(h0, h1));
+        c_umax = max(c_umax, max(q0 ? h0 : 0u, q1 ? h1 : 0u));
+        my_row4[j] = make_uint4(q0 ? (unsigned)__double2loint(x0) : 0xffffffffu, h0, q1 ? (unsigned)__double2loint(x1) : 0xffffffffu, h1);
       } else {
-        kk = make_uint4(0xffffffffu, 0u, 0xffffffffu, 0u);     // padding: the smallest key (kPadStored)
+        my_row4[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);     // padding: the smallest key (kPadStored)
       }
-      my_row4[j] = kk;                       // STS.128, conflict-free (272-byte row stride)
     }
+    const unsigned rmh = a_smax >= 0 ? (unsigned)a_smax : b_umin;          // raw high word of this lane's largest key
+    const unsigned mh = key_hi_of(rmh);
+    const bool lane_empty = c_umax == 0u && b_umin == 0xffffffffu;         // no valid element (windows shorter than 64 samples)
+    const unsigned nh = lane_empty ? 0xffffffffu : key_hi_of((c_umax & 0x80000000u) ? c_umax : b_umin);
     __syncwarp();
 
     // ---- the registers are free again: put the next window's loads in flight under the post-processing below ----
@@ -424,11 +446,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     {
       unsigned rows = __ballot_sync(kFull, nh == wmin.hi);
       unsigned nl = 0xffffffffu;
+      const unsigned raw_min_hi = raw_hi_of(wmin.hi);
       while (rows) {
         const int row = __ffs(rows) - 1;
         rows &= rows - 1;
         const unsigned long long kv = sk[row * kRowU64 + lane];
-        if ((unsigned)(kv >> 32) == wmin.hi && elem_index(row, lane) < m) nl = min(nl, true_lo(wmin.hi, (unsigned)kv));   // the index test screens padding
+        if ((unsigned)(kv >> 32) == raw_min_hi && elem_index(row, lane) < m) nl = min(nl, true_lo(wmin.hi, (unsigned)kv));   // the index test screens padding
       }
       wmin.lo = __reduce_min_sync(kFull, nl);
     }
@@ -461,7 +484,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
 #pragma unroll 4
       for (int i = 0; i < 32; ++i) {
         const unsigned long long kv = sk[lane * kRowU64 + i];
-        if ((unsigned)(kv >> 32) == mh) ml = max(ml, true_lo(mh, (unsigned)kv));
+        if ((unsigned)(kv >> 32) == rmh) ml = max(ml, true_lo(mh, (unsigned)kv));
       }
       wmax = warp_max_k64(mh, ml);
       bool solved = false;
