@@ -285,15 +285,18 @@ __device__ __forceinline__ unsigned warp_kth_largest_smem(unsigned v, int k, uns
   return __reduce_min_sync(kFull, (int)(0u - neg_rank) < k ? v : 0xffffffffu);
 }
 
-struct WinUnit { int f, w, m; int64_t p0; double thr; };
+struct WinUnit { int f, w, m; int64_t p0; };
 // streaming 128-bit load: read-only path, no L1 allocation, 256-byte L2 sector promotion (measured best of the hints on B200)
 __device__ __forceinline__ double2 ld_stream(const double2* p) {
   double2 r;
   asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
   return r;
 }
-constexpr int kHotCtasPerSM = 2;   // 16 register pairs of the next window in flight need 128 registers: 2 CTAs x 8 warps per SM
-   // (measured: 8 pairs in flight + 3 CTAs/SM = 63 % of roofline; 9..12 warps per CTA spill and lose 30-50 %)
+#ifndef GPUD_PREFETCH_PAIRS
+#define GPUD_PREFETCH_PAIRS 16   /* measured: 8 pairs + 3 CTAs/SM = 63 % of roofline, 16 pairs + 2 CTAs/SM = 82 % */
+#endif
+constexpr int kPrefetchPairs = GPUD_PREFETCH_PAIRS;      // register pairs of the NEXT window loaded under the current post-processing
+constexpr int kHotCtasPerSM = kPrefetchPairs < 16 ? 3 : 2;  // 8 pairs in flight fit 80 registers (3 CTAs/SM); all 16 need 128 (2 CTAs/SM)
 
 template <bool ALIGNED, int JF>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kHotCtasPerSM : 2) k_window_reduce(const WinParams p) {
@@ -316,13 +319,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
   int64_t u = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   int uf = (int)(u / per_f), uslot = (int)(u - (int64_t)uf * per_f);
 
-  // The loads of the NEXT window are issued in one batch right after pass 1 and stay outstanding under the post-processing.
-  // INTERLEAVE (issue each pair's load inside pass 1, right after the pair is consumed) was measured slower on B200
-  // (0.723 ms vs 0.699 ms): the write-after-read waits on the STS sources stretch pass 1.
-  constexpr bool INTERLEAVE = false;
-  double2 v[16];                 // the window in flight
-  // choose the next non-skipped unit of this warp (if any); no loads
-  auto pick = [&](WinUnit& q) -> bool {
+  constexpr int PF = (ALIGNED && JF >= 0) ? kPrefetchPairs : 16;
+  double2 v[16];                 // the window in flight: loaded for the NEXT unit while the current one is post-processed
+  double thr_next = 0.0;
+  // fetch the next non-skipped unit of this warp (if any) and issue all of its loads.  Measured alternatives, both slower on
+  // B200: choosing the next unit BEFORE pass 1 (its address/threshold registers live through pass 1: 0.79 ms vs 0.70 ms) and
+  // issuing each pair's load inside pass 1 right after the pair is consumed (0.72 ms).
+  auto fetch = [&](WinUnit& q) -> bool {
     for (;;) {
       if (u >= n_units) return false;
       q.f = uf;
@@ -335,21 +338,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     q.m = JF >= 0 ? p.W : (int)min((int64_t)p.W, p.count - c0);
     q.p0 = p.start + c0;
     if (q.p0 >= p.cap) q.p0 -= p.cap;
-    q.thr = __ldg(p.thr + q.f);
-    return true;
-  };
-  auto load_pair = [&](const WinUnit& q, const double2* __restrict__ b2, int j) {   // ALIGNED only; b2 already includes the lane offset
-    if (JF >= 0 && j < JF) { v[j] = ld_stream(b2 + 32 * j); return; }
-    if (JF >= 0 && j > JF) return;                                   // never read
-    v[j] = make_double2(0.0, 0.0);
-    if (64 * j + 2 * lane < q.m) v[j] = ld_stream(b2 + 32 * j);       // element t0+1 == m is masked in pass 1 (the ring has slack)
-  };
-  auto load_all = [&](const WinUnit& q) {
     const double* __restrict__ base = p.ring + (int64_t)q.f * p.cap;
+    thr_next = __ldg(p.thr + q.f);
     if (ALIGNED) {
       const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + q.p0) + lane;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) load_pair(q, b2, j);
+      for (int j = 0; j < 16; ++j) {
+        if (j >= PF) continue;                                     // the rest is loaded by fetch_rest() at the top of the next trip
+        if (JF >= 0 && j < JF) { v[j] = ld_stream(b2 + 32 * j); continue; }
+        v[j] = make_double2(0.0, 0.0);
+        if (64 * j + 2 * lane < q.m) v[j] = ld_stream(b2 + 32 * j);   // element t0+1 == m is masked in pass 1 (the ring has slack)
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
@@ -359,18 +358,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         if (t0 + 1 < q.m) { int64_t a = q.p0 + t0 + 1; if (a >= p.cap) a -= p.cap; v[j].y = __ldcs(base + a); }
       }
     }
+    return true;
+  };
+
+  auto fetch_rest = [&](const WinUnit& q) {
+    if (PF >= 16) return;
+    const double2* __restrict__ b2 = reinterpret_cast<const double2*>(p.ring + (int64_t)q.f * p.cap + q.p0) + lane;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < PF) continue;
+      if (JF >= 0 && j < JF) { v[j] = ld_stream(b2 + 32 * j); continue; }
+      v[j] = make_double2(0.0, 0.0);
+      if (64 * j + 2 * lane < q.m) v[j] = ld_stream(b2 + 32 * j);
+    }
   };
 
   WinUnit cur, nxt;
-  bool have = pick(cur);
-  if (have) load_all(cur);
+  bool have = fetch(cur);
   while (have) {
-    const bool have_n = pick(nxt);                                   // warp-uniform
-    const double2* __restrict__ nb2 = reinterpret_cast<const double2*>(p.ring + (int64_t)nxt.f * p.cap + nxt.p0) + lane;
+    fetch_rest(cur);
     const int f = cur.f, w = cur.w, m = cur.m;
     const int J = (m + 63) >> 6;                     // register pairs that hold at least one valid element
     const int Jfull = JF >= 0 ? JF : (m >> 6);       // register pairs in which every lane's two elements are valid
-    const double thr = cur.thr;
+    const double thr = thr_next;
 
     // ---- pass 1: consume the loaded registers once ----
     double sum0 = 0.0, sum1 = 0.0, es0 = 0.0, es1 = 0.0;
@@ -394,7 +404,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         b_umin = min(b_umin, min((unsigned)h0, (unsigned)h1));
         c_umax = max(c_umax, max((unsigned)h0, (unsigned)h1));
         my_row2[j] = v[j];                     // STS.128 of the loaded registers, conflict-free (272-byte row stride)
-        if (INTERLEAVE && have_n) load_pair(nxt, nb2, j);
       } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
         const int t0 = 64 * j + 2 * lane;
         const bool q0 = t0 < m, q1 = t0 + 1 < m;
@@ -408,7 +417,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         b_umin = min(b_umin, min(h0, h1));
         c_umax = max(c_umax, max(q0 ? h0 : 0u, q1 ? h1 : 0u));
         my_row4[j] = make_uint4(q0 ? (unsigned)__double2loint(x0) : 0xffffffffu, h0, q1 ? (unsigned)__double2loint(x1) : 0xffffffffu, h1);
-        if (INTERLEAVE && have_n) load_pair(nxt, nb2, j);
       } else {
         my_row4[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);     // padding: the smallest key (kPadStored)
       }
@@ -420,7 +428,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     __syncwarp();
 
     // ---- the registers are free again: put the next window's loads in flight under the post-processing below ----
-    if (!INTERLEAVE && have_n) load_all(nxt);
+    have = fetch(nxt);
 
     // ---- sums (the two shuffle trees are interleaved) ----
     const int eb = m - 1 - 64 * (J - 1) - 2 * lane;          // exponent of this lane's h=0 element in pair J-1, in [-62, 63]
@@ -522,7 +530,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       p.part[o] = ep;
     }
     cur = nxt;
-    have = have_n;
   }
 }
 
