@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 F, CAP, W = 512, 1 << 20, 1000
+LO, HI, THR = 30000, 90000, 88000.0   # synthetic raw counter samples: integer readings (a power gauge in mW), threshold in the same unit
 METRIC = "counter-samples/sec"
 FALLBACK_HBM_GBS = 6650.0
 
@@ -44,6 +45,17 @@ def peaks():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback"
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_window_reduce launch on this workload, from the committed
+    `ncu --set full` capture (profiles/window_reduce_traffic.json, written by tools/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "window_reduce_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -93,8 +105,8 @@ def cpu_leg(steps, warmup, sample_fields, threads=0):
     """Times the C oracle on a bounded sample of the same workload: `sample_fields` fields x CAP samples per step."""
     from oracle import coracle
     rng = np.random.default_rng(0x67707564)
-    ring = rng.random((sample_fields, CAP)) * 60.0 + 30.0
-    thr = np.full(sample_fields, 88.0)
+    ring = rng.integers(LO, HI, (sample_fields, CAP)).astype(np.float64)     # the same raw-counter stream shape as the GPU arm
+    thr = np.full(sample_fields, THR)
     cores = coracle.max_threads() if threads <= 0 else threads
     for _ in range(warmup):
         coracle.windows_fields(ring[: max(1, sample_fields // 8)], W, thr, threads=cores)
@@ -120,6 +132,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     config = {"workload": "ring 512 fields x 1Mi f64 samples per GPU (4 GiB), W=1000 tumbling, fused min/max/mean/ema/p99/n_over",
+              "samples": "synthetic raw counters: integer readings uniform in [30000, 90000) held as float64 in the ring",
               "n_fields": F, "capacity": CAP, "window": W, "parallelism": "one ring per GPU, no data-path collective (weak)",
               "l2": "input 4 GiB per GPU >> 126 MB L2; every step re-streams HBM"}
 
@@ -151,7 +164,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     ctx = g.Context([local])
-    thr = np.full(F, 88.0)
+    thr = np.full(F, THR)
     ring = g.Ring(ctx, F, CAP, W, thresholds=thr, dev=local)
     stream = torch.cuda.Stream(device=dev)            # a real (non-NULL) stream: the library launches on it and torch events time it
     torch.cuda.set_stream(stream)
@@ -162,7 +175,7 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0x67707564 + rank)
     chunk = 1 << 16
     for i in range(CAP // chunk):
-        t = torch.rand((chunk, F), dtype=torch.float64, device=dev, generator=gen) * 60.0 + 30.0
+        t = torch.randint(LO, HI, (chunk, F), dtype=torch.int32, device=dev, generator=gen).to(torch.float64)
         ring.push_device(t.data_ptr(), chunk)
     torch.cuda.synchronize()
     del t
@@ -224,38 +237,45 @@ def main():
     achieved = F * CAP * 8 / (k_reduce * 1e-3) / 1e9
 
     # ---- e2e: pinned host rows -> push (H2D + append) -> reduce -> D2H of all aggregates, every step ----
-    e2e = None
+    # Headline e2e: the poller hands over RAW NVML samples in the getter's own type (uint32) through gpud_ring_push_raw; the
+    # widening to float64 happens in the append kernel.  e2e_f64: the same stream already widened on the host (gpud_ring_push).
+    e2e = e2e_f64 = None
     if not a.no_e2e:
-        rows_chunk = 1 << 18                                   # 1 GiB pinned, pushed 4x per step = the whole 4 GiB ring
-        host = torch.empty((rows_chunk, F), dtype=torch.float64).pin_memory()
-        host.uniform_(30.0, 90.0)
         nw = (CAP + W - 1) // W
         outs = {k: np.empty((F, nw), dtype=np.uint32 if k == "n_over" else np.float64) for k in g.OPS}
         d2h = sum(o.nbytes for o in outs.values())
 
-        def e2e_step():
-            for _ in range(CAP // rows_chunk):
-                ring.push_ptr(host.data_ptr(), rows_chunk)
-            ring.reduce()
-            for k in g.OPS:
-                ctx._check(ring._L.gpud_ring_read(ring._h, g.OPS[k], C.c_void_p(outs[k].ctypes.data), outs[k].nbytes))
+        def run_e2e(host, rows_chunk, dtype_code, esz, steps):
+            def e2e_step():
+                for _ in range(CAP // rows_chunk):
+                    ring.push_raw_ptr(host.data_ptr(), rows_chunk, dtype_code)
+                ring.reduce()
+                for k in g.OPS:
+                    ctx._check(ring._L.gpud_ring_read(ring._h, g.OPS[k], C.c_void_p(outs[k].ctypes.data), outs[k].nbytes))
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(steps):
+                e2e_step()
+            e1.record()
+            barrier()
+            ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / steps
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return {"value": samples_step / (ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": F * CAP * esz, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms, "steps": steps}
 
         e2e_steps = max(2, min(a.steps, 5))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        e1.record()
-        barrier()
-        ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
-        if world > 1:
-            t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {"value": samples_step / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": F * CAP * 8, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e2e, "steps": e2e_steps}
+        host = torch.randint(LO, HI, (1 << 19, F), dtype=torch.int32).pin_memory()        # 1 GiB pinned, pushed 2x per step = the whole ring
+        e2e = run_e2e(host, 1 << 19, g.DTYPES["uint32"], 4, e2e_steps)
+        e2e["sample_dtype"] = "uint32 raw NVML counters (gpud_ring_push_raw), widened to f64 on the device"
+        del host
+        host = torch.randint(LO, HI, (1 << 18, F), dtype=torch.int32).to(torch.float64).pin_memory()   # 1 GiB pinned, pushed 4x per step
+        e2e_f64 = run_e2e(host, 1 << 18, g.DTYPES["float64"], 8, 2)
+        e2e_f64["sample_dtype"] = "float64 widened on the host (gpud_ring_push)"
         del host
 
     cpu = None
@@ -319,10 +339,10 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "gpu_launches": (3 + (1 if world > 1 else 0)) * a.steps,   # window_reduce (specialised + generic tail) + ema_carry (+ fabric pack)
                 "clocks": clocks, "e2e": e2e,
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "k_window_reduce", "kernel_ms": k_reduce, "carry_kernel_ms": k_carry, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"
                              if how == "measured" else "fallback 6650 GB/s (B200_PROFILING.md)", "algorithmic_bytes_per_launch": F * CAP * 8},
-                "cpu_baseline": cpu, "scan": scan}
+                "cpu_baseline": cpu, "e2e_f64": e2e_f64, "scan": scan}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

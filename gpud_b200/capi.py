@@ -15,6 +15,7 @@ EVENT_NAMES = ["Unknown", "Info", "Warning", "Critical", "Fatal"]
 ACTION_WIRE = {1: "IGNORE_NO_ACTION_REQUIRED", 2: "REBOOT_SYSTEM", 3: "HARDWARE_INSPECTION", 4: "CHECK_USER_APP_AND_GPU"}
 SCAN_LINES, SCAN_RAW_KMSG = 0, 1
 SCAN_EXT_MATCHERS = 0x100
+DTYPES = {"float64": 0, "uint32": 1, "int32": 2, "float32": 3, "int64": 4, "uint64": 5}   # GPUD_DT_*
 MAX_LINKS, MAX_GPUS = 18, 16
 
 
@@ -87,7 +88,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_kmsg_event_name", "gpud_kmsg_event_message",
            "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -111,7 +112,7 @@ def lib() -> C.CDLL:
         "gpud_last_error": (i32, [vp, C.c_char_p, i32]),
         "gpud_host_alloc": (i32, [i64, C.POINTER(vp)]), "gpud_host_free": (i32, [vp]),
         "gpud_ring_create": (i32, [vp, i32, C.POINTER(RingCfg), C.POINTER(vp)]), "gpud_ring_destroy": (i32, [vp]),
-        "gpud_ring_set_stream": (i32, [vp, vp]), "gpud_ring_push": (i32, [vp, vp, i64]), "gpud_ring_push_device": (i32, [vp, vp, i64]),
+        "gpud_ring_set_stream": (i32, [vp, vp]), "gpud_ring_push": (i32, [vp, vp, i64]), "gpud_ring_push_device": (i32, [vp, vp, i64]), "gpud_ring_push_raw": (i32, [vp, vp, i64, i32]),
         "gpud_ring_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "gpud_ring_reduce": (i32, [vp]), "gpud_ring_sync": (i32, [vp]),
         "gpud_ring_kernel_ms": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]), "gpud_ring_read": (i32, [vp, i32, vp, i64]),
@@ -295,6 +296,15 @@ class Ring:
 
     def push_ptr(self, host_ptr: int, n_rows: int):
         self.ctx._check(self._L.gpud_ring_push(self._h, C.c_void_p(host_ptr), n_rows))
+
+    def push_raw(self, rows: np.ndarray):
+        """rows [n][F] of raw counter samples in the getter's own type (uint32 / int32 / float32 / int64 / uint64 / float64)"""
+        rows = np.ascontiguousarray(rows)
+        assert rows.ndim == 2 and rows.shape[1] == self.F
+        self.ctx._check(self._L.gpud_ring_push_raw(self._h, C.c_void_p(rows.ctypes.data), rows.shape[0], DTYPES[rows.dtype.name]))
+
+    def push_raw_ptr(self, host_ptr: int, n_rows: int, dtype: int):
+        self.ctx._check(self._L.gpud_ring_push_raw(self._h, C.c_void_p(host_ptr), n_rows, dtype))
 
     def push_device(self, dev_ptr: int, n_rows: int):
         self.ctx._check(self._L.gpud_ring_push_device(self._h, C.c_void_p(dev_ptr), n_rows))

@@ -57,7 +57,10 @@ struct WinParams {
 // K1: append.  src [n][F] row-major (one row per poll) -> ring [F][CAP] at columns (head + i) % CAP.
 // 32x32 tile transpose through shared memory: reads coalesced along F, writes coalesced along time.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_ring_append(const double* __restrict__ src, double* __restrict__ ring, int64_t n, int F,
+// T = the caller's sample type: double, or a raw NVML / DCGM counter type widened here exactly like Go's float64(v)
+// (round-to-nearest-even for 64-bit integers above 2^53).
+template <typename T>
+__global__ void __launch_bounds__(256) k_ring_append(const T* __restrict__ src, double* __restrict__ ring, int64_t n, int F,
                                                       int64_t cap, int64_t head) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(256) k_ring_append(const double* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int64_t r = r0 + ty + 8 * k, f = f0 + tx;
-      if (r < n && f < F) tile[ty + 8 * k][tx] = __ldcs(src + r * F + f);
+      if (r < n && f < F) tile[ty + 8 * k][tx] = (double)__ldcs(src + r * F + f);
     }
     __syncthreads();
 #pragma unroll
@@ -689,17 +692,33 @@ extern "C" int32_t gpud_ring_set_stream(gpud_ring* r, void* s) {
   return GPUD_OK;
 }
 
-static int32_t launch_append(gpud_ring* r, const double* d_rows, int64_t n) {
+static size_t dtype_size(int32_t dt) {
+  switch (dt) {
+    case GPUD_DT_F64: case GPUD_DT_I64: case GPUD_DT_U64: return 8;
+    case GPUD_DT_U32: case GPUD_DT_I32: case GPUD_DT_F32: return 4;
+  }
+  return 0;
+}
+
+static int32_t launch_append(gpud_ring* r, const void* d_rows, int64_t n, int32_t dt) {
   // only the newest CAP rows can survive
   if (n > r->cap) {
-    d_rows += (n - r->cap) * r->F;
+    d_rows = (const char*)d_rows + (size_t)(n - r->cap) * r->F * dtype_size(dt);
     r->total += n - r->cap;
     n = r->cap;
   }
   const int64_t head = r->total % r->cap;
   const int64_t tiles = ((r->F + 31) / 32) * ((n + 31) / 32);
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)r->sm_count * 16);
-  k_ring_append<<<grid, 256, 0, r->stream>>>(d_rows, r->d_ring, n, r->F, r->cap, head);
+  switch (dt) {
+    case GPUD_DT_F64: k_ring_append<double><<<grid, 256, 0, r->stream>>>((const double*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_U32: k_ring_append<uint32_t><<<grid, 256, 0, r->stream>>>((const uint32_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_I32: k_ring_append<int32_t><<<grid, 256, 0, r->stream>>>((const int32_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_F32: k_ring_append<float><<<grid, 256, 0, r->stream>>>((const float*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_I64: k_ring_append<long long><<<grid, 256, 0, r->stream>>>((const long long*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_U64: k_ring_append<unsigned long long><<<grid, 256, 0, r->stream>>>((const unsigned long long*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    default: return gpud_fail(r->ctx, GPUD_E_INVALID, "unknown sample dtype %d", dt);
+  }
   GPUD_CUDA(r->ctx, cudaGetLastError());
   r->total += n;
   r->reduced_nw = -1;
@@ -710,15 +729,17 @@ extern "C" int32_t gpud_ring_push_device(gpud_ring* r, const double* dev_rows, i
   if (!r || (!dev_rows && n) || n < 0) return GPUD_E_INVALID;
   if (n == 0) return GPUD_OK;
   GPUD_CUDA(r->ctx, cudaSetDevice(r->dev));
-  return launch_append(r, dev_rows, n);
+  return launch_append(r, dev_rows, n, GPUD_DT_F64);
 }
 
-extern "C" int32_t gpud_ring_push(gpud_ring* r, const double* host_rows, int64_t n) {
-  if (!r || (!host_rows && n) || n < 0) return GPUD_E_INVALID;
+extern "C" int32_t gpud_ring_push_raw(gpud_ring* r, const void* host_rows_v, int64_t n, int32_t dt) {
+  const size_t esz = dtype_size(dt);
+  if (!r || (!host_rows_v && n) || n < 0 || esz == 0) return GPUD_E_INVALID;
   if (n == 0) return GPUD_OK;
+  const char* host_rows = (const char*)host_rows_v;
   GPUD_CUDA(r->ctx, cudaSetDevice(r->dev));
   if (n > r->cap) {                      // rows that would be overwritten immediately never cross PCIe
-    host_rows += (n - r->cap) * r->F;
+    host_rows += (size_t)(n - r->cap) * r->F * esz;
     r->total += n - r->cap;
     n = r->cap;
   }
@@ -726,19 +747,21 @@ extern "C" int32_t gpud_ring_push(gpud_ring* r, const double* host_rows, int64_t
   bool pinned = false;
   if (cudaPointerGetAttributes(&attr, host_rows) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
   else cudaGetLastError();
+  // the staging pair is sized in bytes for stage_rows rows of doubles: narrower samples move more rows per piece
+  const int64_t piece_rows = r->stage_rows * (int64_t)(sizeof(double) / esz);
   int64_t done = 0;
   int buf = 0;
   while (done < n) {
-    const int64_t rows = std::min(r->stage_rows, n - done);
-    const size_t bytes = (size_t)rows * r->F * sizeof(double);
+    const int64_t rows = std::min(piece_rows, n - done);
+    const size_t bytes = (size_t)rows * r->F * esz;
     GPUD_CUDA(r->ctx, cudaEventSynchronize(r->ev_stage[buf]));   // previous use of this staging pair has drained
-    const double* src = host_rows + done * r->F;
+    const char* src = host_rows + (size_t)done * r->F * esz;
     if (!pinned) {
       memcpy(r->h_stage[buf], src, bytes);                     // pageable caller memory: stage through pinned
-      src = r->h_stage[buf];
+      src = (const char*)r->h_stage[buf];
     }
     GPUD_CUDA(r->ctx, cudaMemcpyAsync(r->d_stage[buf], src, bytes, cudaMemcpyHostToDevice, r->stream));
-    int32_t rc = launch_append(r, r->d_stage[buf], rows);
+    int32_t rc = launch_append(r, r->d_stage[buf], rows, dt);
     if (rc) return rc;
     GPUD_CUDA(r->ctx, cudaEventRecord(r->ev_stage[buf], r->stream));
     done += rows;
@@ -747,6 +770,8 @@ extern "C" int32_t gpud_ring_push(gpud_ring* r, const double* host_rows, int64_t
   if (pinned) GPUD_CUDA(r->ctx, cudaStreamSynchronize(r->stream));   // caller may reuse its buffer on return
   return GPUD_OK;
 }
+
+extern "C" int32_t gpud_ring_push(gpud_ring* r, const double* host_rows, int64_t n) { return gpud_ring_push_raw(r, host_rows, n, GPUD_DT_F64); }
 
 extern "C" int32_t gpud_ring_counts(gpud_ring* r, int64_t* total, int64_t* count, int64_t* n_windows) {
   if (!r) return GPUD_E_INVALID;

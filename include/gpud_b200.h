@@ -82,6 +82,13 @@ int32_t gpud_ring_set_stream(gpud_ring* ring, void* cuda_stream);
 int32_t gpud_ring_push(gpud_ring* ring, const double* host_rows, int64_t n_rows);
 /* Same, source already in device memory on the ring's device (append kernel only). */
 int32_t gpud_ring_push_device(gpud_ring* ring, const double* dev_rows, int64_t n_rows);
+/* Same as gpud_ring_push for rows of RAW counter samples in the getter's own type: NVML returns uint32 (temperature C,
+ * power mW, clocks MHz, utilisation %: pkg/nvidia/nvml/lib/... getters behind temperature/component.go:252-272,
+ * power/component.go, clock-speed/component.go) or uint64 (memory bytes, ECC counts); DCGM fields are int64 or double.
+ * The widening the reference does on the host - metric.Set(float64(v)) - happens in the append kernel instead (exact;
+ * round-to-nearest-even above 2^53 like Go), so a uint32 poll row crosses PCIe at half the bytes. */
+enum { GPUD_DT_F64 = 0, GPUD_DT_U32 = 1, GPUD_DT_I32 = 2, GPUD_DT_F32 = 3, GPUD_DT_I64 = 4, GPUD_DT_U64 = 5 };
+int32_t gpud_ring_push_raw(gpud_ring* ring, const void* host_rows, int64_t n_rows, int32_t dtype);
 int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
 /* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
 int32_t gpud_ring_reduce(gpud_ring* ring);

@@ -246,6 +246,31 @@ def test_ring_wrap_and_odd_start(ctx):
     r.close()
 
 
+@pytest.mark.parametrize("dt", ["uint32", "int32", "float32", "int64", "uint64"])
+def test_ring_push_raw_types(ctx, dt):
+    """raw NVML / DCGM sample types are widened on the device exactly like float64(v) on the host"""
+    F, n, W, cap = 40, 5000, 250, 4096
+    rng = np.random.default_rng(7)
+    if dt == "float32":
+        raw = (rng.standard_normal((n, F)) * 1e3).astype(np.float32)
+    elif dt == "uint64":
+        raw = rng.integers(0, 1 << 63, (n, F), dtype=np.uint64) * np.uint64(2) + np.uint64(1)      # above 2^53: rounding matters
+    elif dt == "int64":
+        raw = rng.integers(-(1 << 62), 1 << 62, (n, F), dtype=np.int64)
+    elif dt == "int32":
+        raw = rng.integers(-(1 << 31), 1 << 31, (n, F), dtype=np.int64).astype(np.int32)
+    else:
+        raw = rng.integers(0, 1 << 32, (n, F), dtype=np.uint64).astype(np.uint32)
+    x = raw.astype(np.float64)                       # numpy widens with round-to-nearest-even, like Go's float64(v)
+    thr = synth.thresholds_for(x)
+    ring = g.Ring(ctx, F, cap, W, thresholds=thr)
+    ring.push_raw(raw[:1234])                        # pageable, split pushes, wraps the ring
+    ring.push_raw(raw[1234:])
+    got = ring.reduce_all()
+    _check_windows(got, x[-cap:], W, thr)
+    ring.close()
+
+
 def test_ring_push_larger_than_capacity(ctx):
     F, cap, W = 3, 1024, 100
     x = synth.gauge_stream(F, 5000, seed=9)

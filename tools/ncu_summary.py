@@ -41,3 +41,14 @@ print("\nwarp-instructions executed per unit (%g units/launch): **%.1f**\n" % (u
 print("| opcode | per unit | stall samples |\n|---|---|---|", file=out)
 for op, c in hist.most_common(32):
     print("| %s | %.1f | %d |" % (op, c / units, stall[op]), file=out)
+
+# optional 4th argument: write {dram_bytes_read, dram_bytes_write} (bytes per launch) as JSON for bench.py's roofline.traffic
+if len(sys.argv) > 4:
+    import json
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    def val(k):
+        return float(v[h.index(k)].replace(",", "")) * scale[u[h.index(k)]]
+    json.dump({"dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
+               "gpu_time_us_under_ncu": float(v[h.index("gpu__time_duration.sum")].replace(",", "")),
+               "kernel": v[h.index("Kernel Name")] if "Kernel Name" in h else "?", "source": rep.split("/")[-1] + " (ncu --set full --clock-control none)"},
+              open(sys.argv[4], "w"), indent=1)
