@@ -452,6 +452,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       unsigned rows = __ballot_sync(kFull, nh == wmin.hi);
       unsigned nl = 0xffffffffu;
       const unsigned raw_min_hi = raw_hi_of(wmin.hi);
+      if (__popc(rows) > 6) {
+        // tie-heavy window (integer readings, flat gauges): most rows hold the minimum high word, so every lane scans its own
+        // row instead of the warp visiting the rows one by one
+        rows = 0u;
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const unsigned long long kv = sk[lane * kRowU64 + i];
+          if ((unsigned)(kv >> 32) == raw_min_hi && elem_index(lane, i) < m) nl = min(nl, true_lo(wmin.hi, (unsigned)kv));
+        }
+      }
       while (rows) {
         const int row = __ffs(rows) - 1;
         rows &= rows - 1;
@@ -476,10 +486,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       // Only rows whose maximum reaches L' can hold keys above it.
       const unsigned Lh = warp_kth_largest_smem(mh, k, s32, lane);
       // at least k lane maxima reach Lh, so at least k keys pass: the k-th largest of the gathered set is the answer
-      const int cnt = gather_rows<true>(wbase, __ballot_sync(kFull, mh >= Lh), Lh, 0u, lane, lt_mask);
-      if (cnt <= 32) {
-        ans = select_from_candidates(cand, cnt, k, lane, &wmax);
-        done = true;
+      // Several lanes sharing the bounding high word means ties around the order statistic (integer readings, flat or slowly
+      // moving gauges): materialising such a class costs one shared atomic per member (a flat gauge ran 4x slower than white
+      // noise).  Those windows skip to the 64-bit-bound path below, where a class of equal keys collapses to its value.
+      if (__popc(__ballot_sync(kFull, mh == Lh)) == 1) {
+        const int cnt = gather_rows<true>(wbase, __ballot_sync(kFull, mh >= Lh), Lh, 0u, lane, lt_mask);
+        if (cnt <= 32) {
+          ans = select_from_candidates(cand, cnt, k, lane, &wmax);
+          done = true;
+        }
       }
       __syncwarp();
     }

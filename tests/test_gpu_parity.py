@@ -246,6 +246,30 @@ def test_ring_wrap_and_odd_start(ctx):
     r.close()
 
 
+@pytest.mark.parametrize("W,qn,qd", [(1000, 99, 100), (1000, 50, 100), (1024, 999, 1000), (250, 90, 100), (64, 99, 100)])
+def test_ring_tie_heavy_gauges(ctx, W, qn, qd):
+    """integer readings, flat and slowly moving gauges: whole classes of equal keys around the order statistic"""
+    n, cap = 8000, 8192
+    rng = np.random.default_rng(W * 7 + qn)
+    cols = [rng.integers(30, 90, n).astype(np.float64),                       # degrees: ~16 copies of every value per window
+            np.full(n, 100.0),                                                # flat
+            60.0 + np.cumsum(rng.integers(-1, 2, n) * (rng.random(n) < 0.05)),   # slow integer walk: long runs
+            rng.integers(0, 2, n).astype(np.float64),                         # two values
+            -rng.integers(30, 90, n).astype(np.float64),                      # negative readings (keys of negative doubles)
+            rng.integers(0, 3, n).astype(np.float64) * -0.0,                  # +0 / -0 mix: distinct keys, equal values
+            rng.standard_normal(n).astype(np.float32).astype(np.float64).round(1),   # few distinct values with non-zero low words
+            (rng.integers(0, 4, n) + 0.1 * rng.integers(0, 3, n)).astype(np.float64),  # classes that share a high word but not the low word
+            np.where(rng.random(n) < 0.02, 500.0, 40.0),                      # flat with rare spikes
+            rng.integers(30000, 90000, n).astype(np.float64)]                 # mW: few ties
+    x = np.ascontiguousarray(np.stack(cols, axis=1))
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, x.shape[1], cap, W, thresholds=thr, q_num=qn, q_den=qd)
+    r.push(x)
+    got = r.reduce_all()
+    _check_windows(got, x, W, thr, 0.0, qn, qd)
+    r.close()
+
+
 @pytest.mark.parametrize("dt", ["uint32", "int32", "float32", "int64", "uint64"])
 def test_ring_push_raw_types(ctx, dt):
     """raw NVML / DCGM sample types are widened on the device exactly like float64(v) on the host"""
