@@ -288,15 +288,48 @@ extern "C" const char* gpud_nvlink_rule_hint(int32_t idx) {
   return h;
 }
 
-extern "C" const char* gpud_kmsg_event_name(int32_t kind) {          // nccl/kmsg_matcher.go:11, peermem/kmsg_matcher.go:13
-  if (kind == GPUD_KIND_NCCL_SEGFAULT) return "nvidia_nccl_segfault_in_libnccl";
-  if (kind == GPUD_KIND_PEERMEM_INVALID_CONTEXT) return "nvidia_peermem_invalid_context";
-  return "";
-}
-extern "C" const char* gpud_kmsg_event_message(int32_t kind) {       // nccl/kmsg_matcher.go:13, peermem/kmsg_matcher.go:15
-  if (kind == GPUD_KIND_NCCL_SEGFAULT) return "NCCL communication error (segfault in libnccl.so)";
-  if (kind == GPUD_KIND_PEERMEM_INVALID_CONTEXT) return "peermem error detected (possible GPU communication issue)";
-  return "";
+// (component, eventName, message) of the stateless kmsg line matchers, by hit kind.  nccl/kmsg_matcher.go:11-13,
+// peermem/kmsg_matcher.go:13-15, infiniband/kmsg_matcher.go:14-58, cpu/kmsg_matcher.go:17-31, os/kmsg_matcher.go:17-19,
+// disk/kmsg_matcher.go:10-56.
+namespace {
+struct KmsgEvent { const char *component, *event, *message; };
+const KmsgEvent kKmsgEvents[GPUD_KIND_COUNT] = {
+    {"", "", ""}, {"", "", ""}, {"", "", ""},
+    {"nccl", "nvidia_nccl_segfault_in_libnccl", "NCCL communication error (segfault in libnccl.so)"},
+    {"peermem", "nvidia_peermem_invalid_context", "peermem error detected (possible GPU communication issue)"},
+    {"infiniband", "pci_power_insufficient", "Insufficient power on MLX5 PCIe slot"},
+    {"infiniband", "port_module_high_temperature", "Overheated MLX5 adapter"},
+    {"infiniband", "access_reg_failed", "MLX5 ACCESS_REG command failed - device may have restricted PF access"},
+    {"cpu", "cpu_blocked_too_long", "CPU task blocked for more than 120 seconds"},
+    {"cpu", "cpu_soft_lockup", "CPU soft lockup detected, not releasing for a period of time"},
+    {"os", "vfs_file_max_limit_reached", "VFS file-max limit reached"},
+    {"disk", "raid_array_failure", "RAID array has failed due to disk failure"},
+    {"disk", "filesystem_read_only", "filesystem remounted as read-only due to errors"},
+    {"disk", "nvme_path_failure", "NVMe device has no available path, I/O failing"},
+    {"disk", "nvme_controller_timeout", "NVME controller I/O timeout detected, attempting reset"},
+    {"disk", "nvme_device_disabled", "NVME device disabled after reset failure"},
+    {"disk", "beyond_end_of_device", "I/O attempt beyond device boundaries detected"},
+    {"disk", "buffer_io_error", "Buffer I/O error detected on device"},
+    {"disk", "superblock_write_error", "I/O error while writing superblock"},
+};
+const KmsgEvent& kmsg_event(int32_t kind) { return kKmsgEvents[(kind > 0 && kind < GPUD_KIND_COUNT) ? kind : 0]; }
+}  // namespace
+extern "C" const char* gpud_kmsg_event_name(int32_t kind) { return kmsg_event(kind).event; }
+extern "C" const char* gpud_kmsg_event_message(int32_t kind) { return kmsg_event(kind).message; }
+extern "C" const char* gpud_kmsg_component(int32_t kind) { return kmsg_event(kind).component; }
+extern "C" int32_t gpud_kmsg_hit_message(const gpud_xid_hit* h, const uint8_t* buf, char* out, int32_t cap) {
+  if (!h || !out || cap <= 0) return -1;
+  std::string m = kmsg_event(h->kind).message;
+  std::string capture;
+  if (h->dev_len > 0) {
+    if ((h->flags & GPUD_HIT_DEV_TRUNCATED) && buf) capture.assign((const char*)buf + h->dev_off, (size_t)h->dev_len);
+    else capture.assign(h->device, strnlen(h->device, sizeof h->device));
+  }
+  if (h->kind == GPUD_KIND_CPU_BLOCKED_TOO_LONG || h->kind == GPUD_KIND_CPU_SOFT_LOCKUP) m += " (" + capture + ")";      // cpu/kmsg_matcher.go:54-63
+  else if (h->kind == GPUD_KIND_IB_ACCESS_REG_FAILED && !capture.empty()) m += " (PCI device " + capture + ")";           // infiniband/kmsg_matcher.go:136-142
+  if ((int32_t)m.size() + 1 > cap) return -1;
+  memcpy(out, m.c_str(), m.size() + 1);
+  return (int32_t)m.size();
 }
 
 // xidErrorEventDetail JSON (xid/health_state.go:284-315), field order and omitempty as encoding/json emits them;

@@ -28,8 +28,9 @@ constexpr int kChunk = 512;                 // bytes per warp step
 constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid ("
 constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVIDIA GPU "
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
-constexpr unsigned long long kFamN = 4ull;  // "segfault at"      (GPUD_SCAN_EXT_MATCHERS: nccl/kmsg_matcher.go:12)
-constexpr unsigned long long kFamP = 5ull;  // "ERROR detected invalid context, skipping further processing"   (peermem/kmsg_matcher.go:14)
+// families >= 4: the anchor literals of the extra line matchers (GPUD_SCAN_EXT_MATCHERS), index into kExtLit[]
+constexpr int kFamShift = 58;               // candidate word = byte offset | family << 58
+constexpr int kExtFam0 = 4, kNumFam = 19;
 constexpr int kModeMask = 0xff;
 constexpr unsigned kMatchLanes = 16;        // candidates per warp in k_scan_match
 
@@ -118,7 +119,7 @@ __device__ __noinline__ void filter_verify(const ScanBuf& b, int64_t a, bool is_
     if (!fam) return;
   }
   const unsigned long long slot = atomicAdd(n_cand, 1ull);
-  if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << 60);
+  if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << kFamShift);
 }
 
 // nvrm_family for the R3/R4 shapes, by the whole warp: the 32 bytes after "NVRM:" are fetched one per lane, the
@@ -138,13 +139,37 @@ __device__ __forceinline__ unsigned long long nvrm_family_coop(const ScanBuf& b,
   return (bad1 == 0u || bad2 == 0u) ? kFamB : 0ull;
 }
 
-// extra matchers (GPUD_SCAN_EXT_MATCHERS): four-byte anchor words and the literals the warp verifies behind them
-constexpr unsigned kSegf = 0x66676573u;   // "segf"
-constexpr unsigned kERRO = 0x4f525245u;   // "ERRO"
-__device__ const char kLitSegfault[] = "segfault at";
-__device__ const char kLitLibnccl[] = "in libnccl.so";
-__device__ const char kLitPeermem[] = "ERROR detected invalid context, skipping further processing";
-constexpr int kLenSegfault = 11, kLenLibnccl = 13, kLenPeermem = 59;
+// Extra line matchers (GPUD_SCAN_EXT_MATCHERS).  Every pattern contains a literal that each of its matches must contain:
+// the ANCHOR.  The filter looks the four bytes of every window up in a 32-slot perfect hash of the anchors' first words
+// (one multiply, one shift, one LDS, one compare per window - independent of the number of patterns), the warp verifies
+// the whole literal, and the match kernel runs the pattern's hand-written automaton from that position.
+//   fam  anchor literal                                             patterns (reference file:line)
+//    4   "segfault at"                                              nccl/kmsg_matcher.go:12
+//    5   "ERROR detected invalid context, skipping further processing"   peermem/kmsg_matcher.go:14
+//    6   "Detected insufficient power on the PCIe slot ("          infiniband/kmsg_matcher.go:15
+//    7   "Port module event"                                        infiniband/kmsg_matcher.go:25
+//    8   "mlx5_cmd_out_err"                                         infiniband/kmsg_matcher.go:57
+//    9   "task "                                                    cpu/kmsg_matcher.go:18
+//   10   "soft lockup - CPU#"                                       cpu/kmsg_matcher.go:30
+//   11   "VFS: file-max limit "                                     os/kmsg_matcher.go:18
+//   12   "md/raid"                                                  disk/kmsg_matcher.go:11
+//   13   "Remounting filesystem read-only"                          disk/kmsg_matcher.go:19
+//   14   "block nvme"                                               disk/kmsg_matcher.go:25
+//   15   "nvme nvme"                                                disk/kmsg_matcher.go:31,37
+//   16   "attempt to access beyond end of device"                   disk/kmsg_matcher.go:43
+//   17   "Buffer I/O error on dev "                                 disk/kmsg_matcher.go:49
+//   18   "I/O error while writing superblock"                       disk/kmsg_matcher.go:55
+struct ExtLit { unsigned char len; char text[63]; };
+#define GPUD_EXT_LITS \
+  {0, ""}, {4, "NVRM"}, {0, ""}, {4, "SXid"}, {11, "segfault at"}, {59, "ERROR detected invalid context, skipping further processing"}, \
+  {46, "Detected insufficient power on the PCIe slot ("}, {17, "Port module event"}, {16, "mlx5_cmd_out_err"}, {5, "task "}, \
+  {18, "soft lockup - CPU#"}, {20, "VFS: file-max limit "}, {7, "md/raid"}, {31, "Remounting filesystem read-only"}, {10, "block nvme"}, \
+  {9, "nvme nvme"}, {38, "attempt to access beyond end of device"}, {24, "Buffer I/O error on dev "}, {34, "I/O error while writing superblock"}
+__device__ const ExtLit kExtLit[kNumFam] = {GPUD_EXT_LITS};
+static const ExtLit kExtLitHost[kNumFam] = {GPUD_EXT_LITS};
+constexpr unsigned kHashMul = 0x9e3779dfu;   // (word * kHashMul) >> 27 is injective on the 17 anchor words (checked at start-up)
+struct ExtTab { unsigned word[32]; unsigned char fam[32]; };
+__device__ __forceinline__ unsigned ext_slot(unsigned x) { return (x * kHashMul) >> 27; }
 
 // whole warp: does the n-byte literal start at a?  One byte per lane and round.
 __device__ __forceinline__ bool coop_lit(const ScanBuf& b, int64_t a, const char* lit, int n, int lane) {
@@ -166,7 +191,13 @@ __device__ __forceinline__ bool lit_at_n(const ScanBuf& b, int64_t i, int64_t e,
 
 template <int MODE, bool EXT>
 __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
-                                                      unsigned long long* n_cand, unsigned long long cand_cap) {
+                                                      unsigned long long* n_cand, unsigned long long cand_cap, const ExtTab tab) {
+  __shared__ unsigned s_word[32];
+  __shared__ unsigned char s_fam[32];
+  if (EXT) {
+    if (threadIdx.x < 32) { s_word[threadIdx.x] = tab.word[threadIdx.x]; s_fam[threadIdx.x] = tab.fam[threadIdx.x]; }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -206,8 +237,8 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const unsigned x1 = __funnelshift_r(w[k], w[k + 1], 8), x2 = __funnelshift_r(w[k], w[k + 1], 16), x3 = __funnelshift_r(w[k], w[k + 1], 24);
-        hit = hit || w[k] == kNVRM || w[k] == kSXid || x1 == kNVRM || x1 == kSXid || x2 == kNVRM || x2 == kSXid || x3 == kNVRM || x3 == kSXid;
-        if (EXT) hit = hit || w[k] == kSegf || w[k] == kERRO || x1 == kSegf || x1 == kERRO || x2 == kSegf || x2 == kERRO || x3 == kSegf || x3 == kERRO;
+        if (EXT) hit = hit || s_word[ext_slot(w[k])] == w[k] || s_word[ext_slot(x1)] == x1 || s_word[ext_slot(x2)] == x2 || s_word[ext_slot(x3)] == x3;
+        else hit = hit || w[k] == kNVRM || w[k] == kSXid || x1 == kNVRM || x1 == kSXid || x2 == kNVRM || x2 == kSXid || x3 == kNVRM || x3 == kSXid;
         unsigned z = zero_bytes(w[k] ^ 0x0a0a0a0au);                           // '\n'
         if (MODE == GPUD_SCAN_RAW_KMSG) z &= ~zero_bytes(x1 ^ 0x20202020u);     // ... not followed by ' ' (continuation line)
         sepbits |= z >> (k + 4);                                                // bit 7 of each byte -> bit 3-k: four words share one POPC
@@ -229,21 +260,17 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
         const unsigned lo = k16 < 4 ? bw[0] : (k16 < 8 ? bw[1] : (k16 < 12 ? bw[2] : bw[3]));
         const unsigned hi = k16 < 4 ? bw[1] : (k16 < 8 ? bw[2] : (k16 < 12 ? bw[3] : bw[4]));
         const unsigned x = __funnelshift_r(lo, hi, 8 * (k16 & 3));
-        const unsigned is_nv = __ballot_sync(kFull, lane < 16 && x == kNVRM);
-        unsigned anchors = is_nv | __ballot_sync(kFull, lane < 16 && x == kSXid);
-        unsigned is_sg = 0, is_er = 0;
-        if (EXT) {
-          is_sg = __ballot_sync(kFull, lane < 16 && x == kSegf);
-          is_er = __ballot_sync(kFull, lane < 16 && x == kERRO);
-          anchors |= is_sg | is_er;
-        }
+        unsigned my_fam = 0;
+        if (EXT) { if (lane < 16 && s_word[ext_slot(x)] == x) my_fam = s_fam[ext_slot(x)]; }
+        else if (lane < 16) my_fam = x == kNVRM ? (unsigned)kFamX : (x == kSXid ? (unsigned)kFamS : 0u);
+        unsigned anchors = __ballot_sync(kFull, my_fam != 0u);
         const int64_t off0 = chunk * kChunk + (int64_t)src * 16;
         while (anchors) {
           const int k = __ffs(anchors) - 1;
           anchors &= anchors - 1;
           const int64_t a = off0 + k;
-          unsigned long long fam = kFamS;
-          if ((is_nv >> k) & 1u) {
+          unsigned long long fam = __shfl_sync(kFull, my_fam, k);
+          if (fam == kFamX) {
             // ": Xid (" must follow "NVRM": lanes 0..6 fetch one byte each (one 32-byte sector) and vote
             const int cb = lane < 7 ? ld8(b, a + 4 + lane) : 0;
             const unsigned long long pat = 0x2820646958203aull;            // bytes ':',' ','X','i','d',' ','(' little-endian
@@ -253,14 +280,12 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
             else if (bad & 1u) fam = 0;                                    // not even "NVRM:"
             else if (!is_ws(__shfl_sync(kFull, cb, 1))) fam = 0;          // R3/R4 need \s+ right after the colon
             else fam = nvrm_family_coop(b, a, lane);                      // whitespace run, then "GPU " / "The NVIDIA GPU "
-          } else if (EXT && ((is_sg >> k) & 1u)) {
-            fam = coop_lit(b, a, kLitSegfault, kLenSegfault, lane) ? kFamN : 0ull;
-          } else if (EXT && ((is_er >> k) & 1u)) {
-            fam = coop_lit(b, a, kLitPeermem, kLenPeermem, lane) ? kFamP : 0ull;
+          } else if (EXT && fam >= (unsigned long long)kExtFam0) {
+            if (!coop_lit(b, a, kExtLit[fam].text, kExtLit[fam].len, lane)) fam = 0;
           }
           if (fam && lane == 0) {
             const unsigned long long slot = atomicAdd(n_cand, 1ull);
-            if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << 60);
+            if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << kFamShift);
           }
         }
       }
@@ -739,6 +764,118 @@ __device__ bool sxid_match_unit(const ScanBuf& g, int64_t s, int64_t e, const gp
 }
 
 // ---------------------------------------------------------------------------------------------
+// Extra line matchers: the pattern behind a verified anchor literal at `a`, evaluated inside the message [ms, ue).
+// `.` never crosses '\n' (no (?s) in these patterns); negated classes do.  Returns the hit kind (0 = no match) and,
+// for the patterns with a capture the component puts in its message, the capture span.
+// ---------------------------------------------------------------------------------------------
+__device__ int64_t find_lit(const ScanBuf& b, int64_t from, int64_t to, const char* lit, int n) {   // first start in [from, to - n], else -1
+  const unsigned c0 = (unsigned char)lit[0];
+  for (int64_t i = find_byte(b, from, to, c0); i + n <= to; i = find_byte(b, i + 1, to, c0)) {
+    bool ok = true;
+    for (int k = 1; k < n && ok; ++k) ok = __ldg(b.p + i + k) == (uint8_t)lit[k];
+    if (ok) return i;
+  }
+  return -1;
+}
+template <int N>
+__device__ __forceinline__ int64_t find_lit(const ScanBuf& b, int64_t from, int64_t to, const char (&s)[N]) { return find_lit(b, from, to, s, N - 1); }
+__device__ __forceinline__ int64_t digits_end(const ScanBuf& b, int64_t p, int64_t e) { while (p < e && is_digit(ld8(b, p))) ++p; return p; }
+__device__ __forceinline__ bool is_word(int c) { return is_digit(c) || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_'; }
+
+__device__ int ext_match_at(int fam, const ScanBuf& b, int64_t a, int64_t ms, int64_t ue, int64_t* cap_off, int32_t* cap_len) {
+  const int64_t la = a + kExtLit[fam].len;                       // first byte after the anchor literal
+  const int64_t seg_e = find_byte(b, la, ue, '\n');              // `.` runs end here
+  switch (fam) {
+    case 4:    // `.*segfault at.*in libnccl\.so.*`
+      return find_lit(b, la, seg_e, "in libnccl.so") >= 0 ? GPUD_KIND_NCCL_SEGFAULT : 0;
+    case 5:    // `.*ERROR detected invalid context, skipping further processing`
+      return GPUD_KIND_PEERMEM_INVALID_CONTEXT;
+    case 6: {  // `Detected insufficient power on the PCIe slot \(([0-9]+W)\)`
+      const int64_t d = digits_end(b, la, ue);
+      return (d > la && lit_at(b, d, ue, "W)")) ? GPUD_KIND_IB_PCI_POWER_INSUFFICIENT : 0;
+    }
+    case 7:    // `Port module event.*High Temperature`
+      return find_lit(b, la, seg_e, "High Temperature") >= 0 ? GPUD_KIND_IB_PORT_MODULE_HIGH_TEMPERATURE : 0;
+    case 8: {  // `mlx5_cmd_out_err.*ACCESS_REG.*failed`
+      const int64_t o = find_lit(b, la, seg_e, "ACCESS_REG");
+      if (o < 0 || find_lit(b, o + 10, seg_e, "failed") < 0) return 0;
+      // message suffix: first `\b[0-9a-fA-F]{4}:[0-9a-fA-F]{2}:[0-9a-fA-F]{2}\.[0-7]\b` of the whole line (infiniband/kmsg_matcher.go:59,136-142)
+      for (int64_t i = ms; i + 12 <= ue; ++i) {
+        if (!is_hex(ld8(b, i)) || (i > ms && is_word(ld8(b, i - 1)))) continue;
+        if (is_hex(ld8(b, i + 1)) && is_hex(ld8(b, i + 2)) && is_hex(ld8(b, i + 3)) && ld8(b, i + 4) == ':' && is_hex(ld8(b, i + 5)) &&
+            is_hex(ld8(b, i + 6)) && ld8(b, i + 7) == ':' && is_hex(ld8(b, i + 8)) && is_hex(ld8(b, i + 9)) && ld8(b, i + 10) == '.' &&
+            ld8(b, i + 11) >= '0' && ld8(b, i + 11) <= '7' && (i + 12 >= ue || !is_word(ld8(b, i + 12)))) {
+          *cap_off = i; *cap_len = 12;
+          break;
+        }
+      }
+      return GPUD_KIND_IB_ACCESS_REG_FAILED;
+    }
+    case 9: {  // `(?:INFO: )?task ([^:]+:[\d]+).+blocked for more than \d+ seconds`
+      const int64_t q = find_byte(b, la, ue, ':');                // [^:]+ ends at the first colon (it may cross '\n')
+      if (q >= ue || q == la) return 0;
+      const int64_t dmax = digits_end(b, q + 1, ue);
+      if (dmax == q + 1) return 0;
+      const int64_t se = find_byte(b, q + 1, ue, '\n');           // the `.+` run and everything after it stay on this line
+      int64_t best = -1;                                           // last literal that is followed by `\d+ seconds`
+      for (int64_t o = find_lit(b, q + 3, se, "blocked for more than "); o >= 0; o = find_lit(b, o + 1, se, "blocked for more than ")) {
+        const int64_t d = digits_end(b, o + 22, se);
+        if (d > o + 22 && lit_at(b, d, se, " seconds")) best = o;
+      }
+      if (best < 0) return 0;
+      // [\d]+ is greedy but must leave one byte for `.+`: it gives digits back until the literal still fits
+      const int64_t dend = dmax < best - 1 ? dmax : best - 1;
+      if (dend <= q + 1) return 0;
+      *cap_off = la; *cap_len = (int32_t)(dend - la);
+      return GPUD_KIND_CPU_BLOCKED_TOO_LONG;
+    }
+    case 10: { // `soft lockup - CPU#\d+ stuck for \d+s! \[([^:]+:[\d]+)\]`
+      int64_t p = digits_end(b, la, ue);
+      if (p == la || !lit_at(b, p, ue, " stuck for ")) return 0;
+      const int64_t p2 = digits_end(b, p + 11, ue);
+      if (p2 == p + 11 || !lit_at(b, p2, ue, "s! [")) return 0;
+      const int64_t c0 = p2 + 4;
+      const int64_t q = find_byte(b, c0, ue, ':');
+      if (q >= ue || q == c0) return 0;
+      const int64_t d = digits_end(b, q + 1, ue);
+      if (d == q + 1 || d >= ue || ld8(b, d) != ']') return 0;
+      *cap_off = c0; *cap_len = (int32_t)(d - c0);
+      return GPUD_KIND_CPU_SOFT_LOCKUP;
+    }
+    case 11: { // `VFS: file-max limit \d+ reached`
+      const int64_t d = digits_end(b, la, ue);
+      return (d > la && lit_at(b, d, ue, " reached")) ? GPUD_KIND_OS_VFS_FILE_MAX_LIMIT_REACHED : 0;
+    }
+    case 12: { // `md/raid.*: Disk failure on .* detected, failing array`
+      const int64_t o = find_lit(b, la, seg_e, ": Disk failure on ");
+      return (o >= 0 && find_lit(b, o + 18, seg_e, " detected, failing array") >= 0) ? GPUD_KIND_DISK_RAID_ARRAY_FAILURE : 0;
+    }
+    case 13:   // `.*Remounting filesystem read-only`
+      return GPUD_KIND_DISK_FILESYSTEM_READ_ONLY;
+    case 14:   // `block nvme.*: no available path - failing I/O`
+      return find_lit(b, la, seg_e, ": no available path - failing I/O") >= 0 ? GPUD_KIND_DISK_NVME_PATH_FAILURE : 0;
+    case 15: { // `nvme nvme[0-9]+: I/O .* timeout, reset controller` | `nvme nvme[0-9]+: Disabling device after reset failure`
+      const int64_t d = digits_end(b, la, ue);
+      if (d == la) return 0;
+      if (lit_at(b, d, ue, ": I/O ")) return find_lit(b, d + 6, seg_e, " timeout, reset controller") >= 0 ? GPUD_KIND_DISK_NVME_TIMEOUT : 0;
+      return lit_at(b, d, ue, ": Disabling device after reset failure") ? GPUD_KIND_DISK_NVME_DEVICE_DISABLED : 0;
+    }
+    case 16:   // `attempt to access beyond end of device`
+      return GPUD_KIND_DISK_BEYOND_END_OF_DEVICE;
+    case 17: { // `Buffer I/O error on dev [^ ]+, logical block [0-9]+`: the literal's second byte is a space, so the
+               // non-space run must end in the comma and hold at least one byte before it
+      int64_t r = la;
+      while (r < ue && ld8(b, r) != ' ') ++r;
+      if (r - la < 2 || ld8(b, r - 1) != ',' || !lit_at(b, r, ue, " logical block ")) return 0;
+      return (r + 15 < ue && is_digit(ld8(b, r + 15))) ? GPUD_KIND_DISK_BUFFER_IO_ERROR : 0;
+    }
+    case 18:   // `I/O error while writing superblock`
+      return GPUD_KIND_DISK_SUPERBLOCK_WRITE_ERROR;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5c: one thread per candidate anchor
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool is_sep(const ScanBuf& b, int64_t i, int mode) {
@@ -760,8 +897,8 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
   const unsigned long long slots = (((unsigned long long)gridDim.x * blockDim.x) >> 5) * kMatchLanes;
   for (unsigned long long ci = slot0; ci < n; ci += slots) {
     const unsigned long long cv = cands[ci];
-    const unsigned long long fam = cv >> 60;
-    const int64_t a = (int64_t)(cv & ((1ull << 60) - 1));
+    const unsigned long long fam = cv >> kFamShift;
+    const int64_t a = (int64_t)(cv & ((1ull << kFamShift) - 1));
     // unit bounds
     int64_t us = a, ue = a;
     for (;;) {                                             // previous separator: a '\n' (in RAW mode one not followed by ' ')
@@ -796,40 +933,23 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
       ms = semi + 1;
       if (a < ms) continue;
     }
-    if (fam == kFamN || fam == kFamP) {                  // extra matchers: literal-only patterns, `.` never crosses '\n'
-      const bool is_n = fam == kFamN;
-      const char* lit = is_n ? kLitSegfault : kLitPeermem;
-      const int ln = is_n ? kLenSegfault : kLenPeermem;
-      const unsigned c0 = is_n ? 's' : 'E';
-      bool first_ext = true;                               // one hit per unit: its first anchor looks at every later one
-      for (int64_t i = find_byte(b, ms, a, c0); i < a && first_ext; i = find_byte(b, i + 1, a, c0))
-        if (lit_at_n(b, i, ue, lit, ln)) first_ext = false;
-      if (!first_ext) continue;
-      bool ok_ext = !is_n;
-      if (is_n) {
-        // `.*segfault at.*in libnccl\.so.*`: both literals inside one '\n'-free segment, the second starting after the first ends
-        int64_t p = a;
-        while (p < ue && !ok_ext) {
-          const int64_t seg_e = find_byte(b, p, ue, '\n');
-          for (int64_t j = find_byte(b, p + kLenSegfault, seg_e, 'i'); j < seg_e && !ok_ext; j = find_byte(b, j + 1, seg_e, 'i'))
-            if (lit_at_n(b, j, seg_e, kLitLibnccl, kLenLibnccl)) ok_ext = true;
-          if (ok_ext) break;
-          p = seg_e + 1;                                   // next segment of the record: its first "segfault at"
-          for (;;) {
-            p = find_byte(b, p, ue, 's');
-            if (p >= ue || lit_at_n(b, p, ue, kLitSegfault, kLenSegfault)) break;
-            ++p;
-          }
-        }
-      }
-      if (!ok_ext) continue;
+    if (fam >= (unsigned long long)kExtFam0) {          // extra line matchers: every verified anchor is tried on its own;
+      int64_t cap_off = 0;                                 // duplicates per (unit, kind) are dropped on the host (leftmost wins)
+      int32_t cap_len = 0;
+      const int kind = ext_match_at((int)fam, b, a, ms, ue, &cap_off, &cap_len);
+      if (!kind) continue;
       gpud_xid_hit h;
       memset(&h, 0, sizeof h);
-      h.kind = is_n ? GPUD_KIND_NCCL_SEGFAULT : GPUD_KIND_PEERMEM_INVALID_CONTEXT;
+      h.kind = kind;
       h.event_type = GPUD_EVENT_WARNING;                   // pkg/kmsg/syncer.go:94
       h.n_actions = -1;
       h.rule_index = -1;
       h.unit_offset = us;
+      h.pid_off = a;                                       // where the match is anchored (ties between candidates of one unit)
+      h.dev_off = cap_off;
+      h.dev_len = cap_len;
+      for (int i = 0; i < cap_len && i < 39; ++i) h.device[i] = (char)ld8(b, cap_off + i);
+      if (cap_len > 39) h.flags |= GPUD_HIT_DEV_TRUNCATED;
       h.kmsg_priority = (int32_t)k_prio;
       h.kmsg_seq = k_seq;
       h.kmsg_usec = k_usec;
@@ -958,6 +1078,27 @@ static cudaError_t grow(T** p, size_t* cap, size_t need) {
   return e;
 }
 
+static const ExtTab& ext_tab() {
+  static ExtTab t;
+  static bool ready = false;
+  if (!ready) {
+    memset(&t, 0, sizeof t);
+    for (int i = 0; i < 32; ++i) t.word[i] = 0xffffffffu;       // never equal to a window that hashes to a free slot ... except slot(~0): family 0
+    for (int f = 1; f < kNumFam; ++f) {
+      if (!kExtLitHost[f].len) continue;
+      if (strlen(kExtLitHost[f].text) != kExtLitHost[f].len) abort();
+      unsigned w;
+      memcpy(&w, kExtLitHost[f].text, 4);
+      const unsigned slot = (w * kHashMul) >> 27;
+      if (t.fam[slot]) abort();                                  // the multiplier must stay injective when a pattern is added
+      t.word[slot] = w;
+      t.fam[slot] = (unsigned char)f;
+    }
+    ready = true;
+  }
+  return t;
+}
+
 static bool scan_mode_ok(int32_t mode) {
   const int32_t base = mode & ~GPUD_SCAN_EXT_MATCHERS;
   return base == GPUD_SCAN_LINES || base == GPUD_SCAN_RAW_KMSG;
@@ -987,10 +1128,10 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   mode &= kModeMask;
   const int grid = std::max(grid_f, 1);
   const unsigned long long ccap = (unsigned long long)s->cand_cap;
-  if (mode == GPUD_SCAN_LINES && !ext) k_scan_filter<GPUD_SCAN_LINES, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
-  else if (mode == GPUD_SCAN_LINES) k_scan_filter<GPUD_SCAN_LINES, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
-  else if (!ext) k_scan_filter<GPUD_SCAN_RAW_KMSG, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
-  else k_scan_filter<GPUD_SCAN_RAW_KMSG, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap);
+  if (mode == GPUD_SCAN_LINES && !ext) k_scan_filter<GPUD_SCAN_LINES, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
+  else if (mode == GPUD_SCAN_LINES) k_scan_filter<GPUD_SCAN_LINES, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
+  else if (!ext) k_scan_filter<GPUD_SCAN_RAW_KMSG, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
+  else k_scan_filter<GPUD_SCAN_RAW_KMSG, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[1], st);
   k_scan_prefix_tiles<<<(unsigned)n_tiles, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_local, n_chunks, s->d_tile_base);
@@ -1025,9 +1166,23 @@ static int32_t scan_collect(gpud_ctx* ctx, gpud_scan_state* s, gpud_xid_hit* hit
   std::sort(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
     return a.unit_index != b.unit_index ? a.unit_index < b.unit_index : a.kind < b.kind;
   });
-  const int64_t n_copy = std::min<int64_t>(have, cap);
+  // extra line matchers: several anchors of one unit may match the same pattern; the reference reports the leftmost
+  if (have == found) {
+    std::stable_sort(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
+      if (a.unit_index != b.unit_index) return a.unit_index < b.unit_index;
+      if (a.kind != b.kind) return a.kind < b.kind;
+      return a.kind > GPUD_KIND_SXID && a.pid_off < b.pid_off;
+    });
+    tmp.erase(std::unique(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
+                return a.kind > GPUD_KIND_SXID && a.unit_index == b.unit_index && a.kind == b.kind;
+              }), tmp.end());
+  }
+  const int64_t found_u = have == found ? (int64_t)tmp.size() : found;
+  if (n_hits) *n_hits = found_u;
+  const int64_t have_u = (int64_t)tmp.size();
+  const int64_t n_copy = std::min<int64_t>(have_u, cap);
   if (n_copy && hits) memcpy(hits, tmp.data(), (size_t)n_copy * sizeof(gpud_xid_hit));
-  if (found > cap || found > have) return gpud_fail(ctx, GPUD_E_CAPACITY, "%lld hits, caller capacity %lld", (long long)found, (long long)cap);
+  if (found_u > cap || found > have) return gpud_fail(ctx, GPUD_E_CAPACITY, "%lld hits, caller capacity %lld", (long long)found_u, (long long)cap);
   return GPUD_OK;
 }
 

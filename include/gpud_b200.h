@@ -114,11 +114,26 @@ int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64,
 enum { GPUD_SCAN_LINES = 0,   /* units are '\n'-separated lines (strings.Split(buf, "\n"))                  */
        GPUD_SCAN_RAW_KMSG = 1 /* units are /dev/kmsg records "prio,seq,usec,flags;msg" (+ " KEY=val" lines);
                                  Match runs on the message part (pkg/kmsg/watcher.go:292-332)               */ };
-/* OR into `mode`: also run the next kmsg matchers of the reference on every unit:
- *   nccl     `.*segfault at.*in libnccl\.so.*`            components/accelerator/nvidia/nccl/kmsg_matcher.go:12
- *   peermem  `.*ERROR detected invalid context, skipping further processing`   .../peermem/kmsg_matcher.go:14 */
+/* OR into `mode`: also run the stateless line matchers of the other kmsg-reading components on every unit (SURVEY.md
+ * 8f.1), one hit per (unit, pattern); the pattern is the hit's `kind`:
+ *   nccl        `.*segfault at.*in libnccl\.so.*`                      components/accelerator/nvidia/nccl/kmsg_matcher.go:12
+ *   peermem     `.*ERROR detected invalid context, skipping further processing`      .../peermem/kmsg_matcher.go:14
+ *   infiniband  pci power / port module temperature / ACCESS_REG        .../infiniband/kmsg_matcher.go:15,25,57
+ *   cpu         blocked too long / soft lockup (capture: "comm:pid")    components/cpu/kmsg_matcher.go:18,30
+ *   os          VFS file-max limit reached                              components/os/kmsg_matcher.go:18
+ *   disk        the eight patterns of                                   components/disk/kmsg_matcher.go:11-55
+ * For these kinds dev_off/dev_len (and device[], truncated) hold the capture the component appends to its message
+ * (cpu: process info; infiniband ACCESS_REG: the first PCI BDF of the line; else empty) and pid_off the byte offset the
+ * match is anchored at.  Not covered: the two STATEFUL matchers (os kernel-panic assembly, memory OOM parser). */
 #define GPUD_SCAN_EXT_MATCHERS 0x100
-enum { GPUD_KIND_XID = 1, GPUD_KIND_SXID = 2, GPUD_KIND_NCCL_SEGFAULT = 3, GPUD_KIND_PEERMEM_INVALID_CONTEXT = 4 };
+enum {
+  GPUD_KIND_XID = 1, GPUD_KIND_SXID = 2, GPUD_KIND_NCCL_SEGFAULT = 3, GPUD_KIND_PEERMEM_INVALID_CONTEXT = 4,
+  GPUD_KIND_IB_PCI_POWER_INSUFFICIENT = 5, GPUD_KIND_IB_PORT_MODULE_HIGH_TEMPERATURE = 6, GPUD_KIND_IB_ACCESS_REG_FAILED = 7,
+  GPUD_KIND_CPU_BLOCKED_TOO_LONG = 8, GPUD_KIND_CPU_SOFT_LOCKUP = 9, GPUD_KIND_OS_VFS_FILE_MAX_LIMIT_REACHED = 10,
+  GPUD_KIND_DISK_RAID_ARRAY_FAILURE = 11, GPUD_KIND_DISK_FILESYSTEM_READ_ONLY = 12, GPUD_KIND_DISK_NVME_PATH_FAILURE = 13,
+  GPUD_KIND_DISK_NVME_TIMEOUT = 14, GPUD_KIND_DISK_NVME_DEVICE_DISABLED = 15, GPUD_KIND_DISK_BEYOND_END_OF_DEVICE = 16,
+  GPUD_KIND_DISK_BUFFER_IO_ERROR = 17, GPUD_KIND_DISK_SUPERBLOCK_WRITE_ERROR = 18, GPUD_KIND_COUNT = 19
+};
 enum { GPUD_EVENT_UNKNOWN = 0, GPUD_EVENT_INFO = 1, GPUD_EVENT_WARNING = 2, GPUD_EVENT_CRITICAL = 3, GPUD_EVENT_FATAL = 4 };
 enum { GPUD_ACT_IGNORE_NO_ACTION_REQUIRED = 1, GPUD_ACT_REBOOT_SYSTEM = 2, GPUD_ACT_HARDWARE_INSPECTION = 3,
        GPUD_ACT_CHECK_USER_APP_AND_GPU = 4 };
@@ -190,6 +205,12 @@ const char* gpud_nvlink_rule_hint(int32_t rule_index);
 /* kmsg.MatchFunc results (eventName, message) of the extra matchers, by hit kind; "" for xid / sxid kinds. */
 const char* gpud_kmsg_event_name(int32_t kind);
 const char* gpud_kmsg_event_message(int32_t kind);
+/* Component name that owns the pattern ("nccl", "peermem", "infiniband", "cpu", "os", "disk"). */
+const char* gpud_kmsg_component(int32_t kind);
+/* The message `Match` returns for this hit: the pattern's text plus the capture where the reference appends one
+ * (cpu/kmsg_matcher.go:54-63, infiniband/kmsg_matcher.go:136-142).  `buf` is the scanned buffer (needed only when the
+ * capture is longer than device[]: GPUD_HIT_DEV_TRUNCATED) or NULL.  Returns the length, -1 if `cap` is too small. */
+int32_t gpud_kmsg_hit_message(const gpud_xid_hit* hit, const uint8_t* buf, char* out, int32_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-box NVLink / fabric view.

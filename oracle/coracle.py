@@ -60,11 +60,14 @@ def sxid_match(line: bytes):
     return h if L.orc_sxid_match(line, C.c_int32(len(line)), C.byref(h)) else None
 
 
-def ext_match(line: bytes) -> int:
-    """bit 0 = nccl segfault-in-libnccl matcher, bit 1 = peermem invalid-context matcher."""
+def ext_match(line: bytes):
+    """(bitmask, captures): bit i = pattern of hit kind 3 + i fires; captures[kind] = group 1 of the cpu patterns"""
     L = lib()
     L.orc_ext_match.restype = C.c_int32
-    return L.orc_ext_match(line, C.c_int32(len(line)))
+    cap = (C.c_int32 * 32)()
+    m = L.orc_ext_match(line, C.c_int32(len(line)), cap)
+    caps = {3 + i: line[cap[2 * i]:cap[2 * i + 1]] for i in range(16) if (m >> i) & 1 and cap[2 * i] >= 0}
+    return m, caps
 
 
 def scan_lines(buf: bytes, threads: int = 0, cap: int = 1 << 20, ext: bool = False):

@@ -136,7 +136,7 @@ void orc_windows_fields(const double* ring, int32_t F, int64_t n, int32_t W, con
 #include "../gpud_b200/csrc/catalog_data.inc"   /* DATA ONLY: generated tables (tools/gen_catalog.py) */
 
 /* components/accelerator/nvidia/xid/kmsg.go:22,29,38,43 ; sxid/kmsg.go:17,20 — verbatim */
-static const char* RX[8] = {
+static const char* RX[22] = {
     "NVRM: Xid \\(((?:PCI:)?[0-9a-fA-F:]+)\\).*?: (\\d+),",
     "NVRM: Xid \\(PCI:([0-9a-fA-F:]+)\\): (\\d+)(?:, pid=(\\d+), name=([^,]+))?, ([A-Z_]+(?:/[A-Z_]+)?)\\s+(Nonfatal|Fatal)\\s+(XC[01])\\s+(i\\d+)\\s+Link\\s+(-?\\d+)\\s+\\((0x[0-9a-fA-F]+)\\s+(0x[0-9a-fA-F]+)(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?",
     "(?s)NVRM:\\s+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\\.0.*?fallen off the bus and is not responding to commands\\.",
@@ -145,10 +145,27 @@ static const char* RX[8] = {
     "SXid \\((PCI:[0-9a-fA-F:\\.]+)\\)",
     /* next matchers on the same scanner: nccl/kmsg_matcher.go:12 ; peermem/kmsg_matcher.go:14 — verbatim */
     ".*segfault at.*in libnccl\\.so.*",
-    ".*ERROR detected invalid context, skipping further processing"};
-static orx_prog* PR[8];
+    ".*ERROR detected invalid context, skipping further processing",
+    /* infiniband/kmsg_matcher.go:15,25,57 ; cpu/kmsg_matcher.go:18,30 ; os/kmsg_matcher.go:18 ; disk/kmsg_matcher.go:11-55 — verbatim */
+    "Detected insufficient power on the PCIe slot \\(([0-9]+W)\\)",
+    "Port module event.*High Temperature",
+    "mlx5_cmd_out_err.*ACCESS_REG.*failed",
+    "(?:INFO: )?task ([^:]+:[\\d]+).+blocked for more than \\d+ seconds",
+    "soft lockup - CPU#\\d+ stuck for \\d+s! \\[([^:]+:[\\d]+)\\]",
+    "VFS: file-max limit \\d+ reached",
+    "md/raid.*: Disk failure on .* detected, failing array",
+    ".*Remounting filesystem read-only",
+    "block nvme.*: no available path - failing I/O",
+    "nvme nvme[0-9]+: I/O .* timeout, reset controller",
+    "nvme nvme[0-9]+: Disabling device after reset failure",
+    "attempt to access beyond end of device",
+    "Buffer I/O error on dev [^ ]+, logical block [0-9]+",
+    "I/O error while writing superblock"};
+#define ORC_N_RX 22
+#define ORC_N_EXT 16          /* RX[6 + i] is hit kind 3 + i */
+static orx_prog* PR[ORC_N_RX];
 static pthread_once_t rx_once = PTHREAD_ONCE_INIT;
-static void rx_init(void) { for (int i = 0; i < 8; ++i) PR[i] = orx_compile(RX[i]); }
+static void rx_init(void) { for (int i = 0; i < ORC_N_RX; ++i) PR[i] = orx_compile(RX[i]); }
 int32_t orc_regex_ok(void) {
   pthread_once(&rx_once, rx_init);
   for (int i = 0; i < 6; ++i) if (!PR[i]) return 0;
@@ -260,14 +277,20 @@ int32_t orc_sxid_match(const char* s, int32_t n, orc_hit* h) {
   return 1;
 }
 
-/* HasNCCLSegfaultInLibnccl / HasPeermemInvalidContext (nccl/kmsg_matcher.go:20-25, peermem/kmsg_matcher.go:22-27):
- * bit 0 = nccl segfault, bit 1 = peermem invalid context. */
-int32_t orc_ext_match(const char* s, int32_t n) {
+/* The Has* functions of the stateless line matchers (e.g. nccl/kmsg_matcher.go:20-25, disk/kmsg_matcher.go:70-125):
+ * bit i = pattern of hit kind 3 + i fires.  cap[2*i], cap[2*i+1] = span of capture group 1 (cpu patterns), -1 if none. */
+int32_t orc_ext_match(const char* s, int32_t n, int32_t* cap) {
   pthread_once(&rx_once, rx_init);
-  int c[4];
+  int c[8];
   int32_t m = 0;
-  if (orx_search(PR[6], s, n, c)) m |= 1;
-  if (orx_search(PR[7], s, n, c)) m |= 2;
+  for (int i = 0; i < ORC_N_EXT; ++i) {
+    if (cap) cap[2 * i] = cap[2 * i + 1] = -1;
+    c[2] = c[3] = -1;
+    if (orx_search(PR[6 + i], s, n, c)) {
+      m |= 1 << i;
+      if (cap && (i == 5 || i == 6)) { cap[2 * i] = c[2]; cap[2 * i + 1] = c[3]; }
+    }
+  }
   return m;
 }
 
@@ -286,9 +309,9 @@ static void orc_scan_one(void* a, int64_t idx) {
         if (orc_xid_match(P->buf + ls, n, &h)) { h.line = line; h.offset = ls; if (P->n < P->cap) P->hits[P->n] = h; ++P->n; }
         if (orc_sxid_match(P->buf + ls, n, &h)) { h.line = line; h.offset = ls; if (P->n < P->cap) P->hits[P->n] = h; ++P->n; }
       }
-      if (P->ext && n >= 11 && (memmem(P->buf + ls, (size_t)n, "segfault at", 11) || memmem(P->buf + ls, (size_t)n, "ERROR detected", 14))) {
-        const int32_t m = orc_ext_match(P->buf + ls, n);
-        for (int k = 0; k < 2; ++k)
+      if (P->ext && n >= 7) {
+        const int32_t m = orc_ext_match(P->buf + ls, n, NULL);
+        for (int k = 0; k < ORC_N_EXT; ++k)
           if (m & (1 << k)) {
             orc_hit h;
             memset(&h, 0, sizeof h);

@@ -39,9 +39,38 @@ R3 = re.compile(rb"(?s)NVRM:[\t\n\f\r ]+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9
 R4 = re.compile(rb"NVRM:[\t\n\f\r ]+GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\.0:[\t\n\f\r ]+GPU has fallen off the bus\.?")
 R5 = re.compile(rb"SXid.*?: (\d+),")
 R6 = re.compile(rb"SXid \((PCI:[0-9a-fA-F:\.]+)\)")
-# next matchers riding the same scanner: nccl/kmsg_matcher.go:12, peermem/kmsg_matcher.go:14 (verbatim)
-R_NCCL = re.compile(rb".*segfault at.*in libnccl\.so.*")
-R_PEERMEM = re.compile(rb".*ERROR detected invalid context, skipping further processing")
+# next matchers riding the same scanner: the stateless line patterns, regex strings verbatim.
+# (kind, component, eventName, message, regex, capture group appended to the message or None) -- reference file:line
+EXT_PATTERNS = [
+    (3, "nccl", "nvidia_nccl_segfault_in_libnccl", "NCCL communication error (segfault in libnccl.so)",
+     rb".*segfault at.*in libnccl\.so.*", None),                                           # nccl/kmsg_matcher.go:11-13
+    (4, "peermem", "nvidia_peermem_invalid_context", "peermem error detected (possible GPU communication issue)",
+     rb".*ERROR detected invalid context, skipping further processing", None),            # peermem/kmsg_matcher.go:13-15
+    (5, "infiniband", "pci_power_insufficient", "Insufficient power on MLX5 PCIe slot",
+     rb"Detected insufficient power on the PCIe slot \(([0-9]+W)\)", None),                # infiniband/kmsg_matcher.go:14-16
+    (6, "infiniband", "port_module_high_temperature", "Overheated MLX5 adapter",
+     rb"Port module event.*High Temperature", None),                                      # infiniband/kmsg_matcher.go:24-26
+    (7, "infiniband", "access_reg_failed", "MLX5 ACCESS_REG command failed - device may have restricted PF access",
+     rb"mlx5_cmd_out_err.*ACCESS_REG.*failed", None),                                     # infiniband/kmsg_matcher.go:56-58
+    (8, "cpu", "cpu_blocked_too_long", "CPU task blocked for more than 120 seconds",
+     rb"(?:INFO: )?task ([^:]+:[\d]+).+blocked for more than \d+ seconds", 1),             # cpu/kmsg_matcher.go:17-19
+    (9, "cpu", "cpu_soft_lockup", "CPU soft lockup detected, not releasing for a period of time",
+     rb"soft lockup - CPU#\d+ stuck for \d+s! \[([^:]+:[\d]+)\]", 1),                      # cpu/kmsg_matcher.go:29-31
+    (10, "os", "vfs_file_max_limit_reached", "VFS file-max limit reached", rb"VFS: file-max limit \d+ reached", None),   # os/kmsg_matcher.go:17-19
+    (11, "disk", "raid_array_failure", "RAID array has failed due to disk failure",
+     rb"md/raid.*: Disk failure on .* detected, failing array", None),                    # disk/kmsg_matcher.go:10-12
+    (12, "disk", "filesystem_read_only", "filesystem remounted as read-only due to errors", rb".*Remounting filesystem read-only", None),   # :18-20
+    (13, "disk", "nvme_path_failure", "NVMe device has no available path, I/O failing", rb"block nvme.*: no available path - failing I/O", None),   # :24-26
+    (14, "disk", "nvme_controller_timeout", "NVME controller I/O timeout detected, attempting reset",
+     rb"nvme nvme[0-9]+: I/O .* timeout, reset controller", None),                         # :30-32
+    (15, "disk", "nvme_device_disabled", "NVME device disabled after reset failure", rb"nvme nvme[0-9]+: Disabling device after reset failure", None),   # :36-38
+    (16, "disk", "beyond_end_of_device", "I/O attempt beyond device boundaries detected", rb"attempt to access beyond end of device", None),   # :42-44
+    (17, "disk", "buffer_io_error", "Buffer I/O error detected on device", rb"Buffer I/O error on dev [^ ]+, logical block [0-9]+", None),   # :48-50
+    (18, "disk", "superblock_write_error", "I/O error while writing superblock", rb"I/O error while writing superblock", None),   # :54-56
+]
+EXT_RE = {k: re.compile(rx) for k, _c, _e, _m, rx, _g in EXT_PATTERNS}
+EXT_BY_KIND = {k: (c, e, m, g) for k, c, e, m, _rx, g in EXT_PATTERNS}
+R_PCI_DEVICE = re.compile(rb"\b[0-9a-fA-F]{4}:[0-9a-fA-F]{2}:[0-9a-fA-F]{2}\.[0-7]\b")       # infiniband/kmsg_matcher.go:59
 # NOTE: Go/RE2 `\s` is [\t\n\f\r ] (no \v); Python bytes `\s` also matches \v, hence the explicit class.
 
 INT64_MAX = (1 << 63) - 1
@@ -452,14 +481,41 @@ def sxid_match(line: bytes):                                          # sxid/kms
 
 
 def ext_match(line: bytes):
-    """kinds of the extra matchers that fire on this line: 3 = nccl segfault, 4 = peermem invalid context
-    (nccl/kmsg_matcher.go:20-35, peermem/kmsg_matcher.go:22-37: FindStringSubmatch != nil)."""
-    out = []
-    if R_NCCL.search(line):
-        out.append(3)
-    if R_PEERMEM.search(line):
-        out.append(4)
-    return out
+    """kinds of the extra line patterns that fire on this line, ascending (FindStringSubmatch != nil, e.g.
+    nccl/kmsg_matcher.go:20-25, disk/kmsg_matcher.go:70-125)."""
+    return [k for k, *_ in EXT_PATTERNS if EXT_RE[k].search(line)]
+
+
+def ext_capture(kind: int, line: bytes) -> bytes:
+    """the text the component appends to its message: cpu process info (cpu/kmsg_matcher.go:38-52), the first PCI BDF of an
+    ACCESS_REG line (infiniband/kmsg_matcher.go:136-142), else empty"""
+    g = EXT_BY_KIND[kind][3]
+    if g is not None:
+        return EXT_RE[kind].search(line).group(g)
+    if kind == 7:
+        m = R_PCI_DEVICE.search(line)
+        return m.group(0) if m else b""
+    return b""
+
+
+def ext_message(kind: int, line: bytes) -> str:
+    """the message string `Match` returns for a line on which pattern `kind` fires"""
+    msg = EXT_BY_KIND[kind][2]
+    cap = ext_capture(kind, line).decode("latin-1")
+    if kind in (8, 9):
+        return msg + " (" + cap + ")"
+    if kind == 7 and cap:
+        return msg + " (PCI device " + cap + ")"
+    return msg
+
+
+def component_match(component: str, line: bytes):
+    """(eventName, message) of the first pattern of `component` that fires, in the component's own order
+    (e.g. disk/kmsg_matcher.go:127-134, 143-154); ("", "") if none"""
+    for k, c, e, _m, _rx, _g in EXT_PATTERNS:
+        if c == component and EXT_RE[k].search(line):
+            return e, ext_message(k, line)
+    return "", ""
 
 
 def scan_lines(buf: bytes, ext: bool = False):
@@ -485,7 +541,8 @@ def scan_lines(buf: bytes, ext: bool = False):
                          "hint": "", "description": ""})
         if ext:
             for kind in ext_match(line):
-                hits.append({"line": ln, "offset": off, "kind": kind, "code": 0, "device": "", "event_type": EV_WARNING, "actions": [],
+                hits.append({"line": ln, "offset": off, "kind": kind, "code": 0, "device": ext_capture(kind, line).decode("latin-1")[:39],
+                             "capture": ext_capture(kind, line), "message": ext_message(kind, line), "event_type": EV_WARNING, "actions": [],
                              "extended": False, "sub_code": 0, "unit": "", "error_status": 0, "intrinfo": 0, "link": 0, "hint": "", "description": ""})
         off += len(line) + 1
     return hits
@@ -650,7 +707,8 @@ def scan_raw_kmsg(buf: bytes, ext: bool = False):
                          "extended": False, "sub_code": 0, "error_status": 0})
         if ext:
             for kind in ext_match(m):
-                hits.append({"line": idx, "offset": off, "kind": kind, "code": 0, "device": "", "event_type": EV_WARNING, "actions": [],
+                hits.append({"line": idx, "offset": off, "kind": kind, "code": 0, "device": ext_capture(kind, m).decode("latin-1")[:39],
+                             "capture": ext_capture(kind, m), "message": ext_message(kind, m), "event_type": EV_WARNING, "actions": [],
                              "kmsg": (prio, seq, usec), "extended": False, "sub_code": 0, "error_status": 0})
         off += len(rec) + 1
     return hits, len(recs)

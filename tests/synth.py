@@ -88,11 +88,44 @@ EDGE_LINES = [
 
 
 def ext_lines():
-    """every line of the nccl / peermem matcher tables of the reference (tests/golden/ext_kmsg.json)"""
+    """every line of the nccl / peermem / infiniband / cpu / os / disk matcher tables of the reference (tests/golden/ext*_kmsg.json)"""
     G = golden("ext_kmsg.json")
     out = []
     for k in ("nccl_has", "nccl_match", "peermem_has", "peermem_match"):
         out += [r["line"] for r in G[k]["rows"]]
+    G2 = golden("ext2_kmsg.json")
+    for k, v in G2.items():
+        out += [r["line"] for r in v["rows"] if "line" in r]
+    return out
+
+
+def ext_fuzz_lines(n: int, seed: int = SEED):
+    """mutations of the matcher vectors: truncations, one-byte edits, duplicated / swapped halves, two vectors glued together
+    (several anchors per line, patterns cut short, digits and colons moved) - the oracle decides what they mean"""
+    rng = np.random.default_rng(seed)
+    base = [l for l in ext_lines() + EXT_EDGE_LINES if l]
+    repl = list(" :,.[]()#!0179aWs-/") + ["", "  ", "::", "12", "task ", " seconds", "blocked for more than ", "nvme nvme", "in libnccl.so"]
+    out = []
+    for i in range(n):
+        l = base[int(rng.integers(0, len(base)))]
+        op = int(rng.integers(0, 6))
+        if op == 0:
+            l = l[: int(rng.integers(0, len(l) + 1))]
+        elif op == 1:
+            l = l[int(rng.integers(0, len(l))):]
+        elif op == 2:
+            p = int(rng.integers(0, len(l)))
+            l = l[:p] + repl[int(rng.integers(0, len(repl)))] + l[p + int(rng.integers(0, 2)):]
+        elif op == 3:
+            p = int(rng.integers(0, len(l)))
+            l = l[p:] + " " + l[:p]
+        elif op == 4:
+            m = base[int(rng.integers(0, len(base)))]
+            l = l + (" " if rng.random() < 0.5 else "") + m
+        else:
+            p, q = sorted(int(x) for x in rng.integers(0, len(l) + 1, 2))
+            l = l[:p] + l[q:]
+        out.append(l.replace("\n", " "))
     return out
 
 
@@ -110,6 +143,27 @@ EXT_EDGE_LINES = [
     PEERMEM_LIT + " " + PEERMEM_LIT,
     "NVRM: Xid (PCI:0000:05:00): 79, pid=1, GPU has fallen off the bus. segfault at 0 in libnccl.so " + PEERMEM_LIT,
     "nvswitch0: SXid (PCI:0000:c1:00.0): 12028, Non-fatal, " + PEERMEM_LIT,
+    "task a:123blocked for more than 5 seconds",                  # [\\d]+ gives a digit back to `.+`
+    "task a:1blocked for more than 5 seconds",                    # ... and cannot here
+    "task a:1 blocked for more than 5 seconds blocked for more than x seconds",
+    "task a:12 blocked for more than x seconds blocked for more than 7 seconds",
+    "task :1 blocked for more than 5 seconds", "task a: blocked for more than 5 seconds",
+    "task a b task c:9 x blocked for more than 5 seconds", "INFO: task x:1 y blocked for more than 1 secondsblocked for more than 22 seconds",
+    "soft lockup - CPU#1 stuck for 2s! [a:1]", "soft lockup - CPU# stuck for 2s! [a:1]", "soft lockup - CPU#1 stuck for 2s! [a:1x]",
+    "soft lockup - CPU#1 stuck for 2s! [:1]", "soft lockup - CPU#12 stuck for 345s! [a]b:77]",
+    "Detected insufficient power on the PCIe slot (27W)", "Detected insufficient power on the PCIe slot (27W", "Detected insufficient power on the PCIe slot ()",
+    "Port module eventHigh Temperature", "High Temperature Port module event", "mlx5_cmd_out_errACCESS_REGfailed",
+    "mlx5_cmd_out_err failed ACCESS_REG", "mlx5_cmd_out_err ACCESS_REG failed on 0000:d2:00.0x and 00000:d2:00.0 then 0000:d2:00.7.",
+    "mlx5_cmd_out_err ACCESS_REG failed 0000:d2:00.8 abcd:ef:01.2", "x0000:d2:00.1 mlx5_cmd_out_err ACCESS_REG failed _0000:d2:00.1 -0000:d2:00.1",
+    "VFS: file-max limit  reached", "VFS: file-max limit 5 reached", "VFS: file-max limit 5reached",
+    "md/raid: Disk failure on  detected, failing array", "md/raid: Disk failure on detected, failing array", "md/raid1: Disk failure on x detected, failing arra",
+    "block nvme: no available path - failing I/O", "block nvm: no available path - failing I/O",
+    "nvme nvme1: I/O  timeout, reset controller", "nvme nvme1: I/O timeout, reset controller", "nvme nvme: I/O x timeout, reset controller",
+    "nvme nvme12: Disabling device after reset failure", "nvme nvme12 : Disabling device after reset failure", "nvme nvme nvme3: Disabling device after reset failure",
+    "Buffer I/O error on dev a,, logical block 1", "Buffer I/O error on dev ,, logical block 1", "Buffer I/O error on dev , logical block 1",
+    "Buffer I/O error on dev dm-0, logical block x", "Buffer I/O error on dev dm-0 , logical block 1", "Buffer I/O error on dev a,b, logical block 9",
+    "I/O error while writing superbloc", "attempt to access beyond end of devic", "Remounting filesystem read-onl",
+    "Remounting filesystem read-only Remounting filesystem read-only", "I/O error while writing superblock and attempt to access beyond end of device",
     "segfault at" + " " * 300 + "in libnccl.so",                  # literals more than one chunk row apart
     "s" * 40 + "egfault at in libnccl.so",
 ]

@@ -104,23 +104,53 @@ def test_scan_edges(ctx, buf):
     _cmp_hits(hits, want)
 
 
+def _cmp_ext(ctx, buf, hits, want):
+    _cmp_hits(hits, want)
+    for a, b in zip(hits, want):
+        if b["kind"] >= 3:
+            assert a.dev_len == len(b["capture"]) and buf[a.dev_off:a.dev_off + a.dev_len] == b["capture"], (a.as_dict(), b)
+            assert ctx.kmsg_message(a, buf) == b["message"], (a.as_dict(), b)
+            comp, ev, _m, _g = O.EXT_BY_KIND[b["kind"]]
+            L = ctx._L
+            assert L.gpud_kmsg_event_name(b["kind"]).decode() == ev and L.gpud_kmsg_component(b["kind"]).decode() == comp
+
+
 def test_scan_ext_matchers(ctx):
-    """GPUD_SCAN_EXT_MATCHERS: nccl / peermem matchers ride the same scan; default mode is unaffected"""
+    """GPUD_SCAN_EXT_MATCHERS: the stateless line matchers of nccl / peermem / infiniband / cpu / os / disk ride
+    the same scan; default mode is unaffected"""
     lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:40]
     for buf in ("\n".join(lines).encode(), synth.ext_buffer(2_000_000, hit_every=60)):
         hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS)
         want = O.scan_lines(buf, ext=True)
         assert n_units == buf.count(b"\n") + 1
-        assert sum(h["kind"] == 3 for h in want) >= 8 and sum(h["kind"] == 4 for h in want) >= 8
-        _cmp_hits(hits, want)
+        assert {h["kind"] for h in want} >= set(range(3, 19))
+        _cmp_ext(ctx, buf, hits, want)
         _cmp_hits(ctx.kmsg_scan(buf)[0], O.scan_lines(buf))
     for l in lines:                                   # every vector as its own buffer
-        _cmp_hits(ctx.kmsg_scan(l.encode(), mode=g.SCAN_EXT_MATCHERS)[0], O.scan_lines(l.encode(), ext=True))
-    import gpud_b200.capi as capi
-    L = capi.lib()
-    G = synth.golden("ext_kmsg.json")["constants"]
-    assert L.gpud_kmsg_event_name(3).decode() == G["nccl"]["event"] and L.gpud_kmsg_event_message(3).decode() == G["nccl"]["message"]
-    assert L.gpud_kmsg_event_name(4).decode() == G["peermem"]["event"] and L.gpud_kmsg_event_message(4).decode() == G["peermem"]["message"]
+        b = l.encode()
+        _cmp_ext(ctx, b, ctx.kmsg_scan(b, mode=g.SCAN_EXT_MATCHERS)[0], O.scan_lines(b, ext=True))
+
+
+def test_scan_ext_matchers_fuzz(ctx):
+    """20 000 mutated matcher lines (cut, spliced, glued, edited): every decision and capture must equal the regex oracle"""
+    lines = synth.ext_fuzz_lines(20000, seed=99)
+    buf = "\n".join(lines).encode()
+    hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS, cap=1 << 17)
+    want = O.scan_lines(buf, ext=True)
+    assert n_units == len(lines) and len(want) > 5000
+    _cmp_ext(ctx, buf, hits, want)
+
+
+def test_scan_ext_golden_match_tables(ctx):
+    """the components' Match(line) -> (eventName, message) tables, answered from the scan hits in the component's pattern order"""
+    G = synth.golden("ext2_kmsg.json")
+    for comp in ("infiniband", "cpu", "os", "disk"):
+        for r in G[comp + ".match"]["rows"]:
+            b = r["line"].encode()
+            hits, _ = ctx.kmsg_scan(b, mode=g.SCAN_EXT_MATCHERS)
+            mine = [h for h in hits if ctx._L.gpud_kmsg_component(h.kind).decode() == comp]
+            got = (ctx._L.gpud_kmsg_event_name(mine[0].kind).decode(), ctx.kmsg_message(mine[0], b)) if mine else ("", "")
+            assert got == (r["wantEvent"], r["wantMessage"]), (comp, r, got)
 
 
 def test_scan_ext_matchers_raw_mode(ctx):
@@ -137,8 +167,8 @@ def test_scan_ext_matchers_raw_mode(ctx):
     hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_RAW_KMSG | g.SCAN_EXT_MATCHERS)
     want, n_rec = O.scan_raw_kmsg(buf, ext=True)
     assert n_units == n_rec
-    assert sum(h["kind"] == 3 for h in want) >= 8 and sum(h["kind"] == 4 for h in want) >= 8
-    _cmp_hits(hits, want)
+    assert {h["kind"] for h in want} >= set(range(3, 19))
+    _cmp_ext(ctx, buf, hits, want)
     for a, b in zip(hits, want):
         assert (a.kmsg_priority, a.kmsg_seq, a.kmsg_usec) == b["kmsg"]
 

@@ -93,24 +93,32 @@ def test_windows_c_equals_python():
             assert np.allclose(c["mean"][f], w["mean"], rtol=1e-12, atol=0) and np.allclose(c["ema"][f], w["ema"], rtol=1e-9, atol=0)
 
 
-def test_ext_matchers_golden_and_python(golden):   # nccl/kmsg_matcher_test.go:5,67 ; peermem/kmsg_matcher_test.go:5,62
+def test_ext_matchers_golden_and_python(golden):   # nccl / peermem / infiniband / cpu / os / disk kmsg_matcher_test.go tables
     G = golden("ext_kmsg.json")
     for r in G["nccl_has"]["rows"]:
-        assert bool(CO.ext_match(r["line"].encode()) & 1) == r["want"], r
+        assert bool(CO.ext_match(r["line"].encode())[0] & 1) == r["want"], r
     for r in G["peermem_has"]["rows"]:
-        assert bool(CO.ext_match(r["line"].encode()) & 2) == r["want"], r
-    for l in synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:50]:
+        assert bool(CO.ext_match(r["line"].encode())[0] & 2) == r["want"], r
+    lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:50] + synth.ext_fuzz_lines(3000)
+    fired = set()
+    for l in lines:
         b = l.encode()
-        want = sum(1 << (k - 3) for k in O.ext_match(b))
-        assert CO.ext_match(b) == want, l
+        kinds = O.ext_match(b)
+        fired.update(kinds)
+        m, caps = CO.ext_match(b)
+        assert m == sum(1 << (k - 3) for k in kinds), l
+        for k in (8, 9):
+            if k in kinds:
+                assert caps[k] == O.ext_capture(k, b), l
+    assert fired == set(range(3, 19))
 
 
 def test_c_ext_scan_equals_python_scan():
-    buf = synth.ext_buffer(300_000, hit_every=40)
+    buf = synth.ext_buffer(600_000, hit_every=40)
     ch, nl = CO.scan_lines(buf, ext=True)
     ph = O.scan_lines(buf, ext=True)
     assert nl == buf.count(b"\n") + 1
     assert [(h.line, h.kind, h.code, h.offset) for h in ch] == [(h["line"], h["kind"], h["code"], h["offset"]) for h in ph]
-    assert sum(h.kind == 3 for h in ch) >= 10 and sum(h.kind == 4 for h in ch) >= 10
+    assert len({h.kind for h in ch}) >= 17 and sum(h.kind >= 3 for h in ch) >= 80
     # the default scan is unchanged by the extra lines
     assert [(h.line, h.kind) for h in CO.scan_lines(buf)[0]] == [(h["line"], h["kind"]) for h in O.scan_lines(buf)]

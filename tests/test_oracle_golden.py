@@ -164,3 +164,30 @@ def test_ext_matchers(golden):                     # nccl/kmsg_matcher_test.go:5
         assert (4 in O.ext_match(r["line"].encode())) == r["want"], r
     for r in G["peermem_match"]["rows"]:
         assert (4 in O.ext_match(r["line"].encode())) == bool(r["wantName"]), r
+
+
+def test_ext2_matchers(golden):                    # infiniband / cpu / os / disk kmsg_matcher_test.go tables
+    G = golden("ext2_kmsg.json")
+    kinds = {}
+    for comp in ("infiniband", "cpu", "os", "disk"):
+        for pat in G[comp + ".patterns"]["patterns"]:
+            k = [k for k, c, e, *_ in O.EXT_PATTERNS if c == comp and e == pat["event"]]
+            assert len(k) == 1, pat
+            assert O.EXT_PATTERNS[k[0] - 3][4].decode() == pat["regex"] and O.EXT_PATTERNS[k[0] - 3][3] == pat["message"], pat
+            kinds[comp + "." + pat["key"]] = k[0]
+    n = 0
+    for key, kind in kinds.items():
+        for r in G[key]["rows"]:
+            want = r.get("want", r.get("expectedMatch"))
+            assert (kind in O.ext_match(r["line"].encode())) == want, (key, r)
+            if want and "expectedProcess" in r:
+                assert O.ext_capture(kind, r["line"].encode()).decode() == r["expectedProcess"], r
+            n += 1
+    for comp in ("infiniband", "cpu", "os", "disk"):
+        for r in G[comp + ".match"]["rows"]:
+            assert O.component_match(comp, r["line"].encode()) == (r["wantEvent"], r["wantMessage"]), (comp, r)
+            n += 1
+    for r in G["infiniband.access_reg_message"]["rows"]:
+        assert O.ext_message(7, r["line"].encode()) == r["want"], r
+        n += 1
+    assert n > 140

@@ -312,6 +312,65 @@ def main():
                         "nccl": {"event": "nvidia_nccl_segfault_in_libnccl", "message": "NCCL communication error (segfault in libnccl.so)"},
                         "peermem": {"event": "nvidia_peermem_invalid_context", "message": "peermem error detected (possible GPU communication issue)"}}
     dump("ext_kmsg.json", ext)
+
+    # ---- the stateless line matchers of infiniband / cpu / os / disk (second batch) ----
+    def consts(path):
+        """name -> string for every `name = "..."` / `name = `...`` constant of a Go file (behavioural data only)"""
+        out = {}
+        for i, ln in enumerate(open(os.path.join(REF, path)).read().split("\n"), 1):
+            m = re.match(r'^\s*(\w+)\s*=\s*(?:"((?:[^"\\]|\\.)*)"|`([^`]*)`)\s*$', ln)
+            if m:
+                out[m.group(1)] = {"value": m.group(3) if m.group(3) is not None else bytes(m.group(2), "utf-8").decode("unicode_escape"), "line": i}
+        return out
+
+    def resolve_msgs(path, func, field, rows, cs):
+        """re-read `field: <expr>,` of every row as Go source: identifiers -> constants, strings literal, + concatenates"""
+        body, _ = find_func(open(os.path.join(REF, path)).read(), func)
+        exprs = re.findall(r"\b%s:\s*(.+?),\s*\n" % field, body)
+        assert len(exprs) == len(rows), (path, func, field, len(exprs), len(rows))
+        for r, e in zip(rows, exprs):
+            val = ""
+            for tok in re.findall(r'"(?:[^"\\]|\\.)*"|\w+', e):
+                val += bytes(tok[1:-1], "utf-8").decode("unicode_escape") if tok.startswith('"') else cs[tok]["value"]
+            r[field] = val
+
+    comps = {"infiniband": (N + "infiniband/", [("pci_power_insufficient", "TestHasPCIPowerInsufficient", "regexPCIPowerInsufficient", "eventPCIPowerInsufficient", "messagePCIPowerInsufficient"),
+                                                 ("port_module_high_temperature", "TestHasPortModuleHighTemperature", "regexPortModuleHighTemperature", "eventPortModuleHighTemperature", "messagePortModuleHighTemperature"),
+                                                 ("access_reg_failed", "TestHasAccessRegFailed", "regexAccessRegFailed", "eventAccessRegFailed", "messageAccessRegFailed")], "wantEvent"),
+             "cpu": ("components/cpu/", [("blocked_too_long", "TestHasBlockedTooLong", "regexBlockedTooLong", "eventBlockedTooLong", "messageBlockedTooLong"),
+                                         ("soft_lockup", "TestHasSoftLockup", "regexSoftLockup", "eventSoftLockup", "messageSoftLockup")], "wantName"),
+             "os": ("components/os/", [("vfs_file_max", "TestHasVFSFileMaxLimitReached", "regexVFSFileMaxLimitReached", "eventNameVFSFileMaxLimitReached", "messageVFSFileMaxLimitReached")], "wantName"),
+             "disk": ("components/disk/", [("raid_array_failure", "TestHasRAIDArrayFailure", "regexRAIDArrayFailure", "eventRAIDArrayFailure", "messageRAIDArrayFailure"),
+                                           ("filesystem_read_only", "TestHasFilesystemReadOnly", "regexFilesystemReadOnly", "eventFilesystemReadOnly", "messageFilesystemReadOnly"),
+                                           ("nvme_path_failure", "TestHasNVMePathFailure", "regexNVMePathFailure", "eventNVMePathFailure", "messageNVMePathFailure"),
+                                           ("nvme_timeout", "TestHasNVMeTimeout", "regexNVMeTimeout", "eventNVMeTimeout", "messageNVMeTimeout"),
+                                           ("nvme_device_disabled", "TestHasNVMeDeviceDisabled", "regexNVMeDeviceDisabled", "eventNVMeDeviceDisabled", "messageNVMeDeviceDisabled"),
+                                           ("beyond_end_of_device", "TestHasBeyondEndOfDevice", "regexBeyondEndOfDevice", "eventBeyondEndOfDevice", "messageBeyondEndOfDevice"),
+                                           ("buffer_io_error", "TestHasBufferIOError", "regexBufferIOError", "eventBufferIOError", "messageBufferIOError"),
+                                           ("superblock_write_error", "TestHasSuperblockWriteError", "regexSuperblockWriteError", "eventSuperblockWriteError", "messageSuperblockWriteError")], "wantEventName")}
+    ext2 = {}
+    for comp, (d, pats, ev_field) in comps.items():
+        cs = consts(d + "kmsg_matcher.go")
+        plist = []
+        for key, fn, rx, ev, msg in pats:
+            rows, src = table(d + "kmsg_matcher_test.go", fn)
+            ext2["%s.%s" % (comp, key)] = {"src": src, "rows": ident(rows)}
+            plist.append({"key": key, "regex": cs[rx]["value"], "event": cs[ev]["value"], "message": cs[msg]["value"],
+                          "src": "%skmsg_matcher.go:%d" % (d, cs[rx]["line"])})
+        rows, src = table(d + "kmsg_matcher_test.go", "TestMatch")
+        rows = ident(rows)
+        resolve_msgs(d + "kmsg_matcher_test.go", "TestMatch", ev_field, rows, cs)
+        resolve_msgs(d + "kmsg_matcher_test.go", "TestMatch", "wantMessage", rows, cs)
+        for r in rows:
+            r["wantEvent"] = r.pop(ev_field)
+        ext2["%s.match" % comp] = {"src": src, "rows": rows}
+        ext2["%s.patterns" % comp] = {"src": d + "kmsg_matcher.go", "rows": [], "patterns": plist}
+    cs = consts(N + "infiniband/kmsg_matcher.go")
+    rows, src = table(N + "infiniband/kmsg_matcher_test.go", "TestAccessRegFailedMessage")
+    rows = ident(rows)
+    resolve_msgs(N + "infiniband/kmsg_matcher_test.go", "TestAccessRegFailedMessage", "want", rows, cs)
+    ext2["infiniband.access_reg_message"] = {"src": src, "rows": rows, "regexPCIDevice": cs["regexPCIDevice"]["value"], "prefix": cs["pciDeviceMessagePrefix"]["value"]}
+    dump("ext2_kmsg.json", ext2)
     return 0
 
 
