@@ -53,6 +53,34 @@ class XidHit(C.Structure):
                 "kmsg": (self.kmsg_priority, self.kmsg_seq, self.kmsg_usec)}
 
 
+class KmsgEvent(C.Structure):
+    _fields_ = [("unit_index", C.c_int64), ("component", C.c_char * 16), ("event", C.c_char * 32), ("message", C.c_char * 440)]
+
+
+class KmsgStateful:
+    """the reference's two stateful kmsg matchers (os kernel panic, memory OOM) over the primitives of EXT scans"""
+
+    def __init__(self):
+        self._L = lib()
+        self._h = C.c_void_p()
+        if self._L.gpud_kmsg_stateful_create(C.byref(self._h)):
+            raise GpudError(-1, "gpud_kmsg_stateful_create")
+
+    def feed(self, hits, buf: bytes, n_units: int, cap: int = 4096):
+        arr = (XidHit * max(1, len(hits)))(*hits)
+        out = (KmsgEvent * cap)()
+        n = C.c_int32()
+        rc = self._L.gpud_kmsg_stateful_feed(self._h, arr, len(hits), C.cast(C.c_char_p(buf), C.c_void_p), n_units, out, cap, C.byref(n))
+        if rc:
+            raise GpudError(rc, "gpud_kmsg_stateful_feed")
+        return [(out[i].unit_index, out[i].component.decode(), out[i].event.decode(), out[i].message.decode("latin-1")) for i in range(n.value)]
+
+    def close(self):
+        if self._h:
+            self._L.gpud_kmsg_stateful_destroy(self._h)
+            self._h = None
+
+
 class FabricRaw(C.Structure):
     _fields_ = [("gpu_index", C.c_uint32), ("nvlink_supported", C.c_uint32), ("system_expected_nvlink", C.c_uint32),
                 ("n_links", C.c_uint32), ("link_feature_enabled", C.c_uint8 * MAX_LINKS), ("pad0", C.c_uint8 * 2),
@@ -90,7 +118,7 @@ SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destr
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
            "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
-           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message",
+           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
@@ -127,6 +155,8 @@ def lib() -> C.CDLL:
         "gpud_sxid_name": (C.c_char_p, [i32]), "gpud_nvlink_rule_hint": (C.c_char_p, [i32]),
         "gpud_kmsg_event_name": (C.c_char_p, [i32]), "gpud_kmsg_event_message": (C.c_char_p, [i32]),
         "gpud_kmsg_component": (C.c_char_p, [i32]), "gpud_kmsg_hit_message": (i32, [vp, vp, vp, i32]),
+        "gpud_kmsg_stateful_create": (i32, [vp]), "gpud_kmsg_stateful_destroy": (None, [vp]),
+        "gpud_kmsg_stateful_feed": (i32, [vp, vp, i64, vp, i64, vp, i32, vp]),
         "gpud_fabric_pack": (i32, [vp, i32, C.POINTER(FabricRaw), vp, vp]),
         "gpud_fabric_verdict_device": (i32, [vp, i32, vp, i32, i32, C.POINTER(FabricVerdict), vp]),
         "gpud_comm_unique_id": (i32, [vp]), "gpud_comm_init": (i32, [vp, i32, i32, i32, vp]),

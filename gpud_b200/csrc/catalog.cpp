@@ -311,6 +311,8 @@ const KmsgEvent kKmsgEvents[GPUD_KIND_COUNT] = {
     {"disk", "beyond_end_of_device", "I/O attempt beyond device boundaries detected"},
     {"disk", "buffer_io_error", "Buffer I/O error detected on device"},
     {"disk", "superblock_write_error", "I/O error while writing superblock"},
+    // line primitives of the stateful matchers: no event of their own (gpud_kmsg_stateful_feed assembles "kernel_panic" / "OOM")
+    {"os", "", ""}, {"os", "", ""}, {"memory", "", ""}, {"memory", "", ""}, {"memory", "", ""}, {"memory", "", ""},
 };
 const KmsgEvent& kmsg_event(int32_t kind) { return kKmsgEvents[(kind > 0 && kind < GPUD_KIND_COUNT) ? kind : 0]; }
 }  // namespace

@@ -74,3 +74,4 @@ int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v);
 
 void gpud_scan_state_free(gpud_scan_state*);
 void gpud_comm_state_free(gpud_comm_state*);
+void gpud_parallel_memcpy(void* dst, const void* src, size_t n);

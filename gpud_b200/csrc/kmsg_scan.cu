@@ -18,6 +18,8 @@
 
 #include <algorithm>
 
+#include <thread>
+
 #include "catalog.h"
 #include "internal.h"
 
@@ -30,7 +32,7 @@ constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVI
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
 // families >= 4: the anchor literals of the extra line matchers (GPUD_SCAN_EXT_MATCHERS), index into kExtLit[]
 constexpr int kFamShift = 58;               // candidate word = byte offset | family << 58
-constexpr int kExtFam0 = 4, kNumFam = 19;
+constexpr int kExtFam0 = 4, kNumFam = 25;
 constexpr int kModeMask = 0xff;
 constexpr unsigned kMatchLanes = 16;        // candidates per warp in k_scan_match
 
@@ -159,15 +161,22 @@ __device__ __forceinline__ unsigned long long nvrm_family_coop(const ScanBuf& b,
 //   16   "attempt to access beyond end of device"                   disk/kmsg_matcher.go:43
 //   17   "Buffer I/O error on dev "                                 disk/kmsg_matcher.go:49
 //   18   "I/O error while writing superblock"                       disk/kmsg_matcher.go:55
+//   19   "Kernel "            `Kernel [Pp]anic`                      os/kmsg_matcher.go:35     } line primitives of the two
+//   20   "CPU: "              `CPU: (\d+) PID: (\d+) Comm: (\S+)`     os/kmsg_matcher.go:39     } stateful matchers; the host
+//   21   "invoked oom-killer:"                                      memory/kmsg_matcher.go:156 } state machines
+//   22   "oom-kill:constraint="  (nine greedy groups)               memory/kmsg_matcher.go:148 } (host_component.cpp) turn
+//   23   "Task in "           `Task in (.*) killed as a result of limit of (.*)`   memory/kmsg_matcher.go:143 } them into
+//   24   "Killed process "    `Killed process ([0-9]+) \((.+)\)`     memory/kmsg_matcher.go:152 } events
 struct ExtLit { unsigned char len; char text[63]; };
 #define GPUD_EXT_LITS \
   {0, ""}, {4, "NVRM"}, {0, ""}, {4, "SXid"}, {11, "segfault at"}, {59, "ERROR detected invalid context, skipping further processing"}, \
   {46, "Detected insufficient power on the PCIe slot ("}, {17, "Port module event"}, {16, "mlx5_cmd_out_err"}, {5, "task "}, \
   {18, "soft lockup - CPU#"}, {20, "VFS: file-max limit "}, {7, "md/raid"}, {31, "Remounting filesystem read-only"}, {10, "block nvme"}, \
-  {9, "nvme nvme"}, {38, "attempt to access beyond end of device"}, {24, "Buffer I/O error on dev "}, {34, "I/O error while writing superblock"}
+  {9, "nvme nvme"}, {38, "attempt to access beyond end of device"}, {24, "Buffer I/O error on dev "}, {34, "I/O error while writing superblock"}, \
+  {7, "Kernel "}, {5, "CPU: "}, {19, "invoked oom-killer:"}, {20, "oom-kill:constraint="}, {8, "Task in "}, {15, "Killed process "}
 __device__ const ExtLit kExtLit[kNumFam] = {GPUD_EXT_LITS};
 static const ExtLit kExtLitHost[kNumFam] = {GPUD_EXT_LITS};
-constexpr unsigned kHashMul = 0x9e3779dfu;   // (word * kHashMul) >> 27 is injective on the 17 anchor words (checked at start-up)
+constexpr unsigned kHashMul = 0x9e384155u;   // (word * kHashMul) >> 27 is injective on the 23 anchor words (checked at start-up)
 struct ExtTab { unsigned word[32]; unsigned char fam[32]; };
 __device__ __forceinline__ unsigned ext_slot(unsigned x) { return (x * kHashMul) >> 27; }
 
@@ -782,7 +791,23 @@ __device__ __forceinline__ int64_t find_lit(const ScanBuf& b, int64_t from, int6
 __device__ __forceinline__ int64_t digits_end(const ScanBuf& b, int64_t p, int64_t e) { while (p < e && is_digit(ld8(b, p))) ++p; return p; }
 __device__ __forceinline__ bool is_word(int c) { return is_digit(c) || (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c == '_'; }
 
-__device__ int ext_match_at(int fam, const ScanBuf& b, int64_t a, int64_t ms, int64_t ue, int64_t* cap_off, int32_t* cap_len) {
+// last start in [from, to - n] of the n-byte literal, else -1
+__device__ int64_t rfind_lit(const ScanBuf& b, int64_t from, int64_t to, const char* lit, int n) {
+  const unsigned c0 = (unsigned char)lit[0];
+  for (int64_t i = rfind_byte(b, from, to - n + 1, c0); i >= from; i = rfind_byte(b, from, i, c0)) {
+    bool ok = true;
+    for (int k = 1; k < n && ok; ++k) ok = __ldg(b.p + i + k) == (uint8_t)lit[k];
+    if (ok) return i;
+  }
+  return -1;
+}
+template <int N>
+__device__ __forceinline__ int64_t rfind_lit(const ScanBuf& b, int64_t from, int64_t to, const char (&s)[N]) { return rfind_lit(b, from, to, s, N - 1); }
+
+// sp_off / sp_len: up to five capture spans in the hit's slot order (dev, unit_name, pid, pname, inj)
+__device__ int ext_match_at(int fam, const ScanBuf& b, int64_t a, int64_t ms, int64_t ue, int64_t* sp_off, int32_t* sp_len) {
+  int64_t* cap_off = sp_off;
+  int32_t* cap_len = sp_len;
   const int64_t la = a + kExtLit[fam].len;                       // first byte after the anchor literal
   const int64_t seg_e = find_byte(b, la, ue, '\n');              // `.` runs end here
   switch (fam) {
@@ -871,6 +896,61 @@ __device__ int ext_match_at(int fam, const ScanBuf& b, int64_t a, int64_t ms, in
     }
     case 18:   // `I/O error while writing superblock`
       return GPUD_KIND_DISK_SUPERBLOCK_WRITE_ERROR;
+    case 19: { // `Kernel [Pp]anic`
+      const int c = ld8(b, la);
+      return (la < ue && (c == 'P' || c == 'p') && lit_at(b, la + 1, ue, "anic")) ? GPUD_KIND_OS_PANIC_START : 0;
+    }
+    case 20: { // `CPU: (\d+) PID: (\d+) Comm: (\S+)`
+      const int64_t d1 = digits_end(b, la, ue);
+      if (d1 == la || !lit_at(b, d1, ue, " PID: ")) return 0;
+      const int64_t d2 = digits_end(b, d1 + 6, ue);
+      if (d2 == d1 + 6 || !lit_at(b, d2, ue, " Comm: ")) return 0;
+      int64_t e = d2 + 7;
+      while (e < ue && !is_ws(ld8(b, e))) ++e;
+      if (e == d2 + 7) return 0;
+      sp_off[0] = la; sp_len[0] = (int32_t)(d1 - la);                        // CPU
+      sp_off[2] = d1 + 6; sp_len[2] = (int32_t)(d2 - d1 - 6);                // PID
+      sp_off[3] = d2 + 7; sp_len[3] = (int32_t)(e - d2 - 7);                 // Comm
+      return GPUD_KIND_OS_PANIC_CPU_PID;
+    }
+    case 21:   // `invoked oom-killer:`
+      return GPUD_KIND_MEM_OOM_START;
+    case 22: { // `oom-kill:constraint=(.*),nodemask=(.*),cpuset=(.*),mems_allowed=(.*),oom_memcg=(.*),task_memcg=(.*),task=(.*),pid=(.*),uid=(.*)`
+      // Every group is greedy, so delimiter k sits at its LAST position that still leaves room for delimiters k+1..8:
+      // fit them right to left, each as late as possible before the next.
+      int64_t pos[8];
+      int64_t lim = seg_e;
+      const char* const D[8] = {",nodemask=", ",cpuset=", ",mems_allowed=", ",oom_memcg=", ",task_memcg=", ",task=", ",pid=", ",uid="};
+      const int DL[8] = {10, 8, 14, 11, 12, 6, 5, 5};
+      for (int k = 7; k >= 0; --k) {
+        pos[k] = rfind_lit(b, la, lim, D[k], DL[k]);
+        if (pos[k] < 0) return 0;
+        lim = pos[k];
+      }
+      sp_off[0] = la; sp_len[0] = (int32_t)(pos[0] - la);                                        // 1 constraint
+      sp_off[1] = pos[3] + DL[3]; sp_len[1] = (int32_t)(pos[4] - pos[3] - DL[3]);                // 5 oom_memcg
+      sp_off[4] = pos[4] + DL[4]; sp_len[4] = (int32_t)(pos[5] - pos[4] - DL[4]);                // 6 task_memcg
+      sp_off[3] = pos[5] + DL[5]; sp_len[3] = (int32_t)(pos[6] - pos[5] - DL[5]);                // 7 task
+      sp_off[2] = pos[6] + DL[6]; sp_len[2] = (int32_t)(pos[7] - pos[6] - DL[6]);                // 8 pid
+      return GPUD_KIND_MEM_OOM_CONTAINER;
+    }
+    case 23: { // `Task in (.*) killed as a result of limit of (.*)`
+      const int64_t o = rfind_lit(b, la, seg_e, " killed as a result of limit of ");
+      if (o < 0) return 0;
+      sp_off[0] = la; sp_len[0] = (int32_t)(o - la);
+      sp_off[1] = o + 32; sp_len[1] = (int32_t)(seg_e - o - 32);
+      return GPUD_KIND_MEM_OOM_LEGACY_CONTAINER;
+    }
+    case 24: { // `Killed process ([0-9]+) \((.+)\)`
+      const int64_t d = digits_end(b, la, ue);
+      if (d == la || !lit_at(b, d, ue, " (")) return 0;
+      const int64_t se = find_byte(b, d, ue, '\n');
+      const int64_t r = rfind_byte(b, d + 3, se, ')');              // `.+` is greedy and needs one byte
+      if (r < d + 3) return 0;
+      sp_off[2] = la; sp_len[2] = (int32_t)(d - la);
+      sp_off[3] = d + 2; sp_len[3] = (int32_t)(r - d - 2);
+      return GPUD_KIND_MEM_OOM_KILLED_PROCESS;
+    }
   }
   return 0;
 }
@@ -934,9 +1014,9 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
       if (a < ms) continue;
     }
     if (fam >= (unsigned long long)kExtFam0) {          // extra line matchers: every verified anchor is tried on its own;
-      int64_t cap_off = 0;                                 // duplicates per (unit, kind) are dropped on the host (leftmost wins)
-      int32_t cap_len = 0;
-      const int kind = ext_match_at((int)fam, b, a, ms, ue, &cap_off, &cap_len);
+      int64_t sp_off[5] = {0, 0, 0, 0, 0};                 // duplicates per (unit, kind) are dropped on the host (leftmost wins)
+      int32_t sp_len[5] = {0, 0, 0, 0, 0};
+      const int kind = ext_match_at((int)fam, b, a, ms, ue, sp_off, sp_len);
       if (!kind) continue;
       gpud_xid_hit h;
       memset(&h, 0, sizeof h);
@@ -945,11 +1025,15 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
       h.n_actions = -1;
       h.rule_index = -1;
       h.unit_offset = us;
-      h.pid_off = a;                                       // where the match is anchored (ties between candidates of one unit)
-      h.dev_off = cap_off;
-      h.dev_len = cap_len;
-      for (int i = 0; i < cap_len && i < 39; ++i) h.device[i] = (char)ld8(b, cap_off + i);
-      if (cap_len > 39) h.flags |= GPUD_HIT_DEV_TRUNCATED;
+      h.link = a;                                          // where the match is anchored (ties between candidates of one unit)
+      h.dev_off = sp_off[0]; h.dev_len = sp_len[0];
+      h.unit_name_off = sp_off[1]; h.unit_name_len = sp_len[1];
+      h.pid_off = sp_off[2]; h.pid_len = sp_len[2];
+      h.pname_off = sp_off[3]; h.pname_len = sp_len[3];
+      h.inj_off = sp_off[4]; h.inj_len = sp_len[4];
+      for (int i = 0; i < sp_len[0] && i < 39; ++i) h.device[i] = (char)ld8(b, sp_off[0] + i);
+      for (int i = 0; i < sp_len[1] && i < 39; ++i) h.unit_name[i] = (char)ld8(b, sp_off[1] + i);
+      if (sp_len[0] > 39) h.flags |= GPUD_HIT_DEV_TRUNCATED;
       h.kmsg_priority = (int32_t)k_prio;
       h.kmsg_seq = k_seq;
       h.kmsg_usec = k_usec;
@@ -1099,6 +1183,20 @@ static const ExtTab& ext_tab() {
   return t;
 }
 
+// Pageable -> pinned staging copy on a few host threads: one core moves ~8 GB/s, the PCIe link wants 50.
+void gpud_parallel_memcpy(void* dst, const void* src, size_t n) {
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int T = n < (1u << 20) ? 1 : (int)std::min<unsigned>(8u, std::max(1u, hw / 2));
+  if (T == 1) { memcpy(dst, src, n); return; }
+  std::thread th[8];
+  const size_t part = ((n + T - 1) / T + 63) & ~(size_t)63;
+  for (int t = 0; t < T; ++t) {
+    const size_t a = std::min(n, (size_t)t * part), e = std::min(n, a + part);
+    th[t] = std::thread([=] { if (e > a) memcpy((char*)dst + a, (const char*)src + a, e - a); });
+  }
+  for (int t = 0; t < T; ++t) th[t].join();
+}
+
 static bool scan_mode_ok(int32_t mode) {
   const int32_t base = mode & ~GPUD_SCAN_EXT_MATCHERS;
   return base == GPUD_SCAN_LINES || base == GPUD_SCAN_RAW_KMSG;
@@ -1171,7 +1269,7 @@ static int32_t scan_collect(gpud_ctx* ctx, gpud_scan_state* s, gpud_xid_hit* hit
     std::stable_sort(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
       if (a.unit_index != b.unit_index) return a.unit_index < b.unit_index;
       if (a.kind != b.kind) return a.kind < b.kind;
-      return a.kind > GPUD_KIND_SXID && a.pid_off < b.pid_off;
+      return a.kind > GPUD_KIND_SXID && a.link < b.link;
     });
     tmp.erase(std::unique(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
                 return a.kind > GPUD_KIND_SXID && a.unit_index == b.unit_index && a.kind == b.kind;
@@ -1224,7 +1322,7 @@ extern "C" int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf
       for (size_t off = 0; off < (size_t)len; off += piece, k ^= 1) {
         const size_t n = std::min(piece, (size_t)len - off);
         GPUD_CUDA(ctx, cudaEventSynchronize(s->ev_stage[k]));
-        memcpy(s->h_stage[k], buf + off, n);
+        gpud_parallel_memcpy(s->h_stage[k], buf + off, n);
         GPUD_CUDA(ctx, cudaMemcpyAsync(s->d_buf + off, s->h_stage[k], n, cudaMemcpyHostToDevice, s->stream));
         GPUD_CUDA(ctx, cudaEventRecord(s->ev_stage[k], s->stream));
       }

@@ -772,7 +772,7 @@ extern "C" int32_t gpud_ring_push_raw(gpud_ring* r, const void* host_rows_v, int
     GPUD_CUDA(r->ctx, cudaEventSynchronize(r->ev_stage[buf]));   // previous use of this staging pair has drained
     const char* src = host_rows + (size_t)done * r->F * esz;
     if (!pinned) {
-      memcpy(r->h_stage[buf], src, bytes);                     // pageable caller memory: stage through pinned
+      gpud_parallel_memcpy(r->h_stage[buf], src, bytes);       // pageable caller memory: stage through pinned
       src = (const char*)r->h_stage[buf];
     }
     GPUD_CUDA(r->ctx, cudaMemcpyAsync(r->d_stage[buf], src, bytes, cudaMemcpyHostToDevice, r->stream));

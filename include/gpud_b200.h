@@ -123,8 +123,15 @@ enum { GPUD_SCAN_LINES = 0,   /* units are '\n'-separated lines (strings.Split(b
  *   os          VFS file-max limit reached                              components/os/kmsg_matcher.go:18
  *   disk        the eight patterns of                                   components/disk/kmsg_matcher.go:11-55
  * For these kinds dev_off/dev_len (and device[], truncated) hold the capture the component appends to its message
- * (cpu: process info; infiniband ACCESS_REG: the first PCI BDF of the line; else empty) and pid_off the byte offset the
- * match is anchored at.  Not covered: the two STATEFUL matchers (os kernel-panic assembly, memory OOM parser). */
+ * (cpu: process info; infiniband ACCESS_REG: the first PCI BDF of the line; else empty) and `link` the byte offset the
+ * match is anchored at.
+ * The two STATEFUL matchers (os kernel-panic assembly os/kmsg_matcher.go:60-125, memory OOM parser
+ * memory/kmsg_matcher.go:29-109) are split: the scan reports their six line primitives (kinds 19..24) with the capture
+ * groups the state machines read as buffer spans -
+ *   OS_PANIC_CPU_PID       dev = CPU digits, pid = PID digits, pname = Comm
+ *   MEM_OOM_CONTAINER      dev = constraint, unit_name = oom_memcg, inj = task_memcg, pname = task, pid = pid
+ *   MEM_OOM_LEGACY_CONTAINER  dev = group 1, unit_name = group 2        MEM_OOM_KILLED_PROCESS  pid, pname
+ * - and gpud_kmsg_stateful_feed() runs the reference's two state machines over them. */
 #define GPUD_SCAN_EXT_MATCHERS 0x100
 enum {
   GPUD_KIND_XID = 1, GPUD_KIND_SXID = 2, GPUD_KIND_NCCL_SEGFAULT = 3, GPUD_KIND_PEERMEM_INVALID_CONTEXT = 4,
@@ -132,7 +139,10 @@ enum {
   GPUD_KIND_CPU_BLOCKED_TOO_LONG = 8, GPUD_KIND_CPU_SOFT_LOCKUP = 9, GPUD_KIND_OS_VFS_FILE_MAX_LIMIT_REACHED = 10,
   GPUD_KIND_DISK_RAID_ARRAY_FAILURE = 11, GPUD_KIND_DISK_FILESYSTEM_READ_ONLY = 12, GPUD_KIND_DISK_NVME_PATH_FAILURE = 13,
   GPUD_KIND_DISK_NVME_TIMEOUT = 14, GPUD_KIND_DISK_NVME_DEVICE_DISABLED = 15, GPUD_KIND_DISK_BEYOND_END_OF_DEVICE = 16,
-  GPUD_KIND_DISK_BUFFER_IO_ERROR = 17, GPUD_KIND_DISK_SUPERBLOCK_WRITE_ERROR = 18, GPUD_KIND_COUNT = 19
+  GPUD_KIND_DISK_BUFFER_IO_ERROR = 17, GPUD_KIND_DISK_SUPERBLOCK_WRITE_ERROR = 18,
+  /* line primitives of the two stateful matchers: not events by themselves, input of gpud_kmsg_stateful_feed */
+  GPUD_KIND_OS_PANIC_START = 19, GPUD_KIND_OS_PANIC_CPU_PID = 20, GPUD_KIND_MEM_OOM_START = 21, GPUD_KIND_MEM_OOM_CONTAINER = 22,
+  GPUD_KIND_MEM_OOM_LEGACY_CONTAINER = 23, GPUD_KIND_MEM_OOM_KILLED_PROCESS = 24, GPUD_KIND_COUNT = 25
 };
 enum { GPUD_EVENT_UNKNOWN = 0, GPUD_EVENT_INFO = 1, GPUD_EVENT_WARNING = 2, GPUD_EVENT_CRITICAL = 3, GPUD_EVENT_FATAL = 4 };
 enum { GPUD_ACT_IGNORE_NO_ACTION_REQUIRED = 1, GPUD_ACT_REBOOT_SYSTEM = 2, GPUD_ACT_HARDWARE_INSPECTION = 3,
@@ -211,6 +221,23 @@ const char* gpud_kmsg_component(int32_t kind);
  * (cpu/kmsg_matcher.go:54-63, infiniband/kmsg_matcher.go:136-142).  `buf` is the scanned buffer (needed only when the
  * capture is longer than device[]: GPUD_HIT_DEV_TRUNCATED) or NULL.  Returns the length, -1 if `cap` is too small. */
 int32_t gpud_kmsg_hit_message(const gpud_xid_hit* hit, const uint8_t* buf, char* out, int32_t cap);
+
+/* The stateful matchers.  One object per kmsg stream (the reference keeps one closure per component:
+ * os/kmsg_matcher.go:159, memory/kmsg_matcher.go:29); feed it the hits of every GPUD_SCAN_EXT_MATCHERS scan of that stream in
+ * scan order together with the scanned buffer and the scan's n_units.  Events come out exactly where the reference's
+ * Match returns them: (component, eventName, message) at unit_index (index inside this scan; a kernel-panic fallback event
+ * belongs to the 10th line after the panic start whatever that line holds).  State carries over to the next feed. */
+typedef struct gpud_kmsg_stateful gpud_kmsg_stateful;
+typedef struct {
+  int64_t unit_index;      /* line / record of THIS scan the event is returned for; negative = a line of an earlier scan */
+  char component[16];      /* "os" | "memory" */
+  char event[32];          /* "kernel_panic" | "OOM" */
+  char message[440];
+} gpud_kmsg_event;
+int32_t gpud_kmsg_stateful_create(gpud_kmsg_stateful** out);
+void gpud_kmsg_stateful_destroy(gpud_kmsg_stateful* st);
+int32_t gpud_kmsg_stateful_feed(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
+                                gpud_kmsg_event* out, int32_t cap, int32_t* n_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole-box NVLink / fabric view.

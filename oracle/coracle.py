@@ -60,14 +60,27 @@ def sxid_match(line: bytes):
     return h if L.orc_sxid_match(line, C.c_int32(len(line)), C.byref(h)) else None
 
 
+N_EXT = 22    # ORC_N_EXT: hit kinds 3 .. 24
+
+
 def ext_match(line: bytes):
     """(bitmask, captures): bit i = pattern of hit kind 3 + i fires; captures[kind] = group 1 of the cpu patterns"""
     L = lib()
     L.orc_ext_match.restype = C.c_int32
-    cap = (C.c_int32 * 32)()
+    cap = (C.c_int32 * (2 * N_EXT))()
     m = L.orc_ext_match(line, C.c_int32(len(line)), cap)
-    caps = {3 + i: line[cap[2 * i]:cap[2 * i + 1]] for i in range(16) if (m >> i) & 1 and cap[2 * i] >= 0}
+    caps = {3 + i: line[cap[2 * i]:cap[2 * i + 1]] for i in range(N_EXT) if (m >> i) & 1 and cap[2 * i] >= 0}
     return m, caps
+
+
+def ext_groups(kind: int, line: bytes):
+    """capture groups 0..9 of pattern `kind` on `line` as bytes (None = unset), or None if it does not match"""
+    L = lib()
+    L.orc_ext_groups.restype = C.c_int32
+    c = (C.c_int32 * 20)()
+    if not L.orc_ext_groups(C.c_int32(kind), line, C.c_int32(len(line)), c):
+        return None
+    return [line[c[2 * i]:c[2 * i + 1]] if c[2 * i] >= 0 else None for i in range(10)]
 
 
 def scan_lines(buf: bytes, threads: int = 0, cap: int = 1 << 20, ext: bool = False):

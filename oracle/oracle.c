@@ -136,7 +136,7 @@ void orc_windows_fields(const double* ring, int32_t F, int64_t n, int32_t W, con
 #include "../gpud_b200/csrc/catalog_data.inc"   /* DATA ONLY: generated tables (tools/gen_catalog.py) */
 
 /* components/accelerator/nvidia/xid/kmsg.go:22,29,38,43 ; sxid/kmsg.go:17,20 — verbatim */
-static const char* RX[22] = {
+static const char* RX[28] = {
     "NVRM: Xid \\(((?:PCI:)?[0-9a-fA-F:]+)\\).*?: (\\d+),",
     "NVRM: Xid \\(PCI:([0-9a-fA-F:]+)\\): (\\d+)(?:, pid=(\\d+), name=([^,]+))?, ([A-Z_]+(?:/[A-Z_]+)?)\\s+(Nonfatal|Fatal)\\s+(XC[01])\\s+(i\\d+)\\s+Link\\s+(-?\\d+)\\s+\\((0x[0-9a-fA-F]+)\\s+(0x[0-9a-fA-F]+)(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?(?:\\s+(0x[0-9a-fA-F]+))?",
     "(?s)NVRM:\\s+The NVIDIA GPU ((?:[0-9a-fA-F]{4}:)?[0-9a-fA-F]{2}:[0-9a-fA-F]{2})\\.0.*?fallen off the bus and is not responding to commands\\.",
@@ -160,9 +160,16 @@ static const char* RX[22] = {
     "nvme nvme[0-9]+: Disabling device after reset failure",
     "attempt to access beyond end of device",
     "Buffer I/O error on dev [^ ]+, logical block [0-9]+",
-    "I/O error while writing superblock"};
-#define ORC_N_RX 22
-#define ORC_N_EXT 16          /* RX[6 + i] is hit kind 3 + i */
+    "I/O error while writing superblock",
+    /* line primitives of the two stateful matchers: os/kmsg_matcher.go:35,39 ; memory/kmsg_matcher.go:156,148,143,152 — verbatim */
+    "Kernel [Pp]anic",
+    "CPU: (\\d+) PID: (\\d+) Comm: (\\S+)",
+    "invoked oom-killer:",
+    "oom-kill:constraint=(.*),nodemask=(.*),cpuset=(.*),mems_allowed=(.*),oom_memcg=(.*),task_memcg=(.*),task=(.*),pid=(.*),uid=(.*)",
+    "Task in (.*) killed as a result of limit of (.*)",
+    "Killed process ([0-9]+) \\((.+)\\)"};
+#define ORC_N_RX 28
+#define ORC_N_EXT 22          /* RX[6 + i] is hit kind 3 + i */
 static orx_prog* PR[ORC_N_RX];
 static pthread_once_t rx_once = PTHREAD_ONCE_INIT;
 static void rx_init(void) { for (int i = 0; i < ORC_N_RX; ++i) PR[i] = orx_compile(RX[i]); }
@@ -279,9 +286,19 @@ int32_t orc_sxid_match(const char* s, int32_t n, orc_hit* h) {
 
 /* The Has* functions of the stateless line matchers (e.g. nccl/kmsg_matcher.go:20-25, disk/kmsg_matcher.go:70-125):
  * bit i = pattern of hit kind 3 + i fires.  cap[2*i], cap[2*i+1] = span of capture group 1 (cpu patterns), -1 if none. */
+/* one pattern: spans of groups 0..9 into c[20] (-1 = unset); returns 1 on match */
+int32_t orc_ext_groups(int32_t kind, const char* s, int32_t n, int32_t* c20) {
+  pthread_once(&rx_once, rx_init);
+  int c[24];
+  for (int i = 0; i < 24; ++i) c[i] = -1;
+  if (kind < 3 || kind >= 3 + ORC_N_EXT || !orx_search(PR[6 + kind - 3], s, n, c)) return 0;
+  for (int i = 0; i < 20; ++i) c20[i] = c[i];
+  return 1;
+}
+
 int32_t orc_ext_match(const char* s, int32_t n, int32_t* cap) {
   pthread_once(&rx_once, rx_init);
-  int c[8];
+  int c[24];
   int32_t m = 0;
   for (int i = 0; i < ORC_N_EXT; ++i) {
     if (cap) cap[2 * i] = cap[2 * i + 1] = -1;

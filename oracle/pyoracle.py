@@ -67,7 +67,18 @@ EXT_PATTERNS = [
     (16, "disk", "beyond_end_of_device", "I/O attempt beyond device boundaries detected", rb"attempt to access beyond end of device", None),   # :42-44
     (17, "disk", "buffer_io_error", "Buffer I/O error detected on device", rb"Buffer I/O error on dev [^ ]+, logical block [0-9]+", None),   # :48-50
     (18, "disk", "superblock_write_error", "I/O error while writing superblock", rb"I/O error while writing superblock", None),   # :54-56
+    # line primitives of the two STATEFUL matchers (their events are assembled by KernelPanicMatcher / OOMMatcher below)
+    (19, "os", "", "", rb"Kernel [Pp]anic", None),                                        # os/kmsg_matcher.go:35
+    (20, "os", "", "", rb"CPU: (\d+) PID: (\d+) Comm: (\S+)", None),                      # os/kmsg_matcher.go:39
+    (21, "memory", "", "", rb"invoked oom-killer:", None),                                # memory/kmsg_matcher.go:156
+    (22, "memory", "", "", rb"oom-kill:constraint=(.*),nodemask=(.*),cpuset=(.*),mems_allowed=(.*),oom_memcg=(.*),task_memcg=(.*),task=(.*),pid=(.*),uid=(.*)", None),   # :148
+    (23, "memory", "", "", rb"Task in (.*) killed as a result of limit of (.*)", None),   # memory/kmsg_matcher.go:143
+    (24, "memory", "", "", rb"Killed process ([0-9]+) \((.+)\)", None),                   # memory/kmsg_matcher.go:152
 ]
+N_STATELESS_KINDS = 19          # kinds 3..18 are complete matchers; 19..24 are primitives
+# which capture groups of a primitive the product reports, in the order of the hit's span slots
+# (dev, unit_name, pid, pname, inj): os/kmsg_matcher.go:133-157, memory/kmsg_matcher.go:159-208
+PRIM_GROUPS = {20: (1, None, 2, 3, None), 22: (1, 5, 8, 7, 6), 23: (1, 2, None, None, None), 24: (None, None, 1, 2, None)}
 EXT_RE = {k: re.compile(rx) for k, _c, _e, _m, rx, _g in EXT_PATTERNS}
 EXT_BY_KIND = {k: (c, e, m, g) for k, c, e, m, _rx, g in EXT_PATTERNS}
 R_PCI_DEVICE = re.compile(rb"\b[0-9a-fA-F]{4}:[0-9a-fA-F]{2}:[0-9a-fA-F]{2}\.[0-7]\b")       # infiniband/kmsg_matcher.go:59
@@ -77,7 +88,9 @@ INT64_MAX = (1 << 63) - 1
 
 
 def go_atoi(b: bytes) -> Optional[int]:
-    """strconv.Atoi on an optionally signed decimal string; None on range error (int is 64-bit)."""
+    """strconv.Atoi: optional sign, then ASCII digits only; None on syntax or range error (int is 64-bit)."""
+    if not re.fullmatch(rb"[+-]?[0-9]+", b):
+        return None
     v = int(b)
     if v > INT64_MAX or v < -INT64_MAX - 1:
         return None
@@ -492,6 +505,8 @@ def ext_capture(kind: int, line: bytes) -> bytes:
     g = EXT_BY_KIND[kind][3]
     if g is not None:
         return EXT_RE[kind].search(line).group(g)
+    if kind in PRIM_GROUPS:
+        return prim_spans(kind, line)[0]
     if kind == 7:
         m = R_PCI_DEVICE.search(line)
         return m.group(0) if m else b""
@@ -510,12 +525,124 @@ def ext_message(kind: int, line: bytes) -> str:
 
 
 def component_match(component: str, line: bytes):
-    """(eventName, message) of the first pattern of `component` that fires, in the component's own order
+    """(eventName, message) of the first STATELESS pattern of `component` that fires, in the component's own order
     (e.g. disk/kmsg_matcher.go:127-134, 143-154); ("", "") if none"""
     for k, c, e, _m, _rx, _g in EXT_PATTERNS:
-        if c == component and EXT_RE[k].search(line):
+        if k < N_STATELESS_KINDS and c == component and EXT_RE[k].search(line):
             return e, ext_message(k, line)
     return "", ""
+
+
+def prim_spans(kind: int, line: bytes):
+    """the capture spans a primitive hit reports, as bytes per span slot (b"" = slot unused)"""
+    m = EXT_RE[kind].search(line)
+    return [m.group(g) if g is not None else b"" for g in PRIM_GROUPS.get(kind, (None,) * 5)]
+
+
+def go_path_join_root(x: str) -> str:
+    """path.Join("/", x) (memory/kmsg_matcher.go:165-166): Clean("/" + x) - collapse slashes, drop ".", resolve ".." at the root"""
+    out = []
+    for part in x.split("/"):
+        if part in ("", "."):
+            continue
+        if part == "..":
+            if out:
+                out.pop()
+            continue
+        out.append(part)
+    return "/" + "/".join(out)
+
+
+def stateful_events(lines):
+    """(line index, component, eventName, message) of the two stateful matchers run line by line over `lines`, as the
+    os and memory components' Match would return them"""
+    pm, om, out = KernelPanicMatcher(), OOMMatcher(), []
+    for i, l in enumerate(lines):
+        ev = pm.feed(l)
+        if ev[0]:
+            out.append((i, "os") + ev)
+        ev = om.feed(l)
+        if ev[0]:
+            out.append((i, "memory") + ev)
+    return out
+
+
+class KernelPanicMatcher:
+    """createKernelPanicMatchFunc (os/kmsg_matcher.go:60-125): one call per line, returns (eventName, message)"""
+    MAX_LINES = 10
+
+    def __init__(self):
+        self.reading, self.lines = False, 0
+
+    def feed(self, line: bytes):
+        if EXT_RE[19].search(line):                                   # checkIfStartOfPanicMessages (:127-134)
+            ev = ("kernel_panic", "Kernel panic detected (no CPU/PID info found)") if self.reading else ("", "")
+            self.reading, self.lines = True, 0
+            return ev
+        if not self.reading:
+            return "", ""
+        self.lines += 1
+        m = EXT_RE[20].search(line)                                   # extractCPUandPID (:136-157)
+        if m:
+            cpu, pid = go_atoi(m.group(1)), go_atoi(m.group(2))
+            if cpu is not None and pid is not None and pid >= 0:
+                self.reading, self.lines = False, 0
+                return "kernel_panic", "Kernel panic detected - CPU: %d, PID: %d, Process: %s" % (cpu, pid, m.group(3).decode("latin-1"))
+        if self.lines >= self.MAX_LINES:
+            self.reading, self.lines = False, 0
+            return "kernel_panic", "Kernel panic detected (no CPU/PID info found)"
+        return "", ""
+
+
+class OOMMatcher:
+    """createMatchFunc (memory/kmsg_matcher.go:29-109): one call per line, returns (eventName, message)"""
+
+    def __init__(self):
+        self.cur = None
+
+    @staticmethod
+    def summary(o) -> str:                                            # OOMInstance.Summary (:124-137)
+        msg = "System OOM encountered" if o["victim"] == "/" else "OOM encountered"
+        if o["process"] != "" and o["pid"] != 0:
+            msg = "%s, victim process: %s, pid: %d" % (msg, o["process"], o["pid"])
+        return msg
+
+    def feed(self, line: bytes):
+        if EXT_RE[21].search(line):
+            self.cur = {"pid": 0, "process": "", "container": "/", "victim": "/", "constraint": ""}
+            return "", ""
+        if self.cur is None:
+            return "", ""
+        o = self.cur
+        found = False
+        m = EXT_RE[22].search(line)                                   # getContainerName (:169-189)
+        if m is None:
+            lm = EXT_RE[23].search(line)                              # getLegacyContainerName (:159-167)
+            if lm:
+                o["container"] = go_path_join_root(lm.group(1).decode("latin-1"))
+                o["victim"] = go_path_join_root(lm.group(2).decode("latin-1"))
+        else:
+            o["container"], o["victim"], o["constraint"] = m.group(6).decode("latin-1"), m.group(5).decode("latin-1"), m.group(1).decode("latin-1")
+            pid = go_atoi(m.group(8))
+            if pid is None:
+                self.cur = None
+                return "", ""
+            o["pid"], o["process"] = pid, m.group(7).decode("latin-1")
+            found = True
+        if found and o["pid"] != 0:
+            self.cur = None
+            return "OOM", self.summary(o)
+        if not found:
+            km = EXT_RE[24].search(line)                              # getProcessNamePid (:191-208)
+            if km:
+                pid = go_atoi(km.group(1))
+                if pid is None:
+                    self.cur = None
+                    return "", ""
+                o["pid"], o["process"] = pid, km.group(2).decode("latin-1")
+                self.cur = None
+                return "OOM", self.summary(o)
+        return "", ""
 
 
 def scan_lines(buf: bytes, ext: bool = False):
@@ -543,6 +670,7 @@ def scan_lines(buf: bytes, ext: bool = False):
             for kind in ext_match(line):
                 hits.append({"line": ln, "offset": off, "kind": kind, "code": 0, "device": ext_capture(kind, line).decode("latin-1")[:39],
                              "capture": ext_capture(kind, line), "message": ext_message(kind, line), "event_type": EV_WARNING, "actions": [],
+                             "spans": prim_spans(kind, line) if kind in PRIM_GROUPS else None,
                              "extended": False, "sub_code": 0, "unit": "", "error_status": 0, "intrinfo": 0, "link": 0, "hint": "", "description": ""})
         off += len(line) + 1
     return hits
@@ -709,6 +837,7 @@ def scan_raw_kmsg(buf: bytes, ext: bool = False):
             for kind in ext_match(m):
                 hits.append({"line": idx, "offset": off, "kind": kind, "code": 0, "device": ext_capture(kind, m).decode("latin-1")[:39],
                              "capture": ext_capture(kind, m), "message": ext_message(kind, m), "event_type": EV_WARNING, "actions": [],
+                             "spans": prim_spans(kind, m) if kind in PRIM_GROUPS else None,
                              "kmsg": (prio, seq, usec), "extended": False, "sub_code": 0, "error_status": 0})
         off += len(rec) + 1
     return hits, len(recs)

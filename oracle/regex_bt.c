@@ -103,10 +103,11 @@ static Node* parse_atom(Parser* P) {
     ++P->i;
     if (P->i >= P->n) { P->err = 1; return mk('e'); }
     int e = (unsigned char)P->s[P->i++];
-    if (e == 'd' || e == 's') {
+    if (e == 'd' || e == 's' || e == 'S') {
       Node* k = mk('[');
       k->cls = new_class(P->p);
-      cls_escape(P->p->classes[k->cls], e);
+      cls_escape(P->p->classes[k->cls], e == 'S' ? 's' : e);
+      if (e == 'S') for (int b = 0; b < 32; ++b) P->p->classes[k->cls][b] = (unsigned char)~P->p->classes[k->cls][b];   /* \S = [^\t\n\f\r ] */
       return k;
     }
     Node* l = mk('c');

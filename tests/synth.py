@@ -103,7 +103,7 @@ def ext_fuzz_lines(n: int, seed: int = SEED):
     """mutations of the matcher vectors: truncations, one-byte edits, duplicated / swapped halves, two vectors glued together
     (several anchors per line, patterns cut short, digits and colons moved) - the oracle decides what they mean"""
     rng = np.random.default_rng(seed)
-    base = [l for l in ext_lines() + EXT_EDGE_LINES if l]
+    base = [l for l in ext_lines() + EXT_EDGE_LINES + PRIM_EDGE_LINES + [x for sq in stateful_sequences() for x in sq] if l]
     repl = list(" :,.[]()#!0179aWs-/") + ["", "  ", "::", "12", "task ", " seconds", "blocked for more than ", "nvme nvme", "in libnccl.so"]
     out = []
     for i in range(n):
@@ -169,10 +169,59 @@ EXT_EDGE_LINES = [
 ]
 
 
+def stateful_sequences():
+    """every multi-line scenario of the os kernel-panic and memory OOM matcher tests (tests/golden/ext3_kmsg.json)"""
+    G = golden("ext3_kmsg.json")
+    seqs = [r["logLines"] for r in G["os.panic_detection"]["rows"]]
+    seqs += [[st[0] for st in r["scenario"]] for r in G["os.panic_stateful"]["rows"]]
+    seqs += [r["messages"] for r in G["memory.match_func"]["rows"] + G["memory.stream"]["rows"]]
+    seqs += [[r["line"]] for k in ("os.panic_start", "os.panic_cpu_pid", "memory.container_name", "memory.process_pid", "memory.oom_start")
+             for r in G[k]["rows"]]
+    return [[l.replace("\n", " ") for l in s] for s in seqs]
+
+
+PRIM_EDGE_LINES = [
+    "Kernel panic", "Kernel Panic", "Kernel PANIC", "Kernel  panic", "kernel panic", "Kernel pani", "xKernel panicx",
+    "CPU: 1 PID: 2 Comm: a", "CPU: 1 PID: 2 Comm: ", "CPU: 1 PID: 2 Comm:  a", "CPU:  1 PID: 2 Comm: a", "CPU: 1 PID: 2 Comm: a\tb",
+    "CPU: 99999999999999999999 PID: 2 Comm: a", "CPU: 1 PID: 99999999999999999999 Comm: a", "CPU: 1 PID: 2 Comm: a CPU: 3 PID: 4 Comm: b",
+    "CPU: x CPU: 5 PID: 6 Comm: c", "x invoked oom-killer:", "invoked oom-killer", "invoked oom-killer: invoked oom-killer:",
+    "oom-kill:constraint=A,nodemask=B,cpuset=C,mems_allowed=D,oom_memcg=E,task_memcg=F,task=G,pid=7,uid=8",
+    "oom-kill:constraint=A,nodemask=B,cpuset=C,mems_allowed=D,oom_memcg=E,task_memcg=F,task=G,pid=7,uid=8,pid=9,uid=10",
+    "oom-kill:constraint=A,nodemask=B,nodemask=B2,cpuset=C,mems_allowed=D,oom_memcg=E,oom_memcg=E2,task_memcg=F,task=G,task=G2,pid=7,uid=8",
+    "oom-kill:constraint=,nodemask=,cpuset=,mems_allowed=,oom_memcg=,task_memcg=,task=,pid=,uid=",
+    "oom-kill:constraint=A,nodemask=B,cpuset=C,mems_allowed=D,oom_memcg=E,task_memcg=F,task=G,pid=x7,uid=8",
+    "oom-kill:constraint=A,nodemask=B,cpuset=C,mems_allowed=D,oom_memcg=E,task_memcg=F,task=G,uid=8,pid=7",
+    "oom-kill:constraint=A,uid=0,nodemask=B,cpuset=C,mems_allowed=D,oom_memcg=/a,task_memcg=/b,task=G,pid=12,uid=8 oom-kill:constraint=Z,nodemask=,cpuset=,mems_allowed=,oom_memcg=/c,task_memcg=/d,task=H,pid=13,uid=9",
+    "Task in /a killed as a result of limit of /b", "Task in  killed as a result of limit of ", "Task in /a/../b//c/. killed as a result of limit of ../x",
+    "Task in /a killed as a result of limit of /b killed as a result of limit of /c", "Task in /a killed as a result of limit of",
+    "Killed process 12 (a)", "Killed process 12 ()", "Killed process 12 (a) (b) c)", "Killed process  12 (a)", "Killed process 12(a)",
+    "Killed process 99999999999999999999 (a)", "Killed process 12 (a", "Killed process 0 (zero)",
+]
+
+
+def stateful_stream(n_lines: int, seed: int = SEED):
+    """a long log: noise lines with the reference's panic / OOM scenarios, single primitive lines and edge lines dropped in
+    at random distances (so sequences overlap, time out, restart and interleave)"""
+    rng = np.random.default_rng(seed)
+    seqs = stateful_sequences()
+    singles = [l for l in PRIM_EDGE_LINES]
+    out = []
+    while len(out) < n_lines:
+        r = rng.random()
+        if r < 0.08:
+            sq = seqs[int(rng.integers(0, len(seqs)))]
+            out += sq[: int(rng.integers(1, len(sq) + 1))] if rng.random() < 0.3 else sq
+        elif r < 0.2:
+            out.append(singles[int(rng.integers(0, len(singles)))])
+        else:
+            out += ["[%d.%06d] usb 1-%d: noise line %d" % (len(out), i, i % 7, i) for i in range(int(rng.integers(1, 9)))]
+    return out[:n_lines]
+
+
 def ext_buffer(n_bytes: int, seed: int = SEED, hit_every: int = 50):
     """dmesg_buffer with the extra matchers' lines and decoys mixed in"""
     base = dmesg_buffer(n_bytes, seed, hit_every).split(b"\n")
-    ext = [l.encode() for l in ext_lines() + EXT_EDGE_LINES]
+    ext = [l.encode() for l in ext_lines() + EXT_EDGE_LINES + PRIM_EDGE_LINES]
     out = []
     for i, l in enumerate(base):
         out.append(l)

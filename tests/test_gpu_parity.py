@@ -107,6 +107,10 @@ def test_scan_edges(ctx, buf):
 def _cmp_ext(ctx, buf, hits, want):
     _cmp_hits(hits, want)
     for a, b in zip(hits, want):
+        if b["kind"] >= 19:                              # line primitives of the stateful matchers: every capture span
+            got = [buf[o:o + n] for o, n in ((a.dev_off, a.dev_len), (a.unit_name_off, a.unit_name_len), (a.pid_off, a.pid_len),
+                                             (a.pname_off, a.pname_len), (a.inj_off, a.inj_len))]
+            assert got == (b["spans"] or [b""] * 5), (a.as_dict(), b, got)
         if b["kind"] >= 3:
             assert a.dev_len == len(b["capture"]) and buf[a.dev_off:a.dev_off + a.dev_len] == b["capture"], (a.as_dict(), b)
             assert ctx.kmsg_message(a, buf) == b["message"], (a.as_dict(), b)
@@ -118,12 +122,12 @@ def _cmp_ext(ctx, buf, hits, want):
 def test_scan_ext_matchers(ctx):
     """GPUD_SCAN_EXT_MATCHERS: the stateless line matchers of nccl / peermem / infiniband / cpu / os / disk ride
     the same scan; default mode is unaffected"""
-    lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:40]
+    lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.PRIM_EDGE_LINES + synth.hit_lines()[:40]
     for buf in ("\n".join(lines).encode(), synth.ext_buffer(2_000_000, hit_every=60)):
         hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS)
         want = O.scan_lines(buf, ext=True)
         assert n_units == buf.count(b"\n") + 1
-        assert {h["kind"] for h in want} >= set(range(3, 19))
+        assert {h["kind"] for h in want} >= set(range(3, 25))
         _cmp_ext(ctx, buf, hits, want)
         _cmp_hits(ctx.kmsg_scan(buf)[0], O.scan_lines(buf))
     for l in lines:                                   # every vector as its own buffer
@@ -139,6 +143,35 @@ def test_scan_ext_matchers_fuzz(ctx):
     want = O.scan_lines(buf, ext=True)
     assert n_units == len(lines) and len(want) > 5000
     _cmp_ext(ctx, buf, hits, want)
+
+
+@pytest.mark.parametrize("seed,chunk", [(11, 1 << 30), (12, 997), (13, 50)])
+def test_scan_stateful_matchers(ctx, seed, chunk):
+    """os kernel-panic assembly and the memory OOM parser: scan primitives -> gpud_kmsg_stateful_feed == the reference's
+    closures run line by line; the stream is scanned in pieces to exercise the carried state"""
+    lines = [l.encode() for l in synth.stateful_stream(6000, seed=seed)]
+    want = O.stateful_events(lines)
+    assert sum(1 for e in want if e[1] == "os") >= 10 and sum(1 for e in want if e[1] == "memory") >= 10
+    st = g.KmsgStateful()
+    got = []
+    for a in range(0, len(lines), chunk):
+        part = lines[a:a + chunk]
+        buf = b"\n".join(part)
+        hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS)
+        assert n_units == len(part)
+        got += [(u + a, c, e, m) for u, c, e, m in st.feed(hits, buf, n_units)]
+    st.close()
+    assert got == want
+
+
+def test_scan_stateful_golden_sequences(ctx):
+    for seq in synth.stateful_sequences():
+        lines = [l.encode() for l in seq]
+        buf = b"\n".join(lines)
+        hits, n_units = ctx.kmsg_scan(buf, mode=g.SCAN_EXT_MATCHERS)
+        st = g.KmsgStateful()
+        assert st.feed(hits, buf, n_units) == O.stateful_events(lines), seq
+        st.close()
 
 
 def test_scan_ext_golden_match_tables(ctx):

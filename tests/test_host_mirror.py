@@ -127,3 +127,58 @@ def test_temperature_rule():                      # temperature/component.go:206
     assert L.gpudh_temperature(89, 89, 96, 95, 20, 10) == 2
     assert L.gpudh_temperature(80, 89, 70, 95, 10, 10) == 4
     assert L.gpudh_temperature(80, 0, 70, 0, 5, 0) == 0
+
+
+# ---- the stateful kmsg matchers (csrc/kmsg_stateful.cpp) over oracle-built primitive hits: no GPU needed ----
+def _oracle_prim_hits(lines, unit0=0):
+    """XidHit records for the six line primitives, spans from the oracle's regexes (what the scan kernel reports)"""
+    import gpud_b200 as g
+    from oracle import pyoracle as O
+    buf = b"\n".join(lines)
+    hits, off = [], 0
+    for u, l in enumerate(lines):
+        for k in range(19, 25):
+            m = O.EXT_RE[k].search(l)
+            if not m:
+                continue
+            h = g.XidHit()
+            h.unit_index, h.unit_offset, h.kind, h.link = u + unit0, off, k, off + m.start()
+            slots = ("dev", "unit_name", "pid", "pname", "inj")
+            for slot, grp in zip(slots, O.PRIM_GROUPS.get(k, (None,) * 5)):
+                if grp is not None:
+                    setattr(h, slot + "_off", off + m.start(grp))
+                    setattr(h, slot + "_len", m.end(grp) - m.start(grp))
+            hits.append(h)
+        off += len(l) + 1
+    return hits, buf
+
+
+def test_kmsg_stateful_golden_sequences():
+    import gpud_b200 as g
+    import synth
+    from oracle import pyoracle as O
+    for seq in synth.stateful_sequences():
+        lines = [l.encode() for l in seq]
+        hits, buf = _oracle_prim_hits(lines)
+        st = g.KmsgStateful()
+        assert st.feed(hits, buf, len(lines)) == O.stateful_events(lines), seq
+        st.close()
+
+
+@pytest.mark.parametrize("seed,chunk", [(1, 100000), (2, 7), (3, 1), (4, 64), (5, 13)])
+def test_kmsg_stateful_long_stream_in_chunks(seed, chunk):
+    """state (panic line counter, OOM instance) carries across feeds: the same events whatever the chunking"""
+    import gpud_b200 as g
+    import synth
+    from oracle import pyoracle as O
+    lines = [l.encode() for l in synth.stateful_stream(4000, seed=seed)]
+    want = O.stateful_events(lines)
+    assert sum(1 for e in want if e[1] == "os") >= 10 and sum(1 for e in want if e[1] == "memory") >= 10
+    st = g.KmsgStateful()
+    got = []
+    for a in range(0, len(lines), chunk):
+        part = lines[a:a + chunk]
+        hits, buf = _oracle_prim_hits(part)
+        got += [(u + a, c, e, m) for u, c, e, m in st.feed(hits, buf, len(part))]
+    st.close()
+    assert got == want

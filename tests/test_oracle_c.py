@@ -99,7 +99,7 @@ def test_ext_matchers_golden_and_python(golden):   # nccl / peermem / infiniband
         assert bool(CO.ext_match(r["line"].encode())[0] & 1) == r["want"], r
     for r in G["peermem_has"]["rows"]:
         assert bool(CO.ext_match(r["line"].encode())[0] & 2) == r["want"], r
-    lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.hit_lines()[:50] + synth.ext_fuzz_lines(3000)
+    lines = synth.ext_lines() + synth.EXT_EDGE_LINES + synth.PRIM_EDGE_LINES + synth.hit_lines()[:50] + synth.ext_fuzz_lines(3000)
     fired = set()
     for l in lines:
         b = l.encode()
@@ -110,15 +110,19 @@ def test_ext_matchers_golden_and_python(golden):   # nccl / peermem / infiniband
         for k in (8, 9):
             if k in kinds:
                 assert caps[k] == O.ext_capture(k, b), l
-    assert fired == set(range(3, 19))
+        for k in (20, 22, 23, 24):                       # line primitives of the stateful matchers: every capture group
+            if k in kinds:
+                m = O.EXT_RE[k].search(b)
+                assert CO.ext_groups(k, b)[: m.re.groups + 1] == [m.group(i) for i in range(m.re.groups + 1)], l
+    assert fired == set(range(3, 25))
 
 
 def test_c_ext_scan_equals_python_scan():
-    buf = synth.ext_buffer(600_000, hit_every=40)
+    buf = synth.ext_buffer(1_500_000, hit_every=40)
     ch, nl = CO.scan_lines(buf, ext=True)
     ph = O.scan_lines(buf, ext=True)
     assert nl == buf.count(b"\n") + 1
     assert [(h.line, h.kind, h.code, h.offset) for h in ch] == [(h["line"], h["kind"], h["code"], h["offset"]) for h in ph]
-    assert len({h.kind for h in ch}) >= 17 and sum(h.kind >= 3 for h in ch) >= 80
+    assert len({h.kind for h in ch}) >= 20 and sum(h.kind >= 3 for h in ch) >= 80
     # the default scan is unchanged by the extra lines
     assert [(h.line, h.kind) for h in CO.scan_lines(buf)[0]] == [(h["line"], h["kind"]) for h in O.scan_lines(buf)]

@@ -191,3 +191,67 @@ def test_ext2_matchers(golden):                    # infiniband / cpu / os / dis
         assert O.ext_message(7, r["line"].encode()) == r["want"], r
         n += 1
     assert n > 140
+
+
+def test_stateful_matchers(golden):                # os kernel-panic assembly + memory OOM parser (kmsg_matcher_test.go tables)
+    G = golden("ext3_kmsg.json")
+    for r in G["os.panic_start"]["rows"]:
+        assert bool(O.EXT_RE[19].search(r["line"].encode())) == r["want"], r
+    for r in G["os.panic_cpu_pid"]["rows"]:
+        m = O.EXT_RE[20].search(r["line"].encode())
+        ok = bool(m) and O.go_atoi(m.group(1)) is not None and O.go_atoi(m.group(2)) is not None
+        assert ok == r["wantFound"], r
+        if ok:
+            assert (int(m.group(1)), int(m.group(2)), m.group(3).decode()) == (r["wantCPU"], r["wantPID"], r["wantProcess"]), r
+    for r in G["os.panic_detection"]["rows"]:
+        pm, got = O.KernelPanicMatcher(), ("", "")
+        for l in r["logLines"]:
+            ev = pm.feed(l.encode())
+            if ev[0]:
+                got = ev
+                break
+        assert got == (r["wantEventName"], r["wantMessage"]), (r["name"], got)
+    for r in G["os.panic_stateful"]["rows"]:
+        pm = O.KernelPanicMatcher()
+        for line, ev, msg in r["scenario"]:
+            assert pm.feed(line.encode()) == (ev, msg), (r["name"], line)
+    pm = O.KernelPanicMatcher()
+    assert pm.feed(b"Kernel panic - not syncing: hung_task: blocked tasks") == ("", "")
+    for _ in range(G["os.max_lines"]["max_lines_after_start"] - 1):
+        assert pm.feed(b"line without cpu pid") == ("", "")
+    assert pm.feed(b"10th line without cpu pid") == (G["os.max_lines"]["event"], G["os.max_lines"]["fallback_message"])
+    for key in ("memory.match_func", "memory.stream"):
+        for r in G[key]["rows"]:
+            om = O.OOMMatcher()
+            got = [ev for ev in (om.feed(l.encode()) for l in r["messages"]) if ev[0] or ev[1]]
+            assert got == [(e["eventName"], e["message"]) for e in r["expectedEvents"]], (r["name"], got)
+    for r in G["memory.oom_start"]["rows"]:
+        assert bool(O.EXT_RE[21].search(r["line"].encode())) == r["expected"], r
+    for r in G["memory.container_name"]["rows"]:
+        om = O.OOMMatcher()
+        om.feed(b"x invoked oom-killer:")
+        om.feed(r["line"].encode())
+        m = O.EXT_RE[22].search(r["line"].encode())
+        assert bool(m) == (r["expectedFound"] or r["expectedError"]), r
+        if r["expectedError"]:
+            assert O.go_atoi(m.group(8)) is None and om.cur is None, r
+        elif "expectedContainer" in r and om.cur is not None:
+            assert (om.cur["container"], om.cur["victim"]) == (r["expectedContainer"], r["expectedVictim"]), r
+        elif r["expectedFound"]:
+            assert (m.group(6).decode(), m.group(5).decode(), m.group(1).decode(), int(m.group(8)), m.group(7).decode()) == \
+                   (r["expectedContainer"], r["expectedVictim"], r["expectedConstraint"], r["expectedPid"], r["expectedProcess"]), r
+    for r in G["memory.process_pid"]["rows"]:
+        m = O.EXT_RE[24].search(r["line"].encode())
+        assert bool(m) == (r["expectedFound"] or r["expectedError"]), r
+        if r["expectedError"]:
+            assert O.go_atoi(m.group(1)) is None, r
+        elif r["expectedFound"]:
+            assert (int(m.group(1)), m.group(2).decode()) == (r["expectedPid"], r["expectedProcess"]), r
+    for r in G["memory.summary"]["rows"]:
+        inst = r["instance"]
+        if inst is None:
+            continue                               # nil receiver: "" (Go-only case)
+        inst = inst if isinstance(inst, dict) else {}
+        o = {"pid": inst.get("Pid", 0), "process": inst.get("ProcessName", ""), "container": inst.get("ContainerName", ""),
+             "victim": inst.get("VictimContainerName", ""), "constraint": inst.get("Constraint", "")}
+        assert O.OOMMatcher.summary(o) == r["expected"], r

@@ -371,6 +371,41 @@ def main():
     resolve_msgs(N + "infiniband/kmsg_matcher_test.go", "TestAccessRegFailedMessage", "want", rows, cs)
     ext2["infiniband.access_reg_message"] = {"src": src, "rows": rows, "regexPCIDevice": cs["regexPCIDevice"]["value"], "prefix": cs["pciDeviceMessagePrefix"]["value"]}
     dump("ext2_kmsg.json", ext2)
+
+    # ---- the two STATEFUL matchers: os kernel-panic assembly and the memory OOM parser ----
+    ext3 = {}
+    OSD, MEMD = "components/os/", "components/memory/"
+    cs = consts(OSD + "kmsg_matcher.go")
+    rows, src = table(OSD + "kmsg_matcher_test.go", "TestKernelPanicDetection")
+    rows = ident(rows)
+    for r in rows:
+        r["wantEventName"] = cs[r["wantEventName"]]["value"] if r["wantEventName"] in cs else r["wantEventName"]
+    ext3["os.panic_detection"] = {"src": src, "rows": rows, "note": "lines fed to Match until the first non-empty event"}
+    rows, src = table(OSD + "kmsg_matcher_test.go", "TestKernelPanicStatefulMatcher")
+    rows = ident(rows)
+    for r in rows:
+        r["scenario"] = [[st[0], cs[st[1]]["value"] if st[1] in cs else st[1], st[2]] for st in r["scenario"]]
+    ext3["os.panic_stateful"] = {"src": src, "rows": rows, "note": "scenario steps: [line, eventName, message] through one matcher instance"}
+    body, line = find_func(open(os.path.join(REF, OSD + "kmsg_matcher_test.go")).read(), "TestKernelPanicHelperFunctions")
+    starts = [{"line": bytes(m.group(1), "utf-8").decode("unicode_escape"), "want": m.group(2) == "true"}
+              for m in re.finditer(r'\{"((?:[^"\\\\]|\\\\.)*)",\s*(true|false)\}', body)]
+    ext3["os.panic_start"] = {"src": OSD + "kmsg_matcher_test.go:%d" % line, "rows": starts}
+    cpu = []
+    for m in re.finditer(r'\{\s*line:\s*"((?:[^"\\\\]|\\\\.)*)",(?:\s*//[^\n]*)?\s*wantFound:\s*(true|false),((?:\s*want\w+:\s*[^,]+,)*)\s*\}', body):
+        r = {"line": bytes(m.group(1), "utf-8").decode("unicode_escape"), "wantFound": m.group(2) == "true"}
+        for k, v in re.findall(r'(want\w+):\s*([^,]+),', m.group(3)):
+            r[k] = int(v) if v.strip().isdigit() else v.strip().strip('"')
+        cpu.append(r)
+    ext3["os.panic_cpu_pid"] = {"src": OSD + "kmsg_matcher_test.go:%d" % line, "rows": cpu}
+    ext3["os.max_lines"] = {"src": OSD + "kmsg_matcher_test.go:712 ; " + OSD + "kmsg_matcher.go:64", "rows": [],
+                            "max_lines_after_start": 10, "fallback_message": "Kernel panic detected (no CPU/PID info found)",
+                            "event": cs["eventNameKernelPanic"]["value"]}
+    for key, fn in [("memory.match_func", "TestCreateMatchFunc"), ("memory.stream", "TestCreateMatchFuncStreamOOMs"),
+                    ("memory.container_name", "TestGetContainerName"), ("memory.process_pid", "TestGetProcessNamePid"),
+                    ("memory.oom_start", "TestCheckIfStartOfOomMessages"), ("memory.summary", "TestOomInstanceSummary")]:
+        rows, src = table(MEMD + "kmsg_matcher_test.go", fn)
+        ext3[key] = {"src": src, "rows": ident(rows)}
+    dump("ext3_kmsg.json", ext3)
     return 0
 
 
