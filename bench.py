@@ -332,6 +332,26 @@ def main():
         except Exception as ex:   # the scan leg must never cost the headline line
             scan = {"error": repr(ex)}
 
+    # ---- real ingest (BASELINE configs[1] shape): NVML getters -> pinned uint32 rows -> K1, rank 0 at N=1 only ----
+    ingest = None
+    if rank == 0 and world == 1 and not a.no_scan:
+        try:
+            iring = g.Ring(ctx, len(g.POLL_FIELDS), 1 << 16, 1000, thresholds=np.zeros(len(g.POLL_FIELDS)), dev=local)
+            poller = g.Poller(ctx, iring, dev=local)
+            poller.poll(200)
+            poller.poll(5000)
+            rows, sec = poller.last_rows()
+            iring.reduce()
+            iring.sync()
+            ingest = {"source": "NVML getters (temperature, power, 3 clocks, 2 utilisations, memory used) via the library's poller",
+                      "fields": len(g.POLL_FIELDS), "polls": int(rows.shape[0]), "polls_per_s": rows.shape[0] / sec,
+                      "samples_per_s": rows.shape[0] * len(g.POLL_FIELDS) / sec,
+                      "last_row": {k: int(v) for k, v in zip(g.POLL_FIELDS, rows[-1])}}
+            poller.close()
+            iring.close()
+        except Exception as ex:
+            ingest = {"error": repr(ex)}
+
     ring.close()
     ctx.close()
     if rank == 0:
@@ -342,7 +362,7 @@ def main():
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(),
                              "kernel": "k_window_reduce", "kernel_ms": k_reduce, "carry_kernel_ms": k_carry, "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst copy)"
                              if how == "measured" else "fallback 6650 GB/s (B200_PROFILING.md)", "algorithmic_bytes_per_launch": F * CAP * 8},
-                "cpu_baseline": cpu, "e2e_f64": e2e_f64, "scan": scan}
+                "cpu_baseline": cpu, "e2e_f64": e2e_f64, "scan": scan, "ingest": ingest}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -53,6 +53,33 @@ class XidHit(C.Structure):
                 "kmsg": (self.kmsg_priority, self.kmsg_seq, self.kmsg_usec)}
 
 
+POLL_FIELDS = ["temperature_c", "power_mw", "clock_graphics_mhz", "clock_sm_mhz", "clock_mem_mhz", "util_gpu_pct", "util_mem_pct", "memory_used_mib"]
+
+
+class Poller:
+    """host NVML poller feeding a ring with raw uint32 poll rows (gpud_poller_*)"""
+
+    def __init__(self, ctx: "Context", ring: "Ring", dev: Optional[int] = None):
+        self.ctx, self._L = ctx, ctx._L
+        self._h = C.c_void_p()
+        dev = ctx.devices[0] if dev is None else dev
+        ctx._check(self._L.gpud_poller_create(ctx._h, dev, ring._h, C.byref(self._h)))
+
+    def poll(self, n_polls: int, interval_us: int = 0):
+        self.ctx._check(self._L.gpud_poller_poll(self._h, n_polls, interval_us))
+
+    def last_rows(self, cap_rows: int = 1 << 14):
+        rows = np.empty((cap_rows, len(POLL_FIELDS)), dtype=np.uint32)
+        n, sec = C.c_int64(), C.c_double()
+        self.ctx._check(self._L.gpud_poller_last_rows(self._h, C.c_void_p(rows.ctypes.data), cap_rows, C.byref(n), C.byref(sec)))
+        return rows[: min(cap_rows, n.value)], sec.value
+
+    def close(self):
+        if self._h:
+            self._L.gpud_poller_destroy(self._h)
+            self._h = None
+
+
 class KmsgEvent(C.Structure):
     _fields_ = [("unit_index", C.c_int64), ("component", C.c_char * 16), ("event", C.c_char * 32), ("message", C.c_char * 440)]
 
@@ -116,7 +143,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -141,6 +168,8 @@ def lib() -> C.CDLL:
         "gpud_host_alloc": (i32, [i64, C.POINTER(vp)]), "gpud_host_free": (i32, [vp]),
         "gpud_ring_create": (i32, [vp, i32, C.POINTER(RingCfg), C.POINTER(vp)]), "gpud_ring_destroy": (i32, [vp]),
         "gpud_ring_set_stream": (i32, [vp, vp]), "gpud_ring_push": (i32, [vp, vp, i64]), "gpud_ring_push_device": (i32, [vp, vp, i64]), "gpud_ring_push_raw": (i32, [vp, vp, i64, i32]),
+        "gpud_poller_create": (i32, [vp, i32, vp, vp]), "gpud_poller_destroy": (None, [vp]), "gpud_poller_poll": (i32, [vp, i64, i64]),
+        "gpud_poller_last_rows": (i32, [vp, vp, i64, vp, vp]),
         "gpud_ring_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "gpud_ring_reduce": (i32, [vp]), "gpud_ring_sync": (i32, [vp]),
         "gpud_ring_kernel_ms": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]), "gpud_ring_read": (i32, [vp, i32, vp, i64]),

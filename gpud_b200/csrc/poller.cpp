@@ -1,0 +1,148 @@
+// poller.cpp — real ingest: the host poller that reads the NVML gauges of one GPU and feeds K1 with raw
+// uint32 poll rows through pinned memory (gpud_ring_push_raw).  The getters are the ones the reference's components call
+// once per minute and widen with metric.Set(float64(v)):
+//   temperature C     dev.GetTemperature(nvml.TEMPERATURE_GPU)        components/accelerator/nvidia/temperature/temperature.go:85
+//   power mW          dev.GetPowerUsage()                              components/accelerator/nvidia/power/power.go:46
+//   graphics / mem MHz dev.GetClockInfo(CLOCK_GRAPHICS / CLOCK_MEM)    components/accelerator/nvidia/clock-speed/clock_speed.go:41,59
+//   SM MHz            nvmlDeviceGetClockInfo(NVML_CLOCK_SM)
+//   gpu / mem util %  dev.GetUtilizationRates()                        components/accelerator/nvidia/utilization/utilization.go:44
+//   memory used MiB   dev.GetMemoryInfo()                              components/accelerator/nvidia/memory/memory.go:83
+// NVML is dlopen'ed (libnvidia-ml.so.1 ships with the driver, not with CUDA); a getter the device does not support
+// reports GPUD_POLL_UNSUPPORTED (0xffffffff) in its column, like the reference's "...Supported = false" fields.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "internal.h"
+
+namespace {
+
+typedef int nvmlReturn_t;
+typedef struct nvmlDevice_st* nvmlDevice_t;
+struct nvmlUtilization_t { unsigned int gpu, memory; };
+struct nvmlMemory_t { unsigned long long total, free, used; };
+
+struct Nvml {
+  void* so = nullptr;
+  nvmlReturn_t (*init)() = nullptr;
+  nvmlReturn_t (*by_pci)(const char*, nvmlDevice_t*) = nullptr;
+  nvmlReturn_t (*temperature)(nvmlDevice_t, int, unsigned int*) = nullptr;
+  nvmlReturn_t (*power)(nvmlDevice_t, unsigned int*) = nullptr;
+  nvmlReturn_t (*clock)(nvmlDevice_t, int, unsigned int*) = nullptr;
+  nvmlReturn_t (*util)(nvmlDevice_t, nvmlUtilization_t*) = nullptr;
+  nvmlReturn_t (*memory)(nvmlDevice_t, nvmlMemory_t*) = nullptr;
+  const char* (*err)(nvmlReturn_t) = nullptr;
+};
+
+Nvml* nvml() {
+  static Nvml n;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    n.so = dlopen("libnvidia-ml.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (n.so) {
+      *(void**)&n.init = dlsym(n.so, "nvmlInit_v2");
+      *(void**)&n.by_pci = dlsym(n.so, "nvmlDeviceGetHandleByPciBusId_v2");
+      *(void**)&n.temperature = dlsym(n.so, "nvmlDeviceGetTemperature");
+      *(void**)&n.power = dlsym(n.so, "nvmlDeviceGetPowerUsage");
+      *(void**)&n.clock = dlsym(n.so, "nvmlDeviceGetClockInfo");
+      *(void**)&n.util = dlsym(n.so, "nvmlDeviceGetUtilizationRates");
+      *(void**)&n.memory = dlsym(n.so, "nvmlDeviceGetMemoryInfo");
+      *(void**)&n.err = dlsym(n.so, "nvmlErrorString");
+      if (!n.init || !n.by_pci || !n.temperature || !n.power || !n.clock || !n.util || !n.memory || n.init() != 0) { dlclose(n.so); n.so = nullptr; }
+    }
+  }
+  return n.so ? &n : nullptr;
+}
+
+}  // namespace
+
+struct gpud_poller {
+  gpud_ctx* ctx = nullptr;
+  gpud_ring* ring = nullptr;
+  int dev = 0;
+  nvmlDevice_t h = nullptr;
+  uint32_t* rows = nullptr;      // pinned [cap_rows][GPUD_POLL_N_FIELDS]
+  int64_t cap_rows = 0, n_rows = 0;
+  double last_poll_s = 0.0;      // wall time of the last gpud_poller_poll call
+};
+
+extern "C" int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* ring, gpud_poller** out) {
+  if (!ctx || !ring || !out) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return gpud_fail(ctx, GPUD_E_UNSUPPORTED, "libnvidia-ml.so.1 not available (no driver on this host)");
+  char bus[32];
+  GPUD_CUDA(ctx, cudaDeviceGetPCIBusId(bus, sizeof bus, dev));
+  nvmlDevice_t h;
+  const nvmlReturn_t rc = N->by_pci(bus, &h);
+  if (rc != 0) return gpud_fail(ctx, GPUD_E_UNSUPPORTED, "nvmlDeviceGetHandleByPciBusId(%s): %s", bus, N->err ? N->err(rc) : "error");
+  gpud_poller* p = new gpud_poller();
+  p->ctx = ctx; p->ring = ring; p->dev = dev; p->h = h;
+  p->cap_rows = 1 << 14;
+  if (cudaMallocHost(&p->rows, (size_t)p->cap_rows * GPUD_POLL_N_FIELDS * sizeof(uint32_t)) != cudaSuccess) {
+    delete p;
+    return gpud_fail(ctx, GPUD_E_CUDA, "pinned poll buffer");
+  }
+  *out = p;
+  return GPUD_OK;
+}
+
+extern "C" void gpud_poller_destroy(gpud_poller* p) {
+  if (!p) return;
+  if (p->rows) cudaFreeHost(p->rows);
+  delete p;
+}
+
+// one poll row: eight getters, in GPUD_POLL_* order
+static void poll_row(Nvml* N, nvmlDevice_t h, uint32_t* r) {
+  unsigned int v;
+  r[GPUD_POLL_TEMPERATURE_C] = N->temperature(h, 0 /* NVML_TEMPERATURE_GPU */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
+  r[GPUD_POLL_POWER_MW] = N->power(h, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
+  r[GPUD_POLL_CLOCK_GRAPHICS_MHZ] = N->clock(h, 0 /* NVML_CLOCK_GRAPHICS */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
+  r[GPUD_POLL_CLOCK_SM_MHZ] = N->clock(h, 1 /* NVML_CLOCK_SM */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
+  r[GPUD_POLL_CLOCK_MEM_MHZ] = N->clock(h, 2 /* NVML_CLOCK_MEM */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
+  nvmlUtilization_t u;
+  if (N->util(h, &u) == 0) { r[GPUD_POLL_UTIL_GPU_PCT] = u.gpu; r[GPUD_POLL_UTIL_MEM_PCT] = u.memory; }
+  else r[GPUD_POLL_UTIL_GPU_PCT] = r[GPUD_POLL_UTIL_MEM_PCT] = GPUD_POLL_UNSUPPORTED;
+  nvmlMemory_t m;
+  r[GPUD_POLL_MEMORY_USED_MIB] = N->memory(h, &m) == 0 ? (uint32_t)(m.used >> 20) : GPUD_POLL_UNSUPPORTED;
+}
+
+extern "C" int32_t gpud_poller_poll(gpud_poller* p, int64_t n_polls, int64_t interval_us) {
+  if (!p || n_polls < 0 || interval_us < 0) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return GPUD_E_UNSUPPORTED;
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  int64_t done = 0;
+  while (done < n_polls) {
+    const int64_t batch = std::min<int64_t>(p->cap_rows, n_polls - done);
+    for (int64_t i = 0; i < batch; ++i) {
+      poll_row(N, p->h, p->rows + i * GPUD_POLL_N_FIELDS);
+      if (interval_us) { timespec ts{(time_t)(interval_us / 1000000), (long)(interval_us % 1000000) * 1000L}; nanosleep(&ts, nullptr); }
+    }
+    p->n_rows = batch;
+    const int32_t rc = gpud_ring_push_raw(p->ring, p->rows, batch, GPUD_DT_U32);   // pinned: direct DMA + widening append, synchronous return
+    if (rc) return rc;
+    done += batch;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  p->last_poll_s = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_poller_last_rows(gpud_poller* p, uint32_t* rows, int64_t cap_rows, int64_t* n_rows, double* seconds) {
+  if (!p) return GPUD_E_INVALID;
+  const int64_t n = std::min(cap_rows, p->n_rows);
+  if (n > 0 && rows) memcpy(rows, p->rows, (size_t)n * GPUD_POLL_N_FIELDS * sizeof(uint32_t));
+  if (n_rows) *n_rows = p->n_rows;
+  if (seconds) *seconds = p->last_poll_s;
+  return GPUD_OK;
+}

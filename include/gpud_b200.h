@@ -31,6 +31,7 @@ extern "C" {
 #define GPUD_E_CAPACITY (-4) /* caller's output buffer too small; *n_* = needed */
 #define GPUD_E_NCCL (-5)
 #define GPUD_E_STATE (-6)    /* call order (e.g. read before reduce)            */
+#define GPUD_E_UNSUPPORTED (-7) /* a host facility is missing (NVML for the poller) */
 
 typedef struct gpud_ctx gpud_ctx;
 typedef struct gpud_ring gpud_ring;
@@ -89,6 +90,23 @@ int32_t gpud_ring_push_device(gpud_ring* ring, const double* dev_rows, int64_t n
  * round-to-nearest-even above 2^53 like Go), so a uint32 poll row crosses PCIe at half the bytes. */
 enum { GPUD_DT_F64 = 0, GPUD_DT_U32 = 1, GPUD_DT_I32 = 2, GPUD_DT_F32 = 3, GPUD_DT_I64 = 4, GPUD_DT_U64 = 5 };
 int32_t gpud_ring_push_raw(gpud_ring* ring, const void* host_rows, int64_t n_rows, int32_t dtype);
+
+/* Real ingest: a host poller that reads the NVML gauges of CUDA device `dev` - the getters behind the
+ * reference's temperature / power / clock-speed / utilization / memory components (temperature/temperature.go:85,
+ * power/power.go:46, clock-speed/clock_speed.go:41,59, utilization/utilization.go:44, memory/memory.go:83) - into pinned
+ * uint32 poll rows and appends them to `ring` with gpud_ring_push_raw.  The ring must have GPUD_POLL_N_FIELDS fields, in this
+ * column order.  NVML is dlopen'ed; GPUD_E_UNSUPPORTED if the host has no driver library. */
+enum { GPUD_POLL_TEMPERATURE_C = 0, GPUD_POLL_POWER_MW = 1, GPUD_POLL_CLOCK_GRAPHICS_MHZ = 2, GPUD_POLL_CLOCK_SM_MHZ = 3,
+       GPUD_POLL_CLOCK_MEM_MHZ = 4, GPUD_POLL_UTIL_GPU_PCT = 5, GPUD_POLL_UTIL_MEM_PCT = 6, GPUD_POLL_MEMORY_USED_MIB = 7,
+       GPUD_POLL_N_FIELDS = 8 };
+#define GPUD_POLL_UNSUPPORTED 0xffffffffu   /* column value when the device does not support the getter */
+typedef struct gpud_poller gpud_poller;
+int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* ring, gpud_poller** out);
+void gpud_poller_destroy(gpud_poller* poller);
+/* Take n_polls poll rows (interval_us apart; 0 = back to back) and append them.  Synchronous. */
+int32_t gpud_poller_poll(gpud_poller* poller, int64_t n_polls, int64_t interval_us);
+/* The rows of the last push batch (at most 16384) as they went over PCIe, and the wall time of the last poll call. */
+int32_t gpud_poller_last_rows(gpud_poller* poller, uint32_t* rows, int64_t cap_rows, int64_t* n_rows, double* seconds);
 int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
 /* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
 int32_t gpud_ring_reduce(gpud_ring* ring);

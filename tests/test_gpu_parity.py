@@ -358,6 +358,38 @@ def test_ring_push_raw_types(ctx, dt):
     ring.close()
 
 
+def test_poller_real_ingest(ctx):
+    """the NVML poller appends real gauge readings as raw uint32 rows; the ring's aggregates equal the oracle's on
+    exactly the rows that crossed PCIe"""
+    W, cap, n = 100, 4096, 3000
+    thr = np.array([60.0, 200000.0, 1500.0, 1500.0, 3000.0, 50.0, 50.0, 1000.0])
+    ring = g.Ring(ctx, len(g.POLL_FIELDS), cap, W, thresholds=thr)
+    try:
+        poller = g.Poller(ctx, ring)
+    except g.GpudError as e:
+        ring.close()
+        pytest.skip("no NVML on this host: %s" % e)
+    poller.poll(n)
+    rows, seconds = poller.last_rows()
+    assert rows.shape == (n, len(g.POLL_FIELDS)) and seconds > 0
+    assert ring.counts() == (n, n, (n + W - 1) // W)
+    ok = rows != 0xffffffff                                  # a getter the device does not support reports the sentinel
+    col = {k: rows[:, i][ok[:, i]] for i, k in enumerate(g.POLL_FIELDS)}
+    assert ok[:, 0].all() and ok[:, 1].all(), "temperature and power are supported on every data-centre GPU"
+    assert col["temperature_c"].min() >= 10 and col["temperature_c"].max() <= 110
+    assert col["power_mw"].min() >= 10_000 and col["power_mw"].max() <= 1_500_000
+    for k in ("clock_graphics_mhz", "clock_sm_mhz", "clock_mem_mhz"):
+        assert col[k].size == 0 or (col[k].min() >= 100 and col[k].max() <= 5000), k
+    for k in ("util_gpu_pct", "util_mem_pct"):
+        assert col[k].size == 0 or col[k].max() <= 100, k
+    got = ring.reduce_all()
+    _check_windows(got, rows.astype(np.float64), W, thr)
+    poller.poll(500, interval_us=100)                        # paced polls; the ring keeps appending
+    assert ring.counts()[0] == n + 500
+    poller.close()
+    ring.close()
+
+
 def test_ring_push_larger_than_capacity(ctx):
     F, cap, W = 3, 1024, 100
     x = synth.gauge_stream(F, 5000, seed=9)
