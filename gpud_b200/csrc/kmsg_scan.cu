@@ -1120,6 +1120,7 @@ struct gpud_scan_state {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // around filter / prefix / match of the last scan
   uint8_t* h_stage[2] = {nullptr, nullptr};                    // pinned staging for pageable caller buffers
+  gpud_xid_hit* h_hits = nullptr; size_t h_hits_cap = 0;      // pinned landing buffer of the hit list
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
 };
 
@@ -1128,6 +1129,7 @@ void gpud_scan_state_free(gpud_scan_state* s) {
   cudaFree(s->d_tables); cudaFree(s->d_buf); cudaFree(s->d_chunk_sep); cudaFree(s->d_chunk_local); cudaFree(s->d_tile_base); cudaFree(s->d_cands);
   cudaFree(s->d_hits); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
+  if (s->h_hits) cudaFreeHost(s->h_hits);
   for (auto& e : s->ev) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) { if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]); if (s->ev_stage[i]) cudaEventDestroy(s->ev_stage[i]); }
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -1305,31 +1307,41 @@ static int32_t scan_collect(gpud_ctx* ctx, gpud_scan_state* s, gpud_xid_hit* hit
   if (n_hits) *n_hits = found;
   if (n_units) *n_units = (int64_t)s->h_counters[2] + 1;
   if (s->h_counters[0] > s->cand_cap) return gpud_fail(ctx, GPUD_E_CAPACITY, "candidate list overflow (%llu)", s->h_counters[0]);
-  std::vector<gpud_xid_hit> tmp((size_t)have);
+  // hits land in a pinned host buffer; only 24-byte keys are sorted, each 288-byte record moves once
+  if ((size_t)have > s->h_hits_cap) {
+    if (s->h_hits) cudaFreeHost(s->h_hits);
+    s->h_hits = nullptr;
+    s->h_hits_cap = 0;
+    const size_t want = std::max<size_t>((size_t)have, 4096);
+    GPUD_CUDA(ctx, cudaMallocHost(&s->h_hits, want * sizeof(gpud_xid_hit)));
+    s->h_hits_cap = want;
+  }
   if (have) {
-    GPUD_CUDA(ctx, cudaMemcpyAsync(tmp.data(), s->d_hits, (size_t)have * sizeof(gpud_xid_hit), cudaMemcpyDeviceToHost, st));
+    GPUD_CUDA(ctx, cudaMemcpyAsync(s->h_hits, s->d_hits, (size_t)have * sizeof(gpud_xid_hit), cudaMemcpyDeviceToHost, st));
     GPUD_CUDA(ctx, cudaStreamSynchronize(st));
   }
-  // device threads finish in arbitrary order: present hits in (unit, kind) order like the sequential reference loop
-  std::sort(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
-    return a.unit_index != b.unit_index ? a.unit_index < b.unit_index : a.kind < b.kind;
-  });
-  // extra line matchers: several anchors of one unit may match the same pattern; the reference reports the leftmost
-  if (have == found) {
-    std::stable_sort(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
-      if (a.unit_index != b.unit_index) return a.unit_index < b.unit_index;
-      if (a.kind != b.kind) return a.kind < b.kind;
-      return a.kind > GPUD_KIND_SXID && a.link < b.link;
-    });
-    tmp.erase(std::unique(tmp.begin(), tmp.end(), [](const gpud_xid_hit& a, const gpud_xid_hit& b) {
-                return a.kind > GPUD_KIND_SXID && a.unit_index == b.unit_index && a.kind == b.kind;
-              }), tmp.end());
+  // device threads finish in arbitrary order: present hits in (unit, kind) order like the sequential reference loop.
+  // Extra line matchers: several anchors of one unit may match the same pattern; the reference reports the leftmost.
+  struct Key { int64_t unit; int64_t link; int32_t kind; int32_t idx; };
+  std::vector<Key> keys((size_t)have);
+  for (int64_t i = 0; i < have; ++i) {
+    const gpud_xid_hit& h = s->h_hits[i];
+    keys[(size_t)i] = Key{h.unit_index, h.kind > GPUD_KIND_SXID ? h.link : 0, h.kind, (int32_t)i};
   }
-  const int64_t found_u = have == found ? (int64_t)tmp.size() : found;
+  std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+    if (a.unit != b.unit) return a.unit < b.unit;
+    if (a.kind != b.kind) return a.kind < b.kind;
+    return a.link != b.link ? a.link < b.link : a.idx < b.idx;
+  });
+  if (have == found)
+    keys.erase(std::unique(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+                 return a.kind > GPUD_KIND_SXID && a.unit == b.unit && a.kind == b.kind;
+               }), keys.end());
+  const int64_t found_u = have == found ? (int64_t)keys.size() : found;
   if (n_hits) *n_hits = found_u;
-  const int64_t have_u = (int64_t)tmp.size();
-  const int64_t n_copy = std::min<int64_t>(have_u, cap);
-  if (n_copy && hits) memcpy(hits, tmp.data(), (size_t)n_copy * sizeof(gpud_xid_hit));
+  const int64_t n_copy = std::min<int64_t>((int64_t)keys.size(), cap);
+  if (hits)
+    for (int64_t i = 0; i < n_copy; ++i) hits[i] = s->h_hits[keys[(size_t)i].idx];
   if (found_u > cap || found > have) return gpud_fail(ctx, GPUD_E_CAPACITY, "%lld hits, caller capacity %lld", (long long)found_u, (long long)cap);
   return GPUD_OK;
 }
