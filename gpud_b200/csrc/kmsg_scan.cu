@@ -33,10 +33,14 @@ constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid ("
 constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVIDIA GPU "
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
 // families >= 4: the anchor literals of the extra line matchers (GPUD_SCAN_EXT_MATCHERS), index into kExtLit[]
+constexpr int kPendingExtended = -77;         // event_type of an extended hit whose table searches run in k_classify_ext_coop
 constexpr int kFamShift = 58;               // candidate word = byte offset | family << 58
 constexpr int kExtFam0 = 4, kNumFam = 25;
 constexpr int kModeMask = 0xff;
-constexpr unsigned kMatchLanes = 16;        // candidates per warp in k_scan_match
+#ifndef GPUD_MATCH_LANES
+#define GPUD_MATCH_LANES 16
+#endif
+constexpr unsigned kMatchLanes = GPUD_MATCH_LANES;        // candidates per warp in k_scan_match
 
 struct ScanBuf {
   const uint8_t* p;
@@ -82,10 +86,29 @@ constexpr unsigned kSXid = 0x64695853u;   // "SXid"
 // bit 7 of every byte of the result is set exactly where the byte of x is zero
 __device__ __forceinline__ unsigned zero_bytes(unsigned x) { return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu); }
 
-// first index in [from, to) holding byte `c`, else `to`: bytes up to 4-byte alignment, then one aligned word per step
+// first index in [from, to) holding byte `c`, else `to`.  One thread walks a line here, so the cost is the chain of dependent
+// loads: a 16-byte aligned buffer (the library's own staging copy always is) is read one 128-bit block per step, with the
+// bytes outside [from, to) masked off; any other buffer one aligned word per step.
 __device__ int64_t find_byte(const ScanBuf& b, int64_t from, int64_t to, unsigned c) {
-  int64_t i = from;
+  if (from >= to) return to;
   const unsigned pat = c * 0x01010101u;
+  if ((((uintptr_t)b.p) & 15) == 0) {
+    int64_t blk = from & ~(int64_t)15;
+    for (; blk < to && blk + 16 <= b.len; blk += 16) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(b.p + blk));
+      const unsigned z[4] = {zero_bytes(q.x ^ pat), zero_bytes(q.y ^ pat), zero_bytes(q.z ^ pat), zero_bytes(q.w ^ pat)};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        unsigned zz = z[w];
+        const int64_t w0 = blk + 4 * w;
+        if (w0 < from) { const int sh = (int)(from - w0); zz = sh >= 4 ? 0u : (zz & (0xffffffffu << (8 * sh))); }   // bytes before `from`
+        if (zz) { const int64_t p = w0 + ((__ffs(zz) - 1) >> 3); return p < to ? p : to; }
+      }
+    }
+    for (int64_t i = from > blk ? from : blk; i < to; ++i) if (__ldg(b.p + i) == c) return i;   // the block that crosses the buffer end
+    return to;
+  }
+  int64_t i = from;
   while (i < to && (((uintptr_t)(b.p + i)) & 3)) { if (__ldg(b.p + i) == c) return i; ++i; }
   for (; i + 4 <= to; i += 4) {
     const unsigned z = zero_bytes(__ldg(reinterpret_cast<const unsigned*>(b.p + i)) ^ pat);
@@ -96,8 +119,28 @@ __device__ int64_t find_byte(const ScanBuf& b, int64_t from, int64_t to, unsigne
 }
 // last index in [lo, from) holding byte `c`, else lo - 1
 __device__ int64_t rfind_byte(const ScanBuf& b, int64_t lo, int64_t from, unsigned c) {
-  int64_t i = from;                              // exclusive
+  if (from <= lo) return lo - 1;
   const unsigned pat = c * 0x01010101u;
+  if ((((uintptr_t)b.p) & 15) == 0) {
+    int64_t blk = (from - 1) & ~(int64_t)15;
+    if (blk + 16 > b.len) {                                  // the block that crosses the buffer end: bytewise
+      for (int64_t i = from; i > lo && i > blk;) { --i; if (__ldg(b.p + i) == c) return i; }
+      blk -= 16;
+    }
+    for (; blk + 16 > lo && blk >= 0; blk -= 16) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(b.p + blk));
+      const unsigned z[4] = {zero_bytes(q.x ^ pat), zero_bytes(q.y ^ pat), zero_bytes(q.z ^ pat), zero_bytes(q.w ^ pat)};
+#pragma unroll
+      for (int w = 3; w >= 0; --w) {
+        unsigned zz = z[w];
+        const int64_t w0 = blk + 4 * w;
+        if (w0 + 4 > from) { const int keep = (int)(from - w0); zz = keep <= 0 ? 0u : (zz & (0xffffffffu >> (8 * (4 - keep)))); }   // bytes at or after `from`
+        if (zz) { const int64_t p = w0 + ((31 - __clz(zz)) >> 3); return p >= lo ? p : lo - 1; }
+      }
+    }
+    return lo - 1;
+  }
+  int64_t i = from;                              // exclusive
   while (i > lo && (((uintptr_t)(b.p + i)) & 3)) { --i; if (__ldg(b.p + i) == c) return i; }
   for (; i - 4 >= lo; i -= 4) {
     const unsigned z = zero_bytes(__ldg(reinterpret_cast<const unsigned*>(b.p + i - 4)) ^ pat);
@@ -612,6 +655,25 @@ __device__ bool pattern_ok(uint8_t kind, uint32_t care, uint32_t val, uint32_t i
 }
 
 // normalizeUnit(log unit) == normalizeUnit(alias) for any alias (xid.go:3174-3218)
+__device__ bool unit_matches_norm(const gpud_t_rule& r, const char* norm) {
+  if (norm[0] == 0) return false;
+  for (int a = 0; a < r.n_alias; ++a) {
+    int i = 0;
+    while (r.alias[a][i] && r.alias[a][i] == norm[i]) ++i;
+    if (r.alias[a][i] == 0 && norm[i] == 0) return true;
+  }
+  return false;
+}
+__device__ void normalize_unit(const char* unit, char* norm) {          // TrimSpace + ToUpper + '-'->'_' + keep [A-Z0-9_]
+  int n = 0;
+  for (int i = 0; unit[i] && n < GPUD_T_ALIAS_LEN - 1; ++i) {
+    int c = (unsigned char)unit[i];
+    if (c >= 'a' && c <= 'z') c -= 32;
+    if (c == '-') c = '_';
+    if ((c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_') norm[n++] = (char)c;
+  }
+  norm[n] = 0;
+}
 __device__ bool unit_matches(const gpud_t_rule& r, const char* unit) {
   char norm[GPUD_T_ALIAS_LEN];
   int n = 0;
@@ -721,7 +783,8 @@ __device__ bool xid_match_unit(const ScanBuf& g, int64_t s, int64_t e, const gpu
       h->inj_off = m2.inj_s; h->inj_len = (int32_t)(m2.inj_e - m2.inj_s);
       copy_span(b, m2.unit_s, m2.unit_e, h->unit_name, 40, nullptr);
       if (h->unit_name_len >= 40) h->flags |= GPUD_HIT_DEV_TRUNCATED;   // inline copy cut; no catalog alias is that long
-      if (classify_extended(T, h)) {
+      if (h->code > 0 && h->code < GPUD_T_MAX_XID && T->xid[h->code].present) {   // detailFromNVLinkInfo needs only the base code to
+        h->event_type = kPendingExtended;                                            // exist; the table searches run warp-wide in k_classify_ext_coop
         h->dev_off = m2.dev_s; h->dev_len = (int32_t)(m2.dev_e - m2.dev_s);
         copy_span(b, m2.dev_s, m2.dev_e, h->device, 40, "PCI:");      // kmsg.go:206-208
         if (h->dev_len + 4 > 39) h->flags |= GPUD_HIT_DEV_TRUNCATED;
@@ -965,11 +1028,47 @@ __device__ __forceinline__ bool is_sep(const ScanBuf& b, int64_t i, int mode) {
   return mode == GPUD_SCAN_LINES || ld8(b, i + 1) != ' ';
 }
 
-__global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const unsigned long long* __restrict__ cands,
+// Candidates leave the filter in arrival order.  Grouping them by family (a counting sort: histogram + scatter, two tiny
+// kernels) puts the same automaton on neighbouring lanes of the match kernel, which otherwise spends most of its issue
+// slots on 3-4 active lanes per instruction.  Only done when the list fits the side buffer; order inside a family is free.
+constexpr int kSortBins = 32;
+__global__ void __launch_bounds__(256) k_cand_count(const unsigned long long* __restrict__ cands, const unsigned long long* __restrict__ n_cand,
+                                                     unsigned long long cand_cap, unsigned long long side_cap, unsigned long long* fam_cnt) {
+  __shared__ unsigned s_cnt[kSortBins];
+  const unsigned long long n = min(*n_cand, cand_cap);
+  if (n > side_cap) return;
+  if (threadIdx.x < kSortBins) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    atomicAdd(&s_cnt[(cands[i] >> kFamShift) & (kSortBins - 1)], 1u);
+  __syncthreads();
+  if (threadIdx.x < kSortBins && s_cnt[threadIdx.x]) atomicAdd(&fam_cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_cand_scatter(const unsigned long long* __restrict__ cands, const unsigned long long* __restrict__ n_cand,
+                                                       unsigned long long cand_cap, unsigned long long side_cap, const unsigned long long* __restrict__ fam_cnt,
+                                                       unsigned long long* fam_pos, unsigned long long* __restrict__ side) {
+  __shared__ unsigned long long s_base[kSortBins];
+  const unsigned long long n = min(*n_cand, cand_cap);
+  if (n > side_cap) return;
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int f = 0; f < kSortBins; ++f) { s_base[f] = acc; acc += fam_cnt[f]; }
+  }
+  __syncthreads();
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long cv = cands[i];
+    const int f = (int)((cv >> kFamShift) & (kSortBins - 1));
+    side[s_base[f] + atomicAdd(&fam_pos[f], 1ull)] = cv;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const unsigned long long* __restrict__ cands_in,
+                                                     const unsigned long long* __restrict__ side, unsigned long long side_cap,
                                                      const unsigned long long* __restrict__ n_cand, unsigned long long cand_cap,
                                                      const uint32_t* __restrict__ chunk_local, const unsigned long long* __restrict__ tile_base, const gpud_tables* __restrict__ T,
                                                      gpud_xid_hit* hits, unsigned long long hit_cap, unsigned long long* n_hits) {
   const unsigned long long n = min(*n_cand, cand_cap);
+  const unsigned long long* __restrict__ cands = n <= side_cap ? side : cands_in;    // family-sorted copy when it exists
   // Every candidate runs its own data-dependent automaton, so lanes of a warp serialise on divergent paths.  Only
   // kMatchLanes lanes per warp take a candidate: the same work spreads over 32 / kMatchLanes times more warps, which the
   // schedulers overlap (measured: the kernel is latency-bound, not issue-bound).
@@ -1089,6 +1188,70 @@ __global__ void __launch_bounds__(256) k_scan_unit_index(ScanBuf b, int mode, co
   }
 }
 
+// detailFromNVLinkInfo for the extended hits of a scan, one WARP per hit: the three table searches (sub-code + status
+// override, sub-code detail, the 94 NVLink rules with their alias lists) are spread over the lanes and the first match in
+// table order is the minimum matching index - the same answer as the sequential loops of classify_extended(), which a
+// single thread of the match kernel spent about as long on as on the whole regex automaton.
+__global__ void __launch_bounds__(256) k_classify_ext_coop(const gpud_tables* __restrict__ T, gpud_xid_hit* hits, const unsigned long long* __restrict__ n_hits,
+                                                            unsigned long long hit_cap) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long n = min(*n_hits, hit_cap);
+  const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long hi = warp_g; hi < n; hi += n_warps) {
+    gpud_xid_hit* h = hits + hi;
+    if (h->event_type != kPendingExtended) continue;                 // warp-uniform
+    const int xid = h->code, sub = h->sub_code;
+    const uint32_t st = h->error_status, intr = h->intrinfo;
+    char unit[40], norm[GPUD_T_ALIAS_LEN];
+    for (int i = 0; i < 40; ++i) unit[i] = h->unit_name[i];
+    unit[39] = 0;
+    normalize_unit(unit, norm);
+    int i_status = 0x7fffffff, i_sub = 0x7fffffff, i_sub0 = 0x7fffffff, i_rule = 0x7fffffff;
+    for (int i = lane; i < T->n_by_status; i += 32)
+      if (i < i_status && T->by_status[i].xid == xid && T->by_status[i].sub_code == sub && T->by_status[i].error_status == st) i_status = i;
+    for (int i = lane; i < T->n_by_sub; i += 32) {
+      if (T->by_sub[i].xid != xid) continue;
+      if (i < i_sub && T->by_sub[i].sub_code == sub) i_sub = i;
+      if (i < i_sub0 && T->by_sub[i].sub_code == 0) i_sub0 = i;
+    }
+    for (int i = lane; i < T->n_rules; i += 32) {
+      const gpud_t_rule& r = T->rules[i];
+      if (i >= i_rule || r.xid != xid || r.error_status != st) continue;
+      if (!unit_matches_norm(r, norm)) continue;
+      if (pattern_ok(r.v2_kind, r.v2_care, r.v2_val, intr) || pattern_ok(r.v1_kind, r.v1_care, r.v1_val, intr)) i_rule = i;
+    }
+    i_status = __reduce_min_sync(kFull, i_status);
+    i_sub = __reduce_min_sync(kFull, i_sub);
+    i_sub0 = __reduce_min_sync(kFull, i_sub0);
+    i_rule = __reduce_min_sync(kFull, i_rule);
+    if (lane == 0) {
+      const gpud_t_detail base = T->xid[xid];
+      gpud_t_detail d = base;
+      int variant = 0;
+      if (i_status != 0x7fffffff) { d = T->by_status[i_status].d; variant = T->by_status[i_status].variant; }          // xid.go:97-107
+      else if (T->has_sub_map[xid]) {                                                                                   // xid.go:79-93
+        const int k = i_sub != 0x7fffffff ? i_sub : i_sub0;
+        if (k != 0x7fffffff) { d = T->by_sub[k].d; variant = T->by_sub[k].variant; }
+      }
+      h->rule_index = -1;
+      if (i_rule != 0x7fffffff) {                                                                                       // xid.go:3099-3114
+        const gpud_t_rule& r = T->rules[i_rule];
+        h->rule_index = i_rule;
+        h->flags |= GPUD_HIT_HAS_RULE;
+        if (r.rule_event != GPUD_EVENT_UNKNOWN) d.event = r.rule_event;
+        if (r.rule_n_actions > 0) { d.n_actions = 1; d.actions[0] = r.rule_action; d.actions[1] = d.actions[2] = d.actions[3] = 0; }
+      }
+      const int log_ev = h->severity_fatal ? GPUD_EVENT_FATAL : GPUD_EVENT_WARNING;   // eventTypeFromLogSeverity
+      if (log_ev > d.event) d.event = (int8_t)log_ev;
+      if (d.n_actions < 0) { d.n_actions = base.n_actions; for (int i = 0; i < 4; ++i) d.actions[i] = base.actions[i]; }
+      set_detail(h, d);
+      h->detail_variant = variant;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void k_classify(const gpud_tables* __restrict__ T, gpud_xid_hit* hits, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -1114,6 +1277,7 @@ struct gpud_scan_state {
   uint8_t* d_buf = nullptr; size_t buf_cap = 0;
   uint32_t* d_chunk_sep = nullptr; uint32_t* d_chunk_local = nullptr; unsigned long long* d_tile_base = nullptr; size_t chunk_cap = 0;
   unsigned long long* d_cands = nullptr; size_t cand_cap = 0;
+  unsigned long long* d_side = nullptr; size_t side_cap = 0;   // family-sorted copy of short candidate lists
   gpud_xid_hit* d_hits = nullptr; size_t hit_cap = 0;
   unsigned long long* d_counters = nullptr;   // [0] n_cand [1] n_hits [2] n_sep
   unsigned long long* h_counters = nullptr;   // pinned
@@ -1126,7 +1290,7 @@ struct gpud_scan_state {
 
 void gpud_scan_state_free(gpud_scan_state* s) {
   if (!s) return;
-  cudaFree(s->d_tables); cudaFree(s->d_buf); cudaFree(s->d_chunk_sep); cudaFree(s->d_chunk_local); cudaFree(s->d_tile_base); cudaFree(s->d_cands);
+  cudaFree(s->d_tables); cudaFree(s->d_buf); cudaFree(s->d_chunk_sep); cudaFree(s->d_chunk_local); cudaFree(s->d_tile_base); cudaFree(s->d_cands); cudaFree(s->d_side);
   cudaFree(s->d_hits); cudaFree(s->d_counters);
   if (s->h_counters) cudaFreeHost(s->h_counters);
   if (s->h_hits) cudaFreeHost(s->h_hits);
@@ -1146,7 +1310,7 @@ static int32_t scan_state_get(gpud_ctx* ctx, int dev, gpud_scan_state** out) {
     ctx->scan[slot] = s;
     GPUD_CUDA(ctx, cudaMalloc(&s->d_tables, sizeof(gpud_tables)));
     GPUD_CUDA(ctx, cudaMemcpy(s->d_tables, gpud_host_tables(), sizeof(gpud_tables), cudaMemcpyHostToDevice));
-    GPUD_CUDA(ctx, cudaMalloc(&s->d_counters, 4 * sizeof(unsigned long long)));
+    GPUD_CUDA(ctx, cudaMalloc(&s->d_counters, (4 + 2 * kSortBins) * sizeof(unsigned long long)));   // + family histogram and cursors
     GPUD_CUDA(ctx, cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long)));
     GPUD_CUDA(ctx, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) GPUD_CUDA(ctx, cudaEventCreate(&e));
@@ -1267,7 +1431,8 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   s->chunk_cap = cc;
   GPUD_CUDA(ctx, grow(&s->d_cands, &s->cand_cap, (size_t)(len / 4 + 1024)));
   GPUD_CUDA(ctx, grow(&s->d_hits, &s->hit_cap, (size_t)std::max<int64_t>(hit_cap_req, 1024)));
-  GPUD_CUDA(ctx, cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
+  GPUD_CUDA(ctx, cudaMemsetAsync(s->d_counters, 0, (4 + 2 * kSortBins) * sizeof(unsigned long long), st));
+  GPUD_CUDA(ctx, grow(&s->d_side, &s->side_cap, std::min<size_t>(s->cand_cap, (size_t)1 << 20)));
   if (len == 0) {
     GPUD_CUDA(ctx, cudaMemsetAsync(s->d_chunk_sep, 0, sizeof(uint32_t), st));
   }
@@ -1289,8 +1454,17 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   k_scan_prefix_top<<<1, 1024, 0, st>>>(s->d_tile_base, n_tiles, s->d_counters + 2);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[2], st);
-  k_scan_match<<<ctx->sm_count * 16, 128, 0, st>>>(b, mode, s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, s->d_chunk_local, s->d_tile_base,
-                                                   s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
+  // measured (100 MiB buffers, match step): default matchers 0.193 ms unsorted -> 0.176 ms sorted; 22 families 0.541 -> 0.226 ms
+  const unsigned long long side_cap = (unsigned long long)s->side_cap;
+  {
+  k_cand_count<<<64, 256, 0, st>>>(s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, (unsigned long long)s->side_cap, s->d_counters + 4);
+  k_cand_scatter<<<64, 256, 0, st>>>(s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, (unsigned long long)s->side_cap, s->d_counters + 4,
+                                      s->d_counters + 4 + kSortBins, s->d_side);
+  }
+  k_scan_match<<<ctx->sm_count * 16, 128, 0, st>>>(b, mode, s->d_cands, s->d_side, side_cap, s->d_counters + 0, (unsigned long long)s->cand_cap,
+                                                   s->d_chunk_local, s->d_tile_base, s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
+  GPUD_CUDA(ctx, cudaGetLastError());
+  k_classify_ext_coop<<<ctx->sm_count * 2, 256, 0, st>>>(s->d_tables, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
   k_scan_unit_index<<<ctx->sm_count * 2, 256, 0, st>>>(b, mode, s->d_chunk_local, s->d_tile_base, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
