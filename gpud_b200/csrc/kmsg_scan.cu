@@ -261,6 +261,12 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
   for (int64_t c0 = warp_g * 4; c0 < n_chunks; c0 += n_warps * 4) {
     uint4 q[4];
     unsigned tail = 0;                        // first word after the 2 KB run (lane 31 of the last chunk needs it)
+    if (aligned && (c0 + 4) * kChunk + 4 <= b.len) {   // the whole 2 KB run and its look-ahead word are inside the buffer (warp-uniform):
+      const uint4* __restrict__ src = reinterpret_cast<const uint4*>(b.p + c0 * kChunk) + lane;     // straight-line loads, no bounds logic
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] = __ldcs(src + u * (kChunk / 16));
+      tail = __ldg(reinterpret_cast<const unsigned*>(b.p + (c0 + 4) * kChunk));
+    } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t off = (c0 + u) * kChunk + lane * 16;
@@ -276,6 +282,7 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
     if (lane == 31) {
       const int64_t off = (c0 + 4) * kChunk;
       for (int k = 0; k < 4 && off + k < b.len; ++k) tail |= (unsigned)__ldg(b.p + off + k) << (k * 8);
+    }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
