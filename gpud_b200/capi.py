@@ -53,6 +53,23 @@ class XidHit(C.Structure):
                 "kmsg": (self.kmsg_priority, self.kmsg_seq, self.kmsg_usec)}
 
 
+class IbSnapshot(C.Structure):
+    _fields_ = [("ts", C.c_int64), ("total_link_downed", C.c_uint64), ("down", C.c_int32), ("pad", C.c_int32)]
+
+
+class IbVerdict(C.Structure):
+    _fields_ = [("drop", C.c_int32), ("flap", C.c_int32), ("drop_down_since", C.c_int64), ("drop_index", C.c_int64),
+                ("flap_down_since", C.c_int64), ("flap_index", C.c_int64), ("n_reverts", C.c_int64)]
+
+
+def ib_reason(device: str, port: int, down_since: int, flap: bool) -> str:
+    out = C.create_string_buffer(256)
+    n = lib().gpud_ib_reason(device.encode(), port, down_since, 1 if flap else 0, out, 256)
+    if n < 0:
+        raise GpudError(n, "gpud_ib_reason")
+    return out.value.decode()
+
+
 POLL_FIELDS = ["temperature_c", "power_mw", "clock_graphics_mhz", "clock_sm_mhz", "clock_mem_mhz", "util_gpu_pct", "util_mem_pct", "memory_used_mib"]
 
 
@@ -143,7 +160,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -168,6 +185,7 @@ def lib() -> C.CDLL:
         "gpud_host_alloc": (i32, [i64, C.POINTER(vp)]), "gpud_host_free": (i32, [vp]),
         "gpud_ring_create": (i32, [vp, i32, C.POINTER(RingCfg), C.POINTER(vp)]), "gpud_ring_destroy": (i32, [vp]),
         "gpud_ring_set_stream": (i32, [vp, vp]), "gpud_ring_push": (i32, [vp, vp, i64]), "gpud_ring_push_device": (i32, [vp, vp, i64]), "gpud_ring_push_raw": (i32, [vp, vp, i64, i32]),
+        "gpud_ib_scan": (i32, [vp, i32, vp, vp, i64, i64, i64, i32, vp]), "gpud_ib_reason": (i32, [C.c_char_p, C.c_uint32, i64, i32, vp, i32]),
         "gpud_poller_create": (i32, [vp, i32, vp, vp]), "gpud_poller_destroy": (None, [vp]), "gpud_poller_poll": (i32, [vp, i64, i64]),
         "gpud_poller_last_rows": (i32, [vp, vp, i64, vp, vp]),
         "gpud_ring_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
@@ -284,6 +302,23 @@ class Context:
         if rc:
             raise GpudError(rc, "gpud_hit_detail_json")
         return buf.value.decode("utf-8")
+
+    def ib_scan(self, series, drop_threshold: int, flap_down_interval: int, flap_back_threshold: int, dev: Optional[int] = None):
+        """series: list of lists of (ts, down, total_link_downed); returns one IbVerdict per series"""
+        dev = self.devices[0] if dev is None else dev
+        total = sum(len(s) for s in series)
+        snaps = (IbSnapshot * max(1, total))()
+        offs = (C.c_int64 * (len(series) + 1))()
+        k = 0
+        for i, s in enumerate(series):
+            offs[i] = k
+            for ts, down, tld in s:
+                snaps[k].ts, snaps[k].down, snaps[k].total_link_downed = ts, 1 if down else 0, tld
+                k += 1
+        offs[len(series)] = k
+        out = (IbVerdict * max(1, len(series)))()
+        self._check(self._L.gpud_ib_scan(self._h, dev, snaps, offs, len(series), drop_threshold, flap_down_interval, flap_back_threshold, out))
+        return [out[i] for i in range(len(series))]
 
     def kmsg_message(self, hit: XidHit, buf: bytes = None) -> str:
         """(eventName, message) of an extra-matcher hit exactly as the component's Match returns it"""

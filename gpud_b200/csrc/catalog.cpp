@@ -334,6 +334,20 @@ extern "C" int32_t gpud_kmsg_hit_message(const gpud_xid_hit* h, const uint8_t* b
   return (int32_t)m.size();
 }
 
+extern "C" int32_t gpud_ib_reason(const char* device, uint32_t port, int64_t t, int32_t flap, char* out, int32_t cap) {
+  if (!device || !out || cap <= 0) return -1;
+  // civil-from-days (proleptic Gregorian), UTC: time.Time.UTC().Format(time.RFC3339)
+  int64_t days = t / 86400, rem = t % 86400;
+  if (rem < 0) { rem += 86400; --days; }
+  const int64_t z = days + 719468, era = (z >= 0 ? z : z - 146096) / 146097;
+  const unsigned doe = (unsigned)(z - era * 146097), yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+  const int64_t y = (int64_t)yoe + era * 400;
+  const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100), mp = (5 * doy + 2) / 153, d = doy - (153 * mp + 2) / 5 + 1, m = mp < 10 ? mp + 3 : mp - 9;
+  const int n = snprintf(out, (size_t)cap, "%s port %u down since %04lld-%02u-%02uT%02d:%02d:%02dZ%s", device, port, (long long)(y + (m <= 2)), m, d,
+                         (int)(rem / 3600), (int)(rem % 3600 / 60), (int)(rem % 60), flap ? " (and flapped back to active)" : "");
+  return n < cap ? n : -1;
+}
+
 // xidErrorEventDetail JSON (xid/health_state.go:284-315), field order and omitempty as encoding/json emits them;
 // time is RFC3339 UTC seconds like metav1.Time.
 extern "C" int32_t gpud_hit_detail_json(const gpud_xid_hit* h, int64_t unix_seconds, char* out, int32_t cap) {

@@ -1,6 +1,7 @@
 // internal.h — shared by the translation units of libgpud_b200.so (not part of the ABI)
 #pragma once
 #include <cuda_runtime.h>
+#include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>

@@ -283,3 +283,23 @@ def raw_kmsg_buffer(n_records: int, seed: int = SEED):
             rec += "\n SUBSYSTEM=pci\n DEVICE=+pci:0000:%02x:00.0" % (i % 256)
         recs.append(rec)
     return ("\n".join(recs) + "\n").encode("utf-8", "surrogateescape")
+
+
+def ib_series(n_series: int, seed: int = SEED, max_len: int = 200):
+    """random (device, port) snapshot series: (ts, down, total_link_downed), time-ordered, with down runs of random length,
+    link counters that sometimes move inside a run, equal timestamps, and lengths around the 32-wide step of the kernel"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for s in range(n_series):
+        n = int(rng.choice([0, 1, 2, 3, 31, 32, 33, 63, 64, 65, int(rng.integers(0, max_len))]))
+        ts, t, tld, down = [], 1_700_000_000 + int(rng.integers(0, 10**6)), int(rng.integers(0, 50)), bool(rng.random() < 0.5)
+        p_flip = float(rng.choice([0.02, 0.1, 0.3, 0.6]))
+        for i in range(n):
+            t += int(rng.choice([0, 1, 5, 10, 30, 60, 300]))
+            if rng.random() < p_flip:
+                down = not down
+            if rng.random() < 0.05:
+                tld += 1
+            ts.append((t, down, tld))
+        out.append(ts)
+    return out

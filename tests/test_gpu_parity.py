@@ -358,6 +358,33 @@ def test_ring_push_raw_types(ctx, dt):
     ring.close()
 
 
+@pytest.mark.parametrize("drop_thr,flap_thr,flap_k", [(240, 25, 3), (60, 10, 1), (0, 0, 2), (1000, 300, 5)])
+def test_ib_drop_flap_scans(ctx, drop_thr, flap_thr, flap_k):
+    """findDrops / findFlaps over many port series at once == the sequential reference walk"""
+    from oracle import ib_scans as IB
+    G = synth.golden("ib_scans.json")
+    base = 1_700_000_000
+    series = [[(base + int(x["t"]), x["state"] != "active", x["total_link_downed"]) for x in r["snapshots"]]
+              for r in G["drops"]["rows"] + G["flaps"]["rows"]]
+    series += synth.ib_series(3000, seed=drop_thr + flap_k) + synth.ib_series(20, seed=5, max_len=5000)
+    got = ctx.ib_scan(series, drop_thr, flap_thr, flap_k)
+    n_drop = n_flap = 0
+    for s, v in zip(series, got):
+        d, f = IB.find_drops(s, drop_thr), IB.find_flaps(s, flap_thr, flap_k)
+        assert bool(v.drop) == (d is not None) and bool(v.flap) == (f is not None), (s[:40], v.drop, v.flap, d, f)
+        if d:
+            assert (v.drop_down_since, v.drop_index) == (d["down_since"], d["index"]), s[:40]
+            n_drop += 1
+        if f:
+            assert (v.flap_down_since, v.flap_index, v.n_reverts) == (f["down_since"], f["index"], f["reverts"]), s[:40]
+            n_flap += 1
+    assert n_drop > 20 and (n_flap > 20 or flap_k == 5)
+    if (drop_thr, flap_thr, flap_k) == (240, 25, 3):                      # the reference's own tables at its own thresholds
+        nd = len(G["drops"]["rows"])
+        assert [v.drop for v in got[:nd]] == [r["expected"] for r in G["drops"]["rows"]]
+        assert [v.flap for v in got[nd:nd + len(G["flaps"]["rows"])]] == [r["expected"] for r in G["flaps"]["rows"]]
+
+
 def test_poller_real_ingest(ctx):
     """the NVML poller appends real gauge readings as raw uint32 rows; the ring's aggregates equal the oracle's on
     exactly the rows that crossed PCIe"""

@@ -255,3 +255,22 @@ def test_stateful_matchers(golden):                # os kernel-panic assembly + 
         o = {"pid": inst.get("Pid", 0), "process": inst.get("ProcessName", ""), "container": inst.get("ContainerName", ""),
              "victim": inst.get("VictimContainerName", ""), "constraint": inst.get("Constraint", "")}
         assert O.OOMMatcher.summary(o) == r["expected"], r
+
+
+def test_ib_drop_flap_scans(golden):               # infiniband/store/scan_drops_test.go:15, scan_flaps_test.go:15
+    from oracle import ib_scans as IB
+    G = golden("ib_scans.json")
+    base = 1_700_000_000
+    def series(r):
+        return [(base + int(x["t"]), x["state"] != "active", x["total_link_downed"]) for x in r["snapshots"]]
+    for r in G["drops"]["rows"]:
+        got = IB.find_drops(series(r), G["drops"]["threshold_s"])
+        assert (1 if got else 0) == r["expected"], r["name"]
+    for r in G["flaps"]["rows"]:
+        got = IB.find_flaps(series(r), G["flaps"]["down_interval_threshold_s"], G["flaps"]["flap_back_to_active_threshold"])
+        assert (1 if got else 0) == r["expected"], r["name"]
+    assert sum(r["expected"] for r in G["drops"]["rows"]) >= 3 and sum(r["expected"] for r in G["flaps"]["rows"]) >= 3
+    import gpud_b200 as g                          # host-side reason formatting (no GPU needed)
+    for t in (0, 1, 86399, 86400, 951782400, 1_700_000_000, 1709251199, 1709251200, 4102444800):
+        assert g.ib_reason("mlx5_0", 1, t, False) == IB.drop_reason("mlx5_0", 1, t)
+        assert g.ib_reason("mlx5_10", 2, t, True) == IB.flap_reason("mlx5_10", 2, t)

@@ -406,6 +406,41 @@ def main():
         rows, src = table(MEMD + "kmsg_matcher_test.go", fn)
         ext3[key] = {"src": src, "rows": ident(rows)}
     dump("ext3_kmsg.json", ext3)
+
+    # ---- InfiniBand port drop / flap scans over snapshot series (infiniband/store/scan_drops.go, scan_flaps.go) ----
+    IBD = N + "infiniband/store/"
+    DUR = {"time.Second": 1, "time.Minute": 60, "time.Hour": 3600, "time.Millisecond": 0.001}
+
+    def dur_seconds(expr):
+        """30*time.Second / 1*time.Minute+30*time.Second / -5 * time.Minute -> seconds (float)"""
+        total = 0.0
+        for term in re.findall(r"[+-]?[^+-]+", expr.replace(" ", "")):
+            sign = -1.0 if term.startswith("-") else 1.0
+            term = term.lstrip("+-")
+            val = 1.0
+            for f in term.split("*"):
+                val *= DUR[f] if f in DUR else float(f)
+            total += sign * val
+        return total
+
+    def snapshot_cases(path, func):
+        """cases of a `tests := []struct{ name; snapshots devPortSnapshots; expected int }` table: time offsets relative to baseTime"""
+        body, line = find_func(open(os.path.join(REF, path)).read(), func)
+        out = []
+        for m in re.finditer(r'name:\s*"([^"]+)",\s*snapshots:\s*devPortSnapshots\{(.*?)\},\s*expected:\s*(\d+)', body, re.S):
+            snaps = []
+            for sm in re.finditer(r'createSnapshot\(baseTime(?:\.Add\(([^)]*)\))?,\s*"(\w+)",\s*(\d+)\)', m.group(2)):
+                snaps.append({"t": dur_seconds(sm.group(1)) if sm.group(1) else 0.0, "state": sm.group(2), "total_link_downed": int(sm.group(3))})
+            out.append({"name": m.group(1), "snapshots": snaps, "expected": int(m.group(3))})
+        return out, "%s:%d" % (path, line)
+
+    ib = {}
+    rows, src = snapshot_cases(IBD + "scan_drops_test.go", "TestFindDrops")
+    ib["drops"] = {"src": src, "rows": rows, "threshold_s": 240, "note": "threshold := 4 * time.Minute (scan_drops_test.go:27)"}
+    rows, src = snapshot_cases(IBD + "scan_flaps_test.go", "TestFindFlaps")
+    ib["flaps"] = {"src": src, "rows": rows, "down_interval_threshold_s": 25, "flap_back_to_active_threshold": 3,
+                   "note": "downIntervalThreshold := 25 * time.Second, flapBackToActiveThreshold := 3 (scan_flaps_test.go:27-28)"}
+    dump("ib_scans.json", ib)
     return 0
 
 
