@@ -53,6 +53,59 @@ class XidHit(C.Structure):
                 "kmsg": (self.kmsg_priority, self.kmsg_seq, self.kmsg_usec)}
 
 
+class Metric(C.Structure):
+    _fields_ = [("unix_ms", C.c_int64), ("component", C.c_char_p), ("name", C.c_char_p), ("labels_json", C.c_char_p), ("value", C.c_double)]
+
+
+class Store:
+    """the reference's SQLite event / metrics stores, written by the library (gpud_store_*)"""
+
+    def __init__(self, path: str):
+        self._L = lib()
+        self._h = C.c_void_p()
+        rc = self._L.gpud_store_open(path.encode(), C.byref(self._h))
+        if rc:
+            raise GpudError(rc, "gpud_store_open")
+
+    def _check(self, rc):
+        if rc:
+            buf = C.create_string_buffer(512)
+            self._L.gpud_store_last_error(self._h, buf, 512)
+            raise GpudError(rc, buf.value.decode())
+
+    def event_table(self, component: str) -> str:
+        out = C.create_string_buffer(256)
+        self._check(self._L.gpud_store_event_table(self._h, component.encode(), out, 256))
+        return out.value.decode()
+
+    def insert_event(self, table, unix_s, name, typ, message="", extra_info_json=""):
+        self._check(self._L.gpud_store_insert_event(self._h, table.encode(), unix_s, name.encode(), typ.encode(), message.encode(), extra_info_json.encode()))
+
+    def insert_xid_hits(self, table, hits, fallback_unix=0, boot_unix=0, raw_kmsg=False) -> int:
+        arr = (XidHit * max(1, len(hits)))(*hits)
+        n = C.c_int32()
+        self._check(self._L.gpud_store_insert_xid_hits(self._h, table.encode(), arr, len(hits), fallback_unix, boot_unix, 1 if raw_kmsg else 0, C.byref(n)))
+        return n.value
+
+    def metrics_table(self, table: str = ""):
+        self._check(self._L.gpud_store_metrics_table(self._h, table.encode()))
+
+    def record_metrics(self, rows, table: str = ""):
+        """rows: (unix_ms, component, name, labels_json, value)"""
+        arr = (Metric * max(1, len(rows)))()
+        keep = []
+        for i, (ms, comp, name, labels, val) in enumerate(rows):
+            b = (comp.encode(), name.encode(), labels.encode())
+            keep.append(b)
+            arr[i].unix_ms, arr[i].component, arr[i].name, arr[i].labels_json, arr[i].value = ms, b[0], b[1], b[2], val
+        self._check(self._L.gpud_store_record_metrics(self._h, table.encode(), arr, len(rows)))
+
+    def close(self):
+        if self._h:
+            self._L.gpud_store_close(self._h)
+            self._h = None
+
+
 class IbSnapshot(C.Structure):
     _fields_ = [("ts", C.c_int64), ("total_link_downed", C.c_uint64), ("down", C.c_int32), ("pad", C.c_int32)]
 
@@ -160,7 +213,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -185,6 +238,11 @@ def lib() -> C.CDLL:
         "gpud_host_alloc": (i32, [i64, C.POINTER(vp)]), "gpud_host_free": (i32, [vp]),
         "gpud_ring_create": (i32, [vp, i32, C.POINTER(RingCfg), C.POINTER(vp)]), "gpud_ring_destroy": (i32, [vp]),
         "gpud_ring_set_stream": (i32, [vp, vp]), "gpud_ring_push": (i32, [vp, vp, i64]), "gpud_ring_push_device": (i32, [vp, vp, i64]), "gpud_ring_push_raw": (i32, [vp, vp, i64, i32]),
+        "gpud_store_open": (i32, [C.c_char_p, vp]), "gpud_store_close": (None, [vp]), "gpud_store_last_error": (i32, [vp, vp, i32]),
+        "gpud_store_event_table": (i32, [vp, C.c_char_p, vp, i32]),
+        "gpud_store_insert_event": (i32, [vp, C.c_char_p, i64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]),
+        "gpud_store_insert_xid_hits": (i32, [vp, C.c_char_p, vp, i64, i64, i64, i32, vp]),
+        "gpud_store_metrics_table": (i32, [vp, C.c_char_p]), "gpud_store_record_metrics": (i32, [vp, C.c_char_p, vp, i64]),
         "gpud_ib_scan": (i32, [vp, i32, vp, vp, i64, i64, i64, i32, vp]), "gpud_ib_reason": (i32, [C.c_char_p, C.c_uint32, i64, i32, vp, i32]),
         "gpud_poller_create": (i32, [vp, i32, vp, vp]), "gpud_poller_destroy": (None, [vp]), "gpud_poller_poll": (i32, [vp, i64, i64]),
         "gpud_poller_last_rows": (i32, [vp, vp, i64, vp, vp]),

@@ -1,0 +1,263 @@
+// store_sqlite.cpp — the write path into the reference's SQLite event store and metrics store, so that
+// the /v1/events and /v1/metrics readers of gpud find what this library produced without any change on their side.
+//   events   pkg/eventstore/database.go:18-31 (schema version, columns), :136-143 (table name), :198-246 (createTable),
+//            :248-275 (insertEvent: NULLIF(?, '') for message / extra_info), :277-324 (findEvent duplicate check)
+//   metrics  pkg/metrics/store/sqlite.go:22-36 (schema version, columns, default table), :87-106 (CreateTable),
+//            :108-164 (insert: INSERT OR REPLACE, labels as JSON or '')
+//   xid events as persisted by xid/component.go:503-554 (name "error_xid", extra_info {"data", "device_uuid"})
+// SQLite itself is dlopen'ed (libsqlite3.so.0; the image carries the library but no headers), WAL + busy timeout like
+// pkg/sqlite (`_journal_mode=WAL&_busy_timeout=5000`).
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/gpud_b200.h"
+
+namespace {
+
+struct Sq {
+  void* so = nullptr;
+  int (*open_v2)(const char*, void**, int, const char*) = nullptr;
+  int (*close)(void*) = nullptr;
+  int (*exec)(void*, const char*, int (*)(void*, int, char**, char**), void*, char**) = nullptr;
+  int (*prepare_v2)(void*, const char*, int, void**, const char**) = nullptr;
+  int (*bind_int64)(void*, int, long long) = nullptr;
+  int (*bind_double)(void*, int, double) = nullptr;
+  int (*bind_text)(void*, int, const char*, int, void (*)(void*)) = nullptr;
+  int (*step)(void*) = nullptr;
+  int (*reset)(void*) = nullptr;
+  int (*finalize)(void*) = nullptr;
+  const unsigned char* (*column_text)(void*, int) = nullptr;
+  const char* (*errmsg)(void*) = nullptr;
+  int (*busy_timeout)(void*, int) = nullptr;
+  void (*free)(void*) = nullptr;
+};
+constexpr int kOk = 0, kRow = 100, kDone = 101;
+void (*const kTransient)(void*) = (void (*)(void*))(intptr_t)-1;
+
+Sq* sq() {
+  static Sq s;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    s.so = dlopen("libsqlite3.so.0", RTLD_NOW);
+    if (s.so) {
+#define SYM(f, name) *(void**)&s.f = dlsym(s.so, name)
+      SYM(open_v2, "sqlite3_open_v2"); SYM(close, "sqlite3_close"); SYM(exec, "sqlite3_exec"); SYM(prepare_v2, "sqlite3_prepare_v2");
+      SYM(bind_int64, "sqlite3_bind_int64"); SYM(bind_double, "sqlite3_bind_double"); SYM(bind_text, "sqlite3_bind_text"); SYM(step, "sqlite3_step");
+      SYM(reset, "sqlite3_reset"); SYM(finalize, "sqlite3_finalize"); SYM(column_text, "sqlite3_column_text"); SYM(errmsg, "sqlite3_errmsg");
+      SYM(busy_timeout, "sqlite3_busy_timeout"); SYM(free, "sqlite3_free");
+#undef SYM
+      if (!s.open_v2 || !s.close || !s.exec || !s.prepare_v2 || !s.bind_int64 || !s.bind_double || !s.bind_text || !s.step || !s.finalize ||
+          !s.column_text || !s.errmsg) { dlclose(s.so); s.so = nullptr; }
+    }
+  }
+  return s.so ? &s : nullptr;
+}
+
+// encoding/json string escaping (HTML-safe, like json.Marshal)
+void jstr(std::string& o, const std::string& s) {
+  o.push_back('"');
+  for (unsigned char c : s) {
+    if (c == '"') o += "\\\"";
+    else if (c == '\\') o += "\\\\";
+    else if (c == '\n') o += "\\n";
+    else if (c == '\r') o += "\\r";
+    else if (c == '\t') o += "\\t";
+    else if (c < 0x20 || c == '<' || c == '>' || c == '&') { char b[8]; snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o.push_back((char)c);
+  }
+  o.push_back('"');
+}
+
+bool ident_ok(const char* t) {          // table names are spliced into SQL (as the reference does with fmt.Sprintf): keep them identifiers
+  if (!t || !*t) return false;
+  for (const char* p = t; *p; ++p)
+    if (!((*p >= 'a' && *p <= 'z') || (*p >= 'A' && *p <= 'Z') || (*p >= '0' && *p <= '9') || *p == '_')) return false;
+  return true;
+}
+
+const char* event_type_string(int32_t ev) {   // api/v1/types.go:222-244
+  switch (ev) {
+    case GPUD_EVENT_INFO: return "Info";
+    case GPUD_EVENT_WARNING: return "Warning";
+    case GPUD_EVENT_CRITICAL: return "Critical";
+    case GPUD_EVENT_FATAL: return "Fatal";
+  }
+  return "Unknown";
+}
+
+}  // namespace
+
+struct gpud_store {
+  void* db = nullptr;
+  std::string err;
+};
+
+static int32_t sfail(gpud_store* st, const char* what) {
+  Sq* S = sq();
+  st->err = std::string(what) + ": " + (S && st->db ? S->errmsg(st->db) : "sqlite unavailable");
+  return GPUD_E_STATE;
+}
+
+extern "C" int32_t gpud_store_open(const char* path, gpud_store** out) {
+  if (!path || !out) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  gpud_store* st = new gpud_store();
+  if (S->open_v2(path, &st->db, 0x2 | 0x4 /* READWRITE | CREATE */, nullptr) != kOk) { if (st->db) S->close(st->db); delete st; return GPUD_E_STATE; }
+  if (S->busy_timeout) S->busy_timeout(st->db, 5000);
+  S->exec(st->db, "PRAGMA journal_mode=WAL;", nullptr, nullptr, nullptr);
+  *out = st;
+  return GPUD_OK;
+}
+extern "C" void gpud_store_close(gpud_store* st) {
+  if (!st) return;
+  if (Sq* S = sq()) if (st->db) S->close(st->db);
+  delete st;
+}
+extern "C" int32_t gpud_store_last_error(gpud_store* st, char* out, int32_t cap) {
+  if (!st || !out || cap <= 0) return GPUD_E_INVALID;
+  snprintf(out, (size_t)cap, "%s", st->err.c_str());
+  return GPUD_OK;
+}
+
+// defaultTableName (database.go:136-143) + createTable (database.go:198-246)
+extern "C" int32_t gpud_store_event_table(gpud_store* st, const char* component, char* table_out, int32_t cap) {
+  if (!st || !component || !table_out || cap <= 0) return GPUD_E_INVALID;
+  Sq* S = sq();
+  std::string c = component;
+  for (auto& ch : c) if (ch == ' ' || ch == '-') ch = '_';
+  for (size_t p; (p = c.find("__")) != std::string::npos;) c.replace(p, 2, "_");     // strings.ReplaceAll(c, "__", "_") is one left-to-right pass
+  // ReplaceAll does not rescan its own output; redo it faithfully
+  {
+    std::string src = component, a;
+    for (char ch : src) a.push_back((ch == ' ' || ch == '-') ? '_' : ch);
+    std::string b;
+    for (size_t i = 0; i < a.size();) { if (i + 1 < a.size() && a[i] == '_' && a[i + 1] == '_') { b.push_back('_'); i += 2; } else b.push_back(a[i++]); }
+    for (auto& ch : b) if (ch >= 'A' && ch <= 'Z') ch = (char)(ch - 'A' + 'a');
+    c = b;
+  }
+  const std::string t = "components_" + c + "_events_v0_5_0";
+  if (!ident_ok(t.c_str()) || (int32_t)t.size() + 1 > cap) return GPUD_E_INVALID;
+  const std::string ddl = "\nCREATE TABLE IF NOT EXISTS " + t + " (\n\ttimestamp INTEGER NOT NULL,\n\tname TEXT NOT NULL,\n\ttype TEXT NOT NULL,\n\tmessage TEXT,\n\textra_info TEXT\n);";
+  std::string sql = "BEGIN;" + ddl;
+  for (const char* col : {"timestamp", "name", "type"})
+    sql += "CREATE INDEX IF NOT EXISTS idx_" + t + "_" + col + " ON " + t + "(" + col + ");";
+  sql += "COMMIT;";
+  if (S->exec(st->db, sql.c_str(), nullptr, nullptr, nullptr) != kOk) { S->exec(st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return sfail(st, "create event table"); }
+  memcpy(table_out, t.c_str(), t.size() + 1);
+  return GPUD_OK;
+}
+
+static int32_t insert_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
+                            const char* extra_json, bool skip_duplicate, bool* inserted) {
+  Sq* S = sq();
+  if (inserted) *inserted = false;
+  const std::string t = table;
+  void* q = nullptr;
+  if (skip_duplicate) {                                          // findEvent (database.go:277-324) + compareEvent
+    std::string sel = "\nSELECT timestamp, name, type, message, extra_info FROM " + t + " WHERE timestamp = ? AND name = ? AND type = ?";
+    if (message && *message) sel += " AND message = ?";
+    if (S->prepare_v2(st->db, sel.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare find");
+    S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
+    if (message && *message) S->bind_text(q, 4, message, -1, kTransient);
+    bool dup = false;
+    while (S->step(q) == kRow) {
+      const char* ex = (const char*)S->column_text(q, 4);
+      if (std::string(ex ? ex : "") == std::string(extra_json ? extra_json : "")) { dup = true; break; }
+    }
+    S->finalize(q);
+    if (dup) return GPUD_OK;
+  }
+  const std::string ins = "INSERT INTO " + t + " (timestamp, name, type, message, extra_info) VALUES (?, ?, ?, NULLIF(?, ''), NULLIF(?, ''))";
+  if (S->prepare_v2(st->db, ins.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare insert");
+  S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
+  S->bind_text(q, 4, message ? message : "", -1, kTransient); S->bind_text(q, 5, extra_json ? extra_json : "", -1, kTransient);
+  const int rc = S->step(q);
+  S->finalize(q);
+  if (rc != kDone) return sfail(st, "insert event");
+  if (inserted) *inserted = true;
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_store_insert_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
+                                           const char* extra_info_json) {
+  if (!st || !ident_ok(table) || !name || !type) return GPUD_E_INVALID;
+  if (!sq()) return GPUD_E_UNSUPPORTED;
+  return insert_event(st, table, unix_s, name, type, message, extra_info_json, false, nullptr);
+}
+
+// the Insert loop of xid/component.go:468-577 for one scan's hits: one "error_xid" event per Xid hit, time = boot + kmsg usec
+// in RAW_KMSG mode else `fallback_unix`, extra_info = {"data": xidErrorEventDetail JSON, "device_uuid": device}; an event that
+// is already in the table is skipped (component.go:555-563).
+extern "C" int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
+                                              int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted) {
+  if (!st || !ident_ok(table) || n < 0 || (n && !hits)) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  int32_t ins = 0;
+  if (S->exec(st->db, "BEGIN;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "begin");
+  for (int64_t i = 0; i < n; ++i) {
+    const gpud_xid_hit& h = hits[i];
+    if (h.kind != GPUD_KIND_XID) continue;
+    const int64_t t = raw_kmsg ? boot_unix + h.kmsg_usec / 1000000 : fallback_unix;
+    char payload[4096];
+    if (gpud_hit_detail_json(&h, t, payload, sizeof payload) != GPUD_OK) continue;
+    std::string extra = "{\"data\":";                               // json.Marshal(map[string]string): keys sorted
+    jstr(extra, payload);
+    extra += ",\"device_uuid\":";
+    jstr(extra, std::string(h.device, strnlen(h.device, sizeof h.device)));
+    extra += "}";
+    bool did = false;
+    const int32_t rc = insert_event(st, table, t, "error_xid", event_type_string(h.event_type), "", extra.c_str(), true, &did);
+    if (rc) { S->exec(st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return rc; }
+    ins += did ? 1 : 0;
+  }
+  if (S->exec(st->db, "COMMIT;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "commit");
+  if (n_inserted) *n_inserted = ins;
+  return GPUD_OK;
+}
+
+// metrics/store/sqlite.go:87-106
+extern "C" int32_t gpud_store_metrics_table(gpud_store* st, const char* table) {
+  if (!st) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  const std::string t = table && *table ? table : "gpud_metrics_v0_5";
+  if (!ident_ok(t.c_str())) return GPUD_E_INVALID;
+  const std::string ddl = "\nCREATE TABLE IF NOT EXISTS " + t + " (\n\tunix_milliseconds INTEGER NOT NULL,\n\tcomponent_name TEXT NOT NULL,\n\tmetric_name TEXT NOT NULL,\n"
+                          "\tmetric_labels TEXT,\n\tmetric_value REAL NOT NULL,\n\tPRIMARY KEY (unix_milliseconds, component_name, metric_name, metric_labels)\n) WITHOUT ROWID;";
+  if (S->exec(st->db, ddl.c_str(), nullptr, nullptr, nullptr) != kOk) return sfail(st, "create metrics table");
+  return GPUD_OK;
+}
+
+// metrics/store/sqlite.go:108-164: INSERT OR REPLACE, one transaction per call
+extern "C" int32_t gpud_store_record_metrics(gpud_store* st, const char* table, const gpud_metric* ms, int64_t n) {
+  if (!st || n < 0 || (n && !ms)) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  const std::string t = table && *table ? table : "gpud_metrics_v0_5";
+  if (!ident_ok(t.c_str())) return GPUD_E_INVALID;
+  for (int64_t i = 0; i < n; ++i)
+    if (!ms[i].component || !*ms[i].component || !ms[i].name || !*ms[i].name) return GPUD_E_INVALID;   // ErrEmptyComponentName / ErrEmptyMetricName
+  if (n == 0) return GPUD_OK;
+  void* q = nullptr;
+  const std::string ins = "INSERT OR REPLACE INTO " + t + " (unix_milliseconds, component_name, metric_name, metric_labels, metric_value) VALUES (?, ?, ?, ?, ?)";
+  if (S->exec(st->db, "BEGIN;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "begin");
+  if (S->prepare_v2(st->db, ins.c_str(), -1, &q, nullptr) != kOk) { S->exec(st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return sfail(st, "prepare metrics insert"); }
+  for (int64_t i = 0; i < n; ++i) {
+    S->bind_int64(q, 1, ms[i].unix_ms); S->bind_text(q, 2, ms[i].component, -1, kTransient); S->bind_text(q, 3, ms[i].name, -1, kTransient);
+    S->bind_text(q, 4, ms[i].labels_json ? ms[i].labels_json : "", -1, kTransient); S->bind_double(q, 5, ms[i].value);
+    if (S->step(q) != kDone) { S->finalize(q); S->exec(st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return sfail(st, "insert metric"); }
+    S->reset(q);
+  }
+  S->finalize(q);
+  if (S->exec(st->db, "COMMIT;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "commit");
+  return GPUD_OK;
+}

@@ -276,6 +276,26 @@ void gpud_kmsg_stateful_destroy(gpud_kmsg_stateful* st);
 int32_t gpud_kmsg_stateful_feed(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
                                 gpud_kmsg_event* out, int32_t cap, int32_t* n_out);
 
+/* Write path into the reference's SQLite stores: the same tables, columns, indexes and statements as
+ * pkg/eventstore/database.go:136-143,198-275 and pkg/metrics/store/sqlite.go:87-164, so gpud's /v1/events and /v1/metrics
+ * readers work on them unchanged.  SQLite is dlopen'ed (GPUD_E_UNSUPPORTED without libsqlite3.so.0). */
+typedef struct gpud_store gpud_store;
+typedef struct { int64_t unix_ms; const char* component; const char* name; const char* labels_json; double value; } gpud_metric;
+int32_t gpud_store_open(const char* path, gpud_store** out);
+void gpud_store_close(gpud_store* st);
+int32_t gpud_store_last_error(gpud_store* st, char* out, int32_t cap);
+/* Bucket(component): creates "components_<name>_events_v0_5_0" (+ its three indexes) and returns the table name. */
+int32_t gpud_store_event_table(gpud_store* st, const char* component, char* table_out, int32_t cap);
+int32_t gpud_store_insert_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
+                                const char* extra_info_json);
+/* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
+int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
+                                   int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);
+/* table NULL or "" = "gpud_metrics_v0_5" (metrics/store/sqlite.go:36) */
+int32_t gpud_store_metrics_table(gpud_store* st, const char* table);
+int32_t gpud_store_record_metrics(gpud_store* st, const char* table, const gpud_metric* ms, int64_t n);
+
+
 /* ------------------------------------------------------------------------------------------------
  * Whole-box NVLink / fabric view.
  * Replaces: the single-process loops of nvlink.Check (nvlink/component.go:164-311),

@@ -232,6 +232,42 @@ def test_hit_json_matches_oracle(ctx):
     assert n > 200
 
 
+def test_store_persists_xid_events(ctx, tmp_path):
+    """scan -> gpud_store_insert_xid_hits -> the reference's getEvents query returns exactly the events the xid
+    component would have persisted (name, type, extra_info JSON with the xidErrorEventDetail payload), duplicates skipped"""
+    import json
+    import sqlite3
+    try:
+        st = g.Store(str(tmp_path / "gpud.state"))
+    except g.GpudError as e:
+        pytest.skip("no libsqlite3.so.0: %s" % e)
+    G = synth.golden("store_sql.json")
+    lines = synth.hit_lines()
+    buf = "\n".join(lines).encode()
+    hits, _ = ctx.kmsg_scan(buf)
+    t = st.event_table("accelerator-nvidia-error-xid")
+    now = 1740327858
+    n_ins = st.insert_xid_hits(t, hits, fallback_unix=now)
+    assert st.insert_xid_hits(t, hits, fallback_unix=now) == 0          # second pass: every event is found already (component.go:555-563)
+    want = set()
+    ev_names = {1: "Info", 2: "Warning", 3: "Critical", 4: "Fatal", 0: "Unknown"}
+    for h in hits:
+        if h.kind != 1:
+            continue
+        line = buf[h.unit_offset:].split(b"\n", 1)[0]
+        x = O.xid_match(line)
+        extra = "{" + '"data":' + O._go_json_str(O.xid_event_detail_json(x, now)) + ',"device_uuid":' + O._go_json_str(x.device) + "}"
+        want.add((now, "error_xid", ev_names[x.detail.event_type], None, extra))
+    db = sqlite3.connect(str(tmp_path / "gpud.state"))
+    rows = list(db.execute(G["event_get"]["sql"].format(table=t), (0,)))
+    assert n_ins == len(rows) == len(want) and set(rows) == want and len(want) > 150
+    for r in rows[:20]:
+        d = json.loads(r[4])
+        assert set(d) == {"data", "device_uuid"} and "xid" in json.loads(d["data"])
+    db.close()
+    st.close()
+
+
 def test_classify_entry(ctx):
     """gpud_xid_classify on hand-built hits: the status-specific vectors of xid/xid_test.go:13-55"""
     for r in synth.golden("xid_kmsg.json")["status_specific"]["rows"]:

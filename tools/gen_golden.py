@@ -318,7 +318,7 @@ def main():
         """name -> string for every `name = "..."` / `name = `...`` constant of a Go file (behavioural data only)"""
         out = {}
         for i, ln in enumerate(open(os.path.join(REF, path)).read().split("\n"), 1):
-            m = re.match(r'^\s*(\w+)\s*=\s*(?:"((?:[^"\\]|\\.)*)"|`([^`]*)`)\s*$', ln)
+            m = re.match(r'^\s*(?:const\s+)?(\w+)\s*=\s*(?:"((?:[^"\\]|\\.)*)"|`([^`]*)`)\s*$', ln)
             if m:
                 out[m.group(1)] = {"value": m.group(3) if m.group(3) is not None else bytes(m.group(2), "utf-8").decode("unicode_escape"), "line": i}
         return out
@@ -441,6 +441,31 @@ def main():
     ib["flaps"] = {"src": src, "rows": rows, "down_interval_threshold_s": 25, "flap_back_to_active_threshold": 3,
                    "note": "downIntervalThreshold := 25 * time.Second, flapBackToActiveThreshold := 3 (scan_flaps_test.go:27-28)"}
     dump("ib_scans.json", ib)
+
+    # ---- the SQL of the event store and the metrics store, as the Go sources format it ----
+    def go_fmt_sql(path, func, which=0):
+        """the `which`-th backquoted or quoted fmt.Sprintf format string of `func`, with its %s arguments substituted"""
+        src = open(os.path.join(REF, path)).read()
+        body, line = find_func(src, func)
+        cs = consts(path)
+        cs["tableName"] = cs["table"] = {"value": "{table}"}
+        fm = list(re.finditer(r'fmt\.Sprintf\(\s*(`[^`]*`|"(?:[^"\\]|\\.)*")\s*,([^;]*?)\)\s*[,)\n]', body, re.S))[which]
+        f = fm.group(1)
+        f = f[1:-1] if f.startswith("`") else bytes(f[1:-1], "utf-8").decode("unicode_escape")
+        args = [a.strip() for a in re.sub(r"//[^\n]*", "", fm.group(2)).split(",") if a.strip()]
+        vals = [cs[a]["value"] if a in cs else "{" + a + "}" for a in args]
+        return f % tuple(vals[: f.count("%s")]), "%s:%d" % (path, line)
+
+    sql = {}
+    ES, MS = "pkg/eventstore/database.go", "pkg/metrics/store/sqlite.go"
+    for key, path, func, which in [("event_create_table", ES, "createTable", 0), ("event_index_0", ES, "createTable", 1), ("event_index_1", ES, "createTable", 2),
+                                   ("event_index_2", ES, "createTable", 3), ("event_insert", ES, "insertEvent", 0), ("event_get", ES, "getEvents", 0),
+                                   ("event_table_name", ES, "defaultTableName", 0), ("metrics_create_table", MS, "CreateTable", 0), ("metrics_insert_prefix", MS, "insert", 0)]:
+        text, src = go_fmt_sql(path, func, which)
+        sql[key] = {"src": src, "rows": [], "sql": text}
+    sql["constants"] = {"src": ES + ":18 ; " + MS + ":22,36", "rows": [], "event_schema_version": consts(ES)["schemaVersion"]["value"],
+                        "metrics_schema_version": consts(MS)["schemaVersion"]["value"]}
+    dump("store_sql.json", sql)
     return 0
 
 
