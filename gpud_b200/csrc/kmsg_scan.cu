@@ -150,24 +150,6 @@ __device__ int64_t rfind_byte(const ScanBuf& b, int64_t lo, int64_t from, unsign
   return lo - 1;
 }
 
-// Verify one anchor position and append it to the candidate list.  The seven bytes after "NVRM" are fetched with
-// independent loads (one round trip) before any of them is compared.
-__device__ __noinline__ void filter_verify(const ScanBuf& b, int64_t a, bool is_nvrm, unsigned long long* cands, unsigned long long* n_cand,
-                                           unsigned long long cand_cap) {
-  unsigned long long fam = kFamS;
-  if (is_nvrm) {
-    int c[7];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) c[k] = ld8(b, a + 4 + k);
-    if (c[0] != ':') return;
-    if (c[1] == ' ' && c[2] == 'X' && c[3] == 'i' && c[4] == 'd' && c[5] == ' ' && c[6] == '(') fam = kFamX;
-    else if (!is_ws(c[1])) return;
-    else fam = nvrm_family(b, a, b.len);
-    if (!fam) return;
-  }
-  const unsigned long long slot = atomicAdd(n_cand, 1ull);
-  if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << kFamShift);
-}
 
 // nvrm_family for the R3/R4 shapes, by the whole warp: the 32 bytes after "NVRM:" are fetched one per lane, the
 // whitespace run ends at the first non-\s ballot bit, and the two literals are compared lane-wise against it.
@@ -234,13 +216,6 @@ __device__ __forceinline__ bool coop_lit(const ScanBuf& b, int64_t a, const char
     bad |= __ballot_sync(kFull, i < n && cb != (int)(unsigned char)__ldg(lit + (i < n ? i : 0)));
   }
   return bad == 0u;
-}
-// one thread: literal of n bytes at i inside [.., e)
-__device__ __forceinline__ bool lit_at_n(const ScanBuf& b, int64_t i, int64_t e, const char* lit, int n) {
-  if (i + n > e) return false;
-  for (int k = 0; k < n; ++k)
-    if (__ldg(b.p + i + k) != (uint8_t)__ldg(lit + k)) return false;
-  return true;
 }
 
 template <int MODE, bool EXT>

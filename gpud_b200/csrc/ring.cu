@@ -116,28 +116,10 @@ __device__ __forceinline__ K64 warp_min_k64(unsigned hi, unsigned lo) {
   r.lo = __reduce_min_sync(kFull, hi == r.hi ? lo : 0xffffffffu);
   return r;
 }
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
 __device__ __forceinline__ double k64_to_f64(K64 k) {
   const unsigned m = (k.hi & 0x80000000u) ? 0x80000000u : 0xffffffffu;   // inverse of the totalOrder key map
   const unsigned lo = (k.hi & 0x80000000u) ? k.lo : ~k.lo;
   return __hiloint2double((int)(k.hi ^ m), (int)lo);
-}
-// k-th largest (1-based, k <= 32) of one 32-bit value per lane, counting multiplicity: 32-bit bitonic sort, straight-line
-__device__ __forceinline__ unsigned warp_kth_largest_u32(unsigned v, int k, int lane) {
-#pragma unroll
-  for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-    for (int j = kk >> 1; j > 0; j >>= 1) {
-      const unsigned o = __shfl_xor_sync(kFull, v, j);
-      const bool keep_max = (((lane & kk) == 0) == ((lane & j) == 0));
-      v = keep_max ? max(v, o) : min(v, o);
-    }
-  }
-  return __shfl_sync(kFull, v, k - 1);
 }
 // bitonic sort across the 32 lanes, descending, on (hi, lo)
 __device__ __forceinline__ void warp_sort_desc_k64(unsigned& hi, unsigned& lo, int lane) {
