@@ -271,7 +271,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg)):
+    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric)):
         if L.gpud_sizeof(which) != C.sizeof(st):
             raise GpudError(-1, "ABI layout mismatch for %s: C %d vs ctypes %d" % (st.__name__, L.gpud_sizeof(which), C.sizeof(st)))
     _lib = L

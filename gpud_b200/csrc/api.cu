@@ -64,7 +64,8 @@ extern "C" int32_t gpud_host_free(void* p) {
   return cudaFreeHost(p) == cudaSuccess ? GPUD_OK : GPUD_E_CUDA;
 }
 
-// struct sizes for binding layout checks (ctypes / cgo): 0 hit, 1 fabric_raw, 2 fabric_local, 3 fabric_verdict, 4 ring_cfg
+// struct sizes for binding layout checks (ctypes / cgo): 0 hit, 1 fabric_raw, 2 fabric_local, 3 fabric_verdict, 4 ring_cfg,
+// 5 kmsg_event, 6 ib_snapshot, 7 ib_verdict, 8 metric
 extern "C" int32_t gpud_sizeof(int32_t which) {
   switch (which) {
     case 0: return (int32_t)sizeof(gpud_xid_hit);
@@ -72,6 +73,10 @@ extern "C" int32_t gpud_sizeof(int32_t which) {
     case 2: return (int32_t)sizeof(gpud_fabric_local);
     case 3: return (int32_t)sizeof(gpud_fabric_verdict);
     case 4: return (int32_t)sizeof(gpud_ring_cfg);
+    case 5: return (int32_t)sizeof(gpud_kmsg_event);
+    case 6: return (int32_t)sizeof(gpud_ib_snapshot);
+    case 7: return (int32_t)sizeof(gpud_ib_verdict);
+    case 8: return (int32_t)sizeof(gpud_metric);
   }
   return -1;
 }

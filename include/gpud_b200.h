@@ -37,7 +37,8 @@ typedef struct gpud_ctx gpud_ctx;
 typedef struct gpud_ring gpud_ring;
 
 int32_t gpud_abi_version(void);
-/* sizeof of the ABI structs for binding layout checks: 0 gpud_xid_hit, 1 gpud_fabric_raw, 2 gpud_fabric_local,
+/* sizeof of the ABI structs for binding layout checks (5 gpud_kmsg_event, 6 gpud_ib_snapshot, 7 gpud_ib_verdict, 8 gpud_metric):
+ * 0 gpud_xid_hit, 1 gpud_fabric_raw, 2 gpud_fabric_local,
  * 3 gpud_fabric_verdict, 4 gpud_ring_cfg; -1 otherwise. */
 int32_t gpud_sizeof(int32_t which);
 
