@@ -92,25 +92,6 @@ int32_t gpud_ring_push_device(gpud_ring* ring, const double* dev_rows, int64_t n
 enum { GPUD_DT_F64 = 0, GPUD_DT_U32 = 1, GPUD_DT_I32 = 2, GPUD_DT_F32 = 3, GPUD_DT_I64 = 4, GPUD_DT_U64 = 5 };
 int32_t gpud_ring_push_raw(gpud_ring* ring, const void* host_rows, int64_t n_rows, int32_t dtype);
 
-/* InfiniBand port drop / flap scans (SURVEY.md 8f.4): findDrops / findFlaps of
- * components/accelerator/nvidia/infiniband/store/scan_drops.go:41-116 and scan_flaps.go:47-134 over many (device, port)
- * snapshot series at once.  snaps = the series back to back, each in ascending time; series s is
- * snaps[series_off[s] .. series_off[s+1]).  `down` = (state != "active").  ts and the thresholds share one unit (the
- * store keeps unix seconds; defaults 4 min drop, scan_drops.go:11).  One verdict per series. */
-typedef struct { int64_t ts; uint64_t total_link_downed; int32_t down; int32_t pad; } gpud_ib_snapshot;
-typedef struct {
-  int32_t drop, flap;          /* 1 = the reference returns a drop / flap event for this series                       */
-  int64_t drop_down_since;     /* ts of the oldest snapshot of the trailing down run ("... down since %s")             */
-  int64_t drop_index;          /* index (in the series) of the snapshot returned with the event: the latest one      */
-  int64_t flap_down_since;     /* ts of down1 of the revert that reached the threshold                                 */
-  int64_t flap_index;          /* index of that revert-to-active snapshot                                              */
-  int64_t n_reverts;           /* persistent-down -> active reverts in the series                                      */
-} gpud_ib_verdict;
-int32_t gpud_ib_scan(gpud_ctx* ctx, int32_t dev, const gpud_ib_snapshot* snaps, const int64_t* series_off, int64_t n_series,
-                     int64_t drop_threshold, int64_t flap_down_interval, int32_t flap_back_to_active_threshold, gpud_ib_verdict* out);
-/* "%s port %d down since %s" / "... (and flapped back to active)" with the RFC3339 UTC time (scan_drops.go:112, scan_flaps.go:67). */
-int32_t gpud_ib_reason(const char* device, uint32_t port, int64_t down_since_unix_s, int32_t flap, char* out, int32_t cap);
-
 /* Real ingest: a host poller that reads the NVML gauges of CUDA device `dev` - the getters behind the
  * reference's temperature / power / clock-speed / utilization / memory components (temperature/temperature.go:85,
  * power/power.go:46, clock-speed/clock_speed.go:41,59, utilization/utilization.go:44, memory/memory.go:83) - into pinned
@@ -295,6 +276,25 @@ int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud
 /* table NULL or "" = "gpud_metrics_v0_5" (metrics/store/sqlite.go:36) */
 int32_t gpud_store_metrics_table(gpud_store* st, const char* table);
 int32_t gpud_store_record_metrics(gpud_store* st, const char* table, const gpud_metric* ms, int64_t n);
+
+/* InfiniBand port drop / flap scans (SURVEY.md 8f.4): findDrops / findFlaps of
+ * components/accelerator/nvidia/infiniband/store/scan_drops.go:41-116 and scan_flaps.go:47-134 over many (device, port)
+ * snapshot series at once.  snaps = the series back to back, each in ascending time; series s is
+ * snaps[series_off[s] .. series_off[s+1]).  `down` = (state != "active").  ts and the thresholds share one unit (the
+ * store keeps unix seconds; defaults 4 min drop, scan_drops.go:11).  One verdict per series. */
+typedef struct { int64_t ts; uint64_t total_link_downed; int32_t down; int32_t pad; } gpud_ib_snapshot;
+typedef struct {
+  int32_t drop, flap;          /* 1 = the reference returns a drop / flap event for this series                       */
+  int64_t drop_down_since;     /* ts of the oldest snapshot of the trailing down run ("... down since %s")             */
+  int64_t drop_index;          /* index (in the series) of the snapshot returned with the event: the latest one      */
+  int64_t flap_down_since;     /* ts of down1 of the revert that reached the threshold                                 */
+  int64_t flap_index;          /* index of that revert-to-active snapshot                                              */
+  int64_t n_reverts;           /* persistent-down -> active reverts in the series                                      */
+} gpud_ib_verdict;
+int32_t gpud_ib_scan(gpud_ctx* ctx, int32_t dev, const gpud_ib_snapshot* snaps, const int64_t* series_off, int64_t n_series,
+                     int64_t drop_threshold, int64_t flap_down_interval, int32_t flap_back_to_active_threshold, gpud_ib_verdict* out);
+/* "%s port %d down since %s" / "... (and flapped back to active)" with the RFC3339 UTC time (scan_drops.go:112, scan_flaps.go:67). */
+int32_t gpud_ib_reason(const char* device, uint32_t port, int64_t down_since_unix_s, int32_t flap, char* out, int32_t cap);
 
 
 /* ------------------------------------------------------------------------------------------------
