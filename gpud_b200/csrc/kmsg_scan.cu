@@ -315,7 +315,12 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
             if (bad == 0u) fam = kFamX;
             else if (bad & 1u) fam = 0;                                    // not even "NVRM:"
             else if (!is_ws(__shfl_sync(kFull, cb, 1))) fam = 0;          // R3/R4 need \s+ right after the colon
-            else fam = nvrm_family_coop(b, a, lane);                      // whitespace run, then "GPU " / "The NVIDIA GPU "
+            else {
+              // most "NVRM: ..." lines are neither: after one whitespace byte anything but more whitespace, 'G' or 'T' settles it
+              const int c2 = __shfl_sync(kFull, cb, 2);
+              if (!is_ws(c2) && c2 != 'G' && c2 != 'T') fam = 0;
+              else fam = nvrm_family_coop(b, a, lane);                    // whitespace run, then "GPU " / "The NVIDIA GPU "
+            }
           } else if (EXT && fam >= (unsigned long long)kExtFam0) {
             if (!coop_lit(b, a, kExtLit[fam].text, kExtLit[fam].len, lane)) fam = 0;
           }
