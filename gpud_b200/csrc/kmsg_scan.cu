@@ -1451,9 +1451,9 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   k_scan_match<<<ctx->sm_count * 16, 128, 0, st>>>(b, mode, s->d_cands, s->d_side, side_cap, s->d_counters + 0, (unsigned long long)s->cand_cap,
                                                    s->d_chunk_local, s->d_tile_base, s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
   GPUD_CUDA(ctx, cudaGetLastError());
-  k_classify_ext_coop<<<ctx->sm_count * 2, 256, 0, st>>>(s->d_tables, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
+  k_classify_ext_coop<<<ctx->sm_count * 16, 256, 0, st>>>(s->d_tables, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
-  k_scan_unit_index<<<ctx->sm_count * 2, 256, 0, st>>>(b, mode, s->d_chunk_local, s->d_tile_base, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
+  k_scan_unit_index<<<ctx->sm_count * 8, 256, 0, st>>>(b, mode, s->d_chunk_local, s->d_tile_base, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[3], st);
   GPUD_CUDA(ctx, cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
