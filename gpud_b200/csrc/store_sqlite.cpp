@@ -224,6 +224,67 @@ extern "C" int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table,
   return GPUD_OK;
 }
 
+// ---- pkg/kmsg Syncer over the hits of RAW_KMSG scans (syncer.go:73-143) -----------------------------------------------
+// For every kmsg record on which the component's Match fires: Event{Time: boot + usec, Name, Message, Type: Warning};
+// dropped when the parsed form "name_message" was already seen in the same truncation bucket (deduper.go:63-125: default 60 s
+// buckets, 15 min TTL against the wall clock), or when the identical event is already in the table (Find), else inserted.
+// The watcher's raw-message dedup upstream (watcher.go) drops nothing this step would keep: identical raw lines of one bucket
+// parse to identical events.  Event-specific dedup windows (infiniband's kmsgEventDedupWindow) are not modelled.
+struct gpud_kmsg_syncer {
+  std::string component, table;
+  gpud_store* st = nullptr;
+  struct Entry { int count; int64_t expires; };
+  std::map<std::string, Entry> cache;
+};
+
+extern "C" int32_t gpud_kmsg_syncer_create(gpud_store* st, const char* component, gpud_kmsg_syncer** out) {
+  if (!st || !component || !out) return GPUD_E_INVALID;
+  char t[256];
+  const int32_t rc = gpud_store_event_table(st, component, t, sizeof t);
+  if (rc) return rc;
+  gpud_kmsg_syncer* sy = new gpud_kmsg_syncer();
+  sy->component = component; sy->table = t; sy->st = st;
+  *out = sy;
+  return GPUD_OK;
+}
+extern "C" void gpud_kmsg_syncer_destroy(gpud_kmsg_syncer* sy) { delete sy; }
+
+extern "C" int32_t gpud_kmsg_syncer_feed(gpud_kmsg_syncer* sy, const char* kmsg_component, const gpud_xid_hit* hits, int64_t n, const uint8_t* buf,
+                                         int64_t boot_unix, int64_t now_unix, int32_t* n_inserted) {
+  if (!sy || !kmsg_component || n < 0 || (n && !hits)) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  int32_t ins = 0;
+  if (S->exec(sy->st->db, "BEGIN;", nullptr, nullptr, nullptr) != kOk) return sfail(sy->st, "begin");
+  int64_t last_unit = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    const gpud_xid_hit& h = hits[i];
+    if (h.kind < GPUD_KIND_NCCL_SEGFAULT || h.kind >= GPUD_KIND_OS_PANIC_START) continue;       // the stateless line matchers only
+    if (strcmp(gpud_kmsg_component(h.kind), kmsg_component) != 0) continue;
+    if (h.unit_index == last_unit) continue;                   // Match returns the first pattern of the component that fires (hits are in kind order)
+    last_unit = h.unit_index;
+    char msg[4096];
+    if (gpud_kmsg_hit_message(&h, buf, msg, sizeof msg) < 0) continue;
+    const char* name = gpud_kmsg_event_name(h.kind);
+    const int64_t t = boot_unix + h.kmsg_usec / 1000000;
+    // parsed dedup (syncer.go:99-110, deduper.go:63-74,111-125)
+    const int64_t bucket = t - (t % 60);
+    const std::string key = std::to_string(bucket) + "-" + name + "_" + msg;
+    auto it = sy->cache.find(key);
+    int freq = 1;
+    if (it != sy->cache.end() && it->second.expires > now_unix) freq = it->second.count + 1;
+    sy->cache[key] = gpud_kmsg_syncer::Entry{freq, now_unix + 15 * 60};
+    if (freq > 1) continue;
+    bool did = false;
+    const int32_t rc = insert_event(sy->st, sy->table.c_str(), t, name, "Warning", msg, "", true, &did);   // Find, then Insert (syncer.go:112-135)
+    if (rc) { S->exec(sy->st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return rc; }
+    ins += did ? 1 : 0;
+  }
+  if (S->exec(sy->st->db, "COMMIT;", nullptr, nullptr, nullptr) != kOk) return sfail(sy->st, "commit");
+  if (n_inserted) *n_inserted = ins;
+  return GPUD_OK;
+}
+
 // metrics/store/sqlite.go:87-106
 extern "C" int32_t gpud_store_metrics_table(gpud_store* st, const char* table) {
   if (!st) return GPUD_E_INVALID;

@@ -273,6 +273,16 @@ int32_t gpud_store_insert_event(gpud_store* st, const char* table, int64_t unix_
 /* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
 int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);
+/* The pkg/kmsg Syncer step (syncer.go:73-143) for the hits of RAW_KMSG + GPUD_SCAN_EXT_MATCHERS scans: `component` names the
+ * event table (e.g. "disk" -> components_disk_events_v0_5_0), `kmsg_component` selects the line matchers
+ * (gpud_kmsg_component()); per record the component's first firing pattern becomes Event{boot + usec, name, message, "Warning"},
+ * goes through the parsed-message dedup (60 s buckets, 15 min TTL against `now_unix`) and the store's duplicate check, and is
+ * inserted.  One syncer per (component, kmsg stream); its dedup cache carries over between feeds. */
+typedef struct gpud_kmsg_syncer gpud_kmsg_syncer;
+int32_t gpud_kmsg_syncer_create(gpud_store* st, const char* component, gpud_kmsg_syncer** out);
+void gpud_kmsg_syncer_destroy(gpud_kmsg_syncer* sy);
+int32_t gpud_kmsg_syncer_feed(gpud_kmsg_syncer* sy, const char* kmsg_component, const gpud_xid_hit* hits, int64_t n, const uint8_t* buf,
+                              int64_t boot_unix, int64_t now_unix, int32_t* n_inserted);
 /* table NULL or "" = "gpud_metrics_v0_5" (metrics/store/sqlite.go:36) */
 int32_t gpud_store_metrics_table(gpud_store* st, const char* table);
 int32_t gpud_store_record_metrics(gpud_store* st, const char* table, const gpud_metric* ms, int64_t n);

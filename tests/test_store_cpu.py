@@ -91,3 +91,78 @@ def test_metrics_store(store, golden):
     with pytest.raises(g.GpudError):
         st.record_metrics([(1, "", "m", "", 0.0)])                # ErrEmptyComponentName
     db.close()
+
+
+def _raw_ext_buffer(n_records=600, seed=3):
+    """/dev/kmsg records whose messages are the line-matcher vectors, several per minute, some repeated inside one minute"""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(seed)
+    msgs = [l for l in synth.ext_lines() + synth.EXT_EDGE_LINES if l and "\n" not in l]
+    recs, usec = [], 5_000_000
+    for i in range(n_records):
+        usec += int(rng.choice([1000, 200_000, 7_000_000, 45_000_000]))
+        m = msgs[int(rng.integers(0, len(msgs)))] if rng.random() < 0.7 else "usb 1-%d: new high-speed USB device" % i
+        recs.append("%d,%d,%d,-;%s" % (int(rng.integers(0, 8)), 1000 + i, usec, m))
+        if rng.random() < 0.15:
+            recs.append(recs[-1].replace(",%d,%d," % (1000 + i, usec), ",%d,%d," % (9000 + i, usec + 500)))   # same message, same minute
+    return "\n".join(recs).encode()
+
+
+def _oracle_hits(buf):
+    from oracle import pyoracle as O
+    want, n_units = O.scan_raw_kmsg(buf, ext=True)
+    hits = []
+    for w in want:
+        if w["kind"] < 3:
+            continue
+        h = g.XidHit()
+        h.unit_index, h.kind, h.kmsg_priority, h.kmsg_seq, h.kmsg_usec = w["line"], w["kind"], w["kmsg"][0], w["kmsg"][1], w["kmsg"][2]
+        cap = w["capture"]
+        assert len(cap) <= 39
+        h.dev_len, h.device = len(cap), cap
+        hits.append(h)
+    return hits, want
+
+
+@pytest.mark.parametrize("component", ["disk", "infiniband", "cpu", "os", "nccl", "peermem"])
+def test_kmsg_syncer_rows_match_the_reference_flow(store, golden, component):
+    from oracle import pyoracle as O
+    st, path = store
+    G = golden("store_sql.json")
+    buf = _raw_ext_buffer()
+    hits, want = _oracle_hits(buf)
+    boot = 1_740_000_000
+    # restatement of Syncer.sync (pkg/kmsg/syncer.go:73-143) over the records, in order
+    recs = buf.split(b"\n")
+    seen, rows = set(), []
+    for rec in recs:
+        try:
+            _p, _s, usec, msg = O.parse_kmsg_line(0, rec.decode("latin-1"))
+        except ValueError:
+            continue
+        name, message = O.component_match(component, msg.encode("latin-1"))
+        if not name:
+            continue
+        t = boot + usec // 1_000_000
+        key = (t - t % 60, name + "_" + message)
+        if key in seen:
+            continue
+        seen.add(key)
+        row = (t, name, "Warning", message, None)
+        if row not in rows:
+            rows.append(row)
+    assert len(rows) >= 5
+    sy = st.syncer(component)
+    t = st.event_table(component)
+    half = len(hits) // 2
+    n1 = st.syncer_feed(sy, component, hits[:half], buf, boot, now_unix=boot + 100)
+    n2 = st.syncer_feed(sy, component, hits[half:], buf, boot, now_unix=boot + 200)
+    db = sqlite3.connect(path)
+    got = list(db.execute(G["event_get"]["sql"].format(table=t), (0,)))
+    assert n1 + n2 == len(got) == len(rows) and sorted(got) == sorted(rows)
+    assert [r[0] for r in got] == sorted((r[0] for r in got), reverse=True)
+    # a restarted syncer (cold dedup cache, e.g. after a gpud restart) re-reading the same kmsg inserts nothing: Find
+    sy2 = st.syncer(component)
+    assert st.syncer_feed(sy2, component, hits, buf, boot, now_unix=boot + 10_000) == 0
+    db.close()
