@@ -15,7 +15,7 @@ EVENT_NAMES = ["Unknown", "Info", "Warning", "Critical", "Fatal"]
 ACTION_WIRE = {1: "IGNORE_NO_ACTION_REQUIRED", 2: "REBOOT_SYSTEM", 3: "HARDWARE_INSPECTION", 4: "CHECK_USER_APP_AND_GPU"}
 SCAN_LINES, SCAN_RAW_KMSG = 0, 1
 SCAN_EXT_MATCHERS = 0x100
-DTYPES = {"float64": 0, "uint32": 1, "int32": 2, "float32": 3, "int64": 4, "uint64": 5}   # GPUD_DT_*
+DTYPES = {"float64": 0, "uint32": 1, "int32": 2, "float32": 3, "int64": 4, "uint64": 5, "uint16": 6, "int16": 7, "uint8": 8}   # GPUD_DT_*
 MAX_LINKS, MAX_GPUS = 18, 16
 
 

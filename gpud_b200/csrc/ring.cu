@@ -693,6 +693,8 @@ static size_t dtype_size(int32_t dt) {
   switch (dt) {
     case GPUD_DT_F64: case GPUD_DT_I64: case GPUD_DT_U64: return 8;
     case GPUD_DT_U32: case GPUD_DT_I32: case GPUD_DT_F32: return 4;
+    case GPUD_DT_U16: case GPUD_DT_I16: return 2;
+    case GPUD_DT_U8: return 1;
   }
   return 0;
 }
@@ -714,6 +716,9 @@ static int32_t launch_append(gpud_ring* r, const void* d_rows, int64_t n, int32_
     case GPUD_DT_F32: k_ring_append<float><<<grid, 256, 0, r->stream>>>((const float*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
     case GPUD_DT_I64: k_ring_append<long long><<<grid, 256, 0, r->stream>>>((const long long*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
     case GPUD_DT_U64: k_ring_append<unsigned long long><<<grid, 256, 0, r->stream>>>((const unsigned long long*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_U16: k_ring_append<uint16_t><<<grid, 256, 0, r->stream>>>((const uint16_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_I16: k_ring_append<int16_t><<<grid, 256, 0, r->stream>>>((const int16_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_U8: k_ring_append<uint8_t><<<grid, 256, 0, r->stream>>>((const uint8_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
     default: return gpud_fail(r->ctx, GPUD_E_INVALID, "unknown sample dtype %d", dt);
   }
   GPUD_CUDA(r->ctx, cudaGetLastError());

@@ -89,7 +89,8 @@ int32_t gpud_ring_push_device(gpud_ring* ring, const double* dev_rows, int64_t n
  * power/component.go, clock-speed/component.go) or uint64 (memory bytes, ECC counts); DCGM fields are int64 or double.
  * The widening the reference does on the host - metric.Set(float64(v)) - happens in the append kernel instead (exact;
  * round-to-nearest-even above 2^53 like Go), so a uint32 poll row crosses PCIe at half the bytes. */
-enum { GPUD_DT_F64 = 0, GPUD_DT_U32 = 1, GPUD_DT_I32 = 2, GPUD_DT_F32 = 3, GPUD_DT_I64 = 4, GPUD_DT_U64 = 5 };
+enum { GPUD_DT_F64 = 0, GPUD_DT_U32 = 1, GPUD_DT_I32 = 2, GPUD_DT_F32 = 3, GPUD_DT_I64 = 4, GPUD_DT_U64 = 5,
+       GPUD_DT_U16 = 6, GPUD_DT_I16 = 7, GPUD_DT_U8 = 8 };   /* narrow gauges: degrees C, percent, MHz */
 int32_t gpud_ring_push_raw(gpud_ring* ring, const void* host_rows, int64_t n_rows, int32_t dtype);
 
 /* Real ingest: a host poller that reads the NVML gauges of CUDA device `dev` - the getters behind the

@@ -369,7 +369,7 @@ def test_ring_tie_heavy_gauges(ctx, W, qn, qd):
     r.close()
 
 
-@pytest.mark.parametrize("dt", ["uint32", "int32", "float32", "int64", "uint64"])
+@pytest.mark.parametrize("dt", ["uint32", "int32", "float32", "int64", "uint64", "uint16", "int16", "uint8"])
 def test_ring_push_raw_types(ctx, dt):
     """raw NVML / DCGM sample types are widened on the device exactly like float64(v) on the host"""
     F, n, W, cap = 40, 5000, 250, 4096
@@ -382,6 +382,9 @@ def test_ring_push_raw_types(ctx, dt):
         raw = rng.integers(-(1 << 62), 1 << 62, (n, F), dtype=np.int64)
     elif dt == "int32":
         raw = rng.integers(-(1 << 31), 1 << 31, (n, F), dtype=np.int64).astype(np.int32)
+    elif dt in ("uint16", "int16", "uint8"):
+        info = np.iinfo(dt)
+        raw = rng.integers(info.min, int(info.max) + 1, (n, F), dtype=np.int64).astype(dt)
     else:
         raw = rng.integers(0, 1 << 32, (n, F), dtype=np.uint64).astype(np.uint32)
     x = raw.astype(np.float64)                       # numpy widens with round-to-nearest-even, like Go's float64(v)
