@@ -603,7 +603,9 @@ struct gpud_ring {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   double* h_stage[2] = {nullptr, nullptr};
   double* d_stage[2] = {nullptr, nullptr};
-  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};    // d_stage[i] is free again (its append has run)
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // the H2D into d_stage[i] has landed
+  cudaStream_t copy_stream = nullptr;
   int64_t stage_rows = 0;
   int sm_count = 148;
   double* d_rng[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // range-reduce scratch: per-window min,max,mean,ema,partials
@@ -641,11 +643,13 @@ extern "C" int32_t gpud_ring_create(gpud_ctx* ctx, int32_t dev, const gpud_ring_
   if (e == cudaSuccess) e = cudaMalloc(&r->d_nover, (size_t)r->F * r->nw_max * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&r->d_part, res_bytes);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking);
   r->stage_rows = std::max<int64_t>(1, (int64_t)(kStageBytes / (sizeof(double) * r->F)));
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaMallocHost(&r->h_stage[i], (size_t)r->stage_rows * r->F * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&r->d_stage[i], (size_t)r->stage_rows * r->F * sizeof(double));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_stage[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r->ev_copied[i], cudaEventDisableTiming);
   }
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&r->ev_k[i]);
   if (e != cudaSuccess) {
@@ -676,8 +680,10 @@ extern "C" int32_t gpud_ring_destroy(gpud_ring* r) {
     if (r->h_stage[i]) cudaFreeHost(r->h_stage[i]);
     cudaFree(r->d_stage[i]);
     if (r->ev_stage[i]) cudaEventDestroy(r->ev_stage[i]);
+    if (r->ev_copied[i]) cudaEventDestroy(r->ev_copied[i]);
   }
   for (auto& ev : r->ev_k) if (ev) cudaEventDestroy(ev);
+  if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
   if (r->own_stream) cudaStreamDestroy(r->own_stream);
   delete r;
   return GPUD_OK;
@@ -751,18 +757,24 @@ extern "C" int32_t gpud_ring_push_raw(gpud_ring* r, const void* host_rows_v, int
   else cudaGetLastError();
   // the staging pair is sized in bytes for stage_rows rows of doubles: narrower samples move more rows per piece
   const int64_t piece_rows = r->stage_rows * (int64_t)(sizeof(double) / esz);
+  // Copies run on their own stream so the H2D of piece k+1 overlaps the append of piece k (PCIe never waits for K1):
+  //   copy stream:    wait(free[buf]) -> H2D into d_stage[buf] -> record(copied[buf])
+  //   compute stream: wait(copied[buf]) -> append from d_stage[buf] -> record(free[buf])
   int64_t done = 0;
   int buf = 0;
   while (done < n) {
     const int64_t rows = std::min(piece_rows, n - done);
     const size_t bytes = (size_t)rows * r->F * esz;
-    GPUD_CUDA(r->ctx, cudaEventSynchronize(r->ev_stage[buf]));   // previous use of this staging pair has drained
     const char* src = host_rows + (size_t)done * r->F * esz;
     if (!pinned) {
-      gpud_parallel_memcpy(r->h_stage[buf], src, bytes);       // pageable caller memory: stage through pinned
+      GPUD_CUDA(r->ctx, cudaEventSynchronize(r->ev_copied[buf]));   // the previous H2D out of this pinned piece has finished
+      gpud_parallel_memcpy(r->h_stage[buf], src, bytes);           // pageable caller memory: stage through pinned
       src = (const char*)r->h_stage[buf];
     }
-    GPUD_CUDA(r->ctx, cudaMemcpyAsync(r->d_stage[buf], src, bytes, cudaMemcpyHostToDevice, r->stream));
+    GPUD_CUDA(r->ctx, cudaStreamWaitEvent(r->copy_stream, r->ev_stage[buf], 0));   // the append that last read d_stage[buf] is done
+    GPUD_CUDA(r->ctx, cudaMemcpyAsync(r->d_stage[buf], src, bytes, cudaMemcpyHostToDevice, r->copy_stream));
+    GPUD_CUDA(r->ctx, cudaEventRecord(r->ev_copied[buf], r->copy_stream));
+    GPUD_CUDA(r->ctx, cudaStreamWaitEvent(r->stream, r->ev_copied[buf], 0));
     int32_t rc = launch_append(r, r->d_stage[buf], rows, dt);
     if (rc) return rc;
     GPUD_CUDA(r->ctx, cudaEventRecord(r->ev_stage[buf], r->stream));
