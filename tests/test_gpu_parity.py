@@ -422,6 +422,12 @@ def test_ib_drop_flap_scans(ctx, drop_thr, flap_thr, flap_k):
         nd = len(G["drops"]["rows"])
         assert [v.drop for v in got[:nd]] == [r["expected"] for r in G["drops"]["rows"]]
         assert [v.flap for v in got[nd:nd + len(G["flaps"]["rows"])]] == [r["expected"] for r in G["flaps"]["rows"]]
+        for r in G["edge"]["rows"]:                 # the t.Run sub-tests with their own thresholds and index asserts
+            sr = [(base + int(x["t"]), x["state"] != "active", x["total_link_downed"]) for x in r["snapshots"]]
+            a = [int(x) for x in r["args"]]
+            v = ctx.ib_scan([sr], a[0] if r["kind"] == "drops" else 240, a[0] if r["kind"] == "flaps" else 25, a[1] if r["kind"] == "flaps" else 3)[0]
+            hit, idx = (v.drop, v.drop_index) if r["kind"] == "drops" else (v.flap, v.flap_index)
+            assert hit == r["expected"] and ("expected_index" not in r or idx == r["expected_index"]), r["name"]
 
 
 def test_poller_real_ingest(ctx):

@@ -270,6 +270,14 @@ def test_ib_drop_flap_scans(golden):               # infiniband/store/scan_drops
         got = IB.find_flaps(series(r), G["flaps"]["down_interval_threshold_s"], G["flaps"]["flap_back_to_active_threshold"])
         assert (1 if got else 0) == r["expected"], r["name"]
     assert sum(r["expected"] for r in G["drops"]["rows"]) >= 3 and sum(r["expected"] for r in G["flaps"]["rows"]) >= 3
+    for r in G["edge"]["rows"]:                    # the t.Run sub-tests: per-call thresholds, Len and index asserts
+        if r["kind"] == "drops":
+            got = IB.find_drops(series(r), int(r["args"][0]))
+        else:
+            got = IB.find_flaps(series(r), int(r["args"][0]), int(r["args"][1]))
+        assert (1 if got else 0) == r["expected"], r["name"]
+        if "expected_index" in r:
+            assert got["index"] == r["expected_index"], r["name"]
     import gpud_b200 as g                          # host-side reason formatting (no GPU needed)
     for t in (0, 1, 86399, 86400, 951782400, 1_700_000_000, 1709251199, 1709251200, 4102444800):
         assert g.ib_reason("mlx5_0", 1, t, False) == IB.drop_reason("mlx5_0", 1, t)

@@ -440,6 +440,40 @@ def main():
     rows, src = snapshot_cases(IBD + "scan_flaps_test.go", "TestFindFlaps")
     ib["flaps"] = {"src": src, "rows": rows, "down_interval_threshold_s": 25, "flap_back_to_active_threshold": 3,
                    "note": "downIntervalThreshold := 25 * time.Second, flapBackToActiveThreshold := 3 (scan_flaps_test.go:27-28)"}
+    def snapshot_subtests(path, func, kind):
+        """the t.Run sub-tests (and a bare body) of `func`: struct-literal snapshots, the call's thresholds, Len / index asserts"""
+        body, line = find_func(open(os.path.join(REF, path)).read(), func)
+        env = {m.group(1): m.group(2).strip() for m in re.finditer(r"(\w+)\s*:=\s*([^\n]+)", body)}
+        blocks = re.split(r't\.Run\("', body)
+        out = []
+        for blk in blocks:
+            name = blk.split('"', 1)[0] if blk is not blocks[0] else func
+            snaps = [{"t": dur_seconds(m.group(1)) if m.group(1) else 0.0, "state": m.group(2), "total_link_downed": int(m.group(3))}
+                     for m in re.finditer(r'\{ts:\s*baseTime(?:\.Add\(([^)]*)\))?,\s*state:\s*"(\w+)",\s*totalLinkDowned:\s*(\d+)\}', blk)]
+            call = re.search(r"\.find(?:Drops|Flaps)\(device,\s*port,\s*([^)]*)\)", blk)
+            ln = re.search(r"assert\.Len\(t,\s*result,\s*(\d+)", blk)
+            if not call or not ln or "nilSnapshots" in blk:
+                continue
+            args = [a.strip() for a in call.group(1).split(",")]
+            def val(a):
+                a = env.get(a, a)
+                return int(a) if re.fullmatch(r"\d+", a) else dur_seconds(a)
+            row = {"name": name, "snapshots": snaps, "expected": int(ln.group(1)), "args": [val(a) for a in args]}
+            ix = re.search(r"assert\.Equal\(t,\s*snapshots\[(\d+)\]\.ts,\s*(?:result\[0\]|flap|drop)\.ts\)", blk)
+            if ix:
+                row["expected_index"] = int(ix.group(1))
+            out.append(row)
+        return out, "%s:%d" % (path, line)
+
+    edge = []
+    for fn in ("TestFindDrops_EdgeCases", "TestFindDrops_ReasonMessage"):
+        rows, src = snapshot_subtests(IBD + "scan_drops_test.go", fn, "drops")
+        edge += [dict(r, kind="drops", src=src) for r in rows]
+    for fn in ("TestFindFlaps_EdgeCases", "TestFindFlaps_ReasonMessage", "TestFindFlaps_ComplexScenarios"):
+        rows, src = snapshot_subtests(IBD + "scan_flaps_test.go", fn, "flaps")
+        edge += [dict(r, kind="flaps", src=src) for r in rows]
+    ib["edge"] = {"src": IBD + "scan_drops_test.go:174,215 ; " + IBD + "scan_flaps_test.go:216,279,316", "rows": edge,
+                  "note": "args = the thresholds of the call: drops [threshold_s], flaps [down_interval_s, flap_back_to_active]"}
     dump("ib_scans.json", ib)
 
     # ---- SURVEY 8f.2: the SQL of the event store and the metrics store, as the Go sources format it ----
