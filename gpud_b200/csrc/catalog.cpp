@@ -334,6 +334,48 @@ extern "C" int32_t gpud_kmsg_hit_message(const gpud_xid_hit* h, const uint8_t* b
   return (int32_t)m.size();
 }
 
+// setNVLinkSuggestedActions (nvlink/evaluate_threshold.go:37-52) + peerNVLinkStatusesSuggestReboot (component.go:398-415): does an
+// unhealthy verdict come with RepairActionTypeRebootSystem?
+extern "C" int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v) {
+  if (!v || v->nvlink_health != 2) return 0;
+  const bool complete = v->p2p_expected_pairs != 0 && v->p2p_probed_pairs == v->p2p_expected_pairs;
+  const uint32_t other = v->p2p_observed_status_mask & ~0x3eu;       // anything but the five "not supported" status codes
+  return (v->inactive > 0 || (complete && v->p2p_ok_pairs == 0 && other != 0)) ? 1 : 0;
+}
+
+// FabricState.GetIssues (pkg/nvidia/nvml/device/fabric_state.go:115-177) for one GPU's record: the sorted issue strings,
+// joined with ", " (how fabric-manager/fabric_state.go:95-105 prints them); "" when healthy or when no fabric info was read.
+extern "C" int32_t gpud_fabric_issues(const gpud_fabric_raw* g, char* out, int32_t cap) {
+  if (!g || !out || cap <= 0) return -1;
+  std::vector<std::string> is;
+  if (g->fabric_valid) {
+    if (g->fabric_state != 3) {
+      static const char* kState[] = {"Not Supported", "Not Started", "In Progress", "Completed"};
+      is.push_back(std::string("state=") + (g->fabric_state < 4 ? kState[g->fabric_state] : ("Unknown(" + std::to_string(g->fabric_state) + ")").c_str()));
+    }
+    if (g->fabric_status != 0) {
+      const char* n = nullptr;
+      switch (g->fabric_status) {            // nvml.Return names (go-nvml v0.13.0-1)
+        case 1: n = "ERROR_UNINITIALIZED"; break; case 2: n = "ERROR_INVALID_ARGUMENT"; break; case 3: n = "ERROR_NOT_SUPPORTED"; break;
+        case 4: n = "ERROR_NO_PERMISSION"; break; case 6: n = "ERROR_NOT_FOUND"; break; case 9: n = "ERROR_DRIVER_NOT_LOADED"; break;
+        case 10: n = "ERROR_TIMEOUT"; break; case 15: n = "ERROR_GPU_IS_LOST"; break; case 999: n = "ERROR_UNKNOWN"; break;
+      }
+      is.push_back("status=" + (n ? std::string(n) : "ERROR_" + std::to_string(g->fabric_status)));
+    }
+    if (g->fabric_summary == 2) is.push_back("summary=Unhealthy");
+    else if (g->fabric_summary == 3) is.push_back("summary=Limited Capacity");
+    static const char* kMask[] = {"bandwidth degraded", "route recovery in progress", "route unhealthy", "access timeout recovery in progress"};
+    for (int f = 0; f < 4; ++f)
+      if (((g->fabric_health_mask >> (2 * f)) & 3u) == 1u) is.push_back(kMask[f]);
+    std::sort(is.begin(), is.end());
+  }
+  std::string j;
+  for (size_t i = 0; i < is.size(); ++i) { if (i) j += ", "; j += is[i]; }
+  if ((int32_t)j.size() + 1 > cap) return -1;
+  memcpy(out, j.c_str(), j.size() + 1);
+  return (int32_t)j.size();
+}
+
 extern "C" int32_t gpud_ib_reason(const char* device, uint32_t port, int64_t t, int32_t flap, char* out, int32_t cap) {
   if (!device || !out || cap <= 0) return -1;
   // civil-from-days (proleptic Gregorian), UTC: time.Time.UTC().Format(time.RFC3339)

@@ -367,6 +367,10 @@ enum { GPUD_NVLINK_NO_ISSUE = 0, GPUD_NVLINK_P2P_FAILURE = 1, GPUD_NVLINK_NO_ACT
 #define GPUD_FAB_ROUTE_UNHEALTHY 0x40u
 #define GPUD_FAB_ACCESS_TIMEOUT 0x80u
 
+/* FabricState.GetIssues (pkg/nvidia/nvml/device/fabric_state.go:115-177) of one GPU's record as text: the sorted issue
+ * strings joined with ", " ("" = healthy or no fabric info).  Returns the length, -1 if cap is too small. */
+int32_t gpud_fabric_issues(const gpud_fabric_raw* gpu, char* out, int32_t cap);
+
 typedef struct {
   int32_t n_gpus;
   int32_t nvlink_health;  /* 0 Healthy, 2 Unhealthy (api/v1/types.go:20-25)                                 */
@@ -381,6 +385,9 @@ typedef struct {
   uint8_t fabric_issue_bits[GPUD_MAX_GPUS];
   uint64_t total_replay, total_recovery, total_crc;
 } gpud_fabric_verdict;
+/* Does this (unhealthy) verdict carry RepairActionTypeRebootSystem?  setNVLinkSuggestedActions, nvlink/evaluate_threshold.go:37-52:
+ * a GPU with inactive links, or complete P2P coverage with no OK pair and a status outside the five "not supported" codes. */
+int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v);
 
 /* Single-rank pieces (one process per GPU; the collective itself is done by the host plumbing, e.g.
  * torch.distributed / ncclAllGather on `dev_send` -> `dev_all`): */

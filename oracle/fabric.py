@@ -30,6 +30,34 @@ def fabric_issue_bits(g: Dict) -> int:
     return b
 
 
+NVML_RETURN_NAMES = {0: "SUCCESS", 1: "ERROR_UNINITIALIZED", 2: "ERROR_INVALID_ARGUMENT", 3: "ERROR_NOT_SUPPORTED", 4: "ERROR_NO_PERMISSION",
+                     6: "ERROR_NOT_FOUND", 9: "ERROR_DRIVER_NOT_LOADED", 10: "ERROR_TIMEOUT", 15: "ERROR_GPU_IS_LOST", 999: "ERROR_UNKNOWN"}
+
+
+def get_issues(g: Dict) -> List[str]:
+    """FabricState.GetIssues (pkg/nvidia/nvml/device/fabric_state.go:115-146) + getHealthMaskIssues (:150-177): sorted strings"""
+    issues = []
+    st = g["fabric_state"]
+    if st != 3:
+        issues.append("state=" + {0: "Not Supported", 1: "Not Started", 2: "In Progress", 3: "Completed"}.get(st, "Unknown(%d)" % st))
+    if g["fabric_status"] != 0:
+        issues.append("status=" + NVML_RETURN_NAMES.get(g["fabric_status"], "ERROR_%d" % g["fabric_status"]))
+    if g["fabric_summary"] == 2:
+        issues.append("summary=Unhealthy")
+    elif g["fabric_summary"] == 3:
+        issues.append("summary=Limited Capacity")
+    issues += health_mask_issues(g["fabric_health_mask"])
+    return sorted(issues)
+
+
+def health_mask_issues(m: int) -> List[str]:
+    out = []
+    for shift, text in ((0, "bandwidth degraded"), (2, "route recovery in progress"), (4, "route unhealthy"), (6, "access timeout recovery in progress")):
+        if (m >> shift) & 3 == 1:
+            out.append(text)
+    return out
+
+
 def verdict(gpus: List[Dict], at_least: int) -> Dict:
     n = len(gpus)
     v = {"n_gpus": n, "active": 0, "inactive": 0, "unsupported": 0, "active_mask": 0, "inactive_mask": 0, "unsupported_mask": 0,
@@ -90,3 +118,14 @@ def verdict(gpus: List[Dict], at_least: int) -> Dict:
         health, reason = 2, 4
     v["nvlink_health"], v["nvlink_reason"] = health, reason
     return v
+
+
+def suggest_reboot(v: Dict) -> bool:
+    """setNVLinkSuggestedActions (nvlink/evaluate_threshold.go:37-52, only reached on the unhealthy paths) +
+    peerNVLinkStatusesSuggestReboot (component.go:398-415): RebootSystem when a GPU has inactive links, or when every pair
+    was probed, none is OK and some observed status is not one of the five "not supported" codes."""
+    if v["nvlink_health"] != 2:
+        return False
+    complete = v["p2p_expected_pairs"] != 0 and v["p2p_probed_pairs"] == v["p2p_expected_pairs"]
+    other = v["p2p_observed_status_mask"] & ~0b0111110
+    return v["inactive"] > 0 or (complete and v["p2p_ok_pairs"] == 0 and other != 0)

@@ -109,3 +109,96 @@ def test_single_gpu_is_left_alone():
     g = [gpu(0, 1, enabled=[0] * 18)]
     v = OF.verdict(g, 0)
     assert (v["nvlink_health"], v["p2p_expected_pairs"]) == (0, 0)
+
+
+def test_get_issues_tables_of_the_reference(golden):
+    """FabricState.GetIssues / getHealthMaskIssues: the reference's own tables (fabric_state_test.go:10,87) against the oracle, the
+    oracle's issue bits, and the library's host rendering"""
+    import ctypes as C
+    import gpud_b200 as g
+    G = golden("fabric_issues.json")
+    L = g.lib()
+    out = C.create_string_buffer(512)
+    for r in G["get_issues"]["rows"]:
+        d = {"fabric_valid": 1, "fabric_state": r["state"], "fabric_status": r["status"], "fabric_summary": r["summary"], "fabric_health_mask": r["health_mask"]}
+        assert OF.get_issues(d) == r["expected"], r["name"]
+        assert bool(OF.fabric_issue_bits(d)) == bool(r["expected"]), r["name"]
+        raw = g.FabricRaw()
+        raw.fabric_valid, raw.fabric_state, raw.fabric_status, raw.fabric_summary, raw.fabric_health_mask = 1, r["state"], r["status"], r["summary"], r["health_mask"]
+        n = L.gpud_fabric_issues(C.byref(raw), out, 512)
+        assert n >= 0 and out.value.decode() == ", ".join(r["expected"]), r["name"]
+    for r in G["health_mask_issues"]["rows"]:
+        assert OF.health_mask_issues(r["mask"]) == r["expected"], r["name"]
+        raw = g.FabricRaw()
+        raw.fabric_valid, raw.fabric_state, raw.fabric_summary, raw.fabric_health_mask = 1, 3, 1, r["mask"]
+        L.gpud_fabric_issues(C.byref(raw), out, 512)
+        assert out.value.decode() == ", ".join(sorted(r["expected"])), r["name"]
+
+
+def golden_threshold_case(r):
+    """one TestEvaluateThresholds_* vector (tests/golden/nvlink_thresholds.json) as the per-GPU records the library takes, plus the
+    (health, reason id, reboot) its assertions mean"""
+    uu = [g["uuid"] for g in r["nvlinks"]]
+    n = len(uu)
+    gs = []
+    for i, e in enumerate(r["nvlinks"]):
+        if e["uuid"] in r["active"]:
+            cls = "a"
+        elif e["uuid"] in r["inactive"]:
+            cls = "i"
+        elif e["uuid"] in r["unsupported"]:
+            cls = "u"
+        else:                                       # the test left the lists empty: classify like nvlink.Check does (component.go:271-289)
+            cls = "u" if not e["supported"] else ("a" if e["states"] and all(e["states"]) else "i")
+        nl = len(e["states"])
+        en = [1] * max(nl, 1) if cls == "a" else ([int(x) for x in e["states"]] if nl and not all(e["states"]) else [0] * nl)
+        if cls == "a":
+            nl = max(nl, 1)
+        d = gpu(i, max(n, 1), supported=0 if cls == "u" else 1, expected=1 if r["system_expected"] else 0, n_links=nl if cls != "u" else 0,
+                enabled=(en + [0] * 18)[:18], p2p=0xFF)
+        gs.append(d)
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    bad = next((c for c in r["p2p_observed"] if c != 0), 5)
+    for k, (i, j) in enumerate(pairs[: r["p2p_probed"]]):
+        st = 0 if k < r["p2p_ok"] else bad
+        gs[i]["p2p_status"][j] = st
+        gs[j]["p2p_status"][i] = st
+    assert r["p2p_expected"] in (0, len(pairs)), r["name"]
+    want_h = {"Healthy": 0, "Unhealthy": 2, "": 0}[r["want_health"] or r["preset_health"]]
+    txt = " ".join(r["want_reason_contains"]) + " " + r["want_reason_equal"]
+    if "no GPU pairs report NVLink P2P connectivity" in txt:
+        rid = 1
+    elif "no GPUs report active nvlink links" in txt:
+        rid = 2
+    elif "reasonNoNVLinkData" in txt:
+        rid = 6
+    elif "satisfied" in txt:
+        rid = 3
+    elif want_h == 2 and r["at_least"] > 0:
+        rid = 4
+    elif want_h == 2:
+        rid = 1 if r["p2p_probed"] else 2
+    else:
+        rid = 3 if (r["at_least"] > 0 and n) else 0
+    return gs, r["at_least"], want_h, rid, r["want_reboot"]
+
+
+def test_threshold_vectors_of_the_reference(golden):
+    """every TestEvaluateThresholds_* function of nvlink/evaluate_threshold_test.go, its checkResult turned into per-GPU records"""
+    rows = golden("nvlink_thresholds.json")["evaluate"]["rows"]
+    assert len(rows) == 17
+    for r in rows:
+        gs, at_least, want_h, rid, reboot = golden_threshold_case(r)
+        v = OF.verdict(gs, at_least)
+        assert (v["nvlink_health"], v["nvlink_reason"]) == (want_h, rid), (r["name"], v["nvlink_health"], v["nvlink_reason"], want_h, rid)
+        if reboot is not None:
+            assert OF.suggest_reboot(v) == reboot, r["name"]
+        import ctypes as C
+        import gpud_b200 as g
+        fv = g.FabricVerdict()
+        for k, val in v.items():
+            if k != "fabric_issue_bits":
+                setattr(fv, k, val)
+        assert bool(g.lib().gpud_fabric_suggest_reboot(C.byref(fv))) == OF.suggest_reboot(v), r["name"]
+        if len(r["active"]) + len(r["inactive"]) + len(r["unsupported"]) == len(r["nvlinks"]) > 0:      # the test listed every GPU
+            assert (v["active"], v["inactive"], v["unsupported"]) == (len(r["active"]), len(r["inactive"]), len(r["unsupported"])), r["name"]

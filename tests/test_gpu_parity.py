@@ -594,6 +594,23 @@ def test_fabric_pack_and_verdict(ctx):
         want = OF.verdict(gpus, at_least)
         for k, val in want.items():
             assert v[k] == val, (name, k, v[k], val)
+    # every TestEvaluateThresholds_* vector of the reference through the pack + verdict kernels
+    from test_fabric_host import golden_threshold_case
+    for r in synth.golden("nvlink_thresholds.json")["evaluate"]["rows"]:
+        gpus, at_least, want_h, rid, reboot = golden_threshold_case(r)
+        n = len(gpus)
+        table = torch.zeros(max(n, 1) * 128, dtype=torch.uint8, device="cuda")
+        for d in gpus:
+            ctx.fabric_pack(_raw(d), table.data_ptr() + 128 * d["gpu_index"])
+        torch.cuda.synchronize()
+        fv = ctx.fabric_verdict(table.data_ptr(), n, at_least)
+        v = fv.as_dict()
+        want = OF.verdict(gpus, at_least)
+        for k, val in want.items():
+            assert v[k] == val, (r["name"], k, v[k], val)
+        assert (v["nvlink_health"], v["nvlink_reason"]) == (want_h, rid), r["name"]
+        if reboot is not None:
+            assert bool(g.lib().gpud_fabric_suggest_reboot(C.byref(fv))) == reboot, r["name"]
 
 
 # ------------------------------------------------------------------------------------------------ host-side component mirror

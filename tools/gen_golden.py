@@ -500,6 +500,103 @@ def main():
     sql["constants"] = {"src": ES + ":18 ; " + MS + ":22,36", "rows": [], "event_schema_version": consts(ES)["schemaVersion"]["value"],
                         "metrics_schema_version": consts(MS)["schemaVersion"]["value"]}
     dump("store_sql.json", sql)
+
+    # ---- fabric GetIssues / getHealthMaskIssues tables (pkg/nvidia/nvml/device/fabric_state_test.go) ----
+    # the nvml.* constants are go-nvml's (v0.13.0-1, go.mod:6), i.e. nvml.h's published values
+    NV = {"GPU_FABRIC_STATE_NOT_SUPPORTED": 0, "GPU_FABRIC_STATE_NOT_STARTED": 1, "GPU_FABRIC_STATE_IN_PROGRESS": 2, "GPU_FABRIC_STATE_COMPLETED": 3,
+          "GPU_FABRIC_HEALTH_SUMMARY_NOT_SUPPORTED": 0, "GPU_FABRIC_HEALTH_SUMMARY_HEALTHY": 1, "GPU_FABRIC_HEALTH_SUMMARY_UNHEALTHY": 2,
+          "GPU_FABRIC_HEALTH_SUMMARY_LIMITED_CAPACITY": 3, "SUCCESS": 0, "ERROR_UNKNOWN": 999,
+          "GPU_FABRIC_HEALTH_MASK_SHIFT_DEGRADED_BW": 0, "GPU_FABRIC_HEALTH_MASK_SHIFT_ROUTE_RECOVERY": 2,
+          "GPU_FABRIC_HEALTH_MASK_SHIFT_ROUTE_UNHEALTHY": 4, "GPU_FABRIC_HEALTH_MASK_SHIFT_ACCESS_TIMEOUT_RECOVERY": 6}
+    for f in ("DEGRADED_BW", "ROUTE_RECOVERY", "ROUTE_UNHEALTHY", "ACCESS_TIMEOUT_RECOVERY"):
+        NV.update({"GPU_FABRIC_HEALTH_MASK_%s_NOT_SUPPORTED" % f: 0, "GPU_FABRIC_HEALTH_MASK_%s_TRUE" % f: 1, "GPU_FABRIC_HEALTH_MASK_%s_FALSE" % f: 2})
+
+    def nv_eval(expr):
+        e = re.sub(r"nvml\.(\w+)", lambda m: str(NV[m.group(1)]), expr)
+        e = re.sub(r"uint32\(([^()]*)\)", r"(\1)", e)
+        assert re.fullmatch(r"[\d\s()<|]+", e), expr
+        return int(eval(" ".join(e.split())))
+
+    FT = "pkg/nvidia/nvml/device/fabric_state_test.go"
+    src_txt = open(os.path.join(REF, FT)).read()
+    fab = {}
+    body, line = find_func(src_txt, "TestFabricState_GetIssues")
+    rows = []
+    for m in re.finditer(r'name:\s*"([^"]+)",\s*state:\s*FabricState\{(.*?)\n\t\t\t\},\s*expected:\s*\[\]string\{(.*?)\},\n\t\t\}', body, re.S):
+        fields = {k: nv_eval(v) for k, v in re.findall(r"(State|Status|HealthMask|HealthSummary):\s*((?:[^,\n]|\n\t\t\t\t\t)+),", m.group(2))}
+        rows.append({"name": m.group(1), "state": fields["State"], "status": fields["Status"], "health_mask": fields["HealthMask"],
+                     "summary": fields["HealthSummary"], "expected": re.findall(r'"([^"]*)"', m.group(3))})
+    fab["get_issues"] = {"src": "%s:%d" % (FT, line), "rows": rows}
+    body, line = find_func(src_txt, "TestGetHealthMaskIssues")
+    rows = []
+    for m in re.finditer(r'name:\s*"([^"]+)",\s*mask:\s*(.*?),\n\s*expected:\s*\[\]string\{(.*?)\},', body, re.S):
+        rows.append({"name": m.group(1), "mask": nv_eval(m.group(2)), "expected": re.findall(r'"([^"]*)"', m.group(3))})
+    fab["health_mask_issues"] = {"src": "%s:%d" % (FT, line), "rows": rows}
+    fab["constants"] = {"src": "go-nvml v0.13.0-1 (go.mod:6) = nvml.h", "rows": [], "nvml": NV}
+    dump("fabric_issues.json", fab)
+
+    # ---- nvlink threshold evaluation: every TestEvaluateThresholds_* function as one vector (nvlink/evaluate_threshold_test.go) ----
+    NT = N + "nvlink/evaluate_threshold_test.go"
+    ntxt = open(os.path.join(REF, NT)).read()
+    P2P_CONST = {"p2pStatusOK": 0, "p2pStatusChipsetNotSupported": 1, "p2pStatusGPUNotSupported": 2, "p2pStatusTopologyNotSupported": 3,
+                 "p2pStatusDisabledByRegkey": 4, "p2pStatusNotSupported": 5, "p2pStatusUnknown": 6}   # nvlink/p2p.go:12-18,33-49
+
+    def brace_block(text, start):
+        d, i = 0, start
+        while True:
+            if text[i] == "{":
+                d += 1
+            elif text[i] == "}":
+                d -= 1
+                if d == 0:
+                    return text[start:i + 1]
+            i += 1
+
+    rows = []
+    for fm in re.finditer(r"func (TestEvaluateThresholds_\w+)\(t \*testing\.T\) \{", ntxt):
+        name = fm.group(1)
+        body, line = find_func(ntxt, name)
+        r = {"name": name, "line": line}
+        m = re.search(r"AtLeastGPUsWithAllLinksFeatureEnabled:\s*(-?\d+)", body)
+        r["at_least"] = int(m.group(1)) if m else 0
+        gpus = []
+        m = re.search(r"NVLinks:\s*\[\]NVLink\{", body)
+        if m:
+            blk = brace_block(body, m.end() - 1)
+            i = 1
+            while True:
+                j = blk.find("{", i)
+                if j < 0:
+                    break
+                ent = brace_block(blk, j)
+                i = j + len(ent)
+                u = re.search(r'UUID:\s*"([^"]+)"', ent)
+                sup = re.search(r"Supported:\s*(true|false)", ent)
+                gpus.append({"uuid": u.group(1), "supported": bool(sup and sup.group(1) == "true"),
+                             "states": [x == "true" for x in re.findall(r"FeatureEnabled:\s*(true|false)", ent)]})
+        r["nvlinks"] = gpus
+        for key, field in (("active", "ActiveNVLinkUUIDs"), ("inactive", "InactiveNVLinkUUIDs"), ("unsupported", "UnsupportedNVLinkUUIDs"), ("p2p_ok_gpus", "PeerNVLinkOKGPUUUIDs")):
+            m = re.search(field + r":\s*\[\]string\{([^}]*)\}", body)
+            r[key] = re.findall(r'"([^"]+)"', m.group(1)) if m else []
+        for key, field in (("p2p_probed", "PeerNVLinkProbePairCount"), ("p2p_expected", "PeerNVLinkExpectedPairCount"), ("p2p_ok", "PeerNVLinkOKPairCount")):
+            m = re.search(field + r":\s*(\d+)", body)
+            r[key] = int(m.group(1)) if m else 0
+        m = re.search(r"PeerNVLinkObservedStatusCodes:\s*\[\]string\{([^}]*)\}", body)
+        r["p2p_observed"] = [P2P_CONST[c] for c in re.findall(r"\w+", m.group(1))] if m else []
+        r["system_expected"] = bool(re.search(r"SystemExpectedNVLink:\s*true", body))
+        m = re.search(r"\n\t\thealth:\s*apiv1\.HealthStateType(\w+)", body)
+        r["preset_health"] = m.group(1) if m else ""
+        m = re.search(r'\n\t\treason:\s*"([^"]*)"', body)
+        r["preset_reason"] = m.group(1) if m else ""
+        m = re.search(r"assert\.Equal\(t,\s*apiv1\.HealthStateType(\w+),\s*cr\.health\)", body)
+        r["want_health"] = m.group(1) if m else ""
+        r["want_reason_contains"] = re.findall(r'assert\.Contains\(t,\s*cr\.reason,\s*"([^"]*)"\)', body)
+        m = re.search(r'assert\.Equal\(t,\s*("[^"]*"|\w+),\s*cr\.reason\)', body)
+        r["want_reason_equal"] = m.group(1).strip('"') if m else ""
+        r["want_reboot"] = True if "RepairActionTypeRebootSystem" in body else (False if re.search(r"assert\.Nil\(t,\s*cr\.suggestedActions\)", body) else None)
+        rows.append(r)
+    dump("nvlink_thresholds.json", {"evaluate": {"src": NT + ":12-490", "rows": rows,
+                                                  "note": "one row per TestEvaluateThresholds_* function: the checkResult it builds and what it asserts"}})
     return 0
 
 
