@@ -365,6 +365,41 @@ int32_t XidComponent::SetHealthy(int64_t now_unix) {            // set_healthy.g
 
 }  // namespace gpud
 
+// getClockEventReasons (hw-slowdown/clock_events.go:168-190) over clockEventReasonsToInclude (:192-264): the descriptions of the
+// set bits of an nvmlDeviceGetCurrentClocksEventReasons bitmask, HW-slowdown ones and the others, each sorted; one per line.
+namespace {
+struct ClockReason { unsigned long long flag; int hw; const char* text; };
+const ClockReason kClockReasons[] = {
+    {0x1ull, 0, "GPU is idle and clocks are dropping to Idle state"},
+    {0x2ull, 0, "GPU clocks are limited by current setting of applications clocks"},
+    {0x4ull, 0, "Clocks have been optimized to not exceed currently set power limits ('SW Power Cap: Active' in nvidia-smi --query)"},
+    {0x8ull, 1, "HW Slowdown is engaged due to high temperature, power brake assertion, or high power draw ('HW Slowdown: Active' in nvidia-smi --query)"},
+    {0x10ull, 0, "GPU is part of a Sync boost group to maximize performance per watt"},
+    {0x20ull, 0, "SW Thermal Slowdown is active to keep GPU and memory temperatures within operating limits"},
+    {0x40ull, 1, "HW Thermal Slowdown (reducing the core clocks by a factor of 2 or more) is engaged (temperature being too high) ('HW Thermal Slowdown' in nvidia-smi --query)"},
+    {0x80ull, 1, "HW Power Brake Slowdown (reducing the core clocks by a factor of 2 or more) is engaged (External Power Brake Assertion being triggered) ('HW Power Brake Slowdown' in nvidia-smi --query)"},
+    {0x100ull, 0, "GPU clocks are limited by current setting of Display clocks"},
+};
+}  // namespace
+extern "C" int32_t gpud_clock_event_reasons(uint64_t bitmask, char* hw_out, int32_t hw_cap, char* other_out, int32_t other_cap, int32_t* flags3) {
+  std::vector<std::string> hw, other;
+  for (const ClockReason& r : kClockReasons)
+    if (bitmask & r.flag) (r.hw ? hw : other).push_back(r.text);
+  std::sort(hw.begin(), hw.end());
+  std::sort(other.begin(), other.end());
+  auto join = [](const std::vector<std::string>& v, char* out, int32_t cap) -> bool {
+    std::string j;
+    for (size_t i = 0; i < v.size(); ++i) { if (i) j += "\n"; j += v[i]; }
+    if (!out || (int32_t)j.size() + 1 > cap) return false;
+    memcpy(out, j.c_str(), j.size() + 1);
+    return true;
+  };
+  if (flags3) {      // ClockEvents.HWSlowdown / HWSlowdownThermal / HWSlowdownPowerBrake (clock_events.go:151-153)
+    flags3[0] = (bitmask & 0x8ull) != 0; flags3[1] = (bitmask & 0x40ull) != 0; flags3[2] = (bitmask & 0x80ull) != 0;
+  }
+  return (join(hw, hw_out, hw_cap) && join(other, other_out, other_cap)) ? (int32_t)(hw.size() * 100 + other.size()) : -1;
+}
+
 // ---- flat C entry points so the host mirror is testable through ctypes (not part of gpud_b200.h) ----
 extern "C" {
 

@@ -93,6 +93,11 @@ enum { GPUD_DT_F64 = 0, GPUD_DT_U32 = 1, GPUD_DT_I32 = 2, GPUD_DT_F32 = 3, GPUD_
        GPUD_DT_U16 = 6, GPUD_DT_I16 = 7, GPUD_DT_U8 = 8 };   /* narrow gauges: degrees C, percent, MHz */
 int32_t gpud_ring_push_raw(gpud_ring* ring, const void* host_rows, int64_t n_rows, int32_t dtype);
 
+/* getClockEventReasons (hw-slowdown/clock_events.go:151-153,168-264): what the set bits of an
+ * nvmlDeviceGetCurrentClocksEventReasons bitmask mean.  hw_out / other_out receive the sorted descriptions, one per line;
+ * flags3 = {HWSlowdown, HWSlowdownThermal, HWSlowdownPowerBrake}.  Returns 100 * n_hw + n_other, -1 if a buffer is too small. */
+int32_t gpud_clock_event_reasons(uint64_t bitmask, char* hw_out, int32_t hw_cap, char* other_out, int32_t other_cap, int32_t* flags3);
+
 /* Real ingest: a host poller that reads the NVML gauges of CUDA device `dev` - the getters behind the
  * reference's temperature / power / clock-speed / utilization / memory components (temperature/temperature.go:85,
  * power/power.go:46, clock-speed/clock_speed.go:41,59, utilization/utilization.go:44, memory/memory.go:83) - into pinned

@@ -746,6 +746,27 @@ def evolve_healthy_state(events, reboot_threshold: int = 2):
 # --------------------------------------------------------------------------------------------
 # threshold rules
 # --------------------------------------------------------------------------------------------
+# clockEventReasonsToInclude (hw-slowdown/clock_events.go:192-264): (flag, isHWSlowdown, description)
+CLOCK_EVENT_REASONS = [
+    (0x1, False, 'GPU is idle and clocks are dropping to Idle state'),
+    (0x2, False, 'GPU clocks are limited by current setting of applications clocks'),
+    (0x4, False, "Clocks have been optimized to not exceed currently set power limits ('SW Power Cap: Active' in nvidia-smi --query)"),
+    (0x8, True, "HW Slowdown is engaged due to high temperature, power brake assertion, or high power draw ('HW Slowdown: Active' in nvidia-smi --query)"),
+    (0x10, False, 'GPU is part of a Sync boost group to maximize performance per watt'),
+    (0x20, False, 'SW Thermal Slowdown is active to keep GPU and memory temperatures within operating limits'),
+    (0x40, True, "HW Thermal Slowdown (reducing the core clocks by a factor of 2 or more) is engaged (temperature being too high) ('HW Thermal Slowdown' in nvidia-smi --query)"),
+    (0x80, True, "HW Power Brake Slowdown (reducing the core clocks by a factor of 2 or more) is engaged (External Power Brake Assertion being triggered) ('HW Power Brake Slowdown' in nvidia-smi --query)"),
+    (0x100, False, 'GPU clocks are limited by current setting of Display clocks'),
+]
+
+
+def clock_event_reasons(bitmask: int):
+    """getClockEventReasons (hw-slowdown/clock_events.go:168-190): (sorted HW-slowdown descriptions, sorted other descriptions)"""
+    hw = sorted(d for f, is_hw, d in CLOCK_EVENT_REASONS if bitmask & f and is_hw)
+    other = sorted(d for f, is_hw, d in CLOCK_EVENT_REASONS if bitmask & f and not is_hw)
+    return hw, other
+
+
 def hw_slowdown_state(event_unix_s: List[int], now_unix: int, window_seconds: int, threshold_freq_per_min: float):
     """hw-slowdown/component.go:352-407: distinct event-minutes since (now - window) / window minutes >= threshold -> Unhealthy."""
     if window_seconds == 0:

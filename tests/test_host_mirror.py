@@ -182,3 +182,17 @@ def test_kmsg_stateful_long_stream_in_chunks(seed, chunk):
         got += [(u + a, c, e, m) for u, c, e, m in st.feed(hits, buf, len(part))]
     st.close()
     assert got == want
+
+
+def test_clock_event_reasons(golden):              # hw-slowdown/clock_events_test.go:21 ; clock_events.go:168-264
+    G = golden("clock_events.json")
+    tab = G["table"]["entries"]
+    assert [(f, h, d) for f, h, d in O.CLOCK_EVENT_REASONS] == [(e["flag"], e["hw_slowdown"], e["description"]) for e in tab]
+    L = g.lib()
+    hw, other, fl = C.create_string_buffer(4096), C.create_string_buffer(4096), (C.c_int32 * 3)()
+    for r in G["reasons"]["rows"]:
+        assert O.clock_event_reasons(r["reasons"]) == (r["want_hw"], r["want_other"]), r["name"]
+        rc = L.gpud_clock_event_reasons(C.c_uint64(r["reasons"]), hw, 4096, other, 4096, fl)
+        assert rc == 100 * len(r["want_hw"]) + len(r["want_other"]), r["name"]
+        assert [x for x in hw.value.decode().split("\n") if x] == r["want_hw"] and [x for x in other.value.decode().split("\n") if x] == r["want_other"]
+        assert list(fl) == [int(bool(r["reasons"] & 0x8)), int(bool(r["reasons"] & 0x40)), int(bool(r["reasons"] & 0x80))]

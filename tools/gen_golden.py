@@ -595,6 +595,25 @@ def main():
         r["want_reason_equal"] = m.group(1).strip('"') if m else ""
         r["want_reboot"] = True if "RepairActionTypeRebootSystem" in body else (False if re.search(r"assert\.Nil\(t,\s*cr\.suggestedActions\)", body) else None)
         rows.append(r)
+    # ---- hw-slowdown: clock-event reason bitmask -> descriptions (hw-slowdown/clock_events.go:168-264, clock_events_test.go:21) ----
+    HS = N + "hw-slowdown/"
+    ctxt = open(os.path.join(REF, HS + "clock_events.go")).read()
+    flags = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"(reason\w+)\s+uint64\s*=\s*(0x[0-9a-fA-F]+)", ctxt)}
+    ce_table = []
+    for m in re.finditer(r"(reason\w+):\s*\{\s*description:\s*\"((?:[^\"\\]|\\.)*)\",\s*isHWSlowdown:\s*(true|false),", ctxt):
+        ce_table.append({"flag": flags[m.group(1)], "name": m.group(1), "description": m.group(2), "hw_slowdown": m.group(3) == "true"})
+    body, line = find_func(open(os.path.join(REF, HS + "clock_events_test.go")).read(), "TestGetClockEventReasons")
+    crow = []
+    for m in re.finditer(r'name:\s*"([^"]+)",\s*reasons:\s*([^,]+),\s*wantHWSlowdown:\s*\[\]string\{(.*?)\},\s*wantOtherReasons:\s*\[\]string\{(.*?)\},\n\t\t\}', body, re.S):
+        ex = m.group(2).strip()
+        val = 0
+        for tok in ex.split("|"):
+            tok = tok.strip()
+            val |= int(tok, 16) if tok.startswith("0x") else flags[tok]
+        crow.append({"name": m.group(1), "reasons": val, "want_hw": re.findall(r'"((?:[^"\\]|\\.)*)"', m.group(3)), "want_other": re.findall(r'"((?:[^"\\]|\\.)*)"', m.group(4))})
+    dump("clock_events.json", {"reasons": {"src": HS + "clock_events_test.go:%d" % line, "rows": crow},
+                               "table": {"src": HS + "clock_events.go:192-264", "rows": [], "entries": ce_table}})
+
     dump("nvlink_thresholds.json", {"evaluate": {"src": NT + ":12-490", "rows": rows,
                                                   "note": "one row per TestEvaluateThresholds_* function: the checkResult it builds and what it asserts"}})
     return 0
