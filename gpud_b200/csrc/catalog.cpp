@@ -334,6 +334,20 @@ extern "C" int32_t gpud_kmsg_hit_message(const gpud_xid_hit* h, const uint8_t* b
   return (int32_t)m.size();
 }
 
+// Reason of the sxid component's state (sxid/health_state.go:93-106): "SXID %d(%s) detected on %s" with the catalog name when the
+// code is known, "SXID %d detected on %s" otherwise; sxid < 0 = no error -> "SXIDComponent is healthy".
+extern "C" int32_t gpud_sxid_reason(int64_t sxid, const char* device, char* out, int32_t cap) {
+  if (!out || cap <= 0) return -1;
+  int n;
+  if (sxid < 0) n = snprintf(out, (size_t)cap, "SXIDComponent is healthy");
+  else {
+    const char* name = (sxid <= 0x7fffffff) ? gpud_sxid_name((int32_t)sxid) : "";
+    if (name && *name) n = snprintf(out, (size_t)cap, "SXID %lld(%s) detected on %s", (long long)sxid, name, device ? device : "");
+    else n = snprintf(out, (size_t)cap, "SXID %lld detected on %s", (long long)sxid, device ? device : "");
+  }
+  return n < cap ? n : -1;
+}
+
 // setNVLinkSuggestedActions (nvlink/evaluate_threshold.go:37-52) + peerNVLinkStatusesSuggestReboot (component.go:398-415): does an
 // unhealthy verdict come with RepairActionTypeRebootSystem?
 extern "C" int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v) {

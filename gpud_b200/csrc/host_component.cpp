@@ -140,12 +140,12 @@ int EventBucket::purge(int64_t before_unix) {
 }
 
 // ---- health evolution ----
-EvolveResult evolve_healthy_state(const std::vector<XidEventView>& ev, int reboot_threshold) {   // health_state.go:57-128
+EvolveResult evolve_healthy_state(const std::vector<XidEventView>& ev, int reboot_threshold, const char* event_name) {   // xid/health_state.go:57-128 ; sxid/health_state.go:38-111 (name "error_sxid", threshold 2)
   EvolveResult r;
   int last_health = 0;
   std::map<uint64_t, int> reboot_map;
   for (auto it = ev.rbegin(); it != ev.rend(); ++it) {          // oldest -> newest
-    if (it->name == "error_xid") {
+    if (it->name == event_name) {
       int cur = 0;
       if (it->type == "Critical") cur = 1;
       else if (it->type == "Fatal") cur = 2;
@@ -338,7 +338,7 @@ void XidComponent::update_state() {                // component.go:581-611
     }
     views.push_back(v);
   }
-  const EvolveResult r = evolve_healthy_state(views, reboot_threshold_);
+  const EvolveResult r = evolve_healthy_state(views, reboot_threshold_, "error_xid");
   cur_.health = r.health;
   cur_.has_actions = r.has_actions;
   cur_.actions.repair_actions = r.actions;
@@ -421,18 +421,25 @@ void gpudh_deduper_free(void* d) { delete static_cast<gpud::Deduper*>(d); }
 
 // events: n records of {kind 0 xid / 1 reboot / 2 SetHealthy(ignored here), event_type, xid, n_actions(-1 nil), actions[4]} newest first
 typedef struct { int32_t kind, event_type; uint64_t xid; int32_t n_actions; int32_t actions[4]; } gpudh_event;
+static int32_t evolve_flat(const gpudh_event* ev, int32_t n, int32_t reboot_threshold, const char* err_name, int32_t* health, int32_t* action, uint64_t* xid);
 int32_t gpudh_evolve(const gpudh_event* ev, int32_t n, int32_t reboot_threshold, int32_t* health, int32_t* action, uint64_t* xid) {
+  return evolve_flat(ev, n, reboot_threshold, "error_xid", health, action, xid);
+}
+int32_t gpudh_evolve_sxid(const gpudh_event* ev, int32_t n, int32_t* health, int32_t* action, uint64_t* sxid) {
+  return evolve_flat(ev, n, 2 /* sxid/health_state.go:36 */, "error_sxid", health, action, sxid);
+}
+static int32_t evolve_flat(const gpudh_event* ev, int32_t n, int32_t reboot_threshold, const char* err_name, int32_t* health, int32_t* action, uint64_t* xid) {
   std::vector<gpud::XidEventView> v;
   for (int i = 0; i < n; ++i) {
     gpud::XidEventView e;
-    e.name = ev[i].kind == 0 ? "error_xid" : (ev[i].kind == 1 ? "reboot" : "SetHealthy");
+    e.name = ev[i].kind == 0 ? err_name : (ev[i].kind == 1 ? "reboot" : "SetHealthy");
     e.type = gpud::event_type_string(ev[i].event_type);
     e.xid = ev[i].xid;
     e.has_actions = ev[i].n_actions >= 0;
     for (int k = 0; k < ev[i].n_actions && k < 4; ++k) e.actions.push_back(ev[i].actions[k]);
     v.push_back(e);
   }
-  const gpud::EvolveResult r = gpud::evolve_healthy_state(v, reboot_threshold);
+  const gpud::EvolveResult r = gpud::evolve_healthy_state(v, reboot_threshold, err_name);
   *health = (int32_t)r.health;
   *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
   *xid = r.has_xid ? r.xid : 0;

@@ -237,6 +237,8 @@ const char* gpud_xid_description(int32_t code, int32_t detail_variant);
 const char* gpud_xid_mnemonic(int32_t code);
 const char* gpud_sxid_name(int32_t code);
 const char* gpud_nvlink_rule_hint(int32_t rule_index);
+/* Reason string of the sxid component's health state (sxid/health_state.go:93-106); sxid < 0 = healthy. Returns the length. */
+int32_t gpud_sxid_reason(int64_t sxid, const char* device, char* out, int32_t cap);
 /* kmsg.MatchFunc results (eventName, message) of the extra matchers, by hit kind; "" for xid / sxid kinds. */
 const char* gpud_kmsg_event_name(int32_t kind);
 const char* gpud_kmsg_event_message(int32_t kind);

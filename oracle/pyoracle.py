@@ -714,13 +714,21 @@ def trim_events_after_set_healthy(events):                            # componen
     return events
 
 
-def evolve_healthy_state(events, reboot_threshold: int = 2):
+def sxid_reason(sxid, device: str, name: str = "") -> str:
+    """the Reason string of sxid's evolveHealthyState (sxid/health_state.go:93-106); name = GetDetail(sxid).Name or "" """
+    if sxid is None:
+        return "SXIDComponent is healthy"
+    return ("SXID %d(%s) detected on %s" % (sxid, name, device)) if name else ("SXID %d detected on %s" % (sxid, device))
+
+
+def evolve_healthy_state(events, reboot_threshold: int = 2, event_name: str = "error_xid"):
+    """xid/health_state.go:57-128 ; the sxid twin (sxid/health_state.go:38-111) differs in the event name and the fixed threshold 2"""
     last_action = None
     last_xid = None
     last_health = 0
     reboot_map: Dict[int, int] = {}
     for e in reversed(events):
-        if e["name"] == "error_xid":
+        if e["name"] == event_name:
             cur = {"Critical": 1, "Fatal": 2}.get(e.get("type", ""), 0)
             if cur < last_health:
                 continue

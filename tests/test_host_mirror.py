@@ -196,3 +196,48 @@ def test_clock_event_reasons(golden):              # hw-slowdown/clock_events_te
         assert rc == 100 * len(r["want_hw"]) + len(r["want_other"]), r["name"]
         assert [x for x in hw.value.decode().split("\n") if x] == r["want_hw"] and [x for x in other.value.decode().split("\n") if x] == r["want_other"]
         assert list(fl) == [int(bool(r["reasons"] & 0x8)), int(bool(r["reasons"] & 0x40)), int(bool(r["reasons"] & 0x80))]
+
+
+ACT_BY_GO = {"IgnoreNoActionRequired": 1, "RebootSystem": 2, "HardwareInspection": 3, "CheckUserAppAndGPU": 4}   # apiv1.RepairActionType* identifiers
+
+
+def test_sxid_evolve_and_reason(golden):           # sxid/health_state_test.go:38-134 ; sxid/health_state.go:38-111
+    L = g.lib()
+    out = C.create_string_buffer(256)
+    for r in golden("sxid_health.json")["scenarios"]["rows"]:
+        ev = [{"k": "xid", "xid": e["code"], "type": e["type"], "actions": e["actions"]} if e["k"] == "err" else {"k": "reboot"} for e in r["events"]]
+        arr = (HEvent * max(1, len(ev)))()
+        for i, e in enumerate(ev):
+            if e["k"] == "xid":
+                arr[i].kind, arr[i].event_type, arr[i].xid, arr[i].n_actions = 0, EV[e["type"]], e["xid"], len(e["actions"])
+                for k, a in enumerate(e["actions"]):
+                    arr[i].actions[k] = ACT_BY_GO[a]
+            else:
+                arr[i].kind = 1
+        h, a, x = C.c_int32(), C.c_int32(), C.c_uint64()
+        L.gpudh_evolve_sxid(arr, len(ev), C.byref(h), C.byref(a), C.byref(x))
+        oev = [{"name": "error_sxid", "type": e["type"], "xid": e["xid"], "actions": [ACT_BY_GO[q] for q in e["actions"]]} if e["k"] == "xid" else {"name": "reboot"} for e in ev]
+        o = O.evolve_healthy_state(oev, 2, "error_sxid")
+        assert HEALTH[h.value] == o["health"] and a.value == (o["actions"][0] if o["actions"] else 0), r["name"]
+        if "health" in r:
+            assert HEALTH[h.value] == r["health"], r["name"]
+        if "action" in r:
+            assert a.value == (ACT_BY_GO[r["action"]] if r["action"] else 0), r["name"]
+        if "reason" in r:
+            sx = o["xid"]
+            assert O.sxid_reason(sx, "PCI:0000:9b:00") == r["reason"], r["name"]
+            n = L.gpud_sxid_reason(C.c_int64(-1 if sx is None else sx), b"PCI:0000:9b:00", out, 256)
+            assert n > 0 and out.value.decode() == r["reason"], r["name"]
+
+
+def test_xid_evolve_extracted_scenarios(golden):   # xid/health_state_test.go:78-246, extracted by script
+    for r in golden("xid_health_extracted.json")["scenarios"]["rows"]:
+        if not r["events"] and "health" not in r:
+            continue
+        ev = [{"k": "xid", "xid": e["code"], "type": e["type"], "actions": [a for a in e["actions"]]} if e["k"] == "err" else {"k": "reboot"} for e in r["events"]]
+        oev = [{"name": "error_xid", "type": e["type"], "xid": e["xid"], "actions": [ACT_BY_GO[q] for q in e["actions"]]} if e["k"] == "xid" else {"name": "reboot"} for e in ev]
+        o = O.evolve_healthy_state(oev, 2)
+        if "health" in r:
+            assert o["health"] == r["health"], r["name"]
+        if r.get("action"):
+            assert o["actions"] and o["actions"][0] == ACT_BY_GO[r["action"]], r["name"]

@@ -552,7 +552,7 @@ def main():
                     return text[start:i + 1]
             i += 1
 
-    rows = []
+    nv_rows = []
     for fm in re.finditer(r"func (TestEvaluateThresholds_\w+)\(t \*testing\.T\) \{", ntxt):
         name = fm.group(1)
         body, line = find_func(ntxt, name)
@@ -594,7 +594,40 @@ def main():
         m = re.search(r'assert\.Equal\(t,\s*("[^"]*"|\w+),\s*cr\.reason\)', body)
         r["want_reason_equal"] = m.group(1).strip('"') if m else ""
         r["want_reboot"] = True if "RepairActionTypeRebootSystem" in body else (False if re.search(r"assert\.Nil\(t,\s*cr\.suggestedActions\)", body) else None)
-        rows.append(r)
+        nv_rows.append(r)
+    # ---- xid / sxid evolveHealthyState scenarios (health_state_test.go: TestStateUpdateBasedOnEvents), events newest first ----
+    def health_scenarios(path, ctor):
+        body, line = find_func(open(os.path.join(REF, path)).read(), "TestStateUpdateBasedOnEvents")
+        out = []
+        for blk in re.split(r'\n\tt\.Run\("', body)[1:]:
+            name = blk.split('"', 1)[0]
+            if "trimEventsAfterSetHealthy" in blk or "invalid json" in blk or "ExtraInfo:" in blk:
+                continue                                   # scenarios about merge/trim plumbing or undecodable payloads
+            m = re.search(r"eventstore\.Events\{(.*?)\n\t\t\}", blk, re.S)
+            evs = []
+            if m:
+                for em in re.finditer(ctor + r"\([^,]+,\s*(\d+),\s*apiv1\.EventType(\w+),\s*apiv1\.RepairActionType(\w+)\)|\{Name:\s*\"reboot\"\}", m.group(1)):
+                    evs.append({"k": "reboot"} if em.group(1) is None else {"k": "err", "code": int(em.group(1)), "type": em.group(2), "actions": [em.group(3)]})
+            r = {"name": name, "events": evs}
+            hm = re.search(r"assert\.Equal\(t,\s*apiv1\.HealthStateType(\w+),\s*state\.Health\)", blk)
+            if hm:
+                r["health"] = hm.group(1)
+            rm = re.search(r'assert\.Equal\(t,\s*"([^"]*)",\s*state\.Reason\)', blk)
+            if rm:
+                r["reason"] = rm.group(1)
+            am = re.search(r"assert\.Equal\(t,\s*apiv1\.RepairActionType(\w+),\s*state\.SuggestedActions\.RepairActions\[0\]\)", blk)
+            if am:
+                r["action"] = am.group(1)
+            if re.search(r"assert\.Nil\(t,\s*state\.SuggestedActions\)", blk):
+                r["action"] = None
+            out.append(r)
+        return out, "%s:%d" % (path, line)
+
+    rows, src = health_scenarios(N + "sxid/health_state_test.go", "createSXidEvent")
+    dump("sxid_health.json", {"scenarios": {"src": src, "rows": rows, "note": "rebootThreshold = 2 (sxid/health_state.go:36)"}})
+    rows, src = health_scenarios(N + "xid/health_state_test.go", "createXidEvent")
+    dump("xid_health_extracted.json", {"scenarios": {"src": src, "rows": rows, "note": "DefaultRebootThreshold = 2; script-extracted twin of xid_health.json"}})
+
     # ---- hw-slowdown: clock-event reason bitmask -> descriptions (hw-slowdown/clock_events.go:168-264, clock_events_test.go:21) ----
     HS = N + "hw-slowdown/"
     ctxt = open(os.path.join(REF, HS + "clock_events.go")).read()
@@ -614,7 +647,7 @@ def main():
     dump("clock_events.json", {"reasons": {"src": HS + "clock_events_test.go:%d" % line, "rows": crow},
                                "table": {"src": HS + "clock_events.go:192-264", "rows": [], "entries": ce_table}})
 
-    dump("nvlink_thresholds.json", {"evaluate": {"src": NT + ":12-490", "rows": rows,
+    dump("nvlink_thresholds.json", {"evaluate": {"src": NT + ":12-490", "rows": nv_rows,
                                                   "note": "one row per TestEvaluateThresholds_* function: the checkResult it builds and what it asserts"}})
     return 0
 
