@@ -131,10 +131,8 @@ extern "C" int32_t gpud_store_last_error(gpud_store* st, char* out, int32_t cap)
 extern "C" int32_t gpud_store_event_table(gpud_store* st, const char* component, char* table_out, int32_t cap) {
   if (!st || !component || !table_out || cap <= 0) return GPUD_E_INVALID;
   Sq* S = sq();
-  std::string c = component;
-  for (auto& ch : c) if (ch == ' ' || ch == '-') ch = '_';
-  for (size_t p; (p = c.find("__")) != std::string::npos;) c.replace(p, 2, "_");     // strings.ReplaceAll(c, "__", "_") is one left-to-right pass
-  // ReplaceAll does not rescan its own output; redo it faithfully
+  std::string c;
+  // strings.ReplaceAll is one non-overlapping left-to-right pass each: ' ' -> '_', '-' -> '_', "__" -> "_", then ToLower
   {
     std::string src = component, a;
     for (char ch : src) a.push_back((ch == ' ' || ch == '-') ? '_' : ch);

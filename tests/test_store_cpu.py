@@ -33,6 +33,8 @@ def test_event_table_is_the_references(store, golden):
     st, path = store
     G = golden("store_sql.json")
     ver = G["constants"]["event_schema_version"]
+    for r in G["table_names"]["rows"]:                  # Test_defaultTableName (pkg/eventstore/database_test.go:19)
+        assert st.event_table(r["input"]) == r["expected"], r["name"]
     for comp in ("accelerator-nvidia-error-xid", "accelerator-nvidia-error-sxid", "os", "Some Comp--Name", "a__b___c", "x - y"):
         t = st.event_table(comp)
         assert t == _go_table_name(comp, ver)

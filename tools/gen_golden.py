@@ -499,6 +499,10 @@ def main():
         sql[key] = {"src": src, "rows": [], "sql": text}
     sql["constants"] = {"src": ES + ":18 ; " + MS + ":22,36", "rows": [], "event_schema_version": consts(ES)["schemaVersion"]["value"],
                         "metrics_schema_version": consts(MS)["schemaVersion"]["value"]}
+    body, line = find_func(open(os.path.join(REF, "pkg/eventstore/database_test.go")).read(), "Test_defaultTableName")
+    tn = [{"name": m.group(1), "input": m.group(2), "expected": m.group(3) % consts(ES)["schemaVersion"]["value"]}
+          for m in re.finditer(r'name:\s*"([^"]*)",\s*input:\s*"([^"]*)",\s*expected:\s*fmt\.Sprintf\("([^"]*)",\s*schemaVersion\)', body)]
+    sql["table_names"] = {"src": "pkg/eventstore/database_test.go:%d" % line, "rows": tn}
     dump("store_sql.json", sql)
 
     # ---- fabric GetIssues / getHealthMaskIssues tables (pkg/nvidia/nvml/device/fabric_state_test.go) ----
