@@ -216,11 +216,14 @@ SlowdownVerdict evaluate_hw_slowdown(const std::vector<int64_t>& ev, int64_t now
   return v;
 }
 
-int evaluate_temperature(uint32_t cur, uint32_t gpu_max, uint32_t hbm, uint32_t mem_max, int32_t margin, int32_t margin_thr) {   // temperature/component.go:206-248
+// The per-GPU rules of temperature Check (temperature/component.go:206-248).  Returns a bit set: 1 GPU core above its max-operating
+// threshold, 2 HBM above the memory max, 4 thermal margin at or below the configured margin threshold.  The reason the component
+// reports is the first of margin > gpu > hbm (:273-287).
+int evaluate_temperature(const TemperatureReading& t, int32_t margin_threshold) {
   int m = 0;
-  if (gpu_max > 0 && cur > gpu_max) m |= 1;          // strict '>' like the reference (the same compare n_over uses)
-  if (mem_max > 0 && hbm > mem_max) m |= 2;
-  if (margin_thr > 0 && margin <= margin_thr) m |= 4;
+  if (t.threshold_gpu_max > 0 && t.current_gpu_core > t.threshold_gpu_max) m |= 1;          // strict '>' (the compare n_over uses too)
+  if (t.threshold_mem_max > 0 && t.hbm_supported && t.current_hbm > t.threshold_mem_max) m |= 2;
+  if (t.threshold_slowdown > 0 && t.margin_supported && margin_threshold > 0 && t.slowdown_margin > 0 && t.slowdown_margin <= margin_threshold) m |= 4;
   return m;
 }
 
@@ -476,5 +479,11 @@ int32_t gpudh_hw_slowdown(const int64_t* ev, int32_t n, int64_t now, int64_t win
   *freq = v.freq_per_min; *distinct = v.distinct_minutes;
   return (int32_t)v.health;
 }
-int32_t gpudh_temperature(uint32_t cur, uint32_t gmax, uint32_t hbm, uint32_t mmax, int32_t margin, int32_t mthr) { return gpud::evaluate_temperature(cur, gmax, hbm, mmax, margin, mthr); }
+int32_t gpudh_temperature(uint32_t cur, uint32_t gmax, uint32_t hbm, uint32_t mmax, int32_t hbm_supported, uint32_t slowdown, int32_t margin, int32_t margin_supported,
+                          int32_t mthr) {
+  gpud::TemperatureReading t;
+  t.current_gpu_core = cur; t.threshold_gpu_max = gmax; t.current_hbm = hbm; t.threshold_mem_max = mmax; t.hbm_supported = hbm_supported != 0;
+  t.threshold_slowdown = slowdown; t.slowdown_margin = margin; t.margin_supported = margin_supported != 0;
+  return gpud::evaluate_temperature(t, mthr);
+}
 }

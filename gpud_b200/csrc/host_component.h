@@ -80,7 +80,13 @@ struct SlowdownVerdict { Health health = Health::Healthy; double freq_per_min = 
 SlowdownVerdict evaluate_hw_slowdown(const std::vector<int64_t>& event_unix_seconds, int64_t now_unix, int64_t window_seconds, double threshold_per_min);
 // temperature: current > max-operating, HBM > max-memory, margin <= configured threshold -> Degraded-class reasons
 // (components/accelerator/nvidia/temperature/component.go:206-248); returns a bit mask 1 gpu, 2 hbm, 4 margin
-int evaluate_temperature(uint32_t cur_c, uint32_t gpu_max_c, uint32_t hbm_c, uint32_t mem_max_c, int32_t margin_c, int32_t margin_threshold_c);
+struct TemperatureReading {                    // the fields of temperature.Temperature the rules read (temperature/temperature.go:17-60)
+  uint32_t current_gpu_core = 0, current_hbm = 0;
+  uint32_t threshold_slowdown = 0, threshold_mem_max = 0, threshold_gpu_max = 0;
+  int32_t slowdown_margin = 0;
+  bool hbm_supported = false, margin_supported = false;
+};
+int evaluate_temperature(const TemperatureReading& t, int32_t margin_threshold_c);
 
 // ---- components.Component (types.go:20-66) ----
 struct CheckResult {

@@ -754,6 +754,23 @@ def evolve_healthy_state(events, reboot_threshold: int = 2, event_name: str = "e
 # --------------------------------------------------------------------------------------------
 # threshold rules
 # --------------------------------------------------------------------------------------------
+def temperature_check(t: dict, margin_threshold: int = 0):
+    """the per-GPU rules of the temperature component's Check (temperature/component.go:206-248) and the priority of its reasons
+    (:273-287): returns (health, reason class) with class in {"margin", "gpu", "hbm", ""}; default margin threshold 0 = disabled
+    (temperature/threshold.go:13)."""
+    margin = (t.get("ThresholdCelsiusSlowdown", 0) > 0 and t.get("MarginTemperatureSupported", False) and margin_threshold > 0
+              and t.get("ThresholdCelsiusSlowdownMargin", 0) > 0 and t["ThresholdCelsiusSlowdownMargin"] <= margin_threshold)
+    gpu = t.get("ThresholdCelsiusGPUMax", 0) > 0 and t.get("CurrentCelsiusGPUCore", 0) > t["ThresholdCelsiusGPUMax"]
+    hbm = t.get("ThresholdCelsiusMemMax", 0) > 0 and t.get("HBMTemperatureSupported", False) and t.get("CurrentCelsiusHBM", 0) > t["ThresholdCelsiusMemMax"]
+    if margin:
+        return "Degraded", "margin"
+    if gpu:
+        return "Degraded", "gpu"
+    if hbm:
+        return "Degraded", "hbm"
+    return "Healthy", ""
+
+
 # clockEventReasonsToInclude (hw-slowdown/clock_events.go:192-264): (flag, isHWSlowdown, description)
 CLOCK_EVENT_REASONS = [
     (0x1, False, 'GPU is idle and clocks are dropping to Idle state'),

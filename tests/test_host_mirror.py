@@ -123,10 +123,14 @@ def test_hw_slowdown_window_rule():               # hw-slowdown/component.go:352
 
 def test_temperature_rule():                      # temperature/component.go:206-248: strict '>' on limits, '<=' on the margin
     L = g.lib()
-    assert L.gpudh_temperature(90, 89, 70, 95, 20, 10) == 1
-    assert L.gpudh_temperature(89, 89, 96, 95, 20, 10) == 2
-    assert L.gpudh_temperature(80, 89, 70, 95, 10, 10) == 4
-    assert L.gpudh_temperature(80, 0, 70, 0, 5, 0) == 0
+    T = lambda cur, gmax, hbm, mmax, margin, mthr, hs=1, sl=95, ms=1: L.gpudh_temperature(cur, gmax, hbm, mmax, hs, sl, margin, ms, mthr)
+    assert T(90, 89, 70, 95, 20, 10) == 1
+    assert T(89, 89, 96, 95, 20, 10) == 2
+    assert T(80, 89, 70, 95, 10, 10) == 4
+    assert T(80, 0, 70, 0, 5, 0) == 0
+    assert T(80, 89, 96, 95, 20, 10, hs=0) == 0          # HBM sensor not supported
+    assert T(80, 89, 70, 95, 0, 10) == 0 and T(80, 89, 70, 95, -3, 10) == 0     # unreliable margin readings are skipped
+    assert T(80, 89, 70, 95, 5, 10, ms=0) == 0 and T(80, 89, 70, 95, 5, 10, sl=0) == 0
 
 
 # ---- the stateful kmsg matchers (csrc/kmsg_stateful.cpp) over oracle-built primitive hits: no GPU needed ----
@@ -241,3 +245,22 @@ def test_xid_evolve_extracted_scenarios(golden):   # xid/health_state_test.go:78
             assert o["health"] == r["health"], r["name"]
         if r.get("action"):
             assert o["actions"] and o["actions"][0] == ACT_BY_GO[r["action"]], r["name"]
+
+
+def test_temperature_checks_of_the_reference(golden):   # temperature/component_test.go: TestCheck_* with a Temperature literal
+    L = g.lib()
+    rows = golden("temperature_checks.json")["checks"]["rows"]
+    assert len(rows) >= 10
+    for r in rows:
+        t = r["temperature"]
+        thr = r["margin_threshold"] or 0                 # default 0 = margin rule disabled (temperature/threshold.go:13)
+        health, cls = O.temperature_check(t, thr)
+        assert health == r["health"], r["name"]
+        want_cls = {"margin threshold exceeded": "margin", "GPU temperature anomalies detected": "gpu", "HBM temperature anomalies detected": "hbm",
+                    "temperature is": "hbm", "no temperature issue found": ""}[r["reason_contains"][0]]
+        assert cls == want_cls, r["name"]
+        bits = L.gpudh_temperature(t.get("CurrentCelsiusGPUCore", 0), t.get("ThresholdCelsiusGPUMax", 0), t.get("CurrentCelsiusHBM", 0),
+                                   t.get("ThresholdCelsiusMemMax", 0), int(t.get("HBMTemperatureSupported", False)), t.get("ThresholdCelsiusSlowdown", 0),
+                                   t.get("ThresholdCelsiusSlowdownMargin", 0), int(t.get("MarginTemperatureSupported", False)), thr)
+        got_cls = "margin" if bits & 4 else ("gpu" if bits & 1 else ("hbm" if bits & 2 else ""))
+        assert got_cls == cls and (bits != 0) == (health == "Degraded"), r["name"]

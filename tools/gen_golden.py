@@ -632,6 +632,44 @@ def main():
     rows, src = health_scenarios(N + "xid/health_state_test.go", "createXidEvent")
     dump("xid_health_extracted.json", {"scenarios": {"src": src, "rows": rows, "note": "DefaultRebootThreshold = 2; script-extracted twin of xid_health.json"}})
 
+    # ---- temperature thresholds: every TestCheck_* that builds a Temperature literal and asserts a health (temperature/component_test.go) ----
+    TT = N + "temperature/component_test.go"
+    ttxt = open(os.path.join(REF, TT)).read()
+    trows = []
+    for fm in re.finditer(r"func (TestCheck_\w+)\(t \*testing\.T\) \{", ttxt):
+        body, line = find_func(ttxt, fm.group(1))
+        lit = re.search(r"temperature := Temperature\{(.*?)\n\t*\}", body, re.S)
+        if not lit:
+            continue
+        fields = {}
+        for k, v in re.findall(r"(\w+):\s*([^,\n]+),", lit.group(1)):
+            v = v.strip()
+            fields[k] = v == "true" if v in ("true", "false") else (int(v) if re.fullmatch(r"-?\d+", v) else v)
+        mthr = re.search(r"SetDefaultMarginThreshold\(Thresholds\{CelsiusSlowdownMargin:\s*(\d+)\}\)", body)
+        cases = []
+        tbl = re.findall(r'name:\s*"([^"]*)",\s*marginCelsius:\s*(-?\d+),\s*expectHealthy:\s*apiv1\.HealthStateType(\w+),\s*expectReasonContains:\s*"([^"]*)"', body)
+        tbl2 = re.findall(r'name:\s*"([^"]*)",\s*hbmTemp:\s*(\d+),\s*memMaxThreshold:\s*(\d+),\s*expectHealthy:\s*apiv1\.HealthStateType(\w+),\s*expectReasonContains:\s*"([^"]*)"', body)
+        if tbl:
+            for nm, mc, hl, rs in tbl:
+                f2 = dict(fields)
+                f2["ThresholdCelsiusSlowdownMargin"] = int(mc)
+                cases.append((fm.group(1) + "/" + nm, f2, hl, [rs]))
+        elif tbl2:
+            for nm, ht, mm, hl, rs in tbl2:
+                f2 = dict(fields)
+                f2["CurrentCelsiusHBM"], f2["ThresholdCelsiusMemMax"] = int(ht), int(mm)
+                cases.append((fm.group(1) + "/" + nm, f2, hl, [rs]))
+        else:
+            hm = re.search(r"assert\.Equal\(t,\s*apiv1\.HealthStateType(\w+),\s*data\.health", body)
+            if not hm:
+                continue
+            cases.append((fm.group(1), fields, hm.group(1), re.findall(r'assert\.Contains\(t,\s*data\.reason,\s*"([^"]*)"\)', body)))
+        for nm, f, hl, rs in cases:
+            trows.append({"name": nm, "line": line, "margin_threshold": int(mthr.group(1)) if mthr else None, "health": hl, "reason_contains": rs,
+                          "temperature": {k: v for k, v in f.items() if isinstance(v, (int, bool))}})
+    dthr = re.search(r"CelsiusSlowdownMargin:\s*(\d+)", open(os.path.join(REF, N + "temperature/threshold.go")).read()) if os.path.exists(os.path.join(REF, N + "temperature/threshold.go")) else None
+    dump("temperature_checks.json", {"checks": {"src": TT, "rows": trows, "default_margin_threshold": int(dthr.group(1)) if dthr else None}})
+
     # ---- hw-slowdown: clock-event reason bitmask -> descriptions (hw-slowdown/clock_events.go:168-264, clock_events_test.go:21) ----
     HS = N + "hw-slowdown/"
     ctxt = open(os.path.join(REF, HS + "clock_events.go")).read()
