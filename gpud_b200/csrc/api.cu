@@ -65,7 +65,7 @@ extern "C" int32_t gpud_host_free(void* p) {
 }
 
 // struct sizes for binding layout checks (ctypes / cgo): 0 hit, 1 fabric_raw, 2 fabric_local, 3 fabric_verdict, 4 ring_cfg,
-// 5 kmsg_event, 6 ib_snapshot, 7 ib_verdict, 8 metric
+// 5 kmsg_event, 6 ib_snapshot, 7 ib_verdict, 8 metric, 9 dedup_rule
 extern "C" int32_t gpud_sizeof(int32_t which) {
   switch (which) {
     case 0: return (int32_t)sizeof(gpud_xid_hit);
@@ -77,6 +77,7 @@ extern "C" int32_t gpud_sizeof(int32_t which) {
     case 6: return (int32_t)sizeof(gpud_ib_snapshot);
     case 7: return (int32_t)sizeof(gpud_ib_verdict);
     case 8: return (int32_t)sizeof(gpud_metric);
+    case 9: return (int32_t)sizeof(gpud_dedup_rule);
   }
   return -1;
 }

@@ -192,26 +192,40 @@ std::vector<Event> merge_events(const std::vector<Event>& a, const std::vector<E
 }
 
 // ---- threshold rules ----
+// time.Duration.String() for a whole number of seconds ("10m0s", "1h0m0s", "45s", "0s", "-10m0s"): what %s prints for the window.
+std::string go_duration_seconds(int64_t sec) {
+  if (sec == 0) return "0s";
+  std::string out = sec < 0 ? "-" : "";
+  uint64_t u = sec < 0 ? (uint64_t)(-(sec + 1)) + 1 : (uint64_t)sec;
+  const uint64_t h = u / 3600, m = (u / 60) % 60, s = u % 60;
+  if (h) out += std::to_string(h) + "h";
+  if (h || m) out += std::to_string(m) + "m";
+  return out + std::to_string(s) + "s";
+}
+
 SlowdownVerdict evaluate_hw_slowdown(const std::vector<int64_t>& ev, int64_t now, int64_t window_s, double thr) {   // hw-slowdown/component.go:352-407
   SlowdownVerdict v;
   if (window_s == 0) { v.reason = "no time window to evaluate states"; return v; }
   const int64_t since = now - window_s;
   std::vector<int64_t> minutes;
-  for (int64_t t : ev) if (t >= since) minutes.push_back(t / 60);        // eventBucket.Get(since) then Unix()/60
+  for (int64_t t : ev) if (t > since) minutes.push_back(t / 60);         // eventBucket.Get(since) is "timestamp > since" (eventstore/database.go:330), then Unix()/60
   if (minutes.empty()) { v.reason = "no clock events found"; return v; }
   std::sort(minutes.begin(), minutes.end());
   minutes.erase(std::unique(minutes.begin(), minutes.end()), minutes.end());
   v.distinct_minutes = (int)minutes.size();
   v.freq_per_min = (double)v.distinct_minutes / ((double)window_s / 60.0);
-  char buf[256];
+  char buf[320];
+  const std::string win = go_duration_seconds(window_s);
   if (v.freq_per_min < thr) {
-    snprintf(buf, sizeof buf, "hw slowdown events frequency per minute %.2f (total events per minute count %d) is less than threshold %.2f", v.freq_per_min, v.distinct_minutes, thr);
+    snprintf(buf, sizeof buf, "hw slowdown events frequency per minute %.2f (total events per minute count %d) is less than threshold %.2f for the last %s",
+             v.freq_per_min, v.distinct_minutes, thr, win.c_str());
     v.reason = buf;
     return v;
   }
   v.health = Health::Unhealthy;
   v.inspect = true;
-  snprintf(buf, sizeof buf, "hw slowdown events frequency per minute %.2f (total events per minute count %d) exceeded threshold %.2f", v.freq_per_min, v.distinct_minutes, thr);
+  snprintf(buf, sizeof buf, "hw slowdown events frequency per minute %.2f (total events per minute count %d) exceeded threshold %.2f for the last %s",
+           v.freq_per_min, v.distinct_minutes, thr, win.c_str());
   v.reason = buf;
   return v;
 }
@@ -478,6 +492,12 @@ int32_t gpudh_hw_slowdown(const int64_t* ev, int32_t n, int64_t now, int64_t win
   const gpud::SlowdownVerdict v = gpud::evaluate_hw_slowdown(std::vector<int64_t>(ev, ev + n), now, window_s, thr);
   *freq = v.freq_per_min; *distinct = v.distinct_minutes;
   return (int32_t)v.health;
+}
+void gpudh_go_duration(int64_t sec, char* out, int32_t cap) { snprintf(out, (size_t)cap, "%s", gpud::go_duration_seconds(sec).c_str()); }
+int32_t gpudh_hw_slowdown_reason(const int64_t* ev, int32_t n, int64_t now, int64_t window_s, double thr, char* out, int32_t cap) {
+  const gpud::SlowdownVerdict v = gpud::evaluate_hw_slowdown(std::vector<int64_t>(ev, ev + n), now, window_s, thr);
+  snprintf(out, (size_t)cap, "%s", v.reason.c_str());
+  return (int32_t)v.inspect;
 }
 int32_t gpudh_temperature(uint32_t cur, uint32_t gmax, uint32_t hbm, uint32_t mmax, int32_t hbm_supported, uint32_t slowdown, int32_t margin, int32_t margin_supported,
                           int32_t mthr) {

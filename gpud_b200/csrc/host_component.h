@@ -77,6 +77,7 @@ std::vector<Event> merge_events(const std::vector<Event>& a, const std::vector<E
 // hw-slowdown: distinct event-minutes in the evaluation window / window minutes >= threshold -> Unhealthy + HARDWARE_INSPECTION
 // (components/accelerator/nvidia/hw-slowdown/component.go:352-407; defaults 10 min / 0.6 at :29-35)
 struct SlowdownVerdict { Health health = Health::Healthy; double freq_per_min = 0.0; int distinct_minutes = 0; bool inspect = false; std::string reason; };
+std::string go_duration_seconds(int64_t seconds);   // time.Duration.String() of a whole number of seconds
 SlowdownVerdict evaluate_hw_slowdown(const std::vector<int64_t>& event_unix_seconds, int64_t now_unix, int64_t window_seconds, double threshold_per_min);
 // temperature: current > max-operating, HBM > max-memory, margin <= configured threshold -> Degraded-class reasons
 // (components/accelerator/nvidia/temperature/component.go:206-248); returns a bit mask 1 gpu, 2 hbm, 4 margin

@@ -153,26 +153,126 @@ extern "C" int32_t gpud_store_event_table(gpud_store* st, const char* component,
   return GPUD_OK;
 }
 
+// ExtraInfo as the reference reads it back (database.go:428-447 scanRows + :471-482 unmarshalIfValid into map[string]string):
+// NULL, "" and "null" are no map at all; anything else must be one JSON object of string values (a null value leaves "").
+// Returns false where json.Unmarshal would fail -- the reference's findEvent then returns that error.
+static void utf8_put(std::string& o, uint32_t c) {
+  if (c < 0x80) o += (char)c;
+  else if (c < 0x800) { o += (char)(0xC0 | (c >> 6)); o += (char)(0x80 | (c & 63)); }
+  else if (c < 0x10000) { o += (char)(0xE0 | (c >> 12)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
+  else { o += (char)(0xF0 | (c >> 18)); o += (char)(0x80 | ((c >> 12) & 63)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
+}
+static bool json_ws(const char*& p) { while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p; return true; }
+static bool json_hex4(const char*& p, uint32_t* v) {
+  uint32_t x = 0;
+  for (int i = 0; i < 4; ++i, ++p) {
+    const char c = *p;
+    if (c >= '0' && c <= '9') x = x * 16 + (uint32_t)(c - '0');
+    else if (c >= 'a' && c <= 'f') x = x * 16 + (uint32_t)(c - 'a' + 10);
+    else if (c >= 'A' && c <= 'F') x = x * 16 + (uint32_t)(c - 'A' + 10);
+    else return false;
+  }
+  *v = x;
+  return true;
+}
+static bool json_string(const char*& p, std::string* out) {
+  if (*p != '"') return false;
+  ++p;
+  out->clear();
+  while (*p && *p != '"') {
+    if ((unsigned char)*p < 0x20) return false;
+    if (*p != '\\') { *out += *p++; continue; }
+    ++p;
+    switch (*p) {
+      case '"': *out += '"'; ++p; break;
+      case '\\': *out += '\\'; ++p; break;
+      case '/': *out += '/'; ++p; break;
+      case 'b': *out += '\b'; ++p; break;
+      case 'f': *out += '\f'; ++p; break;
+      case 'n': *out += '\n'; ++p; break;
+      case 'r': *out += '\r'; ++p; break;
+      case 't': *out += '\t'; ++p; break;
+      case 'u': {
+        ++p;
+        uint32_t c;
+        if (!json_hex4(p, &c)) return false;
+        if (c >= 0xD800 && c < 0xDC00 && p[0] == '\\' && p[1] == 'u') {       // surrogate pair; a lone half becomes U+FFFD like encoding/json
+          const char* q = p + 2;
+          uint32_t lo;
+          if (json_hex4(q, &lo) && lo >= 0xDC00 && lo < 0xE000) { c = 0x10000 + ((c - 0xD800) << 10) + (lo - 0xDC00); p = q; }
+          else c = 0xFFFD;
+        } else if (c >= 0xD800 && c < 0xE000) c = 0xFFFD;
+        utf8_put(*out, c);
+        break;
+      }
+      default: return false;
+    }
+  }
+  if (*p != '"') return false;
+  ++p;
+  return true;
+}
+static bool parse_extra_info(const char* text, std::map<std::string, std::string>* m) {
+  m->clear();
+  if (!text || !*text || !strcmp(text, "null")) return true;
+  if (text[0] != '{') return false;
+  const char* p = text + 1;
+  json_ws(p);
+  if (*p == '}') { ++p; json_ws(p); return *p == 0; }
+  for (;;) {
+    std::string k, v;
+    json_ws(p);
+    if (!json_string(p, &k)) return false;
+    json_ws(p);
+    if (*p++ != ':') return false;
+    json_ws(p);
+    if (!strncmp(p, "null", 4)) p += 4;
+    else if (!json_string(p, &v)) return false;
+    (*m)[k] = v;
+    json_ws(p);
+    if (*p == ',') { ++p; continue; }
+    if (*p == '}') { ++p; break; }
+    return false;
+  }
+  json_ws(p);
+  return *p == 0;
+}
+
+// findEvent (database.go:277-324): rows of the same (timestamp, name, type[, message]) whose ExtraInfo MAP equals the event's
+// (compareEvent :459-469 -- same size, same key/value pairs; the JSON text may differ in key order or spacing).
+static int32_t find_event(gpud_store* st, const std::string& t, int64_t unix_s, const char* name, const char* type, const char* message,
+                          const char* extra_json, bool* found) {
+  Sq* S = sq();
+  *found = false;
+  std::map<std::string, std::string> want, have;
+  if (!parse_extra_info(extra_json, &want)) return sfail(st, "extra_info is not a JSON object of strings");
+  void* q = nullptr;
+  std::string sel = "\nSELECT timestamp, name, type, message, extra_info FROM " + t + " WHERE timestamp = ? AND name = ? AND type = ?";
+  if (message && *message) sel += " AND message = ?";
+  if (S->prepare_v2(st->db, sel.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare find");
+  S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
+  if (message && *message) S->bind_text(q, 4, message, -1, kTransient);
+  int32_t rc = GPUD_OK;
+  while (S->step(q) == kRow) {
+    if (!parse_extra_info((const char*)S->column_text(q, 4), &have)) { rc = sfail(st, "stored extra_info is not a JSON object of strings"); break; }
+    if (have == want) { *found = true; break; }
+  }
+  S->finalize(q);
+  return rc;
+}
+
 static int32_t insert_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
                             const char* extra_json, bool skip_duplicate, bool* inserted) {
   Sq* S = sq();
   if (inserted) *inserted = false;
   const std::string t = table;
-  void* q = nullptr;
-  if (skip_duplicate) {                                          // findEvent (database.go:277-324) + compareEvent
-    std::string sel = "\nSELECT timestamp, name, type, message, extra_info FROM " + t + " WHERE timestamp = ? AND name = ? AND type = ?";
-    if (message && *message) sel += " AND message = ?";
-    if (S->prepare_v2(st->db, sel.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare find");
-    S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
-    if (message && *message) S->bind_text(q, 4, message, -1, kTransient);
+  if (skip_duplicate) {
     bool dup = false;
-    while (S->step(q) == kRow) {
-      const char* ex = (const char*)S->column_text(q, 4);
-      if (std::string(ex ? ex : "") == std::string(extra_json ? extra_json : "")) { dup = true; break; }
-    }
-    S->finalize(q);
+    const int32_t rc = find_event(st, t, unix_s, name, type, message, extra_json, &dup);
+    if (rc) return rc;
     if (dup) return GPUD_OK;
   }
+  void* q = nullptr;
   const std::string ins = "INSERT INTO " + t + " (timestamp, name, type, message, extra_info) VALUES (?, ?, ?, NULLIF(?, ''), NULLIF(?, ''))";
   if (S->prepare_v2(st->db, ins.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare insert");
   S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
@@ -189,6 +289,17 @@ extern "C" int32_t gpud_store_insert_event(gpud_store* st, const char* table, in
   if (!st || !ident_ok(table) || !name || !type) return GPUD_E_INVALID;
   if (!sq()) return GPUD_E_UNSUPPORTED;
   return insert_event(st, table, unix_s, name, type, message, extra_info_json, false, nullptr);
+}
+
+// Bucket.Find (eventstore/types.go:44-47, database.go:277-324)
+extern "C" int32_t gpud_store_find_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
+                                         const char* extra_info_json, int32_t* found) {
+  if (!st || !ident_ok(table) || !name || !type || !found) return GPUD_E_INVALID;
+  if (!sq()) return GPUD_E_UNSUPPORTED;
+  bool f = false;
+  const int32_t rc = find_event(st, table, unix_s, name, type, message, extra_info_json, &f);
+  *found = f ? 1 : 0;
+  return rc;
 }
 
 // the Insert loop of xid/component.go:468-577 for one scan's hits: one "error_xid" event per Xid hit, time = boot + kmsg usec
@@ -225,14 +336,18 @@ extern "C" int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table,
 // ---- pkg/kmsg Syncer over the hits of RAW_KMSG scans (syncer.go:73-143) -----------------------------------------------
 // For every kmsg record on which the component's Match fires: Event{Time: boot + usec, Name, Message, Type: Warning};
 // dropped when the parsed form "name_message" was already seen in the same truncation bucket (deduper.go:63-125: default 60 s
-// buckets, 15 min TTL against the wall clock), or when the identical event is already in the table (Find), else inserted.
+// buckets, 15 min TTL against the wall clock; an event-specific window replaces both, syncer.go:145-155), or when the
+// identical event is already in the table (Find), else inserted.
 // The watcher's raw-message dedup upstream (watcher.go) drops nothing this step would keep: identical raw lines of one bucket
-// parse to identical events.  Event-specific dedup windows (infiniband's kmsgEventDedupWindow) are not modelled.
+// parse to identical events.
 struct gpud_kmsg_syncer {
   std::string component, table;
   gpud_store* st = nullptr;
+  int truncate_seconds = 60;                       // defaultCacheKeyTruncateSeconds (deduper.go:14), WithCacheKeyTruncateSeconds
+  bool disable_dedup = false;                      // withDisableDedup
+  std::vector<gpud_dedup_rule> rules;              // the EventDedupWindowFunc as data: first rule that matches decides
   struct Entry { int count; int64_t expires; };
-  std::map<std::string, Entry> cache;
+  std::map<std::string, Entry> cache;              // go-cache: an item is live while now <= its expiration
 };
 
 extern "C" int32_t gpud_kmsg_syncer_create(gpud_store* st, const char* component, gpud_kmsg_syncer** out) {
@@ -246,6 +361,68 @@ extern "C" int32_t gpud_kmsg_syncer_create(gpud_store* st, const char* component
   return GPUD_OK;
 }
 extern "C" void gpud_kmsg_syncer_destroy(gpud_kmsg_syncer* sy) { delete sy; }
+
+extern "C" int32_t gpud_kmsg_syncer_configure(gpud_kmsg_syncer* sy, int32_t truncate_seconds, int32_t disable_dedup, const gpud_dedup_rule* rules,
+                                              int32_t n_rules) {
+  if (!sy || n_rules < 0 || (n_rules && !rules)) return GPUD_E_INVALID;
+  for (int32_t i = 0; i < n_rules; ++i)
+    if (!memchr(rules[i].event, 0, sizeof rules[i].event) || !memchr(rules[i].message_contains, 0, sizeof rules[i].message_contains)) return GPUD_E_INVALID;
+  sy->truncate_seconds = truncate_seconds > 0 ? truncate_seconds : 60;          // WithCacheKeyTruncateSeconds ignores values <= 0 (deduper.go:35-41)
+  sy->disable_dedup = disable_dedup != 0;
+  sy->rules.assign(rules, rules + n_rules);
+  return GPUD_OK;
+}
+
+// The options each reference component passes to kmsg.NewSyncer: infiniband/component.go:149-155 + :166-179 (5 min buckets;
+// access_reg_failed: 24 h per PCI device, 5 min without one), peermem/component.go:64-70 and disk/component.go:198-203 (5 min),
+// nccl / os / cpu / memory: defaults (nccl/component.go:61, os/component.go:144, cpu/component.go:74, memory/component.go:89).
+extern "C" int32_t gpud_kmsg_syncer_configure_component(gpud_kmsg_syncer* sy, const char* kmsg_component) {
+  if (!sy || !kmsg_component) return GPUD_E_INVALID;
+  const std::string c = kmsg_component;
+  if (c == "infiniband") {
+    gpud_dedup_rule r[2];
+    memset(r, 0, sizeof r);
+    snprintf(r[0].event, sizeof r[0].event, "access_reg_failed"); snprintf(r[0].message_contains, sizeof r[0].message_contains, "(PCI device ");
+    r[0].window_seconds = 24 * 3600;
+    snprintf(r[1].event, sizeof r[1].event, "access_reg_failed"); r[1].window_seconds = 5 * 60;
+    return gpud_kmsg_syncer_configure(sy, 300, 0, r, 2);
+  }
+  if (c == "peermem" || c == "disk") return gpud_kmsg_syncer_configure(sy, 300, 0, nullptr, 0);
+  if (c == "nccl" || c == "os" || c == "cpu" || c == "memory") return gpud_kmsg_syncer_configure(sy, 60, 0, nullptr, 0);
+  return GPUD_E_INVALID;
+}
+
+// One pass of the loop body of Syncer.sync (syncer.go:84-140) for an event the matcher produced.  Caller holds the transaction.
+static int32_t syncer_step(gpud_kmsg_syncer* sy, int64_t t, const char* name, const char* msg, int64_t now_unix, bool* inserted) {
+  *inserted = false;
+  const bool has_deduper = !sy->disable_dedup || !sy->rules.empty();            // syncer.go:54-59
+  if (has_deduper) {
+    int64_t trunc = sy->disable_dedup ? 60 : sy->truncate_seconds, ttl = 15 * 60;                // dedupParams (syncer.go:145-155)
+    for (const gpud_dedup_rule& r : sy->rules) {
+      if (strcmp(r.event, name) != 0) continue;
+      if (r.message_contains[0] && !strstr(msg, r.message_contains)) continue;
+      if (r.window_seconds > 0) { trunc = r.window_seconds; ttl = r.window_seconds; }
+      break;
+    }
+    int64_t rem = t % trunc;                                                   // Go's % truncates toward zero, like C's
+    const std::string key = std::to_string(t - rem) + "-" + name + "_" + msg;  // cacheKeyWithTruncateSeconds of Message{name + "_" + message}
+    auto it = sy->cache.find(key);
+    int freq = 1;
+    if (it != sy->cache.end() && it->second.expires >= now_unix) freq = it->second.count + 1;
+    sy->cache[key] = gpud_kmsg_syncer::Entry{freq, now_unix + ttl};
+    if (freq > 1) return GPUD_OK;
+  }
+  return insert_event(sy->st, sy->table.c_str(), t, name, "Warning", msg, "", true, inserted);   // Find, then Insert (syncer.go:112-135)
+}
+
+extern "C" int32_t gpud_kmsg_syncer_offer(gpud_kmsg_syncer* sy, int64_t unix_s, const char* name, const char* message, int64_t now_unix, int32_t* inserted) {
+  if (!sy || !name || !*name) return GPUD_E_INVALID;                            // Match's "" name means no event (syncer.go:85-88)
+  if (!sq()) return GPUD_E_UNSUPPORTED;
+  bool did = false;
+  const int32_t rc = syncer_step(sy, unix_s, name, message ? message : "", now_unix, &did);
+  if (inserted) *inserted = did ? 1 : 0;
+  return rc;
+}
 
 extern "C" int32_t gpud_kmsg_syncer_feed(gpud_kmsg_syncer* sy, const char* kmsg_component, const gpud_xid_hit* hits, int64_t n, const uint8_t* buf,
                                          int64_t boot_unix, int64_t now_unix, int32_t* n_inserted) {
@@ -263,18 +440,8 @@ extern "C" int32_t gpud_kmsg_syncer_feed(gpud_kmsg_syncer* sy, const char* kmsg_
     last_unit = h.unit_index;
     char msg[4096];
     if (gpud_kmsg_hit_message(&h, buf, msg, sizeof msg) < 0) continue;
-    const char* name = gpud_kmsg_event_name(h.kind);
-    const int64_t t = boot_unix + h.kmsg_usec / 1000000;
-    // parsed dedup (syncer.go:99-110, deduper.go:63-74,111-125)
-    const int64_t bucket = t - (t % 60);
-    const std::string key = std::to_string(bucket) + "-" + name + "_" + msg;
-    auto it = sy->cache.find(key);
-    int freq = 1;
-    if (it != sy->cache.end() && it->second.expires > now_unix) freq = it->second.count + 1;
-    sy->cache[key] = gpud_kmsg_syncer::Entry{freq, now_unix + 15 * 60};
-    if (freq > 1) continue;
     bool did = false;
-    const int32_t rc = insert_event(sy->st, sy->table.c_str(), t, name, "Warning", msg, "", true, &did);   // Find, then Insert (syncer.go:112-135)
+    const int32_t rc = syncer_step(sy, boot_unix + h.kmsg_usec / 1000000, gpud_kmsg_event_name(h.kind), msg, now_unix, &did);
     if (rc) { S->exec(sy->st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return rc; }
     ins += did ? 1 : 0;
   }

@@ -278,6 +278,10 @@ int32_t gpud_store_last_error(gpud_store* st, char* out, int32_t cap);
 int32_t gpud_store_event_table(gpud_store* st, const char* component, char* table_out, int32_t cap);
 int32_t gpud_store_insert_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
                                 const char* extra_info_json);
+/* Bucket.Find (database.go:277-324): *found = 1 when a row of the same (timestamp, name, type[, message if non-empty]) carries an
+ * equal ExtraInfo map (compareEvent :459-469; NULL / "" / "null" = no map).  extra_info_json: one JSON object of string values. */
+int32_t gpud_store_find_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
+                              const char* extra_info_json, int32_t* found);
 /* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
 int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);
@@ -287,8 +291,20 @@ int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud
  * goes through the parsed-message dedup (60 s buckets, 15 min TTL against `now_unix`) and the store's duplicate check, and is
  * inserted.  One syncer per (component, kmsg stream); its dedup cache carries over between feeds. */
 typedef struct gpud_kmsg_syncer gpud_kmsg_syncer;
+/* One clause of a kmsg.EventDedupWindowFunc (pkg/kmsg/deduper.go:26,49-56) as data: an event whose name equals `event` and whose
+ * message contains `message_contains` ("" = any) is coalesced over `window_seconds` (bucket width and cache TTL, syncer.go:145-155);
+ * the first matching rule decides, window_seconds <= 0 = "not configured" for that event. */
+typedef struct { char event[32]; char message_contains[32]; int64_t window_seconds; } gpud_dedup_rule;
 int32_t gpud_kmsg_syncer_create(gpud_store* st, const char* component, gpud_kmsg_syncer** out);
 void gpud_kmsg_syncer_destroy(gpud_kmsg_syncer* sy);
+/* kmsg.WithCacheKeyTruncateSeconds (<= 0 keeps 60), withDisableDedup, WithEventDedupWindowFunc (rules copied). */
+int32_t gpud_kmsg_syncer_configure(gpud_kmsg_syncer* sy, int32_t truncate_seconds, int32_t disable_dedup, const gpud_dedup_rule* rules, int32_t n_rules);
+/* The options the reference's own component passes to kmsg.NewSyncer: "infiniband" (5 min; access_reg_failed 24 h per PCI device,
+ * infiniband/component.go:149-179), "peermem", "disk" (5 min), "nccl", "os", "cpu", "memory" (defaults). */
+int32_t gpud_kmsg_syncer_configure_component(gpud_kmsg_syncer* sy, const char* kmsg_component);
+/* The loop body of Syncer.sync (syncer.go:84-140) for ONE event a matcher produced -- the entry for the events of the stateful
+ * matchers (gpud_kmsg_stateful_feed) and for callers with their own MatchFunc: parsed dedup, Find, Insert as type "Warning". */
+int32_t gpud_kmsg_syncer_offer(gpud_kmsg_syncer* sy, int64_t unix_s, const char* name, const char* message, int64_t now_unix, int32_t* inserted);
 int32_t gpud_kmsg_syncer_feed(gpud_kmsg_syncer* sy, const char* kmsg_component, const gpud_xid_hit* hits, int64_t n, const uint8_t* buf,
                               int64_t boot_unix, int64_t now_unix, int32_t* n_inserted);
 /* table NULL or "" = "gpud_metrics_v0_5" (metrics/store/sqlite.go:36) */

@@ -702,6 +702,52 @@ def dedup_key(ts_unix_s: int, message: str) -> str:                   # deduper.
     return "%d-%s" % (ts_unix_s - ts_unix_s % 60, message)
 
 
+def infiniband_dedup_window(name: str, message: str):
+    """(*component).kmsgEventDedupWindow (infiniband/component.go:166-179) -> (window seconds, ok)"""
+    if name != "access_reg_failed":
+        return 0, False
+    if "(PCI device " not in message:                     # pciDeviceMessagePrefix (kmsg_matcher.go:63)
+        return 5 * 60, True                               # defaultKmsgEventDedupWindow (component.go:38)
+    return 24 * 3600, True                                # defaultAccessRegEventDedupWindow (component.go:43)
+
+
+class KmsgSyncerModel:
+    """pkg/kmsg Syncer.sync loop body (syncer.go:84-140) + newSyncer's option handling (:30-59) + dedupParams (:145-155) +
+    deduper.addCacheWithWindow (deduper.go:111-125, go-cache: live while now <= expiration) over an in-memory bucket whose Find
+    is findEvent (eventstore/database.go:277-324) for events without ExtraInfo."""
+
+    def __init__(self, truncate_seconds: int = 60, disable_dedup: bool = False, window_func=None):
+        self.window_func = window_func
+        self.has_deduper = (not disable_dedup) or window_func is not None
+        self.truncate = 60 if disable_dedup else (truncate_seconds if truncate_seconds > 0 else 60)
+        self.cache: Dict[str, Tuple[int, int]] = {}
+        self.rows: List[Tuple[int, str, str, str]] = []
+
+    def dedup_params(self, name: str, message: str):
+        if self.window_func is not None:
+            w, ok = self.window_func(name, message)
+            if ok and w > 0:
+                return w, w
+        return self.truncate, 15 * 60
+
+    def offer(self, t: int, name: str, message: str, now: int) -> bool:
+        if not name:
+            return False
+        if self.has_deduper:
+            trunc, ttl = self.dedup_params(name, message)
+            key = "%d-%s" % (t - t % trunc, name + "_" + message)
+            cnt, exp = self.cache.get(key, (0, -1))
+            freq = cnt + 1 if (cnt and exp >= now) else 1
+            self.cache[key] = (freq, now + ttl)
+            if freq > 1:
+                return False
+        for (rt, rn, ry, rm) in self.rows:                # Find: same (timestamp, name, type) and, for a non-empty message, same message
+            if rt == t and rn == name and ry == "Warning" and (message == "" or rm == message):
+                return False
+        self.rows.append((t, name, "Warning", message))
+        return True
+
+
 # --------------------------------------------------------------------------------------------
 # health evolution     (xid/health_state.go:57-128 ; xid/component.go:614-642)
 # events: list of dicts newest-first: {"name": "error_xid"|"reboot"|"SetHealthy", "type": "Fatal"..,
@@ -792,15 +838,34 @@ def clock_event_reasons(bitmask: int):
     return hw, other
 
 
+def go_duration_seconds(sec: int) -> str:
+    """time.Duration.String() of a whole number of seconds."""
+    if sec == 0:
+        return "0s"
+    u = abs(sec)
+    h, m, s_ = u // 3600, (u // 60) % 60, u % 60
+    return ("-" if sec < 0 else "") + (f"{h}h" if h else "") + (f"{m}m" if h or m else "") + f"{s_}s"
+
+
 def hw_slowdown_state(event_unix_s: List[int], now_unix: int, window_seconds: int, threshold_freq_per_min: float):
-    """hw-slowdown/component.go:352-407: distinct event-minutes since (now - window) / window minutes >= threshold -> Unhealthy."""
+    """hw-slowdown/component.go:352-407: distinct event-minutes since (now - window) / window minutes >= threshold -> Unhealthy.
+    The bucket read is `timestamp > since` (pkg/eventstore/database.go:327-335)."""
+    return hw_slowdown_check(event_unix_s, now_unix, window_seconds, threshold_freq_per_min)[:3]
+
+
+def hw_slowdown_check(event_unix_s: List[int], now_unix: int, window_seconds: int, threshold_freq_per_min: float):
+    """-> (health, freq, distinct minutes, reason, hardware_inspection) with the reason strings of component.go:352-401."""
     if window_seconds == 0:
-        return "Healthy", 0.0, 0
-    mins = {t // 60 for t in event_unix_s if t >= now_unix - window_seconds}
+        return "Healthy", 0.0, 0, "no time window to evaluate states", False
+    mins = {t // 60 for t in event_unix_s if t > now_unix - window_seconds}
     if not mins:
-        return "Healthy", 0.0, 0
+        return "Healthy", 0.0, 0, "no clock events found", False
     freq = len(mins) / (window_seconds / 60.0)
-    return ("Healthy" if freq < threshold_freq_per_min else "Unhealthy"), freq, len(mins)
+    head = "hw slowdown events frequency per minute %.2f (total events per minute count %d) " % (freq, len(mins))
+    tail = " threshold %.2f for the last %s" % (threshold_freq_per_min, go_duration_seconds(window_seconds))
+    if freq < threshold_freq_per_min:
+        return "Healthy", freq, len(mins), head + "is less than" + tail, False
+    return "Unhealthy", freq, len(mins), head + "exceeded" + tail, True
 
 
 # --------------------------------------------------------------------------------------------

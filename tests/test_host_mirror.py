@@ -119,6 +119,23 @@ def test_hw_slowdown_window_rule():               # hw-slowdown/component.go:352
         h = L.gpudh_hw_slowdown(arr, len(ev), C.c_int64(now), C.c_int64(win), C.c_double(thr), C.byref(freq), C.byref(distinct))
         oh, ofreq, on = O.hw_slowdown_state(ev, now, win, thr)
         assert HEALTH[h] == want == oh and distinct.value == on and abs(freq.value - ofreq) < 1e-12
+        out = C.create_string_buffer(400)
+        insp = L.gpudh_hw_slowdown_reason(arr, len(ev), C.c_int64(now), C.c_int64(win), C.c_double(thr), out, 400)
+        full = O.hw_slowdown_check(ev, now, win, thr)
+        assert out.value.decode() == full[3] and bool(insp) == full[4] == (want == "Unhealthy")
+    # the bucket read is strictly newer than (now - window) (pkg/eventstore/database.go:330 "timestamp > ?")
+    assert O.hw_slowdown_check([now - 600], now, 600, 0.05)[3] == "no clock events found"
+    assert O.hw_slowdown_check([now - 599], now, 600, 0.05)[0] == "Unhealthy"
+    # TestHighFrequencySlowdownEvents (hw-slowdown/component_test.go:862-896): 10 events one per minute back from now, window 10 min, 0.6
+    r = O.hw_slowdown_check([now - 60 * i for i in range(10)], now, 600, 0.6)
+    assert r[0] == "Unhealthy" and "hw slowdown events frequency per minute" in r[3] and "exceeded threshold" in r[3] and r[3].endswith("for the last 10m0s")
+    # negative window (TestComponentStatesEdgeCases :446): since lies in the future, nothing is read
+    assert O.hw_slowdown_check([now - 300], now, -600, 0.6)[3] == "no clock events found"
+    for sec, want in [(0, "0s"), (45, "45s"), (600, "10m0s"), (3600, "1h0m0s"), (5405, "1h30m5s"), (-600, "-10m0s"), (86400 * 3, "72h0m0s")]:
+        assert O.go_duration_seconds(sec) == want
+        L.gpudh_go_duration.restype = None
+        L.gpudh_go_duration(C.c_int64(sec), out, 400)
+        assert out.value.decode() == want
 
 
 def test_temperature_rule():                      # temperature/component.go:206-248: strict '>' on limits, '<=' on the margin

@@ -168,3 +168,154 @@ def test_kmsg_syncer_rows_match_the_reference_flow(store, golden, component):
     sy2 = st.syncer(component)
     assert st.syncer_feed(sy2, component, hits, buf, boot, now_unix=boot + 10_000) == 0
     db.close()
+
+
+# ---- Bucket.Find / compareEvent (pkg/eventstore/database.go:277-324, 459-469) ------------------------------------------
+def test_find_event_compares_extra_info_as_a_map(store, golden):
+    st, path = store
+    G = golden("eventstore_cases.json")
+    t = st.event_table("test_table")
+    js = lambda m: json.dumps(m, separators=(",", ":"), sort_keys=True) if m is not None else ""
+    for i, r in enumerate(G["compare_event"]["rows"]):            # TestCompareEvent: stored event A, searched event B
+        ts = 1_750_000_000 + i
+        st.insert_event(t, ts, "kmsg", "Warning", "", js(r["a"]))
+        assert st.find_event(t, ts, "kmsg", "Warning", "", js(r["b"])) == r["expected"], r["name"]
+        # the text of the JSON does not matter, the map does: reversed key order and extra spaces
+        spaced = "{ " + " , ".join("%s : %s" % (json.dumps(k), json.dumps(v)) for k, v in reversed(list(r["b"].items()))) + " }"
+        assert st.find_event(t, ts, "kmsg", "Warning", "", spaced) == r["expected"], r["name"]
+    # TestFindEvent (database_test.go:309): absent before the insert, present after
+    ev = (1_750_001_000, "kmsg", "Warning", "", js({"a": "b"}))
+    assert not st.find_event(t, *ev)
+    st.insert_event(t, *ev)
+    assert st.find_event(t, *ev)
+    # TestFindEventPartialMatch (:351): same timestamp / name / type, different details -> nil
+    assert not st.find_event(t, 1_750_001_000, "kmsg", "Warning", "", js({"a": "c"}))
+    # TestFindEventMultipleMatches (:391): two rows of the same (timestamp, name, type); the one with the equal map is found
+    st.insert_event(t, 1_750_002_000, "kmsg", "Warning", "", js({"a": "b", "c": "d"}))
+    st.insert_event(t, 1_750_002_000, "kmsg", "Warning", "", js({"a": "b"}))
+    assert st.find_event(t, 1_750_002_000, "kmsg", "Warning", "", js({"a": "b"}))
+    assert st.find_event(t, 1_750_002_000, "kmsg", "Warning", "", js({"c": "d", "a": "b"}))
+    assert not st.find_event(t, 1_750_002_000, "kmsg", "Warning", "", js({"c": "d"}))
+    # message: part of the WHERE clause only when non-empty (database.go:291-298)
+    st.insert_event(t, 1_750_003_000, "kmsg", "Warning", "hello", "")
+    assert st.find_event(t, 1_750_003_000, "kmsg", "Warning", "", "") and st.find_event(t, 1_750_003_000, "kmsg", "Warning", "hello", "")
+    assert not st.find_event(t, 1_750_003_000, "kmsg", "Warning", "other", "") and not st.find_event(t, 1_750_003_000, "kmsg", "Fatal", "", "")
+    # escapes decode to the same strings (json.Unmarshal): \\u0041 is "A", a surrogate pair is one code point
+    st.insert_event(t, 1_750_004_000, "kmsg", "Warning", "", json.dumps({"k": "A\n\U0001F600/"}, ensure_ascii=False))
+    assert st.find_event(t, 1_750_004_000, "kmsg", "Warning", "", '{"k":"\\u0041\\n\\ud83d\\ude00\\/"}')
+    assert not st.find_event(t, 1_750_004_000, "kmsg", "Warning", "", '{"k":"\\u0042\\n\\ud83d\\ude00\\/"}')
+
+
+def test_stored_extra_info_is_read_like_unmarshal_if_valid(store, golden):
+    st, path = store
+    G = golden("eventstore_cases.json")
+    t = st.event_table("test_table")
+    db = sqlite3.connect(path)
+    for i, r in enumerate(G["unmarshal_if_valid"]["rows"]):       # TestUnmarshalIfValid (database_test.go:1438)
+        if r["name"] in ("valid JSON", "invalid JSON format"):     # rows about the test's own struct type (an int field), not map[string]string
+            continue
+        ts = 1_760_000_000 + i
+        db.execute("INSERT INTO %s (timestamp, name, type, message, extra_info) VALUES (?, 'kmsg', 'Warning', NULL, ?)" % t, (ts, r["string"] if r["valid"] else None))
+        db.commit()
+        if r["expected_error"]:
+            with pytest.raises(g.GpudError):
+                st.find_event(t, ts, "kmsg", "Warning", "", "")
+        else:
+            assert st.find_event(t, ts, "kmsg", "Warning", "", "")          # NULL, "" and "null" all read back as "no ExtraInfo"
+            assert st.find_event(t, ts, "kmsg", "Warning", "", "null") and st.find_event(t, ts, "kmsg", "Warning", "", "{}")
+    # map[string]string: a non-string value is an Unmarshal error, a null value leaves ""
+    db.execute("INSERT INTO %s (timestamp, name, type, message, extra_info) VALUES (1760000100, 'kmsg', 'Warning', NULL, '{\"key\":\"test\",\"value\":123}')" % t)
+    db.execute("INSERT INTO %s (timestamp, name, type, message, extra_info) VALUES (1760000200, 'kmsg', 'Warning', NULL, '{\"key\":null}')" % t)
+    db.commit()
+    with pytest.raises(g.GpudError):
+        st.find_event(t, 1760000100, "kmsg", "Warning", "", "")
+    assert st.find_event(t, 1760000200, "kmsg", "Warning", "", '{"key":""}')
+    db.close()
+
+
+# ---- the Syncer's dedup options (pkg/kmsg/syncer.go:30-59, 84-155; syncer_test.go:62-383) -----------------------------
+BASE = 1767270610                                   # time.Date(2026, 1, 1, 12, 30, 10, 0, time.UTC) of the reference's tests
+
+
+def _syncer_case(st, path, G, bucket, cfg, sends, match):
+    """the shape of every TestSyncer_* dedup test: a mock watcher channel, a matchFunc, options; returns the rows (time DESC)"""
+    sy = st.syncer(bucket)
+    st.syncer_configure(sy, **cfg)
+    for dt, raw in sends:
+        name, message = match(raw)
+        if name:
+            st.syncer_offer(sy, BASE + dt, name, message, now_unix=BASE + 1000)
+    db = sqlite3.connect(path)
+    rows = list(db.execute(G["event_get"]["sql"].format(table=st.event_table(bucket)), (0,)))
+    db.close()
+    return rows
+
+
+def test_syncer_dedup_options_follow_the_references_tests(store, golden):
+    import datetime
+    assert BASE == int(datetime.datetime(2026, 1, 1, 12, 30, 10, tzinfo=datetime.timezone.utc).timestamp())
+    st, path = store
+    G = golden("store_sql.json")
+    const = lambda raw: ("test_event", "constant parsed message") if raw else ("", "")
+    pids = [(0, "raw message with pid 123"), (1, "raw message with pid 456"), (2, "raw message with pid 789")]
+    # TestSyncer_Deduplication (:62): WithCacheKeyTruncateSeconds(60), three raw lines one parsed form -> exactly 1 event
+    rows = _syncer_case(st, path, G, "test_dedup", dict(truncate_seconds=60), pids, const)
+    assert len(rows) == 1 and rows[0][1:4] == ("test_event", "Warning", "constant parsed message")
+    # TestSyncer_DisableDedup (:119): withDisableDedup -> 3 events
+    assert len(_syncer_case(st, path, G, "test_disable_dedup", dict(disable_dedup=True), pids, const)) == 3
+    # TestSyncer_EventDedupWindowFunc (:164): 5 min window for test_event; +0, +4 min, +6 min -> 2 events
+    five = [("test_event", "", 300)]
+    rows = _syncer_case(st, path, G, "test_event_dedup_window", dict(rules=five), [(0, "a"), (240, "b"), (360, "c")], const)
+    assert len(rows) == 2
+    # TestSyncer_EventDedupWindowFunc_BypassesGenericDedup (:216): generic 300 s, event window 1 min; +0, +2 min -> 2 events
+    one = [("test_event", "", 60)]
+    assert len(_syncer_case(st, path, G, "test_event_dedup_bypass_generic", dict(truncate_seconds=300, rules=one), [(0, "a"), (120, "b")], const)) == 2
+    # TestSyncer_EventDedupWindowFunc_PreservesGenericDedupForOtherEvents (:266): base 12:30:00; generic 300 s keeps 1 generic, window 60 s keeps 2 custom
+    def two(raw):
+        return {"custom-1": ("custom_event", "custom parsed message"), "custom-2": ("custom_event", "custom parsed message"),
+                "generic-1": ("generic_event", "generic parsed message"), "generic-2": ("generic_event", "generic parsed message")}.get(raw, ("", ""))
+    rows = _syncer_case(st, path, G, "test_event_dedup_preserves_generic", dict(truncate_seconds=300, rules=[("custom_event", "", 60)]),
+                        [(-10, "generic-1"), (110, "generic-2"), (-10, "custom-1"), (110, "custom-2"), (5, "unmatched")], two)
+    assert len(rows) == 3 and sum(r[1] == "generic_event" for r in rows) == 1 and sum(r[1] == "custom_event" for r in rows) == 2
+    # TestSyncer_DisableDedup_KeepsEventDedupWindowFunc (:334): disabled generic dedup, 5 min window still coalesces -> 1 event
+    assert len(_syncer_case(st, path, G, "test_disable_dedup_keeps_event_window", dict(disable_dedup=True, rules=five), pids[:2], const)) == 1
+
+
+def test_syncer_component_options_and_random_streams_match_the_model(store, golden):
+    import numpy as np
+    from oracle import pyoracle as O
+    st, path = store
+    G = golden("store_sql.json")
+    E = golden("eventstore_cases.json")["infiniband_dedup_window"]
+    assert E["constants"] == {"defaultKmsgEventDedupWindow": 300, "defaultAccessRegEventDedupWindow": 86400}
+    for r in E["rows"]:                              # TestComponentKmsgEventDedupWindow_* (infiniband/component_test.go:261-315)
+        assert O.infiniband_dedup_window(r["event"], r["message"]) == (r["window_seconds"], r["ok"]), r["name"]
+    rng = np.random.default_rng(11)
+    events = [(r["event"], r["message"]) for r in E["rows"]] + [("access_reg_failed", E["rows"][0]["message"].replace("d2", "3b")), ("port_module_high_temperature", "x")]
+    configs = {"infiniband": (dict(truncate_seconds=300, window_func=O.infiniband_dedup_window), None),
+               "peermem": (dict(truncate_seconds=300), None), "disk": (dict(truncate_seconds=300), None), "nccl": (dict(), None), "memory": (dict(), None),
+               "custom": (dict(truncate_seconds=120, disable_dedup=True, window_func=lambda n, m: (90, True) if n == "other_event" else (0, n == "access_reg_failed")),
+                          dict(truncate_seconds=120, disable_dedup=True, rules=[("other_event", "", 90), ("access_reg_failed", "", 0)])),
+               "off": (dict(disable_dedup=True), dict(disable_dedup=True))}
+    for i, (comp, (mcfg, pcfg)) in enumerate(configs.items()):
+        model = O.KmsgSyncerModel(**mcfg)
+        bucket = "model_%s" % comp
+        sy = st.syncer(bucket)
+        if pcfg is None:
+            st.syncer_configure_component(sy, comp)
+        else:
+            st.syncer_configure(sy, **pcfg)
+        t, now = 1_770_000_000, 1_770_000_000
+        for _ in range(1500):
+            t += int(rng.choice([0, 1, 20, 70, 400, 4000, 50_000]))
+            now += int(rng.choice([0, 5, 100, 1000, 100_000]))
+            name, msg = events[int(rng.integers(0, len(events)))]
+            tt = t - int(rng.choice([0, 0, 30, 500]))            # kmsg timestamps are not always monotone across sources
+            assert st.syncer_offer(sy, tt, name, msg, now) == model.offer(tt, name, msg, now), (comp, tt, name)
+        db = sqlite3.connect(path)
+        rows = list(db.execute(G["event_get"]["sql"].format(table=st.event_table(bucket)), (0,)))
+        db.close()
+        assert sorted((r[0], r[1], r[2], r[3]) for r in rows) == sorted(model.rows) and len(rows) > 10
+    sy = st.syncer("model_bad")
+    with pytest.raises(g.GpudError):
+        st.syncer_configure_component(sy, "no-such-component")

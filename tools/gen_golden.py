@@ -505,6 +505,38 @@ def main():
     sql["table_names"] = {"src": "pkg/eventstore/database_test.go:%d" % line, "rows": tn}
     dump("store_sql.json", sql)
 
+    # ---- eventstore compareEvent / unmarshalIfValid tables + infiniband's kmsg dedup-window policy ----
+    es = {}
+    rows, src = table("pkg/eventstore/database_test.go", "TestCompareEvent")
+    mp = lambda v: v if isinstance(v, dict) else {}                # `map[string]string{}` parses as an empty composite
+    es["compare_event"] = {"src": src, "rows": [{"name": r["name"], "a": mp(r["eventA"].get("ExtraInfo", {})), "b": mp(r["eventB"].get("ExtraInfo", {})), "expected": r["expected"]} for r in rows]}
+    rows, src = table("pkg/eventstore/database_test.go", "TestUnmarshalIfValid")
+    es["unmarshal_if_valid"] = {"src": src, "rows": [{"name": r["name"], "valid": r["data"].get("Valid", False), "string": r["data"].get("String", ""),
+                                                      "expected_error": r["expectedError"]} for r in rows]}
+    IBC = N + "infiniband/component_test.go"
+    ib_src = open(os.path.join(REF, IBC)).read()
+    cs = consts(N + "infiniband/kmsg_matcher.go")
+    durs = {}
+    for m in re.finditer(r"^\s*(default\w+DedupWindow)\s*=\s*(\d+)\s*\*\s*time\.(Minute|Hour)\s*$", open(os.path.join(REF, N + "infiniband/component.go")).read(), re.M):
+        durs[m.group(1)] = int(m.group(2)) * {"Minute": 60, "Hour": 3600}[m.group(3)]
+    dw = []
+    for fm in re.finditer(r"^func (TestComponentKmsgEventDedupWindow_\w+)\(", ib_src, re.M):
+        body, line = find_func(ib_src, fm.group(1))
+        def expr(e):
+            val = ""
+            for tok in re.findall(r'"(?:[^"\\]|\\.)*"|\w+', e):
+                val += bytes(tok[1:-1], "utf-8").decode("unicode_escape") if tok.startswith('"') else cs[tok]["value"]
+            return val
+        name = expr(re.search(r"Name:\s*(.+?),\s*\n", body).group(1))
+        msg = expr(re.search(r"Message:\s*(.+?),\s*\n", body).group(1))
+        if "assert.False(t, ok)" in body:
+            ok, win = False, 0
+        else:
+            ok, win = True, durs[re.search(r"assert\.Equal\(t, (default\w+), dedupWindow\)", body).group(1)]
+        dw.append({"name": fm.group(1), "event": name, "message": msg, "ok": ok, "window_seconds": win, "line": line})
+    es["infiniband_dedup_window"] = {"src": IBC, "rows": dw, "constants": durs}
+    dump("eventstore_cases.json", es)
+
     # ---- fabric GetIssues / getHealthMaskIssues tables (pkg/nvidia/nvml/device/fabric_state_test.go) ----
     # the nvml.* constants are go-nvml's (v0.13.0-1, go.mod:6), i.e. nvml.h's published values
     NV = {"GPU_FABRIC_STATE_NOT_SUPPORTED": 0, "GPU_FABRIC_STATE_NOT_STARTED": 1, "GPU_FABRIC_STATE_IN_PROGRESS": 2, "GPU_FABRIC_STATE_COMPLETED": 3,
