@@ -14,13 +14,13 @@ $(SRC)/%.o: $(SRC)/%.cu $(SRC)/internal.h $(SRC)/catalog.h include/gpud_b200.h
 $(SRC)/catalog.o: $(SRC)/catalog.cpp $(SRC)/catalog.h $(SRC)/catalog_data.inc include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
-$(SRC)/host_component.o: $(SRC)/host_component.cpp $(SRC)/host_component.h include/gpud_b200.h
+$(SRC)/host_component.o: $(SRC)/host_component.cpp $(SRC)/host_component.h $(SRC)/json_min.h include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
 $(SRC)/poller.o: $(SRC)/poller.cpp $(SRC)/internal.h include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
 
-$(SRC)/store_sqlite.o: $(SRC)/store_sqlite.cpp include/gpud_b200.h
+$(SRC)/store_sqlite.o: $(SRC)/store_sqlite.cpp $(SRC)/json_min.h include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
 $(SRC)/kmsg_stateful.o: $(SRC)/kmsg_stateful.cpp include/gpud_b200.h

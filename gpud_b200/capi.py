@@ -57,6 +57,33 @@ class Metric(C.Structure):
     _fields_ = [("unix_ms", C.c_int64), ("component", C.c_char_p), ("name", C.c_char_p), ("labels_json", C.c_char_p), ("value", C.c_double)]
 
 
+def xid_detail(xid: int, sub_code: int = 0, error_status: int = 0):
+    """getDetailWithSubCodeAndStatus -> None or dict(event_type, actions (None = nil), description, sub_code)"""
+    ev, na, var, sc = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    acts = (C.c_int32 * 4)()
+    L = lib()
+    if not L.gpud_xid_detail(xid, sub_code, error_status, C.byref(ev), C.byref(na), acts, C.byref(var), C.byref(sc)):
+        return None
+    return {"event_type": ev.value, "actions": None if na.value < 0 else [acts[i] for i in range(na.value)],
+            "description": L.gpud_xid_description(xid, var.value).decode("utf-8"), "sub_code": sc.value}
+
+
+def xid_build_message(xid: int, sub_code: int = 0, error_status: int = 0, description: str = "", device_uuid: str = "", gpu_uuid: str = "") -> str:
+    buf = C.create_string_buffer(1024)
+    n = lib().gpud_xid_build_message(xid, sub_code, error_status, description.encode(), device_uuid.encode(), gpu_uuid.encode() if gpu_uuid else None, buf, 1024)
+    if n < 0:
+        raise GpudError(n, "gpud_xid_build_message")
+    return buf.value.decode("utf-8")
+
+
+def xid_hit_message(hit, gpu_uuid: str = "") -> str:
+    buf = C.create_string_buffer(1024)
+    n = lib().gpud_xid_hit_message(C.byref(hit), gpu_uuid.encode() if gpu_uuid else None, buf, 1024)
+    if n < 0:
+        raise GpudError(n, "gpud_xid_hit_message")
+    return buf.value.decode("utf-8")
+
+
 class DedupRule(C.Structure):
     _fields_ = [("event", C.c_char * 32), ("message_contains", C.c_char * 32), ("window_seconds", C.c_int64)]
 
@@ -250,7 +277,7 @@ SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destr
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
            "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
-           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
+           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
@@ -299,7 +326,11 @@ def lib() -> C.CDLL:
         "gpud_hit_detail_json": (i32, [C.POINTER(XidHit), i64, C.c_char_p, i32]),
         "gpud_xid_description": (C.c_char_p, [i32, i32]), "gpud_xid_mnemonic": (C.c_char_p, [i32]),
         "gpud_sxid_name": (C.c_char_p, [i32]), "gpud_nvlink_rule_hint": (C.c_char_p, [i32]),
-        "gpud_sxid_reason": (i32, [i64, C.c_char_p, vp, i32]), "gpud_kmsg_event_name": (C.c_char_p, [i32]), "gpud_kmsg_event_message": (C.c_char_p, [i32]),
+        "gpud_sxid_reason": (i32, [i64, C.c_char_p, vp, i32]),
+        "gpud_xid_get_detail": (i32, [i32, vp, vp, vp]),
+        "gpud_xid_detail": (i32, [i32, i32, C.c_uint32, vp, vp, vp, vp, vp]),
+        "gpud_xid_build_message": (i32, [C.c_uint64, i32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p, vp, i32]),
+        "gpud_xid_hit_message": (i32, [C.POINTER(XidHit), C.c_char_p, vp, i32]), "gpud_xid_device_matches_bus_id": (i32, [C.c_char_p, C.c_char_p]), "gpud_kmsg_event_name": (C.c_char_p, [i32]), "gpud_kmsg_event_message": (C.c_char_p, [i32]),
         "gpud_kmsg_component": (C.c_char_p, [i32]), "gpud_kmsg_hit_message": (i32, [vp, vp, vp, i32]),
         "gpud_kmsg_stateful_create": (i32, [vp]), "gpud_kmsg_stateful_destroy": (None, [vp]),
         "gpud_kmsg_stateful_feed": (i32, [vp, vp, i64, vp, i64, vp, i32, vp]),
@@ -402,6 +433,9 @@ class Context:
         if rc:
             raise GpudError(rc, "gpud_hit_detail_json")
         return buf.value.decode("utf-8")
+
+    def hit_message(self, hit: XidHit, gpu_uuid: str = "") -> str:
+        return xid_hit_message(hit, gpu_uuid)
 
     def ib_scan(self, series, drop_threshold: int, flap_down_interval: int, flap_back_threshold: int, dev: Optional[int] = None):
         """series: list of lists of (ts, down, total_link_downed); returns one IbVerdict per series"""

@@ -348,6 +348,98 @@ extern "C" int32_t gpud_sxid_reason(int64_t sxid, const char* device, char* out,
   return n < cap ? n : -1;
 }
 
+// GetDetail (xid/xid.go:74-77): the base catalog entry
+extern "C" int32_t gpud_xid_get_detail(int32_t xid, int32_t* event_type, int32_t* n_actions, int32_t* actions4) {
+  const gpud_tables* T = gpud_host_tables();
+  if (xid < 0 || xid >= GPUD_T_MAX_XID || !T->xid[xid].present) return 0;
+  const gpud_t_detail& d = T->xid[xid];
+  if (event_type) *event_type = d.event;
+  if (n_actions) *n_actions = d.n_actions;
+  if (actions4) for (int i = 0; i < 4; ++i) actions4[i] = i < d.n_actions ? d.actions[i] : 0;
+  return 1;
+}
+
+// getDetailWithSubCodeAndStatus (xid/xid.go:97-107) with its fallbacks getDetailWithSubCode (:79-93) and GetDetail (:74-77), over
+// the merged sub-code tables buildNVLinkSubCodeDetails made: 1 = found.  n_actions -1 = SuggestedActionsByGPUd nil;
+// detail_variant selects the description (gpud_xid_description); sub_code_out = the Detail's SubCode.
+extern "C" int32_t gpud_xid_detail(int32_t xid, int32_t sub_code, uint32_t error_status, int32_t* event_type, int32_t* n_actions, int32_t* actions4,
+                                   int32_t* detail_variant, int32_t* sub_code_out) {
+  const gpud_tables* T = gpud_host_tables();
+  const gpud_t_detail* d = nullptr;
+  int variant = 0, sc_out = 0;
+  if (xid >= 0 && xid < GPUD_T_MAX_XID) {
+    for (int i = 0; i < T->n_by_status && !d; ++i)
+      if (T->by_status[i].xid == xid && T->by_status[i].sub_code == sub_code && T->by_status[i].error_status == error_status) {
+        d = &T->by_status[i].d; variant = T->by_status[i].variant; sc_out = sub_code;
+      }
+    if (!d && T->has_sub_map[xid]) {
+      for (int pass = 0; pass < 2 && !d; ++pass) {
+        const int want = pass == 0 ? sub_code : 0;
+        for (int i = 0; i < T->n_by_sub && !d; ++i)
+          if (T->by_sub[i].xid == xid && T->by_sub[i].sub_code == want) { d = &T->by_sub[i].d; variant = T->by_sub[i].variant; sc_out = want; }
+      }
+    }
+    if (!d && T->xid[xid].present) d = &T->xid[xid];
+  }
+  if (!d) return 0;
+  if (event_type) *event_type = d->event;
+  if (n_actions) *n_actions = d->n_actions;
+  if (actions4) for (int i = 0; i < 4; ++i) actions4[i] = i < d->n_actions ? d->actions[i] : 0;
+  if (detail_variant) *detail_variant = variant;
+  if (sub_code_out) *sub_code_out = sc_out;
+  return 1;
+}
+
+// (*xidErrorEventDetail).buildMessage (xid/health_state.go:130-169): the Message of a resolved xid event and the Reason of the
+// component's health state.  NVLink codes 144-150 always carry the dotted sub-code and the error status; the text is the catalog
+// mnemonic, followed by the description unless that is empty, "Unused" or the mnemonic itself; without a mnemonic the
+// description alone.  gpu_uuid = what convertBusIDToUUID found ("" / NULL: none).  Returns the length, -1 if it does not fit.
+extern "C" int32_t gpud_xid_build_message(uint64_t xid, int32_t sub_code, uint32_t error_status, const char* description, const char* device_uuid,
+                                          const char* gpu_uuid, char* out, int32_t cap) {
+  if (!out || cap <= 0) return -1;
+  const char* dev = device_uuid ? device_uuid : "";
+  const char* descr = description ? description : "";
+  char header[96];
+  if (xid >= 144 && xid <= 150) snprintf(header, sizeof header, "XID %llu.%d (err status 0x%08x)", (unsigned long long)xid, sub_code, error_status);
+  else snprintf(header, sizeof header, "XID %llu", (unsigned long long)xid);
+  std::string o = header;
+  if (xid > (uint64_t)INT64_MAX) {                                   // intFromUint64 fails (xid/convert.go): no catalog lookup
+    o += " detected on GPU ";
+    o += dev;
+  } else {
+    std::string desc = xid <= 0x7fffffff ? gpud_xid_mnemonic((int32_t)xid) : "";
+    if (desc.empty()) desc = descr;
+    else if (descr[0] && strcmp(descr, "Unused") != 0 && desc != descr) { desc += " "; desc += descr; }
+    o += " " + desc + " detected on GPU " + dev;
+    if (gpu_uuid && *gpu_uuid) { o += " UUID:"; o += gpu_uuid; }
+  }
+  if ((int)o.size() + 1 > cap) return -1;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return (int32_t)o.size();
+}
+
+// buildMessage for the payload the xid component persists for this hit (xid/component.go:503-521: sub-code, error status and
+// description of Match's Detail).
+extern "C" int32_t gpud_xid_hit_message(const gpud_xid_hit* h, const char* gpu_uuid, char* out, int32_t cap) {
+  if (!h || h->kind != GPUD_KIND_XID) return -1;
+  const bool ext = (h->flags & GPUD_HIT_EXTENDED) != 0;
+  char dev[sizeof h->device + 1];
+  memcpy(dev, h->device, sizeof h->device);
+  dev[sizeof h->device] = 0;
+  return gpud_xid_build_message((uint64_t)h->code, ext ? h->sub_code : 0, ext ? h->error_status : 0u, gpud_xid_description(h->code, h->detail_variant), dev,
+                                gpu_uuid, out, cap);
+}
+
+// The test inside convertBusIDToUUID (xid/health_state.go:171-182): does the NVML device with this PCI bus id ("0000:04:00.0")
+// belong to the device id of an xid event ("PCI:0000:04:00")?
+extern "C" int32_t gpud_xid_device_matches_bus_id(const char* device_uuid, const char* pci_bus_id) {
+  if (!device_uuid || !pci_bus_id) return 0;
+  std::string want = device_uuid;
+  if (want.compare(0, 4, "PCI:") == 0) want.erase(0, 4);
+  want += ".";
+  return strncmp(pci_bus_id, want.c_str(), want.size()) == 0 ? 1 : 0;
+}
+
 // setNVLinkSuggestedActions (nvlink/evaluate_threshold.go:37-52) + peerNVLinkStatusesSuggestReboot (component.go:398-415): does an
 // unhealthy verdict come with RepairActionTypeRebootSystem?
 extern "C" int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v) {

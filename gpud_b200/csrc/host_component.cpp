@@ -1,5 +1,6 @@
 // host_component.cpp — see host_component.h.  Every function cites the reference code it mirrors.
 #include "host_component.h"
+#include "json_min.h"
 
 #include <string.h>
 
@@ -153,6 +154,7 @@ EvolveResult evolve_healthy_state(const std::vector<XidEventView>& ev, int reboo
       last_health = cur;
       r.has_xid = true;
       r.xid = it->xid;
+      r.last_index = (int)(ev.rend() - it) - 1;
       if (it->has_actions && !it->actions.empty()) {
         std::vector<int32_t> acts = it->actions;
         if (acts[0] == GPUD_ACT_REBOOT_SYSTEM) {
@@ -171,12 +173,189 @@ EvolveResult evolve_healthy_state(const std::vector<XidEventView>& ev, int reboo
         r.actions.clear();
         r.has_xid = false;
         r.xid = 0;
+        r.last_index = -1;
       }
       for (auto& kv : reboot_map) kv.second += 1;
     }
   }
   r.health = last_health == 2 ? Health::Unhealthy : (last_health == 1 ? Health::Degraded : Health::Healthy);
   return r;
+}
+
+// ---- stored xid events: payload, resolve, message ----
+static bool parse_actions_object(const char*& p, XidPayload* out) {      // {"repair_actions":[...]} | null
+  jsonmin::ws(p);
+  if (!strncmp(p, "null", 4)) { p += 4; return true; }
+  if (*p != '{') return false;
+  ++p;
+  out->has_actions = true;
+  jsonmin::ws(p);
+  if (*p == '}') { ++p; return true; }
+  for (;;) {
+    std::string k;
+    jsonmin::ws(p);
+    if (!jsonmin::string(p, &k)) return false;
+    jsonmin::ws(p);
+    if (*p++ != ':') return false;
+    jsonmin::ws(p);
+    if (k == "repair_actions" && *p == '[') {
+      ++p;
+      jsonmin::ws(p);
+      if (*p == ']') ++p;
+      else for (;;) {
+        std::string a;
+        jsonmin::ws(p);
+        if (!jsonmin::string(p, &a)) return false;
+        int id = 0;                                                    // an unknown action string stays in the list as itself in Go; 0 here
+        for (int i = 1; i <= 4; ++i) if (a == repair_action_string(i)) id = i;
+        out->actions.push_back(id);
+        jsonmin::ws(p);
+        if (*p == ',') { ++p; continue; }
+        if (*p == ']') { ++p; break; }
+        return false;
+      }
+    } else if (!jsonmin::skip(p)) return false;
+    jsonmin::ws(p);
+    if (*p == ',') { ++p; continue; }
+    if (*p == '}') { ++p; return true; }
+    return false;
+  }
+}
+
+static bool parse_uint(const char*& p, uint64_t* v) {
+  if (*p < '0' || *p > '9') return false;
+  uint64_t x = 0;
+  while (*p >= '0' && *p <= '9') {
+    if (x > (UINT64_MAX - (uint64_t)(*p - '0')) / 10) return false;
+    x = x * 10 + (uint64_t)(*p++ - '0');
+  }
+  if (*p == '.' || *p == 'e' || *p == 'E') return false;               // encoding/json refuses a non-integer for an integer field
+  *v = x;
+  return true;
+}
+
+static bool parse_xid_payload(const std::string& raw, XidPayload* out) {   // json.Unmarshal([]byte(rawData), &xidErr) == nil
+  *out = XidPayload();
+  const char* p = raw.c_str();
+  jsonmin::ws(p);
+  if (*p != '{') return false;
+  ++p;
+  jsonmin::ws(p);
+  if (*p == '}') { ++p; jsonmin::ws(p); return *p == 0; }
+  for (;;) {
+    std::string k;
+    jsonmin::ws(p);
+    if (!jsonmin::string(p, &k)) return false;
+    jsonmin::ws(p);
+    if (*p++ != ':') return false;
+    jsonmin::ws(p);
+    uint64_t u = 0;
+    if (!strncmp(p, "null", 4) && k != "suggested_actions_by_gpud") p += 4;                 // null leaves the zero value
+    else if (k == "xid") { if (!parse_uint(p, &u)) return false; out->xid = u; }
+    else if (k == "sub_code") {
+      const bool neg = *p == '-';
+      if (neg) ++p;
+      if (!parse_uint(p, &u) || u > 0x7fffffffu) return false;
+      out->sub_code = neg ? -(int32_t)u : (int32_t)u;
+    }
+    else if (k == "error_status") { if (!parse_uint(p, &u) || u > 0xffffffffull) return false; out->error_status = (uint32_t)u; }
+    else if (k == "device_uuid") { if (!jsonmin::string(p, &out->device_uuid)) return false; }
+    else if (k == "sub_code_description") { if (!jsonmin::string(p, &out->sub_code_description)) return false; }
+    else if (k == "description") { if (!jsonmin::string(p, &out->description)) return false; }
+    else if (k == "suggested_actions_by_gpud") { if (!parse_actions_object(p, out)) return false; }
+    else if (!jsonmin::skip(p)) return false;                                              // time, data_source, investigatory_hint, unknown keys
+    jsonmin::ws(p);
+    if (*p == ',') { ++p; continue; }
+    if (*p == '}') { ++p; break; }
+    return false;
+  }
+  jsonmin::ws(p);
+  return *p == 0;
+}
+
+std::string convert_bus_id_to_uuid(const std::string& bus_id, const DeviceMap& devices) {
+  for (const auto& kv : devices)
+    if (gpud_xid_device_matches_bus_id(bus_id.c_str(), kv.second.c_str())) return kv.first;
+  return "";
+}
+
+std::string xid_payload_message(const XidPayload& p, const DeviceMap& devices) {
+  char buf[1536];
+  const std::string uuid = convert_bus_id_to_uuid(p.device_uuid, devices);
+  const int n = gpud_xid_build_message(p.xid, p.sub_code, p.error_status, p.description.c_str(), p.device_uuid.c_str(), uuid.c_str(), buf, sizeof buf);
+  return n >= 0 ? std::string(buf, (size_t)n) : std::string("unknown");
+}
+
+bool resolve_xid_event(std::string* type, const std::string& raw, const std::string& event_device_uuid, const DeviceMap& devices, XidPayload* out,
+                       std::string* message) {
+  XidPayload p;
+  if (!parse_xid_payload(raw, &p) || p.xid == 0) {
+    // legacy rows: only the decimal code (strconv.Atoi), the device in ExtraInfo["device_uuid"]
+    const char* q = raw.c_str();
+    bool neg = false;
+    if (*q == '+' || *q == '-') { neg = *q == '-'; ++q; }
+    uint64_t u = 0;
+    const char* q0 = q;
+    while (*q >= '0' && *q <= '9' && u < (1ull << 40)) u = u * 10 + (uint64_t)(*q++ - '0');
+    if (q == q0 || *q != 0 || neg || u > 0x7fffffffu) return false;
+    int32_t n_act = -1, acts[4] = {0, 0, 0, 0};
+    if (!gpud_xid_get_detail((int32_t)u, nullptr, &n_act, acts)) return false;          // GetDetail(currXid), the base entry (:203)
+    p = XidPayload();
+    p.xid = u;
+    p.device_uuid = event_device_uuid;
+    p.has_actions = n_act >= 0;
+    for (int i = 0; i < n_act; ++i) p.actions.push_back(acts[i]);
+  }
+  // addEventDetails (:222-281)
+  if (p.xid <= (uint64_t)INT64_MAX) {
+    int32_t ev = 0, n_act = -1, acts[4] = {0, 0, 0, 0}, variant = 0, sc = 0;
+    const bool found = p.xid <= 0x7fffffffu && p.sub_code >= 0 && gpud_xid_detail((int32_t)p.xid, p.sub_code, p.error_status, &ev, &n_act, acts, &variant, &sc);
+    if (found) {
+      if (type->empty() && ev != GPUD_EVENT_UNKNOWN) *type = event_type_string(ev);
+      if (p.description.empty()) p.description = gpud_xid_description((int32_t)p.xid, variant);
+      if (p.sub_code == 0) p.sub_code = sc;
+      if (!p.has_actions && n_act >= 0) { p.has_actions = true; p.actions.assign(acts, acts + n_act); }
+      // SubCodeDescription is not part of any message or decision; the merged tables keep the unit only in the reference's Detail
+    } else if (type->empty()) {
+      *type = "Unknown";
+    }
+  } else {
+    return false;                                                      // intFromUint64 fails: the event is returned unchanged
+  }
+  if (message) *message = xid_payload_message(p, devices);
+  *out = p;
+  return true;
+}
+
+StoredEvolveResult evolve_stored_events(const std::vector<Event>& events, const DeviceMap& devices, int reboot_threshold) {
+  std::vector<XidEventView> views;
+  std::vector<XidPayload> payloads;
+  for (const Event& e : events) {
+    XidEventView v;
+    v.name = e.name;
+    XidPayload p;
+    if (e.name == "error_xid") {
+      std::string type = e.type;
+      auto it = e.extra_info.find("data");
+      auto dv = e.extra_info.find("device_uuid");
+      if (!resolve_xid_event(&type, it == e.extra_info.end() ? std::string() : it->second, dv == e.extra_info.end() ? std::string() : dv->second, devices, &p,
+                             nullptr))
+        continue;                                                      // unmarshal of the unresolved payload fails -> skipped (:71-74)
+      v.type = type;
+      v.xid = p.xid;
+      v.has_actions = p.has_actions;
+      v.actions = p.actions;
+    }
+    views.push_back(v);
+    payloads.push_back(p);
+  }
+  const EvolveResult r = evolve_healthy_state(views, reboot_threshold, "error_xid");
+  StoredEvolveResult out;
+  out.health = r.health;
+  out.has_actions = r.has_actions;
+  out.actions = r.actions;
+  out.reason = (r.has_xid && r.last_index >= 0) ? xid_payload_message(payloads[(size_t)r.last_index], devices) : "XIDComponent is healthy";
+  return out;
 }
 
 std::vector<Event> trim_events_after_set_healthy(const std::vector<Event>& e) {   // component.go:630-642
@@ -328,38 +507,11 @@ int32_t XidComponent::IngestHits(const std::vector<gpud_xid_hit>& hits, int64_t 
 void XidComponent::update_state() {                // component.go:581-611
   std::vector<Event> local = trim_events_after_set_healthy(bucket_.get(0));
   std::vector<Event> all = merge_events(reboots_.get(0), local);
-  std::vector<XidEventView> views;
-  for (const Event& e : all) {
-    XidEventView v;
-    v.name = e.name;
-    v.type = e.type;
-    auto it = e.extra_info.find("data");
-    if (it != e.extra_info.end()) {
-      // the payload is our own rendering: pull xid and the first-listed actions back out
-      const std::string& d = it->second;
-      const size_t px = d.find("\"xid\":");
-      if (px != std::string::npos) v.xid = strtoull(d.c_str() + px + 6, nullptr, 10);
-      size_t pa = d.find("\"repair_actions\":[");
-      if (pa != std::string::npos) {
-        v.has_actions = true;
-        pa += 18;
-        while (pa < d.size() && d[pa] != ']') {
-          if (d[pa] == '"') {
-            const size_t e2 = d.find('"', pa + 1);
-            const std::string a = d.substr(pa + 1, e2 - pa - 1);
-            for (int id = 1; id <= 4; ++id) if (a == repair_action_string(id)) v.actions.push_back(id);
-            pa = e2 + 1;
-          } else ++pa;
-        }
-      }
-    }
-    views.push_back(v);
-  }
-  const EvolveResult r = evolve_healthy_state(views, reboot_threshold_, "error_xid");
+  const StoredEvolveResult r = evolve_stored_events(all, devices_, reboot_threshold_);
   cur_.health = r.health;
   cur_.has_actions = r.has_actions;
   cur_.actions.repair_actions = r.actions;
-  cur_.reason = r.has_xid ? ("XID " + std::to_string(r.xid) + " detected") : "XIDComponent is healthy";
+  cur_.reason = r.reason;
 }
 
 std::vector<HealthState> XidComponent::LastHealthStates() {     // types.go:55-58
@@ -460,6 +612,62 @@ static int32_t evolve_flat(const gpudh_event* ev, int32_t n, int32_t reboot_thre
   *health = (int32_t)r.health;
   *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
   *xid = r.has_xid ? r.xid : 0;
+  return 0;
+}
+
+static gpud::DeviceMap parse_devices(const char* spec) {     // "uuid=busid;uuid=busid"
+  gpud::DeviceMap m;
+  std::string s = spec ? spec : "";
+  size_t a = 0;
+  while (a < s.size()) {
+    size_t e = s.find(';', a);
+    if (e == std::string::npos) e = s.size();
+    const size_t q = s.find('=', a);
+    if (q != std::string::npos && q < e) m[s.substr(a, q - a)] = s.substr(q + 1, e - q - 1);
+    a = e + 1;
+  }
+  return m;
+}
+// resolveXIDEvent for one stored event: 1 resolved (type_out / message_out filled), 0 left as is
+int32_t gpudh_resolve_xid_event(const char* type_in, const char* raw, const char* device_uuid, const char* devices, char* type_out, int32_t tcap, char* msg_out,
+                                int32_t mcap, int32_t* n_actions, int32_t* actions4) {
+  std::string type = type_in ? type_in : "", msg;
+  gpud::XidPayload p;
+  if (!gpud::resolve_xid_event(&type, raw ? raw : "", device_uuid ? device_uuid : "", parse_devices(devices), &p, &msg)) return 0;
+  snprintf(type_out, (size_t)tcap, "%s", type.c_str());
+  snprintf(msg_out, (size_t)mcap, "%s", msg.c_str());
+  *n_actions = p.has_actions ? (int32_t)p.actions.size() : -1;
+  for (int i = 0; i < 4; ++i) actions4[i] = i < (int)p.actions.size() ? p.actions[(size_t)i] : 0;
+  return 1;
+}
+// evolveHealthyState over stored events; events = records "name\x1ftype\x1fdevice_uuid\x1fdata" joined by \x1e, newest first
+int32_t gpudh_evolve_stored(const char* events, const char* devices, int32_t reboot_threshold, int32_t* health, int32_t* action, char* reason, int32_t cap) {
+  std::vector<gpud::Event> evs;
+  std::string s = events ? events : "";
+  size_t a = 0;
+  while (a < s.size()) {
+    size_t e = s.find('\x1e', a);
+    if (e == std::string::npos) e = s.size();
+    const std::string rec = s.substr(a, e - a);
+    std::vector<std::string> f;
+    size_t b = 0;
+    for (;;) {
+      const size_t q = rec.find('\x1f', b);
+      f.push_back(rec.substr(b, q == std::string::npos ? std::string::npos : q - b));
+      if (q == std::string::npos) break;
+      b = q + 1;
+    }
+    f.resize(4);
+    gpud::Event ev;
+    ev.name = f[0]; ev.type = f[1];
+    if (ev.name == "error_xid") { ev.extra_info["device_uuid"] = f[2]; ev.extra_info["data"] = f[3]; }
+    evs.push_back(ev);
+    a = e + 1;
+  }
+  const gpud::StoredEvolveResult r = gpud::evolve_stored_events(evs, parse_devices(devices), reboot_threshold);
+  *health = (int32_t)r.health;
+  *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
+  snprintf(reason, (size_t)cap, "%s", r.reason.c_str());
   return 0;
 }
 

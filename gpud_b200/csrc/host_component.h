@@ -67,8 +67,29 @@ class EventBucket {
 };
 
 // ---- xid health evolution (health_state.go:57-128; component.go:614-642) ----
+// xidErrorEventDetail (xid/health_state.go:284-315) as read back from a stored event's "data" payload
+struct XidPayload {
+  uint64_t xid = 0;
+  int32_t sub_code = 0;
+  uint32_t error_status = 0;
+  std::string device_uuid, sub_code_description, description;
+  bool has_actions = false;                     // SuggestedActionsByGPUd != nil
+  std::vector<int32_t> actions;
+};
+typedef std::map<std::string, std::string> DeviceMap;     // NVML UUID -> PCIBusID() ("0000:04:00.0")
+// resolveXIDEvent + addEventDetails (xid/health_state.go:184-281): JSON payload (xid != 0) or the legacy decimal code; fills the
+// fields the catalog Detail supplies, sets *type when it was "", renders *message with buildMessage.  false = the reference
+// leaves the event unresolved (evolveHealthyState then skips it).
+bool resolve_xid_event(std::string* type, const std::string& raw_data, const std::string& event_device_uuid, const DeviceMap& devices, XidPayload* out,
+                       std::string* message);
+std::string convert_bus_id_to_uuid(const std::string& bus_id, const DeviceMap& devices);      // health_state.go:171-182
+std::string xid_payload_message(const XidPayload& p, const DeviceMap& devices);               // buildMessage, :130-169
+struct StoredEvolveResult { Health health = Health::Healthy; bool has_actions = false; std::vector<int32_t> actions; std::string reason; };
+// evolveHealthyState over stored events, newest first (health_state.go:57-128), reason included
+StoredEvolveResult evolve_stored_events(const std::vector<Event>& events_newest_first, const DeviceMap& devices, int reboot_threshold);
+
 struct XidEventView { std::string name; std::string type; uint64_t xid = 0; bool has_actions = false; std::vector<int32_t> actions; };
-struct EvolveResult { Health health = Health::Healthy; bool has_actions = false; std::vector<int32_t> actions; bool has_xid = false; uint64_t xid = 0; };
+struct EvolveResult { Health health = Health::Healthy; bool has_actions = false; std::vector<int32_t> actions; bool has_xid = false; uint64_t xid = 0; int last_index = -1; /* index into the input of the event that is lastXidErr */ };
 EvolveResult evolve_healthy_state(const std::vector<XidEventView>& events_newest_first, int reboot_threshold);
 std::vector<Event> trim_events_after_set_healthy(const std::vector<Event>& events_newest_first);     // component.go:630-642
 std::vector<Event> merge_events(const std::vector<Event>& a, const std::vector<Event>& b);           // component.go:614-628
@@ -117,6 +138,7 @@ class XidComponent : public Component {
   XidComponent(gpud_ctx* ctx, int32_t dev, bool row_remapping_supported, int reboot_threshold = 2);
   void SetKmsgSource(std::string buffer, bool raw_kmsg, int64_t boot_unix) { buf_ = std::move(buffer); raw_ = raw_kmsg; boot_unix_ = boot_unix; }
   void AddRebootEvent(int64_t unix_seconds);
+  void SetDevices(DeviceMap devices) { std::lock_guard<std::mutex> g(mu_); devices_ = std::move(devices); }   // nvmlInstance.Devices() for the UUID in the reason
   std::string Name() const override { return kName; }
   std::vector<std::string> Tags() const override { return {"accelerator", "gpu", "nvidia", kName}; }
   bool IsSupported() const override { return ctx_ != nullptr; }
@@ -138,6 +160,7 @@ class XidComponent : public Component {
   int64_t boot_unix_ = 0;
   std::mutex mu_;
   EventBucket bucket_, reboots_;
+  DeviceMap devices_;
   HealthState cur_;
   bool checked_ = false;
 };

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/gpud_b200.h"
+#include "json_min.h"
 
 namespace {
 
@@ -156,85 +157,29 @@ extern "C" int32_t gpud_store_event_table(gpud_store* st, const char* component,
 // ExtraInfo as the reference reads it back (database.go:428-447 scanRows + :471-482 unmarshalIfValid into map[string]string):
 // NULL, "" and "null" are no map at all; anything else must be one JSON object of string values (a null value leaves "").
 // Returns false where json.Unmarshal would fail -- the reference's findEvent then returns that error.
-static void utf8_put(std::string& o, uint32_t c) {
-  if (c < 0x80) o += (char)c;
-  else if (c < 0x800) { o += (char)(0xC0 | (c >> 6)); o += (char)(0x80 | (c & 63)); }
-  else if (c < 0x10000) { o += (char)(0xE0 | (c >> 12)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
-  else { o += (char)(0xF0 | (c >> 18)); o += (char)(0x80 | ((c >> 12) & 63)); o += (char)(0x80 | ((c >> 6) & 63)); o += (char)(0x80 | (c & 63)); }
-}
-static bool json_ws(const char*& p) { while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p; return true; }
-static bool json_hex4(const char*& p, uint32_t* v) {
-  uint32_t x = 0;
-  for (int i = 0; i < 4; ++i, ++p) {
-    const char c = *p;
-    if (c >= '0' && c <= '9') x = x * 16 + (uint32_t)(c - '0');
-    else if (c >= 'a' && c <= 'f') x = x * 16 + (uint32_t)(c - 'a' + 10);
-    else if (c >= 'A' && c <= 'F') x = x * 16 + (uint32_t)(c - 'A' + 10);
-    else return false;
-  }
-  *v = x;
-  return true;
-}
-static bool json_string(const char*& p, std::string* out) {
-  if (*p != '"') return false;
-  ++p;
-  out->clear();
-  while (*p && *p != '"') {
-    if ((unsigned char)*p < 0x20) return false;
-    if (*p != '\\') { *out += *p++; continue; }
-    ++p;
-    switch (*p) {
-      case '"': *out += '"'; ++p; break;
-      case '\\': *out += '\\'; ++p; break;
-      case '/': *out += '/'; ++p; break;
-      case 'b': *out += '\b'; ++p; break;
-      case 'f': *out += '\f'; ++p; break;
-      case 'n': *out += '\n'; ++p; break;
-      case 'r': *out += '\r'; ++p; break;
-      case 't': *out += '\t'; ++p; break;
-      case 'u': {
-        ++p;
-        uint32_t c;
-        if (!json_hex4(p, &c)) return false;
-        if (c >= 0xD800 && c < 0xDC00 && p[0] == '\\' && p[1] == 'u') {       // surrogate pair; a lone half becomes U+FFFD like encoding/json
-          const char* q = p + 2;
-          uint32_t lo;
-          if (json_hex4(q, &lo) && lo >= 0xDC00 && lo < 0xE000) { c = 0x10000 + ((c - 0xD800) << 10) + (lo - 0xDC00); p = q; }
-          else c = 0xFFFD;
-        } else if (c >= 0xD800 && c < 0xE000) c = 0xFFFD;
-        utf8_put(*out, c);
-        break;
-      }
-      default: return false;
-    }
-  }
-  if (*p != '"') return false;
-  ++p;
-  return true;
-}
 static bool parse_extra_info(const char* text, std::map<std::string, std::string>* m) {
   m->clear();
   if (!text || !*text || !strcmp(text, "null")) return true;
   if (text[0] != '{') return false;
   const char* p = text + 1;
-  json_ws(p);
-  if (*p == '}') { ++p; json_ws(p); return *p == 0; }
+  jsonmin::ws(p);
+  if (*p == '}') { ++p; jsonmin::ws(p); return *p == 0; }
   for (;;) {
     std::string k, v;
-    json_ws(p);
-    if (!json_string(p, &k)) return false;
-    json_ws(p);
+    jsonmin::ws(p);
+    if (!jsonmin::string(p, &k)) return false;
+    jsonmin::ws(p);
     if (*p++ != ':') return false;
-    json_ws(p);
+    jsonmin::ws(p);
     if (!strncmp(p, "null", 4)) p += 4;
-    else if (!json_string(p, &v)) return false;
+    else if (!jsonmin::string(p, &v)) return false;
     (*m)[k] = v;
-    json_ws(p);
+    jsonmin::ws(p);
     if (*p == ',') { ++p; continue; }
     if (*p == '}') { ++p; break; }
     return false;
   }
-  json_ws(p);
+  jsonmin::ws(p);
   return *p == 0;
 }
 

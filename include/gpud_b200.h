@@ -239,6 +239,20 @@ const char* gpud_sxid_name(int32_t code);
 const char* gpud_nvlink_rule_hint(int32_t rule_index);
 /* Reason string of the sxid component's health state (sxid/health_state.go:93-106); sxid < 0 = healthy. Returns the length. */
 int32_t gpud_sxid_reason(int64_t sxid, const char* device, char* out, int32_t cap);
+/* getDetailWithSubCodeAndStatus (xid/xid.go:97-107; falls back to the sub-code table, sub-code 0, then GetDetail): 1 = found.
+ * event_type GPUD_EVENT_*, n_actions -1 = SuggestedActionsByGPUd nil, actions4[4] GPUD_ACT_*, detail_variant for
+ * gpud_xid_description, sub_code_out = the Detail's SubCode.  Any out pointer may be NULL. */
+int32_t gpud_xid_get_detail(int32_t xid, int32_t* event_type, int32_t* n_actions, int32_t* actions4);   /* GetDetail (xid/xid.go:74-77) */
+int32_t gpud_xid_detail(int32_t xid, int32_t sub_code, uint32_t error_status, int32_t* event_type, int32_t* n_actions, int32_t* actions4,
+                        int32_t* detail_variant, int32_t* sub_code_out);
+/* (*xidErrorEventDetail).buildMessage (xid/health_state.go:130-169): Message of a resolved xid event / Reason of the xid health
+ * state, e.g. "XID 149.37 (err status 0x00000000) NVLINK_NETIR_ERROR detected on GPU PCI:0000:04:00 UUID:GPU-..."; gpu_uuid is the
+ * NVML UUID convertBusIDToUUID resolved, or NULL.  _hit_ renders it for the payload gpud_hit_detail_json persists.  Return the
+ * length, -1 if `out` is too small.  gpud_xid_device_matches_bus_id: the prefix test of convertBusIDToUUID (:171-182). */
+int32_t gpud_xid_build_message(uint64_t xid, int32_t sub_code, uint32_t error_status, const char* description, const char* device_uuid,
+                               const char* gpu_uuid, char* out, int32_t cap);
+int32_t gpud_xid_hit_message(const gpud_xid_hit* hit, const char* gpu_uuid, char* out, int32_t cap);
+int32_t gpud_xid_device_matches_bus_id(const char* device_uuid, const char* pci_bus_id);
 /* kmsg.MatchFunc results (eventName, message) of the extra matchers, by hit kind; "" for xid / sxid kinds. */
 const char* gpud_kmsg_event_name(int32_t kind);
 const char* gpud_kmsg_event_message(int32_t kind);

@@ -768,18 +768,22 @@ def sxid_reason(sxid, device: str, name: str = "") -> str:
 
 
 def evolve_healthy_state(events, reboot_threshold: int = 2, event_name: str = "error_xid"):
-    """xid/health_state.go:57-128 ; the sxid twin (sxid/health_state.go:38-111) differs in the event name and the fixed threshold 2"""
+    """xid/health_state.go:57-128 ; the sxid twin (sxid/health_state.go:38-111) differs in the event name and the fixed threshold 2.
+    "last_index" = index into `events` of the event that ends up as lastXidErr (None: healthy reason)."""
     last_action = None
     last_xid = None
+    last_index = None
     last_health = 0
     reboot_map: Dict[int, int] = {}
-    for e in reversed(events):
+    for i in range(len(events) - 1, -1, -1):
+        e = events[i]
         if e["name"] == event_name:
             cur = {"Critical": 1, "Fatal": 2}.get(e.get("type", ""), 0)
             if cur < last_health:
                 continue
             last_health = cur
             last_xid = e["xid"]
+            last_index = i
             acts = e.get("actions")
             if acts:
                 acts = list(acts)
@@ -791,10 +795,106 @@ def evolve_healthy_state(events, reboot_threshold: int = 2, event_name: str = "e
                 last_action = acts[:1]
         elif e["name"] == "reboot":
             if last_action and last_action[0] in (ACT_REBOOT, ACT_CHECK_APP):
-                last_health, last_action, last_xid = 0, None, None
+                last_health, last_action, last_xid, last_index = 0, None, None, None
             for k in reboot_map:
                 reboot_map[k] += 1
-    return {"health": ["Healthy", "Degraded", "Unhealthy"][last_health], "actions": last_action, "xid": last_xid}
+    return {"health": ["Healthy", "Degraded", "Unhealthy"][last_health], "actions": last_action, "xid": last_xid, "last_index": last_index}
+
+
+def xid_build_message(xid: int, sub_code: int = 0, error_status: int = 0, description: str = "", device_uuid: str = "", gpu_uuid: str = "") -> str:
+    """(*xidErrorEventDetail).buildMessage (xid/health_state.go:130-169); gpu_uuid = the result of convertBusIDToUUID ("" none)"""
+    header = "XID %d" % xid
+    if 144 <= xid <= 150:
+        header = "XID %d.%d (err status 0x%08x)" % (xid, sub_code, error_status)
+    if xid > (1 << 63) - 1:                               # intFromUint64 fails
+        return "%s detected on GPU %s" % (header, device_uuid)
+    desc = MNEMONIC.get(xid, "")
+    if desc == "":
+        desc = description
+    elif description not in ("", "Unused") and desc != description:
+        desc += " " + description
+    gpu = "GPU %s" % device_uuid
+    if gpu_uuid:
+        gpu = "GPU %s UUID:%s" % (device_uuid, gpu_uuid)
+    return "%s %s detected on %s" % (header, desc, gpu)
+
+
+def convert_bus_id_to_uuid(bus_id: str, devices: Dict[str, str]) -> str:
+    """convertBusIDToUUID (xid/health_state.go:171-182); devices: NVML uuid -> PCIBusID()"""
+    want = (bus_id[4:] if bus_id.startswith("PCI:") else bus_id) + "."
+    for uuid, pci in devices.items():
+        if pci.startswith(want):
+            return uuid
+    return ""
+
+
+def resolve_xid_event(event_type: str, raw_data: str, device_uuid: str = "", devices: Optional[Dict[str, str]] = None):
+    """resolveXIDEvent + addEventDetails (xid/health_state.go:184-281) for the "data" payload of a stored error_xid event:
+    -> (type, message, payload dict) or None where the reference leaves the event unresolved.  The payload dict uses the JSON
+    keys of xidErrorEventDetail; "actions" is a list of ids or None."""
+    devices = devices or {}
+    p = None
+    try:
+        j = json.loads(raw_data)
+        if isinstance(j, dict) and int(j.get("xid", 0)) != 0:
+            acts = j.get("suggested_actions_by_gpud")
+            p = {"xid": int(j["xid"]), "device_uuid": j.get("device_uuid", ""), "sub_code": int(j.get("sub_code", 0)),
+                 "sub_code_description": j.get("sub_code_description", ""), "error_status": int(j.get("error_status", 0)),
+                 "description": j.get("description", ""),
+                 "actions": None if acts is None else [{v: k for k, v in ACTION_WIRE.items()}[a] for a in (acts.get("repair_actions") or [])]}
+    except (ValueError, TypeError):
+        p = None
+    if p is None:                                          # legacy rows keep only the decimal code
+        try:
+            code = go_atoi(raw_data.encode("utf-8"))
+        except ValueError:
+            return None
+        d = get_detail(code)
+        if d is None or code < 0:
+            return None
+        p = {"xid": code, "device_uuid": device_uuid, "sub_code": 0, "sub_code_description": "", "error_status": 0, "description": "",
+             "actions": None if d.actions is None else list(d.actions)}
+    typ = event_type
+    d = get_detail_with_sub_code_and_status(p["xid"], p["sub_code"], p["error_status"]) if p["xid"] <= (1 << 63) - 1 else None
+    if d is not None:
+        if typ == "" and d.event_type != EV_UNKNOWN:
+            typ = EVENT_NAMES[d.event_type]
+        if p["description"] == "":
+            p["description"] = d.description
+        if p["sub_code"] == 0:
+            p["sub_code"] = d.sub_code
+        if p["sub_code_description"] == "":
+            p["sub_code_description"] = d.sub_code_description
+        if p["actions"] is None and d.actions is not None:
+            p["actions"] = list(d.actions)
+    elif typ == "":
+        typ = "Unknown"
+    msg = xid_build_message(p["xid"], p["sub_code"], p["error_status"], p["description"], p["device_uuid"], convert_bus_id_to_uuid(p["device_uuid"], devices))
+    return typ, msg, p
+
+
+def evolve_healthy_state_stored(events, devices: Optional[Dict[str, str]] = None, reboot_threshold: int = 2):
+    """evolveHealthyState over STORED events (xid/health_state.go:57-128): events newest first, each
+    {"name", "type", "data": payload string, "device_uuid"}; resolves every error_xid event like the reference and returns
+    {"health", "actions", "reason"}."""
+    views, payloads = [], {}
+    for i, e in enumerate(events):
+        if e["name"] != "error_xid":
+            views.append({"name": e["name"]})
+            continue
+        r = resolve_xid_event(e.get("type", ""), e.get("data", ""), e.get("device_uuid", ""), devices)
+        if r is None:
+            continue                                       # json.Unmarshal of the unresolved payload fails -> the event is skipped (:71-74)
+        typ, _msg, p = r
+        payloads[i] = p
+        views.append({"name": "error_xid", "type": typ, "xid": p["xid"], "actions": p["actions"], "_i": i})
+    st = evolve_healthy_state(views, reboot_threshold)
+    reason = "XIDComponent is healthy"
+    if st["last_index"] is not None:
+        p = payloads[views[st["last_index"]]["_i"]]
+        reason = xid_build_message(p["xid"], p["sub_code"], p["error_status"], p["description"], p["device_uuid"],
+                                   convert_bus_id_to_uuid(p["device_uuid"], devices or {}))
+    return {"health": st["health"], "actions": st["actions"], "reason": reason}
 
 
 # --------------------------------------------------------------------------------------------

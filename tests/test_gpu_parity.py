@@ -64,6 +64,40 @@ def test_scan_each_golden_vector(ctx):
     assert [(h.code, h.device.decode()) for h in hits] == [(119, "PCI:0000:9b:00")] * 5
 
 
+def test_xid_hit_message_is_build_message_of_the_match(ctx):
+    """buildMessage (xid/health_state.go:130-169) for every hit of the golden lines, and the reference's own message tests that
+    start from a kmsg line (health_state_test.go:318-362, 363-412, 505-562, 564-690)"""
+    lines = synth.hit_lines() + synth.EDGE_LINES
+    buf = "\n".join(lines).encode()
+    hits, _ = ctx.kmsg_scan(buf)
+    n = 0
+    for h in hits:
+        if h.kind != 1:
+            continue
+        raw = buf.split(b"\n")[h.unit_index]
+        x = O.xid_match(raw)
+        if x is None:                                  # multi-line fallen-off-the-bus records are compared in the raw-mode tests
+            continue
+        d = x.detail
+        for uuid in ("", "GPU-test-uuid"):
+            assert g.xid_hit_message(h, uuid) == O.xid_build_message(x.xid, d.sub_code, d.error_status, d.description, x.device, uuid), raw
+        n += 1
+    assert n > 200
+    G = synth.golden("xid_messages.json")["from_lines"]
+    for r in G["rows"]:
+        hits, _ = ctx.kmsg_scan(r["line"].encode())
+        assert len(hits) == 1, r["name"]
+        h = hits[0]
+        uuid = O.convert_bus_id_to_uuid(h.device.decode(), r["devices"])
+        msg = g.xid_hit_message(h, uuid)
+        for c in r["contains"]:
+            assert c in msg, (r["name"], c, msg)
+        if "sub_code" in r:
+            assert ("%d.%d" % (h.code, r["sub_code"])) in msg
+        if "event_type" in r:
+            assert g.EVENT_NAMES[h.event_type] == r["event_type"]
+
+
 def test_scan_multiline_record_raw_mode(ctx):
     """the multiline fallen-off-the-bus vector only matches when the record is one unit (RAW_KMSG continuation lines)"""
     rec = b"4,1,5,-;NVRM: The NVIDIA GPU 0000:18:00.0\n NVRM: (PCI ID: 10de:2901) installed in this system has\n NVRM: fallen off the bus and is not responding to commands.\n"

@@ -252,16 +252,38 @@ def test_sxid_evolve_and_reason(golden):           # sxid/health_state_test.go:3
 
 
 def test_xid_evolve_extracted_scenarios(golden):   # xid/health_state_test.go:78-246, extracted by script
-    for r in golden("xid_health_extracted.json")["scenarios"]["rows"]:
-        if not r["events"] and "health" not in r:
-            continue
-        ev = [{"k": "xid", "xid": e["code"], "type": e["type"], "actions": [a for a in e["actions"]]} if e["k"] == "err" else {"k": "reboot"} for e in r["events"]]
-        oev = [{"name": "error_xid", "type": e["type"], "xid": e["xid"], "actions": [ACT_BY_GO[q] for q in e["actions"]]} if e["k"] == "xid" else {"name": "reboot"} for e in ev]
+    rows = golden("xid_health_extracted.json")["scenarios"]["rows"]
+    assert len(rows) == 10 and all("health" in r for r in rows)
+    for r in rows:
+        oev = [{"name": "error_xid", "type": e["type"], "xid": e["code"], "actions": None if e["actions"] is None else [ACT_BY_GO[q] for q in e["actions"]]}
+               if e["k"] == "err" else {"name": "reboot"} for e in r["events"]]
         o = O.evolve_healthy_state(oev, 2)
-        if "health" in r:
-            assert o["health"] == r["health"], r["name"]
+        assert o["health"] == r["health"], r["name"]
         if r.get("action"):
             assert o["actions"] and o["actions"][0] == ACT_BY_GO[r["action"]], r["name"]
+        if "action" in r and r["action"] is None:
+            assert o["actions"] is None
+        # the same scenario as STORED events: the payload createXidEvent / createXidEventWithNilSuggestedActions marshals
+        # (health_state_test.go:20-39, 59-76), resolved like evolveHealthyState does, on the oracle and on the C++ side
+        stored = []
+        for e in r["events"]:
+            if e["k"] != "err":
+                stored.append({"name": "reboot"})
+                continue
+            data = '{"time":null,"data_source":"test","device_uuid":"PCI:0000:9b:00","xid":%d' % e["code"]
+            if e["actions"] is not None:
+                data += ',"suggested_actions_by_gpud":{"repair_actions":["%s"]}' % O.ACTION_WIRE[ACT_BY_GO[e["actions"][0]]]
+            stored.append({"name": "error_xid", "type": e["type"], "device_uuid": "PCI:0000:9b:00", "data": data + "}"})
+        want = O.evolve_healthy_state_stored(stored, {}, 2)
+        assert want["health"] == r["health"], r["name"]
+        if r.get("action"):
+            assert want["actions"][0] == ACT_BY_GO[r["action"]], r["name"]
+        if "reason" in r:
+            assert want["reason"] == r["reason"], r["name"]
+        assert _evolve_stored(stored, {}, 2) == (want["health"], (want["actions"] or [0])[0], want["reason"]), r["name"]
+    # "invalid xid" (:236-246): an undecodable payload is skipped -> Healthy
+    bad = [{"name": "error_xid", "type": "Critical", "device_uuid": "", "data": "invalid json"}]
+    assert O.evolve_healthy_state_stored(bad, {}, 2)["health"] == "Healthy" and _evolve_stored(bad, {}, 2)[0] == "Healthy"
 
 
 def test_temperature_checks_of_the_reference(golden):   # temperature/component_test.go: TestCheck_* with a Temperature literal
@@ -281,3 +303,168 @@ def test_temperature_checks_of_the_reference(golden):   # temperature/component_
                                    t.get("ThresholdCelsiusSlowdownMargin", 0), int(t.get("MarginTemperatureSupported", False)), thr)
         got_cls = "margin" if bits & 4 else ("gpu" if bits & 1 else ("hbm" if bits & 2 else ""))
         assert got_cls == cls and (bits != 0) == (health == "Degraded"), r["name"]
+
+
+# ---- xid event message / health-state reason (xid/health_state.go:130-281; health_state_test.go:299-942) --------------------
+def _go_payload(ev):
+    """json.Marshal(xidErrorEventDetail) as createXidEvent / createNVLinkXidEvent build it (health_state_test.go:20-39, 887-905)"""
+    import json
+    parts = ['"time":null', '"data_source":"test"', '"device_uuid":%s' % json.dumps(ev["device_uuid"]), '"xid":%d' % ev["xid"]]
+    if ev["sub_code"]:
+        parts.append('"sub_code":%d' % ev["sub_code"])
+    if ev["error_status"]:
+        parts.append('"error_status":%d' % ev["error_status"])
+    if ev["description"]:
+        parts.append('"description":%s' % json.dumps(ev["description"]))
+    wire = {"RebootSystem": "REBOOT_SYSTEM", "HardwareInspection": "HARDWARE_INSPECTION", "CheckUserAppAndGPU": "CHECK_USER_APP_AND_GPU", "IgnoreNoActionRequired": "IGNORE_NO_ACTION_REQUIRED"}
+    parts.append('"suggested_actions_by_gpud":{"repair_actions":["%s"]}' % wire[ev["action"]])
+    return "{" + ",".join(parts) + "}"
+
+
+def _devspec(devices):
+    return ";".join("%s=%s" % kv for kv in devices.items()).encode()
+
+
+def _evolve_stored(events, devices, thr=2):
+    L = g.lib()
+    blob = "\x1e".join("\x1f".join([e["name"], e.get("type", ""), e.get("device_uuid", ""), e.get("data", "")]) for e in events)
+    h, a = C.c_int32(), C.c_int32()
+    out = C.create_string_buffer(2048)
+    L.gpudh_evolve_stored(blob.encode("utf-8"), _devspec(devices), thr, C.byref(h), C.byref(a), out, 2048)
+    return HEALTH[h.value], a.value, out.value.decode("utf-8")
+
+
+def test_xid_build_message_vectors_of_the_reference(golden):
+    G = golden("xid_messages.json")
+    assert len(G["literals"]["rows"]) == 7 and len(G["standard"]["rows"]) == 6
+    for r in G["literals"]["rows"]:                                  # xidErrorEventDetail literals + asserts on buildMessage(nil)
+        f = r["fields"]
+        args = (f["Xid"], f.get("SubCode", 0), f.get("ErrorStatus", 0), f.get("Description", ""), f.get("DeviceUUID", ""))
+        want = O.xid_build_message(*args)
+        assert g.xid_build_message(*args) == want
+        if r["equal"] is not None:
+            assert want == r["equal"], r["func"]
+        for c in r["contains"]:
+            assert c in want, (r["func"], c)
+    S = G["standard"]
+    for r in S["rows"]:                                              # Test_HealthStateReason_StandardXIDs: devices {uuid: bus id}
+        uuid = O.convert_bus_id_to_uuid(r["device_uuid"], {S["uuid"]: S["bus_id"]})
+        assert uuid == S["uuid"] and g.lib().gpud_xid_device_matches_bus_id(r["device_uuid"].encode(), S["bus_id"].encode()) == 1
+        want = O.xid_build_message(r["xid"], 0, 0, r["description"], r["device_uuid"], uuid)
+        assert g.xid_build_message(r["xid"], 0, 0, r["description"], r["device_uuid"], uuid) == want
+        for c in r["contains"]:
+            assert c in want, (r["name"], c)
+        assert ("XID %d." % r["xid"]) not in want and "err status" not in want
+    assert g.lib().gpud_xid_device_matches_bus_id(b"PCI:0000:04:00", b"0000:9b:00.0") == 0
+    assert g.lib().gpud_xid_device_matches_bus_id(b"0000:04:00", b"0000:04:00.0") == 1          # TrimPrefix: the "PCI:" is optional
+    # the uint64 that does not fit an int (intFromUint64 fails): header and device only
+    assert g.xid_build_message(2 ** 63, 0, 0, "x", "PCI:1") == O.xid_build_message(2 ** 63, 0, 0, "x", "PCI:1") == "XID 9223372036854775808 detected on GPU PCI:1"
+    # "Unused" and a description equal to the mnemonic are not appended
+    for xid in (1, 13, 79, 94, 144, 150, 173, 999):
+        for desc in ("", "Unused", O.MNEMONIC.get(xid, ""), "something else"):
+            assert g.xid_build_message(xid, 3, 0x10, desc, "PCI:0000:01:00", "GPU-u") == O.xid_build_message(xid, 3, 0x10, desc, "PCI:0000:01:00", "GPU-u")
+
+
+def test_xid_reason_from_kmsg_lines_oracle(golden):
+    G = golden("xid_messages.json")["from_lines"]
+    assert len(G["rows"]) == 15
+    for r in G["rows"]:
+        x = O.xid_match(r["line"].encode())
+        assert x is not None and x.detail is not None, r["name"]
+        d = x.detail
+        msg = O.xid_build_message(x.xid, d.sub_code, d.error_status, d.description, x.device, O.convert_bus_id_to_uuid(x.device, r["devices"]))
+        for c in r["contains"]:
+            assert c in msg, (r["name"], c, msg)
+        if "sub_code" in r:
+            assert d.sub_code == r["sub_code"] and ("%d.%d" % (x.xid, r["sub_code"])) in msg
+        if "xid" in r:
+            assert x.xid == r["xid"]
+        if "event_type" in r:
+            assert O.EVENT_NAMES[d.event_type] == r["event_type"]
+        if "hint" in r:
+            assert d.investigatory_hint == r["hint"]
+        # gpud_xid_hit_message over a hit carrying what the scan fills in (the scan itself is compared on the GPU)
+        h = g.XidHit()
+        h.kind, h.code, h.device, h.dev_len = 1, x.xid, x.device.encode(), len(x.device)
+        h.flags, h.sub_code, h.error_status = (1 if x.info is not None and x.info.unit else 0), d.sub_code, d.error_status
+        L = g.lib()
+        L.gpud_xid_description.restype = C.c_char_p
+        h.detail_variant = next(v for v in (0, 1, 2) if L.gpud_xid_description(x.xid, v).decode() == d.description)
+        uuid = O.convert_bus_id_to_uuid(x.device, r["devices"])
+        assert g.xid_hit_message(h, uuid) == msg, r["name"]
+
+
+def test_evolve_over_stored_events_with_reason(golden):
+    G = golden("xid_messages.json")["evolve"]
+    assert len(G["rows"]) == 5
+    for r in G["rows"]:                                              # Test_HealthStateReason_evolveHealthyState_Integration
+        events = [dict(e, data=_go_payload(e)) if e["name"] == "error_xid" else e for e in r["events"]]
+        want = O.evolve_healthy_state_stored(events, G["devices"])
+        assert want["health"] == r["health"], r["name"]
+        for c in r["contains"]:
+            assert c in want["reason"], (r["name"], c)
+        got = _evolve_stored(events, G["devices"])
+        assert got == (want["health"], (want["actions"] or [0])[0], want["reason"]), r["name"]
+
+def test_resolve_xid_event_matches_the_oracle_on_random_payloads():
+    import json
+    import numpy as np
+    L = g.lib()
+    rng = np.random.default_rng(5)
+    devices = {"GPU-aaaa": "0000:04:00.0", "GPU-bbbb": "0000:9b:00.0"}
+    wires = list(O.ACTION_WIRE.values())
+    codes = [0, 1, 13, 31, 63, 64, 79, 94, 119, 123, 144, 145, 149, 150, 154, 172, 173, 999, 99999]
+    n_res = 0
+    for i in range(3000):
+        kind = rng.random()
+        typ = str(rng.choice(["", "Warning", "Critical", "Fatal", "Info"]))
+        dev = str(rng.choice(["PCI:0000:04:00", "PCI:0000:9b:00", "PCI:0000:01:00", ""]))
+        if kind < 0.15:                                              # legacy rows: a decimal code, or junk
+            raw = str(rng.choice(["79", "94", "+63", "99999", "0", "-5", "12x", "", " 79", "149", "1e3", "0079"]))
+        else:
+            xid = int(rng.choice(codes))
+            p = {"time": None, "data_source": "kmsg", "device_uuid": dev, "xid": xid}
+            if rng.random() < 0.5:
+                p["sub_code"] = int(rng.choice([0, 4, 10, 37, 38, 63]))
+            if rng.random() < 0.5:
+                p["error_status"] = int(rng.choice([0, 1, 2, 8, 0x80000000]))
+            if rng.random() < 0.5:
+                p["description"] = str(rng.choice(["", "Unused", "some \"quoted\" text", "NVLINK: RLW Error", "café \U0001F600"]))
+            if rng.random() < 0.3:
+                p["investigatory_hint"] = "INVESTIGATE_PEER_DEVICE"
+            r = rng.random()
+            if r < 0.5:
+                p["suggested_actions_by_gpud"] = {"repair_actions": [str(a) for a in rng.choice(wires, size=int(rng.integers(0, 3)))]}
+            elif r < 0.6:
+                p["suggested_actions_by_gpud"] = None
+            raw = json.dumps(p, separators=(",", ":"), ensure_ascii=bool(rng.random() < 0.5))
+            if kind > 0.95:
+                raw = raw[:-3]                                       # truncated JSON
+        want = O.resolve_xid_event(typ, raw, dev, devices)
+        tout, mout = C.create_string_buffer(64), C.create_string_buffer(2048)
+        na, acts = C.c_int32(), (C.c_int32 * 4)()
+        ok = L.gpudh_resolve_xid_event(typ.encode(), raw.encode("utf-8"), dev.encode(), _devspec(devices), tout, 64, mout, 2048, C.byref(na), acts)
+        assert bool(ok) == (want is not None), (typ, raw)
+        if want is None:
+            continue
+        n_res += 1
+        wt, wm, wp = want
+        assert (tout.value.decode(), mout.value.decode("utf-8")) == (wt, wm), raw
+        assert (None if na.value < 0 else [acts[k] for k in range(na.value)]) == wp["actions"], raw
+    assert n_res > 2000
+    # and the fold over random stored histories
+    for i in range(300):
+        events = []
+        for _ in range(int(rng.integers(0, 9))):
+            if rng.random() < 0.3:
+                events.append({"name": "reboot"})
+            else:
+                xid = int(rng.choice([13, 31, 79, 94, 123, 149, 150, 99999]))
+                ev = {"name": "error_xid", "type": str(rng.choice(["Warning", "Critical", "Fatal"])), "xid": xid, "sub_code": int(rng.choice([0, 4, 37])),
+                      "error_status": int(rng.choice([0, 2])), "device_uuid": "PCI:0000:04:00", "description": str(rng.choice(["", "d"])),
+                      "action": str(rng.choice(["RebootSystem", "HardwareInspection", "CheckUserAppAndGPU"]))}
+                ev["data"] = _go_payload(ev) if rng.random() < 0.85 else str(xid)
+                events.append(ev)
+        thr = int(rng.integers(1, 4))
+        want = O.evolve_healthy_state_stored(events, devices, thr)
+        assert _evolve_stored(events, devices, thr) == (want["health"], (want["actions"] or [0])[0], want["reason"]), events

@@ -505,6 +505,68 @@ def main():
     sql["table_names"] = {"src": "pkg/eventstore/database_test.go:%d" % line, "rows": tn}
     dump("store_sql.json", sql)
 
+    # ---- xid buildMessage / health-state reason tests (xid/health_state_test.go:299-942) ----
+    HS = N + "xid/health_state_test.go"
+    hs_src = open(os.path.join(REF, HS)).read()
+    xm = {}
+    go_str = lambda lit: bytes(lit, "utf-8").decode("unicode_escape")
+    # struct-literal tests: every `v := xidErrorEventDetail{...}`, the `r := v.buildMessage(...)` that follows, and the asserts on r
+    lit_rows = []
+    for fn in ("Test_buildMessage_SubCode", "Test_buildMessage_Format", "Test_HealthStateReason_UnknownXID", "Test_HealthStateReason_EmptyDescription"):
+        body, line = find_func(hs_src, fn)
+        for seg in (body.split("t.Run(")[1:] or [body]):
+            lits = {}
+            for m in re.finditer(r"(\w+) := xidErrorEventDetail\{(.*?)\n\t*\}", seg, re.S):
+                f = {}
+                for k, v in re.findall(r"(\w+):\s*(\"(?:[^\"\\]|\\.)*\"|0x[0-9a-fA-F]+|\d+),", m.group(2)):
+                    f[k] = go_str(v[1:-1]) if v.startswith('"') else int(v, 0)
+                lits[m.group(1)] = f
+            for rv, lv in re.findall(r"(\w+) := (\w+)\.buildMessage\(nil\)", seg):
+                eq = [go_str(x) for x in re.findall(r'assert\.Equal\(t, "((?:[^"\\]|\\.)*)", %s\)' % rv, seg)]
+                co = [go_str(x) for x in re.findall(r'assert\.Contains\(t, %s, "((?:[^"\\]|\\.)*)"' % rv, seg)]
+                lit_rows.append({"func": fn, "fields": lits[lv], "equal": eq[0] if eq else None, "contains": co})
+    xm["literals"] = {"src": HS, "rows": lit_rows}
+    rows, src = table(HS, "Test_HealthStateReason_StandardXIDs")
+    xm["standard"] = {"src": src, "rows": [{"name": r["name"], "xid": r["xid"], "device_uuid": r["deviceUUID"], "description": r["description"],
+                                            "contains": r["expectedContains"]} for r in rows], "bus_id": "0000:9b:00.0", "uuid": "GPU-test-uuid"}
+    line_rows = []
+    rows, src = table(HS, "Test_HealthStateReason_NVLinkXIDs")
+    for r in rows:
+        line_rows.append({"func": "Test_HealthStateReason_NVLinkXIDs", "name": r["name"], "line": r["kmsgLine"], "xid": r["expectedXid"], "sub_code": r["expectedSubCode"],
+                          "contains": r["expectedContains"] + ["UUID:GPU-test-uuid"], "devices": {"GPU-test-uuid": "0000:04:00.0"}})
+    rows, src = table(HS, "Test_StatusAwareMessages")
+    for r in rows:
+        line_rows.append({"func": "Test_StatusAwareMessages", "name": r["name"], "line": r["line"], "sub_code": r["expectedSub"], "event_type": ident(r["expectedEvent"]),
+                          "contains": [r["expectedMnemonic"]], "devices": {}})
+    rows, src = table(HS, "Test_MatchToEventMessageFlowFormatsMnemonic")
+    for r in rows:
+        line_rows.append({"func": "Test_MatchToEventMessageFlowFormatsMnemonic", "name": r["name"], "line": r["kmsgLine"], "contains": ["145.0", "NVLINK_RLW_ERROR", "PCI:0000:04:00"], "devices": {}})
+    rows, src = table(HS, "Test_SubCodeDifferentiatesSameUnit")
+    for r in rows:
+        line_rows.append({"func": "Test_SubCodeDifferentiatesSameUnit", "name": r["name"], "line": r["kmsgLine"], "sub_code": r["subCodeValue"],
+                          "contains": ["NVLINK_NETIR_ERROR", "149.%d" % r["subCodeValue"]], "devices": {}})
+    rows, src = table(HS, "Test_InvestigatoryHintFiltering")
+    for r in rows:
+        line_rows.append({"func": "Test_InvestigatoryHintFiltering", "name": r["name"], "line": r["kmsgLine"], "hint": r["expectedVal"], "contains": [], "devices": {}})
+    xm["from_lines"] = {"src": HS, "rows": line_rows}
+    # evolveHealthyState integration: the events each case builds with createXidEvent / createNVLinkXidEvent (:20-39, :887-905)
+    body, line = find_func(hs_src, "Test_HealthStateReason_evolveHealthyState_Integration")
+    ev_rows = []
+    for m in re.finditer(r'name:\s*"([^"]*)",\s*events:\s*eventstore\.Events\{(.*?)\},\s*expectedHealth:\s*apiv1\.HealthStateType(\w+),\s*expectedContains:\s*\[\]string\{(.*?)\}', body, re.S):
+        evs = []
+        for em in re.finditer(r'createNVLinkXidEvent\([^,]+(?:\([^)]*\))?, (\d+), (\d+), (0x[0-9a-fA-F]+|\d+), apiv1\.EventType(\w+), apiv1\.RepairActionType(\w+)\)|createXidEvent\((?:[^,()]|\([^)]*\))+, (\d+), apiv1\.EventType(\w+), apiv1\.RepairActionType(\w+)\)|\{Name: "reboot"', m.group(2)):
+            if em.group(1):
+                evs.append({"name": "error_xid", "type": em.group(4), "xid": int(em.group(1)), "sub_code": int(em.group(2)), "error_status": int(em.group(3), 0),
+                            "device_uuid": "PCI:0000:04:00", "description": "NVLINK Error for XID %s" % em.group(1), "action": em.group(5)})
+            elif em.group(6):
+                evs.append({"name": "error_xid", "type": em.group(7), "xid": int(em.group(6)), "sub_code": 0, "error_status": 0, "device_uuid": "PCI:0000:9b:00",
+                            "description": "", "action": em.group(8)})
+            else:
+                evs.append({"name": "reboot"})
+        ev_rows.append({"name": m.group(1), "events": evs, "health": m.group(3), "contains": [go_str(x) for x in re.findall(r'"((?:[^"\\]|\\.)*)"', m.group(4))]})
+    xm["evolve"] = {"src": "%s:%d" % (HS, line), "rows": ev_rows, "devices": {"GPU-test-uuid": "0000:04:00.0"}}
+    dump("xid_messages.json", xm)
+
     # ---- eventstore compareEvent / unmarshalIfValid tables + infiniband's kmsg dedup-window policy ----
     es = {}
     rows, src = table("pkg/eventstore/database_test.go", "TestCompareEvent")
@@ -642,10 +704,16 @@ def main():
             m = re.search(r"eventstore\.Events\{(.*?)\n\t\t\}", blk, re.S)
             evs = []
             if m:
-                for em in re.finditer(ctor + r"\([^,]+,\s*(\d+),\s*apiv1\.EventType(\w+),\s*apiv1\.RepairActionType(\w+)\)|\{Name:\s*\"reboot\"\}", m.group(1)):
-                    evs.append({"k": "reboot"} if em.group(1) is None else {"k": "err", "code": int(em.group(1)), "type": em.group(2), "actions": [em.group(3)]})
+                for em in re.finditer(ctor + r"\([^,]+,\s*(\d+),\s*apiv1\.EventType(\w+),\s*apiv1\.RepairActionType(\w+)\)|" + ctor +
+                                      r"WithNilSuggestedActions\([^,]+,\s*(\d+),\s*apiv1\.EventType(\w+)\)|\{Name:\s*\"reboot\"[^}]*\}", m.group(1)):
+                    if em.group(1) is not None:
+                        evs.append({"k": "err", "code": int(em.group(1)), "type": em.group(2), "actions": [em.group(3)]})
+                    elif em.group(4) is not None:
+                        evs.append({"k": "err", "code": int(em.group(4)), "type": em.group(5), "actions": None})
+                    else:
+                        evs.append({"k": "reboot"})
             r = {"name": name, "events": evs}
-            hm = re.search(r"assert\.Equal\(t,\s*apiv1\.HealthStateType(\w+),\s*state\.Health\)", blk)
+            hm = re.search(r"assert\.Equal\(t,\s*apiv1\.HealthStateType(\w+),\s*state\.Health[,)]", blk)
             if hm:
                 r["health"] = hm.group(1)
             rm = re.search(r'assert\.Equal\(t,\s*"([^"]*)",\s*state\.Reason\)', blk)
