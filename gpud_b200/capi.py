@@ -206,6 +206,18 @@ class Poller:
         self.ctx._check(self._L.gpud_poller_last_rows(self._h, C.c_void_p(rows.ctypes.data), cap_rows, C.byref(n), C.byref(sec)))
         return rows[: min(cap_rows, n.value)], sec.value
 
+    def fabric_raw(self, gpu_index: int = 0, peer_bus_ids=()) -> "FabricRaw":
+        """this GPU's NVLink / fabric record read from NVML (GetNVLink, GetFabricState, P2P status against the peers)"""
+        raw = FabricRaw()
+        arr = (C.c_char_p * max(1, len(peer_bus_ids)))(*[b.encode() if b else None for b in peer_bus_ids])
+        self.ctx._check(self._L.gpud_poller_fabric_raw(self._h, gpu_index, arr, len(peer_bus_ids), C.byref(raw)))
+        return raw
+
+    def product_name(self) -> str:
+        buf = C.create_string_buffer(96)
+        self.ctx._check(self._L.gpud_poller_product_name(self._h, buf, 96))
+        return buf.value.decode()
+
     def close(self):
         if self._h:
             self._L.gpud_poller_destroy(self._h)
@@ -275,9 +287,9 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
-           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
+           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
@@ -314,6 +326,7 @@ def lib() -> C.CDLL:
         "gpud_ib_scan": (i32, [vp, i32, vp, vp, i64, i64, i64, i32, vp]), "gpud_ib_reason": (i32, [C.c_char_p, C.c_uint32, i64, i32, vp, i32]),
         "gpud_poller_create": (i32, [vp, i32, vp, vp]), "gpud_poller_destroy": (None, [vp]), "gpud_poller_poll": (i32, [vp, i64, i64]),
         "gpud_poller_last_rows": (i32, [vp, vp, i64, vp, vp]),
+        "gpud_poller_fabric_raw": (i32, [vp, C.c_uint32, vp, i32, C.POINTER(FabricRaw)]), "gpud_poller_product_name": (i32, [vp, vp, i32]),
         "gpud_ring_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "gpud_ring_reduce": (i32, [vp]), "gpud_ring_sync": (i32, [vp]),
         "gpud_ring_kernel_ms": (i32, [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]), "gpud_ring_read": (i32, [vp, i32, vp, i64]),
@@ -328,6 +341,7 @@ def lib() -> C.CDLL:
         "gpud_sxid_name": (C.c_char_p, [i32]), "gpud_nvlink_rule_hint": (C.c_char_p, [i32]),
         "gpud_sxid_reason": (i32, [i64, C.c_char_p, vp, i32]),
         "gpud_xid_get_detail": (i32, [i32, vp, vp, vp]),
+        "gpud_product_mem_caps": (i32, [C.c_char_p]), "gpud_product_fm_supported": (i32, [C.c_char_p]), "gpud_product_fabric_state_supported": (i32, [C.c_char_p]),
         "gpud_xid_detail": (i32, [i32, i32, C.c_uint32, vp, vp, vp, vp, vp]),
         "gpud_xid_build_message": (i32, [C.c_uint64, i32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p, vp, i32]),
         "gpud_xid_hit_message": (i32, [C.POINTER(XidHit), C.c_char_p, vp, i32]), "gpud_xid_device_matches_bus_id": (i32, [C.c_char_p, C.c_char_p]), "gpud_kmsg_event_name": (C.c_char_p, [i32]), "gpud_kmsg_event_message": (C.c_char_p, [i32]),

@@ -440,6 +440,48 @@ extern "C" int32_t gpud_xid_device_matches_bus_id(const char* device_uuid, const
   return strncmp(pci_bus_id, want.c_str(), want.size()) == 0 ? 1 : 0;
 }
 
+// ---- GPU product capabilities (pkg/nvidia/product/capabilities.go:6-137): decided from the NVML product name ----
+namespace {
+std::string lower(const char* s) {
+  std::string o = s ? s : "";
+  for (char& c : o) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+  return o;
+}
+struct ProductRow { const char* key; int mem_caps; int fm; };     // mem_caps: 1 containment | 2 page offlining | 4 row remapping; -1 = not in that map
+const ProductRow kProducts[] = {                                   // gpuProductToMemMgmtCaps (:15-23), gpuProductToFMSupported (:25-50)
+    {"a100", 7, 1}, {"b100", 7, 1}, {"b200", 7, 1}, {"gb200", 7, 0}, {"h100", 7, 1}, {"h200", 7, 1}, {"a10", 4, 0}, {"gh200", -1, 0},
+};
+// the longest key contained in the lowered name decides (:65-75, :121-134)
+const ProductRow* longest_product(const std::string& p, bool mem_map) {
+  const ProductRow* best = nullptr;
+  for (const ProductRow& r : kProducts) {
+    if (mem_map && r.mem_caps < 0) continue;
+    if (p.find(r.key) == std::string::npos) continue;
+    if (!best || strlen(best->key) < strlen(r.key)) best = &r;
+  }
+  return best;
+}
+}  // namespace
+
+// SupportedMemoryMgmtCapsByGPUProduct (:119-137): 1 ErrorContainment | 2 DynamicPageOfflining | 4 RowRemapping
+extern "C" int32_t gpud_product_mem_caps(const char* product_name) {
+  const ProductRow* r = longest_product(lower(product_name), true);
+  return r ? r->mem_caps : 0;
+}
+// SupportedFMByGPUProduct (:56-76): the on-node nv-fabricmanager daemon; PCIe variants never
+extern "C" int32_t gpud_product_fm_supported(const char* product_name) {
+  const std::string p = lower(product_name);
+  if (p.find("pcie") != std::string::npos) return 0;
+  const ProductRow* r = longest_product(p, false);
+  return r ? r->fm : 0;
+}
+// SupportFabricStateByGPUProduct (:93-116): NVML fabric-state telemetry
+extern "C" int32_t gpud_product_fabric_state_supported(const char* product_name) {
+  const std::string p = lower(product_name);
+  if (p.find("pcie") != std::string::npos || p.find("gh200") != std::string::npos) return 0;
+  return (p.find("gb200") != std::string::npos || p.find("h100") != std::string::npos || p.find("h200") != std::string::npos) ? 1 : 0;
+}
+
 // setNVLinkSuggestedActions (nvlink/evaluate_threshold.go:37-52) + peerNVLinkStatusesSuggestReboot (component.go:398-415): does an
 // unhealthy verdict come with RepairActionTypeRebootSystem?
 extern "C" int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v) {

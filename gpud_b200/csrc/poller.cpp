@@ -18,6 +18,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "internal.h"
@@ -39,6 +40,11 @@ struct Nvml {
   nvmlReturn_t (*util)(nvmlDevice_t, nvmlUtilization_t*) = nullptr;
   nvmlReturn_t (*memory)(nvmlDevice_t, nvmlMemory_t*) = nullptr;
   const char* (*err)(nvmlReturn_t) = nullptr;
+  nvmlReturn_t (*name)(nvmlDevice_t, char*, unsigned int) = nullptr;
+  nvmlReturn_t (*link_state)(nvmlDevice_t, unsigned int, int*) = nullptr;
+  nvmlReturn_t (*link_errors)(nvmlDevice_t, unsigned int, int, unsigned long long*) = nullptr;
+  nvmlReturn_t (*fabric_v)(nvmlDevice_t, void*) = nullptr;
+  nvmlReturn_t (*p2p)(nvmlDevice_t, nvmlDevice_t, int, int*) = nullptr;
 };
 
 Nvml* nvml() {
@@ -56,6 +62,11 @@ Nvml* nvml() {
       *(void**)&n.util = dlsym(n.so, "nvmlDeviceGetUtilizationRates");
       *(void**)&n.memory = dlsym(n.so, "nvmlDeviceGetMemoryInfo");
       *(void**)&n.err = dlsym(n.so, "nvmlErrorString");
+      *(void**)&n.name = dlsym(n.so, "nvmlDeviceGetName");
+      *(void**)&n.link_state = dlsym(n.so, "nvmlDeviceGetNvLinkState");
+      *(void**)&n.link_errors = dlsym(n.so, "nvmlDeviceGetNvLinkErrorCounter");
+      *(void**)&n.fabric_v = dlsym(n.so, "nvmlDeviceGetGpuFabricInfoV");           // driver >= 550 (fabric_state.go:262-267); absent symbol = not supported
+      *(void**)&n.p2p = dlsym(n.so, "nvmlDeviceGetP2PStatus");
       if (!n.init || !n.by_pci || !n.temperature || !n.power || !n.clock || !n.util || !n.memory || n.init() != 0) { dlclose(n.so); n.so = nullptr; }
     }
   }
@@ -144,5 +155,103 @@ extern "C" int32_t gpud_poller_last_rows(gpud_poller* p, uint32_t* rows, int64_t
   if (n > 0 && rows) memcpy(rows, p->rows, (size_t)n * GPUD_POLL_N_FIELDS * sizeof(uint32_t));
   if (n_rows) *n_rows = p->n_rows;
   if (seconds) *seconds = p->last_poll_s;
+  return GPUD_OK;
+}
+
+// ---- NVLink / fabric record of this poller's GPU, straight from NVML -------------------------------
+namespace {
+constexpr nvmlReturn_t kNvmlNotSupported = 3, kNvmlGpuLost = 15, kNvmlResetRequired = 16;     // nvml.h nvmlReturn_t
+// nvmlGpuFabricInfo_v3_t (nvml.h): version, clusterUuid[16], status, cliqueId, state, healthMask, healthSummary
+struct FabricInfoV3 { unsigned int version; unsigned char cluster_uuid[16]; nvmlReturn_t status; unsigned int clique_id; unsigned char state; unsigned int health_mask;
+                      unsigned char health_summary; };
+static_assert(sizeof(FabricInfoV3) == 40, "nvmlGpuFabricInfo_v3_t layout");
+bool contains_ci(const char* hay, const char* needle) {
+  if (!hay) return false;
+  std::string h = hay;
+  for (char& c : h) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
+  return h.find(needle) != std::string::npos;
+}
+// pkg/nvidia/errors/error.go:33-92: the code, or the driver's error string saying so
+bool is_not_supported(Nvml* N, nvmlReturn_t r) { return r == kNvmlNotSupported || (r != 0 && N->err && contains_ci(N->err(r), "not supported")); }
+bool is_gpu_lost(Nvml* N, nvmlReturn_t r) {
+  if (r == kNvmlGpuLost) return true;
+  if (r == 0 || !N->err) return false;
+  const char* e = N->err(r);
+  return contains_ci(e, "gpu lost") || contains_ci(e, "gpu is lost") || contains_ci(e, "gpu_is_lost");
+}
+bool is_reset_required(Nvml* N, nvmlReturn_t r) {
+  if (r == kNvmlResetRequired) return true;
+  if (r == 0 || !N->err) return false;
+  const char* e = N->err(r);
+  return contains_ci(e, "gpu requires reset") || contains_ci(e, "gpu reset");
+}
+}  // namespace
+
+extern "C" int32_t gpud_poller_product_name(gpud_poller* p, char* out, int32_t cap) {
+  if (!p || !out || cap <= 0) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->name) return GPUD_E_UNSUPPORTED;
+  const nvmlReturn_t rc = N->name(p->h, out, (unsigned int)cap);
+  if (rc != 0) return gpud_fail(p->ctx, GPUD_E_UNSUPPORTED, "nvmlDeviceGetName: %s", N->err ? N->err(rc) : "error");
+  return GPUD_OK;
+}
+
+// GetNVLink (nvlink/nvlink.go:93-168), GetFabricState's V3 query (pkg/nvidia/nvml/device/fabric_state.go:268-306) and
+// getPeerNVLinkP2PStatus (nvlink/p2p.go:21-50) for one GPU.
+extern "C" int32_t gpud_poller_fabric_raw(gpud_poller* p, uint32_t gpu_index, const char* const* peer_bus_ids, int32_t n_peers, gpud_fabric_raw* out) {
+  if (!p || !out || n_peers < 0 || n_peers > GPUD_MAX_GPUS || (n_peers && !peer_bus_ids) || gpu_index >= GPUD_MAX_GPUS) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->link_state || !N->link_errors) return gpud_fail(p->ctx, GPUD_E_UNSUPPORTED, "NVML NVLink getters not available");
+  memset(out, 0, sizeof *out);
+  out->gpu_index = gpu_index;
+  out->nvlink_supported = 1;
+  for (unsigned int link = 0; link < GPUD_MAX_LINKS; ++link) {
+    int active = 0;
+    const nvmlReturn_t rc = N->link_state(p->h, link, &active);
+    if (is_not_supported(N, rc)) {               // on link 0: no NVLink hardware; later: fewer links than NVML_NVLINK_MAX_LINKS
+      if (out->n_links == 0) out->nvlink_supported = 0;
+      break;
+    }
+    if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");                  // nvmlerrors.ErrGPULost
+    if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");  // nvmlerrors.ErrGPURequiresReset
+    if (rc != 0) continue;                       // "failed get nvlink state -- retrying": the link is left out of States
+    const uint32_t i = out->n_links++;
+    out->link_feature_enabled[i] = active == 1 /* NVML_FEATURE_ENABLED */ ? 1 : 0;
+    unsigned long long v = 0;
+    if (N->link_errors(p->h, link, 0 /* NVML_NVLINK_ERROR_DL_REPLAY */, &v) == 0) out->link_replay_errors[i] = v;
+    if (N->link_errors(p->h, link, 1 /* NVML_NVLINK_ERROR_DL_RECOVERY */, &v) == 0) out->link_recovery_errors[i] = v;
+    if (N->link_errors(p->h, link, 2 /* NVML_NVLINK_ERROR_DL_CRC_FLIT */, &v) == 0) out->link_crc_errors[i] = v;
+  }
+  // fabric state: the V3 structure carries the health mask and summary; anything else = no fabric telemetry for this GPU
+  if (N->fabric_v) {
+    FabricInfoV3 fi;
+    memset(&fi, 0, sizeof fi);
+    fi.version = (unsigned int)sizeof(FabricInfoV3) | (3u << 24);             // NVML_STRUCT_VERSION(GpuFabricInfo, 3)
+    const nvmlReturn_t rc = N->fabric_v(p->h, &fi);
+    if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+    if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
+    if (rc == 0) {
+      out->fabric_valid = 1;
+      out->fabric_state = fi.state;
+      out->fabric_summary = fi.health_summary;
+      out->fabric_status = (int32_t)fi.status;
+      out->fabric_health_mask = fi.health_mask;
+      out->clique_id = fi.clique_id;
+    }
+  }
+  char name[96] = {0};
+  if (N->name && N->name(p->h, name, sizeof name) == 0)
+    out->system_expected_nvlink = (gpud_product_fm_supported(name) || gpud_product_fabric_state_supported(name)) ? 1u : 0u;   // nvlink/component.go:164-183
+  for (int j = 0; j < GPUD_MAX_GPUS; ++j) out->p2p_status[j] = GPUD_P2P_UNPROBED;
+  if (N->p2p) {
+    for (int32_t j = 0; j < n_peers; ++j) {
+      if ((uint32_t)j == gpu_index || !peer_bus_ids[j] || !*peer_bus_ids[j]) continue;
+      nvmlDevice_t peer;
+      if (N->by_pci(peer_bus_ids[j], &peer) != 0) continue;
+      int st = 6;
+      if (N->p2p(p->h, peer, 2 /* NVML_P2P_CAPS_INDEX_NVLINK */, &st) != 0) continue;           // a failed probe stays unprobed (component.go:430-447)
+      out->p2p_status[j] = (uint8_t)((st >= 0 && st <= 5) ? st : 6);                            // toP2PStatusCode: anything else is "U"
+    }
+  }
   return GPUD_OK;
 }

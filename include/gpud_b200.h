@@ -253,6 +253,12 @@ int32_t gpud_xid_build_message(uint64_t xid, int32_t sub_code, uint32_t error_st
                                const char* gpu_uuid, char* out, int32_t cap);
 int32_t gpud_xid_hit_message(const gpud_xid_hit* hit, const char* gpu_uuid, char* out, int32_t cap);
 int32_t gpud_xid_device_matches_bus_id(const char* device_uuid, const char* pci_bus_id);
+/* GPU product capabilities from the NVML product name (pkg/nvidia/product/capabilities.go:56-137): memory error management
+ * (bit 1 ErrorContainment, 2 DynamicPageOfflining, 4 RowRemapping -- the xid component drops Xid 63/64 when row remapping is
+ * supported, xid/component.go:290,484), the on-node fabric manager, NVML fabric-state telemetry. */
+int32_t gpud_product_mem_caps(const char* product_name);
+int32_t gpud_product_fm_supported(const char* product_name);
+int32_t gpud_product_fabric_state_supported(const char* product_name);
 /* kmsg.MatchFunc results (eventName, message) of the extra matchers, by hit kind; "" for xid / sxid kinds. */
 const char* gpud_kmsg_event_name(int32_t kind);
 const char* gpud_kmsg_event_message(int32_t kind);
@@ -422,6 +428,13 @@ typedef struct {
   uint8_t fabric_issue_bits[GPUD_MAX_GPUS];
   uint64_t total_replay, total_recovery, total_crc;
 } gpud_fabric_verdict;
+/* The host poller's side of the record: GetNVLink (nvlink/nvlink.go:93-168: per-link FEATURE_ENABLED and the
+ * DL replay / recovery / CRC-flit counters; NOT_SUPPORTED on link 0 = no NVLink, later = fewer links), the V3 fabric info
+ * (pkg/nvidia/nvml/device/fabric_state.go:268-306), SystemExpectedNVLink from the product name, and the NVLink P2P status against
+ * each peer (nvlink/p2p.go:21-50; peer_bus_ids[j] = PCI bus id of gpu_index j, NULL / "" entries and j == gpu_index are skipped).
+ * GPUD_E_STATE with "GPU lost" / "GPU requires reset" in gpud_last_error mirrors nvmlerrors.ErrGPULost / ErrGPURequiresReset. */
+int32_t gpud_poller_fabric_raw(gpud_poller* poller, uint32_t gpu_index, const char* const* peer_bus_ids, int32_t n_peers, gpud_fabric_raw* out);
+int32_t gpud_poller_product_name(gpud_poller* poller, char* out, int32_t cap);   /* nvmlDeviceGetName */
 /* Does this (unhealthy) verdict carry RepairActionTypeRebootSystem?  setNVLinkSuggestedActions, nvlink/evaluate_threshold.go:37-52:
  * a GPU with inactive links, or complete P2P coverage with no OK pair and a status outside the five "not supported" codes. */
 int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v);

@@ -897,6 +897,39 @@ def evolve_healthy_state_stored(events, devices: Optional[Dict[str, str]] = None
     return {"health": st["health"], "actions": st["actions"], "reason": reason}
 
 
+# GPU product capabilities (pkg/nvidia/product/capabilities.go:6-137)
+PRODUCT_MEM_CAPS = {"a100": 7, "b100": 7, "b200": 7, "gb200": 7, "h100": 7, "h200": 7, "a10": 4}      # :15-23; 1 containment | 2 offlining | 4 row remapping
+PRODUCT_FM = {"a100": True, "b100": True, "b200": True, "gb200": False, "gh200": False, "h100": True, "h200": True, "a10": False}   # :25-50
+
+
+def _longest_key(p: str, table: dict):
+    best = ""
+    for k in table:
+        if k in p and len(best) < len(k):
+            best = k
+    return best
+
+
+def product_mem_caps(name: str) -> int:                               # SupportedMemoryMgmtCapsByGPUProduct :119-137
+    k = _longest_key(name.lower(), PRODUCT_MEM_CAPS)
+    return PRODUCT_MEM_CAPS[k] if k else 0
+
+
+def product_fm_supported(name: str) -> bool:                          # SupportedFMByGPUProduct :56-76
+    p = name.lower()
+    if "pcie" in p:
+        return False
+    k = _longest_key(p, PRODUCT_FM)
+    return PRODUCT_FM[k] if k else False
+
+
+def product_fabric_state_supported(name: str) -> bool:                # SupportFabricStateByGPUProduct :93-116
+    p = name.lower()
+    if "pcie" in p or "gh200" in p:
+        return False
+    return "gb200" in p or "h100" in p or "h200" in p
+
+
 # --------------------------------------------------------------------------------------------
 # threshold rules
 # --------------------------------------------------------------------------------------------

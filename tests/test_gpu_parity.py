@@ -647,6 +647,82 @@ def test_fabric_pack_and_verdict(ctx):
             assert bool(g.lib().gpud_fabric_suggest_reboot(C.byref(fv))) == reboot, r["name"]
 
 
+def test_poller_fabric_record_matches_nvml(ctx):
+    """the poller's NVLink / fabric record of this GPU against the same NVML getters read through pynvml
+    (GetNVLink nvlink/nvlink.go:93-168, fabric info V3, product name), then through the pack + verdict kernels."""
+    import torch
+    pynvml = pytest.importorskip("pynvml")
+    ring = g.Ring(ctx, len(g.POLL_FIELDS), 1024, 100)
+    try:
+        poller = g.Poller(ctx, ring)
+    except g.GpudError as e:
+        ring.close()
+        pytest.skip("no NVML on this host: %s" % e)
+    pynvml.nvmlInit()
+    bus = torch.cuda.get_device_properties(0)
+    bus_id = "%04x:%02x:%02x.0" % (bus.pci_domain_id, bus.pci_bus_id, bus.pci_device_id) if hasattr(bus, "pci_bus_id") else None
+    h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode()) if bus_id else pynvml.nvmlDeviceGetHandleByIndex(0)
+    name = pynvml.nvmlDeviceGetName(h)
+    name = name.decode() if isinstance(name, bytes) else name
+    assert poller.product_name() == name
+    raw = poller.fabric_raw(0)
+    # GetNVLink: walk the links like the reference does
+    states, supported = [], True
+    for link in range(pynvml.NVML_NVLINK_MAX_LINKS):
+        try:
+            st = pynvml.nvmlDeviceGetNvLinkState(h, link)
+        except pynvml.NVMLError as e:
+            if e.value == pynvml.NVML_ERROR_NOT_SUPPORTED:
+                if not states:
+                    supported = False
+                break
+            continue
+        cnt = []
+        for c in (pynvml.NVML_NVLINK_ERROR_DL_REPLAY, pynvml.NVML_NVLINK_ERROR_DL_RECOVERY, pynvml.NVML_NVLINK_ERROR_DL_CRC_FLIT):
+            try:
+                cnt.append(pynvml.nvmlDeviceGetNvLinkErrorCounter(h, link, c))
+            except pynvml.NVMLError:
+                cnt.append(0)
+        states.append((1 if st == pynvml.NVML_FEATURE_ENABLED else 0, cnt))
+    assert raw.nvlink_supported == int(supported) and raw.n_links == len(states)
+    for i, (en, cnt) in enumerate(states):
+        assert raw.link_feature_enabled[i] == en, i
+        # error counters only grow; the two reads are milliseconds apart
+        for got, want in zip((raw.link_replay_errors[i], raw.link_recovery_errors[i], raw.link_crc_errors[i]), cnt):
+            assert 0 <= want - got <= 1000, (i, got, want)
+    # fabric info V3
+    try:
+        fi = pynvml.c_nvmlGpuFabricInfo_v3_t()
+        fi.version = pynvml.nvmlGpuFabricInfo_v3
+        pynvml.nvmlDeviceGetGpuFabricInfoV(h, C.byref(fi))
+        want_fab = (1, fi.state, fi.healthSummary, fi.status, fi.healthMask, fi.cliqueId)
+    except (pynvml.NVMLError, AttributeError):
+        want_fab = None
+    if want_fab is None:
+        assert raw.fabric_valid == 0
+    else:
+        assert (raw.fabric_valid, raw.fabric_state, raw.fabric_summary, raw.fabric_status, raw.fabric_health_mask, raw.clique_id) == want_fab
+    assert raw.system_expected_nvlink == int(O.product_fm_supported(name) or O.product_fabric_state_supported(name))
+    assert all(raw.p2p_status[j] == 0xFF for j in range(16))                      # no peers given: nothing probed
+    # the record flows through the device path like a hand-built one: pack + verdict of a one-GPU box == the oracle's
+    d = {"gpu_index": 0, "nvlink_supported": raw.nvlink_supported, "system_expected_nvlink": raw.system_expected_nvlink, "n_links": raw.n_links,
+         "link_feature_enabled": list(raw.link_feature_enabled), "link_replay_errors": list(raw.link_replay_errors),
+         "link_recovery_errors": list(raw.link_recovery_errors), "link_crc_errors": list(raw.link_crc_errors), "p2p_status": list(raw.p2p_status),
+         "fabric_valid": raw.fabric_valid, "fabric_state": raw.fabric_state, "fabric_summary": raw.fabric_summary, "fabric_status": raw.fabric_status,
+         "fabric_health_mask": raw.fabric_health_mask, "clique_id": raw.clique_id}
+    table = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    ctx.fabric_pack(raw, table.data_ptr())
+    torch.cuda.synchronize()
+    v = ctx.fabric_verdict(table.data_ptr(), 1, 0).as_dict()
+    for k, val in OF.verdict([d], 0).items():
+        assert v[k] == val, (k, v[k], val)
+    print("fabric record: product %r, nvlink_supported %d, links %d (%d enabled), fabric_valid %d state %d summary %d" % (
+        name, raw.nvlink_supported, raw.n_links, sum(raw.link_feature_enabled[i] for i in range(raw.n_links)), raw.fabric_valid, raw.fabric_state, raw.fabric_summary))
+    pynvml.nvmlShutdown()
+    poller.close()
+    ring.close()
+
+
 # ------------------------------------------------------------------------------------------------ host-side component mirror
 def test_xid_component_check_and_state(ctx):
     """C++ mirror of the xid component (csrc/host_component.cpp): Check() scans on the GPU (xid/component.go:255-311), streaming

@@ -468,3 +468,20 @@ def test_resolve_xid_event_matches_the_oracle_on_random_payloads():
         thr = int(rng.integers(1, 4))
         want = O.evolve_healthy_state_stored(events, devices, thr)
         assert _evolve_stored(events, devices, thr) == (want["health"], (want["actions"] or [0])[0], want["reason"]), events
+
+
+def test_product_capabilities_of_the_reference(golden):   # pkg/nvidia/product/capabilities_test.go:8, :168, :230
+    L = g.lib()
+    G = golden("product_caps.json")
+    assert (len(G["mem_caps"]["rows"]), len(G["fm_supported"]["rows"]), len(G["fabric_state_supported"]["rows"])) == (18, 8, 19)
+    for r in G["mem_caps"]["rows"]:
+        assert L.gpud_product_mem_caps(r["product"].encode()) == O.product_mem_caps(r["product"]) == r["caps"], r["name"]
+    for r in G["fm_supported"]["rows"]:
+        assert bool(L.gpud_product_fm_supported(r["product"].encode())) == O.product_fm_supported(r["product"]) == r["expected"], r["name"]
+    for r in G["fabric_state_supported"]["rows"]:
+        assert bool(L.gpud_product_fabric_state_supported(r["product"].encode())) == O.product_fabric_state_supported(r["product"]) == r["expected"], r["name"]
+    for name in ("NVIDIA B200", "NVIDIA GB200 NVL72", "NVIDIA GH200 480GB", "NVIDIA H200 PCIe", "NVIDIA A100-SXM4-80GB", "NVIDIA A10G", "Tesla T4", ""):
+        assert L.gpud_product_mem_caps(name.encode()) == O.product_mem_caps(name)
+        assert bool(L.gpud_product_fm_supported(name.encode())) == O.product_fm_supported(name)
+        assert bool(L.gpud_product_fabric_state_supported(name.encode())) == O.product_fabric_state_supported(name)
+    assert L.gpud_product_mem_caps(b"NVIDIA B200") == 7 and L.gpud_product_fm_supported(b"NVIDIA B200") == 1      # this framework's target

@@ -567,6 +567,20 @@ def main():
     xm["evolve"] = {"src": "%s:%d" % (HS, line), "rows": ev_rows, "devices": {"GPU-test-uuid": "0000:04:00.0"}}
     dump("xid_messages.json", xm)
 
+    # ---- GPU product capability tables (pkg/nvidia/product/capabilities_test.go) ----
+    PC = "pkg/nvidia/product/capabilities_test.go"
+    pc = {}
+    rows, src = table(PC, "TestSupportedMemoryMgmtCapsByGPUProduct")
+    pc["mem_caps"] = {"src": src, "rows": [{"name": r["name"], "product": r["gpuProductName"],
+                                            "caps": (1 if isinstance(r["expected"], dict) and r["expected"].get("ErrorContainment") else 0)
+                                                    | (2 if isinstance(r["expected"], dict) and r["expected"].get("DynamicPageOfflining") else 0)
+                                                    | (4 if isinstance(r["expected"], dict) and r["expected"].get("RowRemapping") else 0)} for r in rows]}
+    rows, src = table(PC, "TestSupportedFMByGPUProduct")
+    pc["fm_supported"] = {"src": src, "rows": [{"name": r["name"], "product": r["gpuProductName"], "expected": r["expected"]} for r in rows]}
+    rows, src = table(PC, "TestSupportFabricStateByGPUProduct")
+    pc["fabric_state_supported"] = {"src": src, "rows": [{"name": r["name"], "product": r["gpuProductName"], "expected": r["expected"]} for r in rows]}
+    dump("product_caps.json", pc)
+
     # ---- eventstore compareEvent / unmarshalIfValid tables + infiniband's kmsg dedup-window policy ----
     es = {}
     rows, src = table("pkg/eventstore/database_test.go", "TestCompareEvent")
