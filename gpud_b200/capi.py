@@ -188,6 +188,26 @@ def ib_reason(device: str, port: int, down_since: int, flap: bool) -> str:
 POLL_FIELDS = ["temperature_c", "power_mw", "clock_graphics_mhz", "clock_sm_mhz", "clock_mem_mhz", "util_gpu_pct", "util_mem_pct", "memory_used_mib"]
 
 
+class Temperature(C.Structure):
+    _fields_ = [("current_gpu_core_c", C.c_uint32), ("current_hbm_c", C.c_uint32), ("threshold_shutdown_c", C.c_uint32), ("threshold_slowdown_c", C.c_uint32),
+                ("threshold_mem_max_c", C.c_uint32), ("threshold_gpu_max_c", C.c_uint32), ("slowdown_margin_c", C.c_int32),
+                ("hbm_supported", C.c_uint8), ("margin_supported", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class PollCounters(C.Structure):
+    _fields_ = [("clock_event_reasons", C.c_uint64), ("ecc_aggregate_corrected", C.c_uint64), ("ecc_aggregate_uncorrected", C.c_uint64),
+                ("ecc_volatile_corrected", C.c_uint64), ("ecc_volatile_uncorrected", C.c_uint64), ("clock_events_supported", C.c_uint32),
+                ("ecc_read_mask", C.c_uint32)]
+
+
+def temperature_check(t: "Temperature", margin_threshold_c: int = 0) -> int:
+    bits = C.c_int32()
+    rc = lib().gpud_temperature_check(C.byref(t), margin_threshold_c, C.byref(bits))
+    if rc:
+        raise GpudError(rc, "gpud_temperature_check")
+    return bits.value
+
+
 class Poller:
     """host NVML poller feeding a ring with raw uint32 poll rows (gpud_poller_*)"""
 
@@ -212,6 +232,16 @@ class Poller:
         arr = (C.c_char_p * max(1, len(peer_bus_ids)))(*[b.encode() if b else None for b in peer_bus_ids])
         self.ctx._check(self._L.gpud_poller_fabric_raw(self._h, gpu_index, arr, len(peer_bus_ids), C.byref(raw)))
         return raw
+
+    def temperature(self) -> "Temperature":
+        t = Temperature()
+        self.ctx._check(self._L.gpud_poller_temperature(self._h, C.byref(t)))
+        return t
+
+    def counters(self) -> "PollCounters":
+        c = PollCounters()
+        self.ctx._check(self._L.gpud_poller_counters(self._h, C.byref(c)))
+        return c
 
     def product_name(self) -> str:
         buf = C.create_string_buffer(96)
@@ -287,7 +317,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -326,6 +356,8 @@ def lib() -> C.CDLL:
         "gpud_ib_scan": (i32, [vp, i32, vp, vp, i64, i64, i64, i32, vp]), "gpud_ib_reason": (i32, [C.c_char_p, C.c_uint32, i64, i32, vp, i32]),
         "gpud_poller_create": (i32, [vp, i32, vp, vp]), "gpud_poller_destroy": (None, [vp]), "gpud_poller_poll": (i32, [vp, i64, i64]),
         "gpud_poller_last_rows": (i32, [vp, vp, i64, vp, vp]),
+        "gpud_poller_temperature": (i32, [vp, C.POINTER(Temperature)]), "gpud_temperature_check": (i32, [C.POINTER(Temperature), i32, vp]),
+        "gpud_poller_counters": (i32, [vp, C.POINTER(PollCounters)]),
         "gpud_poller_fabric_raw": (i32, [vp, C.c_uint32, vp, i32, C.POINTER(FabricRaw)]), "gpud_poller_product_name": (i32, [vp, vp, i32]),
         "gpud_ring_counts": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "gpud_ring_reduce": (i32, [vp]), "gpud_ring_sync": (i32, [vp]),
@@ -358,7 +390,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule)):
+    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters)):
         if L.gpud_sizeof(which) != C.sizeof(st):
             raise GpudError(-1, "ABI layout mismatch for %s: C %d vs ctypes %d" % (st.__name__, L.gpud_sizeof(which), C.sizeof(st)))
     _lib = L

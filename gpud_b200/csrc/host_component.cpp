@@ -707,6 +707,20 @@ int32_t gpudh_hw_slowdown_reason(const int64_t* ev, int32_t n, int64_t now, int6
   snprintf(out, (size_t)cap, "%s", v.reason.c_str());
   return (int32_t)v.inspect;
 }
+}  // extern "C" (flat test entries)
+
+// public form of the temperature rules over a poller reading
+extern "C" int32_t gpud_temperature_check(const gpud_temperature* t, int32_t margin_threshold_c, int32_t* bits) {
+  if (!t || !bits) return GPUD_E_INVALID;
+  gpud::TemperatureReading r;
+  r.current_gpu_core = t->current_gpu_core_c; r.threshold_gpu_max = t->threshold_gpu_max_c; r.current_hbm = t->current_hbm_c;
+  r.threshold_mem_max = t->threshold_mem_max_c; r.hbm_supported = t->hbm_supported != 0; r.threshold_slowdown = t->threshold_slowdown_c;
+  r.slowdown_margin = t->slowdown_margin_c; r.margin_supported = t->margin_supported != 0;
+  *bits = gpud::evaluate_temperature(r, margin_threshold_c);
+  return GPUD_OK;
+}
+
+extern "C" {
 int32_t gpudh_temperature(uint32_t cur, uint32_t gmax, uint32_t hbm, uint32_t mmax, int32_t hbm_supported, uint32_t slowdown, int32_t margin, int32_t margin_supported,
                           int32_t mthr) {
   gpud::TemperatureReading t;

@@ -45,6 +45,10 @@ struct Nvml {
   nvmlReturn_t (*link_errors)(nvmlDevice_t, unsigned int, int, unsigned long long*) = nullptr;
   nvmlReturn_t (*fabric_v)(nvmlDevice_t, void*) = nullptr;
   nvmlReturn_t (*p2p)(nvmlDevice_t, nvmlDevice_t, int, int*) = nullptr;
+  nvmlReturn_t (*temp_threshold)(nvmlDevice_t, int, unsigned int*) = nullptr;
+  nvmlReturn_t (*margin_temp)(nvmlDevice_t, void*) = nullptr;
+  nvmlReturn_t (*clock_reasons)(nvmlDevice_t, unsigned long long*) = nullptr;
+  nvmlReturn_t (*ecc_total)(nvmlDevice_t, int, int, unsigned long long*) = nullptr;
 };
 
 Nvml* nvml() {
@@ -67,6 +71,11 @@ Nvml* nvml() {
       *(void**)&n.link_errors = dlsym(n.so, "nvmlDeviceGetNvLinkErrorCounter");
       *(void**)&n.fabric_v = dlsym(n.so, "nvmlDeviceGetGpuFabricInfoV");           // driver >= 550 (fabric_state.go:262-267); absent symbol = not supported
       *(void**)&n.p2p = dlsym(n.so, "nvmlDeviceGetP2PStatus");
+      *(void**)&n.temp_threshold = dlsym(n.so, "nvmlDeviceGetTemperatureThreshold");
+      *(void**)&n.margin_temp = dlsym(n.so, "nvmlDeviceGetMarginTemperature");
+      *(void**)&n.clock_reasons = dlsym(n.so, "nvmlDeviceGetCurrentClocksEventReasons");
+      if (!n.clock_reasons) *(void**)&n.clock_reasons = dlsym(n.so, "nvmlDeviceGetCurrentClocksThrottleReasons");   // the pre-535 name of the same getter
+      *(void**)&n.ecc_total = dlsym(n.so, "nvmlDeviceGetTotalEccErrors");
       if (!n.init || !n.by_pci || !n.temperature || !n.power || !n.clock || !n.util || !n.memory || n.init() != 0) { dlclose(n.so); n.so = nullptr; }
     }
   }
@@ -251,6 +260,68 @@ extern "C" int32_t gpud_poller_fabric_raw(gpud_poller* p, uint32_t gpu_index, co
       int st = 6;
       if (N->p2p(p->h, peer, 2 /* NVML_P2P_CAPS_INDEX_NVLINK */, &st) != 0) continue;           // a failed probe stays unprobed (component.go:430-447)
       out->p2p_status[j] = (uint8_t)((st >= 0 && st <= 5) ? st : 6);                            // toP2PStatusCode: anything else is "U"
+    }
+  }
+  return GPUD_OK;
+}
+
+// GetTemperature (temperature/temperature.go:78-221): current GPU and HBM sensors, the thermal margin, the four thresholds.  A
+// getter that fails leaves its field 0 / unsupported like the reference; GPU lost / requires reset end the read.
+extern "C" int32_t gpud_poller_temperature(gpud_poller* p, gpud_temperature* out) {
+  if (!p || !out) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return GPUD_E_UNSUPPORTED;
+  memset(out, 0, sizeof *out);
+  auto fatal = [&](nvmlReturn_t rc) -> int32_t {
+    if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+    if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
+    return GPUD_OK;
+  };
+  unsigned int v = 0;
+  nvmlReturn_t rc = N->temperature(p->h, 0 /* NVML_TEMPERATURE_GPU */, &v);
+  if (rc == 0) out->current_gpu_core_c = v; else if (int32_t e = fatal(rc)) return e;
+  rc = N->temperature(p->h, 1 /* temperatureSensorMemory, temperature.go:75 */, &v);
+  if (rc == 0) { out->current_hbm_c = v; out->hbm_supported = 1; } else if (int32_t e = fatal(rc)) return e;
+  if (N->margin_temp) {
+    struct { unsigned int version; int margin; } mt = {(unsigned int)(8u | (1u << 24)) /* nvmlMarginTemperature_v1 */, 0};
+    rc = N->margin_temp(p->h, &mt);
+    if (rc == 0) { out->slowdown_margin_c = mt.margin; out->margin_supported = 1; } else if (int32_t e = fatal(rc)) return e;
+  }
+  if (N->temp_threshold) {
+    uint32_t* dst[4] = {&out->threshold_shutdown_c, &out->threshold_slowdown_c, &out->threshold_mem_max_c, &out->threshold_gpu_max_c};
+    for (int t = 0; t < 4; ++t) {                  // NVML_TEMPERATURE_THRESHOLD_SHUTDOWN, _SLOWDOWN, _MEM_MAX, _GPU_MAX = 0..3
+      rc = N->temp_threshold(p->h, t, &v);
+      if (rc == 0) *dst[t] = v; else if (int32_t e = fatal(rc)) return e;
+    }
+  }
+  return GPUD_OK;
+}
+
+// GetClockEvents (hw-slowdown/clock_events.go:111-166: the reasons bitmask, decoded by gpud_clock_event_reasons) and the four ECC
+// totals of GetECCErrors (ecc/ecc_errors.go:136-240).
+extern "C" int32_t gpud_poller_counters(gpud_poller* p, gpud_poll_counters* out) {
+  if (!p || !out) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return GPUD_E_UNSUPPORTED;
+  memset(out, 0, sizeof *out);
+  if (N->clock_reasons) {
+    unsigned long long m = 0;
+    const nvmlReturn_t rc = N->clock_reasons(p->h, &m);
+    if (rc == 0) { out->clock_event_reasons = m; out->clock_events_supported = 1; }
+    else if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+    else if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
+    else if (!is_not_supported(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "failed to get device clock event reasons: %s", N->err ? N->err(rc) : "error");
+  }
+  if (N->ecc_total) {
+    // (errorType, counterType): aggregate corrected / uncorrected, volatile corrected / uncorrected -- the reference's order
+    const int q[4][2] = {{0, 1}, {1, 1}, {0, 0}, {1, 0}};   // NVML_MEMORY_ERROR_TYPE_CORRECTED 0 / UNCORRECTED 1 ; NVML_VOLATILE_ECC 0 / AGGREGATE_ECC 1
+    uint64_t* dst[4] = {&out->ecc_aggregate_corrected, &out->ecc_aggregate_uncorrected, &out->ecc_volatile_corrected, &out->ecc_volatile_uncorrected};
+    for (int i = 0; i < 4; ++i) {
+      unsigned long long c = 0;
+      const nvmlReturn_t rc = N->ecc_total(p->h, q[i][0], q[i][1], &c);
+      if (rc == 0) { *dst[i] = c; out->ecc_read_mask |= 1u << i; }
+      else if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+      else if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
     }
   }
   return GPUD_OK;

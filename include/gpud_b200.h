@@ -114,6 +114,27 @@ void gpud_poller_destroy(gpud_poller* poller);
 int32_t gpud_poller_poll(gpud_poller* poller, int64_t n_polls, int64_t interval_us);
 /* The rows of the last push batch (at most 16384) as they went over PCIe, and the wall time of the last poll call. */
 int32_t gpud_poller_last_rows(gpud_poller* poller, uint32_t* rows, int64_t cap_rows, int64_t* n_rows, double* seconds);
+/* GetTemperature (temperature/temperature.go:78-221) for this poller's GPU, and the per-GPU rules of the temperature component's
+ * Check (temperature/component.go:206-248) over such a reading: *bits = 1 GPU core above its max-operating threshold | 2 HBM above
+ * the memory max | 4 thermal margin at or below margin_threshold_c (0 = rule off, temperature/threshold.go:13); the component's
+ * reason is the first of margin, GPU, HBM (:273-287), its health Degraded when any bit is set. */
+typedef struct {
+  uint32_t current_gpu_core_c, current_hbm_c;
+  uint32_t threshold_shutdown_c, threshold_slowdown_c, threshold_mem_max_c, threshold_gpu_max_c;
+  int32_t slowdown_margin_c;
+  uint8_t hbm_supported, margin_supported, pad[2];
+} gpud_temperature;
+int32_t gpud_poller_temperature(gpud_poller* poller, gpud_temperature* out);
+int32_t gpud_temperature_check(const gpud_temperature* t, int32_t margin_threshold_c, int32_t* bits);
+/* GetClockEvents' reasons bitmask (hw-slowdown/clock_events.go:111-166; decode with gpud_clock_event_reasons) and the four ECC
+ * totals of ecc/ecc_errors.go:136-240; ecc_read_mask bit 0..3 = aggregate corrected, aggregate uncorrected, volatile corrected,
+ * volatile uncorrected were read. */
+typedef struct {
+  uint64_t clock_event_reasons;
+  uint64_t ecc_aggregate_corrected, ecc_aggregate_uncorrected, ecc_volatile_corrected, ecc_volatile_uncorrected;
+  uint32_t clock_events_supported, ecc_read_mask;
+} gpud_poll_counters;
+int32_t gpud_poller_counters(gpud_poller* poller, gpud_poll_counters* out);
 int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
 /* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
 int32_t gpud_ring_reduce(gpud_ring* ring);

@@ -104,3 +104,61 @@ def test_fabric_gather_nccl_one_process_per_gpu():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_real_box_nvlink_view_from_nvml():
+    """the whole path on the box's real state: every GPU's poller reads its NVLink / fabric record and probes NVLink P2P against its
+    peers (nvlink/nvlink.go:93-168, p2p.go:21-50), the records meet through the peer-memory gather, and the replicated verdict equals
+    the oracle's on the same records; the P2P codes equal pynvml's."""
+    import torch
+    import gpud_b200 as g
+    pynvml = pytest.importorskip("pynvml")
+    n = min(_n_gpus(), 8)
+    ctx = g.Context(list(range(n)))
+    props = [torch.cuda.get_device_properties(i) for i in range(n)]
+    bus = ["%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id) for p in props]
+    # the reference orders GPUs by UUID (component.go:185-190); any fixed order gives the same verdict, bus order is used here
+    rings, pollers, raws = [], [], []
+    try:
+        for i in range(n):
+            rings.append(g.Ring(ctx, len(g.POLL_FIELDS), 1024, 100, dev=i))
+            pollers.append(g.Poller(ctx, rings[-1], dev=i))
+    except g.GpudError as e:
+        pytest.skip("no NVML on this host: %s" % e)
+    for i in range(n):
+        raws.append(pollers[i].fabric_raw(i, bus))
+    pynvml.nvmlInit()
+    hs = [pynvml.nvmlDeviceGetHandleByPciBusId(b.encode()) for b in bus]
+    for i in range(n):
+        assert raws[i].gpu_index == i and raws[i].p2p_status[i] == 0xFF
+        for j in range(n):
+            if i == j:
+                continue
+            try:
+                want = pynvml.nvmlDeviceGetP2PStatus(hs[i], hs[j], pynvml.NVML_P2P_CAPS_INDEX_NVLINK)
+                want = want if 0 <= want <= 5 else 6
+            except pynvml.NVMLError:
+                want = 0xFF
+            assert raws[i].p2p_status[j] == want, (i, j, raws[i].p2p_status[j], want)
+    pynvml.nvmlShutdown()
+    gpus = [{"gpu_index": r.gpu_index, "nvlink_supported": r.nvlink_supported, "system_expected_nvlink": r.system_expected_nvlink, "n_links": r.n_links,
+             "link_feature_enabled": list(r.link_feature_enabled), "link_replay_errors": list(r.link_replay_errors),
+             "link_recovery_errors": list(r.link_recovery_errors), "link_crc_errors": list(r.link_crc_errors), "p2p_status": list(r.p2p_status),
+             "fabric_valid": r.fabric_valid, "fabric_state": r.fabric_state, "fabric_summary": r.fabric_summary, "fabric_status": r.fabric_status,
+             "fabric_health_mask": r.fabric_health_mask, "clique_id": r.clique_id} for r in raws]
+    for at_least in (0, n):
+        recs, verdicts = ctx.fabric_gather_p2p(raws, at_least)
+        want = OF.verdict(gpus, at_least)
+        for v in verdicts:
+            vd = v.as_dict()
+            for k, val in want.items():
+                assert vd[k] == val, (k, vd[k], val)
+    vd = verdicts[0].as_dict()
+    print("box view: %d GPUs, nvlink health %d reason %d, active %d inactive %d, p2p ok pairs %d / %d, fabric healthy %d" % (
+        n, vd["nvlink_health"], vd["nvlink_reason"], vd["active"], vd["inactive"], vd["p2p_ok_pairs"], vd["p2p_expected_pairs"], vd["fabric_healthy"]))
+    for p in pollers:
+        p.close()
+    for r in rings:
+        r.close()
+    ctx.close()

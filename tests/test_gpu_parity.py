@@ -647,6 +647,63 @@ def test_fabric_pack_and_verdict(ctx):
             assert bool(g.lib().gpud_fabric_suggest_reboot(C.byref(fv))) == reboot, r["name"]
 
 
+def test_poller_temperature_and_counters_match_nvml(ctx):
+    """GetTemperature (temperature/temperature.go:78-221), GetClockEvents' bitmask (hw-slowdown/clock_events.go:111-166) and the ECC
+    totals (ecc/ecc_errors.go:136-240) read by the poller against the same getters through pynvml; the temperature rules on the reading"""
+    import torch
+    pynvml = pytest.importorskip("pynvml")
+    ring = g.Ring(ctx, len(g.POLL_FIELDS), 1024, 100)
+    try:
+        poller = g.Poller(ctx, ring)
+    except g.GpudError as e:
+        ring.close()
+        pytest.skip("no NVML on this host: %s" % e)
+    pynvml.nvmlInit()
+    pr = torch.cuda.get_device_properties(0)
+    h = pynvml.nvmlDeviceGetHandleByPciBusId(("%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+
+    def nv(fn, *a):
+        try:
+            return fn(h, *a)
+        except pynvml.NVMLError:
+            return None
+    t = poller.temperature()
+    cur = nv(pynvml.nvmlDeviceGetTemperature, 0)
+    assert cur is not None and abs(int(t.current_gpu_core_c) - cur) <= 3 and 10 <= t.current_gpu_core_c <= 110
+    hbm = nv(pynvml.nvmlDeviceGetTemperature, 1)
+    assert t.hbm_supported == int(hbm is not None) and (hbm is None or abs(int(t.current_hbm_c) - hbm) <= 3)
+    margin = nv(pynvml.nvmlDeviceGetMarginTemperature) if hasattr(pynvml, "nvmlDeviceGetMarginTemperature") else None
+    assert t.margin_supported == int(margin is not None) and (margin is None or abs(t.slowdown_margin_c - margin) <= 3)
+    for got, which in ((t.threshold_shutdown_c, 0), (t.threshold_slowdown_c, 1), (t.threshold_mem_max_c, 2), (t.threshold_gpu_max_c, 3)):
+        want = nv(pynvml.nvmlDeviceGetTemperatureThreshold, which)
+        assert got == (want or 0), which
+    d = {"CurrentCelsiusGPUCore": t.current_gpu_core_c, "CurrentCelsiusHBM": t.current_hbm_c, "HBMTemperatureSupported": bool(t.hbm_supported),
+         "ThresholdCelsiusSlowdown": t.threshold_slowdown_c, "ThresholdCelsiusMemMax": t.threshold_mem_max_c, "ThresholdCelsiusGPUMax": t.threshold_gpu_max_c,
+         "ThresholdCelsiusSlowdownMargin": t.slowdown_margin_c, "MarginTemperatureSupported": bool(t.margin_supported)}
+    for thr in (0, 5, 200):
+        bits = g.temperature_check(t, thr)
+        health, cls = O.temperature_check(d, thr)
+        assert ("margin" if bits & 4 else ("gpu" if bits & 1 else ("hbm" if bits & 2 else ""))) == cls and (bits != 0) == (health == "Degraded"), thr
+    assert g.temperature_check(t, 0) == 0, "an idle test GPU is inside its limits"
+    c = poller.counters()
+    want = nv(pynvml.nvmlDeviceGetCurrentClocksEventReasons) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else nv(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)
+    assert c.clock_events_supported == int(want is not None)
+    if want is not None:
+        idle_bits = 0x1 | 0x2 | 0x4 | 0x100                       # gpu idle / app clocks / sw power cap / display: may flip between the two reads
+        assert (c.clock_event_reasons & ~idle_bits) == (want & ~idle_bits), (hex(c.clock_event_reasons), hex(want))
+    for i, (et, ct, got) in enumerate(((0, 1, c.ecc_aggregate_corrected), (1, 1, c.ecc_aggregate_uncorrected), (0, 0, c.ecc_volatile_corrected), (1, 0, c.ecc_volatile_uncorrected))):
+        want = nv(pynvml.nvmlDeviceGetTotalEccErrors, et, ct)
+        assert bool(c.ecc_read_mask & (1 << i)) == (want is not None), i
+        if want is not None:
+            assert 0 <= want - got <= 100, (i, got, want)
+    print("temperature: gpu %d C hbm %d C (supported %d) margin %d (supported %d) thresholds shutdown %d slowdown %d mem_max %d gpu_max %d; clock reasons 0x%x; ecc mask 0x%x" % (
+        t.current_gpu_core_c, t.current_hbm_c, t.hbm_supported, t.slowdown_margin_c, t.margin_supported, t.threshold_shutdown_c, t.threshold_slowdown_c,
+        t.threshold_mem_max_c, t.threshold_gpu_max_c, c.clock_event_reasons, c.ecc_read_mask))
+    pynvml.nvmlShutdown()
+    poller.close()
+    ring.close()
+
+
 def test_poller_fabric_record_matches_nvml(ctx):
     """the poller's NVLink / fabric record of this GPU against the same NVML getters read through pynvml
     (GetNVLink nvlink/nvlink.go:93-168, fabric info V3, product name), then through the pack + verdict kernels."""

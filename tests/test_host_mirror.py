@@ -303,6 +303,12 @@ def test_temperature_checks_of_the_reference(golden):   # temperature/component_
                                    t.get("ThresholdCelsiusSlowdownMargin", 0), int(t.get("MarginTemperatureSupported", False)), thr)
         got_cls = "margin" if bits & 4 else ("gpu" if bits & 1 else ("hbm" if bits & 2 else ""))
         assert got_cls == cls and (bits != 0) == (health == "Degraded"), r["name"]
+        # the public entry over the reading a poller returns
+        pt = g.Temperature()
+        pt.current_gpu_core_c, pt.threshold_gpu_max_c, pt.current_hbm_c = t.get("CurrentCelsiusGPUCore", 0), t.get("ThresholdCelsiusGPUMax", 0), t.get("CurrentCelsiusHBM", 0)
+        pt.threshold_mem_max_c, pt.hbm_supported, pt.threshold_slowdown_c = t.get("ThresholdCelsiusMemMax", 0), int(t.get("HBMTemperatureSupported", False)), t.get("ThresholdCelsiusSlowdown", 0)
+        pt.slowdown_margin_c, pt.margin_supported = t.get("ThresholdCelsiusSlowdownMargin", 0), int(t.get("MarginTemperatureSupported", False))
+        assert g.temperature_check(pt, thr) == bits, r["name"]
 
 
 # ---- xid event message / health-state reason (xid/health_state.go:130-281; health_state_test.go:299-942) --------------------
