@@ -482,6 +482,61 @@ extern "C" int32_t gpud_product_fabric_state_supported(const char* product_name)
   return (p.find("gb200") != std::string::npos || p.find("h100") != std::string::npos || p.find("h200") != std::string::npos) ? 1 : 0;
 }
 
+// The reason string of the nvlink component's check result for a verdict (nvlink/evaluate_threshold.go:11-35,77-188;
+// component.go:307 for the no-issue case).  gpu_uuids[i] names gpu_index i (the reference lists UUIDs in sorted order, which is the
+// gpu_index order); a missing name is rendered as "GPU-<index>".
+extern "C" int32_t gpud_fabric_reason(const gpud_fabric_verdict* v, const char* const* gpu_uuids, int32_t n_uuids, char* out, int32_t cap) {
+  if (!v || !out || cap <= 0 || n_uuids < 0) return -1;
+  auto uuid = [&](int i) -> std::string {
+    if (gpu_uuids && i < n_uuids && gpu_uuids[i] && *gpu_uuids[i]) return gpu_uuids[i];
+    return "GPU-" + std::to_string(i);
+  };
+  auto list = [&](uint32_t mask) {
+    std::string o;
+    for (int i = 0; i < GPUD_MAX_GPUS; ++i)
+      if (mask & (1u << i)) { if (!o.empty()) o += ","; o += uuid(i); }
+    return o;
+  };
+  // appendNVLinkFailureDetails (:16-35)
+  auto details = [&](std::string reason) {
+    std::vector<std::string> parts;
+    if (v->p2p_probed_pairs > 0 && v->p2p_ok_pairs == 0 && v->p2p_observed_status_mask != 0) {
+      static const char* const kCode[7] = {"OK", "CNS", "GNS", "TNS", "DR", "NS", "U"};      // p2p.go:11-19
+      std::vector<std::string> codes;
+      for (int c = 0; c < 7; ++c) if (v->p2p_observed_status_mask & (1u << c)) codes.push_back(kCode[c]);
+      std::sort(codes.begin(), codes.end());                                                // sortedKeys
+      std::string j;
+      for (size_t i = 0; i < codes.size(); ++i) { if (i) j += ","; j += codes[i]; }
+      parts.push_back("peer nvlink p2p statuses=" + j);
+    }
+    if (v->inactive_mask) parts.push_back("inactive nvlinks=" + list(v->inactive_mask));
+    if (v->unsupported_mask) parts.push_back("unsupported nvlinks=" + list(v->unsupported_mask));
+    if (parts.empty()) return reason;
+    std::string j;
+    for (size_t i = 0; i < parts.size(); ++i) { if (i) j += "; "; j += parts[i]; }
+    return reason + " (" + j + ")";
+  };
+  char buf[256];
+  std::string o;
+  switch (v->nvlink_reason) {
+    case GPUD_NVLINK_NO_ISSUE: snprintf(buf, sizeof buf, "all %d GPU(s) were checked, no nvlink issue found", v->n_gpus); o = buf; break;
+    case GPUD_NVLINK_P2P_FAILURE:
+      snprintf(buf, sizeof buf, "no GPU pairs report NVLink P2P connectivity on %d-GPU NVLink-capable system", v->n_gpus); o = details(buf); break;
+    case GPUD_NVLINK_NO_ACTIVE_LINKS:
+      snprintf(buf, sizeof buf, "no GPUs report active nvlink links on %d-GPU NVLink-capable system", v->n_gpus); o = details(buf); break;
+    case GPUD_NVLINK_THRESHOLD_SATISFIED:
+      snprintf(buf, sizeof buf, "nvlink threshold satisfied: require >=%d GPUs with all links active; got %d", v->required, v->active); o = buf; break;
+    case GPUD_NVLINK_THRESHOLD_VIOLATED:
+      snprintf(buf, sizeof buf, "nvlink threshold violated: require >=%d GPUs with all links active; got %d", v->required, v->active); o = details(buf); break;
+    case GPUD_NVLINK_NO_THRESHOLD: o = "nvlink threshold not set (skipped evaluation)"; break;
+    case GPUD_NVLINK_NO_DATA: o = "no nvlink data (skipped evaluation)"; break;
+    default: return -1;
+  }
+  if ((int)o.size() + 1 > cap) return -1;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return (int32_t)o.size();
+}
+
 // setNVLinkSuggestedActions (nvlink/evaluate_threshold.go:37-52) + peerNVLinkStatusesSuggestReboot (component.go:398-415): does an
 // unhealthy verdict come with RepairActionTypeRebootSystem?
 extern "C" int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v) {

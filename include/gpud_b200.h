@@ -459,6 +459,10 @@ int32_t gpud_poller_product_name(gpud_poller* poller, char* out, int32_t cap);  
 /* Does this (unhealthy) verdict carry RepairActionTypeRebootSystem?  setNVLinkSuggestedActions, nvlink/evaluate_threshold.go:37-52:
  * a GPU with inactive links, or complete P2P coverage with no OK pair and a status outside the five "not supported" codes. */
 int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v);
+/* The nvlink check result's reason for a verdict, as the reference words it (nvlink/evaluate_threshold.go:11-35,77-188; the
+ * no-issue text of component.go:307): gpu_uuids[i] names gpu_index i in the "inactive nvlinks=" / "unsupported nvlinks=" lists
+ * (NULL or short: "GPU-<i>").  Returns the length, -1 if it does not fit. */
+int32_t gpud_fabric_reason(const gpud_fabric_verdict* v, const char* const* gpu_uuids, int32_t n_uuids, char* out, int32_t cap);
 
 /* Single-rank pieces (one process per GPU; the collective itself is done by the host plumbing, e.g.
  * torch.distributed / ncclAllGather on `dev_send` -> `dev_all`): */

@@ -129,3 +129,34 @@ def suggest_reboot(v: Dict) -> bool:
     complete = v["p2p_expected_pairs"] != 0 and v["p2p_probed_pairs"] == v["p2p_expected_pairs"]
     other = v["p2p_observed_status_mask"] & ~0b0111110
     return v["inactive"] > 0 or (complete and v["p2p_ok_pairs"] == 0 and other != 0)
+
+
+P2P_CODES = ["OK", "CNS", "GNS", "TNS", "DR", "NS", "U"]                       # nvlink/p2p.go:11-19
+
+
+def reason_string(v: Dict, uuids: List[str]) -> str:
+    """cr.reason after evaluateHealthStateWithThresholds (nvlink/evaluate_threshold.go:11-35,77-188; component.go:307)"""
+    def names(mask):
+        return ",".join(uuids[i] if i < len(uuids) and uuids[i] else "GPU-%d" % i for i in range(16) if mask >> i & 1)
+
+    def details(reason):
+        parts = []
+        if v["p2p_probed_pairs"] > 0 and v["p2p_ok_pairs"] == 0 and v["p2p_observed_status_mask"]:
+            parts.append("peer nvlink p2p statuses=" + ",".join(sorted(P2P_CODES[c] for c in range(7) if v["p2p_observed_status_mask"] >> c & 1)))
+        if v["inactive_mask"]:
+            parts.append("inactive nvlinks=" + names(v["inactive_mask"]))
+        if v["unsupported_mask"]:
+            parts.append("unsupported nvlinks=" + names(v["unsupported_mask"]))
+        return reason if not parts else "%s (%s)" % (reason, "; ".join(parts))
+    r, n = v["nvlink_reason"], v["n_gpus"]
+    if r == 0:
+        return "all %d GPU(s) were checked, no nvlink issue found" % n
+    if r == 1:
+        return details("no GPU pairs report NVLink P2P connectivity on %d-GPU NVLink-capable system" % n)
+    if r == 2:
+        return details("no GPUs report active nvlink links on %d-GPU NVLink-capable system" % n)
+    if r == 3:
+        return "nvlink threshold satisfied: require >=%d GPUs with all links active; got %d" % (v["required"], v["active"])
+    if r == 4:
+        return details("nvlink threshold violated: require >=%d GPUs with all links active; got %d" % (v["required"], v["active"]))
+    return {5: "nvlink threshold not set (skipped evaluation)", 6: "no nvlink data (skipped evaluation)"}[r]

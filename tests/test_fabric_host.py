@@ -202,3 +202,27 @@ def test_threshold_vectors_of_the_reference(golden):
         assert bool(g.lib().gpud_fabric_suggest_reboot(C.byref(fv))) == OF.suggest_reboot(v), r["name"]
         if len(r["active"]) + len(r["inactive"]) + len(r["unsupported"]) == len(r["nvlinks"]) > 0:      # the test listed every GPU
             assert (v["active"], v["inactive"], v["unsupported"]) == (len(r["active"]), len(r["inactive"]), len(r["unsupported"])), r["name"]
+        # the reason text: the fragments / exact strings the reference's test asserts (constants resolved from evaluate_threshold.go:11-14)
+        uu = [e["uuid"] for e in r["nvlinks"]]
+        text = OF.reason_string(v, uu)
+        assert g.fabric_reason(fv, uu) == text, r["name"]
+        for frag in r["want_reason_contains"]:
+            assert frag in text, (r["name"], frag, text)
+        eq = {"reasonNoNVLinkData": "no nvlink data (skipped evaluation)", "reasonNoThresholdConfigured": "nvlink threshold not set (skipped evaluation)"}.get(r["want_reason_equal"], r["want_reason_equal"])
+        if eq and eq != "existing reason":               # "existing reason": the test pre-set cr.reason to a placeholder that evaluate leaves alone
+            assert text == eq, (r["name"], text)
+
+
+def test_fabric_reason_strings_on_the_scenarios():
+    import gpud_b200 as g
+    for name in SCENARIOS:
+        for n in (8,):
+            gpus, at_least = scenario(name, n)
+            v = OF.verdict(gpus, min(at_least, n))
+            fv = g.FabricVerdict()
+            for k, val in v.items():
+                if k != "fabric_issue_bits":
+                    setattr(fv, k, val)
+            uu = ["GPU-%08x" % (i * 2654435761 % 2 ** 32) for i in range(n)]
+            assert g.fabric_reason(fv, uu) == OF.reason_string(v, uu), (name, n)
+            assert g.fabric_reason(fv) == OF.reason_string(v, [])          # unnamed GPUs render as GPU-<index>
