@@ -226,3 +226,22 @@ def test_fabric_reason_strings_on_the_scenarios():
             uu = ["GPU-%08x" % (i * 2654435761 % 2 ** 32) for i in range(n)]
             assert g.fabric_reason(fv, uu) == OF.reason_string(v, uu), (name, n)
             assert g.fabric_reason(fv) == OF.reason_string(v, [])          # unnamed GPUs render as GPU-<index>
+
+
+def test_nvlink_states_helpers_of_the_reference():
+    """NVLinkStates.AllFeatureEnabled / Total*Errors (nvlink/nvlink.go:34-68) as the verdict sees them: the tables of
+    nvlink_test.go:57-93 (two links on / one off / no states) and :95-127 (10+15, 20+25, 30+35)"""
+    def one(enabled, replay=(), recovery=(), crc=()):
+        d = gpu(0, 1, n_links=len(enabled), enabled=(list(enabled) + [0] * 18)[:18], p2p=0xFF)
+        d["link_replay_errors"] = (list(replay) + [0] * 18)[:18]
+        d["link_recovery_errors"] = (list(recovery) + [0] * 18)[:18]
+        d["link_crc_errors"] = (list(crc) + [0] * 18)[:18]
+        return OF.verdict([d], 0)
+    v = one([1, 1])
+    assert (v["active"], v["inactive"]) == (1, 0)                      # "All links enabled" -> AllFeatureEnabled true, States non-empty
+    v = one([1, 0])
+    assert (v["active"], v["inactive"]) == (0, 1)                      # "Some links disabled"
+    v = one([])
+    assert (v["active"], v["inactive"]) == (0, 1)                      # "Empty states": AllFeatureEnabled() is true but len(States) == 0 (component.go:271-289)
+    v = one([1, 1], (10, 15), (20, 25), (30, 35))
+    assert (v["total_replay"], v["total_recovery"], v["total_crc"]) == (25, 45, 65)
