@@ -127,6 +127,12 @@ class Store:
         self._check(self._L.gpud_store_insert_xid_hits(self._h, table.encode(), arr, len(hits), fallback_unix, boot_unix, 1 if raw_kmsg else 0, C.byref(n)))
         return n.value
 
+    def insert_sxid_hits(self, table, hits, fallback_unix=0, boot_unix=0, raw_kmsg=False) -> int:
+        arr = (XidHit * max(1, len(hits)))(*hits)
+        n = C.c_int32()
+        self._check(self._L.gpud_store_insert_sxid_hits(self._h, table.encode(), arr, len(hits), fallback_unix, boot_unix, 1 if raw_kmsg else 0, C.byref(n)))
+        return n.value
+
     def syncer(self, component: str):
         h = C.c_void_p()
         self._check(self._L.gpud_kmsg_syncer_create(self._h, component.encode(), C.byref(h)))
@@ -328,7 +334,7 @@ SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destr
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
            "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
-           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
+           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
@@ -381,7 +387,8 @@ def lib() -> C.CDLL:
         "gpud_xid_description": (C.c_char_p, [i32, i32]), "gpud_xid_mnemonic": (C.c_char_p, [i32]),
         "gpud_sxid_name": (C.c_char_p, [i32]), "gpud_nvlink_rule_hint": (C.c_char_p, [i32]),
         "gpud_sxid_reason": (i32, [i64, C.c_char_p, vp, i32]),
-        "gpud_xid_get_detail": (i32, [i32, vp, vp, vp]),
+        "gpud_xid_get_detail": (i32, [i32, vp, vp, vp]), "gpud_sxid_get_detail": (i32, [i32, vp, vp, vp]),
+        "gpud_store_insert_sxid_hits": (i32, [vp, C.c_char_p, vp, i64, i64, i64, i32, vp]),
         "gpud_product_mem_caps": (i32, [C.c_char_p]), "gpud_product_fm_supported": (i32, [C.c_char_p]), "gpud_product_fabric_state_supported": (i32, [C.c_char_p]),
         "gpud_xid_detail": (i32, [i32, i32, C.c_uint32, vp, vp, vp, vp, vp]),
         "gpud_xid_build_message": (i32, [C.c_uint64, i32, C.c_uint32, C.c_char_p, C.c_char_p, C.c_char_p, vp, i32]),

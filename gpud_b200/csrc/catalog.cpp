@@ -359,6 +359,20 @@ extern "C" int32_t gpud_xid_get_detail(int32_t xid, int32_t* event_type, int32_t
   return 1;
 }
 
+// sxid.GetDetail (sxid/sxid.go:31-35): 1 = known; n_actions -1 = SuggestedActionsByGPUd nil
+extern "C" int32_t gpud_sxid_get_detail(int32_t sxid, int32_t* event_type, int32_t* n_actions, int32_t* actions4) {
+  const gpud_tables* T = gpud_host_tables();
+  for (int i = 0; i < T->n_sxid; ++i) {
+    if (T->sxid[i].code != sxid) continue;
+    const gpud_t_detail& d = T->sxid[i].d;
+    if (event_type) *event_type = d.event;
+    if (n_actions) *n_actions = d.n_actions;
+    if (actions4) for (int k = 0; k < 4; ++k) actions4[k] = k < d.n_actions ? d.actions[k] : 0;
+    return 1;
+  }
+  return 0;
+}
+
 // getDetailWithSubCodeAndStatus (xid/xid.go:97-107) with its fallbacks getDetailWithSubCode (:79-93) and GetDetail (:74-77), over
 // the merged sub-code tables buildNVLinkSubCodeDetails made: 1 = found.  n_actions -1 = SuggestedActionsByGPUd nil;
 // detail_variant selects the description (gpud_xid_description); sub_code_out = the Detail's SubCode.

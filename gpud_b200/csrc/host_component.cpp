@@ -358,6 +358,109 @@ StoredEvolveResult evolve_stored_events(const std::vector<Event>& events, const 
   return out;
 }
 
+// ---- stored sxid events ----
+static bool parse_sxid_payload(const std::string& raw, SXidPayload* out) {     // json.Unmarshal into sxidErrorEventDetail (health_state.go:144-162)
+  *out = SXidPayload();
+  const char* p = raw.c_str();
+  jsonmin::ws(p);
+  if (*p != '{') return false;
+  ++p;
+  jsonmin::ws(p);
+  if (*p == '}') { ++p; jsonmin::ws(p); return *p == 0; }
+  for (;;) {
+    std::string k;
+    jsonmin::ws(p);
+    if (!jsonmin::string(p, &k)) return false;
+    jsonmin::ws(p);
+    if (*p++ != ':') return false;
+    jsonmin::ws(p);
+    uint64_t u = 0;
+    XidPayload tmp;
+    if (!strncmp(p, "null", 4) && k != "suggested_actions_by_gpud") p += 4;
+    else if (k == "sxid") { if (!parse_uint(p, &u)) return false; out->sxid = u; }
+    else if (k == "device_uuid") { if (!jsonmin::string(p, &out->device_uuid)) return false; }
+    else if (k == "suggested_actions_by_gpud") {
+      if (!parse_actions_object(p, &tmp)) return false;
+      out->has_actions = tmp.has_actions;
+      out->actions = tmp.actions;
+    }
+    else if (!jsonmin::skip(p)) return false;
+    jsonmin::ws(p);
+    if (*p == ',') { ++p; continue; }
+    if (*p == '}') { ++p; break; }
+    return false;
+  }
+  jsonmin::ws(p);
+  return *p == 0;
+}
+
+// resolveSXIDEvent (sxid/health_state.go:113-142) followed by the Unmarshal of evolveHealthyState (:50-54): false = skipped
+bool resolve_sxid_event(std::string* type, const std::string& raw, const std::string& event_device_uuid, SXidPayload* out, std::string* message) {
+  const char* q = raw.c_str();
+  bool neg = false;
+  if (*q == '+' || *q == '-') { neg = *q == '-'; ++q; }
+  const char* q0 = q;
+  uint64_t u = 0;
+  while (*q >= '0' && *q <= '9' && u < (1ull << 40)) u = u * 10 + (uint64_t)(*q++ - '0');
+  if (q != q0 && *q == 0) {                                            // strconv.Atoi succeeded
+    if (u > 0x7fffffffu) return false;                                 // no such catalog entry: event unchanged, its decimal payload does not unmarshal
+    int32_t ev = 0, n_act = -1, acts[4] = {0, 0, 0, 0};
+    if (!gpud_sxid_get_detail(neg ? -(int32_t)u : (int32_t)u, &ev, &n_act, acts)) return false;
+    *type = event_type_string(ev);
+    if (neg) return false;                                             // uint64FromInt fails: type / message set, payload still the decimal string
+    out->sxid = u;
+    out->device_uuid = event_device_uuid;
+    out->has_actions = n_act >= 0;
+    out->actions.assign(acts, acts + (n_act > 0 ? n_act : 0));
+    if (message) {
+      char buf[512];
+      const int n = gpud_sxid_reason((int64_t)u, event_device_uuid.c_str(), buf, sizeof buf);
+      *message = n >= 0 ? std::string(buf, (size_t)n) : std::string();
+    }
+    return true;
+  }
+  return parse_sxid_payload(raw, out);                                 // already the JSON form: type stays the event's
+}
+
+StoredEvolveResult evolve_stored_sxid_events(const std::vector<Event>& events) {
+  std::vector<XidEventView> views;
+  std::vector<SXidPayload> payloads;
+  for (const Event& e : events) {
+    XidEventView v;
+    v.name = e.name;
+    SXidPayload p;
+    if (e.name == "error_sxid") {
+      std::string type = e.type;
+      auto it = e.extra_info.find("data");
+      auto dv = e.extra_info.find("device_uuid");
+      if (!resolve_sxid_event(&type, it == e.extra_info.end() ? std::string() : it->second, dv == e.extra_info.end() ? std::string() : dv->second, &p, nullptr))
+        continue;
+      v.type = type;
+      v.xid = p.sxid;
+      v.has_actions = p.has_actions;
+      v.actions = p.actions;
+    }
+    views.push_back(v);
+    payloads.push_back(p);
+  }
+  const EvolveResult r = evolve_healthy_state(views, 2 /* rebootThreshold, sxid/health_state.go:36 */, "error_sxid");
+  StoredEvolveResult out;
+  out.health = r.health;
+  out.has_actions = r.has_actions;
+  out.actions = r.actions;
+  char buf[512];
+  int n;
+  if (r.has_xid && r.last_index >= 0) {
+    const SXidPayload& p = payloads[(size_t)r.last_index];
+    n = p.sxid <= (uint64_t)INT64_MAX ? gpud_sxid_reason((int64_t)p.sxid, p.device_uuid.c_str(), buf, sizeof buf)
+                                      : snprintf(buf, sizeof buf, "SXID %llu detected on %s", (unsigned long long)p.sxid, p.device_uuid.c_str());
+  } else {
+    n = gpud_sxid_reason(-1, "", buf, sizeof buf);
+  }
+  out.reason = n >= 0 ? std::string(buf, (size_t)n) : std::string();
+  return out;
+}
+
 std::vector<Event> trim_events_after_set_healthy(const std::vector<Event>& e) {   // component.go:630-642
   for (size_t i = 0; i < e.size(); ++i)
     if (e[i].name == "SetHealthy") return std::vector<Event>(e.begin(), e.begin() + i);
@@ -665,6 +768,36 @@ int32_t gpudh_evolve_stored(const char* events, const char* devices, int32_t reb
     a = e + 1;
   }
   const gpud::StoredEvolveResult r = gpud::evolve_stored_events(evs, parse_devices(devices), reboot_threshold);
+  *health = (int32_t)r.health;
+  *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
+  snprintf(reason, (size_t)cap, "%s", r.reason.c_str());
+  return 0;
+}
+
+int32_t gpudh_evolve_stored_sxid(const char* events, int32_t* health, int32_t* action, char* reason, int32_t cap) {
+  std::vector<gpud::Event> evs;
+  std::string s = events ? events : "";
+  size_t a = 0;
+  while (a < s.size()) {
+    size_t e = s.find('\x1e', a);
+    if (e == std::string::npos) e = s.size();
+    const std::string rec = s.substr(a, e - a);
+    std::vector<std::string> f;
+    size_t b = 0;
+    for (;;) {
+      const size_t q = rec.find('\x1f', b);
+      f.push_back(rec.substr(b, q == std::string::npos ? std::string::npos : q - b));
+      if (q == std::string::npos) break;
+      b = q + 1;
+    }
+    f.resize(4);
+    gpud::Event ev;
+    ev.name = f[0]; ev.type = f[1];
+    if (ev.name == "error_sxid") { ev.extra_info["device_uuid"] = f[2]; ev.extra_info["data"] = f[3]; }
+    evs.push_back(ev);
+    a = e + 1;
+  }
+  const gpud::StoredEvolveResult r = gpud::evolve_stored_sxid_events(evs);
   *health = (int32_t)r.health;
   *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
   snprintf(reason, (size_t)cap, "%s", r.reason.c_str());

@@ -88,6 +88,11 @@ struct StoredEvolveResult { Health health = Health::Healthy; bool has_actions = 
 // evolveHealthyState over stored events, newest first (health_state.go:57-128), reason included
 StoredEvolveResult evolve_stored_events(const std::vector<Event>& events_newest_first, const DeviceMap& devices, int reboot_threshold);
 
+// the sxid twins (sxid/health_state.go:38-142): the stored payload is the decimal code, resolved on read
+struct SXidPayload { uint64_t sxid = 0; std::string device_uuid; bool has_actions = false; std::vector<int32_t> actions; };
+bool resolve_sxid_event(std::string* type, const std::string& raw_data, const std::string& event_device_uuid, SXidPayload* out, std::string* message);
+StoredEvolveResult evolve_stored_sxid_events(const std::vector<Event>& events_newest_first);
+
 struct XidEventView { std::string name; std::string type; uint64_t xid = 0; bool has_actions = false; std::vector<int32_t> actions; };
 struct EvolveResult { Health health = Health::Healthy; bool has_actions = false; std::vector<int32_t> actions; bool has_xid = false; uint64_t xid = 0; int last_index = -1; /* index into the input of the event that is lastXidErr */ };
 EvolveResult evolve_healthy_state(const std::vector<XidEventView>& events_newest_first, int reboot_threshold);

@@ -278,6 +278,32 @@ extern "C" int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table,
   return GPUD_OK;
 }
 
+// sxid/component.go:433-469: Event{Time, Name: "error_sxid", ExtraInfo: {"data": strconv.FormatInt(sxid), "device_uuid": device}} --
+// no Type, no Message; Find, then Insert.
+extern "C" int32_t gpud_store_insert_sxid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
+                                               int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted) {
+  if (!st || !ident_ok(table) || n < 0 || (n && !hits)) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  int32_t ins = 0;
+  if (S->exec(st->db, "BEGIN;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "begin");
+  for (int64_t i = 0; i < n; ++i) {
+    const gpud_xid_hit& h = hits[i];
+    if (h.kind != GPUD_KIND_SXID) continue;
+    const int64_t t = raw_kmsg ? boot_unix + h.kmsg_usec / 1000000 : fallback_unix;
+    std::string extra = "{\"data\":\"" + std::to_string(h.code) + "\",\"device_uuid\":";
+    jstr(extra, std::string(h.device, strnlen(h.device, sizeof h.device)));
+    extra += "}";
+    bool did = false;
+    const int32_t rc = insert_event(st, table, t, "error_sxid", "", "", extra.c_str(), true, &did);
+    if (rc) { S->exec(st->db, "ROLLBACK;", nullptr, nullptr, nullptr); return rc; }
+    ins += did ? 1 : 0;
+  }
+  if (S->exec(st->db, "COMMIT;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "commit");
+  if (n_inserted) *n_inserted = ins;
+  return GPUD_OK;
+}
+
 // ---- pkg/kmsg Syncer over the hits of RAW_KMSG scans (syncer.go:73-143) -----------------------------------------------
 // For every kmsg record on which the component's Match fires: Event{Time: boot + usec, Name, Message, Type: Warning};
 // dropped when the parsed form "name_message" was already seen in the same truncation bucket (deduper.go:63-125: default 60 s

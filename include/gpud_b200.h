@@ -264,6 +264,7 @@ int32_t gpud_sxid_reason(int64_t sxid, const char* device, char* out, int32_t ca
  * event_type GPUD_EVENT_*, n_actions -1 = SuggestedActionsByGPUd nil, actions4[4] GPUD_ACT_*, detail_variant for
  * gpud_xid_description, sub_code_out = the Detail's SubCode.  Any out pointer may be NULL. */
 int32_t gpud_xid_get_detail(int32_t xid, int32_t* event_type, int32_t* n_actions, int32_t* actions4);   /* GetDetail (xid/xid.go:74-77) */
+int32_t gpud_sxid_get_detail(int32_t sxid, int32_t* event_type, int32_t* n_actions, int32_t* actions4); /* GetDetail (sxid/sxid.go:31-35) */
 int32_t gpud_xid_detail(int32_t xid, int32_t sub_code, uint32_t error_status, int32_t* event_type, int32_t* n_actions, int32_t* actions4,
                         int32_t* detail_variant, int32_t* sub_code_out);
 /* (*xidErrorEventDetail).buildMessage (xid/health_state.go:130-169): Message of a resolved xid event / Reason of the xid health
@@ -326,6 +327,10 @@ int32_t gpud_store_find_event(gpud_store* st, const char* table, int64_t unix_s,
 /* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
 int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);
+/* The sxid component's persist step (sxid/component.go:433-469) for the SXid hits of one scan: "error_sxid" events with an empty type,
+ * extra_info {"data": "<decimal code>", "device_uuid": device}, duplicates skipped.  Resolved on read by resolveSXIDEvent. */
+int32_t gpud_store_insert_sxid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
+                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);
 /* The pkg/kmsg Syncer step (syncer.go:73-143) for the hits of RAW_KMSG + GPUD_SCAN_EXT_MATCHERS scans: `component` names the
  * event table (e.g. "disk" -> components_disk_events_v0_5_0), `kmsg_component` selects the line matchers
  * (gpud_kmsg_component()); per record the component's first firing pattern becomes Event{boot + usec, name, message, "Warning"},

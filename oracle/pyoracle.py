@@ -897,6 +897,52 @@ def evolve_healthy_state_stored(events, devices: Optional[Dict[str, str]] = None
     return {"health": st["health"], "actions": st["actions"], "reason": reason}
 
 
+def resolve_sxid_event(event_type: str, raw_data: str, device_uuid: str = ""):
+    """resolveSXIDEvent (sxid/health_state.go:113-142) + the Unmarshal evolveHealthyState does next (:50-54):
+    -> (type, message or None, payload dict) or None when the event is skipped"""
+    try:
+        code = go_atoi(raw_data.encode("utf-8"))
+    except ValueError:
+        code = None
+    if code is not None:
+        d = SXID_DETAILS.get(code)
+        if d is None or code < 0:
+            return None                                    # payload stays the decimal string, which does not unmarshal into the struct
+        name = d["name"]
+        return (EVENT_NAMES[d["event_type"]], sxid_reason(code, device_uuid, name),
+                {"sxid": code, "device_uuid": device_uuid, "actions": list(d["actions"]) if d["actions"] else None})
+    try:
+        j = json.loads(raw_data)
+        if not isinstance(j, dict):
+            return None
+        acts = j.get("suggested_actions_by_gpud")
+        return (event_type, None, {"sxid": int(j.get("sxid", 0)), "device_uuid": j.get("device_uuid", "") or "",
+                                   "actions": None if acts is None else [{v: k for k, v in ACTION_WIRE.items()}[a] for a in (acts.get("repair_actions") or [])]})
+    except (ValueError, TypeError, KeyError):
+        return None
+
+
+def evolve_sxid_stored(events):
+    """sxid evolveHealthyState over stored events, newest first: {"name", "type", "data", "device_uuid"} -> health / actions / reason"""
+    views, payloads = [], {}
+    for i, e in enumerate(events):
+        if e["name"] != "error_sxid":
+            views.append({"name": e["name"]})
+            continue
+        r = resolve_sxid_event(e.get("type", ""), e.get("data", ""), e.get("device_uuid", ""))
+        if r is None:
+            continue
+        payloads[i] = r[2]
+        views.append({"name": "error_sxid", "type": r[0], "xid": r[2]["sxid"], "actions": r[2]["actions"], "_i": i})
+    st = evolve_healthy_state(views, 2, "error_sxid")
+    reason = "SXIDComponent is healthy"
+    if st["last_index"] is not None:
+        p = payloads[views[st["last_index"]]["_i"]]
+        d = SXID_DETAILS.get(p["sxid"])
+        reason = sxid_reason(p["sxid"], p["device_uuid"], d["name"] if d else "")
+    return {"health": st["health"], "actions": st["actions"], "reason": reason}
+
+
 # GPU product capabilities (pkg/nvidia/product/capabilities.go:6-137)
 PRODUCT_MEM_CAPS = {"a100": 7, "b100": 7, "b200": 7, "gb200": 7, "h100": 7, "h200": 7, "a10": 4}      # :15-23; 1 containment | 2 offlining | 4 row remapping
 PRODUCT_FM = {"a100": True, "b100": True, "b200": True, "gb200": False, "gh200": False, "h100": True, "h200": True, "a10": False}   # :25-50

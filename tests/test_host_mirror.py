@@ -491,3 +491,58 @@ def test_product_capabilities_of_the_reference(golden):   # pkg/nvidia/product/c
         assert bool(L.gpud_product_fm_supported(name.encode())) == O.product_fm_supported(name)
         assert bool(L.gpud_product_fabric_state_supported(name.encode())) == O.product_fabric_state_supported(name)
     assert L.gpud_product_mem_caps(b"NVIDIA B200") == 7 and L.gpud_product_fm_supported(b"NVIDIA B200") == 1      # this framework's target
+
+
+# ---- sxid stored events: resolveSXIDEvent + evolveHealthyState (sxid/health_state.go:38-142) ---------------------------------
+def _evolve_stored_sxid(events):
+    L = g.lib()
+    blob = "\x1e".join("\x1f".join([e["name"], e.get("type", ""), e.get("device_uuid", ""), e.get("data", "")]) for e in events)
+    h, a = C.c_int32(), C.c_int32()
+    out = C.create_string_buffer(1024)
+    L.gpudh_evolve_stored_sxid(blob.encode("utf-8"), C.byref(h), C.byref(a), out, 1024)
+    return HEALTH[h.value], a.value, out.value.decode("utf-8")
+
+
+def test_sxid_stored_events_resolve_and_evolve(golden):
+    import numpy as np
+    L = g.lib()
+    # catalog accessor == the oracle's table
+    for code, d in O.SXID_DETAILS.items():
+        ev, na = C.c_int32(), C.c_int32()
+        acts = (C.c_int32 * 4)()
+        assert L.gpud_sxid_get_detail(code, C.byref(ev), C.byref(na), acts) == 1
+        assert ev.value == d["event_type"] and (None if na.value < 0 else [acts[i] for i in range(na.value)]) == (list(d["actions"]) if d["actions"] else None), code
+    assert L.gpud_sxid_get_detail(99999, None, None, None) == 0
+    # the scenarios of sxid/health_state_test.go with the payload createSXidEvent marshals (:15-35): already JSON, so the event's own
+    # type and actions count and the reason has no catalog name for the made-up codes
+    for r in golden("sxid_health.json")["scenarios"]["rows"]:
+        stored = []
+        for e in r["events"]:
+            if e["k"] != "err":
+                stored.append({"name": "reboot"})
+                continue
+            data = '{"time":null,"data_source":"test","device_uuid":"PCI:0000:9b:00","sxid":%d,"suggested_actions_by_gpud":{"repair_actions":["%s"]}}' % (
+                e["code"], O.ACTION_WIRE[ACT_BY_GO[e["actions"][0]]])
+            stored.append({"name": "error_sxid", "type": e["type"], "device_uuid": "", "data": data})
+        want = O.evolve_sxid_stored(stored)
+        if "health" in r:
+            assert want["health"] == r["health"], r["name"]
+        if r.get("action"):
+            assert want["actions"][0] == ACT_BY_GO[r["action"]], r["name"]
+        if "reason" in r:
+            assert want["reason"] == r["reason"], r["name"]
+        assert _evolve_stored_sxid(stored) == (want["health"], (want["actions"] or [0])[0], want["reason"]), r["name"]
+    # what the component itself persists: the decimal code (sxid/component.go:448-455), resolved from the catalog on read
+    rng = np.random.default_rng(9)
+    codes = list(O.SXID_DETAILS)[:40] + [99999, 0]
+    for i in range(400):
+        events = []
+        for _ in range(int(rng.integers(0, 8))):
+            if rng.random() < 0.3:
+                events.append({"name": "reboot"})
+            else:
+                code = int(rng.choice(codes))
+                raw = str(rng.choice([str(code), str(code), "+%d" % code, "-%d" % code, "x%d" % code, '{"sxid":%d,"device_uuid":"PCI:0000:0%d:00"}' % (code, i % 8), "{bad"]))
+                events.append({"name": "error_sxid", "type": str(rng.choice(["", "Warning", "Fatal"])), "device_uuid": "PCI:0000:0%d:00" % (i % 8), "data": raw})
+        want = O.evolve_sxid_stored(events)
+        assert _evolve_stored_sxid(events) == (want["health"], (want["actions"] or [0])[0], want["reason"]), events

@@ -319,3 +319,40 @@ def test_syncer_component_options_and_random_streams_match_the_model(store, gold
     sy = st.syncer("model_bad")
     with pytest.raises(g.GpudError):
         st.syncer_configure_component(sy, "no-such-component")
+
+
+def test_sxid_hits_are_persisted_like_the_component_does(store, golden):
+    """sxid/component.go:433-469: error_sxid rows with an empty type, the decimal code as data, duplicates skipped; read back with the
+    reference's query and resolved like resolveSXIDEvent"""
+    from oracle import pyoracle as O
+    st, path = store
+    G = golden("store_sql.json")
+    t = st.event_table("accelerator-nvidia-error-sxid")
+    lines = [r["input"] for r in golden("sxid_kmsg.json")["match"]["rows"]]
+    hits = []
+    for i, ln in enumerate(lines):
+        m = O.sxid_match(ln.encode())
+        if m is None:
+            continue
+        h = g.XidHit()
+        h.unit_index, h.kind, h.code, h.kmsg_usec = i, 2, m["sxid"], (100 + i) * 1_000_000
+        dev = m["device"].encode()
+        h.device, h.dev_len = dev, len(dev)
+        hits.append(h)
+    assert hits
+    xh = g.XidHit()
+    xh.kind, xh.code = 1, 79                                    # an xid hit in the same list is not this component's
+    n1 = st.insert_sxid_hits(t, hits + [xh], boot_unix=1_740_000_000, raw_kmsg=True)
+    n2 = st.insert_sxid_hits(t, hits, boot_unix=1_740_000_000, raw_kmsg=True)          # the same scan again: all duplicates
+    db = sqlite3.connect(path)
+    rows = list(db.execute(G["event_get"]["sql"].format(table=t), (0,)))
+    db.close()
+    uniq = {(1_740_000_000 + h.kmsg_usec // 1_000_000, h.code, bytes(h.device).rstrip(b"\0").decode()) for h in hits}
+    assert n1 == len(rows) == len(uniq) and n2 == 0
+    for ts, name, typ, msg, extra in rows:
+        assert (name, typ, msg) == ("error_sxid", "", None)
+        e = json.loads(extra)
+        assert set(e) == {"data", "device_uuid"} and (ts, int(e["data"]), e["device_uuid"]) in uniq
+        assert extra == json.dumps(e, separators=(",", ":"), sort_keys=True)       # json.Marshal of a map: sorted keys, compact
+        r = O.resolve_sxid_event(typ, e["data"], e["device_uuid"])
+        assert r is not None and r[1].startswith("SXID %s(" % e["data"])
