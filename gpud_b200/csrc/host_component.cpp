@@ -112,7 +112,7 @@ int Deduper::add(int64_t now_unix, int64_t msg_unix, const std::string& message)
   const std::string k = dedup_key(msg_unix, message, trunc_);
   auto it = cache_.find(k);
   int freq = 1;
-  if (it != cache_.end() && it->second.expires > now_unix) freq = it->second.count + 1;
+  if (it != cache_.end() && it->second.expires >= now_unix) freq = it->second.count + 1;      // go-cache: an item is gone once now > its expiration
   cache_[k] = Entry{freq, now_unix + ttl_};
   return freq;
 }
@@ -688,6 +688,7 @@ int32_t gpudh_dedup_key(int64_t unix_s, const char* msg, char* out, int32_t cap)
   return 0;
 }
 void* gpudh_deduper_new(int64_t ttl) { return new gpud::Deduper(ttl); }
+void* gpudh_deduper_new2(int64_t ttl, int32_t truncate_seconds) { return new gpud::Deduper(ttl, truncate_seconds > 0 ? truncate_seconds : 60); }   // WithCacheKeyTruncateSeconds
 int32_t gpudh_deduper_add(void* d, int64_t now, int64_t t, const char* msg) { return static_cast<gpud::Deduper*>(d)->add(now, t, msg); }
 void gpudh_deduper_free(void* d) { delete static_cast<gpud::Deduper*>(d); }
 

@@ -65,7 +65,31 @@ def test_dedup_key_and_counts():                                      # pkg/kmsg
     assert add(1000, 1000, "a") == 1 and add(1001, 1010, "a") == 2          # same minute bucket: second occurrence is dropped (>1)
     assert add(1002, 1070, "a") == 1                                         # next minute: new key
     assert add(1003, 1000, "b") == 1
-    assert add(1000 + 901, 1000, "a") == 1                                   # TTL (15 min) expired
+    assert add(1000 + 901, 1000, "a") == 3 and add(1000 + 901 + 901, 1000, "a") == 1   # live through the last second of its TTL (refreshed by every add), gone after
+    L.gpudh_deduper_free(d)
+    # the reference's own vectors (pkg/kmsg/deduper_test.go): base = time.Date(2024, 1, 1, 12, 30, 0, 0, time.UTC)
+    import datetime
+    base = int(datetime.datetime(2024, 1, 1, 12, 30, 0, tzinfo=datetime.timezone.utc).timestamp())
+    key = lambda t, m: (L.gpudh_dedup_key(C.c_int64(t), m.encode(), out, 512), out.value.decode())[1]
+    want = "%d-%s" % (base - base % 60, "test message")                       # TestCacheKey :137-160: every second of the minute gives the same key
+    assert [key(base + s, "test message") for s in (0, 15, 30, 59)] == [want] * 4 == [O.dedup_key(base + s, "test message") for s in (0, 15, 30, 59)]
+    k = [key(base + 45, "test message"), key(base + 75, "test message"), key(base + 120, "test message")]     # :162-185 12:30:45, 12:31:15, 12:32:00
+    assert len(set(k)) == 3
+    assert key(base, "message 1") != key(base + 30, "message 2")              # :187-200
+    midnight = int(datetime.datetime(2024, 1, 1, tzinfo=datetime.timezone.utc).timestamp())
+    assert key(midnight, "test message") == "%d-test message" % midnight and key(midnight - 1, "test message") != key(midnight, "test message")   # :202-216
+    assert key(base + 59, "test message") != key(base + 60, "test message")  # :218-229 last second of a minute vs first of the next
+    d = C.c_void_p(L.gpudh_deduper_new(C.c_int64(300)))                      # TestDeduper :63-84 and TestCacheKey :236-268: newDeduper(5 min, ...)
+    assert [add(base, base, "test content"), add(base, base + 30, "test content"), add(base, base + 61, "test content")] == [1, 2, 1]
+    assert [add(base, base + s, "duplicate message") for s in (0, 30, 59, 60)] == [1, 2, 3, 1]
+    assert [add(base, base, "test content 1"), add(base, base, "test content 2"), add(base, base, "test content 1")] == [1, 1, 2]   # :50-61
+    L.gpudh_deduper_free(d)
+    L.gpudh_deduper_new2.restype = C.c_void_p
+    d = C.c_void_p(L.gpudh_deduper_new2(C.c_int64(300), 300))                # :112-133 WithCacheKeyTruncateSeconds(300): +0, +4 min, +5 min
+    assert [add(base, base, "test content"), add(base, base + 240, "test content"), add(base, base + 300, "test content")] == [1, 2, 1]
+    L.gpudh_deduper_free(d)
+    d = C.c_void_p(L.gpudh_deduper_new(C.c_int64(10)))                       # :86-110 expiry: live through its last second, gone after
+    assert [add(100, 60, "x"), add(110, 61, "x"), add(121, 62, "x")] == [1, 2, 1]
     L.gpudh_deduper_free(d)
 
 
