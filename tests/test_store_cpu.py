@@ -356,3 +356,23 @@ def test_sxid_hits_are_persisted_like_the_component_does(store, golden):
         assert extra == json.dumps(e, separators=(",", ":"), sort_keys=True)       # json.Marshal of a map: sorted keys, compact
         r = O.resolve_sxid_event(typ, e["data"], e["device_uuid"])
         assert r is not None and r[1].startswith("SXID %s(" % e["data"])
+
+
+def test_find_event_map_compare_property(store):
+    """Bucket.Find's compareEvent is map equality, whatever the JSON text looks like: random string maps, either escaping style"""
+    from hypothesis import given, settings, strategies as st_, HealthCheck
+    st, path = store
+    t = st.event_table("prop_table")
+    text = st_.text(alphabet=st_.characters(blacklist_categories=("Cs",), blacklist_characters="\x00"), max_size=12)
+    maps = st_.dictionaries(text, text, max_size=4)
+    counter = [1_780_000_000]
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(maps, maps, st_.booleans(), st_.booleans())
+    def prop(a, b, ascii_a, ascii_b):
+        counter[0] += 1
+        ts = counter[0]
+        st.insert_event(t, ts, "kmsg", "Warning", "", json.dumps(a, ensure_ascii=ascii_a) if a else "")
+        assert st.find_event(t, ts, "kmsg", "Warning", "", json.dumps(b, ensure_ascii=ascii_b, indent=1) if b else "") == (a == b)
+        assert st.find_event(t, ts, "kmsg", "Warning", "", json.dumps(a, ensure_ascii=not ascii_a, sort_keys=True) if a else "null")
+    prop()
