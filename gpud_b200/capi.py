@@ -57,6 +57,25 @@ class Metric(C.Structure):
     _fields_ = [("unix_ms", C.c_int64), ("component", C.c_char_p), ("name", C.c_char_p), ("labels_json", C.c_char_p), ("value", C.c_double)]
 
 
+def hw_slowdown_event_message(bitmask: int, gpu_uuid: str) -> str:
+    buf = C.create_string_buffer(2048)
+    n = lib().gpud_hw_slowdown_event_message(bitmask, gpu_uuid.encode(), buf, 2048)
+    if n < 0:
+        raise GpudError(n, "gpud_hw_slowdown_event_message")
+    return buf.value.decode()
+
+
+def hw_slowdown_check(event_unix, now_unix: int, window_seconds: int = 600, threshold_per_minute: float = 0.6):
+    """-> (health 0/2, freq per minute, hardware_inspection, reason)"""
+    arr = (C.c_int64 * max(1, len(event_unix)))(*event_unix)
+    h, insp, freq = C.c_int32(), C.c_int32(), C.c_double()
+    buf = C.create_string_buffer(512)
+    rc = lib().gpud_hw_slowdown_check(arr, len(event_unix), now_unix, window_seconds, threshold_per_minute, C.byref(h), C.byref(freq), C.byref(insp), buf, 512)
+    if rc:
+        raise GpudError(rc, "gpud_hw_slowdown_check")
+    return h.value, freq.value, bool(insp.value), buf.value.decode()
+
+
 def fabric_reason(verdict, gpu_uuids=()) -> str:
     arr = (C.c_char_p * max(1, len(gpu_uuids)))(*[u.encode() for u in gpu_uuids])
     buf = C.create_string_buffer(2048)
@@ -126,6 +145,11 @@ class Store:
         n = C.c_int32()
         self._check(self._L.gpud_store_insert_xid_hits(self._h, table.encode(), arr, len(hits), fallback_unix, boot_unix, 1 if raw_kmsg else 0, C.byref(n)))
         return n.value
+
+    def insert_hw_slowdown(self, table, unix_s: int, bitmask: int, gpu_uuid: str) -> bool:
+        f = C.c_int32()
+        self._check(self._L.gpud_store_insert_hw_slowdown(self._h, table.encode(), unix_s, bitmask, gpu_uuid.encode(), C.byref(f)))
+        return bool(f.value)
 
     def insert_sxid_hits(self, table, hits, fallback_unix=0, boot_unix=0, raw_kmsg=False) -> int:
         arr = (XidHit * max(1, len(hits)))(*hits)
@@ -332,7 +356,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -387,6 +411,9 @@ def lib() -> C.CDLL:
         "gpud_xid_description": (C.c_char_p, [i32, i32]), "gpud_xid_mnemonic": (C.c_char_p, [i32]),
         "gpud_sxid_name": (C.c_char_p, [i32]), "gpud_nvlink_rule_hint": (C.c_char_p, [i32]),
         "gpud_sxid_reason": (i32, [i64, C.c_char_p, vp, i32]),
+        "gpud_hw_slowdown_event_message": (i32, [C.c_uint64, C.c_char_p, vp, i32]),
+        "gpud_hw_slowdown_check": (i32, [vp, i32, i64, i64, C.c_double, vp, vp, vp, vp, i32]),
+        "gpud_store_insert_hw_slowdown": (i32, [vp, C.c_char_p, i64, C.c_uint64, C.c_char_p, vp]),
         "gpud_xid_get_detail": (i32, [i32, vp, vp, vp]), "gpud_sxid_get_detail": (i32, [i32, vp, vp, vp]),
         "gpud_store_insert_sxid_hits": (i32, [vp, C.c_char_p, vp, i64, i64, i64, i32, vp]),
         "gpud_product_mem_caps": (i32, [C.c_char_p]), "gpud_product_fm_supported": (i32, [C.c_char_p]), "gpud_product_fabric_state_supported": (i32, [C.c_char_p]),

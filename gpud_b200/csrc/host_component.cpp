@@ -672,6 +672,41 @@ extern "C" int32_t gpud_clock_event_reasons(uint64_t bitmask, char* hw_out, int3
   return (join(hw, hw_out, hw_cap) && join(other, other_out, other_cap)) ? (int32_t)(hw.size() * 100 + other.size()) : -1;
 }
 
+// ClockEvents.HWSlowdownEvent (hw-slowdown/clock_events.go:87-102): the Message of the "hw_slowdown" event for one reading -- the
+// sorted hardware-slowdown reasons, each prefixed "<uuid>: " (:158-161), joined by ", ".  Returns the length; 0 = no event.
+extern "C" int32_t gpud_hw_slowdown_event_message(uint64_t bitmask, const char* gpu_uuid, char* out, int32_t cap) {
+  if (!out || cap <= 0) return -1;
+  std::vector<std::string> hw;
+  for (const ClockReason& r : kClockReasons)
+    if ((bitmask & r.flag) && r.hw) hw.push_back(r.text);
+  std::sort(hw.begin(), hw.end());
+  std::string j;
+  for (size_t i = 0; i < hw.size(); ++i) {
+    if (i) j += ", ";
+    j += gpu_uuid ? gpu_uuid : "";
+    j += ": ";
+    j += hw[i];
+  }
+  if ((int32_t)j.size() + 1 > cap) return -1;
+  memcpy(out, j.c_str(), j.size() + 1);
+  return (int32_t)j.size();
+}
+
+// The evaluation half of the hw-slowdown Check (hw-slowdown/component.go:352-407) over the event times read back from the bucket.
+extern "C" int32_t gpud_hw_slowdown_check(const int64_t* event_unix, int32_t n, int64_t now_unix, int64_t window_seconds, double threshold_per_minute,
+                                          int32_t* health, double* freq_per_minute, int32_t* hardware_inspection, char* reason, int32_t reason_cap) {
+  if (n < 0 || (n && !event_unix) || !health) return GPUD_E_INVALID;
+  const gpud::SlowdownVerdict v = gpud::evaluate_hw_slowdown(std::vector<int64_t>(event_unix, event_unix + n), now_unix, window_seconds, threshold_per_minute);
+  *health = (int32_t)v.health;
+  if (freq_per_minute) *freq_per_minute = v.freq_per_min;
+  if (hardware_inspection) *hardware_inspection = v.inspect ? 1 : 0;
+  if (reason) {
+    if ((int32_t)v.reason.size() + 1 > reason_cap) return GPUD_E_CAPACITY;
+    memcpy(reason, v.reason.c_str(), v.reason.size() + 1);
+  }
+  return GPUD_OK;
+}
+
 // ---- flat C entry points so the host mirror is testable through ctypes (not part of gpud_b200.h) ----
 extern "C" {
 

@@ -304,6 +304,24 @@ extern "C" int32_t gpud_store_insert_sxid_hits(gpud_store* st, const char* table
   return GPUD_OK;
 }
 
+// hw-slowdown Check's persist step (hw-slowdown/component.go:294-343): the HWSlowdownEvent of one clock-event reading, Find then Insert
+extern "C" int32_t gpud_store_insert_hw_slowdown(gpud_store* st, const char* table, int64_t unix_s, uint64_t bitmask, const char* gpu_uuid, int32_t* inserted) {
+  if (!st || !ident_ok(table) || !gpu_uuid) return GPUD_E_INVALID;
+  if (!sq()) return GPUD_E_UNSUPPORTED;
+  if (inserted) *inserted = 0;
+  char msg[2048];
+  const int32_t n = gpud_hw_slowdown_event_message(bitmask, gpu_uuid, msg, sizeof msg);
+  if (n < 0) return GPUD_E_CAPACITY;
+  if (n == 0) return GPUD_OK;                                      // no hardware slowdown reason in this reading: no event
+  std::string extra = "{\"data_source\":\"nvml\",\"gpu_uuid\":";
+  jstr(extra, gpu_uuid);
+  extra += "}";
+  bool did = false;
+  const int32_t rc = insert_event(st, table, unix_s, "hw_slowdown", "Warning", msg, extra.c_str(), true, &did);
+  if (rc == GPUD_OK && inserted) *inserted = did ? 1 : 0;
+  return rc;
+}
+
 // ---- pkg/kmsg Syncer over the hits of RAW_KMSG scans (syncer.go:73-143) -----------------------------------------------
 // For every kmsg record on which the component's Match fires: Event{Time: boot + usec, Name, Message, Type: Warning};
 // dropped when the parsed form "name_message" was already seen in the same truncation bucket (deduper.go:63-125: default 60 s

@@ -97,6 +97,14 @@ int32_t gpud_ring_push_raw(gpud_ring* ring, const void* host_rows, int64_t n_row
  * nvmlDeviceGetCurrentClocksEventReasons bitmask mean.  hw_out / other_out receive the sorted descriptions, one per line;
  * flags3 = {HWSlowdown, HWSlowdownThermal, HWSlowdownPowerBrake}.  Returns 100 * n_hw + n_other, -1 if a buffer is too small. */
 int32_t gpud_clock_event_reasons(uint64_t bitmask, char* hw_out, int32_t hw_cap, char* other_out, int32_t other_cap, int32_t* flags3);
+/* ClockEvents.HWSlowdownEvent's Message (hw-slowdown/clock_events.go:87-102,158-161): "<uuid>: <reason>" for every hardware-slowdown
+ * reason of the bitmask, sorted, joined by ", ".  Returns the length, 0 when the reading yields no event, -1 if it does not fit. */
+int32_t gpud_hw_slowdown_event_message(uint64_t bitmask, const char* gpu_uuid, char* out, int32_t cap);
+/* The evaluation half of the hw-slowdown Check (hw-slowdown/component.go:352-407): event times as read back from the bucket (the rule
+ * keeps those strictly after now - window, pkg/eventstore/database.go:330), distinct event-minutes / window minutes >= threshold ->
+ * health 2 (Unhealthy) with RepairActionTypeHardwareInspection and the reference's reason text; defaults 10 min / 0.6 (:29-35). */
+int32_t gpud_hw_slowdown_check(const int64_t* event_unix, int32_t n, int64_t now_unix, int64_t window_seconds, double threshold_per_minute,
+                               int32_t* health, double* freq_per_minute, int32_t* hardware_inspection, char* reason, int32_t reason_cap);
 
 /* Real ingest: a host poller that reads the NVML gauges of CUDA device `dev` - the getters behind the
  * reference's temperature / power / clock-speed / utilization / memory components (temperature/temperature.go:85,
@@ -331,6 +339,9 @@ int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud
  * extra_info {"data": "<decimal code>", "device_uuid": device}, duplicates skipped.  Resolved on read by resolveSXIDEvent. */
 int32_t gpud_store_insert_sxid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                     int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);
+/* hw-slowdown's persist step (hw-slowdown/component.go:294-343): Event{unix_s, "hw_slowdown", "Warning", HWSlowdownEvent message,
+ * {"data_source": "nvml", "gpu_uuid": uuid}} unless the reading has no hardware-slowdown reason or the event is already stored. */
+int32_t gpud_store_insert_hw_slowdown(gpud_store* st, const char* table, int64_t unix_s, uint64_t bitmask, const char* gpu_uuid, int32_t* inserted);
 /* The pkg/kmsg Syncer step (syncer.go:73-143) for the hits of RAW_KMSG + GPUD_SCAN_EXT_MATCHERS scans: `component` names the
  * event table (e.g. "disk" -> components_disk_events_v0_5_0), `kmsg_component` selects the line matchers
  * (gpud_kmsg_component()); per record the component's first firing pattern becomes Event{boot + usec, name, message, "Warning"},

@@ -1017,6 +1017,14 @@ def clock_event_reasons(bitmask: int):
     return hw, other
 
 
+def hw_slowdown_event(bitmask: int, uuid: str, unix_s: int):
+    """ClockEvents.HWSlowdownEvent (hw-slowdown/clock_events.go:87-102) for one reading: None or (time, name, type, message, extra_info)"""
+    hw, _other = clock_event_reasons(bitmask)
+    if not hw:
+        return None
+    return (unix_s, "hw_slowdown", "Warning", ", ".join("%s: %s" % (uuid, r) for r in hw), {"data_source": "nvml", "gpu_uuid": uuid})
+
+
 def go_duration_seconds(sec: int) -> str:
     """time.Duration.String() of a whole number of seconds."""
     if sec == 0:

@@ -376,3 +376,46 @@ def test_find_event_map_compare_property(store):
         assert st.find_event(t, ts, "kmsg", "Warning", "", json.dumps(b, ensure_ascii=ascii_b, indent=1) if b else "") == (a == b)
         assert st.find_event(t, ts, "kmsg", "Warning", "", json.dumps(a, ensure_ascii=not ascii_a, sort_keys=True) if a else "null")
     prop()
+
+
+def test_hw_slowdown_flow_through_the_event_store(store, golden):
+    """hw-slowdown Check (component.go:262-407) on the library: clock-event readings -> HWSlowdownEvent -> Find / Insert -> read back with the
+    reference's Get query -> frequency rule; event shape from TestCreateEventFromClockEvents (clock_events_test.go:337-382)"""
+    import numpy as np
+    from oracle import pyoracle as O
+    st, path = store
+    G = golden("store_sql.json")
+    t = st.event_table("accelerator-nvidia-hw-slowdown")
+    test_time = 1704067200                               # time.Date(2024, 1, 1, 0, 0, 0, 0, time.UTC)
+    assert g.hw_slowdown_event_message(0, "GPU-123") == "" and O.hw_slowdown_event(0, "GPU-123", test_time) is None      # "no hardware slowdown reasons" -> nil
+    assert not st.insert_hw_slowdown(t, test_time, 0x1 | 0x4, "GPU-123")                                                # idle / sw power cap are not hw slowdown
+    for mask in (0x8, 0x40, 0x80, 0x8 | 0x40 | 0x80, 0x8 | 0x20 | 0x4, 0xFFFF):
+        ev = O.hw_slowdown_event(mask, "GPU-123", test_time)
+        assert g.hw_slowdown_event_message(mask, "GPU-123") == ev[3]
+    rng = np.random.default_rng(21)
+    now = 1_760_000_000
+    model = []                                           # (time, message, uuid) rows the reference would hold
+    for i in range(400):
+        ts = now - int(rng.integers(0, 1500))
+        uuid = "GPU-%d" % int(rng.integers(0, 3))
+        mask = int(rng.choice([0, 0x1, 0x8, 0x40, 0x80, 0x48, 0x4]))
+        ev = O.hw_slowdown_event(mask, uuid, ts)
+        did = st.insert_hw_slowdown(t, ts, mask, uuid)
+        if ev is None:
+            assert not did
+            continue
+        key = (ts, ev[3], uuid)
+        assert did == (key not in model)
+        if did:
+            model.append(key)
+    db = sqlite3.connect(path)
+    for window, thr in ((600, 0.6), (600, 0.1), (1200, 0.6), (60, 0.6), (0, 0.6)):
+        rows = list(db.execute(G["event_get"]["sql"].format(table=t), (now - window,)))          # Bucket.Get(since)
+        assert sorted((r[0], r[3], json.loads(r[4])["gpu_uuid"]) for r in rows) == sorted(k for k in model if k[0] > now - window)
+        for r in rows:
+            assert (r[1], r[2]) == ("hw_slowdown", "Warning") and json.loads(r[4]) == {"data_source": "nvml", "gpu_uuid": json.loads(r[4])["gpu_uuid"]}
+        times = [r[0] for r in rows]
+        want = O.hw_slowdown_check([k[0] for k in model], now, window, thr)                       # the rule applies the window itself
+        got = g.hw_slowdown_check(times, now, window, thr)
+        assert (["Healthy", "Degraded", "Unhealthy"][got[0]], got[2], got[3]) == (want[0], want[4], want[3]) and abs(got[1] - want[1]) < 1e-12
+    db.close()
