@@ -672,6 +672,44 @@ extern "C" int32_t gpud_clock_event_reasons(uint64_t bitmask, char* hw_out, int3
   return (join(hw, hw_out, hw_cap) && join(other, other_out, other_cap)) ? (int32_t)(hw.size() * 100 + other.size()) : -1;
 }
 
+// The temperature component's check result over the box's readings (temperature/component.go:190-287): health 0 Healthy / 1 Degraded
+// and the reason -- the per-GPU findings of the first non-empty class (margin, GPU, HBM) joined by ", ", in the order given (the
+// reference ranges over a Go map, so its order is unspecified).
+extern "C" int32_t gpud_temperature_reason(const gpud_temperature* ts, const char* const* gpu_uuids, int32_t n, int32_t margin_threshold_c, int32_t* health,
+                                           char* out, int32_t cap) {
+  if (n < 0 || (n && (!ts || !gpu_uuids)) || !out || cap <= 0) return -1;
+  std::vector<std::string> margin, gpu, hbm;
+  char buf[384];
+  for (int32_t i = 0; i < n; ++i) {
+    int32_t bits = 0;
+    if (gpud_temperature_check(&ts[i], margin_threshold_c, &bits) != GPUD_OK) return -1;
+    const char* uuid = gpu_uuids[i] ? gpu_uuids[i] : "";
+    if (bits & 4) {
+      snprintf(buf, sizeof buf, "%s has only %d °C margin left to slowdown (threshold %d °C)", uuid, ts[i].slowdown_margin_c, margin_threshold_c);
+      margin.push_back(buf);
+    }
+    if (bits & 1) {
+      snprintf(buf, sizeof buf, "%s current temperature is %u °C exceeding the threshold %u °C", uuid, ts[i].current_gpu_core_c, ts[i].threshold_gpu_max_c);
+      gpu.push_back(buf);
+    }
+    if (bits & 2) {
+      snprintf(buf, sizeof buf, "%s HBM temperature is %u °C exceeding the threshold %u °C", uuid, ts[i].current_hbm_c, ts[i].threshold_mem_max_c);
+      hbm.push_back(buf);
+    }
+  }
+  auto join = [](const std::vector<std::string>& v) { std::string j; for (size_t i = 0; i < v.size(); ++i) { if (i) j += ", "; j += v[i]; } return j; };
+  std::string o;
+  int32_t h = 1;
+  if (!margin.empty()) o = "margin threshold exceeded: " + join(margin);
+  else if (!gpu.empty()) o = "GPU temperature anomalies detected: " + join(gpu);
+  else if (!hbm.empty()) o = "HBM temperature anomalies detected: " + join(hbm);
+  else { h = 0; o = "all " + std::to_string(n) + " GPU(s) were checked, no temperature issue found"; }
+  if (health) *health = h;
+  if ((int32_t)o.size() + 1 > cap) return -1;
+  memcpy(out, o.c_str(), o.size() + 1);
+  return (int32_t)o.size();
+}
+
 // ClockEvents.HWSlowdownEvent (hw-slowdown/clock_events.go:87-102): the Message of the "hw_slowdown" event for one reading -- the
 // sorted hardware-slowdown reasons, each prefixed "<uuid>: " (:158-161), joined by ", ".  Returns the length; 0 = no event.
 extern "C" int32_t gpud_hw_slowdown_event_message(uint64_t bitmask, const char* gpu_uuid, char* out, int32_t cap) {

@@ -134,6 +134,11 @@ typedef struct {
 } gpud_temperature;
 int32_t gpud_poller_temperature(gpud_poller* poller, gpud_temperature* out);
 int32_t gpud_temperature_check(const gpud_temperature* t, int32_t margin_threshold_c, int32_t* bits);
+/* The component's check result over the box's n readings (temperature/component.go:190-287): *health 0 Healthy / 1 Degraded, and the
+ * reason text -- the findings of the first non-empty class (margin, GPU, HBM) as "<uuid> ..." joined by ", " in the order given, or
+ * "all n GPU(s) were checked, no temperature issue found".  Returns the length, -1 if it does not fit. */
+int32_t gpud_temperature_reason(const gpud_temperature* ts, const char* const* gpu_uuids, int32_t n, int32_t margin_threshold_c, int32_t* health,
+                                char* out, int32_t cap);
 /* GetClockEvents' reasons bitmask (hw-slowdown/clock_events.go:111-166; decode with gpud_clock_event_reasons) and the four ECC
  * totals of ecc/ecc_errors.go:136-240; ecc_read_mask bit 0..3 = aggregate corrected, aggregate uncorrected, volatile corrected,
  * volatile uncorrected were read. */

@@ -996,6 +996,28 @@ def temperature_check(t: dict, margin_threshold: int = 0):
     return "Healthy", ""
 
 
+def temperature_reason(temps: List[dict], uuids: List[str], margin_threshold: int = 0):
+    """the check result of the temperature component (temperature/component.go:190-287) -> (health, reason); per-GPU findings in the
+    order given"""
+    margin, gpu, hbm = [], [], []
+    for t, u in zip(temps, uuids):
+        _h, cls_all = temperature_check(t, margin_threshold), None
+        if (t.get("ThresholdCelsiusSlowdown", 0) > 0 and t.get("MarginTemperatureSupported", False) and margin_threshold > 0
+                and 0 < t.get("ThresholdCelsiusSlowdownMargin", 0) <= margin_threshold):
+            margin.append("%s has only %d \u00b0C margin left to slowdown (threshold %d \u00b0C)" % (u, t["ThresholdCelsiusSlowdownMargin"], margin_threshold))
+        if t.get("ThresholdCelsiusGPUMax", 0) > 0 and t.get("CurrentCelsiusGPUCore", 0) > t["ThresholdCelsiusGPUMax"]:
+            gpu.append("%s current temperature is %d \u00b0C exceeding the threshold %d \u00b0C" % (u, t["CurrentCelsiusGPUCore"], t["ThresholdCelsiusGPUMax"]))
+        if t.get("ThresholdCelsiusMemMax", 0) > 0 and t.get("HBMTemperatureSupported", False) and t.get("CurrentCelsiusHBM", 0) > t["ThresholdCelsiusMemMax"]:
+            hbm.append("%s HBM temperature is %d \u00b0C exceeding the threshold %d \u00b0C" % (u, t["CurrentCelsiusHBM"], t["ThresholdCelsiusMemMax"]))
+    if margin:
+        return "Degraded", "margin threshold exceeded: " + ", ".join(margin)
+    if gpu:
+        return "Degraded", "GPU temperature anomalies detected: " + ", ".join(gpu)
+    if hbm:
+        return "Degraded", "HBM temperature anomalies detected: " + ", ".join(hbm)
+    return "Healthy", "all %d GPU(s) were checked, no temperature issue found" % len(temps)
+
+
 # clockEventReasonsToInclude (hw-slowdown/clock_events.go:192-264): (flag, isHWSlowdown, description)
 CLOCK_EVENT_REASONS = [
     (0x1, False, 'GPU is idle and clocks are dropping to Idle state'),

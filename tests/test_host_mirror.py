@@ -333,6 +333,12 @@ def test_temperature_checks_of_the_reference(golden):   # temperature/component_
         pt.threshold_mem_max_c, pt.hbm_supported, pt.threshold_slowdown_c = t.get("ThresholdCelsiusMemMax", 0), int(t.get("HBMTemperatureSupported", False)), t.get("ThresholdCelsiusSlowdown", 0)
         pt.slowdown_margin_c, pt.margin_supported = t.get("ThresholdCelsiusSlowdownMargin", 0), int(t.get("MarginTemperatureSupported", False))
         assert g.temperature_check(pt, thr) == bits, r["name"]
+        # the component's health + reason for a one-GPU box, with the fragments the reference's test asserts
+        want_h, want_reason = O.temperature_reason([t], ["GPU-12345678"], thr)
+        got_h, got_reason = g.temperature_reason([pt], ["GPU-12345678"], thr)
+        assert (["Healthy", "Degraded"][got_h], got_reason) == (want_h, want_reason) and want_h == r["health"], r["name"]
+        for frag in r["reason_contains"]:
+            assert frag in want_reason, (r["name"], frag, want_reason)
 
 
 # ---- xid event message / health-state reason (xid/health_state.go:130-281; health_state_test.go:299-942) --------------------
@@ -498,6 +504,28 @@ def test_resolve_xid_event_matches_the_oracle_on_random_payloads():
         thr = int(rng.integers(1, 4))
         want = O.evolve_healthy_state_stored(events, devices, thr)
         assert _evolve_stored(events, devices, thr) == (want["health"], (want["actions"] or [0])[0], want["reason"]), events
+
+
+def test_temperature_reason_over_a_box():
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        n = int(rng.integers(0, 9))
+        temps, structs, uuids = [], [], []
+        for i in range(n):
+            t = {"CurrentCelsiusGPUCore": int(rng.integers(30, 100)), "CurrentCelsiusHBM": int(rng.integers(30, 110)), "HBMTemperatureSupported": bool(rng.random() < 0.7),
+                 "ThresholdCelsiusSlowdown": int(rng.choice([0, 95, 100])), "ThresholdCelsiusMemMax": int(rng.choice([0, 95, 105])),
+                 "ThresholdCelsiusGPUMax": int(rng.choice([0, 85, 88])), "ThresholdCelsiusSlowdownMargin": int(rng.integers(-5, 60)),
+                 "MarginTemperatureSupported": bool(rng.random() < 0.7)}
+            pt = g.Temperature()
+            pt.current_gpu_core_c, pt.current_hbm_c, pt.hbm_supported = t["CurrentCelsiusGPUCore"], t["CurrentCelsiusHBM"], int(t["HBMTemperatureSupported"])
+            pt.threshold_slowdown_c, pt.threshold_mem_max_c, pt.threshold_gpu_max_c = t["ThresholdCelsiusSlowdown"], t["ThresholdCelsiusMemMax"], t["ThresholdCelsiusGPUMax"]
+            pt.slowdown_margin_c, pt.margin_supported = t["ThresholdCelsiusSlowdownMargin"], int(t["MarginTemperatureSupported"])
+            temps.append(t); structs.append(pt); uuids.append("GPU-%04d" % i)
+        thr = int(rng.choice([0, 5, 10, 30]))
+        want_h, want_reason = O.temperature_reason(temps, uuids, thr)
+        got_h, got_reason = g.temperature_reason(structs, uuids, thr)
+        assert (["Healthy", "Degraded"][got_h], got_reason) == (want_h, want_reason)
 
 
 def test_product_capabilities_of_the_reference(golden):   # pkg/nvidia/product/capabilities_test.go:8, :168, :230
