@@ -85,6 +85,19 @@ def fabric_reason(verdict, gpu_uuids=()) -> str:
     return buf.value.decode()
 
 
+def fabric_report_reason(raws, gpu_uuids):
+    """collectFabricState -> (healthy, reason)"""
+    n = len(raws)
+    arr = (FabricRaw * max(1, n))(*raws)
+    uu = (C.c_char_p * max(1, n))(*[u.encode() for u in gpu_uuids])
+    h = C.c_int32()
+    buf = C.create_string_buffer(8192)
+    rc = lib().gpud_fabric_report_reason(arr, uu, n, C.byref(h), buf, 8192)
+    if rc < 0:
+        raise GpudError(rc, "gpud_fabric_report_reason")
+    return bool(h.value), buf.value.decode()
+
+
 def xid_detail(xid: int, sub_code: int = 0, error_status: int = 0):
     """getDetailWithSubCodeAndStatus -> None or dict(event_type, actions (None = nil), description, sub_code)"""
     ev, na, var, sc = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
@@ -372,7 +385,7 @@ SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destr
            "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
-           "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
+           "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
 _lib = None
@@ -440,7 +453,7 @@ def lib() -> C.CDLL:
         "gpud_fabric_pack": (i32, [vp, i32, C.POINTER(FabricRaw), vp, vp]),
         "gpud_fabric_verdict_device": (i32, [vp, i32, vp, i32, i32, C.POINTER(FabricVerdict), vp]),
         "gpud_comm_unique_id": (i32, [vp]), "gpud_comm_init": (i32, [vp, i32, i32, i32, vp]),
-        "gpud_fabric_issues": (i32, [vp, vp, i32]), "gpud_fabric_suggest_reboot": (i32, [vp]), "gpud_fabric_reason": (i32, [vp, vp, i32, vp, i32]),
+        "gpud_fabric_issues": (i32, [vp, vp, i32]), "gpud_fabric_suggest_reboot": (i32, [vp]), "gpud_fabric_reason": (i32, [vp, vp, i32, vp, i32]), "gpud_fabric_report_reason": (i32, [vp, vp, i32, vp, vp, i32]),
         "gpud_fabric_gather": (i32, [vp, i32, C.POINTER(FabricRaw), i32, C.POINTER(FabricLocal), C.POINTER(FabricVerdict)]),
         "gpud_fabric_gather_p2p": (i32, [vp, C.POINTER(FabricRaw), i32, C.POINTER(FabricLocal), C.POINTER(FabricVerdict)]),
     }

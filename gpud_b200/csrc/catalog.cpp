@@ -348,6 +348,26 @@ extern "C" int32_t gpud_sxid_reason(int64_t sxid, const char* device, char* out,
   return n < cap ? n : -1;
 }
 
+// collectFabricState's report over the box (fabric-manager/fabric_state.go:67-113): *healthy = no GPU has an issue; the reason is
+// "GPU <uuid>: <issues>" per affected GPU, sorted, joined by "; ".
+extern "C" int32_t gpud_fabric_report_reason(const gpud_fabric_raw* gpus, const char* const* gpu_uuids, int32_t n, int32_t* healthy, char* out, int32_t cap) {
+  if (n < 0 || (n && (!gpus || !gpu_uuids)) || !out || cap <= 0) return -1;
+  std::vector<std::string> reasons;
+  char buf[512];
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t k = gpud_fabric_issues(&gpus[i], buf, sizeof buf);
+    if (k < 0) return -1;
+    if (k > 0) reasons.push_back(std::string("GPU ") + (gpu_uuids[i] ? gpu_uuids[i] : "") + ": " + buf);
+  }
+  std::sort(reasons.begin(), reasons.end());
+  std::string j;
+  for (size_t i = 0; i < reasons.size(); ++i) { if (i) j += "; "; j += reasons[i]; }
+  if (healthy) *healthy = reasons.empty() ? 1 : 0;
+  if ((int32_t)j.size() + 1 > cap) return -1;
+  memcpy(out, j.c_str(), j.size() + 1);
+  return (int32_t)j.size();
+}
+
 // GetDetail (xid/xid.go:74-77): the base catalog entry
 extern "C" int32_t gpud_xid_get_detail(int32_t xid, int32_t* event_type, int32_t* n_actions, int32_t* actions4) {
   const gpud_tables* T = gpud_host_tables();

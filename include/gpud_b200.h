@@ -484,6 +484,9 @@ int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v);
  * no-issue text of component.go:307): gpu_uuids[i] names gpu_index i in the "inactive nvlinks=" / "unsupported nvlinks=" lists
  * (NULL or short: "GPU-<i>").  Returns the length, -1 if it does not fit. */
 int32_t gpud_fabric_reason(const gpud_fabric_verdict* v, const char* const* gpu_uuids, int32_t n_uuids, char* out, int32_t cap);
+/* collectFabricState's report (fabric-manager/fabric_state.go:67-113) over the box's records: *healthy, and the reason
+ * "GPU <uuid>: <issues>" per affected GPU, sorted, joined by "; " ("" when healthy).  Returns the length, -1 if it does not fit. */
+int32_t gpud_fabric_report_reason(const gpud_fabric_raw* gpus, const char* const* gpu_uuids, int32_t n, int32_t* healthy, char* out, int32_t cap);
 
 /* Single-rank pieces (one process per GPU; the collective itself is done by the host plumbing, e.g.
  * torch.distributed / ncclAllGather on `dev_send` -> `dev_all`): */

@@ -160,3 +160,13 @@ def reason_string(v: Dict, uuids: List[str]) -> str:
     if r == 4:
         return details("nvlink threshold violated: require >=%d GPUs with all links active; got %d" % (v["required"], v["active"]))
     return {5: "nvlink threshold not set (skipped evaluation)", 6: "no nvlink data (skipped evaluation)"}[r]
+
+
+def report_reason(gpus: List[Dict], uuids: List[str]):
+    """collectFabricState (fabric-manager/fabric_state.go:67-113) -> (healthy, reason)"""
+    reasons = []
+    for g, u in zip(gpus, uuids):
+        issues = get_issues(g) if g.get("fabric_valid", 0) else []
+        if issues:
+            reasons.append("GPU %s: %s" % (u, ", ".join(issues)))
+    return (not reasons), "; ".join(sorted(reasons))

@@ -245,3 +245,37 @@ def test_nvlink_states_helpers_of_the_reference():
     assert (v["active"], v["inactive"]) == (0, 1)                      # "Empty states": AllFeatureEnabled() is true but len(States) == 0 (component.go:271-289)
     v = one([1, 1], (10, 15), (20, 25), (30, 35))
     assert (v["total_replay"], v["total_recovery"], v["total_crc"]) == (25, 45, 65)
+
+
+def test_fabric_report_reason_of_collect_fabric_state():
+    """TestCollectFabricState_SortsEntriesAndReasons / _SortsReasonsAcrossMultipleGPUs (fabric-manager/fabric_state_test.go:609-744): the
+    FabricState literals of those tests (nvml.h values: state COMPLETED 3 / IN_PROGRESS 2, status SUCCESS 0 / ERROR_UNKNOWN 999, summary
+    HEALTHY 1 / UNHEALTHY 2 / LIMITED_CAPACITY 3, mask fields of two bits at shifts 0, 2, 4, 6 with TRUE = 1), given out of UUID order"""
+    import gpud_b200 as g
+    def raw(state, status, mask, summary):
+        r = g.FabricRaw()
+        r.fabric_valid, r.fabric_state, r.fabric_status, r.fabric_health_mask, r.fabric_summary = 1, state, status, mask, summary
+        return r
+    def d(r):
+        return {"fabric_valid": 1, "fabric_state": r.fabric_state, "fabric_status": r.fabric_status, "fabric_health_mask": r.fabric_health_mask, "fabric_summary": r.fabric_summary}
+    info_a = raw(3, 0, 0, 1)
+    info_b = raw(2, 999, (1 << 0) | (1 << 4), 2)
+    healthy, reason = g.fabric_report_reason([info_b, info_a], ["GPU-B", "GPU-A"])
+    assert not healthy and reason == "GPU GPU-B: " + ", ".join(OF.get_issues(d(info_b)))
+    assert reason == "GPU GPU-B: bandwidth degraded, route unhealthy, state=In Progress, status=ERROR_UNKNOWN, summary=Unhealthy"
+    state_a = raw(3, 0, 1 << 2, 3)                      # route recovery in progress + limited capacity
+    info_c = raw(3, 0, 0, 0)
+    healthy, reason = g.fabric_report_reason([info_c, info_b, state_a], ["GPU-C", "GPU-B", "GPU-A"])
+    want_a = "GPU GPU-A: " + ", ".join(OF.get_issues(d(state_a)))
+    want_b = "GPU GPU-B: " + ", ".join(OF.get_issues(d(info_b)))
+    assert not healthy and reason == want_a + "; " + want_b == OF.report_reason([d(info_c), d(info_b), d(state_a)], ["GPU-C", "GPU-B", "GPU-A"])[1]
+    assert g.fabric_report_reason([info_a, info_c], ["GPU-A", "GPU-C"]) == (True, "") and g.fabric_report_reason([], []) == (True, "")
+    for name in SCENARIOS:                              # and on every scenario of the synthetic boxes
+        gpus, _ = scenario(name, 8)
+        raws = []
+        for x in gpus:
+            r = raw(x["fabric_state"], x["fabric_status"], x["fabric_health_mask"], x["fabric_summary"])
+            r.fabric_valid = x["fabric_valid"]
+            raws.append(r)
+        uu = ["GPU-%02d" % (7 - i) for i in range(8)]
+        assert g.fabric_report_reason(raws, uu) == OF.report_reason(gpus, uu), name
