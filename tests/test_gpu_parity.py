@@ -98,6 +98,22 @@ def test_xid_hit_message_is_build_message_of_the_match(ctx):
             assert g.EVENT_NAMES[h.event_type] == r["event_type"]
 
 
+def test_scan_raw_kmsg_header_fields_of_the_reference_calls(ctx):
+    """the literal parseLine calls of pkg/kmsg/watcher_test.go:35-255 as /dev/kmsg records carrying an Xid line: priority, sequence and
+    microsecond fields of the hit equal the asserted ones (negative priority / sequence, the very large timestamp)"""
+    calls = synth.golden("pkg_kmsg.json")["parse_line_calls"]["rows"]
+    recs = [r["input"].split(";", 1)[0] + ";NVRM: Xid (PCI:0000:05:00): 79, pid=1, GPU has fallen off the bus." for r in calls]
+    buf = "\n".join(recs).encode()
+    hits, n = ctx.kmsg_scan(buf, mode=g.SCAN_RAW_KMSG)
+    want, wn = O.scan_raw_kmsg(buf)
+    assert n == wn == len(recs) and len(hits) == len(want) == len(recs)
+    for h, w, r in zip(hits, want, calls):
+        assert (h.kmsg_priority, h.kmsg_seq, h.kmsg_usec) == tuple(w["kmsg"])
+        for k, got in (("priority", h.kmsg_priority), ("sequence", h.kmsg_seq), ("usec", h.kmsg_usec)):
+            if k in r:
+                assert got == r[k], (r["input"], k)
+
+
 def test_scan_multiline_record_raw_mode(ctx):
     """the multiline fallen-off-the-bus vector only matches when the record is one unit (RAW_KMSG continuation lines)"""
     rec = b"4,1,5,-;NVRM: The NVIDIA GPU 0000:18:00.0\n NVRM: (PCI ID: 10de:2901) installed in this system has\n NVRM: fallen off the bus and is not responding to commands.\n"

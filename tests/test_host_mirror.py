@@ -32,6 +32,19 @@ def test_parse_kmsg_line_matches_reference_vectors(golden):          # pkg/kmsg/
         want = O.parse_kmsg_line(0, r["input"])
         assert (prio.value, seq.value, usec.value, msg.value.decode()) == want, r["name"]
         assert (prio.value, seq.value, msg.value.decode()) == (r["expected"]["Priority"], r["expected"]["SequenceNumber"], r["expected"]["Message"])
+    # the literal calls of Test_parseLine / _WithDifferentBootTimes / _EdgeCases (watcher_test.go:35, :192, :215)
+    calls = golden("pkg_kmsg.json")["parse_line_calls"]["rows"]
+    assert len(calls) == 6
+    for r in calls:
+        prio, seq, usec = C.c_int32(), C.c_int64(), C.c_int64()
+        msg = C.create_string_buffer(8192)
+        assert L.gpudh_parse_kmsg_line(r["input"].encode(), C.byref(prio), C.byref(seq), C.byref(usec), msg, 8192) == 0, r["input"]
+        got = {"priority": prio.value, "sequence": seq.value, "usec": usec.value, "message": msg.value.decode()}
+        want = dict(zip(("priority", "sequence", "usec", "message"), O.parse_kmsg_line(0, r["input"])))
+        assert got == want
+        for k in ("priority", "sequence", "usec", "message"):
+            if k in r:
+                assert got[k] == r[k], (r["input"], k)
 
 
 def test_parse_fixture_records(golden):                               # pkg/kmsg/testdata/kmsg.1.log

@@ -286,12 +286,28 @@ def main():
     K = "pkg/kmsg/"
     k = {}
     ksrc = open(os.path.join(REF, K, "watcher_test.go")).read()
-    for fn in re.findall(r"^func (Test\w*[Pp]arse\w*)\(", ksrc, re.M):
+    for fn in ("Test_parseLineComprehensive",):           # the table test; the others are literal calls, extracted below
         try:
             rows, src = table(K + "watcher_test.go", fn)
             k[fn] = {"src": src, "rows": ident(rows)}
         except Exception as e:  # noqa
             print("  skip", fn, type(e).__name__, e)
+    # the non-table parseLine tests: every `input := "..."` / parseLine(bootTime, "...") literal with the equalities asserted after it
+    calls = []
+    for fn in ("Test_parseLine", "Test_parseLineWithDifferentBootTimes", "Test_parseLineEdgeCases"):
+        body, line = find_func(ksrc, fn)
+        for seg in (re.split(r"\n\tt\.Run\(", body)[1:] if fn == "Test_parseLineEdgeCases" else [body]):
+            m = re.search(r'(?:input := |parseLine\(bootTime, )"((?:[^"\\]|\\.)*)"', seg)
+            row = {"func": fn, "line": line, "input": bytes(m.group(1), "utf-8").decode("unicode_escape")}
+            for pat, key, conv in ((r'assert\.Equal\(t, msg\.Message, "((?:[^"\\]|\\.)*)"\)', "message", str), (r'assert\.Equal\(t, "((?:[^"\\]|\\.)*)", msg\.Message\)', "message", str),
+                                   (r"assert\.Equal\(t, msg\.Priority, (-?\d+)\)", "priority", int), (r"assert\.Equal\(t, (-?\d+), msg\.Priority\)", "priority", int),
+                                   (r"assert\.Equal\(t, msg\.SequenceNumber, (-?\d+)\)", "sequence", int), (r"assert\.Equal\(t, (-?\d+), msg\.SequenceNumber\)", "sequence", int),
+                                   (r"bootTime\.Add\((\d+)\s*\*\s*time\.Microsecond\)", "usec", int)):
+                mm = re.search(pat, seg)
+                if mm:
+                    row[key] = conv(mm.group(1))
+            calls.append(row)
+    k["parse_line_calls"] = {"src": K + "watcher_test.go", "rows": calls}
     for fx in ("kmsg.1.log", "kmsg.2.peermem.log"):
         p = os.path.join(REF, K, "testdata", fx)
         if os.path.exists(p):
