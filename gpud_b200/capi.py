@@ -125,6 +125,11 @@ def xid_hit_message(hit, gpu_uuid: str = "") -> str:
     return buf.value.decode("utf-8")
 
 
+class EventRow(C.Structure):
+    _fields_ = [("unix_s", C.c_int64), ("name", C.c_char * 64), ("type", C.c_char * 16), ("message_off", C.c_int32), ("message_len", C.c_int32),
+                ("extra_off", C.c_int32), ("extra_len", C.c_int32)]
+
+
 class DedupRule(C.Structure):
     _fields_ = [("event", C.c_char * 32), ("message_contains", C.c_char * 32), ("window_seconds", C.c_int64)]
 
@@ -174,6 +179,29 @@ class Store:
         h = C.c_void_p()
         self._check(self._L.gpud_kmsg_syncer_create(self._h, component.encode(), C.byref(h)))
         return h
+
+    @staticmethod
+    def _row(r, text):
+        return (r.unix_s, r.name.decode(), r.type.decode(), text[r.message_off:r.message_off + r.message_len].decode("utf-8"),
+                text[r.extra_off:r.extra_off + r.extra_len].decode("utf-8"))
+
+    def get_events(self, table, since_unix: int, cap_rows: int = 4096, cap_text: int = 1 << 20):
+        """Bucket.Get: (unix_s, name, type, message, extra_info_json) newest first"""
+        rows = (EventRow * max(1, cap_rows))()
+        text = C.create_string_buffer(cap_text)
+        n = C.c_int32()
+        self._check(self._L.gpud_store_get_events(self._h, table.encode(), since_unix, rows, cap_rows, text, cap_text, C.byref(n)))
+        return [self._row(rows[i], text.raw) for i in range(n.value)]
+
+    def latest_event(self, table):
+        row, text, f = EventRow(), C.create_string_buffer(1 << 16), C.c_int32()
+        self._check(self._L.gpud_store_latest_event(self._h, table.encode(), C.byref(row), text, 1 << 16, C.byref(f)))
+        return self._row(row, text.raw) if f.value else None
+
+    def purge_events(self, table, before_unix: int) -> int:
+        n = C.c_int32()
+        self._check(self._L.gpud_store_purge_events(self._h, table.encode(), before_unix, C.byref(n)))
+        return n.value
 
     def find_event(self, table, unix_s, name, typ, message="", extra_info_json="") -> bool:
         f = C.c_int32()
@@ -382,7 +410,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -414,6 +442,8 @@ def lib() -> C.CDLL:
         "gpud_store_insert_xid_hits": (i32, [vp, C.c_char_p, vp, i64, i64, i64, i32, vp]),
         "gpud_kmsg_syncer_create": (i32, [vp, C.c_char_p, vp]), "gpud_kmsg_syncer_destroy": (None, [vp]),
         "gpud_kmsg_syncer_feed": (i32, [vp, C.c_char_p, vp, i64, vp, i64, i64, vp]),
+        "gpud_store_get_events": (i32, [vp, C.c_char_p, i64, vp, i32, vp, i32, vp]), "gpud_store_latest_event": (i32, [vp, C.c_char_p, vp, vp, i32, vp]),
+        "gpud_store_purge_events": (i32, [vp, C.c_char_p, i64, vp]),
         "gpud_store_find_event": (i32, [vp, C.c_char_p, i64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, vp]),
         "gpud_kmsg_syncer_configure": (i32, [vp, i32, i32, vp, i32]), "gpud_kmsg_syncer_configure_component": (i32, [vp, C.c_char_p]),
         "gpud_kmsg_syncer_offer": (i32, [vp, i64, C.c_char_p, C.c_char_p, i64, vp]),
@@ -460,7 +490,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters)):
+    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters, EventRow)):
         if L.gpud_sizeof(which) != C.sizeof(st):
             raise GpudError(-1, "ABI layout mismatch for %s: C %d vs ctypes %d" % (st.__name__, L.gpud_sizeof(which), C.sizeof(st)))
     _lib = L

@@ -65,7 +65,7 @@ extern "C" int32_t gpud_host_free(void* p) {
 }
 
 // struct sizes for binding layout checks (ctypes / cgo): 0 hit, 1 fabric_raw, 2 fabric_local, 3 fabric_verdict, 4 ring_cfg,
-// 5 kmsg_event, 6 ib_snapshot, 7 ib_verdict, 8 metric, 9 dedup_rule, 10 temperature, 11 poll_counters
+// 5 kmsg_event, 6 ib_snapshot, 7 ib_verdict, 8 metric, 9 dedup_rule, 10 temperature, 11 poll_counters, 12 event_row
 extern "C" int32_t gpud_sizeof(int32_t which) {
   switch (which) {
     case 0: return (int32_t)sizeof(gpud_xid_hit);
@@ -80,6 +80,7 @@ extern "C" int32_t gpud_sizeof(int32_t which) {
     case 9: return (int32_t)sizeof(gpud_dedup_rule);
     case 10: return (int32_t)sizeof(gpud_temperature);
     case 11: return (int32_t)sizeof(gpud_poll_counters);
+    case 12: return (int32_t)sizeof(gpud_event_row);
   }
   return -1;
 }

@@ -34,6 +34,8 @@ struct Sq {
   int (*reset)(void*) = nullptr;
   int (*finalize)(void*) = nullptr;
   const unsigned char* (*column_text)(void*, int) = nullptr;
+  long long (*column_int64)(void*, int) = nullptr;
+  int (*changes)(void*) = nullptr;
   const char* (*errmsg)(void*) = nullptr;
   int (*busy_timeout)(void*, int) = nullptr;
   void (*free)(void*) = nullptr;
@@ -52,13 +54,29 @@ Sq* sq() {
       SYM(open_v2, "sqlite3_open_v2"); SYM(close, "sqlite3_close"); SYM(exec, "sqlite3_exec"); SYM(prepare_v2, "sqlite3_prepare_v2");
       SYM(bind_int64, "sqlite3_bind_int64"); SYM(bind_double, "sqlite3_bind_double"); SYM(bind_text, "sqlite3_bind_text"); SYM(step, "sqlite3_step");
       SYM(reset, "sqlite3_reset"); SYM(finalize, "sqlite3_finalize"); SYM(column_text, "sqlite3_column_text"); SYM(errmsg, "sqlite3_errmsg");
-      SYM(busy_timeout, "sqlite3_busy_timeout"); SYM(free, "sqlite3_free");
+      SYM(busy_timeout, "sqlite3_busy_timeout"); SYM(free, "sqlite3_free"); SYM(column_int64, "sqlite3_column_int64"); SYM(changes, "sqlite3_changes");
 #undef SYM
       if (!s.open_v2 || !s.close || !s.exec || !s.prepare_v2 || !s.bind_int64 || !s.bind_double || !s.bind_text || !s.step || !s.finalize ||
-          !s.column_text || !s.errmsg) { dlclose(s.so); s.so = nullptr; }
+          !s.column_text || !s.errmsg || !s.column_int64 || !s.changes) { dlclose(s.so); s.so = nullptr; }
     }
   }
   return s.so ? &s : nullptr;
+}
+
+// Every statement the event side runs, in one place (the text is the reference's: pkg/eventstore/database.go:248-262 insert,
+// :278-298 find, :327-336 get, :367-369 latest, :449-450 purge).  tests/test_store_cpu.py compares them with the strings extracted
+// from the reference (tests/golden/store_sql.json).
+enum { kSqlInsert = 0, kSqlFind = 1, kSqlFindWithMessage = 2, kSqlGet = 3, kSqlLatest = 4, kSqlPurge = 5 };
+std::string event_sql(int which, const std::string& t) {
+  switch (which) {
+    case kSqlInsert: return "INSERT INTO " + t + " (timestamp, name, type, message, extra_info) VALUES (?, ?, ?, NULLIF(?, ''), NULLIF(?, ''))";
+    case kSqlFind: return "\nSELECT timestamp, name, type, message, extra_info FROM " + t + " WHERE timestamp = ? AND name = ? AND type = ?";
+    case kSqlFindWithMessage: return event_sql(kSqlFind, t) + " AND message = ?";
+    case kSqlGet: return "SELECT timestamp, name, type, message, extra_info\nFROM " + t + "\nWHERE timestamp > ?\nORDER BY timestamp DESC";
+    case kSqlLatest: return "SELECT timestamp, name, type, message, extra_info FROM " + t + " ORDER BY timestamp DESC LIMIT 1";
+    case kSqlPurge: return "DELETE FROM " + t + " WHERE timestamp < ?";
+  }
+  return "";
 }
 
 // encoding/json string escaping (HTML-safe, like json.Marshal)
@@ -192,8 +210,7 @@ static int32_t find_event(gpud_store* st, const std::string& t, int64_t unix_s, 
   std::map<std::string, std::string> want, have;
   if (!parse_extra_info(extra_json, &want)) return sfail(st, "extra_info is not a JSON object of strings");
   void* q = nullptr;
-  std::string sel = "\nSELECT timestamp, name, type, message, extra_info FROM " + t + " WHERE timestamp = ? AND name = ? AND type = ?";
-  if (message && *message) sel += " AND message = ?";
+  const std::string sel = event_sql(message && *message ? kSqlFindWithMessage : kSqlFind, t);
   if (S->prepare_v2(st->db, sel.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare find");
   S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
   if (message && *message) S->bind_text(q, 4, message, -1, kTransient);
@@ -218,7 +235,7 @@ static int32_t insert_event(gpud_store* st, const char* table, int64_t unix_s, c
     if (dup) return GPUD_OK;
   }
   void* q = nullptr;
-  const std::string ins = "INSERT INTO " + t + " (timestamp, name, type, message, extra_info) VALUES (?, ?, ?, NULLIF(?, ''), NULLIF(?, ''))";
+  const std::string ins = event_sql(kSqlInsert, t);
   if (S->prepare_v2(st->db, ins.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare insert");
   S->bind_int64(q, 1, unix_s); S->bind_text(q, 2, name, -1, kTransient); S->bind_text(q, 3, type, -1, kTransient);
   S->bind_text(q, 4, message ? message : "", -1, kTransient); S->bind_text(q, 5, extra_json ? extra_json : "", -1, kTransient);
@@ -320,6 +337,88 @@ extern "C" int32_t gpud_store_insert_hw_slowdown(gpud_store* st, const char* tab
   const int32_t rc = insert_event(st, table, unix_s, "hw_slowdown", "Warning", msg, extra.c_str(), true, &did);
   if (rc == GPUD_OK && inserted) *inserted = did ? 1 : 0;
   return rc;
+}
+
+// ---- the read side of a Bucket: Get, Latest, Purge (eventstore/types.go:54-66; database.go:327-402, 449-457) ----
+// one row into the caller's arrays: strings of the row go into the text arena, the row records their offsets
+static int32_t emit_row(gpud_store* st, void* q, gpud_event_row* row, char* text, int32_t cap_text, int32_t* used) {
+  Sq* S = sq();
+  memset(row, 0, sizeof *row);
+  row->unix_s = S->column_int64(q, 0);
+  const char* name = (const char*)S->column_text(q, 1);
+  const char* type = (const char*)S->column_text(q, 2);
+  const char* msg = (const char*)S->column_text(q, 3);
+  const char* extra = (const char*)S->column_text(q, 4);
+  if (strlen(name ? name : "") >= sizeof row->name || strlen(type ? type : "") >= sizeof row->type) return sfail(st, "event name / type longer than the row holds");
+  snprintf(row->name, sizeof row->name, "%s", name ? name : "");
+  snprintf(row->type, sizeof row->type, "%s", type ? type : "");
+  std::map<std::string, std::string> m;
+  if (!parse_extra_info(extra, &m)) return sfail(st, "failed to unmarshal extra info");        // scanRows' error (database.go:441-443)
+  const char* parts[2] = {msg ? msg : "", extra ? extra : ""};
+  int32_t* off[2] = {&row->message_off, &row->extra_off};
+  int32_t* len[2] = {&row->message_len, &row->extra_len};
+  for (int k = 0; k < 2; ++k) {
+    const int32_t n = (int32_t)strlen(parts[k]);
+    if (*used + n + 1 > cap_text) return GPUD_E_CAPACITY;
+    memcpy(text + *used, parts[k], (size_t)n + 1);
+    *off[k] = *used; *len[k] = n;
+    *used += n + 1;
+  }
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_store_get_events(gpud_store* st, const char* table, int64_t since_unix, gpud_event_row* rows, int32_t cap_rows, char* text,
+                                         int32_t cap_text, int32_t* n_rows) {
+  if (!st || !ident_ok(table) || cap_rows < 0 || (cap_rows && !rows) || !text || cap_text <= 0 || !n_rows) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  *n_rows = 0;
+  const std::string sel = event_sql(kSqlGet, table);
+  void* q = nullptr;
+  if (S->prepare_v2(st->db, sel.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare get");
+  S->bind_int64(q, 1, since_unix);
+  int32_t rc = GPUD_OK, used = 0, n = 0;
+  while (S->step(q) == kRow) {
+    if (n >= cap_rows) { rc = GPUD_E_CAPACITY; break; }
+    rc = emit_row(st, q, &rows[n], text, cap_text, &used);
+    if (rc) break;
+    ++n;
+  }
+  S->finalize(q);
+  *n_rows = n;
+  return rc;
+}
+
+extern "C" int32_t gpud_store_latest_event(gpud_store* st, const char* table, gpud_event_row* row, char* text, int32_t cap_text, int32_t* found) {
+  if (!st || !ident_ok(table) || !row || !text || cap_text <= 0 || !found) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  *found = 0;
+  const std::string sel = event_sql(kSqlLatest, table);
+  void* q = nullptr;
+  if (S->prepare_v2(st->db, sel.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare latest");
+  int32_t rc = GPUD_OK, used = 0;
+  if (S->step(q) == kRow) {
+    rc = emit_row(st, q, row, text, cap_text, &used);
+    if (rc == GPUD_OK) *found = 1;
+  }
+  S->finalize(q);
+  return rc;
+}
+
+extern "C" int32_t gpud_store_purge_events(gpud_store* st, const char* table, int64_t before_unix, int32_t* n_purged) {
+  if (!st || !ident_ok(table)) return GPUD_E_INVALID;
+  Sq* S = sq();
+  if (!S) return GPUD_E_UNSUPPORTED;
+  const std::string del = event_sql(kSqlPurge, table);
+  void* q = nullptr;
+  if (S->prepare_v2(st->db, del.c_str(), -1, &q, nullptr) != kOk) return sfail(st, "prepare purge");
+  S->bind_int64(q, 1, before_unix);
+  const int rc = S->step(q);
+  S->finalize(q);
+  if (rc != kDone) return sfail(st, "purge events");
+  if (n_purged) *n_purged = S->changes(st->db);
+  return GPUD_OK;
 }
 
 // ---- pkg/kmsg Syncer over the hits of RAW_KMSG scans (syncer.go:73-143) -----------------------------------------------
@@ -475,4 +574,12 @@ extern "C" int32_t gpud_store_record_metrics(gpud_store* st, const char* table, 
   S->finalize(q);
   if (S->exec(st->db, "COMMIT;", nullptr, nullptr, nullptr) != kOk) return sfail(st, "commit");
   return GPUD_OK;
+}
+
+// test entry (not in gpud_b200.h): the text of event statement `which` for `table`
+extern "C" int32_t gpudh_store_event_sql(int32_t which, const char* table, char* out, int32_t cap) {
+  const std::string q = event_sql(which, table ? table : "");
+  if (q.empty() || (int32_t)q.size() + 1 > cap) return -1;
+  memcpy(out, q.c_str(), q.size() + 1);
+  return (int32_t)q.size();
 }

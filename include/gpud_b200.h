@@ -337,6 +337,15 @@ int32_t gpud_store_insert_event(gpud_store* st, const char* table, int64_t unix_
  * equal ExtraInfo map (compareEvent :459-469; NULL / "" / "null" = no map).  extra_info_json: one JSON object of string values. */
 int32_t gpud_store_find_event(gpud_store* st, const char* table, int64_t unix_s, const char* name, const char* type, const char* message,
                               const char* extra_info_json, int32_t* found);
+/* The read side of a Bucket (eventstore/types.go:54-66): Get = rows with timestamp > since, newest first (database.go:327-365);
+ * Latest (:367-384); Purge = delete rows with timestamp < before (:449-457).  A row's message and extra_info text live in the
+ * caller's `text` arena at [off, off+len) (NUL-terminated); a stored extra_info that is not a JSON object of strings fails the call
+ * like scanRows does.  GPUD_E_CAPACITY when rows or text do not fit (*n_rows = the rows that did). */
+typedef struct { int64_t unix_s; char name[64]; char type[16]; int32_t message_off, message_len, extra_off, extra_len; } gpud_event_row;
+int32_t gpud_store_get_events(gpud_store* st, const char* table, int64_t since_unix, gpud_event_row* rows, int32_t cap_rows, char* text, int32_t cap_text,
+                              int32_t* n_rows);
+int32_t gpud_store_latest_event(gpud_store* st, const char* table, gpud_event_row* row, char* text, int32_t cap_text, int32_t* found);
+int32_t gpud_store_purge_events(gpud_store* st, const char* table, int64_t before_unix, int32_t* n_purged);
 /* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
 int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);

@@ -419,3 +419,55 @@ def test_hw_slowdown_flow_through_the_event_store(store, golden):
         got = g.hw_slowdown_check(times, now, window, thr)
         assert (["Healthy", "Degraded", "Unhealthy"][got[0]], got[2], got[3]) == (want[0], want[4], want[3]) and abs(got[1] - want[1]) < 1e-12
     db.close()
+
+
+def test_event_statements_are_the_references(golden):
+    """the text of every event statement the library prepares == the fmt.Sprintf result in pkg/eventstore/database.go (extracted)"""
+    import ctypes as C
+    G = golden("store_sql.json")
+    L = g.lib()
+    out = C.create_string_buffer(1024)
+    t = "components_x_events_v0_5_0"
+    for which, key, suffix in ((0, "event_insert", ""), (1, "event_find", ""), (2, "event_find", " AND message = ?"), (3, "event_get", ""), (4, "event_latest", ""), (5, "event_purge", "")):
+        assert L.gpudh_store_event_sql(which, t.encode(), out, 1024) > 0
+        assert out.value.decode() == G[key]["sql"].format(table=t) + suffix, key
+
+
+def test_bucket_get_latest_purge(store, golden):
+    """TestGetEventsTimeRange (:122), TestEmptyResults (:173), TestPurgePartial (:247), TestLatest (:1250) of pkg/eventstore/database_test.go"""
+    st, path = store
+    G = golden("store_sql.json")
+    base = 1_765_000_000
+    t = st.event_table("test_table")
+    assert st.get_events(t, base - 3600) == [] and st.latest_event(t) is None and st.purge_events(t, base) == 0      # empty store
+    for dt in (-600, -300, 0):
+        st.insert_event(t, base + dt, "kmsg", "Warning")
+    assert len(st.get_events(t, base - 900)) == 3 and len(st.get_events(t, base - 120)) == 1
+    assert [r[0] for r in st.get_events(t, 0)] == [base, base - 300, base - 600]                   # newest first
+    assert st.get_events(t, base) == []                                                           # strictly newer than since
+    db = sqlite3.connect(path)
+    assert [tuple(r) for r in db.execute(G["event_get"]["sql"].format(table=t), (base - 900,))] == [(r[0], r[1], r[2], r[3] or None, r[4] or None) for r in st.get_events(t, base - 900)]
+    t2 = st.event_table("purge_table")
+    st.insert_event(t2, base - 600, "kmsg", "Warning", "", '{"id":"old_event"}')
+    st.insert_event(t2, base, "kmsg", "Warning", "", '{"id":"new_event"}')
+    assert st.purge_events(t2, base - 300) == 1
+    rows = st.get_events(t2, base - 900)
+    assert len(rows) == 1 and rows[0][4] == '{"id":"new_event"}'
+    assert not st.find_event(t2, base - 600, "test", "Warning", "", '{"id":"old_event"}')
+    t3 = st.event_table("latest_table")
+    for dt, typ, msg, eid in ((-10, "Warning", "old event", "event1"), (0, "Info", "latest event", "event2"), (-5, "Critical", "middle event", "event3")):
+        st.insert_event(t3, base + dt, "test", typ, msg, json.dumps({"id": eid}, separators=(",", ":")))
+    latest = st.latest_event(t3)
+    assert latest == (base, "test", "Info", "latest event", '{"id":"event2"}')
+    assert tuple(db.execute(G["event_latest"]["sql"].format(table=t3)).fetchone()) == latest
+    assert st.purge_events(t3, base + 3600) == 3 and st.latest_event(t3) is None
+    # a stored extra_info that does not unmarshal fails Get like scanRows does; capacity errors are reported, not truncated silently
+    db.execute("INSERT INTO %s (timestamp, name, type, message, extra_info) VALUES (?, 'kmsg', 'Warning', NULL, '[1]')" % t, (base + 50,))
+    db.commit()
+    with pytest.raises(g.GpudError):
+        st.get_events(t, base)
+    db.execute("DELETE FROM %s WHERE timestamp = ?" % t, (base + 50,))
+    db.commit()
+    with pytest.raises(g.GpudError):
+        st.get_events(t, 0, cap_rows=2)
+    db.close()

@@ -510,7 +510,7 @@ def main():
     ES, MS = "pkg/eventstore/database.go", "pkg/metrics/store/sqlite.go"
     for key, path, func, which in [("event_create_table", ES, "createTable", 0), ("event_index_0", ES, "createTable", 1), ("event_index_1", ES, "createTable", 2),
                                    ("event_index_2", ES, "createTable", 3), ("event_insert", ES, "insertEvent", 0), ("event_get", ES, "getEvents", 0),
-                                   ("event_table_name", ES, "defaultTableName", 0), ("metrics_create_table", MS, "CreateTable", 0), ("metrics_insert_prefix", MS, "insert", 0)]:
+                                   ("event_table_name", ES, "defaultTableName", 0), ("event_latest", ES, "lastEvent", 0), ("event_purge", ES, "purgeEvents", 0), ("event_find", ES, "findEvent", 0), ("metrics_create_table", MS, "CreateTable", 0), ("metrics_insert_prefix", MS, "insert", 0)]:
         text, src = go_fmt_sql(path, func, which)
         sql[key] = {"src": src, "rows": [], "sql": text}
     sql["constants"] = {"src": ES + ":18 ; " + MS + ":22,36", "rows": [], "event_schema_version": consts(ES)["schemaVersion"]["value"],
