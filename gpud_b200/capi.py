@@ -203,6 +203,20 @@ class Store:
         self._check(self._L.gpud_store_purge_events(self._h, table.encode(), before_unix, C.byref(n)))
         return n.value
 
+    def xid_state(self, xid_table, os_table, now_unix: int, lookback_seconds: int = 3 * 24 * 3600, reboot_threshold: int = 2, devices=None):
+        """-> (health 0/1/2, first suggested action id or 0, reason)"""
+        h, a, buf = C.c_int32(), C.c_int32(), C.create_string_buffer(2048)
+        spec = ";".join("%s=%s" % kv for kv in (devices or {}).items()).encode()
+        self._check(self._L.gpud_xid_state_from_store(self._h, xid_table.encode(), os_table.encode() if os_table else None, now_unix, lookback_seconds, reboot_threshold,
+                                                      spec, C.byref(h), C.byref(a), buf, 2048))
+        return h.value, a.value, buf.value.decode("utf-8")
+
+    def sxid_state(self, sxid_table, os_table, now_unix: int, lookback_seconds: int = 3 * 24 * 3600):
+        h, a, buf = C.c_int32(), C.c_int32(), C.create_string_buffer(2048)
+        self._check(self._L.gpud_sxid_state_from_store(self._h, sxid_table.encode(), os_table.encode() if os_table else None, now_unix, lookback_seconds,
+                                                       C.byref(h), C.byref(a), buf, 2048))
+        return h.value, a.value, buf.value.decode("utf-8")
+
     def find_event(self, table, unix_s, name, typ, message="", extra_info_json="") -> bool:
         f = C.c_int32()
         self._check(self._L.gpud_store_find_event(self._h, table.encode(), unix_s, name.encode(), typ.encode(), message.encode(), extra_info_json.encode(), C.byref(f)))
@@ -410,7 +424,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -444,6 +458,8 @@ def lib() -> C.CDLL:
         "gpud_kmsg_syncer_feed": (i32, [vp, C.c_char_p, vp, i64, vp, i64, i64, vp]),
         "gpud_store_get_events": (i32, [vp, C.c_char_p, i64, vp, i32, vp, i32, vp]), "gpud_store_latest_event": (i32, [vp, C.c_char_p, vp, vp, i32, vp]),
         "gpud_store_purge_events": (i32, [vp, C.c_char_p, i64, vp]),
+        "gpud_xid_state_from_store": (i32, [vp, C.c_char_p, C.c_char_p, i64, i64, i32, C.c_char_p, vp, vp, vp, i32]),
+        "gpud_sxid_state_from_store": (i32, [vp, C.c_char_p, C.c_char_p, i64, i64, vp, vp, vp, i32]),
         "gpud_store_find_event": (i32, [vp, C.c_char_p, i64, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, vp]),
         "gpud_kmsg_syncer_configure": (i32, [vp, i32, i32, vp, i32]), "gpud_kmsg_syncer_configure_component": (i32, [vp, C.c_char_p]),
         "gpud_kmsg_syncer_offer": (i32, [vp, i64, C.c_char_p, C.c_char_p, i64, vp]),

@@ -710,6 +710,75 @@ extern "C" int32_t gpud_temperature_reason(const gpud_temperature* ts, const cha
   return (int32_t)o.size();
 }
 
+namespace gpud {
+// updateCurrentState (xid/component.go:581-611, sxid/component.go:478-507) over the SQLite stores: reboot events of the "os" bucket
+// (pkg/host/event.go:15-17,134-158: name "reboot", newest first) and the component's own events since now - lookback, the latter cut at
+// the newest SetHealthy, merged newest first, folded by evolveHealthyState.
+int32_t read_bucket(gpud_store* st, const char* table, int64_t since, bool only_reboots, std::vector<Event>* out) {
+  std::vector<gpud_event_row> rows(256);
+  std::vector<char> text(1 << 16);
+  int32_t n = 0;
+  for (;;) {
+    const int32_t rc = gpud_store_get_events(st, table, since, rows.data(), (int32_t)rows.size(), text.data(), (int32_t)text.size(), &n);
+    if (rc == GPUD_OK) break;
+    if (rc != GPUD_E_CAPACITY || rows.size() > (1u << 22)) return rc;
+    rows.resize(rows.size() * 4);
+    text.resize(text.size() * 4);
+  }
+  for (int32_t i = 0; i < n; ++i) {
+    if (only_reboots && strcmp(rows[(size_t)i].name, "reboot") != 0) continue;
+    Event e;
+    e.time_unix = rows[(size_t)i].unix_s;
+    e.name = rows[(size_t)i].name;
+    e.type = rows[(size_t)i].type;
+    e.message = std::string(text.data() + rows[(size_t)i].message_off, (size_t)rows[(size_t)i].message_len);
+    // ExtraInfo of an error event: "data" and "device_uuid" (xid/component.go:536-540); read with the same JSON reader as Find
+    const std::string extra(text.data() + rows[(size_t)i].extra_off, (size_t)rows[(size_t)i].extra_len);
+    const char* p = extra.c_str();
+    jsonmin::ws(p);
+    if (*p == '{') {
+      ++p;
+      for (;;) {
+        std::string k, v;
+        jsonmin::ws(p);
+        if (*p == '}' || !jsonmin::string(p, &k)) break;
+        jsonmin::ws(p);
+        if (*p++ != ':') break;
+        jsonmin::ws(p);
+        if (!strncmp(p, "null", 4)) p += 4;
+        else if (!jsonmin::string(p, &v)) break;
+        e.extra_info[k] = v;
+        jsonmin::ws(p);
+        if (*p == ',') { ++p; continue; }
+        break;
+      }
+    }
+    out->push_back(e);
+  }
+  return GPUD_OK;
+}
+
+int32_t state_from_store(gpud_store* st, const char* table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, bool sxid, int reboot_threshold,
+                                const DeviceMap& devices, int32_t* health, int32_t* action, char* reason, int32_t cap) {
+  if (!st || !table || !health || !reason || cap <= 0) return GPUD_E_INVALID;
+  const int64_t since = now_unix - lookback_seconds;
+  std::vector<Event> reboots, local;
+  if (os_table && *os_table) {
+    const int32_t rc = read_bucket(st, os_table, since, true, &reboots);
+    if (rc) return rc;
+  }
+  const int32_t rc = read_bucket(st, table, since, false, &local);
+  if (rc) return rc;
+  const std::vector<Event> all = merge_events(reboots, trim_events_after_set_healthy(local));
+  const StoredEvolveResult r = sxid ? evolve_stored_sxid_events(all) : evolve_stored_events(all, devices, reboot_threshold);
+  *health = (int32_t)r.health;
+  if (action) *action = r.has_actions && !r.actions.empty() ? r.actions[0] : 0;
+  if ((int32_t)r.reason.size() + 1 > cap) return GPUD_E_CAPACITY;
+  memcpy(reason, r.reason.c_str(), r.reason.size() + 1);
+  return GPUD_OK;
+}
+}  // namespace gpud
+
 // ClockEvents.HWSlowdownEvent (hw-slowdown/clock_events.go:87-102): the Message of the "hw_slowdown" event for one reading -- the
 // sorted hardware-slowdown reasons, each prefixed "<uuid>: " (:158-161), joined by ", ".  Returns the length; 0 = no event.
 extern "C" int32_t gpud_hw_slowdown_event_message(uint64_t bitmask, const char* gpu_uuid, char* out, int32_t cap) {
@@ -804,6 +873,15 @@ static gpud::DeviceMap parse_devices(const char* spec) {     // "uuid=busid;uuid
     a = e + 1;
   }
   return m;
+}
+// health state of the xid / sxid component from the stores (see state_from_store above)
+int32_t gpud_xid_state_from_store(gpud_store* st, const char* xid_table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, int32_t reboot_threshold,
+                                  const char* devices, int32_t* health, int32_t* action, char* reason, int32_t cap) {
+  return gpud::state_from_store(st, xid_table, os_table, now_unix, lookback_seconds, false, reboot_threshold, parse_devices(devices), health, action, reason, cap);
+}
+int32_t gpud_sxid_state_from_store(gpud_store* st, const char* sxid_table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, int32_t* health,
+                                   int32_t* action, char* reason, int32_t cap) {
+  return gpud::state_from_store(st, sxid_table, os_table, now_unix, lookback_seconds, true, 2, gpud::DeviceMap(), health, action, reason, cap);
 }
 // resolveXIDEvent for one stored event: 1 resolved (type_out / message_out filled), 0 left as is
 int32_t gpudh_resolve_xid_event(const char* type_in, const char* raw, const char* device_uuid, const char* devices, char* type_out, int32_t tcap, char* msg_out,

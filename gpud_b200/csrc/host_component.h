@@ -93,6 +93,9 @@ struct SXidPayload { uint64_t sxid = 0; std::string device_uuid; bool has_action
 bool resolve_sxid_event(std::string* type, const std::string& raw_data, const std::string& event_device_uuid, SXidPayload* out, std::string* message);
 StoredEvolveResult evolve_stored_sxid_events(const std::vector<Event>& events_newest_first);
 
+int32_t state_from_store(gpud_store* st, const char* table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, bool sxid, int reboot_threshold,
+                         const DeviceMap& devices, int32_t* health, int32_t* action, char* reason, int32_t cap);
+
 struct XidEventView { std::string name; std::string type; uint64_t xid = 0; bool has_actions = false; std::vector<int32_t> actions; };
 struct EvolveResult { Health health = Health::Healthy; bool has_actions = false; std::vector<int32_t> actions; bool has_xid = false; uint64_t xid = 0; int last_index = -1; /* index into the input of the event that is lastXidErr */ };
 EvolveResult evolve_healthy_state(const std::vector<XidEventView>& events_newest_first, int reboot_threshold);

@@ -346,6 +346,16 @@ int32_t gpud_store_get_events(gpud_store* st, const char* table, int64_t since_u
                               int32_t* n_rows);
 int32_t gpud_store_latest_event(gpud_store* st, const char* table, gpud_event_row* row, char* text, int32_t cap_text, int32_t* found);
 int32_t gpud_store_purge_events(gpud_store* st, const char* table, int64_t before_unix, int32_t* n_purged);
+/* updateCurrentState of the xid / sxid components (xid/component.go:581-611, sxid/component.go:478-507) over the stores: the component's
+ * events and the "reboot" events of the os bucket (os_table = gpud_store_event_table(st, "os"), pkg/host/event.go:15-17; NULL = none)
+ * since now - lookback_seconds (default eventstore.DefaultRetention = 3 days), cut at the newest SetHealthy, merged newest first and
+ * folded by evolveHealthyState (xid/health_state.go:57-128, sxid/health_state.go:38-111).  *health 0 Healthy / 1 Degraded / 2 Unhealthy,
+ * *action the first suggested GPUD_ACT_* (0 = none), reason as the reference words it.  devices = "uuid=pci_bus_id;..." for the UUID
+ * in the xid reason (NULL = none). */
+int32_t gpud_xid_state_from_store(gpud_store* st, const char* xid_table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, int32_t reboot_threshold,
+                                  const char* devices, int32_t* health, int32_t* action, char* reason, int32_t cap);
+int32_t gpud_sxid_state_from_store(gpud_store* st, const char* sxid_table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, int32_t* health,
+                                   int32_t* action, char* reason, int32_t cap);
 /* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
 int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);

@@ -471,3 +471,65 @@ def test_bucket_get_latest_purge(store, golden):
     with pytest.raises(g.GpudError):
         st.get_events(t, 0, cap_rows=2)
     db.close()
+
+
+def test_component_state_from_the_stores_matches_the_reference_flow(store, golden):
+    """updateCurrentState (xid/component.go:581-611, sxid/component.go:478-507) with both buckets in SQLite: random histories of error events
+    (JSON payloads as the library persists them, legacy decimal payloads), reboots in the os bucket, SetHealthy markers; the oracle side is
+    trimEventsAfterSetHealthy + mergeEvents + evolveHealthyState over the same rows"""
+    import numpy as np
+    from oracle import pyoracle as O
+    st, path = store
+    rng = np.random.default_rng(17)
+    devices = {"GPU-aaaa": "0000:04:00.0"}
+    now = 1_766_000_000
+    HEALTH = ["Healthy", "Degraded", "Unhealthy"]
+    wire = O.ACTION_WIRE
+    for trial in range(25):
+        xt, ot, stt = st.event_table("xid-%d" % trial), st.event_table("os-%d" % trial), st.event_table("sxid-%d" % trial)
+        xrows, orows, srows = [], [], []
+        used = set()
+        for _ in range(int(rng.integers(0, 14))):
+            ts = now - int(rng.integers(1, 4 * 24 * 3600))                  # some fall outside the 3-day lookback
+            while ts in used:
+                ts -= 1                                                     # distinct timestamps: sort.Slice is not stable on ties
+            used.add(ts)
+            k = rng.random()
+            if k < 0.25:
+                name = str(rng.choice(["reboot", "reboot", "kernel_panic"]))   # the os bucket holds other events too; only reboots count
+                st.insert_event(ot, ts, name, "Warning", "system reboot detected")
+                orows.append((ts, name))
+            elif k < 0.32:
+                st.insert_event(xt, ts, "SetHealthy", "Info")
+                xrows.append({"time": ts, "name": "SetHealthy"})
+            elif k < 0.75:
+                xid = int(rng.choice([13, 31, 63, 79, 94, 149, 99999]))
+                typ = str(rng.choice(["Warning", "Critical", "Fatal"]))
+                if rng.random() < 0.8:
+                    act = str(rng.choice([wire[2], wire[3], wire[4]]))
+                    data = '{"time":null,"data_source":"kmsg","device_uuid":"PCI:0000:04:00","xid":%d%s,"suggested_actions_by_gpud":{"repair_actions":["%s"]}}' % (
+                        xid, ',"sub_code":4' if xid == 149 and rng.random() < 0.5 else "", act)
+                else:
+                    data = str(xid)
+                st.insert_event(xt, ts, "error_xid", typ, "", json.dumps({"data": data, "device_uuid": "PCI:0000:04:00"}, separators=(",", ":"), sort_keys=True))
+                xrows.append({"time": ts, "name": "error_xid", "type": typ, "data": data, "device_uuid": "PCI:0000:04:00"})
+            else:
+                code = int(rng.choice(list(O.SXID_DETAILS)[:30] + [99999]))
+                st.insert_event(stt, ts, "error_sxid", "", "", json.dumps({"data": str(code), "device_uuid": "PCI:0000:05:00"}, separators=(",", ":"), sort_keys=True))
+                srows.append({"time": ts, "name": "error_sxid", "type": "", "data": str(code), "device_uuid": "PCI:0000:05:00"})
+        for lookback in (3 * 24 * 3600, 3600 * 12):
+            since = now - lookback
+            reboots = sorted(({"time": t, "name": "reboot"} for t, n in orows if n == "reboot" and t > since), key=lambda e: -e["time"])
+            for rows, fn, is_sxid in ((xrows, st.xid_state, False), (srows, st.sxid_state, True)):
+                local = sorted((e for e in rows if e["time"] > since), key=lambda e: -e["time"])
+                local = O.trim_events_after_set_healthy(local)
+                merged = sorted(reboots + local, key=lambda e: -e["time"])
+                if is_sxid:
+                    want = O.evolve_sxid_stored(merged)
+                    got = fn(stt, ot, now, lookback)
+                else:
+                    want = O.evolve_healthy_state_stored(merged, devices, 2)
+                    got = fn(xt, ot, now, lookback, 2, devices)
+                assert (HEALTH[got[0]], got[1], got[2]) == (want["health"], (want["actions"] or [0])[0], want["reason"]), (trial, lookback, is_sxid, merged)
+    # without a reboot store the component's own events still fold
+    assert st.xid_state(st.event_table("xid-0"), None, now)[0] in (0, 1, 2)
