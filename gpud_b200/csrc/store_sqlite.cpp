@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <map>
 #include <string>
@@ -419,6 +420,39 @@ extern "C" int32_t gpud_store_purge_events(gpud_store* st, const char* table, in
   if (rc != kDone) return sfail(st, "purge events");
   if (n_purged) *n_purged = S->changes(st->db);
   return GPUD_OK;
+}
+
+// RebootEventStore.RecordReboot (pkg/host/event.go:40-42, 85-132) into the os bucket: nothing when the boot is older than the
+// retention (3 days), when the same event is stored, when a later boot is already stored, or when the previous one is less than a
+// minute older; else Event{boot time, "reboot", "Warning", "system reboot detected <boot time as Go prints a UTC time.Time>"}.
+extern "C" int32_t gpud_store_record_reboot(gpud_store* st, const char* os_table, int64_t now_unix, int64_t boot_unix, int32_t* inserted) {
+  if (!st || !ident_ok(os_table)) return GPUD_E_INVALID;
+  if (!sq()) return GPUD_E_UNSUPPORTED;
+  if (inserted) *inserted = 0;
+  if (now_unix - boot_unix >= 3 * 24 * 3600) return GPUD_OK;                 // eventstore.DefaultRetention (types.go:48)
+  time_t t = (time_t)boot_unix;
+  struct tm tmv;
+  gmtime_r(&t, &tmv);
+  char when[64];
+  strftime(when, sizeof when, "%Y-%m-%d %H:%M:%S +0000 UTC", &tmv);          // fmt %v of time.Unix(sec, 0).UTC()
+  const std::string msg = std::string("system reboot detected ") + when;
+  bool found = false;
+  int32_t rc = find_event(st, os_table, boot_unix, "reboot", "Warning", msg.c_str(), "", &found);
+  if (rc || found) return rc;
+  gpud_event_row prev;
+  char text[4096];
+  int32_t have = 0;
+  rc = gpud_store_latest_event(st, os_table, &prev, text, sizeof text, &have);      // the latest event of the bucket, whatever its name (:116-119)
+  if (rc) return rc;
+  if (have) {
+    if (prev.unix_s != 0 && prev.unix_s > boot_unix) return GPUD_OK;         // !prev.Time.IsZero() && prev.Time.After(current)
+    const int64_t elapsed = boot_unix - prev.unix_s;
+    if (elapsed > 0 && elapsed < 60) return GPUD_OK;
+  }
+  bool did = false;
+  rc = insert_event(st, os_table, boot_unix, "reboot", "Warning", msg.c_str(), "", false, &did);
+  if (rc == GPUD_OK && inserted) *inserted = did ? 1 : 0;
+  return rc;
 }
 
 // ---- pkg/kmsg Syncer over the hits of RAW_KMSG scans (syncer.go:73-143) -----------------------------------------------

@@ -356,6 +356,9 @@ int32_t gpud_xid_state_from_store(gpud_store* st, const char* xid_table, const c
                                   const char* devices, int32_t* health, int32_t* action, char* reason, int32_t cap);
 int32_t gpud_sxid_state_from_store(gpud_store* st, const char* sxid_table, const char* os_table, int64_t now_unix, int64_t lookback_seconds, int32_t* health,
                                    int32_t* action, char* reason, int32_t cap);
+/* RebootEventStore.RecordReboot (pkg/host/event.go:85-132) into the os bucket: Event{boot time, "reboot", "Warning", "system reboot detected
+ * <time>"} unless the boot is older than 3 days, already stored, older than the latest stored event, or within a minute after it. */
+int32_t gpud_store_record_reboot(gpud_store* st, const char* os_table, int64_t now_unix, int64_t boot_unix, int32_t* inserted);
 /* The xid component's persist loop (xid/component.go:468-577) for the hits of one scan: "error_xid" events, duplicates skipped. */
 int32_t gpud_store_insert_xid_hits(gpud_store* st, const char* table, const gpud_xid_hit* hits, int64_t n, int64_t fallback_unix,
                                    int64_t boot_unix, int32_t raw_kmsg, int32_t* n_inserted);

@@ -533,3 +533,31 @@ def test_component_state_from_the_stores_matches_the_reference_flow(store, golde
                 assert (HEALTH[got[0]], got[1], got[2]) == (want["health"], (want["actions"] or [0])[0], want["reason"]), (trial, lookback, is_sxid, merged)
     # without a reboot store the component's own events still fold
     assert st.xid_state(st.event_table("xid-0"), None, now)[0] in (0, 1, 2)
+
+
+def test_record_reboot_follows_the_references_rules(store):
+    """recordEvent (pkg/host/event.go:85-132) with the sub-tests of TestRecordEvent (event_test.go:158-357): recent boot recorded, boot beyond
+    the retention skipped, same boot again skipped, a boot 30 s after the stored one skipped, two minutes after it recorded, an older boot
+    than the latest event skipped"""
+    import datetime
+    st, path = store
+    utc = lambda *a: int(datetime.datetime(*a, tzinfo=datetime.timezone.utc).timestamp())
+    t = st.event_table("os")
+    now = utc(2025, 5, 21, 15, 0, 0)
+    assert st.record_reboot(t, now, now - 3600)                                  # "recent reboot should record event"
+    assert st.get_events(t, 0) == [(now - 3600, "reboot", "Warning", "system reboot detected 2025-05-21 14:00:00 +0000 UTC", "")]
+    assert not st.record_reboot(t, now, now - 2 * 3 * 24 * 3600)                 # "old reboot should not record event"
+    assert not st.record_reboot(t, now, now - 3 * 24 * 3600) and len(st.get_events(t, 0)) == 1     # exactly the retention: still skipped (>=)
+    assert not st.record_reboot(t, now + 5, now - 3600)                          # "duplicate event should not be recorded"
+    t2 = st.event_table("os-isolated")
+    base = utc(2025, 1, 1, 12, 0, 0)
+    st.insert_event(t2, base, "reboot", "Warning", "system reboot detected 2025-01-01 12:00:00 +0000 UTC")     # fmt.Sprintf("... %v", baseTime)
+    assert not st.record_reboot(t2, base + 100, base)                            # found by Find (same time, name, type, message)
+    assert not st.record_reboot(t2, base + 100, base + 30)                       # "less than a minute different should not be recorded"
+    assert not st.record_reboot(t2, base + 100, base - 500)                      # the stored event is later than this boot
+    assert st.record_reboot(t2, base + 200, base + 120)                          # "more than a minute different should be recorded"
+    assert st.record_reboot(t2, base + 200, base + 180)                          # exactly a minute after the previous one: recorded (elapsed < time.Minute is false)
+    assert [r[0] for r in st.get_events(t2, 0)] == [base + 180, base + 120, base]
+    # the latest event of the bucket counts whatever its name (bucket.Latest, :116)
+    st.insert_event(t2, base + 1000, "kernel_panic", "Warning", "x")
+    assert not st.record_reboot(t2, base + 2000, base + 900) and st.record_reboot(t2, base + 2000, base + 1100)
