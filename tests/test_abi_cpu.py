@@ -55,3 +55,17 @@ def test_hit_json_host_rendering():
 def test_no_cpu_fallback():
     with pytest.raises(g.GpudError):
         g.Context([0])
+
+
+def test_header_is_plain_c():
+    """what cgo would feed its C compiler: the header alone, as C99 with every warning on, and as C++11"""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gpud_b200.h")
+    for cmd in (["gcc", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr],
+                ["g++", "-x", "c++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
