@@ -69,3 +69,19 @@ def test_header_is_plain_c():
                 ["g++", "-x", "c++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", hdr]):
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_c_consumer_links_and_runs(tmp_path):
+    """a C program including only gpud_b200.h, linked with -lgpud_b200: the boundary as a cgo file uses it"""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_consumer")
+    libdir = os.path.dirname(capi.LIB_PATH)
+    libname = os.path.basename(capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_consumer.c"),
+                        "-o", exe, "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
