@@ -174,26 +174,28 @@ constexpr nvmlReturn_t kNvmlNotSupported = 3, kNvmlGpuLost = 15, kNvmlResetRequi
 struct FabricInfoV3 { unsigned int version; unsigned char cluster_uuid[16]; nvmlReturn_t status; unsigned int clique_id; unsigned char state; unsigned int health_mask;
                       unsigned char health_summary; };
 static_assert(sizeof(FabricInfoV3) == 40, "nvmlGpuFabricInfo_v3_t layout");
-bool contains_ci(const char* hay, const char* needle) {
-  if (!hay) return false;
-  std::string h = hay;
+// pkg/nvidia/errors/error.go:33-92: the code, or the driver's error string saying so (lower-cased, trimmed, substring)
+std::string norm(const char* e) {
+  std::string h = e ? e : "";
   for (char& c : h) if (c >= 'A' && c <= 'Z') c = (char)(c - 'A' + 'a');
-  return h.find(needle) != std::string::npos;
+  const size_t a = h.find_first_not_of(" \t\r\n\v\f"), b = h.find_last_not_of(" \t\r\n\v\f");
+  return a == std::string::npos ? std::string() : h.substr(a, b - a + 1);
 }
-// pkg/nvidia/errors/error.go:33-92: the code, or the driver's error string saying so
-bool is_not_supported(Nvml* N, nvmlReturn_t r) { return r == kNvmlNotSupported || (r != 0 && N->err && contains_ci(N->err(r), "not supported")); }
-bool is_gpu_lost(Nvml* N, nvmlReturn_t r) {
+bool has(const std::string& h, const char* needle) { return h.find(needle) != std::string::npos; }
+bool classify_not_supported(nvmlReturn_t r, const char* errstr) { return r == kNvmlNotSupported || has(norm(errstr), "not supported"); }
+bool classify_gpu_lost(nvmlReturn_t r, const char* errstr) {
   if (r == kNvmlGpuLost) return true;
-  if (r == 0 || !N->err) return false;
-  const char* e = N->err(r);
-  return contains_ci(e, "gpu lost") || contains_ci(e, "gpu is lost") || contains_ci(e, "gpu_is_lost");
+  const std::string e = norm(errstr);
+  return has(e, "gpu lost") || has(e, "gpu is lost") || has(e, "gpu_is_lost");
 }
-bool is_reset_required(Nvml* N, nvmlReturn_t r) {
+bool classify_reset_required(nvmlReturn_t r, const char* errstr) {
   if (r == kNvmlResetRequired) return true;
-  if (r == 0 || !N->err) return false;
-  const char* e = N->err(r);
-  return contains_ci(e, "gpu requires reset") || contains_ci(e, "gpu reset");
+  const std::string e = norm(errstr);
+  return has(e, "gpu requires reset") || has(e, "gpu reset");
 }
+bool is_not_supported(Nvml* N, nvmlReturn_t r) { return classify_not_supported(r, N->err ? N->err(r) : ""); }
+bool is_gpu_lost(Nvml* N, nvmlReturn_t r) { return classify_gpu_lost(r, N->err ? N->err(r) : ""); }
+bool is_reset_required(Nvml* N, nvmlReturn_t r) { return classify_reset_required(r, N->err ? N->err(r) : ""); }
 }  // namespace
 
 extern "C" int32_t gpud_poller_product_name(gpud_poller* p, char* out, int32_t cap) {
@@ -325,4 +327,10 @@ extern "C" int32_t gpud_poller_counters(gpud_poller* p, gpud_poll_counters* out)
     }
   }
   return GPUD_OK;
+}
+
+// test entry (not in gpud_b200.h): the error classes of pkg/nvidia/errors for a return code and the text nvmlErrorString gave for it:
+// bit 1 not supported, 2 GPU lost, 4 GPU requires reset
+extern "C" int32_t gpudh_nvml_error_class(int32_t ret, const char* error_string) {
+  return (classify_not_supported(ret, error_string) ? 1 : 0) | (classify_gpu_lost(ret, error_string) ? 2 : 0) | (classify_reset_required(ret, error_string) ? 4 : 0);
 }

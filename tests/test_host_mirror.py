@@ -611,3 +611,20 @@ def test_sxid_stored_events_resolve_and_evolve(golden):
                 events.append({"name": "error_sxid", "type": str(rng.choice(["", "Warning", "Fatal"])), "device_uuid": "PCI:0000:0%d:00" % (i % 8), "data": raw})
         want = O.evolve_sxid_stored(events)
         assert _evolve_stored_sxid(events) == (want["health"], (want["actions"] or [0])[0], want["reason"]), events
+
+
+def test_nvml_error_classes_of_the_reference(golden):   # pkg/nvidia/errors/error_test.go:11, :451, :535 (constant rows + mocked error strings)
+    L = g.lib()
+    G = golden("nvml_error_classes.json")
+    assert {k: len(v["rows"]) for k, v in G.items()} == {"not_supported": 12, "gpu_lost": 7, "reset_required": 9}
+    # what nvmlErrorString / go-nvml's fallback say for the constants the tables use
+    canon = {0: ("Success", "SUCCESS"), 3: ("Not Supported", "ERROR_NOT_SUPPORTED"), 15: ("GPU is lost", "ERROR_GPU_IS_LOST"), 16: ("GPU requires reset", "ERROR_RESET_REQUIRED"),
+             25: ("Argument version mismatch", "ERROR_ARGUMENT_VERSION_MISMATCH"), 999: ("Unknown Error", "ERROR_UNKNOWN"), 27: ("Not Ready", "ERROR_NOT_READY"),
+             6: ("Not Found", "ERROR_NOT_FOUND")}
+    bit = {"not_supported": 1, "gpu_lost": 2, "reset_required": 4}
+    for key, tab in G.items():
+        for r in tab["rows"]:
+            texts = [r["error_string"]] if r["error_string"] is not None else list(canon[r["ret"]])
+            for text in texts:
+                got = L.gpudh_nvml_error_class(r["ret"], text.encode())
+                assert bool(got & bit[key]) == r["expected"], (key, r["name"], text)

@@ -583,6 +583,28 @@ def main():
     xm["evolve"] = {"src": "%s:%d" % (HS, line), "rows": ev_rows, "devices": {"GPU-test-uuid": "0000:04:00.0"}}
     dump("xid_messages.json", xm)
 
+    # ---- NVML error classes (pkg/nvidia/errors/error_test.go): constant tables + the mocked error-string tables ----
+    ET = "pkg/nvidia/errors/error_test.go"
+    et_src = open(os.path.join(REF, ET)).read()
+    NVML_RET = {"SUCCESS": 0, "ERROR_UNINITIALIZED": 1, "ERROR_INVALID_ARGUMENT": 2, "ERROR_NOT_SUPPORTED": 3, "ERROR_NO_PERMISSION": 4, "ERROR_ALREADY_INITIALIZED": 5,
+                "ERROR_NOT_FOUND": 6, "ERROR_INSUFFICIENT_SIZE": 7, "ERROR_INSUFFICIENT_POWER": 8, "ERROR_DRIVER_NOT_LOADED": 9, "ERROR_TIMEOUT": 10,
+                "ERROR_IRQ_ISSUE": 11, "ERROR_LIBRARY_NOT_FOUND": 12, "ERROR_FUNCTION_NOT_FOUND": 13, "ERROR_CORRUPTED_INFOROM": 14, "ERROR_GPU_IS_LOST": 15,
+                "ERROR_RESET_REQUIRED": 16, "ERROR_OPERATING_SYSTEM": 17, "ERROR_LIB_RM_VERSION_MISMATCH": 18, "ERROR_IN_USE": 19, "ERROR_MEMORY": 20,
+                "ERROR_NO_DATA": 21, "ERROR_VGPU_ECC_NOT_SUPPORTED": 22, "ERROR_INSUFFICIENT_RESOURCES": 23, "ERROR_FREQ_NOT_SUPPORTED": 24,
+                "ERROR_ARGUMENT_VERSION_MISMATCH": 25, "ERROR_DEPRECATED": 26, "ERROR_NOT_READY": 27, "ERROR_GPU_NOT_FOUND": 28, "ERROR_INVALID_STATE": 29,
+                "ERROR_UNKNOWN": 999}                     # nvml.h nvmlReturn_t (go-nvml v0.13.0-1 mirrors it)
+    ec = {}
+    for fn, key in (("TestIsNotSupportError", "not_supported"), ("TestIsGPULostError", "gpu_lost"), ("TestIsGPURequiresReset", "reset_required")):
+        body, line = find_func(et_src, fn)
+        mock = {int(c): bytes(v, "utf-8").decode("unicode_escape") for c, v in re.findall(r'case nvml\.Return\((\d+)\):\s*return "((?:[^"\\]|\\.)*)"', body)}
+        rows = []
+        for nm, ret, exp in re.findall(r'name:\s*"((?:[^"\\]|\\.)*)",\s*ret:\s*nvml\.(\w+(?:\(\d+\))?),\s*expected:\s*(true|false)', body):
+            m = re.fullmatch(r"Return\((\d+)\)", ret)
+            code = int(m.group(1)) if m else NVML_RET[ret]
+            rows.append({"name": nm, "ret": code, "error_string": mock.get(code), "expected": exp == "true"})
+        ec[key] = {"src": "%s:%d" % (ET, line), "rows": rows}
+    dump("nvml_error_classes.json", ec)
+
     # ---- GPU product capability tables (pkg/nvidia/product/capabilities_test.go) ----
     PC = "pkg/nvidia/product/capabilities_test.go"
     pc = {}
