@@ -367,7 +367,7 @@ def test_find_event_map_compare_property(store):
     maps = st_.dictionaries(text, text, max_size=4)
     counter = [1_780_000_000]
 
-    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @settings(max_examples=150, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
     @given(maps, maps, st_.booleans(), st_.booleans())
     def prop(a, b, ascii_a, ascii_b):
         counter[0] += 1
