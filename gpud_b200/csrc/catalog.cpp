@@ -658,7 +658,7 @@ extern "C" int32_t gpud_hit_detail_json(const gpud_xid_hit* h, int64_t unix_seco
   const char* desc = gpud_xid_description(h->code, h->detail_variant);
   if (desc[0]) { o += ",\"description\":\""; json_escape(o, desc); o += "\""; }
   if (h->n_actions >= 0) {
-    o += ",\"suggested_actions_by_gpud\":{\"repair_actions\":[";
+    o += ",\"suggested_actions_by_gpud\":{\"description\":\"\",\"repair_actions\":[";   // apiv1.SuggestedActions: description is not omitempty (api/v1/types.go:206-212)
     for (int i = 0; i < h->n_actions; ++i) {
       if (i) o += ",";
       o += "\"";

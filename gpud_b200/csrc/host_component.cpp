@@ -3,6 +3,7 @@
 #include "json_min.h"
 
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -47,6 +48,16 @@ std::string HealthState::to_json() const {       // api/v1/types.go:50-94 (omite
   std::string o = "{";
   bool first = true;
   auto key = [&](const char* k) { if (!first) o += ","; first = false; o += "\""; o += k; o += "\":"; };
+  key("time");                                   // metav1.Time: RFC3339 seconds in UTC, null when zero
+  if (time_unix == 0) o += "null";
+  else {
+    time_t t = (time_t)time_unix;
+    struct tm tmv;
+    gmtime_r(&t, &tmv);
+    char tb[40];
+    strftime(tb, sizeof tb, "\"%Y-%m-%dT%H:%M:%SZ\"", &tmv);
+    o += tb;
+  }
   if (!component.empty()) { key("component"); jstr(o, component); }
   if (!name.empty()) { key("name"); jstr(o, name); }
   key("health"); jstr(o, health_string(health));
@@ -54,7 +65,7 @@ std::string HealthState::to_json() const {       // api/v1/types.go:50-94 (omite
   if (!error.empty()) { key("error"); jstr(o, error); }
   if (has_actions) {
     key("suggested_actions");
-    o += "{\"repair_actions\":[";
+    o += "{\"description\":\"\",\"repair_actions\":[";    // neither field of apiv1.SuggestedActions is omitempty (types.go:206-212)
     for (size_t i = 0; i < actions.repair_actions.size(); ++i) { if (i) o += ","; jstr(o, repair_action_string(actions.repair_actions[i])); }
     o += "]}";
   }

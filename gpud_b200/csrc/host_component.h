@@ -27,6 +27,7 @@ const char* repair_action_string(int32_t a);    // GPUD_ACT_*   -> "REBOOT_SYSTE
 
 struct SuggestedActions { std::vector<int32_t> repair_actions; };
 struct HealthState {
+  int64_t time_unix = 0;                          // 0 = the zero time (JSON null)
   std::string name, component, reason, error;
   Health health = Health::Healthy;
   bool has_actions = false;

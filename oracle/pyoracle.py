@@ -1181,7 +1181,8 @@ def xid_event_detail_json(x: "XidError", unix_seconds: int = 0) -> str:
     if d.description:
         parts.append('"description":' + _go_json_str(d.description))
     if d.actions is not None:
-        parts.append('"suggested_actions_by_gpud":{"repair_actions":[' + ",".join('"%s"' % ACTION_WIRE[a] for a in d.actions) + "]}")
+        # apiv1.SuggestedActions{Description, RepairActions}: neither field is omitempty (api/v1/types.go:206-212); the catalog never sets a description
+        parts.append('"suggested_actions_by_gpud":{"description":"","repair_actions":[' + ",".join('"%s"' % ACTION_WIRE[a] for a in d.actions) + "]}")
     return "{" + ",".join(parts) + "}"
 
 

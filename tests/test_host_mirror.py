@@ -309,7 +309,7 @@ def test_xid_evolve_extracted_scenarios(golden):   # xid/health_state_test.go:78
                 continue
             data = '{"time":null,"data_source":"test","device_uuid":"PCI:0000:9b:00","xid":%d' % e["code"]
             if e["actions"] is not None:
-                data += ',"suggested_actions_by_gpud":{"repair_actions":["%s"]}' % O.ACTION_WIRE[ACT_BY_GO[e["actions"][0]]]
+                data += ',"suggested_actions_by_gpud":{"description":"","repair_actions":["%s"]}' % O.ACTION_WIRE[ACT_BY_GO[e["actions"][0]]]
             stored.append({"name": "error_xid", "type": e["type"], "device_uuid": "PCI:0000:9b:00", "data": data + "}"})
         want = O.evolve_healthy_state_stored(stored, {}, 2)
         assert want["health"] == r["health"], r["name"]
@@ -366,7 +366,7 @@ def _go_payload(ev):
     if ev["description"]:
         parts.append('"description":%s' % json.dumps(ev["description"]))
     wire = {"RebootSystem": "REBOOT_SYSTEM", "HardwareInspection": "HARDWARE_INSPECTION", "CheckUserAppAndGPU": "CHECK_USER_APP_AND_GPU", "IgnoreNoActionRequired": "IGNORE_NO_ACTION_REQUIRED"}
-    parts.append('"suggested_actions_by_gpud":{"repair_actions":["%s"]}' % wire[ev["action"]])
+    parts.append('"suggested_actions_by_gpud":{"description":"","repair_actions":["%s"]}' % wire[ev["action"]])
     return "{" + ",".join(parts) + "}"
 
 
@@ -586,7 +586,7 @@ def test_sxid_stored_events_resolve_and_evolve(golden):
             if e["k"] != "err":
                 stored.append({"name": "reboot"})
                 continue
-            data = '{"time":null,"data_source":"test","device_uuid":"PCI:0000:9b:00","sxid":%d,"suggested_actions_by_gpud":{"repair_actions":["%s"]}}' % (
+            data = '{"time":null,"data_source":"test","device_uuid":"PCI:0000:9b:00","sxid":%d,"suggested_actions_by_gpud":{"description":"","repair_actions":["%s"]}}' % (
                 e["code"], O.ACTION_WIRE[ACT_BY_GO[e["actions"][0]]])
             stored.append({"name": "error_sxid", "type": e["type"], "device_uuid": "", "data": data})
         want = O.evolve_sxid_stored(stored)

@@ -507,7 +507,7 @@ def test_component_state_from_the_stores_matches_the_reference_flow(store, golde
                 typ = str(rng.choice(["Warning", "Critical", "Fatal"]))
                 if rng.random() < 0.8:
                     act = str(rng.choice([wire[2], wire[3], wire[4]]))
-                    data = '{"time":null,"data_source":"kmsg","device_uuid":"PCI:0000:04:00","xid":%d%s,"suggested_actions_by_gpud":{"repair_actions":["%s"]}}' % (
+                    data = '{"time":null,"data_source":"kmsg","device_uuid":"PCI:0000:04:00","xid":%d%s,"suggested_actions_by_gpud":{"description":"","repair_actions":["%s"]}}' % (
                         xid, ',"sub_code":4' if xid == 149 and rng.random() < 0.5 else "", act)
                 else:
                     data = str(xid)
