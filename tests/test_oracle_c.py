@@ -126,3 +126,23 @@ def test_c_ext_scan_equals_python_scan():
     assert len({h.kind for h in ch}) >= 20 and sum(h.kind >= 3 for h in ch) >= 80
     # the default scan is unchanged by the extra lines
     assert [(h.line, h.kind) for h in CO.scan_lines(buf)[0]] == [(h["line"], h["kind"]) for h in O.scan_lines(buf)]
+
+
+def test_message_test_lines_agree_between_the_two_restatements(golden):
+    """the kmsg lines of xid/health_state_test.go:318-690 (message / reason tests): C engine and Python `re` extract the same fields"""
+    rows = golden("xid_messages.json")["from_lines"]["rows"]
+    assert len(rows) == 15
+    for r in rows:
+        line = r["line"].encode()
+        c, p = CO.xid_match(line), O.xid_match(line)
+        _same(c, p)
+        if "sub_code" in r:
+            assert c.sub_code == r["sub_code"]
+        if "xid" in r:
+            assert c.code == r["xid"]
+    # the header-only records of pkg/kmsg/watcher_test.go (negative priority / sequence, large timestamp) scan identically as raw kmsg
+    calls = golden("pkg_kmsg.json")["parse_line_calls"]["rows"]
+    recs = [r["input"].split(";", 1)[0] + ";NVRM: Xid (PCI:0000:05:00): 79, pid=1, GPU has fallen off the bus." for r in calls]
+    buf = "\n".join(recs).encode()
+    want, wn = O.scan_raw_kmsg(buf)
+    assert wn == len(recs) == len(want)
