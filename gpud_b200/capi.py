@@ -432,7 +432,7 @@ SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destr
            "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_record_reboot", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_kmsg_scan", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
-           "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
+           "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_set_nvml_error_string", "gpud_nvml_error_strings_from_driver", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
 _lib = None
@@ -504,7 +504,7 @@ def lib() -> C.CDLL:
         "gpud_fabric_pack": (i32, [vp, i32, C.POINTER(FabricRaw), vp, vp]),
         "gpud_fabric_verdict_device": (i32, [vp, i32, vp, i32, i32, C.POINTER(FabricVerdict), vp]),
         "gpud_comm_unique_id": (i32, [vp]), "gpud_comm_init": (i32, [vp, i32, i32, i32, vp]),
-        "gpud_fabric_issues": (i32, [vp, vp, i32]), "gpud_fabric_suggest_reboot": (i32, [vp]), "gpud_fabric_reason": (i32, [vp, vp, i32, vp, i32]), "gpud_fabric_report_reason": (i32, [vp, vp, i32, vp, vp, i32]),
+        "gpud_fabric_issues": (i32, [vp, vp, i32]), "gpud_fabric_suggest_reboot": (i32, [vp]), "gpud_fabric_reason": (i32, [vp, vp, i32, vp, i32]), "gpud_set_nvml_error_string": (None, [vp]), "gpud_nvml_error_strings_from_driver": (i32, []), "gpud_fabric_report_reason": (i32, [vp, vp, i32, vp, vp, i32]),
         "gpud_fabric_gather": (i32, [vp, i32, C.POINTER(FabricRaw), i32, C.POINTER(FabricLocal), C.POINTER(FabricVerdict)]),
         "gpud_fabric_gather_p2p": (i32, [vp, C.POINTER(FabricRaw), i32, C.POINTER(FabricLocal), C.POINTER(FabricVerdict)]),
     }

@@ -580,6 +580,11 @@ extern "C" int32_t gpud_fabric_suggest_reboot(const gpud_fabric_verdict* v) {
   return (v->inactive > 0 || (complete && v->p2p_ok_pairs == 0 && other != 0)) ? 1 : 0;
 }
 
+// nvml.Return.Error() is nvmlErrorString once go-nvml has loaded libnvidia-ml and a table of constant names before that; the text shows
+// up in "status=..." issues.  NULL (the default) = the constant names.
+static gpud_nvml_error_string_fn g_nvml_error_string = nullptr;
+extern "C" void gpud_set_nvml_error_string(gpud_nvml_error_string_fn fn) { g_nvml_error_string = fn; }
+
 // FabricState.GetIssues (pkg/nvidia/nvml/device/fabric_state.go:115-177) for one GPU's record: the sorted issue strings,
 // joined with ", " (how fabric-manager/fabric_state.go:95-105 prints them); "" when healthy or when no fabric info was read.
 extern "C" int32_t gpud_fabric_issues(const gpud_fabric_raw* g, char* out, int32_t cap) {
@@ -590,9 +595,12 @@ extern "C" int32_t gpud_fabric_issues(const gpud_fabric_raw* g, char* out, int32
       static const char* kState[] = {"Not Supported", "Not Started", "In Progress", "Completed"};
       is.push_back(std::string("state=") + (g->fabric_state < 4 ? kState[g->fabric_state] : ("Unknown(" + std::to_string(g->fabric_state) + ")").c_str()));
     }
-    if (g->fabric_status != 0) {
+    if (g->fabric_status != 0 && g_nvml_error_string) {                       // FabricStatusToString = status.Error() (fabric_state.go:196-201)
+      const char* txt = g_nvml_error_string(g->fabric_status);
+      is.push_back(std::string("status=") + (txt ? txt : ""));
+    } else if (g->fabric_status != 0) {
       const char* n = nullptr;
-      switch (g->fabric_status) {            // nvml.Return names (go-nvml v0.13.0-1)
+      switch (g->fabric_status) {            // go-nvml's built-in names, what Return.Error() gives while libnvidia-ml is not loaded (v0.13.0-1)
         case 1: n = "ERROR_UNINITIALIZED"; break; case 2: n = "ERROR_INVALID_ARGUMENT"; break; case 3: n = "ERROR_NOT_SUPPORTED"; break;
         case 4: n = "ERROR_NO_PERMISSION"; break; case 6: n = "ERROR_NOT_FOUND"; break; case 9: n = "ERROR_DRIVER_NOT_LOADED"; break;
         case 10: n = "ERROR_TIMEOUT"; break; case 15: n = "ERROR_GPU_IS_LOST"; break; case 999: n = "ERROR_UNKNOWN"; break;

@@ -334,3 +334,10 @@ extern "C" int32_t gpud_poller_counters(gpud_poller* p, gpud_poll_counters* out)
 extern "C" int32_t gpudh_nvml_error_class(int32_t ret, const char* error_string) {
   return (classify_not_supported(ret, error_string) ? 1 : 0) | (classify_gpu_lost(ret, error_string) ? 2 : 0) | (classify_reset_required(ret, error_string) ? 4 : 0);
 }
+
+extern "C" int32_t gpud_nvml_error_strings_from_driver(void) {
+  Nvml* N = nvml();
+  if (!N || !N->err) return GPUD_E_UNSUPPORTED;
+  gpud_set_nvml_error_string((gpud_nvml_error_string_fn)N->err);       // const char* nvmlErrorString(nvmlReturn_t): the same shape
+  return GPUD_OK;
+}

@@ -477,6 +477,13 @@ enum { GPUD_NVLINK_NO_ISSUE = 0, GPUD_NVLINK_P2P_FAILURE = 1, GPUD_NVLINK_NO_ACT
 /* FabricState.GetIssues (pkg/nvidia/nvml/device/fabric_state.go:115-177) of one GPU's record as text: the sorted issue
  * strings joined with ", " ("" = healthy or no fabric info).  Returns the length, -1 if cap is too small. */
 int32_t gpud_fabric_issues(const gpud_fabric_raw* gpu, char* out, int32_t cap);
+/* Where the text of an NVML status comes from ("status=<text>" above is nvml.Return.Error()): NULL, the default, gives go-nvml's constant
+ * names ("ERROR_UNKNOWN"), which is what the reference prints while libnvidia-ml is not loaded (its unit tests); a daemon that has NVML
+ * loaded prints nvmlErrorString's text -- pass that function (or call gpud_nvml_error_strings_from_driver, which installs the dlopen'ed
+ * one; GPUD_E_UNSUPPORTED without a driver library). */
+typedef const char* (*gpud_nvml_error_string_fn)(int32_t nvml_return);
+void gpud_set_nvml_error_string(gpud_nvml_error_string_fn fn);
+int32_t gpud_nvml_error_strings_from_driver(void);
 
 typedef struct {
   int32_t n_gpus;

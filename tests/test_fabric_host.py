@@ -279,3 +279,36 @@ def test_fabric_report_reason_of_collect_fabric_state():
             raws.append(r)
         uu = ["GPU-%02d" % (7 - i) for i in range(8)]
         assert g.fabric_report_reason(raws, uu) == OF.report_reason(gpus, uu), name
+
+
+def test_fabric_status_text_follows_the_installed_nvml_error_string():
+    """status.Error() is go-nvml's constant name until libnvidia-ml is loaded and nvmlErrorString's text afterwards; the library takes the
+    function the same way (gpud_set_nvml_error_string), default = the constant names the reference's unit tests see"""
+    import ctypes as C
+    import gpud_b200 as g
+    L = g.lib()
+    r = g.FabricRaw()
+    r.fabric_valid, r.fabric_state, r.fabric_status, r.fabric_summary = 1, 3, 999, 1
+    out = C.create_string_buffer(256)
+    L.gpud_fabric_issues(C.byref(r), out, 256)
+    assert out.value.decode() == "status=ERROR_UNKNOWN"
+    texts = {999: b"Unknown Error", 3: b"Not Supported", 15: b"GPU is lost"}
+    bufs = {k: C.create_string_buffer(v) for k, v in texts.items()}          # the callback hands out pointers that stay valid, like nvmlErrorString
+    other = C.create_string_buffer(b"?")
+    FN = C.CFUNCTYPE(C.c_void_p, C.c_int32)
+    cb = FN(lambda code: C.addressof(bufs.get(code, other)))
+    try:
+        L.gpud_set_nvml_error_string(cb)
+        for code, text in texts.items():
+            r.fabric_status = code
+            L.gpud_fabric_issues(C.byref(r), out, 256)
+            assert out.value.decode() == "status=" + text.decode()
+        assert g.fabric_report_reason([r], ["GPU-A"]) == (False, "GPU GPU-A: status=GPU is lost")
+    finally:
+        L.gpud_set_nvml_error_string(None)
+    r.fabric_status = 999
+    L.gpud_fabric_issues(C.byref(r), out, 256)
+    assert out.value.decode() == "status=ERROR_UNKNOWN"
+    import torch
+    if not torch.cuda.is_available():
+        assert L.gpud_nvml_error_strings_from_driver() != 0        # no driver library on this host: refused, nothing installed
