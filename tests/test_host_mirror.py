@@ -628,3 +628,29 @@ def test_nvml_error_classes_of_the_reference(golden):   # pkg/nvidia/errors/erro
             for text in texts:
                 got = L.gpudh_nvml_error_class(r["ret"], text.encode())
                 assert bool(got & bit[key]) == r["expected"], (key, r["name"], text)
+
+
+def test_catalog_detail_lookups_on_the_references_tables(golden):
+    """TestGetDetailWithSubCode (xid/kmsg_extended_test.go:356-464) through gpud_xid_detail with a status no rule carries (so the lookup is the
+    sub-code fallback chain), Test_detailFromNVLinkInfo_StatusSpecific's codes through the status table, GetDetail through gpud_xid_get_detail"""
+    L = g.lib()
+    G = golden("xid_kmsg.json")
+    assert all(r["ErrorStatus"] != 0xFFFFFFFE for r in O.NVLINK_RULES)
+    for r in G["detail_with_subcode"]["rows"]:
+        d = g.xid_detail(r["xid"], r["subCode"], 0xFFFFFFFE)
+        o = O.get_detail_with_sub_code(r["xid"], r["subCode"])
+        assert (d is not None) == r["expectedFound"] == (o is not None), r["name"]
+        if d is None:
+            continue
+        if r["expectedEventTypeFatal"]:
+            assert d["event_type"] == O.EV_FATAL, r["name"]
+        assert (d["event_type"], d["actions"], d["description"], d["sub_code"]) == (o.event_type, o.actions, o.description, o.sub_code), r["name"]
+    for code in list(range(0, 180)) + [99999, -3]:
+        ev, na = C.c_int32(), C.c_int32()
+        acts = (C.c_int32 * 4)()
+        found = L.gpud_xid_get_detail(code, C.byref(ev), C.byref(na), acts)
+        o = O.get_detail(code)
+        assert bool(found) == (o is not None), code
+        if o is not None:
+            assert (ev.value, None if na.value < 0 else [acts[i] for i in range(na.value)]) == (o.event_type, o.actions), code
+    assert sum(1 for c in range(0, 200) if L.gpud_xid_get_detail(c, None, None, None)) == 172          # SURVEY A.3: {1..173} \\ {133}
