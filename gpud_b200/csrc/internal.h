@@ -72,6 +72,8 @@ struct gpud_range_view {
   int q_num, q_den; cudaStream_t stream; gpud_ctx* ctx; int dev, sm_count;
 };
 int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v);
+void gpud_ring_quantile(gpud_ring* r, int* q_num, int* q_den);
+int32_t gpud_ring_range_partials_ranked(gpud_ring* r, int64_t n, int rank_from_top, gpud_range_view* v, const double** w_stat);
 
 void gpud_scan_state_free(gpud_scan_state*);
 void gpud_comm_state_free(gpud_comm_state*);

@@ -611,6 +611,8 @@ struct gpud_ring {
   double* d_rng[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // range-reduce scratch: per-window min,max,mean,ema,partials
   uint32_t* d_rng_nover = nullptr;
   size_t range_cap = 0;
+  double* d_rng_stat = nullptr;                        // per-window order statistic of the ranked range pass (experimental select, select.cu)
+  size_t range_stat_cap = 0;
   cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};   // around the two kernels of the last reduce (bench roofline)
 };
 
@@ -676,6 +678,7 @@ extern "C" int32_t gpud_ring_destroy(gpud_ring* r) {
   for (auto& p : r->d_res) cudaFree(p);
   for (auto& p : r->d_rng) cudaFree(p);
   cudaFree(r->d_rng_nover);
+  cudaFree(r->d_rng_stat);
   for (int i = 0; i < 2; ++i) {
     if (r->h_stage[i]) cudaFreeHost(r->h_stage[i]);
     cudaFree(r->d_stage[i]);
@@ -941,3 +944,49 @@ int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v) {
   v->q_num = r->q_num; v->q_den = r->q_den; v->stream = r->stream; v->ctx = r->ctx; v->dev = r->dev; v->sm_count = r->sm_count;
   return GPUD_OK;
 }
+
+// The same pass with the per-window order statistic switched on at a caller-chosen rank: every full window also reports its
+// `rank_from_top`-th largest key (nearest-rank fraction (W' - rank + 1) / W' gives exactly that rank for a full window).  Used by the
+// experimental bounded select of select.cu; the pass above is left as it is.
+int32_t gpud_ring_range_partials_ranked(gpud_ring* r, int64_t n, int rank_from_top, gpud_range_view* v, const double** w_stat) {
+  const int64_t count = ring_count(r);
+  if (n <= 0 || n > count) n = count;
+  const int Wp = (int)std::min<int64_t>(kMaxWindow, n);
+  const int nw = (int)((n + Wp - 1) / Wp);
+  if (rank_from_top < 1 || rank_from_top > Wp || !w_stat) return GPUD_E_INVALID;
+  const size_t per = (size_t)r->F * nw;
+  if (per > r->range_cap) {
+    for (auto& q : r->d_rng) { cudaFree(q); q = nullptr; }
+    cudaFree(r->d_rng_nover); r->d_rng_nover = nullptr;
+    r->range_cap = 0;
+    for (auto& q : r->d_rng) GPUD_CUDA(r->ctx, cudaMalloc(&q, per * sizeof(double)));
+    GPUD_CUDA(r->ctx, cudaMalloc(&r->d_rng_nover, per * sizeof(uint32_t)));
+    r->range_cap = per;
+  }
+  if (per > r->range_stat_cap) {
+    cudaFree(r->d_rng_stat); r->d_rng_stat = nullptr;
+    r->range_stat_cap = 0;
+    GPUD_CUDA(r->ctx, cudaMalloc(&r->d_rng_stat, per * sizeof(double)));
+    r->range_stat_cap = per;
+  }
+  int64_t start = ring_start(r) + (count - n);
+  if (start >= r->cap) start -= r->cap;
+  WinParams p;
+  p.ring = r->d_ring; p.cap = r->cap; p.start = start; p.count = n; p.W = Wp; p.F = r->F; p.nw = nw;
+  p.q_num = Wp - rank_from_top + 1; p.q_den = Wp;
+  p.thr = r->d_thr; p.pw = r->d_pw; p.q64 = pow(1.0 - r->alpha, 64.0); p.alpha = r->alpha;
+  p.out_min = r->d_rng[0]; p.out_max = r->d_rng[1]; p.out_mean = r->d_rng[2]; p.out_p99 = r->d_rng_stat; p.out_nover = r->d_rng_nover;
+  p.part = r->d_rng[4]; p.do_select = 1;
+  { int32_t rc = launch_windows(r, p); if (rc) return rc; }
+  const int m_last = (int)(n - (int64_t)(nw - 1) * Wp);
+  k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_rng[4], r->d_ring, r->cap, start, r->F, nw, pow(1.0 - r->alpha, (double)Wp),
+                                                        pow(1.0 - r->alpha, (double)m_last), r->d_rng[3]);
+  GPUD_CUDA(r->ctx, cudaGetLastError());
+  v->ring = r->d_ring; v->F = r->F; v->cap = r->cap; v->start = start; v->n = n; v->Wp = Wp; v->nw = nw;
+  v->w_min = r->d_rng[0]; v->w_max = r->d_rng[1]; v->w_mean = r->d_rng[2]; v->w_ema = r->d_rng[3]; v->w_nover = r->d_rng_nover;
+  v->q_num = r->q_num; v->q_den = r->q_den; v->stream = r->stream; v->ctx = r->ctx; v->dev = r->dev; v->sm_count = r->sm_count;
+  *w_stat = r->d_rng_stat;
+  return GPUD_OK;
+}
+
+void gpud_ring_quantile(gpud_ring* r, int* q_num, int* q_den) { *q_num = r->q_num; *q_den = r->q_den; }

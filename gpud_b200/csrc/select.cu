@@ -11,6 +11,7 @@
 // Typical cost: 3 reads of the range (window pass, histogram, collect) instead of the 7 of a plain 6-digit radix select.
 // Definitions: oracle/SPEC.md (parity unpinned: the reference has no such aggregate).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -214,6 +215,127 @@ __global__ void __launch_bounds__(256) k_sel_final(const SelState* __restrict__ 
   if (t == 0) out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(ans));
 }
 
+// ---- experimental bounded select (off unless GPUD_RANGE_V2=1) ---------------------------------------------------------
+// When the range is a whole number of windows, the window pass can report every window's m-th largest key, m = ceil(k / nw) for the
+// global rank k.  Pigeonhole: every window holds >= m keys >= its own statistic, so >= nw m >= k keys are >= t = min_w stat_w; and no
+// window holds more than m - 1 keys above its statistic, so <= nw (m - 1) <= k - 1 keys are > T = max_w stat_w.  The k-th largest key
+// therefore lies in [t, T], and it is the (k - #{keys > T})-th largest of the keys inside the interval: one more pass over the range
+// counts the former and collects the latter (tests/test_range_bounds_model.py checks the argument on random data).  Fields whose
+// interval holds more than kCollect2Max keys are handed to the histogram path above.
+constexpr int kCollect2Max = 32768;
+
+struct Sel2State {                     // one per field
+  unsigned long long t, T;             // interval bounds as totalOrder keys
+  unsigned long long above;            // keys > T
+  unsigned collected;                  // keys in [t, T] (may exceed kCollect2Max: overflow)
+  int pad;
+};
+
+// one thread per field: interval bounds from the window statistics
+__global__ void k_sel2_bounds(int F, int nw, const double* __restrict__ w_stat, Sel2State* __restrict__ s2) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  unsigned long long t = ~0ull, T = 0ull;
+  for (int w = 0; w < nw; ++w) {
+    const unsigned long long k = gpud_f64_key((unsigned long long)__double_as_longlong(w_stat[(int64_t)f * nw + w]));
+    t = min(t, k);
+    T = max(T, k);
+  }
+  Sel2State s;
+  s.t = t; s.T = T; s.above = 0ull; s.collected = 0u; s.pad = 0;
+  s2[f] = s;
+}
+
+// grid (blocks_per_field, F): count the keys above the interval, collect the keys inside it
+__global__ void __launch_bounds__(256) k_sel2_collect(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, const SelState* __restrict__ st,
+                                                       Sel2State* __restrict__ s2, unsigned long long* __restrict__ lists) {
+  const int f = blockIdx.y;
+  if (st[f].done) return;                                   // constant field: answered by the fold
+  const unsigned long long t = s2[f].t, T = s2[f].T;
+  const int64_t per = (((n + gridDim.x - 1) / gridDim.x) + 1) & ~(int64_t)1;
+  const int64_t b = min(n, (int64_t)blockIdx.x * per), e = min(n, b + per);
+  const double* __restrict__ base = ring + (int64_t)f * cap;
+  unsigned long long* __restrict__ list = lists + (int64_t)f * kCollect2Max;
+  unsigned* fill = &s2[f].collected;
+  unsigned above = 0;
+  for_each_key(base, cap, start, b, e, [&](unsigned long long key) {
+    if (key > T) ++above;
+    else if (key >= t) {
+      const unsigned pos = atomicAdd(fill, 1u);
+      if (pos < (unsigned)kCollect2Max) list[pos] = key;
+    }
+  });
+  above = __reduce_add_sync(0xffffffffu, above);
+  if ((threadIdx.x & 31) == 0 && above) atomicAdd(&s2[f].above, (unsigned long long)above);
+}
+
+// one block per field: radix select (11-bit digits, bits common to t and T skipped) over the collected list; fields that
+// overflowed the list keep done = 0 and go through the histogram path
+__global__ void __launch_bounds__(256) k_sel2_final(SelState* __restrict__ st, const Sel2State* __restrict__ s2, const unsigned long long* __restrict__ lists) {
+  __shared__ unsigned s_hist[kBins];
+  __shared__ unsigned long long s_prefix, s_kk;
+  __shared__ int s_nbits;
+  const int f = blockIdx.x, t = threadIdx.x;
+  if (st[f].done) return;
+  const Sel2State z = s2[f];
+  if (z.collected > (unsigned)kCollect2Max) return;         // overflow: left to the histogram path (st[f] untouched)
+  const unsigned cnt = z.collected;
+  const unsigned long long* __restrict__ list = lists + (int64_t)f * kCollect2Max;
+  if (t == 0) {
+    const unsigned long long diff = z.t ^ z.T;
+    const int cp = diff ? __clzll((long long)diff) : 64;
+    s_nbits = cp;
+    s_prefix = cp ? (cp == 64 ? z.T : (z.T >> (64 - cp))) : 0ull;
+    s_kk = st[f].kk - z.above;                              // rank inside the interval, 1-based from the top
+  }
+  __syncthreads();
+  while (s_nbits < 64) {
+    const int nbits = s_nbits;
+    const unsigned long long prefix = s_prefix;
+    const int d = min(kDigit, 64 - nbits), shift = 64 - nbits - d, nb = 1 << d;
+    for (int i = t; i < kBins; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    for (unsigned i = t; i < cnt; i += 256) {
+      const unsigned long long key = list[i];
+      if (nbits == 0 || (key >> (64 - nbits)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & (unsigned)(nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long acc = 0, kk = s_kk;
+      int bin = nb - 1;
+      while (bin > 0 && acc + s_hist[bin] < kk) { acc += s_hist[bin]; --bin; }
+      s_prefix = (nbits ? (prefix << d) : 0ull) | (unsigned long long)bin;
+      s_nbits = nbits + d;
+      s_kk = kk - acc;
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    SelState s = st[f];
+    s.done = 1;
+    s.ans = s_prefix;
+    s.nbits = 64;
+    s.prefix = s_prefix;
+    st[f] = s;
+  }
+}
+
+// host side of the experimental path: 0 = not applicable (caller runs the regular path), 1 = launched
+static int range_v2_applicable(int64_t n, int q_num, int q_den, int* rank_m) {
+  const char* env = getenv("GPUD_RANGE_V2");
+  if (!env || env[0] != '1') return 0;
+  const int64_t Wp = std::min<int64_t>(1024, n);
+  if (n <= kCollectMax || Wp < 1 || (n % Wp) != 0) return 0;
+  const int64_t nw = n / Wp;
+  long long r = (long long)((n * q_num + q_den - 1) / q_den);
+  r = r < 1 ? 1 : (r > n ? n : r);
+  const int64_t k = n - r + 1;
+  const int64_t m = (k + nw - 1) / nw;
+  if (m < 1 || m > Wp) return 0;
+  *rank_m = (int)m;
+  return 1;
+}
+
 }  // namespace
 
 extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64, uint32_t* out_n_over) {
@@ -222,7 +344,16 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   int64_t total = 0, count = 0, nwin = 0;
   gpud_ring_counts(ring, &total, &count, &nwin);
   if (count == 0) return GPUD_E_STATE;
-  int32_t rc = gpud_ring_range_partials(ring, last_n, &v);
+  int32_t rc;
+  const double* w_stat = nullptr;
+  int rank_m = 0;
+  {
+    const int64_t n_eff = (last_n <= 0 || last_n > count) ? count : last_n;
+    int qn = 99, qd = 100;
+    gpud_ring_quantile(ring, &qn, &qd);
+    if (range_v2_applicable(n_eff, qn, qd, &rank_m)) rc = gpud_ring_range_partials_ranked(ring, last_n, rank_m, &v, &w_stat);
+    else rc = gpud_ring_range_partials(ring, last_n, &v);
+  }
   if (rc) return rc;
   gpud_ctx* ctx = v.ctx;
   GPUD_CUDA(ctx, cudaSetDevice(v.dev));
@@ -231,6 +362,8 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   unsigned* d_hist = nullptr;
   SelState* d_st = nullptr;
   unsigned long long* d_lists = nullptr;
+  Sel2State* d_s2 = nullptr;
+  unsigned long long* d_lists2 = nullptr;
   cudaError_t e = cudaMallocAsync(&d_out, 5 * v.F * sizeof(double), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nover, v.F * sizeof(uint32_t), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_hist, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
@@ -242,20 +375,34 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
                                                          d_out, d_nover, d_st);
     // blocks per field: enough CTAs to fill the machine a few times over, each streaming >= 16 Ki keys
     const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 8 * v.sm_count / v.F + 1)));
-    if (v.n > kCollectMax) {
+    if (w_stat) {                                                  // experimental bounded select; fields it cannot finish stay !done
+      e = cudaMallocAsync(&d_s2, v.F * sizeof(Sel2State), v.stream);
+      if (e == cudaSuccess) e = cudaMallocAsync(&d_lists2, (size_t)v.F * kCollect2Max * sizeof(unsigned long long), v.stream);
+      if (e == cudaSuccess) {
+        k_sel2_bounds<<<(v.F + 127) / 128, 128, 0, v.stream>>>(v.F, v.nw, w_stat, d_s2);
+        k_sel2_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_s2, d_lists2);
+        k_sel2_final<<<v.F, 256, 0, v.stream>>>(d_st, d_s2, d_lists2);
+        e = cudaGetLastError();
+      }
+    }
+    if (e == cudaSuccess && v.n > kCollectMax) {
       for (int pass = 0; pass < kMaxHistPasses; ++pass) {          // later passes exit at once for fields that are already narrow
         k_sel_hist<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_hist);
         k_sel_pick<<<v.F, 256, 0, v.stream>>>(d_hist, d_st);
       }
     }
-    k_sel_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_lists);
-    k_sel_final<<<v.F, 256, 0, v.stream>>>(d_st, d_lists, v.F, d_out);
-    e = cudaGetLastError();
+    if (e == cudaSuccess) {
+      k_sel_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_lists);
+      k_sel_final<<<v.F, 256, 0, v.stream>>>(d_st, d_lists, v.F, d_out);
+      e = cudaGetLastError();
+    }
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
   cudaFreeAsync(d_out, v.stream); cudaFreeAsync(d_nover, v.stream); cudaFreeAsync(d_hist, v.stream);
   cudaFreeAsync(d_st, v.stream); cudaFreeAsync(d_lists, v.stream);
+  if (d_s2) cudaFreeAsync(d_s2, v.stream);
+  if (d_lists2) cudaFreeAsync(d_lists2, v.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
   if (e != cudaSuccess) return gpud_fail(ctx, GPUD_E_CUDA, "reduce_range: %s", cudaGetErrorString(e));
   return GPUD_OK;

@@ -1,6 +1,7 @@
 """GPU parity: the CUDA path behind the C ABI vs the oracle on the same inputs.  Run on the B200 box: pytest -m gpu.
 Integer / byte / selection outputs are compared bit-exactly; mean and EMA at 1e-6 relative (oracle/SPEC.md)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -572,6 +573,49 @@ def test_ring_reduce_range(ctx, last_n):
         scale = float(np.max(np.abs(seg[:, f])))
         for k in ("mean", "ema"):
             assert abs(got[k][f] - want[k][0]) <= 1e-6 * max(abs(want[k][0]), scale), (k, f)
+    r.close()
+
+
+@pytest.mark.skipif(os.environ.get("GPUD_TEST_EXPERIMENTAL") != "1", reason="experimental bounded select (GPUD_RANGE_V2): run with GPUD_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("shape", ["gauge", "ties", "uniform", "drift", "const"])
+@pytest.mark.parametrize("n,qn,qd", [(65536, 99, 100), (32768, 1, 2), (16384, 999, 1000), (131072, 1, 100)])
+def test_ring_reduce_range_bounded_select(ctx, shape, n, qn, qd):
+    """the order statistic of a whole-window range from the per-window statistics' interval; identical to the oracle and to the
+    regular path, on data where the interval is narrow (stationary), wide (drift -> falls back per field) and degenerate (ties, constants)"""
+    F, W = 5, 1000
+    rng = np.random.default_rng(n + qn)
+    if shape == "gauge":
+        x = synth.gauge_stream(F, n, seed=5)
+    elif shape == "ties":
+        x = np.floor(rng.normal(60, 2, (n, F)))
+    elif shape == "uniform":
+        x = np.floor(rng.uniform(30000, 90000, (n, F)))
+    elif shape == "drift":
+        x = 60 + 25 * np.sin(np.arange(n)[:, None] / n * 7.0 + np.arange(F)[None, :]) + rng.normal(0, 0.3, (n, F))
+    else:
+        x = np.full((n, F), 42.0)
+        x[:, 1] = -0.0
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, n, W, thresholds=thr, q_num=qn, q_den=qd)
+    r.push(np.ascontiguousarray(x))
+    old = os.environ.pop("GPUD_RANGE_V2", None)
+    try:
+        base = r.reduce_range(0)
+        os.environ["GPUD_RANGE_V2"] = "1"
+        got = r.reduce_range(0)
+    finally:
+        os.environ.pop("GPUD_RANGE_V2", None)
+        if old is not None:
+            os.environ["GPUD_RANGE_V2"] = old
+    for f in range(F):
+        want = O.window_aggregates(x[:, f], n, thr[f], 2.0 / (W + 1.0), q_num=qn, q_den=qd) if "q_num" in O.window_aggregates.__code__.co_varnames else None
+        for k in ("min", "max", "p99"):
+            assert got[k][f:f + 1].view(np.uint64)[0] == base[k][f:f + 1].view(np.uint64)[0], (k, f)
+            if want is not None:
+                assert got[k][f:f + 1].view(np.uint64)[0] == want[k].view(np.uint64)[0], (k, f)
+        assert int(got["n_over"][f]) == int(base["n_over"][f])
+        for k in ("mean", "ema"):
+            assert got[k][f] == base[k][f], (k, f)
     r.close()
 
 
