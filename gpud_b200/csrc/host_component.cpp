@@ -967,6 +967,31 @@ int32_t gpudh_evolve_stored_sxid(const char* events, int32_t* health, int32_t* a
   return 0;
 }
 
+// mergeEvents / trimEventsAfterSetHealthy (xid/component.go:614-642) on bare (time, name) lists; names joined by '\n'
+int32_t gpudh_merge_times(const int64_t* a, int32_t na, const int64_t* b, int32_t nb, int64_t* out) {
+  std::vector<gpud::Event> ea((size_t)na), eb((size_t)nb);
+  for (int32_t i = 0; i < na; ++i) ea[(size_t)i].time_unix = a[i];
+  for (int32_t i = 0; i < nb; ++i) eb[(size_t)i].time_unix = b[i];
+  const std::vector<gpud::Event> m = gpud::merge_events(ea, eb);
+  for (size_t i = 0; i < m.size(); ++i) out[i] = m[i].time_unix;
+  return (int32_t)m.size();
+}
+int32_t gpudh_trim_count(const char* names_newest_first) {
+  std::vector<gpud::Event> ev;
+  std::string s = names_newest_first ? names_newest_first : "";
+  size_t a = 0;
+  while (a <= s.size() && !s.empty()) {
+    size_t e = s.find('\n', a);
+    if (e == std::string::npos) e = s.size();
+    gpud::Event x;
+    x.name = s.substr(a, e - a);
+    ev.push_back(x);
+    if (e == s.size()) break;
+    a = e + 1;
+  }
+  return (int32_t)gpud::trim_events_after_set_healthy(ev).size();
+}
+
 void* gpudh_xid_component_new(gpud_ctx* ctx, int32_t dev, int32_t row_remap, int32_t reboot_threshold) {
   return new gpud::XidComponent(ctx, dev, row_remap != 0, reboot_threshold);
 }

@@ -654,3 +654,25 @@ def test_catalog_detail_lookups_on_the_references_tables(golden):
         if o is not None:
             assert (ev.value, None if na.value < 0 else [acts[i] for i in range(na.value)]) == (o.event_type, o.actions), code
     assert sum(1 for c in range(0, 200) if L.gpud_xid_get_detail(c, None, None, None)) == 172          # {1..173} \\ {133}
+
+
+def test_merge_and_trim_scenarios_of_the_reference():
+    """TestMergeEvents / TestTrimEventsAfterSetHealthy (xid/component_test.go:81-207; the sxid twins are the same functions)"""
+    L = g.lib()
+    now = 1_770_000_000
+    H, M = 3600, 60
+
+    def merge(a, b):
+        aa, bb = (C.c_int64 * max(1, len(a)))(*a), (C.c_int64 * max(1, len(b)))(*b)
+        out = (C.c_int64 * max(1, len(a) + len(b)))()
+        n = L.gpudh_merge_times(aa, len(a), bb, len(b), out)
+        return [out[i] for i in range(n)]
+    for a, b, want_len in (([], [], 0), ([], [now], 1), ([now], [], 1), ([now - H, now], [now - 2 * H, now - 30 * M], 4)):     # the table
+        got = merge(a, b)
+        assert len(got) == want_len and got == sorted(got, reverse=True)
+    assert merge([now + 2 * H, now - H], [now, now - 2 * H]) == [now + 2 * H, now, now - H, now - 2 * H]                           # "verify sorting"
+    assert L.gpudh_trim_count(b"error_xid\nSetHealthy\nerror_xid") == 1          # dropsEventsOlderThanSetHealthy
+    assert L.gpudh_trim_count(b"error_xid\nerror_xid") == 2                       # noSetHealthyReturnsOriginal
+    assert L.gpudh_trim_count(b"SetHealthy") == 0                                 # onlySetHealthyReturnsEmpty
+    assert O.trim_events_after_set_healthy([{"name": "error_xid"}, {"name": "SetHealthy"}, {"name": "error_xid"}]) == [{"name": "error_xid"}]
+    assert O.trim_events_after_set_healthy([{"name": "SetHealthy"}]) == []
