@@ -65,3 +65,59 @@ def test_bound_with_a_short_last_window():
             if m2 <= wp:
                 T = srt[:, wp - m2].max()
                 assert int((keys > T).sum()) < k and ans <= T               # at most nw (m2 - 1) + s <= k - 1 keys lie above T
+
+
+def _emulate_sel2(keys, nw, wp, k):
+    """line-by-line emulation of k_sel2_bounds / k_sel2_collect / k_sel2_final (csrc/select.cu) with Python integers"""
+    win = keys.reshape(nw, wp)
+    m = -(-k // nw)
+    stat = np.sort(win, axis=1)[:, wp - m]                       # what the ranked window pass reports
+    t, T = int(stat.min()), int(stat.max())
+    above, lst = 0, []
+    for key in map(int, keys):
+        if key > T:
+            above += 1
+        elif key >= t:
+            lst.append(key)
+    diff = t ^ T
+    cp = 64 if diff == 0 else 64 - diff.bit_length()             # __clzll
+    nbits = cp
+    prefix = 0 if cp == 0 else (T if cp == 64 else T >> (64 - cp))
+    kk = k - above
+    assert kk >= 1
+    while nbits < 64:
+        d = min(11, 64 - nbits)
+        shift, nb = 64 - nbits - d, 1 << d
+        hist = [0] * nb
+        for key in lst:
+            if nbits == 0 or (key >> (64 - nbits)) == prefix:
+                hist[(key >> shift) & (nb - 1)] += 1
+        acc, b = 0, nb - 1
+        while b > 0 and acc + hist[b] < kk:
+            acc += hist[b]
+            b -= 1
+        prefix = ((prefix << d) if nbits else 0) | b
+        nbits += d
+        kk -= acc
+    return prefix, len(lst)
+
+
+def test_emulated_bounded_select_equals_sort():
+    rng = np.random.default_rng(31)
+    for trial in range(120):
+        nw, wp = int(rng.integers(1, 12)), int(rng.integers(1, 64))
+        n = nw * wp
+        shape = rng.integers(0, 4)
+        if shape == 0:
+            x = rng.normal(0.0, 1.0, n)                          # both signs: keys span the sign bit (no common prefix)
+        elif shape == 1:
+            x = np.floor(rng.uniform(30, 34, n))
+        elif shape == 2:
+            x = np.full(n, 7.25)
+        else:
+            x = rng.uniform(1e-300, 1e300, n) * rng.choice([-1.0, 1.0], n)
+        keys = O.total_order_key(x)
+        k = int(rng.integers(1, n + 1))
+        got, n_list = _emulate_sel2(keys, nw, wp, k)
+        assert got == int(np.sort(keys)[n - k]), (trial, nw, wp, k)
+        assert 1 <= n_list <= n
