@@ -85,3 +85,20 @@ def test_c_consumer_links_and_runs(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
+
+
+def test_product_never_touches_the_oracle():
+    """the oracle is the checker only: no Python module of the product imports it, the shared library neither links nor dlopens it"""
+    import glob
+    import subprocess
+    for path in glob.glob(os.path.join(ROOT, "gpud_b200", "*.py")):
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
+    for path in glob.glob(os.path.join(ROOT, "gpud_b200", "csrc", "*")):
+        if path.endswith((".cu", ".cpp", ".h")):
+            src = open(path).read()
+            assert "liboracle" not in src and not re.search(r'#include\s+"[^"]*oracle', src), path
+    out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "liboracle" not in out
+    blob = open(capi.LIB_PATH, "rb").read()
+    assert b"liboracle" not in blob and b"orc_scan_lines" not in blob
