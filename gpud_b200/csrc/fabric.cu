@@ -85,11 +85,12 @@ __global__ void __launch_bounds__(32) k_fabric_pack(const gpud_fabric_raw* __res
 
 // wait until all n ranks have published this epoch into my table (peer-store mode), then evaluate
 __global__ void __launch_bounds__(32) k_fabric_verdict(const gpud_fabric_local* __restrict__ all, int n, int at_least,
-                                                        volatile unsigned* flag, unsigned want, gpud_fabric_verdict* out) {
+                                                        volatile unsigned* flag, unsigned want, gpud_fabric_verdict* out, unsigned* timed_out) {
   if (flag) {
     if (threadIdx.x == 0) {
       long long spins = 0;
-      while (*flag < want && spins < (1ll << 26)) { __nanosleep(100); ++spins; }
+      while (*flag < want && spins < (1ll << 24)) { __nanosleep(100); ++spins; }     // ~2 s: a peer's record never arrived
+      if (timed_out) *timed_out = *flag < want ? 1u : 0u;                           // the host turns this into GPUD_E_STATE
     }
     __syncwarp();
     __threadfence_system();
@@ -193,12 +194,13 @@ struct gpud_comm_state {
   gpud_fabric_local* d_send = nullptr;
   gpud_fabric_local* d_all = nullptr;
   gpud_fabric_verdict* d_verdict = nullptr;
+  unsigned* d_timeout = nullptr;         // set by the verdict kernel when the peer-store arrivals never completed
 };
 
 void gpud_comm_state_free(gpud_comm_state* c) {
   if (!c) return;
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  cudaFree(c->d_raw); cudaFree(c->d_send); cudaFree(c->d_all); cudaFree(c->d_verdict);
+  cudaFree(c->d_raw); cudaFree(c->d_send); cudaFree(c->d_all); cudaFree(c->d_verdict); cudaFree(c->d_timeout);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -208,13 +210,20 @@ static int32_t comm_scratch(gpud_ctx* ctx, int dev, gpud_comm_state** out) {
   if (slot < 0) return gpud_fail(ctx, GPUD_E_INVALID, "device %d is not part of this ctx", dev);
   GPUD_CUDA(ctx, cudaSetDevice(dev));
   if (!ctx->comm[slot]) {
+    // built locally and published only once every allocation has succeeded: a half-initialised state must never be reused
     gpud_comm_state* c = new gpud_comm_state();
+    cudaError_t e = cudaMalloc(&c->d_raw, sizeof(gpud_fabric_raw));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_send, sizeof(gpud_fabric_local));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_all, GPUD_MAX_GPUS * sizeof(gpud_fabric_local));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_verdict, sizeof(gpud_fabric_verdict));
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_timeout, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(c->d_timeout, 0, sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      gpud_comm_state_free(c);
+      return gpud_fail(ctx, e == cudaErrorMemoryAllocation ? GPUD_E_NOMEM : GPUD_E_CUDA, "fabric scratch on device %d: %s", dev, cudaGetErrorString(e));
+    }
     ctx->comm[slot] = c;
-    GPUD_CUDA(ctx, cudaMalloc(&c->d_raw, sizeof(gpud_fabric_raw)));
-    GPUD_CUDA(ctx, cudaMalloc(&c->d_send, sizeof(gpud_fabric_local)));
-    GPUD_CUDA(ctx, cudaMalloc(&c->d_all, GPUD_MAX_GPUS * sizeof(gpud_fabric_local)));
-    GPUD_CUDA(ctx, cudaMalloc(&c->d_verdict, sizeof(gpud_fabric_verdict)));
-    GPUD_CUDA(ctx, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   }
   *out = ctx->comm[slot];
   return GPUD_OK;
@@ -246,7 +255,7 @@ extern "C" int32_t gpud_fabric_verdict_device(gpud_ctx* ctx, int32_t dev, const 
   int32_t rc = comm_scratch(ctx, dev, &c);
   if (rc) return rc;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
-  k_fabric_verdict<<<1, 32, 0, st>>>(reinterpret_cast<const gpud_fabric_local*>(dev_all), n, at_least, nullptr, 0, c->d_verdict);
+  k_fabric_verdict<<<1, 32, 0, st>>>(reinterpret_cast<const gpud_fabric_local*>(dev_all), n, at_least, nullptr, 0, c->d_verdict, nullptr);
   GPUD_CUDA(ctx, cudaGetLastError());
   GPUD_CUDA(ctx, cudaMemcpyAsync(out, c->d_verdict, sizeof *out, cudaMemcpyDeviceToHost, st));
   GPUD_CUDA(ctx, cudaStreamSynchronize(st));
@@ -291,7 +300,7 @@ extern "C" int32_t gpud_fabric_gather(gpud_ctx* ctx, int32_t dev, const gpud_fab
   GPUD_CUDA(ctx, cudaGetLastError());
   const int r = g_nccl.AllGather(c->d_send, c->d_all, sizeof(gpud_fabric_local), /*ncclChar*/ 0, c->comm, c->stream);
   if (r != 0) return gpud_fail(ctx, GPUD_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-  k_fabric_verdict<<<1, 32, 0, c->stream>>>(c->d_all, c->n_ranks, at_least, nullptr, 0, c->d_verdict);
+  k_fabric_verdict<<<1, 32, 0, c->stream>>>(c->d_all, c->n_ranks, at_least, nullptr, 0, c->d_verdict, nullptr);
   GPUD_CUDA(ctx, cudaGetLastError());
   GPUD_CUDA(ctx, cudaMemcpyAsync(out, c->d_verdict, sizeof *out, cudaMemcpyDeviceToHost, c->stream));
   if (all_out) GPUD_CUDA(ctx, cudaMemcpyAsync(all_out, c->d_all, (size_t)c->n_ranks * sizeof(gpud_fabric_local), cudaMemcpyDeviceToHost, c->stream));
@@ -327,11 +336,23 @@ extern "C" int32_t gpud_fabric_gather_p2p(gpud_ctx* ctx, const gpud_fabric_raw* 
       }
     }
   }
-  // arrival counters are monotonically increasing: epoch k expects k*n arrivals
-  static std::mutex mu;
-  static unsigned epoch = 0;
-  std::lock_guard<std::mutex> g(mu);
-  ++epoch;
+  // Arrival counters live in this ctx's tables and only grow: call number k of THIS ctx expects k*n arrivals.  A call that
+  // failed after some of its pack kernels were launched leaves the counters out of step; the ctx is then marked dirty and the
+  // next call starts over from zeroed counters.
+  std::lock_guard<std::mutex> g(ctx->fabric_mu);
+  if (ctx->fabric_dirty) {
+    for (int i = 0; i < n; ++i) {
+      GPUD_CUDA(ctx, cudaSetDevice(ctx->devs[i]));
+      GPUD_CUDA(ctx, cudaDeviceSynchronize());
+    }
+    for (int i = 0; i < n; ++i) {
+      GPUD_CUDA(ctx, cudaSetDevice(ctx->devs[i]));
+      GPUD_CUDA(ctx, cudaMemset(&reinterpret_cast<P2PTable*>(ctx->fabric_tables[i])->arrivals, 0, sizeof(unsigned)));
+    }
+    ctx->fabric_epoch = 0;
+  }
+  ctx->fabric_dirty = true;                                            // cleared only when the whole call has succeeded
+  const unsigned epoch = ++ctx->fabric_epoch;
   for (int i = 0; i < n; ++i) {
     GPUD_CUDA(ctx, cudaSetDevice(ctx->devs[i]));
     GPUD_CUDA(ctx, cudaMemcpyAsync(cs[i]->d_raw, &raws[i], sizeof(gpud_fabric_raw), cudaMemcpyHostToDevice, cs[i]->stream));
@@ -350,15 +371,20 @@ extern "C" int32_t gpud_fabric_gather_p2p(gpud_ctx* ctx, const gpud_fabric_raw* 
   for (int i = 0; i < n; ++i) {
     GPUD_CUDA(ctx, cudaSetDevice(ctx->devs[i]));
     P2PTable* t = reinterpret_cast<P2PTable*>(ctx->fabric_tables[i]);
-    k_fabric_verdict<<<1, 32, 0, cs[i]->stream>>>(t->rec, n, at_least, &t->arrivals, epoch * (unsigned)n, cs[i]->d_verdict);
+    k_fabric_verdict<<<1, 32, 0, cs[i]->stream>>>(t->rec, n, at_least, &t->arrivals, epoch * (unsigned)n, cs[i]->d_verdict, cs[i]->d_timeout);
     GPUD_CUDA(ctx, cudaGetLastError());
     GPUD_CUDA(ctx, cudaMemcpyAsync(&verdicts[i], cs[i]->d_verdict, sizeof(gpud_fabric_verdict), cudaMemcpyDeviceToHost, cs[i]->stream));
     if (all_out && i == 0)
       GPUD_CUDA(ctx, cudaMemcpyAsync(all_out, t->rec, (size_t)n * sizeof(gpud_fabric_local), cudaMemcpyDeviceToHost, cs[i]->stream));
   }
+  std::vector<unsigned> late(n, 0u);
   for (int i = 0; i < n; ++i) {
     GPUD_CUDA(ctx, cudaSetDevice(ctx->devs[i]));
+    GPUD_CUDA(ctx, cudaMemcpyAsync(&late[i], cs[i]->d_timeout, sizeof(unsigned), cudaMemcpyDeviceToHost, cs[i]->stream));
     GPUD_CUDA(ctx, cudaStreamSynchronize(cs[i]->stream));
   }
+  for (int i = 0; i < n; ++i)
+    if (late[i]) return gpud_fail(ctx, GPUD_E_STATE, "fabric gather: device %d never saw all %d records (incomplete gather, verdict not valid)", ctx->devs[i], n);
+  ctx->fabric_dirty = false;
   return GPUD_OK;
 }

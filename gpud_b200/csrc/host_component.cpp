@@ -141,7 +141,7 @@ const Event* EventBucket::find(const Event& ev) const {
 }
 std::vector<Event> EventBucket::get(int64_t since_unix) const {
   std::vector<Event> out;
-  for (const Event& e : events_) if (e.time_unix >= since_unix) out.push_back(e);
+  for (const Event& e : events_) if (e.time_unix > since_unix) out.push_back(e);   // getEvents: WHERE timestamp > ? (pkg/eventstore/database.go:330)
   std::stable_sort(out.begin(), out.end(), [](const Event& a, const Event& b) { return a.time_unix > b.time_unix; });
   return out;
 }
@@ -619,8 +619,8 @@ int32_t XidComponent::IngestHits(const std::vector<gpud_xid_hit>& hits, int64_t 
 }
 
 void XidComponent::update_state() {                // component.go:581-611
-  std::vector<Event> local = trim_events_after_set_healthy(bucket_.get(0));
-  std::vector<Event> all = merge_events(reboots_.get(0), local);
+  std::vector<Event> local = trim_events_after_set_healthy(bucket_.get(INT64_MIN));
+  std::vector<Event> all = merge_events(reboots_.get(INT64_MIN), local);
   const StoredEvolveResult r = evolve_stored_events(all, devices_, reboot_threshold_);
   cur_.health = r.health;
   cur_.has_actions = r.has_actions;

@@ -23,6 +23,9 @@ struct gpud_ctx {
   std::vector<gpud_comm_state*> comm;   // per dev slot
   std::vector<void*> fabric_tables;     // per dev slot: device table [GPUD_MAX_GPUS] x 128 B (+flags) for p2p gather
   int sm_count = 148;
+  std::mutex fabric_mu;                 // gpud_fabric_gather_p2p: one gather at a time per ctx
+  unsigned fabric_epoch = 0;            // gathers completed or begun on this ctx's tables (arrival counters expect epoch * n)
+  bool fabric_dirty = false;            // the last gather did not finish: counters are re-zeroed before the next one
 };
 
 inline int32_t gpud_fail(gpud_ctx* ctx, int32_t code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
@@ -65,15 +68,25 @@ __host__ __device__ __forceinline__ unsigned long long gpud_key_f64bits(unsigned
 }
 #endif
 
-// view of a ring range after the per-window pass (ring.cu -> select.cu)
+// view of a ring range around the per-window pass (ring.cu <-> select.cu)
+#define GPUD_RANGE_SAMPLED_MIN 65536   /* ranges at least this long take the sampled-pivot single pass */
+#define GPUD_RANGE_LIST_CAP 65536      /* keys between the pivots kept per field */
 struct gpud_range_view {
   const double* ring; int F; int64_t cap, start, n; int Wp, nw;
   const double *w_min, *w_max, *w_mean, *w_ema; const uint32_t* w_nover;
   int q_num, q_den; cudaStream_t stream; gpud_ctx* ctx; int dev, sm_count;
+  int sampled;                         // 1: the pass classifies against `piv` and fills `lists`
+  unsigned list_cap;
+  double* piv;                         // [F][2] lo, hi
+  unsigned* fill;                      // [F]
+  uint4* w_cls;                        // [F][nw] {above hi, == hi, == lo, strictly inside}
+  unsigned long long* lists;           // [F][list_cap]
+  cudaEvent_t ev[3];
 };
-int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v);
+int32_t gpud_ring_range_prepare(gpud_ring* r, int64_t n, gpud_range_view* v);
+int32_t gpud_ring_range_pass(gpud_ring* r, const gpud_range_view* v);
+void gpud_ring_range_note(gpud_ring* r, bool sampled, unsigned fields_open);
 void gpud_ring_quantile(gpud_ring* r, int* q_num, int* q_den);
-int32_t gpud_ring_range_partials_ranked(gpud_ring* r, int64_t n, int rank_from_top, gpud_range_view* v, const double** w_stat);
 
 void gpud_scan_state_free(gpud_scan_state*);
 void gpud_comm_state_free(gpud_comm_state*);

@@ -1262,7 +1262,7 @@ struct gpud_scan_state {
   int dev = 0;
   gpud_tables* d_tables = nullptr;
   uint8_t* d_buf = nullptr; size_t buf_cap = 0;
-  uint32_t* d_chunk_sep = nullptr; uint32_t* d_chunk_local = nullptr; unsigned long long* d_tile_base = nullptr; size_t chunk_cap = 0;
+  uint32_t* d_chunk_sep = nullptr; uint32_t* d_chunk_local = nullptr; unsigned long long* d_tile_base = nullptr; size_t chunk_sep_cap = 0, chunk_local_cap = 0, tile_cap = 0;
   unsigned long long* d_cands = nullptr; size_t cand_cap = 0;
   unsigned long long* d_side = nullptr; size_t side_cap = 0;   // family-sorted copy of short candidate lists
   gpud_xid_hit* d_hits = nullptr; size_t hit_cap = 0;
@@ -1292,15 +1292,20 @@ static int32_t scan_state_get(gpud_ctx* ctx, int dev, gpud_scan_state** out) {
   if (slot < 0) return gpud_fail(ctx, GPUD_E_INVALID, "device %d is not part of this ctx", dev);
   GPUD_CUDA(ctx, cudaSetDevice(dev));
   if (!ctx->scan[slot]) {
+    // built locally, published only when every allocation has succeeded (a half-built state must never be picked up later)
     gpud_scan_state* s = new gpud_scan_state();
     s->dev = dev;
+    cudaError_t e = cudaMalloc(&s->d_tables, sizeof(gpud_tables));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_tables, gpud_host_tables(), sizeof(gpud_tables), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, (4 + 2 * kSortBins) * sizeof(unsigned long long));   // + family histogram and cursors
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    for (auto& ev : s->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) {
+      gpud_scan_state_free(s);
+      return gpud_fail(ctx, e == cudaErrorMemoryAllocation ? GPUD_E_NOMEM : GPUD_E_CUDA, "scan state on device %d: %s", dev, cudaGetErrorString(e));
+    }
     ctx->scan[slot] = s;
-    GPUD_CUDA(ctx, cudaMalloc(&s->d_tables, sizeof(gpud_tables)));
-    GPUD_CUDA(ctx, cudaMemcpy(s->d_tables, gpud_host_tables(), sizeof(gpud_tables), cudaMemcpyHostToDevice));
-    GPUD_CUDA(ctx, cudaMalloc(&s->d_counters, (4 + 2 * kSortBins) * sizeof(unsigned long long)));   // + family histogram and cursors
-    GPUD_CUDA(ctx, cudaMallocHost(&s->h_counters, 4 * sizeof(unsigned long long)));
-    GPUD_CUDA(ctx, cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (auto& e : s->ev) GPUD_CUDA(ctx, cudaEventCreate(&e));
   }
   *out = ctx->scan[slot];
   return GPUD_OK;
@@ -1409,13 +1414,9 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
                            cudaStream_t st) {
   const int64_t n_chunks = std::max<int64_t>(1, (len + kChunk - 1) / kChunk);
   const int64_t n_tiles = (n_chunks + 1023) / 1024;
-  size_t cc = s->chunk_cap;
-  GPUD_CUDA(ctx, grow(&s->d_chunk_sep, &cc, (size_t)n_chunks));
-  cc = s->chunk_cap;
-  GPUD_CUDA(ctx, grow(&s->d_chunk_local, &cc, (size_t)n_chunks));
-  cc = s->chunk_cap;
-  GPUD_CUDA(ctx, grow(&s->d_tile_base, &cc, (size_t)n_chunks / 1024 + 2));
-  s->chunk_cap = cc;
+  GPUD_CUDA(ctx, grow(&s->d_chunk_sep, &s->chunk_sep_cap, (size_t)n_chunks));
+  GPUD_CUDA(ctx, grow(&s->d_chunk_local, &s->chunk_local_cap, (size_t)n_chunks));
+  GPUD_CUDA(ctx, grow(&s->d_tile_base, &s->tile_cap, (size_t)n_chunks / 1024 + 2));
   GPUD_CUDA(ctx, grow(&s->d_cands, &s->cand_cap, (size_t)(len / 4 + 1024)));
   GPUD_CUDA(ctx, grow(&s->d_hits, &s->hit_cap, (size_t)std::max<int64_t>(hit_cap_req, 1024)));
   GPUD_CUDA(ctx, cudaMemsetAsync(s->d_counters, 0, (4 + 2 * kSortBins) * sizeof(unsigned long long), st));

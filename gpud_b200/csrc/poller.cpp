@@ -7,8 +7,9 @@
 //   SM MHz            nvmlDeviceGetClockInfo(NVML_CLOCK_SM)
 //   gpu / mem util %  dev.GetUtilizationRates()                        components/accelerator/nvidia/utilization/utilization.go:44
 //   memory used MiB   dev.GetMemoryInfo()                              components/accelerator/nvidia/memory/memory.go:83
-// NVML is dlopen'ed (libnvidia-ml.so.1 ships with the driver, not with CUDA); a getter the device does not support
-// reports GPUD_POLL_UNSUPPORTED (0xffffffff) in its column, like the reference's "...Supported = false" fields.
+// NVML is dlopen'ed (libnvidia-ml.so.1 ships with the driver, not with CUDA).  A getter that fails - unsupported or transient -
+// never puts a sentinel into the ring: its column repeats the last good value and the failure is recorded beside the rows
+// (gpud_poll_row_hold / gpud_poller_errors), like the reference's "...Supported = false" fields next to an unset gauge.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
@@ -92,6 +93,10 @@ struct gpud_poller {
   uint32_t* rows = nullptr;      // pinned [cap_rows][GPUD_POLL_N_FIELDS]
   int64_t cap_rows = 0, n_rows = 0;
   double last_poll_s = 0.0;      // wall time of the last gpud_poller_poll call
+  uint32_t held[GPUD_POLL_N_FIELDS] = {0};       // last good value per column (what a failed getter's column repeats)
+  uint32_t fail_mask = 0;                        // columns that failed at least once since create
+  int32_t last_rc[GPUD_POLL_N_FIELDS] = {0};     // the NVML return code of each column's last failure
+  uint64_t n_failed[GPUD_POLL_N_FIELDS] = {0};
 };
 
 extern "C" int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* ring, gpud_poller** out) {
@@ -120,19 +125,52 @@ extern "C" void gpud_poller_destroy(gpud_poller* p) {
   delete p;
 }
 
+// The poller's rule for a getter that fails (oracle/SPEC.md "poll rows"): the column HOLDS its last good value (0 before the first
+// good read) and the failure is recorded beside the row - a sentinel must never reach the ring, where it would be aggregated as a
+// 4.29e9 reading.  Pure, exported for the CPU tests.
+extern "C" int32_t gpud_poll_row_hold(const uint32_t* fresh, const int32_t* nvml_rc, int32_t n_cols, uint32_t* held, uint32_t* row_out, uint32_t* fail_mask) {
+  if (!fresh || !nvml_rc || !held || !row_out || n_cols < 0 || n_cols > 32) return GPUD_E_INVALID;
+  uint32_t mask = 0;
+  for (int32_t c = 0; c < n_cols; ++c) {
+    if (nvml_rc[c] == 0) held[c] = fresh[c];
+    else mask |= 1u << c;
+    row_out[c] = held[c];
+  }
+  if (fail_mask) *fail_mask = mask;
+  return GPUD_OK;
+}
+
 // one poll row: eight getters, in GPUD_POLL_* order
-static void poll_row(Nvml* N, nvmlDevice_t h, uint32_t* r) {
-  unsigned int v;
-  r[GPUD_POLL_TEMPERATURE_C] = N->temperature(h, 0 /* NVML_TEMPERATURE_GPU */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
-  r[GPUD_POLL_POWER_MW] = N->power(h, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
-  r[GPUD_POLL_CLOCK_GRAPHICS_MHZ] = N->clock(h, 0 /* NVML_CLOCK_GRAPHICS */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
-  r[GPUD_POLL_CLOCK_SM_MHZ] = N->clock(h, 1 /* NVML_CLOCK_SM */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
-  r[GPUD_POLL_CLOCK_MEM_MHZ] = N->clock(h, 2 /* NVML_CLOCK_MEM */, &v) == 0 ? v : GPUD_POLL_UNSUPPORTED;
-  nvmlUtilization_t u;
-  if (N->util(h, &u) == 0) { r[GPUD_POLL_UTIL_GPU_PCT] = u.gpu; r[GPUD_POLL_UTIL_MEM_PCT] = u.memory; }
-  else r[GPUD_POLL_UTIL_GPU_PCT] = r[GPUD_POLL_UTIL_MEM_PCT] = GPUD_POLL_UNSUPPORTED;
-  nvmlMemory_t m;
-  r[GPUD_POLL_MEMORY_USED_MIB] = N->memory(h, &m) == 0 ? (uint32_t)(m.used >> 20) : GPUD_POLL_UNSUPPORTED;
+static void poll_row(Nvml* N, gpud_poller* p, uint32_t* r) {
+  unsigned int v = 0;
+  uint32_t fresh[GPUD_POLL_N_FIELDS] = {0};
+  int32_t rc[GPUD_POLL_N_FIELDS];
+  rc[GPUD_POLL_TEMPERATURE_C] = (int32_t)N->temperature(p->h, 0 /* NVML_TEMPERATURE_GPU */, &v); fresh[GPUD_POLL_TEMPERATURE_C] = v;
+  rc[GPUD_POLL_POWER_MW] = (int32_t)N->power(p->h, &v); fresh[GPUD_POLL_POWER_MW] = v;
+  rc[GPUD_POLL_CLOCK_GRAPHICS_MHZ] = (int32_t)N->clock(p->h, 0 /* NVML_CLOCK_GRAPHICS */, &v); fresh[GPUD_POLL_CLOCK_GRAPHICS_MHZ] = v;
+  rc[GPUD_POLL_CLOCK_SM_MHZ] = (int32_t)N->clock(p->h, 1 /* NVML_CLOCK_SM */, &v); fresh[GPUD_POLL_CLOCK_SM_MHZ] = v;
+  rc[GPUD_POLL_CLOCK_MEM_MHZ] = (int32_t)N->clock(p->h, 2 /* NVML_CLOCK_MEM */, &v); fresh[GPUD_POLL_CLOCK_MEM_MHZ] = v;
+  nvmlUtilization_t u{};
+  rc[GPUD_POLL_UTIL_GPU_PCT] = rc[GPUD_POLL_UTIL_MEM_PCT] = (int32_t)N->util(p->h, &u);
+  fresh[GPUD_POLL_UTIL_GPU_PCT] = u.gpu; fresh[GPUD_POLL_UTIL_MEM_PCT] = u.memory;
+  nvmlMemory_t m{};
+  rc[GPUD_POLL_MEMORY_USED_MIB] = (int32_t)N->memory(p->h, &m); fresh[GPUD_POLL_MEMORY_USED_MIB] = (uint32_t)(m.used >> 20);
+  uint32_t mask = 0;
+  gpud_poll_row_hold(fresh, rc, GPUD_POLL_N_FIELDS, p->held, r, &mask);
+  if (mask) {
+    p->fail_mask |= mask;
+    for (int c = 0; c < GPUD_POLL_N_FIELDS; ++c) if (mask & (1u << c)) { p->last_rc[c] = rc[c]; ++p->n_failed[c]; }
+  }
+}
+
+extern "C" int32_t gpud_poller_errors(gpud_poller* p, uint32_t* fail_mask, int32_t* last_nvml_rc, uint64_t* n_failed) {
+  if (!p) return GPUD_E_INVALID;
+  if (fail_mask) *fail_mask = p->fail_mask;
+  for (int c = 0; c < GPUD_POLL_N_FIELDS; ++c) {
+    if (last_nvml_rc) last_nvml_rc[c] = p->last_rc[c];
+    if (n_failed) n_failed[c] = p->n_failed[c];
+  }
+  return GPUD_OK;
 }
 
 extern "C" int32_t gpud_poller_poll(gpud_poller* p, int64_t n_polls, int64_t interval_us) {
@@ -145,7 +183,7 @@ extern "C" int32_t gpud_poller_poll(gpud_poller* p, int64_t n_polls, int64_t int
   while (done < n_polls) {
     const int64_t batch = std::min<int64_t>(p->cap_rows, n_polls - done);
     for (int64_t i = 0; i < batch; ++i) {
-      poll_row(N, p->h, p->rows + i * GPUD_POLL_N_FIELDS);
+      poll_row(N, p, p->rows + i * GPUD_POLL_N_FIELDS);
       if (interval_us) { timespec ts{(time_t)(interval_us / 1000000), (long)(interval_us % 1000000) * 1000L}; nanosleep(&ts, nullptr); }
     }
     p->n_rows = batch;

@@ -51,6 +51,13 @@ struct WinParams {
   int n_list;          // > 0: process only windows w_list[0..n_list) of every field (generic instantiation)
   int w_list[2];
   int w_skip[2];       // windows the specialised launch leaves to the generic one (-1 = none)
+  // RANGE instantiations only (whole-range order statistic, select.cu): the pass classifies every sample against the field's
+  // pivot pair lo <= hi and parks the keys strictly between them in the field's list
+  const double* piv;           // [F][2]: lo, hi
+  uint4* w_cls;                // [F][nw]: per window {keys above hi, keys == hi, keys == lo, keys strictly inside}
+  unsigned long long* lists;   // [F][list_cap] totalOrder keys strictly inside (lo, hi), any order
+  unsigned* fill;              // [F] list fill counters (may run past list_cap: overflow is detected by the reader)
+  unsigned list_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -95,6 +102,11 @@ struct K64 { unsigned hi, lo; };
 // acc += (a > b) for IEEE doubles: DSETP and one predicated integer add
 __device__ __forceinline__ void count_gt_f64(unsigned& acc, double a, double b) {
   asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(acc) : "d"(a), "d"(b));   // DSETP + predicated add
+}
+// RANGE pass: above += (x > hi); otherwise, when x >= lo, set `bit` in mask.  NaN fails both compares (the caller guards +NaN).
+__device__ __forceinline__ void classify_f64(unsigned& above, unsigned& mask, double x, double lo, double hi, unsigned bit) {
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f64 p, %2, %4;\n\t@p add.u32 %0, %0, 1;\n\tsetp.ge.and.f64 q, %2, %3, !p;\n\t@q or.b32 %1, %1, %5;\n\t}"
+      : "+r"(above), "+r"(mask) : "d"(x), "d"(lo), "d"(hi), "r"(bit));
 }
 // acc -= (o > v) for unsigned words through the borrow flag (sub.cc / subc pair): two integer instructions, no predicate
 __device__ __forceinline__ void count_gt_u32_neg(unsigned& acc, unsigned o, unsigned v) {
@@ -283,7 +295,7 @@ __device__ __forceinline__ double2 ld_stream(const double2* p) {
 constexpr int kPrefetchPairs = GPUD_PREFETCH_PAIRS;      // register pairs of the NEXT window loaded under the current post-processing
 constexpr int kHotCtasPerSM = kPrefetchPairs < 16 ? 3 : 2;  // 8 pairs in flight fit 80 registers (3 CTAs/SM); all 16 need 128 (2 CTAs/SM)
 
-template <bool ALIGNED, int JF>
+template <bool ALIGNED, int JF, bool RANGE>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kHotCtasPerSM : 2) k_window_reduce(const WinParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -306,7 +318,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
 
   constexpr int PF = (ALIGNED && JF >= 0) ? kPrefetchPairs : 16;
   double2 v[16];                 // the window in flight: loaded for the NEXT unit while the current one is post-processed
-  double thr_next = 0.0;
+  double thr_next = 0.0, lo_next = 0.0, hi_next = 0.0;
   // fetch the next non-skipped unit of this warp (if any) and issue all of its loads.  Measured alternatives, both slower on
   // B200: choosing the next unit BEFORE pass 1 (its address/threshold registers live through pass 1: 0.79 ms vs 0.70 ms) and
   // issuing each pair's load inside pass 1 right after the pair is consumed (0.72 ms).
@@ -325,6 +337,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     if (q.p0 >= p.cap) q.p0 -= p.cap;
     const double* __restrict__ base = p.ring + (int64_t)q.f * p.cap;
     thr_next = __ldg(p.thr + q.f);
+    if (RANGE) { lo_next = __ldg(p.piv + 2 * q.f); hi_next = __ldg(p.piv + 2 * q.f + 1); }
     if (ALIGNED) {
       const double2* __restrict__ b2 = reinterpret_cast<const double2*>(base + q.p0) + lane;
 #pragma unroll
@@ -366,6 +379,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     const int J = (m + 63) >> 6;                     // register pairs that hold at least one valid element
     const int Jfull = JF >= 0 ? JF : (m >> 6);       // register pairs in which every lane's two elements are valid
     const double thr = thr_next;
+    const double piv_lo = lo_next, piv_hi = hi_next;
+    unsigned abv = 0, inmask = 0;                    // RANGE: keys above the upper pivot; row entries inside [lo, hi] (as doubles)
 
     // ---- pass 1: consume the loaded registers once ----
     double sum0 = 0.0, sum1 = 0.0, es0 = 0.0, es1 = 0.0;
@@ -385,6 +400,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         count_gt_f64(nov, x0, thr);
         count_gt_f64(nov, x1, thr);
+        if (RANGE) {
+          classify_f64(abv, inmask, x0, piv_lo, piv_hi, 1u << (2 * j));
+          classify_f64(abv, inmask, x1, piv_lo, piv_hi, 2u << (2 * j));
+        }
         a_smax = max(a_smax, max(h0, h1));
         b_umin = min(b_umin, min((unsigned)h0, (unsigned)h1));
         c_umax = max(c_umax, max((unsigned)h0, (unsigned)h1));
@@ -398,6 +417,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         es0 = fma(es0, p.q64, x0); es1 = fma(es1, p.q64, x1);
         if (q0 && x0 > thr) ++nov;
         if (q1 && x1 > thr) ++nov;
+        if (RANGE) {
+          if (q0) { if (x0 > piv_hi) ++abv; else if (x0 >= piv_lo) inmask |= 1u << (2 * j); }
+          if (q1) { if (x1 > piv_hi) ++abv; else if (x1 >= piv_lo) inmask |= 2u << (2 * j); }
+        }
         a_smax = max(a_smax, max((int)h0, (int)h1));                       // all-ones is -1: neutral unless every element is negative, and then unused
         b_umin = min(b_umin, min(h0, h1));
         c_umax = max(c_umax, max(q0 ? h0 : 0u, q1 ? h1 : 0u));
@@ -453,70 +476,140 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       wmin.lo = __reduce_min_sync(kFull, nl);
     }
 
-    // ---- exact order statistic: k-th largest, k = m - ceil(m q) + 1; the maximum falls out of the same candidate set ----
-    int k = p.k_full;
-    if (JF < 0 && m != p.W) {
-      long long r = ((long long)m * p.q_num + p.q_den - 1) / p.q_den;
-      r = r < 1 ? 1 : (r > m ? m : r);
-      k = m - (int)r + 1;
-    }
     K64 ans, wmax;
     ans.hi = ans.lo = 0u;
-    bool done = false;
-    if (k <= 32) {
-      // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L', so the answer is too.
-      // Only rows whose maximum reaches L' can hold keys above it.
-      const unsigned Lh = warp_kth_largest_smem(mh, k, s32, lane);
-      // at least k lane maxima reach Lh, so at least k keys pass: the k-th largest of the gathered set is the answer
-      // Several lanes sharing the bounding high word means ties around the order statistic (integer readings, flat or slowly
-      // moving gauges): materialising such a class costs one shared atomic per member (a flat gauge ran 4x slower than white
-      // noise).  Those windows skip to the 64-bit-bound path below, where a class of equal keys collapses to its value.
-      if (__popc(__ballot_sync(kFull, mh == Lh)) == 1) {
-        const int cnt = gather_rows<true>(wbase, __ballot_sync(kFull, mh >= Lh), Lh, 0u, lane, lt_mask);
-        if (cnt <= 32) {
-          ans = select_from_candidates(cand, cnt, k, lane, &wmax);
-          done = true;
-        }
+    uint4 cls = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (!RANGE) {
+      // ---- exact order statistic: k-th largest, k = m - ceil(m q) + 1; the maximum falls out of the same candidate set ----
+      int k = p.k_full;
+      if (JF < 0 && m != p.W) {
+        long long r = ((long long)m * p.q_num + p.q_den - 1) / p.q_den;
+        r = r < 1 ? 1 : (r > m ? m : r);
+        k = m - (int)r + 1;
       }
-      __syncwarp();
-    }
-    if (!done) {
-      // exact lane maximum: low words among this lane's own row entries that carry its top high word
-      unsigned ml = 0u;
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const unsigned long long kv = sk[lane * kRowU64 + i];
-        if ((unsigned)(kv >> 32) == rmh) ml = max(ml, true_lo(mh, (unsigned)kv));
-      }
-      wmax = warp_max_k64(mh, ml);
-      bool solved = false;
+      bool done = false;
       if (k <= 32) {
-        // medium path: exact 64-bit bound L = k-th largest lane maximum; ties collapse here (constant gauges)
-        unsigned sh = mh, sl = ml;
-        warp_sort_desc_k64(sh, sl, lane);
-        const unsigned Lh = __shfl_sync(kFull, sh, k - 1), Ll = __shfl_sync(kFull, sl, k - 1);
-        const int cnt = gather_rows<false>(wbase, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, lane, lt_mask);
-        if (cnt < k) { ans.hi = Lh; ans.lo = Ll; solved = true; }
-        else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); solved = true; }
+        // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L', so the answer is too.
+        // Only rows whose maximum reaches L' can hold keys above it.
+        const unsigned Lh = warp_kth_largest_smem(mh, k, s32, lane);
+        // at least k lane maxima reach Lh, so at least k keys pass: the k-th largest of the gathered set is the answer
+        // Several lanes sharing the bounding high word means ties around the order statistic (integer readings, flat or slowly
+        // moving gauges): materialising such a class costs one shared atomic per member (a flat gauge ran 4x slower than white
+        // noise).  Those windows skip to the 64-bit-bound path below, where a class of equal keys collapses to its value.
+        if (__popc(__ballot_sync(kFull, mh == Lh)) == 1) {
+          const int cnt = gather_rows<true>(wbase, __ballot_sync(kFull, mh >= Lh), Lh, 0u, lane, lt_mask);
+          if (cnt <= 32) {
+            ans = select_from_candidates(cand, cnt, k, lane, &wmax);
+            done = true;
+          }
+        }
         __syncwarp();
       }
-      if (!solved) {
-        // always-correct slow path: MSB-first bit search over the keys of this lane's row
-        unsigned long long pref = 0ull;
-        int kk2 = k;
-#pragma unroll 1
-        for (int b = 63; b >= 0; --b) {
-          const unsigned long long trial = pref | (1ull << b);
-          const unsigned long long himask = ~((1ull << b) - 1ull);
-          unsigned c = 0;
-#pragma unroll 4
-          for (int i = 0; i < 32; ++i) c += ((true_key(sk[lane * kRowU64 + i]) & himask) == trial) ? 1u : 0u;
-          c = __reduce_add_sync(kFull, c);
-          if ((int)c >= kk2) pref = trial; else kk2 -= (int)c;
+      if (!done) {
+        // exact lane maximum: low words among this lane's own row entries that carry its top high word
+        unsigned ml = 0u;
+  #pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const unsigned long long kv = sk[lane * kRowU64 + i];
+          if ((unsigned)(kv >> 32) == rmh) ml = max(ml, true_lo(mh, (unsigned)kv));
         }
-        ans.hi = (unsigned)(pref >> 32);
-        ans.lo = (unsigned)pref;
+        wmax = warp_max_k64(mh, ml);
+        bool solved = false;
+        if (k <= 32) {
+          // medium path: exact 64-bit bound L = k-th largest lane maximum; ties collapse here (constant gauges)
+          unsigned sh = mh, sl = ml;
+          warp_sort_desc_k64(sh, sl, lane);
+          const unsigned Lh = __shfl_sync(kFull, sh, k - 1), Ll = __shfl_sync(kFull, sl, k - 1);
+          const int cnt = gather_rows<false>(wbase, __ballot_sync(kFull, k_gt(mh, ml, Lh, Ll)), Lh, Ll, lane, lt_mask);
+          if (cnt < k) { ans.hi = Lh; ans.lo = Ll; solved = true; }
+          else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); solved = true; }
+          __syncwarp();
+        }
+        if (!solved) {
+          // always-correct slow path: MSB-first bit search over the keys of this lane's row
+          unsigned long long pref = 0ull;
+          int kk2 = k;
+  #pragma unroll 1
+          for (int b = 63; b >= 0; --b) {
+            const unsigned long long trial = pref | (1ull << b);
+            const unsigned long long himask = ~((1ull << b) - 1ull);
+            unsigned c = 0;
+  #pragma unroll 4
+            for (int i = 0; i < 32; ++i) c += ((true_key(sk[lane * kRowU64 + i]) & himask) == trial) ? 1u : 0u;
+            c = __reduce_add_sync(kFull, c);
+            if ((int)c >= kk2) pref = trial; else kk2 -= (int)c;
+          }
+          ans.hi = (unsigned)(pref >> 32);
+          ans.lo = (unsigned)pref;
+        }
       }
+    } else {
+      // ---- whole-range pass: no per-window order statistic.  Exact maximum the way the minimum is found, then the samples
+      // flagged in pass 1 (lo <= x <= hi as doubles) are classified exactly on their totalOrder keys: above hi (+0 over a -0
+      // pivot), == hi, == lo, below lo (-0 under a +0 pivot), and the rest - strictly inside - goes to the field's list.
+      wmax.hi = __reduce_max_sync(kFull, mh);
+      {
+        unsigned rows = __ballot_sync(kFull, mh == wmax.hi);
+        unsigned ml = 0u;
+        const unsigned raw_max_hi = raw_hi_of(wmax.hi);
+        if (__popc(rows) > 6) {
+          rows = 0u;
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const unsigned long long kv = sk[lane * kRowU64 + i];
+            if ((unsigned)(kv >> 32) == raw_max_hi && elem_index(lane, i) < m) ml = max(ml, true_lo(wmax.hi, (unsigned)kv));
+          }
+        }
+        while (rows) {
+          const int row = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const unsigned long long kv = sk[row * kRowU64 + lane];
+          if ((unsigned)(kv >> 32) == raw_max_hi && elem_index(row, lane) < m) ml = max(ml, true_lo(wmax.hi, (unsigned)kv));
+        }
+        wmax.lo = __reduce_max_sync(kFull, ml);
+      }
+      unsigned n_eh = 0, n_el = 0, n_in = 0;
+      if (__any_sync(kFull, inmask != 0u)) {
+        const unsigned long long lok = gpud_f64_key((unsigned long long)__double_as_longlong(piv_lo));
+        const unsigned long long hik = gpud_f64_key((unsigned long long)__double_as_longlong(piv_hi));
+        unsigned mm = inmask;
+        while (mm) {
+          const int i = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const unsigned long long key = true_key(sk[lane * kRowU64 + i]);
+          const bool inside = key > lok && key < hik;
+          abv += key > hik ? 1u : 0u;
+          n_eh += key == hik ? 1u : 0u;
+          n_el += (key == lok && lok != hik) ? 1u : 0u;
+          if (!inside) inmask ^= 1u << i;
+        }
+        const int c = __popc(inmask);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += t;
+        }
+        n_in = (unsigned)__shfl_sync(kFull, incl, 31);
+        if (n_in) {
+          unsigned base = 0;
+          if (lane == 0) base = atomicAdd(p.fill + f, n_in);
+          base = __shfl_sync(kFull, base, 0);
+          unsigned pos = base + (unsigned)(incl - c);
+          unsigned long long* __restrict__ list = p.lists + (int64_t)f * p.list_cap;
+          mm = inmask;
+          while (mm) {
+            const int i = __ffs(mm) - 1;
+            mm &= mm - 1;
+            if (pos < p.list_cap) list[pos] = true_key(sk[lane * kRowU64 + i]);
+            ++pos;
+          }
+        }
+      }
+      cls.x = __reduce_add_sync(kFull, abv);
+      cls.y = __reduce_add_sync(kFull, n_eh);
+      cls.z = __reduce_add_sync(kFull, n_el);
+      cls.w = n_in;
     }
     __syncwarp();                            // every lane is done with this window's rows before pass 1 of the next overwrites them
 
@@ -525,7 +618,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       p.out_min[o] = k64_to_f64(wmin);
       p.out_max[o] = k64_to_f64(wmax);
       p.out_mean[o] = (JF >= 0 || m == p.W) ? sum * p.inv_w : sum / (double)m;
-      if (p.do_select) p.out_p99[o] = k64_to_f64(ans);
+      if (!RANGE && p.do_select) p.out_p99[o] = k64_to_f64(ans);
+      if (RANGE) p.w_cls[o] = cls;
       p.out_nover[o] = nov;
       p.part[o] = ep;
     }
@@ -609,10 +703,18 @@ struct gpud_ring {
   int64_t stage_rows = 0;
   int sm_count = 148;
   double* d_rng[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // range-reduce scratch: per-window min,max,mean,ema,partials
+  size_t rng_bytes[5] = {0, 0, 0, 0, 0};
   uint32_t* d_rng_nover = nullptr;
-  size_t range_cap = 0;
-  double* d_rng_stat = nullptr;                        // per-window order statistic of the ranked range pass (experimental select, select.cu)
-  size_t range_stat_cap = 0;
+  size_t rng_nover_bytes = 0;
+  uint4* d_rng_cls = nullptr;                          // sampled range pass: per-window class counts
+  size_t rng_cls_bytes = 0;
+  unsigned long long* d_rng_lists = nullptr;           // sampled range pass: per-field lists of the keys between the pivots
+  size_t rng_lists_bytes = 0;
+  double* d_rng_piv = nullptr;                         // [F][2] pivots, then [F] u32 list fill counters
+  size_t rng_piv_bytes = 0;
+  cudaEvent_t ev_rng[3] = {nullptr, nullptr, nullptr}; // start / after the range pass / end of the last sampled reduce_range
+  bool range_timed = false;
+  int range_fields_open = 0;                           // fields the last sampled reduce_range handed to the histogram path
   cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};   // around the two kernels of the last reduce (bench roofline)
 };
 
@@ -678,7 +780,8 @@ extern "C" int32_t gpud_ring_destroy(gpud_ring* r) {
   for (auto& p : r->d_res) cudaFree(p);
   for (auto& p : r->d_rng) cudaFree(p);
   cudaFree(r->d_rng_nover);
-  cudaFree(r->d_rng_stat);
+  cudaFree(r->d_rng_cls); cudaFree(r->d_rng_lists); cudaFree(r->d_rng_piv);
+  for (auto& ev : r->ev_rng) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) {
     if (r->h_stage[i]) cudaFreeHost(r->h_stage[i]);
     cudaFree(r->d_stage[i]);
@@ -803,17 +906,18 @@ extern "C" int32_t gpud_ring_counts(gpud_ring* r, int64_t* total, int64_t* count
 // Launch the window kernel(s).  The bulk goes to the aligned 128-bit instantiation (specialised for the window shape when
 // W >> 6 is 15 or 16, i.e. W in 960..1024); the window that wraps the physical end of the ring and a trailing partial
 // window go to the generic run-time instantiation, which also serves rings whose start is odd.
-template <bool ALIGNED, int JF>
+template <bool ALIGNED, int JF, bool RANGE>
 static cudaError_t launch_one(gpud_ring* r, const WinParams& p, int64_t units) {
   // persistent grid: 2 CTAs of 8 warps per SM, a whole number of waves (148 SMs)
   // 72 KB of dynamic shared memory per CTA (8 warps x (32 x 272 B key rows + candidate list)): opt in above 48 KB
-  cudaError_t e = cudaFuncSetAttribute(k_window_reduce<ALIGNED, JF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(k_window_reduce<ALIGNED, JF, RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmemBytes);
   if (e != cudaSuccess) return e;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * ((ALIGNED && JF >= 0) ? kHotCtasPerSM : 2)));
-  k_window_reduce<ALIGNED, JF><<<grid, kWarpsPerBlock * 32, kBlockSmemBytes, r->stream>>>(p);
+  k_window_reduce<ALIGNED, JF, RANGE><<<grid, kWarpsPerBlock * 32, kBlockSmemBytes, r->stream>>>(p);
   return cudaGetLastError();
 }
 
+template <bool RANGE>
 static int32_t launch_windows(gpud_ring* r, WinParams p) {
   {
     long long rr = ((long long)p.W * p.q_num + p.q_den - 1) / p.q_den;
@@ -826,7 +930,7 @@ static int32_t launch_windows(gpud_ring* r, WinParams p) {
   p.w_skip[0] = p.w_skip[1] = -1;
   const int64_t units = (int64_t)p.F * p.nw;
   if ((p.start & 1) || ((p.W & 1) && p.nw > 1)) {          // some window would start on an odd element: 64-bit loads everywhere
-    GPUD_CUDA(r->ctx, (launch_one<false, -1>(r, p, units)));
+    GPUD_CUDA(r->ctx, (launch_one<false, -1, RANGE>(r, p, units)));
     return GPUD_OK;
   }
   int n_skip = 0;
@@ -836,16 +940,16 @@ static int32_t launch_windows(gpud_ring* r, WinParams p) {
   const bool special = (jf == 15 || jf == 16) && p.nw > 1;
   if (special && (p.count % p.W) != 0 && (n_skip == 0 || p.w_skip[0] != p.nw - 1)) p.w_skip[n_skip++] = p.nw - 1;   // trailing partial window
   cudaError_t e;
-  if (special && jf == 15) e = launch_one<true, 15>(r, p, units);
-  else if (special && jf == 16) e = launch_one<true, 16>(r, p, units);
-  else e = launch_one<true, -1>(r, p, units);
+  if (special && jf == 15 && !RANGE) e = launch_one<true, 15, false>(r, p, units);   // the range pass always runs W' = 1024 (jf = 16)
+  else if (special && jf == 16) e = launch_one<true, 16, RANGE>(r, p, units);
+  else e = launch_one<true, -1, RANGE>(r, p, units);
   GPUD_CUDA(r->ctx, e);
   if (n_skip > 0) {
     p.n_list = n_skip;
     p.w_list[0] = p.w_skip[0];
     p.w_list[1] = p.w_skip[1];
     p.w_skip[0] = p.w_skip[1] = -1;
-    GPUD_CUDA(r->ctx, (launch_one<false, -1>(r, p, (int64_t)p.F * n_skip)));
+    GPUD_CUDA(r->ctx, (launch_one<false, -1, RANGE>(r, p, (int64_t)p.F * n_skip)));
   }
   return GPUD_OK;
 }
@@ -863,7 +967,7 @@ extern "C" int32_t gpud_ring_reduce(gpud_ring* r) {
   p.out_min = r->d_res[GPUD_OP_MIN]; p.out_max = r->d_res[GPUD_OP_MAX]; p.out_mean = r->d_res[GPUD_OP_MEAN];
   p.out_p99 = r->d_res[GPUD_OP_P99]; p.out_nover = r->d_nover; p.part = r->d_part; p.do_select = 1;
   cudaEventRecord(r->ev_k[0], r->stream);
-  { int32_t rc = launch_windows(r, p); if (rc) return rc; }
+  { int32_t rc = launch_windows<false>(r, p); if (rc) return rc; }
   cudaEventRecord(r->ev_k[1], r->stream);
   const int m_last = (int)(count - (int64_t)(p.nw - 1) * r->W);
   k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_part, r->d_ring, r->cap, p.start, r->F, p.nw,
@@ -912,80 +1016,81 @@ extern "C" int32_t gpud_ring_read(gpud_ring* r, int32_t op, void* out, int64_t o
   return GPUD_OK;
 }
 
-// ---- range reduce support (select.cu): run the window kernel with W' = 1024 over the last `n` samples into scratch ----
-int32_t gpud_ring_range_partials(gpud_ring* r, int64_t n, gpud_range_view* v) {
+// ---- range reduce support (select.cu): the window kernel with W' = 1024 over the newest `n` samples, into scratch ----
+// gpud_ring_range_prepare sizes the scratch and fills the view; gpud_ring_range_pass launches the pass (+ the EMA carry) in the
+// mode the view names: plain (per-window min / max / mean / EMA partial / n_over) or sampled (the same, plus every sample
+// classified against the field's pivot pair and the keys between the pivots parked in the field's list).
+static cudaError_t grow(void** ptr, size_t* have, size_t need) {
+  if (need <= *have) return cudaSuccess;
+  cudaFree(*ptr);
+  *ptr = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc(ptr, need);
+  if (e == cudaSuccess) *have = need;
+  return e;
+}
+
+int32_t gpud_ring_range_prepare(gpud_ring* r, int64_t n, gpud_range_view* v) {
   const int64_t count = ring_count(r);
   if (n <= 0 || n > count) n = count;
   const int Wp = (int)std::min<int64_t>(kMaxWindow, n);
   const int nw = (int)((n + Wp - 1) / Wp);
   const size_t per = (size_t)r->F * nw;
-  if (per > r->range_cap) {
-    for (auto& q : r->d_rng) { cudaFree(q); q = nullptr; }
-    cudaFree(r->d_rng_nover); r->d_rng_nover = nullptr;
-    r->range_cap = 0;
-    for (auto& q : r->d_rng) GPUD_CUDA(r->ctx, cudaMalloc(&q, per * sizeof(double)));
-    GPUD_CUDA(r->ctx, cudaMalloc(&r->d_rng_nover, per * sizeof(uint32_t)));
-    r->range_cap = per;
+  GPUD_CUDA(r->ctx, cudaSetDevice(r->dev));
+  for (int i = 0; i < 5; ++i) GPUD_CUDA(r->ctx, grow((void**)&r->d_rng[i], &r->rng_bytes[i], per * sizeof(double)));
+  GPUD_CUDA(r->ctx, grow((void**)&r->d_rng_nover, &r->rng_nover_bytes, per * sizeof(uint32_t)));
+  const bool sampled = n >= GPUD_RANGE_SAMPLED_MIN;
+  const unsigned list_cap = (unsigned)std::min<int64_t>(GPUD_RANGE_LIST_CAP, n);
+  if (sampled) {
+    GPUD_CUDA(r->ctx, grow((void**)&r->d_rng_cls, &r->rng_cls_bytes, per * sizeof(uint4)));
+    GPUD_CUDA(r->ctx, grow((void**)&r->d_rng_lists, &r->rng_lists_bytes, (size_t)r->F * list_cap * sizeof(unsigned long long)));
+    GPUD_CUDA(r->ctx, grow((void**)&r->d_rng_piv, &r->rng_piv_bytes, (size_t)r->F * (2 * sizeof(double) + sizeof(unsigned))));
   }
+  for (auto& ev : r->ev_rng) if (!ev) GPUD_CUDA(r->ctx, cudaEventCreate(&ev));
   int64_t start = ring_start(r) + (count - n);
   if (start >= r->cap) start -= r->cap;
-  WinParams p;
-  p.ring = r->d_ring; p.cap = r->cap; p.start = start; p.count = n; p.W = Wp; p.F = r->F; p.nw = nw;
-  p.q_num = r->q_num; p.q_den = r->q_den; p.thr = r->d_thr; p.pw = r->d_pw; p.q64 = pow(1.0 - r->alpha, 64.0); p.alpha = r->alpha;
-  p.out_min = r->d_rng[0]; p.out_max = r->d_rng[1]; p.out_mean = r->d_rng[2]; p.out_p99 = r->d_rng[3]; p.out_nover = r->d_rng_nover;
-  p.part = r->d_rng[4]; p.do_select = 0;
-  { int32_t rc = launch_windows(r, p); if (rc) return rc; }
-  const int m_last = (int)(n - (int64_t)(nw - 1) * Wp);
-  k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_rng[4], r->d_ring, r->cap, start, r->F, nw, pow(1.0 - r->alpha, (double)Wp),
-                                                        pow(1.0 - r->alpha, (double)m_last), r->d_rng[3]);
-  GPUD_CUDA(r->ctx, cudaGetLastError());
   v->ring = r->d_ring; v->F = r->F; v->cap = r->cap; v->start = start; v->n = n; v->Wp = Wp; v->nw = nw;
   v->w_min = r->d_rng[0]; v->w_max = r->d_rng[1]; v->w_mean = r->d_rng[2]; v->w_ema = r->d_rng[3]; v->w_nover = r->d_rng_nover;
   v->q_num = r->q_num; v->q_den = r->q_den; v->stream = r->stream; v->ctx = r->ctx; v->dev = r->dev; v->sm_count = r->sm_count;
+  v->sampled = sampled ? 1 : 0;
+  v->list_cap = list_cap;
+  v->piv = sampled ? r->d_rng_piv : nullptr;
+  v->fill = sampled ? reinterpret_cast<unsigned*>(r->d_rng_piv + 2 * (size_t)r->F) : nullptr;
+  v->w_cls = sampled ? r->d_rng_cls : nullptr;
+  v->lists = sampled ? r->d_rng_lists : nullptr;
+  for (int i = 0; i < 3; ++i) v->ev[i] = r->ev_rng[i];
+  r->range_timed = false;
   return GPUD_OK;
 }
 
-// The same pass with the per-window order statistic switched on at a caller-chosen rank: every full window also reports its
-// `rank_from_top`-th largest key (nearest-rank fraction (W' - rank + 1) / W' gives exactly that rank for a full window).  Used by the
-// experimental bounded select of select.cu; the pass above is left as it is.
-int32_t gpud_ring_range_partials_ranked(gpud_ring* r, int64_t n, int rank_from_top, gpud_range_view* v, const double** w_stat) {
-  const int64_t count = ring_count(r);
-  if (n <= 0 || n > count) n = count;
-  const int Wp = (int)std::min<int64_t>(kMaxWindow, n);
-  const int nw = (int)((n + Wp - 1) / Wp);
-  if (rank_from_top < 1 || rank_from_top > Wp || !w_stat) return GPUD_E_INVALID;
-  const size_t per = (size_t)r->F * nw;
-  if (per > r->range_cap) {
-    for (auto& q : r->d_rng) { cudaFree(q); q = nullptr; }
-    cudaFree(r->d_rng_nover); r->d_rng_nover = nullptr;
-    r->range_cap = 0;
-    for (auto& q : r->d_rng) GPUD_CUDA(r->ctx, cudaMalloc(&q, per * sizeof(double)));
-    GPUD_CUDA(r->ctx, cudaMalloc(&r->d_rng_nover, per * sizeof(uint32_t)));
-    r->range_cap = per;
-  }
-  if (per > r->range_stat_cap) {
-    cudaFree(r->d_rng_stat); r->d_rng_stat = nullptr;
-    r->range_stat_cap = 0;
-    GPUD_CUDA(r->ctx, cudaMalloc(&r->d_rng_stat, per * sizeof(double)));
-    r->range_stat_cap = per;
-  }
-  int64_t start = ring_start(r) + (count - n);
-  if (start >= r->cap) start -= r->cap;
+int32_t gpud_ring_range_pass(gpud_ring* r, const gpud_range_view* v) {
   WinParams p;
-  p.ring = r->d_ring; p.cap = r->cap; p.start = start; p.count = n; p.W = Wp; p.F = r->F; p.nw = nw;
-  p.q_num = Wp - rank_from_top + 1; p.q_den = Wp;
-  p.thr = r->d_thr; p.pw = r->d_pw; p.q64 = pow(1.0 - r->alpha, 64.0); p.alpha = r->alpha;
-  p.out_min = r->d_rng[0]; p.out_max = r->d_rng[1]; p.out_mean = r->d_rng[2]; p.out_p99 = r->d_rng_stat; p.out_nover = r->d_rng_nover;
-  p.part = r->d_rng[4]; p.do_select = 1;
-  { int32_t rc = launch_windows(r, p); if (rc) return rc; }
-  const int m_last = (int)(n - (int64_t)(nw - 1) * Wp);
-  k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_rng[4], r->d_ring, r->cap, start, r->F, nw, pow(1.0 - r->alpha, (double)Wp),
+  p.ring = r->d_ring; p.cap = r->cap; p.start = v->start; p.count = v->n; p.W = v->Wp; p.F = r->F; p.nw = v->nw;
+  p.q_num = r->q_num; p.q_den = r->q_den; p.thr = r->d_thr; p.pw = r->d_pw; p.q64 = pow(1.0 - r->alpha, 64.0); p.alpha = r->alpha;
+  p.out_min = r->d_rng[0]; p.out_max = r->d_rng[1]; p.out_mean = r->d_rng[2]; p.out_p99 = nullptr; p.out_nover = r->d_rng_nover;
+  p.part = r->d_rng[4]; p.do_select = 0;
+  p.piv = v->piv; p.w_cls = v->w_cls; p.lists = v->lists; p.fill = v->fill; p.list_cap = v->list_cap;
+  { int32_t rc = v->sampled ? launch_windows<true>(r, p) : launch_windows<false>(r, p); if (rc) return rc; }
+  const int m_last = (int)(v->n - (int64_t)(v->nw - 1) * v->Wp);
+  k_ema_carry<<<r->F, 128, 0, r->stream>>>(r->d_rng[4], r->d_ring, r->cap, v->start, r->F, v->nw, pow(1.0 - r->alpha, (double)v->Wp),
                                                         pow(1.0 - r->alpha, (double)m_last), r->d_rng[3]);
   GPUD_CUDA(r->ctx, cudaGetLastError());
-  v->ring = r->d_ring; v->F = r->F; v->cap = r->cap; v->start = start; v->n = n; v->Wp = Wp; v->nw = nw;
-  v->w_min = r->d_rng[0]; v->w_max = r->d_rng[1]; v->w_mean = r->d_rng[2]; v->w_ema = r->d_rng[3]; v->w_nover = r->d_rng_nover;
-  v->q_num = r->q_num; v->q_den = r->q_den; v->stream = r->stream; v->ctx = r->ctx; v->dev = r->dev; v->sm_count = r->sm_count;
-  *w_stat = r->d_rng_stat;
+  return GPUD_OK;
+}
+
+void gpud_ring_range_note(gpud_ring* r, bool sampled, unsigned fields_open) {
+  r->range_timed = sampled;
+  r->range_fields_open = (int)fields_open;
+}
+
+extern "C" int32_t gpud_ring_range_stats(gpud_ring* r, float* pass_ms, float* total_ms, int32_t* fields_by_histogram) {
+  if (!r || !pass_ms || !total_ms || !fields_by_histogram) return GPUD_E_INVALID;
+  if (!r->range_timed) return gpud_fail(r->ctx, GPUD_E_STATE, "the last reduce_range (if any) did not take the sampled single pass");
+  GPUD_CUDA(r->ctx, cudaSetDevice(r->dev));
+  GPUD_CUDA(r->ctx, cudaEventSynchronize(r->ev_rng[2]));
+  GPUD_CUDA(r->ctx, cudaEventElapsedTime(pass_ms, r->ev_rng[0], r->ev_rng[1]));
+  GPUD_CUDA(r->ctx, cudaEventElapsedTime(total_ms, r->ev_rng[0], r->ev_rng[2]));
+  *fields_by_histogram = r->range_fields_open;
   return GPUD_OK;
 }
 

@@ -1,8 +1,10 @@
 // select.cu — whole-range aggregates of the newest n samples of every field (gpud_ring_reduce_range).
 //
 // min / max / mean / EMA / n_over are folded from the per-window pass of ring.cu (W' = 1024 windows over the range).
-// The exact order statistic is an MSB-first radix select on the IEEE totalOrder keys that spends HBM passes only where
-// they narrow the candidate set:
+// Long ranges (>= 64 Ki samples, i.e. the whole-ring W = CAP order statistic of BASELINE configs[3]) take ONE HBM read: pivots
+// from a 0.8 % sample, classification fused into the window pass, the answer from class counts + a short list (see below).
+// Short ranges, and any field the sampled pass cannot settle, use an MSB-first radix select on the IEEE totalOrder keys that
+// spends HBM passes only where they narrow the candidate set:
 //   1. the bits on which the field's min and max keys agree are skipped (they are common to every key);
 //   2. one 11-bit histogram pass over the first varying digit usually leaves <= kCollectMax keys in the bin that holds the
 //      rank; further histogram passes run only for fields that still have more (heavy ties);
@@ -66,46 +68,208 @@ __device__ __forceinline__ void for_each_key(const double* __restrict__ base, in
   }
 }
 
-// fold the per-window partials into per-field results; initialise the select state
-__global__ void k_range_fold(int F, int nw, int Wp, int64_t n, const double* __restrict__ w_min, const double* __restrict__ w_max,
-                             const double* __restrict__ w_mean, const double* __restrict__ w_ema, const uint32_t* __restrict__ w_nover,
-                             int q_num, int q_den, double* __restrict__ out /*[5][F]*/, uint32_t* __restrict__ out_nover, SelState* __restrict__ st) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-  unsigned long long kmin = ~0ull, kmax = 0ull;
+// ---- sampled-pivot single pass (ranges of >= GPUD_RANGE_SAMPLED_MIN samples) -----------------------------------------------------
+// One block per field reads a systematic sample of S keys (one 32-byte sector each, the stride apart), and picks two sample order
+// statistics around the wanted rank as the field's pivot pair lo <= hi: for the rank k from the top among n keys the sample rank is
+// about k S / n with a standard deviation of sqrt(S p (1 - p)); five of those to either side (failure odds < 1e-6 per field for
+// independent samples; an autocorrelated gauge is sampled evenly over the range, which is at least as good).  The window pass
+// then counts the keys above hi / equal to hi / equal to lo and parks the keys strictly between the pivots in the field's list
+// (about 10 S p-deviations x n / S keys: 12 Ki of 1 Mi for p99); k_range_finish reads the answer off the counts or selects it
+// from the list.  Any field for which that fails (rank outside the pivots, list overflow, +NaN in the data, NaN pivots) is
+// answered by the histogram path below - results never depend on the sample.
+constexpr int kSampleMax = 8192;
+
+// k-th largest (1-based) of keys[0..cnt) in shared memory; 256 threads, eight 8-bit digits.  All threads return the key.
+__device__ unsigned long long block_select_smem(const unsigned long long* keys, int cnt, int kk, unsigned* hist /*[256]*/, unsigned long long* bc /*[2]*/) {
+  const int t = threadIdx.x, lane = t & 31;
+  unsigned long long prefix = 0ull;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    hist[t] = 0;
+    __syncthreads();
+    for (int i = t; i < cnt; i += 256) {
+      const unsigned long long key = keys[i];
+      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (t < 32) {                                    // lane l owns bins 255-8l .. 248-8l (descending)
+      unsigned loc = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) loc += hist[255 - 8 * lane - j];
+      unsigned incl = loc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      const unsigned before = incl - loc;            // keys in the bins above this lane's
+      const bool mine = before < (unsigned)kk && (unsigned)kk <= incl;
+      if (mine) {
+        unsigned acc = before;
+        int bin = 255 - 8 * lane;
+        while (acc + hist[bin] < (unsigned)kk) { acc += hist[bin]; --bin; }
+        bc[0] = (prefix << 8) | (unsigned long long)bin;
+        bc[1] = (unsigned long long)((unsigned)kk - acc);
+      }
+    }
+    __syncthreads();
+    prefix = bc[0];
+    kk = (int)bc[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, int S, int64_t stride,
+                                                       int64_t k_from_top, double* __restrict__ piv, unsigned* __restrict__ fill) {
+  extern __shared__ __align__(16) unsigned long long s_keys[];
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned long long s_bc[2];
+  const int f = blockIdx.x, t = threadIdx.x;
+  const double* __restrict__ base = ring + (int64_t)f * cap;
+  for (int j = t; j < S; j += 256) {
+    int64_t a = start + (int64_t)j * stride + (stride >> 1);
+    if (a >= cap) a -= cap;
+    s_keys[j] = gpud_f64_key((unsigned long long)__double_as_longlong(__ldg(base + a)));
+  }
+  __syncthreads();
+  const double pr = (double)k_from_top / (double)n;
+  const double r0 = pr * (double)S, d = 5.0 * sqrt((double)S * pr * (1.0 - pr)) + 2.0;
+  const long long rh = (long long)floor(r0 - d), rl = (long long)ceil(r0 + d);
+  unsigned long long hik = gpud_f64_key(0x7ff0000000000000ull), lok = gpud_f64_key(0xfff0000000000000ull);   // +inf, -inf
+  if (rh >= 1) hik = block_select_smem(s_keys, S, (int)rh, s_hist, s_bc);
+  if (rl <= S) lok = block_select_smem(s_keys, S, (int)rl, s_hist, s_bc);
+  if (t == 0) {
+    piv[2 * f] = __longlong_as_double((long long)gpud_key_f64bits(lok));
+    piv[2 * f + 1] = __longlong_as_double((long long)gpud_key_f64bits(hik));
+    fill[f] = 0u;
+  }
+}
+
+// One block per field after the window pass: fold the per-window partials into the field's min / max / mean / EMA / n_over,
+// initialise the histogram path's state, and - sampled mode - settle the order statistic from the class counts and the list.
+// Fields left open (done == 0) are counted in *n_open.
+__global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int64_t n, const double* __restrict__ w_min, const double* __restrict__ w_max,
+                                                       const double* __restrict__ w_mean, const double* __restrict__ w_ema, const uint32_t* __restrict__ w_nover,
+                                                       int q_num, int q_den, int sampled, const double* __restrict__ piv, const unsigned* __restrict__ fill,
+                                                       const uint4* __restrict__ w_cls, const unsigned long long* __restrict__ lists, unsigned list_cap,
+                                                       double* __restrict__ out /*[5][F]*/, uint32_t* __restrict__ out_nover, SelState* __restrict__ st,
+                                                       unsigned* __restrict__ n_open) {
+  __shared__ unsigned long long s_red[8][6];
+  __shared__ double s_sum[8];
+  __shared__ unsigned s_hist[kBins];
+  __shared__ unsigned long long s_prefix, s_kk;
+  __shared__ int s_nbits, s_mode;
+  const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  unsigned long long kmin = ~0ull, kmax = 0ull, c_abv = 0, c_eh = 0, c_el = 0, nov = 0;
   double sum = 0.0;
-  unsigned nov = 0;
-  for (int w = 0; w < nw; ++w) {
+  for (int w = t; w < nw; w += 256) {
     const int64_t o = (int64_t)f * nw + w;
     const int m = (int)min((int64_t)Wp, n - (int64_t)w * Wp);
     kmin = min(kmin, gpud_f64_key((unsigned long long)__double_as_longlong(w_min[o])));
     kmax = max(kmax, gpud_f64_key((unsigned long long)__double_as_longlong(w_max[o])));
     sum += w_mean[o] * (double)m;
     nov += w_nover[o];
+    if (sampled) { const uint4 c = w_cls[o]; c_abv += c.x; c_eh += c.y; c_el += c.z; }
   }
-  out[0 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(kmin));
-  out[1 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(kmax));
-  out[2 * F + f] = sum / (double)n;
-  out[3 * F + f] = w_ema[(int64_t)f * nw + nw - 1];
-  out_nover[f] = nov;
-  long long r = (n * q_num + q_den - 1) / q_den;
-  r = r < 1 ? 1 : (r > n ? n : r);
-  SelState s;
-  s.kk = (unsigned long long)(n - r + 1);
-  s.cnt = (unsigned long long)n;
-  s.collected = 0;
-  s.pad = 0;
-  const unsigned long long diff = kmin ^ kmax;
-  if (diff == 0ull) {                  // a constant field: every key is the answer
-    s.prefix = kmax; s.nbits = 64; s.done = 1; s.ans = kmax;
-  } else {
-    const int cp = __clzll((long long)diff);   // leading bits common to all keys of the field
-    s.nbits = cp;
-    s.prefix = cp ? (kmax >> (64 - cp)) : 0ull;
-    s.done = 0;
-    s.ans = 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    c_abv += __shfl_xor_sync(0xffffffffu, c_abv, o);
+    c_eh += __shfl_xor_sync(0xffffffffu, c_eh, o);
+    c_el += __shfl_xor_sync(0xffffffffu, c_el, o);
+    nov += __shfl_xor_sync(0xffffffffu, nov, o);
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
   }
-  st[f] = s;
+  if (lane == 0) { s_red[wid][0] = kmin; s_red[wid][1] = kmax; s_red[wid][2] = c_abv; s_red[wid][3] = c_eh; s_red[wid][4] = c_el; s_red[wid][5] = nov; s_sum[wid] = sum; }
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < 8; ++w) {
+      kmin = min(kmin, s_red[w][0]); kmax = max(kmax, s_red[w][1]);
+      c_abv += s_red[w][2]; c_eh += s_red[w][3]; c_el += s_red[w][4]; nov += s_red[w][5];
+      sum += s_sum[w];
+    }
+    out[0 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(kmin));
+    out[1 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(kmax));
+    out[2 * F + f] = sum / (double)n;
+    out[3 * F + f] = w_ema[(int64_t)f * nw + nw - 1];
+    out_nover[f] = (uint32_t)nov;
+    long long r = (n * q_num + q_den - 1) / q_den;
+    r = r < 1 ? 1 : (r > n ? n : r);
+    SelState s;
+    s.kk = (unsigned long long)(n - r + 1);
+    s.cnt = (unsigned long long)n;
+    s.collected = 0;
+    s.pad = 0;
+    const unsigned long long diff = kmin ^ kmax;
+    int mode = 0;                      // 0: left to the histogram path, 1: answered, 2: select from the list
+    if (diff == 0ull) {                // a constant field: every key is the answer
+      s.prefix = kmax; s.nbits = 64; s.done = 1; s.ans = kmax;
+      mode = 1;
+    } else {
+      const int cp = __clzll((long long)diff);   // leading bits common to all keys of the field
+      s.nbits = cp;
+      s.prefix = cp ? (kmax >> (64 - cp)) : 0ull;
+      s.done = 0;
+      s.ans = 0ull;
+      if (sampled && kmax <= gpud_f64_key(0x7ff0000000000000ull)) {      // a +NaN would have been classified as "below": not trusted
+        const unsigned long long lok = gpud_f64_key((unsigned long long)__double_as_longlong(piv[2 * f]));
+        const unsigned long long hik = gpud_f64_key((unsigned long long)__double_as_longlong(piv[2 * f + 1]));
+        const unsigned long long inside = fill[f];
+        const unsigned long long k = s.kk;
+        if (lok <= hik && k > c_abv) {
+          if (k <= c_abv + c_eh) { s.done = 1; s.ans = hik; mode = 1; }
+          else if (k <= c_abv + c_eh + inside) {
+            if (inside <= (unsigned long long)list_cap) {
+              mode = 2;
+              const unsigned long long d2 = lok ^ hik;     // every listed key lies between the pivots: skip their common bits
+              const int cp2 = __clzll((long long)d2);
+              s_nbits = cp2;
+              s_prefix = cp2 ? (hik >> (64 - cp2)) : 0ull;
+              s_kk = k - c_abv - c_eh;
+            }
+          } else if (k <= c_abv + c_eh + inside + c_el) { s.done = 1; s.ans = lok; mode = 1; }
+        }
+      }
+    }
+    if (s.done) { s.nbits = 64; s.prefix = s.ans; }
+    st[f] = s;
+    s_mode = mode;
+    if (mode == 1) out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(s.ans));
+    if (mode == 0) atomicAdd(n_open, 1u);
+  }
+  __syncthreads();
+  if (s_mode != 2) return;
+  const unsigned cnt = fill[f];
+  const unsigned long long* __restrict__ list = lists + (int64_t)f * list_cap;
+  while (s_nbits < 64) {               // radix select over the L2-resident list, 11-bit digits
+    const int nbits = s_nbits;
+    const unsigned long long prefix = s_prefix;
+    const int d = min(kDigit, 64 - nbits), shift = 64 - nbits - d, nb = 1 << d;
+    for (int i = t; i < kBins; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    for (unsigned i = t; i < cnt; i += 256) {
+      const unsigned long long key = list[i];
+      if (nbits == 0 || (key >> (64 - nbits)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & (unsigned)(nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long acc = 0, kk = s_kk;
+      int bin = nb - 1;
+      while (bin > 0 && acc + s_hist[bin] < kk) { acc += s_hist[bin]; --bin; }
+      s_prefix = (nbits ? (prefix << d) : 0ull) | (unsigned long long)bin;
+      s_nbits = nbits + d;
+      s_kk = kk - acc;
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    SelState s = st[f];
+    s.done = 1; s.ans = s_prefix; s.nbits = 64; s.prefix = s_prefix;
+    st[f] = s;
+    out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(s_prefix));
+  }
 }
 
 // grid (blocks_per_field, F): histogram of the next digit over the keys that match the field's prefix
@@ -215,127 +379,6 @@ __global__ void __launch_bounds__(256) k_sel_final(const SelState* __restrict__ 
   if (t == 0) out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(ans));
 }
 
-// ---- experimental bounded select (off unless GPUD_RANGE_V2=1) ---------------------------------------------------------
-// When the range is a whole number of windows, the window pass can report every window's m-th largest key, m = ceil(k / nw) for the
-// global rank k.  Pigeonhole: every window holds >= m keys >= its own statistic, so >= nw m >= k keys are >= t = min_w stat_w; and no
-// window holds more than m - 1 keys above its statistic, so <= nw (m - 1) <= k - 1 keys are > T = max_w stat_w.  The k-th largest key
-// therefore lies in [t, T], and it is the (k - #{keys > T})-th largest of the keys inside the interval: one more pass over the range
-// counts the former and collects the latter (tests/test_range_bounds_model.py checks the argument on random data).  Fields whose
-// interval holds more than kCollect2Max keys are handed to the histogram path above.
-constexpr int kCollect2Max = 32768;
-
-struct Sel2State {                     // one per field
-  unsigned long long t, T;             // interval bounds as totalOrder keys
-  unsigned long long above;            // keys > T
-  unsigned collected;                  // keys in [t, T] (may exceed kCollect2Max: overflow)
-  int pad;
-};
-
-// one thread per field: interval bounds from the window statistics
-__global__ void k_sel2_bounds(int F, int nw, const double* __restrict__ w_stat, Sel2State* __restrict__ s2) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-  unsigned long long t = ~0ull, T = 0ull;
-  for (int w = 0; w < nw; ++w) {
-    const unsigned long long k = gpud_f64_key((unsigned long long)__double_as_longlong(w_stat[(int64_t)f * nw + w]));
-    t = min(t, k);
-    T = max(T, k);
-  }
-  Sel2State s;
-  s.t = t; s.T = T; s.above = 0ull; s.collected = 0u; s.pad = 0;
-  s2[f] = s;
-}
-
-// grid (blocks_per_field, F): count the keys above the interval, collect the keys inside it
-__global__ void __launch_bounds__(256) k_sel2_collect(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, const SelState* __restrict__ st,
-                                                       Sel2State* __restrict__ s2, unsigned long long* __restrict__ lists) {
-  const int f = blockIdx.y;
-  if (st[f].done) return;                                   // constant field: answered by the fold
-  const unsigned long long t = s2[f].t, T = s2[f].T;
-  const int64_t per = (((n + gridDim.x - 1) / gridDim.x) + 1) & ~(int64_t)1;
-  const int64_t b = min(n, (int64_t)blockIdx.x * per), e = min(n, b + per);
-  const double* __restrict__ base = ring + (int64_t)f * cap;
-  unsigned long long* __restrict__ list = lists + (int64_t)f * kCollect2Max;
-  unsigned* fill = &s2[f].collected;
-  unsigned above = 0;
-  for_each_key(base, cap, start, b, e, [&](unsigned long long key) {
-    if (key > T) ++above;
-    else if (key >= t) {
-      const unsigned pos = atomicAdd(fill, 1u);
-      if (pos < (unsigned)kCollect2Max) list[pos] = key;
-    }
-  });
-  above = __reduce_add_sync(0xffffffffu, above);
-  if ((threadIdx.x & 31) == 0 && above) atomicAdd(&s2[f].above, (unsigned long long)above);
-}
-
-// one block per field: radix select (11-bit digits, bits common to t and T skipped) over the collected list; fields that
-// overflowed the list keep done = 0 and go through the histogram path
-__global__ void __launch_bounds__(256) k_sel2_final(SelState* __restrict__ st, const Sel2State* __restrict__ s2, const unsigned long long* __restrict__ lists) {
-  __shared__ unsigned s_hist[kBins];
-  __shared__ unsigned long long s_prefix, s_kk;
-  __shared__ int s_nbits;
-  const int f = blockIdx.x, t = threadIdx.x;
-  if (st[f].done) return;
-  const Sel2State z = s2[f];
-  if (z.collected > (unsigned)kCollect2Max) return;         // overflow: left to the histogram path (st[f] untouched)
-  const unsigned cnt = z.collected;
-  const unsigned long long* __restrict__ list = lists + (int64_t)f * kCollect2Max;
-  if (t == 0) {
-    const unsigned long long diff = z.t ^ z.T;
-    const int cp = diff ? __clzll((long long)diff) : 64;
-    s_nbits = cp;
-    s_prefix = cp ? (cp == 64 ? z.T : (z.T >> (64 - cp))) : 0ull;
-    s_kk = st[f].kk - z.above;                              // rank inside the interval, 1-based from the top
-  }
-  __syncthreads();
-  while (s_nbits < 64) {
-    const int nbits = s_nbits;
-    const unsigned long long prefix = s_prefix;
-    const int d = min(kDigit, 64 - nbits), shift = 64 - nbits - d, nb = 1 << d;
-    for (int i = t; i < kBins; i += 256) s_hist[i] = 0;
-    __syncthreads();
-    for (unsigned i = t; i < cnt; i += 256) {
-      const unsigned long long key = list[i];
-      if (nbits == 0 || (key >> (64 - nbits)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & (unsigned)(nb - 1)], 1u);
-    }
-    __syncthreads();
-    if (t == 0) {
-      unsigned long long acc = 0, kk = s_kk;
-      int bin = nb - 1;
-      while (bin > 0 && acc + s_hist[bin] < kk) { acc += s_hist[bin]; --bin; }
-      s_prefix = (nbits ? (prefix << d) : 0ull) | (unsigned long long)bin;
-      s_nbits = nbits + d;
-      s_kk = kk - acc;
-    }
-    __syncthreads();
-  }
-  if (t == 0) {
-    SelState s = st[f];
-    s.done = 1;
-    s.ans = s_prefix;
-    s.nbits = 64;
-    s.prefix = s_prefix;
-    st[f] = s;
-  }
-}
-
-// host side of the experimental path: 0 = not applicable (caller runs the regular path), 1 = launched
-static int range_v2_applicable(int64_t n, int q_num, int q_den, int* rank_m) {
-  const char* env = getenv("GPUD_RANGE_V2");
-  if (!env || env[0] != '1') return 0;
-  const int64_t Wp = std::min<int64_t>(1024, n);
-  if (n <= kCollectMax || Wp < 1 || (n % Wp) != 0) return 0;
-  const int64_t nw = n / Wp;
-  long long r = (long long)((n * q_num + q_den - 1) / q_den);
-  r = r < 1 ? 1 : (r > n ? n : r);
-  const int64_t k = n - r + 1;
-  const int64_t m = (k + nw - 1) / nw;
-  if (m < 1 || m > Wp) return 0;
-  *rank_m = (int)m;
-  return 1;
-}
-
 }  // namespace
 
 extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64, uint32_t* out_n_over) {
@@ -344,66 +387,70 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   int64_t total = 0, count = 0, nwin = 0;
   gpud_ring_counts(ring, &total, &count, &nwin);
   if (count == 0) return GPUD_E_STATE;
-  int32_t rc;
-  const double* w_stat = nullptr;
-  int rank_m = 0;
-  {
-    const int64_t n_eff = (last_n <= 0 || last_n > count) ? count : last_n;
-    int qn = 99, qd = 100;
-    gpud_ring_quantile(ring, &qn, &qd);
-    if (range_v2_applicable(n_eff, qn, qd, &rank_m)) rc = gpud_ring_range_partials_ranked(ring, last_n, rank_m, &v, &w_stat);
-    else rc = gpud_ring_range_partials(ring, last_n, &v);
-  }
-  if (rc) return rc;
+  { int32_t rc = gpud_ring_range_prepare(ring, last_n, &v); if (rc) return rc; }
   gpud_ctx* ctx = v.ctx;
-  GPUD_CUDA(ctx, cudaSetDevice(v.dev));
   double* d_out = nullptr;
   uint32_t* d_nover = nullptr;
-  unsigned* d_hist = nullptr;
+  unsigned* d_hist = nullptr;          // histogram path scratch, allocated only when a field needs it
   SelState* d_st = nullptr;
   unsigned long long* d_lists = nullptr;
-  Sel2State* d_s2 = nullptr;
-  unsigned long long* d_lists2 = nullptr;
+  unsigned* d_open = nullptr;
+  unsigned h_open = 0;
   cudaError_t e = cudaMallocAsync(&d_out, 5 * v.F * sizeof(double), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nover, v.F * sizeof(uint32_t), v.stream);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_hist, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_st, v.F * sizeof(SelState), v.stream);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_lists, (size_t)v.F * kCollectMax * sizeof(unsigned long long), v.stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_hist, 0, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_open, sizeof(unsigned), v.stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_open, 0, sizeof(unsigned), v.stream);
+  if (e == cudaSuccess) e = cudaEventRecord(v.ev[0], v.stream);
+  if (e == cudaSuccess && v.sampled) {
+    long long r = (long long)((v.n * v.q_num + v.q_den - 1) / v.q_den);
+    r = r < 1 ? 1 : (r > v.n ? v.n : r);
+    const int S = (int)std::min<int64_t>(kSampleMax, v.n / 8);
+    const int64_t stride = v.n / S;
+    e = cudaFuncSetAttribute(k_range_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleMax * (int)sizeof(unsigned long long));
+    if (e == cudaSuccess) k_range_pivots<<<v.F, 256, (size_t)S * sizeof(unsigned long long), v.stream>>>(v.ring, v.cap, v.start, v.n, S, stride, v.n - r + 1, v.piv, v.fill);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
   if (e == cudaSuccess) {
-    k_range_fold<<<(v.F + 127) / 128, 128, 0, v.stream>>>(v.F, v.nw, v.Wp, v.n, v.w_min, v.w_max, v.w_mean, v.w_ema, v.w_nover, v.q_num, v.q_den,
-                                                         d_out, d_nover, d_st);
-    // blocks per field: enough CTAs to fill the machine a few times over, each streaming >= 16 Ki keys
-    const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 8 * v.sm_count / v.F + 1)));
-    if (w_stat) {                                                  // experimental bounded select; fields it cannot finish stay !done
-      e = cudaMallocAsync(&d_s2, v.F * sizeof(Sel2State), v.stream);
-      if (e == cudaSuccess) e = cudaMallocAsync(&d_lists2, (size_t)v.F * kCollect2Max * sizeof(unsigned long long), v.stream);
-      if (e == cudaSuccess) {
-        k_sel2_bounds<<<(v.F + 127) / 128, 128, 0, v.stream>>>(v.F, v.nw, w_stat, d_s2);
-        k_sel2_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_s2, d_lists2);
-        k_sel2_final<<<v.F, 256, 0, v.stream>>>(d_st, d_s2, d_lists2);
-        e = cudaGetLastError();
-      }
-    }
-    if (e == cudaSuccess && v.n > kCollectMax) {
-      for (int pass = 0; pass < kMaxHistPasses; ++pass) {          // later passes exit at once for fields that are already narrow
-        k_sel_hist<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_hist);
-        k_sel_pick<<<v.F, 256, 0, v.stream>>>(d_hist, d_st);
-      }
-    }
+    int32_t rc = gpud_ring_range_pass(ring, &v);
+    if (rc) { cudaFreeAsync(d_out, v.stream); cudaFreeAsync(d_nover, v.stream); cudaFreeAsync(d_st, v.stream); cudaFreeAsync(d_open, v.stream); return rc; }
+    e = cudaEventRecord(v.ev[1], v.stream);
+  }
+  if (e == cudaSuccess) {
+    k_range_finish<<<v.F, 256, 0, v.stream>>>(v.F, v.nw, v.Wp, v.n, v.w_min, v.w_max, v.w_mean, v.w_ema, v.w_nover, v.q_num, v.q_den, v.sampled, v.piv, v.fill,
+                                              v.w_cls, v.lists, v.list_cap, d_out, d_nover, d_st, d_open);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(v.ev[2], v.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_open, d_open, sizeof(unsigned), cudaMemcpyDeviceToHost, v.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
+  if (e == cudaSuccess && h_open > 0) {
+    // histogram path for the fields still open: every field of a short range, or the rare field the sampled pass could not settle
+    e = cudaMallocAsync(&d_hist, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_lists, (size_t)v.F * kCollectMax * sizeof(unsigned long long), v.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_hist, 0, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
     if (e == cudaSuccess) {
+      // blocks per field: enough CTAs to fill the machine a few times over, each streaming >= 16 Ki keys
+      const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 8 * v.sm_count / v.F + 1)));
+      if (v.n > kCollectMax) {
+        for (int pass = 0; pass < kMaxHistPasses; ++pass) {          // later passes exit at once for fields that are already narrow
+          k_sel_hist<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_hist);
+          k_sel_pick<<<v.F, 256, 0, v.stream>>>(d_hist, d_st);
+        }
+      }
       k_sel_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_lists);
       k_sel_final<<<v.F, 256, 0, v.stream>>>(d_st, d_lists, v.F, d_out);
       e = cudaGetLastError();
     }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64 + 4 * (size_t)v.F, d_out + 4 * (size_t)v.F, v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
+    if (d_hist) cudaFreeAsync(d_hist, v.stream);
+    if (d_lists) cudaFreeAsync(d_lists, v.stream);
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
-  cudaFreeAsync(d_out, v.stream); cudaFreeAsync(d_nover, v.stream); cudaFreeAsync(d_hist, v.stream);
-  cudaFreeAsync(d_st, v.stream); cudaFreeAsync(d_lists, v.stream);
-  if (d_s2) cudaFreeAsync(d_s2, v.stream);
-  if (d_lists2) cudaFreeAsync(d_lists2, v.stream);
+  cudaFreeAsync(d_out, v.stream); cudaFreeAsync(d_nover, v.stream); cudaFreeAsync(d_st, v.stream); cudaFreeAsync(d_open, v.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
   if (e != cudaSuccess) return gpud_fail(ctx, GPUD_E_CUDA, "reduce_range: %s", cudaGetErrorString(e));
+  gpud_ring_range_note(ring, v.sampled != 0, h_open);
   return GPUD_OK;
 }

@@ -114,7 +114,10 @@ int32_t gpud_hw_slowdown_check(const int64_t* event_unix, int32_t n, int64_t now
 enum { GPUD_POLL_TEMPERATURE_C = 0, GPUD_POLL_POWER_MW = 1, GPUD_POLL_CLOCK_GRAPHICS_MHZ = 2, GPUD_POLL_CLOCK_SM_MHZ = 3,
        GPUD_POLL_CLOCK_MEM_MHZ = 4, GPUD_POLL_UTIL_GPU_PCT = 5, GPUD_POLL_UTIL_MEM_PCT = 6, GPUD_POLL_MEMORY_USED_MIB = 7,
        GPUD_POLL_N_FIELDS = 8 };
-#define GPUD_POLL_UNSUPPORTED 0xffffffffu   /* column value when the device does not support the getter */
+/* A getter that fails does NOT put a sentinel into the ring: the column holds its last good value (0 before the first good read,
+ * oracle/SPEC.md) and the failure is recorded for gpud_poller_errors.  gpud_poll_row_hold is that rule as a pure function:
+ * fresh[c] is taken when nvml_rc[c] == 0, otherwise held[c] is repeated and bit c of *fail_mask is set. */
+int32_t gpud_poll_row_hold(const uint32_t* fresh, const int32_t* nvml_rc, int32_t n_cols, uint32_t* held, uint32_t* row_out, uint32_t* fail_mask);
 typedef struct gpud_poller gpud_poller;
 int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* ring, gpud_poller** out);
 void gpud_poller_destroy(gpud_poller* poller);
@@ -122,6 +125,9 @@ void gpud_poller_destroy(gpud_poller* poller);
 int32_t gpud_poller_poll(gpud_poller* poller, int64_t n_polls, int64_t interval_us);
 /* The rows of the last push batch (at most 16384) as they went over PCIe, and the wall time of the last poll call. */
 int32_t gpud_poller_last_rows(gpud_poller* poller, uint32_t* rows, int64_t cap_rows, int64_t* n_rows, double* seconds);
+/* Columns whose getter failed at least once since create (bit c), each column's last NVML return code and failure count
+ * ([GPUD_POLL_N_FIELDS] each; any pointer may be NULL). */
+int32_t gpud_poller_errors(gpud_poller* poller, uint32_t* fail_mask, int32_t* last_nvml_rc, uint64_t* n_failed);
 /* GetTemperature (temperature/temperature.go:78-221) for this poller's GPU, and the per-GPU rules of the temperature component's
  * Check (temperature/component.go:206-248) over such a reading: *bits = 1 GPU core above its max-operating threshold | 2 HBM above
  * the memory max | 4 thermal margin at or below margin_threshold_c (0 = rule off, temperature/threshold.go:13); the component's
@@ -159,9 +165,14 @@ int32_t gpud_ring_read(gpud_ring* ring, int32_t op, void* out, int64_t out_bytes
 /* Device pointer of an aggregate (same layout), valid until the next reduce/destroy. */
 int32_t gpud_ring_result_ptr(gpud_ring* ring, int32_t op, void** dev_ptr);
 
-/* Whole-range aggregates of the most recent `last_n` samples of every field (last_n = 0 => whole ring):
- * exact order statistic by multi-pass radix select.  out_f64 is [5][F] (MIN,MAX,MEAN,EMA,P99), n_over [F]. */
+/* Whole-range aggregates of the most recent `last_n` samples of every field (last_n = 0 => whole ring, i.e. the W = CAP order
+ * statistic of BASELINE configs[3]); exact.  Ranges of >= 64 Ki samples read HBM once (sampled pivots + classification fused into
+ * the window pass), shorter ones and any field the sample misjudged use a multi-pass radix select.  out_f64 is [5][F]
+ * (MIN,MAX,MEAN,EMA,P99), n_over [F].  Synchronous. */
 int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64, uint32_t* out_n_over);
+/* Device time of the last gpud_ring_reduce_range that took the single-pass route: the fused range pass alone and the whole device
+ * side (pivots + pass + EMA carry + finish), and how many fields had to be re-done by the radix select (normally 0). */
+int32_t gpud_ring_range_stats(gpud_ring* ring, float* pass_ms, float* total_ms, int32_t* fields_by_histogram);
 
 /* ------------------------------------------------------------------------------------------------
  * kmsg Xid / SXid scan + classification.

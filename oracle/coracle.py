@@ -19,6 +19,55 @@ def lib():
     return _lib
 
 
+_native_note = "oracle/liboracle.so (-O3 -march=x86-64-v3, built with the repo)"
+
+
+def use_native():
+    """Rebuild the oracle's C sources with -O3 -march=native for THIS host's CPU (into the temp dir, never into the repo) and time
+    that build from now on; falls back to the shipped x86-64-v3 build.  Returns a one-line note saying which build is loaded."""
+    global _lib, _native_note
+    import hashlib
+    import subprocess
+    import tempfile
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.c", "regex_bt.c")]
+    h = hashlib.sha1(b"".join(open(f, "rb").read() for f in srcs)).hexdigest()[:12]
+    out = os.path.join(tempfile.gettempdir(), "gpud_liboracle_native_%s_%d.so" % (h, os.getuid()))
+    try:
+        if not os.path.exists(out):
+            cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+            subprocess.run([cc, "-O3", "-march=native", "-fPIC", "-shared", "-o", out + ".tmp"] + srcs + ["-lm", "-lpthread"], check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=_HERE)
+            os.replace(out + ".tmp", out)
+        L = C.CDLL(out)
+        L.orc_max_threads.restype = C.c_int32
+        _lib = L
+        _native_note = "oracle sources rebuilt on this host with gcc -O3 -march=native"
+    except Exception as ex:           # no compiler on the box: keep the shipped build
+        _native_note += " (native rebuild failed: %s)" % type(ex).__name__
+    return _native_note
+
+
+def build_note() -> str:
+    return _native_note
+
+
+def host_cpus() -> dict:
+    """what the CPU arm may use: logical CPUs, affinity mask, cgroup quota, and the thread count the oracle takes from them"""
+    d = {"logical": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None, "cgroup_quota": None}
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        d["cgroup_quota"] = None if q == "max" else float(q) / float(p)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            d["cgroup_quota"] = q / p if q > 0 else None
+        except Exception:
+            pass
+    d["threads_used"] = max_threads()
+    return d
+
+
 def windows_fields(ring: np.ndarray, W: int, thr: np.ndarray, alpha: float = 0.0, q_num: int = 0, q_den: int = 0, threads: int = 0):
     """ring: [F][n] f64 field-major.  Returns dict of [F][nw] arrays."""
     L = lib()

@@ -13,10 +13,12 @@
 #define _GNU_SOURCE
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <pthread.h>
+#include <sched.h>
 #include <unistd.h>
 
 static inline uint64_t f64_key(double x) {
@@ -96,8 +98,25 @@ static void* orc_worker(void* p) {
     P->fn(P->arg, i);
   }
 }
+/* CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota (cpu.max "quota period" of cgroup v2,
+ * cpu.cfs_quota_us / cpu.cfs_period_us of v1) - `nproc` of a container reports the host's logical CPUs, not its share. */
 int32_t orc_max_threads(void) {
   long n = sysconf(_SC_NPROCESSORS_ONLN);
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) { const int c = CPU_COUNT(&set); if (c > 0 && c < n) n = c; }
+  long long quota = -1, period = -1;
+  FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r");
+  if (f) {
+    char q[32] = {0};
+    if (fscanf(f, "%31s %lld", q, &period) == 2 && strcmp(q, "max") != 0) quota = atoll(q);
+    fclose(f);
+  } else {
+    f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r");
+    if (f) { if (fscanf(f, "%lld", &quota) != 1) quota = -1; fclose(f); }
+    f = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+    if (f) { if (fscanf(f, "%lld", &period) != 1) period = -1; fclose(f); }
+  }
+  if (quota > 0 && period > 0) { const long c = (long)((quota + period - 1) / period); if (c > 0 && c < n) n = c; }
   return n > 0 ? (int32_t)n : 1;
 }
 void orc_parallel_for(orc_job_fn fn, void* arg, int64_t n, int32_t threads) {

@@ -576,46 +576,84 @@ def test_ring_reduce_range(ctx, last_n):
     r.close()
 
 
-@pytest.mark.skipif(os.environ.get("GPUD_TEST_EXPERIMENTAL") != "1", reason="experimental bounded select (GPUD_RANGE_V2): run with GPUD_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("shape", ["gauge", "ties", "uniform", "drift", "const"])
-@pytest.mark.parametrize("n,qn,qd", [(65536, 99, 100), (32768, 1, 2), (16384, 999, 1000), (131072, 1, 100)])
+def _range_data(shape, n, F, rng):
+    if shape == "gauge":
+        return synth.gauge_stream(F, n, seed=5)
+    if shape == "ties":
+        return np.floor(rng.normal(60, 2, (n, F)))
+    if shape == "uniform":
+        return np.floor(rng.uniform(30000, 90000, (n, F)))
+    if shape == "drift":
+        return 60 + 25 * np.sin(np.arange(n)[:, None] / n * 7.0 + np.arange(F)[None, :]) + rng.normal(0, 0.3, (n, F))
+    if shape == "binary":                     # a utilisation gauge that is either idle or pinned: two huge classes of equal keys
+        return np.where(rng.random((n, F)) < 0.3, 0.0, 100.0)
+    if shape == "zeros":                      # +0 / -0 around the pivots: equal as doubles, different totalOrder keys
+        x = rng.choice(np.array([-1.0, -0.0, 0.0, 1.0]), size=(n, F), p=[0.02, 0.48, 0.48, 0.02])
+        return x
+    if shape == "special":                    # NaN of both signs and infinities among ordinary readings
+        x = rng.normal(50, 5, (n, F))
+        x[rng.random((n, F)) < 0.001] = np.nan
+        x[rng.random((n, F)) < 0.001] = -np.nan
+        x[rng.random((n, F)) < 0.002] = np.inf
+        x[rng.random((n, F)) < 0.002] = -np.inf
+        x[:, 0] = np.copysign(np.nan, -1.0)   # a field of nothing but -NaN
+        return x
+    x = np.full((n, F), 42.0)
+    x[:, 1] = -0.0
+    return x
+
+
+@pytest.mark.parametrize("shape", ["gauge", "ties", "uniform", "drift", "const", "binary", "zeros", "special"])
+@pytest.mark.parametrize("n,qn,qd", [(65536, 99, 100), (32768, 1, 2), (16384, 999, 1000), (131072, 1, 100), (262144, 1, 2), (65536, 0, 1), (65536, 1, 1)])
 def test_ring_reduce_range_bounded_select(ctx, shape, n, qn, qd):
-    """the order statistic of a whole-window range from the per-window statistics' interval; identical to the oracle and to the
-    regular path, on data where the interval is narrow (stationary), wide (drift -> falls back per field) and degenerate (ties, constants)"""
+    """The whole-range order statistic (select.cu): ranges >= 64 Ki take the sampled-pivot single pass, shorter ones the radix
+    select; both identical to a sort (oracle SPEC.md: totalOrder, nearest rank) on stationary, drifting, tie-heavy and
+    degenerate data, incl. signed zeros, infinities and NaN."""
     F, W = 5, 1000
     rng = np.random.default_rng(n + qn)
-    if shape == "gauge":
-        x = synth.gauge_stream(F, n, seed=5)
-    elif shape == "ties":
-        x = np.floor(rng.normal(60, 2, (n, F)))
-    elif shape == "uniform":
-        x = np.floor(rng.uniform(30000, 90000, (n, F)))
-    elif shape == "drift":
-        x = 60 + 25 * np.sin(np.arange(n)[:, None] / n * 7.0 + np.arange(F)[None, :]) + rng.normal(0, 0.3, (n, F))
-    else:
-        x = np.full((n, F), 42.0)
-        x[:, 1] = -0.0
-    thr = synth.thresholds_for(x)
+    x = np.ascontiguousarray(_range_data(shape, n, F, rng))
+    thr = np.full(F, 60.0)
     r = g.Ring(ctx, F, n, W, thresholds=thr, q_num=qn, q_den=qd)
-    r.push(np.ascontiguousarray(x))
-    old = os.environ.pop("GPUD_RANGE_V2", None)
-    try:
-        base = r.reduce_range(0)
-        os.environ["GPUD_RANGE_V2"] = "1"
-        got = r.reduce_range(0)
-    finally:
-        os.environ.pop("GPUD_RANGE_V2", None)
-        if old is not None:
-            os.environ["GPUD_RANGE_V2"] = old
+    r.push(x)
+    got = r.reduce_range(0)
+    if n >= 65536:
+        pass_ms, total_ms, redo = r.range_stats()
+        assert pass_ms > 0 and total_ms >= pass_ms
+        if shape in ("gauge", "uniform", "drift", "ties", "binary", "const"):
+            assert redo == 0, redo            # the sample settles ordinary data; special values may fall back
+    rank = O.quantile_rank(n, qn, qd)
     for f in range(F):
-        want = O.window_aggregates(x[:, f], n, thr[f], 2.0 / (W + 1.0), q_num=qn, q_den=qd) if "q_num" in O.window_aggregates.__code__.co_varnames else None
+        col = x[:, f]
+        ks = np.sort(O.total_order_key(col))
+        want = O.key_to_f64(ks[[0, -1, rank - 1]]).view(np.uint64)
+        have = np.array([got["min"][f], got["max"][f], got["p99"][f]]).view(np.uint64)
+        assert np.array_equal(have, want), (f, have.view(np.float64), want.view(np.float64))
+        assert int(got["n_over"][f]) == int(np.count_nonzero(col > thr[f]))
+        if np.all(np.isfinite(col)):
+            scale = float(np.max(np.abs(col))) or 1.0
+            assert abs(got["mean"][f] - col.mean()) <= 1e-9 * scale
+    r.close()
+
+
+@pytest.mark.parametrize("pushed,last_n", [(300000, 0), (300000, 100000), (200001, 70001), (131072 + 4096, 0)])
+def test_ring_reduce_range_sampled_wrapped(ctx, pushed, last_n):
+    """the single-pass route on a ring that has wrapped (odd starts, a window straddling the physical end, a partial last window)"""
+    F, cap, W = 4, 131072, 1000
+    x = synth.gauge_stream(F, pushed, seed=3)
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    r.push(x)
+    got = r.reduce_range(last_n)
+    n = min(cap, pushed) if last_n == 0 else last_n
+    seg = x[-n:]
+    for f in range(F):
+        want = O.window_aggregates(seg[:, f], n, thr[f], 2.0 / (W + 1.0))
         for k in ("min", "max", "p99"):
-            assert got[k][f:f + 1].view(np.uint64)[0] == base[k][f:f + 1].view(np.uint64)[0], (k, f)
-            if want is not None:
-                assert got[k][f:f + 1].view(np.uint64)[0] == want[k].view(np.uint64)[0], (k, f)
-        assert int(got["n_over"][f]) == int(base["n_over"][f])
+            assert got[k][f:f + 1].view(np.uint64)[0] == want[k].view(np.uint64)[0], (k, f)
+        assert int(got["n_over"][f]) == int(want["n_over"][0])
+        scale = float(np.max(np.abs(seg[:, f])))
         for k in ("mean", "ema"):
-            assert got[k][f] == base[k][f], (k, f)
+            assert abs(got[k][f] - want[k][0]) <= 1e-6 * max(abs(want[k][0]), scale), (k, f)
     r.close()
 
 

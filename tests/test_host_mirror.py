@@ -676,3 +676,22 @@ def test_merge_and_trim_scenarios_of_the_reference():
     assert L.gpudh_trim_count(b"SetHealthy") == 0                                 # onlySetHealthyReturnsEmpty
     assert O.trim_events_after_set_healthy([{"name": "error_xid"}, {"name": "SetHealthy"}, {"name": "error_xid"}]) == [{"name": "error_xid"}]
     assert O.trim_events_after_set_healthy([{"name": "SetHealthy"}]) == []
+
+
+def test_poll_row_holds_the_last_good_value_when_a_getter_fails():
+    """oracle/SPEC.md: a failed getter repeats the column's last good value (0 before the first good read); no sentinel ever
+    reaches the ring.  NVML return codes: 0 success, 3 not supported, 999 unknown (transient)."""
+    held = [0] * 8
+    row, mask = g.capi.poll_row_hold([41, 250000, 1965, 1965, 3996, 97, 30, 1024], [0] * 8, held)
+    assert row == [41, 250000, 1965, 1965, 3996, 97, 30, 1024] and mask == 0
+    # a transient failure of the power getter and an unsupported memory-utilisation getter: both columns repeat
+    row, mask = g.capi.poll_row_hold([42, 0xDEAD, 1950, 1950, 3996, 98, 0xBEEF, 1030], [0, 999, 0, 0, 0, 0, 3, 0], held)
+    assert row == [42, 250000, 1950, 1950, 3996, 98, 30, 1030] and mask == (1 << 1) | (1 << 6)
+    assert 0xFFFFFFFF not in row
+    # the column recovers with the next good read
+    row, mask = g.capi.poll_row_hold([43, 260000, 1950, 1950, 3996, 99, 31, 1031], [0] * 8, held)
+    assert row == [43, 260000, 1950, 1950, 3996, 99, 31, 1031] and mask == 0
+    # never read successfully: the column stays 0, not 0xffffffff
+    held2 = [0] * 8
+    row, mask = g.capi.poll_row_hold([7] * 8, [3] * 8, held2)
+    assert row == [0] * 8 and mask == 0xFF

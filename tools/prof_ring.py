@@ -46,13 +46,14 @@ for _ in range(reps):
     ring.reduce()
 ring.sync()
 print(shape, "kernel ms (reduce, carry):", ring.kernel_ms())
-if len(sys.argv) > 2 and sys.argv[2] == "range":
+if len(sys.argv) > 3 and sys.argv[3] == "range":
     import time
     ring.reduce_range(0)
     ring.sync()
-    ts = []
+    ts, st = [], []
     for _ in range(5):
         t0 = time.perf_counter()
         out = ring.reduce_range(0)
         ts.append(time.perf_counter() - t0)
-    print("reduce_range(whole ring) ms:", [round(t * 1e3, 3) for t in ts], "p99[0..3]", out["p99"][:3])
+        st.append(ring.range_stats())
+    print("reduce_range(whole ring) host ms:", [round(t * 1e3, 3) for t in ts], "device (pass ms, total ms, fields redone):", st, "p99[0..3]", out["p99"][:3])
