@@ -85,7 +85,7 @@ struct gpud_range_view {
 };
 int32_t gpud_ring_range_prepare(gpud_ring* r, int64_t n, gpud_range_view* v);
 int32_t gpud_ring_range_pass(gpud_ring* r, const gpud_range_view* v);
-void gpud_ring_range_note(gpud_ring* r, bool sampled, unsigned fields_open);
+void gpud_ring_range_note(gpud_ring* r, bool sampled, unsigned fields_open, const int* reasons /*[GPUD_RANGE_N_OPEN_REASONS]*/);
 void gpud_ring_quantile(gpud_ring* r, int* q_num, int* q_den);
 
 void gpud_scan_state_free(gpud_scan_state*);

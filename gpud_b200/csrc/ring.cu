@@ -572,6 +572,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       if (__any_sync(kFull, inmask != 0u)) {
         const unsigned long long lok = gpud_f64_key((unsigned long long)__double_as_longlong(piv_lo));
         const unsigned long long hik = gpud_f64_key((unsigned long long)__double_as_longlong(piv_hi));
+        // equal pivots that are not a zero: lo <= x <= hi as doubles already means key == hi (a tie-heavy gauge: every flagged
+        // sample is a copy of the pivot), no need to look at the keys
+        const bool all_equal = lok == hik && piv_hi != 0.0;
+        if (all_equal) { n_eh = (unsigned)__popc(inmask); inmask = 0u; }
         unsigned mm = inmask;
         while (mm) {
           const int i = __ffs(mm) - 1;
@@ -702,6 +706,7 @@ struct gpud_ring {
   cudaStream_t copy_stream = nullptr;
   int64_t stage_rows = 0;
   int sm_count = 148;
+  int cta_reserve = 0;           // CTA slots the persistent window grid leaves free for kernels of other streams (gpud_ring_set_cta_reserve)
   double* d_rng[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // range-reduce scratch: per-window min,max,mean,ema,partials
   size_t rng_bytes[5] = {0, 0, 0, 0, 0};
   uint32_t* d_rng_nover = nullptr;
@@ -714,6 +719,7 @@ struct gpud_ring {
   size_t rng_piv_bytes = 0;
   cudaEvent_t ev_rng[3] = {nullptr, nullptr, nullptr}; // start / after the range pass / end of the last sampled reduce_range
   bool range_timed = false;
+  int range_reasons[GPUD_RANGE_N_OPEN_REASONS] = {0};
   int range_fields_open = 0;                           // fields the last sampled reduce_range handed to the histogram path
   cudaEvent_t ev_k[3] = {nullptr, nullptr, nullptr};   // around the two kernels of the last reduce (bench roofline)
 };
@@ -792,6 +798,12 @@ extern "C" int32_t gpud_ring_destroy(gpud_ring* r) {
   if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
   if (r->own_stream) cudaStreamDestroy(r->own_stream);
   delete r;
+  return GPUD_OK;
+}
+
+extern "C" int32_t gpud_ring_set_cta_reserve(gpud_ring* r, int32_t n_ctas) {
+  if (!r || n_ctas < 0 || n_ctas >= r->sm_count) return GPUD_E_INVALID;
+  r->cta_reserve = n_ctas;
   return GPUD_OK;
 }
 
@@ -912,7 +924,7 @@ static cudaError_t launch_one(gpud_ring* r, const WinParams& p, int64_t units) {
   // 72 KB of dynamic shared memory per CTA (8 warps x (32 x 272 B key rows + candidate list)): opt in above 48 KB
   cudaError_t e = cudaFuncSetAttribute(k_window_reduce<ALIGNED, JF, RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBlockSmemBytes);
   if (e != cudaSuccess) return e;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * ((ALIGNED && JF >= 0) ? kHotCtasPerSM : 2)));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((units + kWarpsPerBlock - 1) / kWarpsPerBlock, (int64_t)r->sm_count * ((ALIGNED && JF >= 0) ? kHotCtasPerSM : 2) - r->cta_reserve));
   k_window_reduce<ALIGNED, JF, RANGE><<<grid, kWarpsPerBlock * 32, kBlockSmemBytes, r->stream>>>(p);
   return cudaGetLastError();
 }
@@ -1078,12 +1090,13 @@ int32_t gpud_ring_range_pass(gpud_ring* r, const gpud_range_view* v) {
   return GPUD_OK;
 }
 
-void gpud_ring_range_note(gpud_ring* r, bool sampled, unsigned fields_open) {
+void gpud_ring_range_note(gpud_ring* r, bool sampled, unsigned fields_open, const int* reasons) {
   r->range_timed = sampled;
   r->range_fields_open = (int)fields_open;
+  for (int i = 0; i < GPUD_RANGE_N_OPEN_REASONS; ++i) r->range_reasons[i] = reasons[i];
 }
 
-extern "C" int32_t gpud_ring_range_stats(gpud_ring* r, float* pass_ms, float* total_ms, int32_t* fields_by_histogram) {
+extern "C" int32_t gpud_ring_range_stats(gpud_ring* r, float* pass_ms, float* total_ms, int32_t* fields_by_histogram, int32_t* reasons) {
   if (!r || !pass_ms || !total_ms || !fields_by_histogram) return GPUD_E_INVALID;
   if (!r->range_timed) return gpud_fail(r->ctx, GPUD_E_STATE, "the last reduce_range (if any) did not take the sampled single pass");
   GPUD_CUDA(r->ctx, cudaSetDevice(r->dev));
@@ -1091,6 +1104,7 @@ extern "C" int32_t gpud_ring_range_stats(gpud_ring* r, float* pass_ms, float* to
   GPUD_CUDA(r->ctx, cudaEventElapsedTime(pass_ms, r->ev_rng[0], r->ev_rng[1]));
   GPUD_CUDA(r->ctx, cudaEventElapsedTime(total_ms, r->ev_rng[0], r->ev_rng[2]));
   *fields_by_histogram = r->range_fields_open;
+  if (reasons) for (int i = 0; i < GPUD_RANGE_N_OPEN_REASONS; ++i) reasons[i] = r->range_reasons[i];
   return GPUD_OK;
 }
 

@@ -79,23 +79,52 @@ __device__ __forceinline__ void for_each_key(const double* __restrict__ base, in
 // answered by the histogram path below - results never depend on the sample.
 constexpr int kSampleMax = 8192;
 
-// k-th largest (1-based) of keys[0..cnt) in shared memory; 256 threads, eight 8-bit digits.  All threads return the key.
-__device__ unsigned long long block_select_smem(const unsigned long long* keys, int cnt, int kk, unsigned* hist /*[256]*/, unsigned long long* bc /*[2]*/) {
-  const int t = threadIdx.x, lane = t & 31;
-  unsigned long long prefix = 0ull;
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = 56 - 8 * pass;
-    hist[t] = 0;
+// The kkA-th and kkB-th largest (1-based) of keys[0..cnt) in shared memory, both at once; 256 threads.  MSB-first 8-bit digits
+// starting below the bits all keys share; a target whose chosen bin holds a single key is finished by one more sweep that
+// finds that key (after two digits of an 8 Ki sample almost every bin does).  Warp 0 walks target A's histogram, warp 1 B's.
+struct Sel2 { unsigned long long prefix[2]; unsigned kk[2]; int single[2]; unsigned long long ans[2]; int done[2]; };
+__device__ void block_select2_smem(const unsigned long long* keys, int cnt, int kkA, int kkB, unsigned* hist /*[2][256]*/, Sel2* z,
+                                   unsigned long long* red /*[16]*/, unsigned long long* outA, unsigned long long* outB) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  unsigned long long kmin = ~0ull, kmax = 0ull;
+  for (int i = t; i < cnt; i += 256) { const unsigned long long k = keys[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if (lane == 0) { red[wid] = kmin; red[8 + wid] = kmax; }
+  __syncthreads();
+  for (int w = 0; w < 8; ++w) { kmin = min(kmin, red[w]); kmax = max(kmax, red[8 + w]); }
+  if (kmin == kmax) { *outA = *outB = kmax; return; }
+  int nfix = __clzll((long long)(kmin ^ kmax));
+  if (t == 0) {
+    for (int x = 0; x < 2; ++x) { z->prefix[x] = nfix ? (kmax >> (64 - nfix)) : 0ull; z->single[x] = 0; z->done[x] = 0; z->ans[x] = 0ull; }
+    z->kk[0] = (unsigned)kkA; z->kk[1] = (unsigned)kkB;
+  }
+  __syncthreads();
+  while (nfix < 64) {
+    const int d = min(8, 64 - nfix), shift = 64 - nfix - d;
+    const unsigned mask = (1u << d) - 1u;
+    const unsigned long long pA = z->prefix[0], pB = z->prefix[1];
+    const bool liveA = !z->done[0], liveB = !z->done[1];
+    if (!liveA && !liveB) break;
+    hist[t] = 0; hist[256 + t] = 0;
     __syncthreads();
     for (int i = t; i < cnt; i += 256) {
       const unsigned long long key = keys[i];
-      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+      const unsigned long long top = nfix ? (key >> (64 - nfix)) : 0ull;
+      const unsigned bin = (unsigned)(key >> shift) & mask;
+      if (liveA && top == pA) atomicAdd(&hist[bin], 1u);
+      if (liveB && top == pB) atomicAdd(&hist[256 + bin], 1u);
     }
     __syncthreads();
-    if (t < 32) {                                    // lane l owns bins 255-8l .. 248-8l (descending)
+    if (wid < 2 && !z->done[wid]) {                  // lane l owns bins 255-8l .. 248-8l (descending) of target `wid`
+      const unsigned* h = hist + 256 * wid;
+      const unsigned kk = z->kk[wid];
       unsigned loc = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) loc += hist[255 - 8 * lane - j];
+      for (int j = 0; j < 8; ++j) loc += h[255 - 8 * lane - j];
       unsigned incl = loc;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -103,28 +132,41 @@ __device__ unsigned long long block_select_smem(const unsigned long long* keys, 
         if (lane >= o) incl += u;
       }
       const unsigned before = incl - loc;            // keys in the bins above this lane's
-      const bool mine = before < (unsigned)kk && (unsigned)kk <= incl;
-      if (mine) {
+      if (before < kk && kk <= incl) {
         unsigned acc = before;
         int bin = 255 - 8 * lane;
-        while (acc + hist[bin] < (unsigned)kk) { acc += hist[bin]; --bin; }
-        bc[0] = (prefix << 8) | (unsigned long long)bin;
-        bc[1] = (unsigned long long)((unsigned)kk - acc);
+        while (acc + h[bin] < kk) { acc += h[bin]; --bin; }
+        z->prefix[wid] = (z->prefix[wid] << d) | (unsigned long long)bin;
+        z->kk[wid] = kk - acc;
+        z->single[wid] = h[bin] == 1u;
       }
     }
     __syncthreads();
-    prefix = bc[0];
-    kk = (int)bc[1];
+    nfix += d;
+    if (nfix == 64) {
+      if (t < 2 && !z->done[t]) { z->ans[t] = z->prefix[t]; z->done[t] = 1; }
+    } else if ((z->single[0] && !z->done[0]) || (z->single[1] && !z->done[1])) {
+      const bool sA = z->single[0] && !z->done[0], sB = z->single[1] && !z->done[1];
+      const unsigned long long qA = z->prefix[0], qB = z->prefix[1];
+      __syncthreads();
+      for (int i = t; i < cnt; i += 256) {
+        const unsigned long long key = keys[i], top = key >> (64 - nfix);
+        if (sA && top == qA) { z->ans[0] = key; z->done[0] = 1; }
+        if (sB && top == qB) { z->ans[1] = key; z->done[1] = 1; }
+      }
+    }
     __syncthreads();
   }
-  return prefix;
+  *outA = z->ans[0];
+  *outB = z->ans[1];
 }
 
 __global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, int S, int64_t stride,
                                                        int64_t k_from_top, double* __restrict__ piv, unsigned* __restrict__ fill) {
   extern __shared__ __align__(16) unsigned long long s_keys[];
-  __shared__ unsigned s_hist[256];
-  __shared__ unsigned long long s_bc[2];
+  __shared__ unsigned s_hist[512];
+  __shared__ unsigned long long s_red[16];
+  __shared__ Sel2 s_z;
   const int f = blockIdx.x, t = threadIdx.x;
   const double* __restrict__ base = ring + (int64_t)f * cap;
   for (int j = t; j < S; j += 256) {
@@ -136,9 +178,10 @@ __global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__
   const double pr = (double)k_from_top / (double)n;
   const double r0 = pr * (double)S, d = 5.0 * sqrt((double)S * pr * (1.0 - pr)) + 2.0;
   const long long rh = (long long)floor(r0 - d), rl = (long long)ceil(r0 + d);
-  unsigned long long hik = gpud_f64_key(0x7ff0000000000000ull), lok = gpud_f64_key(0xfff0000000000000ull);   // +inf, -inf
-  if (rh >= 1) hik = block_select_smem(s_keys, S, (int)rh, s_hist, s_bc);
-  if (rl <= S) lok = block_select_smem(s_keys, S, (int)rl, s_hist, s_bc);
+  unsigned long long hik, lok;
+  block_select2_smem(s_keys, S, (int)max(1ll, min((long long)S, rh)), (int)max(1ll, min((long long)S, rl)), s_hist, &s_z, s_red, &hik, &lok);
+  if (rh < 1) hik = gpud_f64_key(0x7ff0000000000000ull);      // nothing can be trusted to lie above: +inf
+  if (rl > S) lok = gpud_f64_key(0xfff0000000000000ull);      // -inf
   if (t == 0) {
     piv[2 * f] = __longlong_as_double((long long)gpud_key_f64bits(lok));
     piv[2 * f + 1] = __longlong_as_double((long long)gpud_key_f64bits(hik));
@@ -154,12 +197,13 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
                                                        int q_num, int q_den, int sampled, const double* __restrict__ piv, const unsigned* __restrict__ fill,
                                                        const uint4* __restrict__ w_cls, const unsigned long long* __restrict__ lists, unsigned list_cap,
                                                        double* __restrict__ out /*[5][F]*/, uint32_t* __restrict__ out_nover, SelState* __restrict__ st,
-                                                       unsigned* __restrict__ n_open) {
+                                                       unsigned* __restrict__ n_open, int* __restrict__ open_ids) {
   __shared__ unsigned long long s_red[8][6];
   __shared__ double s_sum[8];
   __shared__ unsigned s_hist[kBins];
   __shared__ unsigned long long s_prefix, s_kk;
   __shared__ int s_nbits, s_mode;
+  __shared__ unsigned s_part[256];
   const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   unsigned long long kmin = ~0ull, kmax = 0ull, c_abv = 0, c_eh = 0, c_el = 0, nov = 0;
   double sum = 0.0;
@@ -204,6 +248,7 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
     s.pad = 0;
     const unsigned long long diff = kmin ^ kmax;
     int mode = 0;                      // 0: left to the histogram path, 1: answered, 2: select from the list
+    int why = GPUD_RANGE_OPEN_SHORT;   // why the field stays open (gpud_ring_range_stats)
     if (diff == 0ull) {                // a constant field: every key is the answer
       s.prefix = kmax; s.nbits = 64; s.done = 1; s.ans = kmax;
       mode = 1;
@@ -213,14 +258,17 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
       s.prefix = cp ? (kmax >> (64 - cp)) : 0ull;
       s.done = 0;
       s.ans = 0ull;
-      if (sampled && kmax <= gpud_f64_key(0x7ff0000000000000ull)) {      // a +NaN would have been classified as "below": not trusted
+      if (sampled && kmax > gpud_f64_key(0x7ff0000000000000ull)) why = GPUD_RANGE_OPEN_NAN;   // a +NaN was classified as "below"
+      if (sampled && kmax <= gpud_f64_key(0x7ff0000000000000ull)) {
         const unsigned long long lok = gpud_f64_key((unsigned long long)__double_as_longlong(piv[2 * f]));
         const unsigned long long hik = gpud_f64_key((unsigned long long)__double_as_longlong(piv[2 * f + 1]));
         const unsigned long long inside = fill[f];
         const unsigned long long k = s.kk;
+        why = !(lok <= hik) ? GPUD_RANGE_OPEN_PIVOTS : (k <= c_abv ? GPUD_RANGE_OPEN_ABOVE : GPUD_RANGE_OPEN_BELOW);
         if (lok <= hik && k > c_abv) {
           if (k <= c_abv + c_eh) { s.done = 1; s.ans = hik; mode = 1; }
           else if (k <= c_abv + c_eh + inside) {
+            why = GPUD_RANGE_OPEN_OVERFLOW;
             if (inside <= (unsigned long long)list_cap) {
               mode = 2;
               const unsigned long long d2 = lok ^ hik;     // every listed key lies between the pivots: skip their common bits
@@ -234,10 +282,11 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
       }
     }
     if (s.done) { s.nbits = 64; s.prefix = s.ans; }
+    s.pad = mode == 0 ? why : 0;
     st[f] = s;
     s_mode = mode;
     if (mode == 1) out[4 * F + f] = __longlong_as_double((long long)gpud_key_f64bits(s.ans));
-    if (mode == 0) atomicAdd(n_open, 1u);
+    if (mode == 0) open_ids[atomicAdd(n_open, 1u)] = f;
   }
   __syncthreads();
   if (s_mode != 2) return;
@@ -254,11 +303,27 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
       if (nbits == 0 || (key >> (64 - nbits)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & (unsigned)(nb - 1)], 1u);
     }
     __syncthreads();
-    if (t == 0) {
-      unsigned long long acc = 0, kk = s_kk;
-      int bin = nb - 1;
-      while (bin > 0 && acc + s_hist[bin] < kk) { acc += s_hist[bin]; --bin; }
-      s_prefix = (nbits ? (prefix << d) : 0ull) | (unsigned long long)bin;
+    // thread t owns bins nb-1-8t .. nb-8-8t (from the top); block-wide exclusive scan of the per-thread sums finds the owner
+    unsigned loc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const int b = nb - 1 - 8 * t - j; if (b >= 0) loc += s_hist[b]; }
+    unsigned incl = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_part[wid] = incl;
+    __syncthreads();
+    unsigned before = incl - loc;
+    for (int w = 0; w < wid; ++w) before += s_part[w];
+    const unsigned long long kk = s_kk;
+    __syncthreads();                                   // everyone has read s_kk / s_part before the owner rewrites them
+    if ((unsigned long long)before < kk && kk <= (unsigned long long)before + loc) {
+      unsigned acc = before;
+      int b = nb - 1 - 8 * t;
+      while ((unsigned long long)acc + s_hist[b] < kk) { acc += s_hist[b]; --b; }
+      s_prefix = (nbits ? (prefix << d) : 0ull) | (unsigned long long)b;
       s_nbits = nbits + d;
       s_kk = kk - acc;
     }
@@ -274,9 +339,9 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
 
 // grid (blocks_per_field, F): histogram of the next digit over the keys that match the field's prefix
 __global__ void __launch_bounds__(256) k_sel_hist(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n,
-                                                   const SelState* __restrict__ st, unsigned* __restrict__ hist) {
+                                                   const SelState* __restrict__ st, unsigned* __restrict__ hist, const int* __restrict__ ids) {
   __shared__ unsigned s_hist[kBins];
-  const int f = blockIdx.y;
+  const int f = ids ? ids[blockIdx.y] : blockIdx.y;
   const SelState s = st[f];
   if (s.done || s.cnt <= (unsigned long long)kCollectMax) return;   // block-uniform: nothing left to narrow for this field
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) s_hist[i] = 0;
@@ -291,18 +356,18 @@ __global__ void __launch_bounds__(256) k_sel_hist(const double* __restrict__ rin
   });
   __syncthreads();
   for (int i = threadIdx.x; i < kBins; i += blockDim.x)
-    if (s_hist[i]) atomicAdd(&hist[(int64_t)f * kBins + i], s_hist[i]);
+    if (s_hist[i]) atomicAdd(&hist[(int64_t)blockIdx.y * kBins + i], s_hist[i]);
 }
 
 // one block per field: walk the digit histogram from the top, fix the next digit of the k-th largest key
-__global__ void __launch_bounds__(256) k_sel_pick(unsigned* __restrict__ hist, SelState* __restrict__ st) {
+__global__ void __launch_bounds__(256) k_sel_pick(unsigned* __restrict__ hist, SelState* __restrict__ st, const int* __restrict__ ids) {
   __shared__ unsigned s[kBins];
   __shared__ unsigned s_sum[256];
-  const int f = blockIdx.x, t = threadIdx.x;
+  const int f = ids ? ids[blockIdx.x] : blockIdx.x, t = threadIdx.x;
   SelState cur = st[f];
   if (cur.done || cur.cnt <= (unsigned long long)kCollectMax) return;
   const int d = min(kDigit, 64 - cur.nbits), nb = 1 << d;
-  for (int i = t; i < kBins; i += 256) { s[i] = i < nb ? hist[(int64_t)f * kBins + i] : 0; hist[(int64_t)f * kBins + i] = 0; }
+  for (int i = t; i < kBins; i += 256) { s[i] = i < nb ? hist[(int64_t)blockIdx.x * kBins + i] : 0; hist[(int64_t)blockIdx.x * kBins + i] = 0; }
   __syncthreads();
   unsigned loc = 0;                    // thread t owns bins [8t, 8t+8) counted from the TOP
   for (int j = 8 * t; j < 8 * t + 8; ++j) if (j < nb) loc += s[nb - 1 - j];
@@ -326,14 +391,14 @@ __global__ void __launch_bounds__(256) k_sel_pick(unsigned* __restrict__ hist, S
 
 // grid (blocks_per_field, F): compact the keys that still match into the field's candidate list (<= kCollectMax of them)
 __global__ void __launch_bounds__(256) k_sel_collect(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n,
-                                                      SelState* __restrict__ st, unsigned long long* __restrict__ lists) {
-  const int f = blockIdx.y;
+                                                      SelState* __restrict__ st, unsigned long long* __restrict__ lists, const int* __restrict__ ids) {
+  const int f = ids ? ids[blockIdx.y] : blockIdx.y;
   const SelState s = st[f];
   if (s.done) return;
   const int64_t per = (((n + gridDim.x - 1) / gridDim.x) + 1) & ~(int64_t)1;
   const int64_t b = min(n, (int64_t)blockIdx.x * per), e = min(n, b + per);
   const double* __restrict__ base = ring + (int64_t)f * cap;
-  unsigned long long* __restrict__ list = lists + (int64_t)f * kCollectMax;
+  unsigned long long* __restrict__ list = lists + (int64_t)blockIdx.y * kCollectMax;
   unsigned* fill = &st[f].collected;
   for_each_key(base, cap, start, b, e, [&](unsigned long long key) {
     if (key_matches(key, s)) {
@@ -346,14 +411,14 @@ __global__ void __launch_bounds__(256) k_sel_collect(const double* __restrict__ 
 // one block per field: k-th largest of the (<= kCollectMax) collected keys, remaining bits fixed one at a time;
 // every thread keeps its 32 keys in registers, the per-bit counts meet in shared memory
 __global__ void __launch_bounds__(256) k_sel_final(const SelState* __restrict__ st, const unsigned long long* __restrict__ lists, int F,
-                                                    double* __restrict__ out) {
+                                                    double* __restrict__ out, const int* __restrict__ ids) {
   __shared__ unsigned s_cnt[8];
-  const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int f = ids ? ids[blockIdx.x] : blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const SelState s = st[f];
   unsigned long long ans = s.ans;
   if (!s.done) {
     const unsigned n = (unsigned)min((unsigned long long)kCollectMax, (unsigned long long)s.collected);
-    const unsigned long long* __restrict__ list = lists + (int64_t)f * kCollectMax;
+    const unsigned long long* __restrict__ list = lists + (int64_t)blockIdx.x * kCollectMax;
     unsigned long long key[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) { const unsigned idx = (unsigned)i * 256u + (unsigned)t; key[i] = idx < n ? list[idx] : 0ull; }   // 0 never matches a set bit
@@ -394,12 +459,13 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   unsigned* d_hist = nullptr;          // histogram path scratch, allocated only when a field needs it
   SelState* d_st = nullptr;
   unsigned long long* d_lists = nullptr;
-  unsigned* d_open = nullptr;
+  unsigned* d_open = nullptr;          // [0] = number of fields left open by k_range_finish, [1..] = their ids
   unsigned h_open = 0;
+  int reasons[GPUD_RANGE_N_OPEN_REASONS] = {0};
   cudaError_t e = cudaMallocAsync(&d_out, 5 * v.F * sizeof(double), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nover, v.F * sizeof(uint32_t), v.stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_st, v.F * sizeof(SelState), v.stream);
-  if (e == cudaSuccess) e = cudaMallocAsync(&d_open, sizeof(unsigned), v.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_open, (1 + (size_t)v.F) * sizeof(unsigned), v.stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_open, 0, sizeof(unsigned), v.stream);
   if (e == cudaSuccess) e = cudaEventRecord(v.ev[0], v.stream);
   if (e == cudaSuccess && v.sampled) {
@@ -418,39 +484,55 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
   }
   if (e == cudaSuccess) {
     k_range_finish<<<v.F, 256, 0, v.stream>>>(v.F, v.nw, v.Wp, v.n, v.w_min, v.w_max, v.w_mean, v.w_ema, v.w_nover, v.q_num, v.q_den, v.sampled, v.piv, v.fill,
-                                              v.w_cls, v.lists, v.list_cap, d_out, d_nover, d_st, d_open);
+                                              v.w_cls, v.lists, v.list_cap, d_out, d_nover, d_st, d_open, reinterpret_cast<int*>(d_open + 1));
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(v.ev[2], v.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&h_open, d_open, sizeof(unsigned), cudaMemcpyDeviceToHost, v.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
-  if (e == cudaSuccess && h_open > 0) {
-    // histogram path for the fields still open: every field of a short range, or the rare field the sampled pass could not settle
-    e = cudaMallocAsync(&d_hist, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_lists, (size_t)v.F * kCollectMax * sizeof(unsigned long long), v.stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_hist, 0, (size_t)v.F * kBins * sizeof(unsigned), v.stream);
+  if (e == cudaSuccess && v.sampled) {   // a short range leaves every non-constant field to the radix select: no need to ask
+    e = cudaMemcpyAsync(&h_open, d_open, sizeof(unsigned), cudaMemcpyDeviceToHost, v.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
+  }
+  if (e == cudaSuccess && (h_open > 0 || !v.sampled)) {
+    // radix select for the fields still open: every non-constant field of a short range, or the rare field the sampled pass
+    // could not settle.  The grid covers only the open fields, with enough blocks each to fill the machine.
+    const int* ids = v.sampled ? reinterpret_cast<const int*>(d_open + 1) : nullptr;
+    const int n_sel = v.sampled ? (int)h_open : v.F;
+    if (v.sampled) {
+      std::vector<SelState> h_st(v.F);
+      e = cudaMemcpyAsync(h_st.data(), d_st, v.F * sizeof(SelState), cudaMemcpyDeviceToHost, v.stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
+      for (const SelState& q : h_st) if (q.pad > 0 && q.pad < GPUD_RANGE_N_OPEN_REASONS) ++reasons[q.pad];
+    }
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_hist, (size_t)n_sel * kBins * sizeof(unsigned), v.stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_lists, (size_t)n_sel * kCollectMax * sizeof(unsigned long long), v.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_hist, 0, (size_t)n_sel * kBins * sizeof(unsigned), v.stream);
     if (e == cudaSuccess) {
       // blocks per field: enough CTAs to fill the machine a few times over, each streaming >= 16 Ki keys
-      const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 8 * v.sm_count / v.F + 1)));
+      const int bpf = (int)std::max<int64_t>(1, std::min<int64_t>((v.n + 16383) / 16384, std::max(1, 8 * v.sm_count / n_sel + 1)));
       if (v.n > kCollectMax) {
         for (int pass = 0; pass < kMaxHistPasses; ++pass) {          // later passes exit at once for fields that are already narrow
-          k_sel_hist<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_hist);
-          k_sel_pick<<<v.F, 256, 0, v.stream>>>(d_hist, d_st);
+          k_sel_hist<<<dim3(bpf, n_sel), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_hist, ids);
+          k_sel_pick<<<n_sel, 256, 0, v.stream>>>(d_hist, d_st, ids);
         }
       }
-      k_sel_collect<<<dim3(bpf, v.F), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_lists);
-      k_sel_final<<<v.F, 256, 0, v.stream>>>(d_st, d_lists, v.F, d_out);
+      k_sel_collect<<<dim3(bpf, n_sel), 256, 0, v.stream>>>(v.ring, v.cap, v.start, v.n, d_st, d_lists, ids);
+      k_sel_final<<<n_sel, 256, 0, v.stream>>>(d_st, d_lists, v.F, d_out, ids);
       e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out_f64 + 4 * (size_t)v.F, d_out + 4 * (size_t)v.F, v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
+    if (e == cudaSuccess && !v.sampled) {
+      e = cudaMemcpyAsync(out_f64, d_out, 5 * v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(out_n_over, d_nover, v.F * sizeof(uint32_t), cudaMemcpyDeviceToHost, v.stream);
+    } else if (e == cudaSuccess) {
+      e = cudaMemcpyAsync(out_f64 + 4 * (size_t)v.F, d_out + 4 * (size_t)v.F, v.F * sizeof(double), cudaMemcpyDeviceToHost, v.stream);
+    }
     if (d_hist) cudaFreeAsync(d_hist, v.stream);
     if (d_lists) cudaFreeAsync(d_lists, v.stream);
   }
   cudaFreeAsync(d_out, v.stream); cudaFreeAsync(d_nover, v.stream); cudaFreeAsync(d_st, v.stream); cudaFreeAsync(d_open, v.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(v.stream);
   if (e != cudaSuccess) return gpud_fail(ctx, GPUD_E_CUDA, "reduce_range: %s", cudaGetErrorString(e));
-  gpud_ring_range_note(ring, v.sampled != 0, h_open);
+  gpud_ring_range_note(ring, v.sampled != 0, h_open, reasons);
   return GPUD_OK;
 }

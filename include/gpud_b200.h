@@ -154,6 +154,11 @@ typedef struct {
   uint32_t clock_events_supported, ecc_read_mask;
 } gpud_poll_counters;
 int32_t gpud_poller_counters(gpud_poller* poller, gpud_poll_counters* out);
+/* The fused window reduce runs a persistent grid that fills every CTA slot of the GPU (2 per SM, the whole register file), so a
+ * kernel launched meanwhile on another stream - the fabric record's pack / all-gather / verdict - could only start by delaying one of
+ * the grid's CTAs, which then finishes a whole kernel-time late.  Leaving n_ctas slots out of the grid (work is divided over whatever
+ * grid is launched; each slot costs 1/296 of the throughput) lets such kernels run concurrently.  Default 0. */
+int32_t gpud_ring_set_cta_reserve(gpud_ring* ring, int32_t n_ctas);
 int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
 /* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
 int32_t gpud_ring_reduce(gpud_ring* ring);
@@ -170,9 +175,17 @@ int32_t gpud_ring_result_ptr(gpud_ring* ring, int32_t op, void** dev_ptr);
  * the window pass), shorter ones and any field the sample misjudged use a multi-pass radix select.  out_f64 is [5][F]
  * (MIN,MAX,MEAN,EMA,P99), n_over [F].  Synchronous. */
 int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, double* out_f64, uint32_t* out_n_over);
-/* Device time of the last gpud_ring_reduce_range that took the single-pass route: the fused range pass alone and the whole device
- * side (pivots + pass + EMA carry + finish), and how many fields had to be re-done by the radix select (normally 0). */
-int32_t gpud_ring_range_stats(gpud_ring* ring, float* pass_ms, float* total_ms, int32_t* fields_by_histogram);
+/* Device time of the last gpud_ring_reduce_range that took the single-pass route: pivots + fused range pass + EMA carry, and the
+ * whole device side (+ finish), and how many fields had to be re-done by the radix select (normally 0) with the reason for each
+ * (reasons[GPUD_RANGE_OPEN_*] counts fields; may be NULL). */
+enum { GPUD_RANGE_OPEN_SHORT = 1,    /* the range is shorter than the single-pass threshold          */
+       GPUD_RANGE_OPEN_NAN = 2,      /* the field holds a +NaN (ordered above +inf, SPEC.md)          */
+       GPUD_RANGE_OPEN_PIVOTS = 3,   /* the sample produced NaN pivots                                */
+       GPUD_RANGE_OPEN_ABOVE = 4,    /* the wanted rank lies above the upper pivot                    */
+       GPUD_RANGE_OPEN_BELOW = 5,    /* ... below the lower pivot                                     */
+       GPUD_RANGE_OPEN_OVERFLOW = 6, /* more keys between the pivots than the list holds              */
+       GPUD_RANGE_N_OPEN_REASONS = 7 };
+int32_t gpud_ring_range_stats(gpud_ring* ring, float* pass_ms, float* total_ms, int32_t* fields_by_histogram, int32_t* reasons);
 
 /* ------------------------------------------------------------------------------------------------
  * kmsg Xid / SXid scan + classification.

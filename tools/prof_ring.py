@@ -56,4 +56,4 @@ if len(sys.argv) > 3 and sys.argv[3] == "range":
         out = ring.reduce_range(0)
         ts.append(time.perf_counter() - t0)
         st.append(ring.range_stats())
-    print("reduce_range(whole ring) host ms:", [round(t * 1e3, 3) for t in ts], "device (pass ms, total ms, fields redone):", st, "p99[0..3]", out["p99"][:3])
+    print("reduce_range(whole ring) host ms:", [round(t * 1e3, 3) for t in ts], "device (pass ms, total ms, fields redone):", st, "p99[0..3]", out["p99"][:3], "open reasons:", ring.range_open_reasons)
