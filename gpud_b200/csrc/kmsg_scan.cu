@@ -29,8 +29,8 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kChunk = 512;                 // bytes per warp step
-constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid ("
-constexpr unsigned long long kFamB = 2ull;  // "NVRM:\s+GPU " / "NVRM:\s+The NVIDIA GPU "
+constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid (": the candidate is the offset of "NVRM"
+constexpr unsigned long long kFamB = 2ull;  // "fallen off the bus" (every R3 / R4 match holds it): the candidate is the offset of "fall"
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
 // families >= 4: the anchor literals of the extra line matchers (GPUD_SCAN_EXT_MATCHERS), index into kExtLit[]
 constexpr int kPendingExtended = -77;         // event_type of an extended hit whose table searches run in k_classify_ext_coop
@@ -38,7 +38,7 @@ constexpr int kFamShift = 58;               // candidate word = byte offset | fa
 constexpr int kExtFam0 = 4, kNumFam = 25;
 constexpr int kModeMask = 0xff;
 #ifndef GPUD_MATCH_LANES
-#define GPUD_MATCH_LANES 16
+#define GPUD_MATCH_LANES 8
 #endif
 constexpr unsigned kMatchLanes = GPUD_MATCH_LANES;        // candidates per warp in k_scan_match
 
@@ -80,7 +80,12 @@ __device__ unsigned long long nvrm_family(const ScanBuf& b, int64_t a, int64_t e
 // compares): no false positives, so the verification path below only runs where an anchor really starts.  Separators
 // are counted with an exact zero-byte bit trick.  About 5 integer instructions per byte, no shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned kNVRM = 0x4d52564eu;   // "NVRM" little-endian
+// Anchor words.  Every R1 / R2 match contains "NVRM: Xid (", every R3 / R4 match "fallen off the bus", every R5 / R6 match
+// "SXid" (xid/kmsg.go:22-43, sxid/kmsg.go:17-20).  The filter looks for the RARE four bytes of each - "Xid ", "fall", "SXid" -
+// and walks back to "NVRM: " only from an "Xid " window: the driver's ordinary "NVRM: ..." chatter never reaches the
+// verification path (it used to be 150 of the 251 warp-instructions per 512-byte chunk).
+constexpr unsigned kXidSp = 0x20646958u;  // "Xid " little-endian
+constexpr unsigned kFall = 0x6c6c6166u;   // "fall"
 constexpr unsigned kSXid = 0x64695853u;   // "SXid"
 
 // bit 7 of every byte of the result is set exactly where the byte of x is zero
@@ -94,15 +99,28 @@ __device__ int64_t find_byte(const ScanBuf& b, int64_t from, int64_t to, unsigne
   const unsigned pat = c * 0x01010101u;
   if ((((uintptr_t)b.p) & 15) == 0) {
     int64_t blk = from & ~(int64_t)15;
-    for (; blk < to && blk + 16 <= b.len; blk += 16) {
+    // the block that holds `from`: bytes before it are masked off
+    if (blk + 16 <= b.len) {
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(b.p + blk));
-      const unsigned z[4] = {zero_bytes(q.x ^ pat), zero_bytes(q.y ^ pat), zero_bytes(q.z ^ pat), zero_bytes(q.w ^ pat)};
+      unsigned z[4] = {zero_bytes(q.x ^ pat), zero_bytes(q.y ^ pat), zero_bytes(q.z ^ pat), zero_bytes(q.w ^ pat)};
+      const int skip = (int)(from - blk);                    // 0..15 leading bytes to ignore
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
-        unsigned zz = z[w];
-        const int64_t w0 = blk + 4 * w;
-        if (w0 < from) { const int sh = (int)(from - w0); zz = sh >= 4 ? 0u : (zz & (0xffffffffu << (8 * sh))); }   // bytes before `from`
-        if (zz) { const int64_t p = w0 + ((__ffs(zz) - 1) >> 3); return p < to ? p : to; }
+        const int sh = skip - 4 * w;
+        if (sh >= 4) z[w] = 0u;
+        else if (sh > 0) z[w] &= 0xffffffffu << (8 * sh);
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (z[w]) { const int64_t p = blk + 4 * w + ((__ffs(z[w]) - 1) >> 3); return p < to ? p : to; }
+      blk += 16;
+      // whole blocks: one OR decides "no hit in these 16 bytes", which is the common case on every step of a line walk
+      for (; blk < to && blk + 16 <= b.len; blk += 16) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(b.p + blk));
+        const unsigned z0 = zero_bytes(r.x ^ pat), z1 = zero_bytes(r.y ^ pat), z2 = zero_bytes(r.z ^ pat), z3 = zero_bytes(r.w ^ pat);
+        if ((z0 | z1 | z2 | z3) == 0u) continue;
+        const int64_t p = z0 ? blk + ((__ffs(z0) - 1) >> 3) : (z1 ? blk + 4 + ((__ffs(z1) - 1) >> 3) : (z2 ? blk + 8 + ((__ffs(z2) - 1) >> 3) : blk + 12 + ((__ffs(z3) - 1) >> 3)));
+        return p < to ? p : to;
       }
     }
     for (int64_t i = from > blk ? from : blk; i < to; ++i) if (__ldg(b.p + i) == c) return i;   // the block that crosses the buffer end
@@ -151,23 +169,6 @@ __device__ int64_t rfind_byte(const ScanBuf& b, int64_t lo, int64_t from, unsign
 }
 
 
-// nvrm_family for the R3/R4 shapes, by the whole warp: the 32 bytes after "NVRM:" are fetched one per lane, the
-// whitespace run ends at the first non-\s ballot bit, and the two literals are compared lane-wise against it.
-__device__ const char kLitGPU[] = "GPU ";
-__device__ const char kLitTheGPU[] = "The NVIDIA GPU ";
-__device__ __forceinline__ unsigned long long nvrm_family_coop(const ScanBuf& b, int64_t a, int lane) {
-  const int cb = ld8(b, a + 5 + lane);
-  const unsigned nws = __ballot_sync(kFull, !is_ws(cb));
-  if (nws == 0u) return nvrm_family(b, a, b.len);            // more than 32 whitespace bytes: sequential path
-  const int q = __ffs(nws) - 1;
-  if (q == 0) return 0;                                       // \s+ needs at least one
-  if (q + 15 > 32) return nvrm_family(b, a, b.len);
-  const int k = lane - q;
-  const unsigned bad1 = __ballot_sync(kFull, k >= 0 && k < 4 && cb != (int)(unsigned char)__ldg(kLitGPU + (k < 0 ? 0 : (k > 3 ? 3 : k))));
-  const unsigned bad2 = __ballot_sync(kFull, k >= 0 && k < 15 && cb != (int)(unsigned char)__ldg(kLitTheGPU + (k < 0 ? 0 : (k > 14 ? 14 : k))));
-  return (bad1 == 0u || bad2 == 0u) ? kFamB : 0ull;
-}
-
 // Extra line matchers (GPUD_SCAN_EXT_MATCHERS).  Every pattern contains a literal that each of its matches must contain:
 // the ANCHOR.  The filter looks the four bytes of every window up in a 32-slot perfect hash of the anchors' first words
 // (one multiply, one shift, one LDS, one compare per window - independent of the number of patterns), the warp verifies
@@ -196,14 +197,14 @@ __device__ __forceinline__ unsigned long long nvrm_family_coop(const ScanBuf& b,
 //   24   "Killed process "    `Killed process ([0-9]+) \((.+)\)`     memory/kmsg_matcher.go:152 } events
 struct ExtLit { unsigned char len; char text[63]; };
 #define GPUD_EXT_LITS \
-  {0, ""}, {4, "NVRM"}, {0, ""}, {4, "SXid"}, {11, "segfault at"}, {59, "ERROR detected invalid context, skipping further processing"}, \
+  {0, ""}, {4, "Xid "}, {18, "fallen off the bus"}, {4, "SXid"}, {11, "segfault at"}, {59, "ERROR detected invalid context, skipping further processing"}, \
   {46, "Detected insufficient power on the PCIe slot ("}, {17, "Port module event"}, {16, "mlx5_cmd_out_err"}, {5, "task "}, \
   {18, "soft lockup - CPU#"}, {20, "VFS: file-max limit "}, {7, "md/raid"}, {31, "Remounting filesystem read-only"}, {10, "block nvme"}, \
   {9, "nvme nvme"}, {38, "attempt to access beyond end of device"}, {24, "Buffer I/O error on dev "}, {34, "I/O error while writing superblock"}, \
   {7, "Kernel "}, {5, "CPU: "}, {19, "invoked oom-killer:"}, {20, "oom-kill:constraint="}, {8, "Task in "}, {15, "Killed process "}
 __device__ const ExtLit kExtLit[kNumFam] = {GPUD_EXT_LITS};
 static const ExtLit kExtLitHost[kNumFam] = {GPUD_EXT_LITS};
-constexpr unsigned kHashMul = 0x9e384155u;   // (word * kHashMul) >> 27 is injective on the 23 anchor words (checked at start-up)
+constexpr unsigned kHashMul = 0x0d4973adu;   // (word * kHashMul) >> 27 is injective on the 24 anchor words (checked at start-up)
 struct ExtTab { unsigned word[32]; unsigned char fam[32]; };
 __device__ __forceinline__ unsigned ext_slot(unsigned x) { return (x * kHashMul) >> 27; }
 
@@ -220,7 +221,7 @@ __device__ __forceinline__ bool coop_lit(const ScanBuf& b, int64_t a, const char
 
 template <int MODE, bool EXT>
 __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __restrict__ chunk_sep, unsigned long long* cands,
-                                                      unsigned long long* n_cand, unsigned long long cand_cap, const ExtTab tab) {
+                                                      unsigned long long* n_cand, unsigned long long cand_cap, unsigned long long* fam_cnt, const ExtTab tab) {
   __shared__ unsigned s_word[32];
   __shared__ unsigned char s_fam[32];
   if (EXT) {
@@ -273,8 +274,10 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const unsigned x1 = __funnelshift_r(w[k], w[k + 1], 8), x2 = __funnelshift_r(w[k], w[k + 1], 16), x3 = __funnelshift_r(w[k], w[k + 1], 24);
-        if (EXT) hit = hit || s_word[ext_slot(w[k])] == w[k] || s_word[ext_slot(x1)] == x1 || s_word[ext_slot(x2)] == x2 || s_word[ext_slot(x3)] == x3;
-        else hit = hit || w[k] == kNVRM || w[k] == kSXid || x1 == kNVRM || x1 == kSXid || x2 == kNVRM || x2 == kSXid || x3 == kNVRM || x3 == kSXid;
+        // plain `|` on purpose: `||` compiles to one short-circuit branch per window (16 branches per lane and chunk)
+        if (EXT) hit = hit | (s_word[ext_slot(w[k])] == w[k]) | (s_word[ext_slot(x1)] == x1) | (s_word[ext_slot(x2)] == x2) | (s_word[ext_slot(x3)] == x3);
+        else hit = hit | (w[k] == kXidSp) | (w[k] == kSXid) | (w[k] == kFall) | (x1 == kXidSp) | (x1 == kSXid) | (x1 == kFall) | (x2 == kXidSp) | (x2 == kSXid) |
+                   (x2 == kFall) | (x3 == kXidSp) | (x3 == kSXid) | (x3 == kFall);
         unsigned z = zero_bytes(w[k] ^ 0x0a0a0a0au);                           // '\n'
         if (MODE == GPUD_SCAN_RAW_KMSG) z &= ~zero_bytes(x1 ^ 0x20202020u);     // ... not followed by ' ' (continuation line)
         sepbits |= z >> (k + 4);                                                // bit 7 of each byte -> bit 3-k: four words share one POPC
@@ -298,35 +301,31 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
         const unsigned x = __funnelshift_r(lo, hi, 8 * (k16 & 3));
         unsigned my_fam = 0;
         if (EXT) { if (lane < 16 && s_word[ext_slot(x)] == x) my_fam = s_fam[ext_slot(x)]; }
-        else if (lane < 16) my_fam = x == kNVRM ? (unsigned)kFamX : (x == kSXid ? (unsigned)kFamS : 0u);
+        else if (lane < 16) my_fam = x == kXidSp ? (unsigned)kFamX : (x == kSXid ? (unsigned)kFamS : (x == kFall ? (unsigned)kFamB : 0u));
         unsigned anchors = __ballot_sync(kFull, my_fam != 0u);
         const int64_t off0 = chunk * kChunk + (int64_t)src * 16;
         while (anchors) {
           const int k = __ffs(anchors) - 1;
           anchors &= anchors - 1;
-          const int64_t a = off0 + k;
+          int64_t a = off0 + k;
           unsigned long long fam = __shfl_sync(kFull, my_fam, k);
           if (fam == kFamX) {
-            // ": Xid (" must follow "NVRM": lanes 0..6 fetch one byte each (one 32-byte sector) and vote
-            const int cb = lane < 7 ? ld8(b, a + 4 + lane) : 0;
-            const unsigned long long pat = 0x2820646958203aull;            // bytes ':',' ','X','i','d',' ','(' little-endian
+            // "Xid " at a: "NVRM: " must stand right before it and '(' right after (lanes 0..5 and lane 6 fetch one byte each)
+            const unsigned long long pat = 0x28203a4d52564eull;            // 'N','V','R','M',':',' ','(' little-endian
+            const int cb = lane < 6 ? ld8(b, a - 6 + lane) : (lane == 6 ? ld8(b, a + 4) : 0);
             const int want = (int)((pat >> (8 * (lane < 7 ? lane : 0))) & 0xff);
             const unsigned bad = __ballot_sync(kFull, lane < 7 && cb != want);
-            if (bad == 0u) fam = kFamX;
-            else if (bad & 1u) fam = 0;                                    // not even "NVRM:"
-            else if (!is_ws(__shfl_sync(kFull, cb, 1))) fam = 0;          // R3/R4 need \s+ right after the colon
-            else {
-              // most "NVRM: ..." lines are neither: after one whitespace byte anything but more whitespace, 'G' or 'T' settles it
-              const int c2 = __shfl_sync(kFull, cb, 2);
-              if (!is_ws(c2) && c2 != 'G' && c2 != 'T') fam = 0;
-              else fam = nvrm_family_coop(b, a, lane);                    // whitespace run, then "GPU " / "The NVIDIA GPU "
-            }
+            if (bad != 0u) fam = 0;
+            a -= 6;                                                        // the candidate is the "NVRM" the automata start at
+          } else if (fam == kFamB) {
+            if (!coop_lit(b, a, kExtLit[kFamB].text, kExtLit[kFamB].len, lane)) fam = 0;     // "fallen off the bus"
           } else if (EXT && fam >= (unsigned long long)kExtFam0) {
             if (!coop_lit(b, a, kExtLit[fam].text, kExtLit[fam].len, lane)) fam = 0;
           }
           if (fam && lane == 0) {
             const unsigned long long slot = atomicAdd(n_cand, 1ull);
             if (slot < cand_cap) cands[slot] = (unsigned long long)a | (fam << kFamShift);
+            atomicAdd(fam_cnt + fam, 1ull);                                  // the family histogram of the counting sort (candidates are rare)
           }
         }
       }
@@ -341,8 +340,11 @@ __global__ void __launch_bounds__(256) k_scan_filter(ScanBuf b, uint32_t* __rest
 // CTA (tile-local exclusive prefix + tile total), then one CTA scans the tile totals.  The match kernel adds the two.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_scan_prefix_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ local, int64_t n,
-                                                             unsigned long long* __restrict__ tile_total) {
+                                                             unsigned long long* __restrict__ tile_total, int64_t n_tiles, unsigned long long* total,
+                                                             unsigned long long* ticket) {
   __shared__ unsigned s_w[32];
+  __shared__ unsigned long long s[1024];
+  __shared__ bool s_last;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int64_t i = (int64_t)blockIdx.x * 1024 + t;
   const unsigned v = i < n ? in[i] : 0u;
@@ -360,26 +362,29 @@ __global__ void __launch_bounds__(1024) k_scan_prefix_tiles(const uint32_t* __re
   __syncthreads();
   const unsigned incl = x + (wid ? s_w[wid - 1] : 0u);
   if (i < n) local[i] = incl - v;
-  if (t == 1023) tile_total[blockIdx.x] = incl;
-}
-__global__ void __launch_bounds__(1024) k_scan_prefix_top(unsigned long long* __restrict__ tile_total, int64_t n_tiles, unsigned long long* total) {
+  if (t == 1023) {
+    tile_total[blockIdx.x] = incl;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1ull) == (unsigned long long)(n_tiles - 1);   // the block that finishes last scans the tile totals
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   // n_tiles = len / 512 KiB: a few hundred for 100 MB; serial chunks per thread + one block scan
-  __shared__ unsigned long long s[1024];
-  const int t = threadIdx.x;
   const int64_t per = (n_tiles + 1023) / 1024;
   const int64_t b0 = t * per, e0 = min(n_tiles, b0 + per);
   unsigned long long acc = 0;
-  for (int64_t i = b0; i < e0; ++i) acc += tile_total[i];
+  for (int64_t k = b0; k < e0; ++k) acc += __ldcg(tile_total + k);
   s[t] = acc;
   __syncthreads();
   for (int o = 1; o < 1024; o <<= 1) {
-    const unsigned long long v = t >= o ? s[t - o] : 0;
+    const unsigned long long u = t >= o ? s[t - o] : 0;
     __syncthreads();
-    s[t] += v;
+    s[t] += u;
     __syncthreads();
   }
   unsigned long long run = s[t] - acc;
-  for (int64_t i = b0; i < e0; ++i) { const unsigned long long v = tile_total[i]; tile_total[i] = run; run += v; }
+  for (int64_t k = b0; k < e0; ++k) { const unsigned long long u = __ldcg(tile_total + k); tile_total[k] = run; run += u; }
   if (t == 1023) *total = s[1023];
 }
 
@@ -1019,33 +1024,35 @@ __device__ __forceinline__ bool is_sep(const ScanBuf& b, int64_t i, int mode) {
 // kernels) puts the same automaton on neighbouring lanes of the match kernel, which otherwise spends most of its issue
 // slots on 3-4 active lanes per instruction.  Only done when the list fits the side buffer; order inside a family is free.
 constexpr int kSortBins = 32;
-__global__ void __launch_bounds__(256) k_cand_count(const unsigned long long* __restrict__ cands, const unsigned long long* __restrict__ n_cand,
-                                                     unsigned long long cand_cap, unsigned long long side_cap, unsigned long long* fam_cnt) {
-  __shared__ unsigned s_cnt[kSortBins];
-  const unsigned long long n = min(*n_cand, cand_cap);
-  if (n > side_cap) return;
-  if (threadIdx.x < kSortBins) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
-    atomicAdd(&s_cnt[(cands[i] >> kFamShift) & (kSortBins - 1)], 1u);
-  __syncthreads();
-  if (threadIdx.x < kSortBins && s_cnt[threadIdx.x]) atomicAdd(&fam_cnt[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
-}
 __global__ void __launch_bounds__(256) k_cand_scatter(const unsigned long long* __restrict__ cands, const unsigned long long* __restrict__ n_cand,
                                                        unsigned long long cand_cap, unsigned long long side_cap, const unsigned long long* __restrict__ fam_cnt,
                                                        unsigned long long* fam_pos, unsigned long long* __restrict__ side) {
   __shared__ unsigned long long s_base[kSortBins];
+  __shared__ unsigned s_cnt[kSortBins];
+  __shared__ unsigned long long s_off[kSortBins];
   const unsigned long long n = min(*n_cand, cand_cap);
   if (n > side_cap) return;
+  // each block owns one contiguous slice: count its families in shared memory, reserve a run per family with ONE global atomic,
+  // then place its candidates (the global cursors used to take one contended atomic per candidate)
+  const unsigned long long per = (n + gridDim.x - 1) / gridDim.x;
+  const unsigned long long b0 = min(n, (unsigned long long)blockIdx.x * per), e0 = min(n, b0 + per);
+  if (threadIdx.x < kSortBins) s_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     unsigned long long acc = 0;
     for (int f = 0; f < kSortBins; ++f) { s_base[f] = acc; acc += fam_cnt[f]; }
   }
   __syncthreads();
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+  for (unsigned long long i = b0 + threadIdx.x; i < e0; i += blockDim.x) atomicAdd(&s_cnt[(cands[i] >> kFamShift) & (kSortBins - 1)], 1u);
+  __syncthreads();
+  if (threadIdx.x < kSortBins) {
+    s_off[threadIdx.x] = s_cnt[threadIdx.x] ? s_base[threadIdx.x] + atomicAdd(&fam_pos[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+    s_cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  for (unsigned long long i = b0 + threadIdx.x; i < e0; i += blockDim.x) {
     const unsigned long long cv = cands[i];
     const int f = (int)((cv >> kFamShift) & (kSortBins - 1));
-    side[s_base[f] + atomicAdd(&fam_pos[f], 1ull)] = cv;
+    side[s_off[f] + atomicAdd(&s_cnt[f], 1u)] = cv;
   }
 }
 
@@ -1129,21 +1136,32 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
       if (slot < hit_cap) hits[slot] = h;
       continue;
     }
-    // only the first anchor of this family group in the unit does the work
+    // One candidate per unit does the work of a family group.  SXid: the unit's first "SXid".  Xid: the unit holds a worker iff it
+    // holds "NVRM: Xid (" (R1 / R2) or "fallen off the bus" (R3 / R4); the first such literal of the unit is the worker, whatever
+    // its kind, and it runs the whole decision procedure from the unit's first relevant "NVRM:" anchor.
     bool first = true;
+    int64_t a0 = a;
     if (fam == kFamS) {
       for (int64_t i = find_byte(b, ms, a, 'S'); i < a && first; i = find_byte(b, i + 1, a, 'S'))
         if (lit_at(b, i, ue, "SXid")) first = false;
     } else {
+      if (fam == kFamX && !lit_at(b, a, ue, "NVRM: Xid (")) continue;          // the filter judged it against the buffer end, not the unit end
+      if (fam == kFamB && !lit_at(b, a, ue, "fallen off the bus")) continue;
       for (int64_t i = find_byte(b, ms, a, 'N'); i < a && first; i = find_byte(b, i + 1, a, 'N'))
-        if (lit_at(b, i, ue, "NVRM:") && nvrm_family(b, i, ue)) first = false;
+        if (lit_at(b, i, ue, "NVRM: Xid (")) first = false;
+      for (int64_t i = find_byte(b, ms, a, 'f'); i < a && first; i = find_byte(b, i + 1, a, 'f'))
+        if (lit_at(b, i, ue, "fallen off the bus")) first = false;
+      if (!first) continue;
+      a0 = -1;                                                                   // the unit's first "NVRM:" an R1-R4 match can start at
+      for (int64_t i = find_byte(b, ms, ue, 'N'); i < ue; i = find_byte(b, i + 1, ue, 'N'))
+        if (lit_at(b, i, ue, "NVRM:") && nvrm_family(b, i, ue)) { a0 = i; break; }
+      if (a0 < 0) continue;
     }
     if (!first) continue;
-    if (fam != kFamS && !nvrm_family(b, a, ue)) continue;   // the filter judged the context against the buffer end, not the unit end
     gpud_xid_hit h;
     memset(&h, 0, sizeof h);
     // every pattern starts with this family's anchor literal and `a` is the unit's first such anchor: start there
-    const bool ok = (fam == kFamS) ? sxid_match_unit(b, a, ue, T, &h) : xid_match_unit(b, a, ue, T, &h);
+    const bool ok = (fam == kFamS) ? sxid_match_unit(b, a, ue, T, &h) : xid_match_unit(b, a0, ue, T, &h);
     if (!ok) continue;
     h.unit_index = 0;                              // filled by k_scan_unit_index (one warp per hit, cooperative count)
     h.unit_offset = us;
@@ -1157,14 +1175,9 @@ __global__ void __launch_bounds__(128) k_scan_match(ScanBuf b, int mode, const u
 
 // Unit number of every hit = separators before its unit start = tile base + chunk-local prefix + separators between the
 // chunk start and the unit start.  One warp per hit: each lane counts 16 bytes of the (at most 512-byte) run.
-__global__ void __launch_bounds__(256) k_scan_unit_index(ScanBuf b, int mode, const uint32_t* __restrict__ chunk_local,
-                                                          const unsigned long long* __restrict__ tile_base, gpud_xid_hit* hits,
-                                                          const unsigned long long* __restrict__ n_hits, unsigned long long hit_cap) {
-  const int lane = threadIdx.x & 31;
-  const unsigned long long n = min(*n_hits, hit_cap);
-  const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-  for (unsigned long long hi = warp_g; hi < n; hi += n_warps) {
+__device__ __forceinline__ void unit_index_of_hit(const ScanBuf& b, int mode, const uint32_t* __restrict__ chunk_local,
+                                                  const unsigned long long* __restrict__ tile_base, gpud_xid_hit* hits, unsigned long long hi, int lane) {
+  {
     const int64_t us = hits[hi].unit_offset;
     const int64_t chunk = us / kChunk, c0 = chunk * kChunk;
     unsigned cnt = 0;
@@ -1179,14 +1192,17 @@ __global__ void __launch_bounds__(256) k_scan_unit_index(ScanBuf b, int mode, co
 // override, sub-code detail, the 94 NVLink rules with their alias lists) are spread over the lanes and the first match in
 // table order is the minimum matching index - the same answer as the sequential loops of classify_extended(), which a
 // single thread of the match kernel spent about as long on as on the whole regex automaton.
-__global__ void __launch_bounds__(256) k_classify_ext_coop(const gpud_tables* __restrict__ T, gpud_xid_hit* hits, const unsigned long long* __restrict__ n_hits,
-                                                            unsigned long long hit_cap) {
+// The same warp first numbers the hit's unit (unit_index_of_hit), so one launch finishes every hit of the scan.
+__global__ void __launch_bounds__(256) k_scan_finish(ScanBuf b, int mode, const uint32_t* __restrict__ chunk_local, const unsigned long long* __restrict__ tile_base,
+                                                      const gpud_tables* __restrict__ T, gpud_xid_hit* hits, const unsigned long long* __restrict__ n_hits,
+                                                      unsigned long long hit_cap) {
   const int lane = threadIdx.x & 31;
   const unsigned long long n = min(*n_hits, hit_cap);
   const unsigned long long warp_g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   for (unsigned long long hi = warp_g; hi < n; hi += n_warps) {
     gpud_xid_hit* h = hits + hi;
+    unit_index_of_hit(b, mode, chunk_local, tile_base, hits, hi, lane);
     if (h->event_type != kPendingExtended) continue;                 // warp-uniform
     const int xid = h->code, sub = h->sub_code;
     const uint32_t st = h->error_status, intr = h->intrinfo;
@@ -1431,30 +1447,23 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
   mode &= kModeMask;
   const int grid = std::max(grid_f, 1);
   const unsigned long long ccap = (unsigned long long)s->cand_cap;
-  if (mode == GPUD_SCAN_LINES && !ext) k_scan_filter<GPUD_SCAN_LINES, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
-  else if (mode == GPUD_SCAN_LINES) k_scan_filter<GPUD_SCAN_LINES, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
-  else if (!ext) k_scan_filter<GPUD_SCAN_RAW_KMSG, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
-  else k_scan_filter<GPUD_SCAN_RAW_KMSG, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, ext_tab());
+  if (mode == GPUD_SCAN_LINES && !ext) k_scan_filter<GPUD_SCAN_LINES, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, s->d_counters + 4, ext_tab());
+  else if (mode == GPUD_SCAN_LINES) k_scan_filter<GPUD_SCAN_LINES, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, s->d_counters + 4, ext_tab());
+  else if (!ext) k_scan_filter<GPUD_SCAN_RAW_KMSG, false><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, s->d_counters + 4, ext_tab());
+  else k_scan_filter<GPUD_SCAN_RAW_KMSG, true><<<grid, 256, 0, st>>>(b, s->d_chunk_sep, s->d_cands, s->d_counters + 0, ccap, s->d_counters + 4, ext_tab());
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[1], st);
-  k_scan_prefix_tiles<<<(unsigned)n_tiles, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_local, n_chunks, s->d_tile_base);
-  GPUD_CUDA(ctx, cudaGetLastError());
-  k_scan_prefix_top<<<1, 1024, 0, st>>>(s->d_tile_base, n_tiles, s->d_counters + 2);
+  k_scan_prefix_tiles<<<(unsigned)n_tiles, 1024, 0, st>>>(s->d_chunk_sep, s->d_chunk_local, n_chunks, s->d_tile_base, n_tiles, s->d_counters + 2, s->d_counters + 3);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[2], st);
   // measured (100 MiB buffers, match step): default matchers 0.193 ms unsorted -> 0.176 ms sorted; 22 families 0.541 -> 0.226 ms
   const unsigned long long side_cap = (unsigned long long)s->side_cap;
-  {
-  k_cand_count<<<64, 256, 0, st>>>(s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, (unsigned long long)s->side_cap, s->d_counters + 4);
   k_cand_scatter<<<64, 256, 0, st>>>(s->d_cands, s->d_counters + 0, (unsigned long long)s->cand_cap, (unsigned long long)s->side_cap, s->d_counters + 4,
                                       s->d_counters + 4 + kSortBins, s->d_side);
-  }
   k_scan_match<<<ctx->sm_count * 16, 128, 0, st>>>(b, mode, s->d_cands, s->d_side, side_cap, s->d_counters + 0, (unsigned long long)s->cand_cap,
                                                    s->d_chunk_local, s->d_tile_base, s->d_tables, s->d_hits, (unsigned long long)s->hit_cap, s->d_counters + 1);
   GPUD_CUDA(ctx, cudaGetLastError());
-  k_classify_ext_coop<<<ctx->sm_count * 16, 256, 0, st>>>(s->d_tables, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
-  GPUD_CUDA(ctx, cudaGetLastError());
-  k_scan_unit_index<<<ctx->sm_count * 8, 256, 0, st>>>(b, mode, s->d_chunk_local, s->d_tile_base, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
+  k_scan_finish<<<ctx->sm_count * 16, 256, 0, st>>>(b, mode, s->d_chunk_local, s->d_tile_base, s->d_tables, s->d_hits, s->d_counters + 1, (unsigned long long)s->hit_cap);
   GPUD_CUDA(ctx, cudaGetLastError());
   cudaEventRecord(s->ev[3], st);
   GPUD_CUDA(ctx, cudaMemcpyAsync(s->h_counters, s->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));

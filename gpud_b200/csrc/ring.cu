@@ -222,19 +222,19 @@ template <bool HI_ONLY>
 __device__ __forceinline__ int gather_rows(unsigned char* wbase, unsigned rows, unsigned Lh, unsigned Ll, int lane, unsigned lt_mask) {
   const int n_rows = __popc(rows);
   unsigned* row_off = reinterpret_cast<unsigned*>(wbase + kRowListOff);
-  int* s_cnt = reinterpret_cast<int*>(wbase + kCntOff);
   if ((rows >> lane) & 1u) row_off[__popc(rows & lt_mask)] = (unsigned)lane * (kRowU64 * 8);
   if (lane < 4) row_off[n_rows + lane] = kPadRowOff;
-  if (lane == 0) *s_cnt = 0;
   __syncwarp();
   const unsigned col = (unsigned)__cvta_generic_to_shared(wbase) + lane * 8;        // this lane's column of every row
-  const unsigned cand_a = (unsigned)__cvta_generic_to_shared(wbase + kCandOff);
-  const unsigned cnt_a = (unsigned)__cvta_generic_to_shared(s_cnt);
+  uint2* cand = reinterpret_cast<uint2*>(wbase + kCandOff);
   const unsigned long long Lp = ((unsigned long long)Lh << 32) | Ll;
   const unsigned X = (Lh & 0x80000000u) ? 0u : 0x7fffffffu;
   const int Y = (int)(Lh ^ 0x80000000u);
+  int cnt = 0;
+  // Hits are compacted with warp ballots (slot = hits so far + hits in lower lanes): no shared-memory atomics, and a class of
+  // equal keys that would overflow the candidate list ends the walk after the trip that passes 32 (the caller falls back).
 #pragma unroll 1
-  for (int i = 0; i < n_rows; i += 4) {
+  for (int i = 0; i < n_rows && cnt <= 32; i += 4) {
     const uint4 o4 = *reinterpret_cast<const uint4*>(row_off + i);                   // broadcast
     unsigned lo[4], hi[4];
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[0]), "=r"(hi[0]) : "r"(col + o4.x));
@@ -243,23 +243,17 @@ __device__ __forceinline__ int gather_rows(unsigned char* wbase, unsigned rows, 
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo[3]), "=r"(hi[3]) : "r"(col + o4.w));
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      unsigned hit;
-      if (HI_ONLY) hit = (int)(hi[q] ^ X) >= Y ? 1u : 0u;
-      else hit = (true_key(((unsigned long long)hi[q] << 32) | lo[q]) > Lp) ? 1u : 0u;
-      asm volatile(
-          "{\n\t.reg .pred p, q;\n\t.reg .u32 pos, a;\n\t"
-          "setp.ne.u32 p, %0, 0;\n\t"
-          "@p atom.shared.add.u32 pos, [%1], 1;\n\t"
-          "setp.lt.and.u32 q, pos, %2, p;\n\t"
-          "mad.lo.u32 a, pos, 8, %3;\n\t"
-          "@q st.shared.v2.u32 [a], {%4, %5};\n\t}"
-          :: "r"(hit), "r"(cnt_a), "n"(kCandMax), "r"(cand_a), "r"(lo[q]), "r"(hi[q]) : "memory");
+      bool hit;
+      if (HI_ONLY) hit = (int)(hi[q] ^ X) >= Y;
+      else hit = true_key(((unsigned long long)hi[q] << 32) | lo[q]) > Lp;
+      const unsigned b = __ballot_sync(kFull, hit);
+      const int slot = cnt + __popc(b & lt_mask);
+      if (hit && slot < kCandMax) cand[slot] = make_uint2(lo[q], hi[q]);
+      cnt += __popc(b);
     }
   }
   __syncwarp();
-  const int cnt = *s_cnt;
   // zero-pad to a multiple of 4 so the rank loop can run unrolled without a tail
-  uint2* cand = reinterpret_cast<uint2*>(wbase + kCandOff);
   if (lane < 4 && cnt <= kCandMax) cand[cnt + lane] = make_uint2(0u, 0u);
   __syncwarp();
   return cnt;
@@ -390,6 +384,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     //   the smallest key is umax(h) when any element is negative (umax >= 2^31), else umin(h).
     int a_smax = (int)0x80000000;
     unsigned b_umin = 0xffffffffu, c_umax = 0u;
+    unsigned lor = 0u;                               // OR of the raw low words: zero = an integer-valued gauge, the high words are the whole key
     double2* my_row2 = reinterpret_cast<double2*>(my_row4);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -407,6 +402,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         a_smax = max(a_smax, max(h0, h1));
         b_umin = min(b_umin, min((unsigned)h0, (unsigned)h1));
         c_umax = max(c_umax, max((unsigned)h0, (unsigned)h1));
+        lor |= (unsigned)__double2loint(x0) | (unsigned)__double2loint(x1);
         my_row2[j] = v[j];                     // STS.128 of the loaded registers, conflict-free (272-byte row stride)
       } else if (JF >= 0 ? (j == JF) : (j < J)) {   // the one partially valid pair
         const int t0 = 64 * j + 2 * lane;
@@ -424,6 +420,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         a_smax = max(a_smax, max((int)h0, (int)h1));                       // all-ones is -1: neutral unless every element is negative, and then unused
         b_umin = min(b_umin, min(h0, h1));
         c_umax = max(c_umax, max(q0 ? h0 : 0u, q1 ? h1 : 0u));
+        lor |= (q0 ? (unsigned)__double2loint(x0) : 0u) | (q1 ? (unsigned)__double2loint(x1) : 0u);
         my_row4[j] = make_uint4(q0 ? (unsigned)__double2loint(x0) : 0xffffffffu, h0, q1 ? (unsigned)__double2loint(x1) : 0xffffffffu, h1);
       } else {
         my_row4[j] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);     // padding: the smallest key (kPadStored)
@@ -451,9 +448,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
     nov = __reduce_add_sync(kFull, nov);
 
     // ---- exact minimum: global min of the high words, then the low words of the rows that hold it ----
+    // Every raw low word zero (integer readings below 2^21: degrees, %, MHz, MiB, mW): the high words order the window by
+    // themselves and a key's low word follows from its sign - no row is revisited for min / max, ties cost nothing.
+    const bool lo_zero = __reduce_or_sync(kFull, lor) == 0u;
     K64 wmin;
     wmin.hi = __reduce_min_sync(kFull, nh);
-    {
+    if (lo_zero) {
+      wmin.lo = true_lo(wmin.hi, 0u);
+    } else {
       unsigned rows = __ballot_sync(kFull, nh == wmin.hi);
       unsigned nl = 0xffffffffu;
       const unsigned raw_min_hi = raw_hi_of(wmin.hi);
@@ -492,11 +494,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
         // Lower bound L' = (k-th largest lane maximum of the HIGH words, 0): at least k keys are >= L', so the answer is too.
         // Only rows whose maximum reaches L' can hold keys above it.
         const unsigned Lh = warp_kth_largest_smem(mh, k, s32, lane);
-        // at least k lane maxima reach Lh, so at least k keys pass: the k-th largest of the gathered set is the answer
-        // Several lanes sharing the bounding high word means ties around the order statistic (integer readings, flat or slowly
-        // moving gauges): materialising such a class costs one shared atomic per member (a flat gauge ran 4x slower than white
-        // noise).  Those windows skip to the 64-bit-bound path below, where a class of equal keys collapses to its value.
-        if (__popc(__ballot_sync(kFull, mh == Lh)) == 1) {
+        if (lo_zero) {
+          // high words are whole keys: fewer than k lanes lie above Lh; if they hold fewer than k keys above Lh the answer is Lh
+          // itself (a tie-heavy gauge: usually no lane lies above and nothing is gathered at all)
+          const unsigned rows = __ballot_sync(kFull, mh > Lh);
+          const int cnt = rows ? gather_rows<true>(wbase, rows, Lh + 1u, 0u, lane, lt_mask) : 0;
+          if (cnt < k) { ans.hi = Lh; ans.lo = true_lo(Lh, 0u); done = true; }
+          else if (cnt <= 32) { K64 unused; ans = select_from_candidates(cand, cnt, k, lane, &unused); done = true; }
+          if (done) { wmax.hi = __reduce_max_sync(kFull, mh); wmax.lo = true_lo(wmax.hi, 0u); }
+        } else {
+          // at least k lane maxima reach Lh, so at least k keys pass: the k-th largest of the gathered set is the answer.  A class
+          // of equal keys around the bound (a flat non-integer gauge) overflows the list; the gather stops early and the
+          // 64-bit-bound path below takes over, where such a class collapses to its value.
           const int cnt = gather_rows<true>(wbase, __ballot_sync(kFull, mh >= Lh), Lh, 0u, lane, lt_mask);
           if (cnt <= 32) {
             ans = select_from_candidates(cand, cnt, k, lane, &wmax);
@@ -548,7 +557,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (ALIGNED && JF >= 0) ? kH
       // flagged in pass 1 (lo <= x <= hi as doubles) are classified exactly on their totalOrder keys: above hi (+0 over a -0
       // pivot), == hi, == lo, below lo (-0 under a +0 pivot), and the rest - strictly inside - goes to the field's list.
       wmax.hi = __reduce_max_sync(kFull, mh);
-      {
+      if (lo_zero) {
+        wmax.lo = true_lo(wmax.hi, 0u);
+      } else {
         unsigned rows = __ballot_sync(kFull, mh == wmax.hi);
         unsigned ml = 0u;
         const unsigned raw_max_hi = raw_hi_of(wmax.hi);

@@ -89,6 +89,7 @@ def fill_ring(ring, shape: str, F: int, cap: int, seed: int, dev, chunk: int = 1
     t0 = 0
     for x, n in chunks(shape, F, cap, chunk, seed, dev):
         x = x.contiguous()
+        torch.cuda.current_stream().synchronize()      # the ring appends on ITS stream: the chunk must be complete before the append reads it
         ring.push_device(x.data_ptr(), n)
         ring.sync()
         if host_copy is not None:

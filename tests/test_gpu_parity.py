@@ -670,6 +670,7 @@ def test_ring_full_size_properties(ctx):
         t = torch.rand((chunk, F), dtype=torch.float64, device="cuda", generator=gen)
         if i == 3:
             xs.append(t[:, :4].cpu().numpy())
+        torch.cuda.synchronize()              # the ring appends on its own stream: the chunk must be complete first
         r.push_device(t.data_ptr(), chunk)
         r.sync()
     r.reduce()
