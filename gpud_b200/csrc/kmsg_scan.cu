@@ -1566,6 +1566,71 @@ extern "C" int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf
   return scan_collect(ctx, s, hits, cap, n_hits, n_units, s->stream);
 }
 
+// One large buffer over every GPU of the ctx: the buffer is cut just after a unit separator near each k/n of its
+// length (a record and its continuation lines stay together), every GPU scans its own piece - staging, filter and match run
+// concurrently, one host thread per device - and the hit lists are concatenated in piece order with unit numbers and byte offsets
+// made global.  The result is the one gpud_kmsg_scan gives for the whole buffer on one GPU.
+extern "C" int32_t gpud_kmsg_scan_sharded(gpud_ctx* ctx, const uint8_t* buf, int64_t len, int32_t mode, gpud_xid_hit* hits, int64_t cap,
+                                          int64_t* n_hits, int64_t* n_units) {
+  if (!ctx || len < 0 || (len && !buf) || cap < 0 || (cap && !hits) || !scan_mode_ok(mode)) return GPUD_E_INVALID;
+  const int n_dev = (int)ctx->devs.size();
+  const bool raw = (mode & kModeMask) == GPUD_SCAN_RAW_KMSG;
+  std::vector<int64_t> cut(1, 0);
+  for (int r = 1; r < n_dev; ++r) {
+    int64_t pos = std::max<int64_t>(cut.back(), len / n_dev * r);
+    for (;;) {
+      const void* nl = pos < len ? memchr(buf + pos, '\n', (size_t)(len - pos)) : nullptr;
+      if (!nl) { pos = len; break; }
+      pos = (const uint8_t*)nl - buf + 1;
+      if (!raw || pos >= len || buf[pos] != ' ') break;       // RAW_KMSG: "\n " continues the record
+    }
+    cut.push_back(pos);
+  }
+  cut.push_back(len);
+  struct Piece { int dev; int64_t b, e; std::vector<gpud_xid_hit> hits; int64_t found = 0, units = 0; int32_t rc = GPUD_OK; };
+  std::vector<Piece> pieces;
+  for (int r = 0; r < n_dev; ++r)
+    if (cut[r + 1] > cut[r]) { Piece p; p.dev = ctx->devs[r]; p.b = cut[r]; p.e = cut[r + 1]; pieces.push_back(std::move(p)); }
+  if (pieces.size() <= 1) return gpud_kmsg_scan(ctx, ctx->devs[0], buf, len, mode, hits, cap, n_hits, n_units);
+  std::vector<std::thread> th;
+  for (Piece& p : pieces)
+    th.emplace_back([&, pp = &p] {
+      int64_t local_cap = std::max<int64_t>(4096, std::min<int64_t>(cap, (pp->e - pp->b) / 32 + 4096));
+      for (;;) {                                                // a piece denser in hits than expected: once more with room for all
+        pp->hits.resize((size_t)local_cap);
+        pp->rc = gpud_kmsg_scan(ctx, pp->dev, buf + pp->b, pp->e - pp->b, mode, pp->hits.data(), local_cap, &pp->found, &pp->units);
+        if (pp->rc != GPUD_E_CAPACITY || pp->found <= local_cap) break;
+        local_cap = pp->found;
+      }
+    });
+  for (std::thread& t : th) t.join();
+  int64_t total = 0, unit0 = 0;
+  for (size_t k = 0; k < pieces.size(); ++k) {
+    Piece& p = pieces[k];
+    if (p.rc != GPUD_OK) return p.rc;
+    for (int64_t i = 0; i < p.found; ++i) {
+      if (total < cap) {
+        gpud_xid_hit h = p.hits[(size_t)i];
+        h.unit_index += unit0;
+        h.unit_offset += p.b;
+        if (h.dev_len || h.dev_off) h.dev_off += p.b;                  // an empty capture still has a position; 0 / 0 = no capture
+        if (h.unit_name_len || h.unit_name_off) h.unit_name_off += p.b;                  // an empty capture still has a position; 0 / 0 = no capture
+        if (h.pid_len || h.pid_off) h.pid_off += p.b;                  // an empty capture still has a position; 0 / 0 = no capture
+        if (h.pname_len || h.pname_off) h.pname_off += p.b;                  // an empty capture still has a position; 0 / 0 = no capture
+        if (h.inj_len || h.inj_off) h.inj_off += p.b;                  // an empty capture still has a position; 0 / 0 = no capture
+        if (h.kind > GPUD_KIND_SXID) h.link += p.b;            // the extra matchers keep their anchor offset there
+        hits[total] = h;
+      }
+      ++total;
+    }
+    // a piece that ends with its separator counts one trailing empty unit that really is the next piece's first unit
+    unit0 += k + 1 < pieces.size() ? p.units - 1 : p.units;
+  }
+  if (n_hits) *n_hits = total;
+  if (n_units) *n_units = unit0;
+  return total > cap ? gpud_fail(ctx, GPUD_E_CAPACITY, "hit list needs room for %lld", (long long)total) : GPUD_OK;
+}
+
 extern "C" int32_t gpud_xid_classify(gpud_ctx* ctx, int32_t dev, gpud_xid_hit* hits, int64_t n) {
   if (!ctx || n < 0 || (n && !hits)) return GPUD_E_INVALID;
   if (n == 0) return GPUD_OK;

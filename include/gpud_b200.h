@@ -277,6 +277,10 @@ typedef struct {
  * number found (may exceed cap -> GPUD_E_CAPACITY, first cap are valid); *n_units = number of lines/records. */
 int32_t gpud_kmsg_scan(gpud_ctx* ctx, int32_t dev, const uint8_t* buf, int64_t len, int32_t mode,
                        gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units);
+/* The same scan over every GPU of the ctx: the buffer is cut at unit boundaries into one piece per device, the pieces
+ * are scanned concurrently and the hits merged in unit order; result identical to gpud_kmsg_scan of the whole buffer. */
+int32_t gpud_kmsg_scan_sharded(gpud_ctx* ctx, const uint8_t* buf, int64_t len, int32_t mode,
+                               gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units);
 /* Device-resident variant: dev_buf on `dev`; kernels only, results copied to the caller's host arrays. */
 int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8_t* dev_buf, int64_t len, int32_t mode,
                               gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units, void* cuda_stream);

@@ -162,3 +162,56 @@ def test_real_box_nvlink_view_from_nvml():
     for r in rings:
         r.close()
     ctx.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("raw", [False, True])
+def test_kmsg_scan_sharded_equals_single_gpu(raw):
+    """one buffer cut at unit boundaries over every GPU of the context (gpud_kmsg_scan_sharded, in C behind the ABI):
+    hits, unit numbers and byte offsets identical to the scan of the whole buffer on one GPU, for both unit forms, incl. the
+    fabric epoch fix (a second context in the same process gathers without stalling)."""
+    import gpud_b200 as g
+    import synth
+    n = min(_n_gpus(), 8)
+    buf = synth.raw_kmsg_buffer(40000) if raw else synth.dmesg_buffer(3 << 20, hit_every=300)
+    mode = g.SCAN_RAW_KMSG if raw else g.SCAN_LINES
+    one = g.Context([0])
+    want, want_units = one.kmsg_scan(buf, mode=mode, cap=1 << 17)
+    one.close()
+    ctx = g.Context(list(range(n)))
+    got, got_units = ctx.kmsg_scan_sharded(buf, mode=mode, cap=1 << 17)
+    assert got_units == want_units and len(got) == len(want) > 100
+    key = lambda h: (h.unit_index, h.unit_offset, h.kind, h.code, h.device, h.dev_off, h.dev_len, h.event_type, h.sub_code, h.link, h.kmsg_seq, h.kmsg_usec,
+                     h.unit_name_off, h.pid_off, h.pname_off, h.inj_off, tuple(h.actions), h.n_actions, h.rule_index)
+    assert [key(h) for h in got] == [key(h) for h in want]
+    # offsets are global: the device capture can be read back out of the whole buffer
+    for h in got[:: max(1, len(got) // 50)]:
+        if h.dev_len and not (h.flags & 0x1):
+            assert buf[h.dev_off:h.dev_off + h.dev_len].decode() in h.device.decode()
+    # extra matchers too (their anchor offset travels in `link`)
+    ebuf = synth.ext_buffer(2 << 20, hit_every=200)
+    one = g.Context([0])
+    want, wu = one.kmsg_scan(ebuf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS, cap=1 << 17)
+    one.close()
+    got, gu = ctx.kmsg_scan_sharded(ebuf, mode=g.SCAN_LINES | g.SCAN_EXT_MATCHERS, cap=1 << 17)
+    assert gu == wu and [key(h) for h in got] == [key(h) for h in want] and len(got) > 100
+    ctx.close()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_fabric_gather_p2p_second_context_and_recovery():
+    """the arrival epoch lives in the context - a second context in the same process gathers at once (it used to wait
+    out the 7 s timeout and still return OK), and both keep working alternately."""
+    import time
+    import gpud_b200 as g
+    n = min(_n_gpus(), 8)
+    gpus, at_least = scenario("all_healthy", n)
+    a, b = g.Context(list(range(n))), g.Context(list(range(n)))
+    for _ in range(3):
+        for ctx in (a, b):
+            t0 = time.perf_counter()
+            recs, verdicts = ctx.fabric_gather_p2p([_raw(g, d) for d in gpus], min(at_least, n))
+            assert time.perf_counter() - t0 < 1.0
+            assert all(v.as_dict()["active"] == n for v in verdicts)
+    a.close()
+    b.close()
