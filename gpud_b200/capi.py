@@ -320,6 +320,69 @@ def temperature_reason(readings, gpu_uuids, margin_threshold_c: int = 0):
     return h.value, buf.value.decode("utf-8")
 
 
+class NvmlDevice(C.Structure):
+    _fields_ = [("index", C.c_int32), ("cuda_device", C.c_int32), ("nvml_rc", C.c_int32), ("pad", C.c_int32), ("uuid", C.c_char * 96), ("bus_id", C.c_char * 32),
+                ("name", C.c_char * 96)]
+
+
+class RemappedRows(C.Structure):
+    _fields_ = [("remapped_due_to_correctable_errors", C.c_int32), ("remapped_due_to_uncorrectable_errors", C.c_int32), ("remapping_pending", C.c_uint8),
+                ("remapping_failed", C.c_uint8), ("supported", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class EccCounts(C.Structure):
+    _fields_ = [("corrected", C.c_uint64), ("uncorrected", C.c_uint64)]
+
+
+ECC_LOCATIONS = ("total", "l1_cache", "l2_cache", "dram", "sram", "gpu_device_memory", "gpu_texture_memory", "shared_memory", "gpu_register_file")
+FIELD_ROW = ("power_instant_mw", "power_average_mw", "memory_temp_c", "total_energy_mj", "ecc_sbe_volatile", "ecc_dbe_volatile", "ecc_sbe_aggregate",
+             "ecc_dbe_aggregate", "nvlink_crc_flit_total", "nvlink_crc_data_total", "nvlink_replay_total", "nvlink_recovery_total", "remapped_correctable",
+             "remapped_uncorrectable", "remapped_pending", "remapped_failure", "pcie_replay")
+
+
+class EccErrors(C.Structure):
+    _fields_ = [("aggregate", EccCounts * 9), ("volatile_", EccCounts * 9), ("ecc_mode_current", C.c_uint8), ("ecc_mode_pending", C.c_uint8), ("supported", C.c_uint8),
+                ("pad", C.c_uint8 * 5)]
+
+
+def nvml_devices(cap: int = 16):
+    """gpud_nvml_devices: (list of NvmlDevice, driver version)"""
+    arr = (NvmlDevice * cap)()
+    n = C.c_int32()
+    drv = C.create_string_buffer(96)
+    rc = lib().gpud_nvml_devices(arr, cap, C.byref(n), drv, 96)
+    if rc not in (0, -4):
+        raise GpudError(rc, "gpud_nvml_devices")
+    return [arr[i] for i in range(min(n.value, cap))], drv.value.decode()
+
+
+def nvml_devices_arg() -> str:
+    buf = C.create_string_buffer(4096)
+    rc = lib().gpud_nvml_devices_arg(buf, 4096)
+    if rc < 0:
+        raise GpudError(rc, "gpud_nvml_devices_arg")
+    return buf.value.decode()
+
+
+def nvml_bus_id(nvml_bus_id_str: str) -> str:
+    buf = C.create_string_buffer(64)
+    lib().gpud_nvml_bus_id(nvml_bus_id_str.encode(), buf, 64)
+    return buf.value.decode()
+
+
+def remapped_rows_check(rows, bus_ids):
+    """gpud_remapped_rows_check: (health, action, reason)"""
+    n = len(rows)
+    arr = (RemappedRows * max(n, 1))(*rows)
+    ids = (C.c_char_p * max(n, 1))(*[b.encode() for b in bus_ids])
+    health, action = C.c_int32(), C.c_int32()
+    buf = C.create_string_buffer(4096)
+    k = lib().gpud_remapped_rows_check(arr, ids, n, C.byref(health), C.byref(action), buf, 4096)
+    if k < 0:
+        raise GpudError(k, "gpud_remapped_rows_check")
+    return health.value, action.value, buf.value.decode()
+
+
 def poll_row_hold(fresh, nvml_rc, held):
     """gpud_poll_row_hold: the row that goes to the ring when some getters failed; updates `held` in place.  Returns (row, fail_mask)."""
     n = len(fresh)
@@ -352,6 +415,28 @@ class Poller:
         n, sec = C.c_int64(), C.c_double()
         self.ctx._check(self._L.gpud_poller_last_rows(self._h, C.c_void_p(rows.ctypes.data), cap_rows, C.byref(n), C.byref(sec)))
         return rows[: min(cap_rows, n.value)], sec.value
+
+    def remapped_rows(self) -> "RemappedRows":
+        r = RemappedRows()
+        self.ctx._check(self._L.gpud_poller_remapped_rows(self._h, C.byref(r)))
+        return r
+
+    def ecc_errors(self) -> "EccErrors":
+        e = EccErrors()
+        self.ctx._check(self._L.gpud_poller_ecc_errors(self._h, C.byref(e)))
+        return e
+
+    def field_row(self):
+        """one nvmlDeviceGetFieldValues call: ({name: value}, {name: nvml return code})"""
+        v = (C.c_uint64 * len(FIELD_ROW))()
+        rc = (C.c_int32 * len(FIELD_ROW))()
+        self.ctx._check(self._L.gpud_poller_field_row(self._h, v, rc))
+        return dict(zip(FIELD_ROW, list(v))), dict(zip(FIELD_ROW, list(rc)))
+
+    def poll_fields(self, ring: "Ring", n_polls: int, interval_us: int = 0) -> float:
+        sec = C.c_double()
+        self.ctx._check(self._L.gpud_poller_poll_fields(self._h, ring._h, n_polls, interval_us, C.byref(sec)))
+        return sec.value
 
     def errors(self):
         """(fail_mask, last NVML return code per column, failures per column): getters that failed since create"""
@@ -452,7 +537,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_record_reboot", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_errors", "gpud_poll_row_hold", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_record_reboot", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_errors", "gpud_poll_row_hold", "gpud_nvml_devices", "gpud_nvml_devices_arg", "gpud_nvml_bus_id", "gpud_poller_remapped_rows", "gpud_remapped_rows_check", "gpud_poller_ecc_errors", "gpud_poller_field_row", "gpud_poller_poll_fields", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_ring_range_stats", "gpud_ring_set_cta_reserve", "gpud_kmsg_scan", "gpud_kmsg_scan_sharded", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_set_nvml_error_string", "gpud_nvml_error_strings_from_driver", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -496,6 +581,9 @@ def lib() -> C.CDLL:
         "gpud_poller_create": (i32, [vp, i32, vp, vp]), "gpud_poller_destroy": (None, [vp]), "gpud_poller_poll": (i32, [vp, i64, i64]),
         "gpud_poller_last_rows": (i32, [vp, vp, i64, vp, vp]), "gpud_poller_errors": (i32, [vp, vp, vp, vp]),
         "gpud_poll_row_hold": (i32, [vp, vp, i32, vp, vp, vp]),
+        "gpud_nvml_devices": (i32, [vp, i32, vp, vp, i32]), "gpud_nvml_devices_arg": (i32, [vp, i32]), "gpud_nvml_bus_id": (i32, [C.c_char_p, vp, i32]),
+        "gpud_poller_remapped_rows": (i32, [vp, vp]), "gpud_remapped_rows_check": (i32, [vp, vp, i32, vp, vp, vp, i32]),
+        "gpud_poller_ecc_errors": (i32, [vp, vp]), "gpud_poller_field_row": (i32, [vp, vp, vp]), "gpud_poller_poll_fields": (i32, [vp, vp, i64, i64, vp]),
         "gpud_poller_temperature": (i32, [vp, C.POINTER(Temperature)]), "gpud_temperature_check": (i32, [C.POINTER(Temperature), i32, vp]),
         "gpud_temperature_reason": (i32, [vp, vp, i32, i32, vp, vp, i32]),
         "gpud_poller_counters": (i32, [vp, C.POINTER(PollCounters)]),
@@ -538,7 +626,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters, EventRow)):
+    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters, EventRow, NvmlDevice, RemappedRows, EccErrors)):
         if L.gpud_sizeof(which) != C.sizeof(st):
             raise GpudError(-1, "ABI layout mismatch for %s: C %d vs ctypes %d" % (st.__name__, L.gpud_sizeof(which), C.sizeof(st)))
     _lib = L

@@ -89,6 +89,9 @@ extern "C" int32_t gpud_sizeof(int32_t which) {
     case 10: return (int32_t)sizeof(gpud_temperature);
     case 11: return (int32_t)sizeof(gpud_poll_counters);
     case 12: return (int32_t)sizeof(gpud_event_row);
+    case 13: return (int32_t)sizeof(gpud_nvml_device);
+    case 14: return (int32_t)sizeof(gpud_remapped_rows);
+    case 15: return (int32_t)sizeof(gpud_ecc_errors);
   }
   return -1;
 }

@@ -50,6 +50,15 @@ struct Nvml {
   nvmlReturn_t (*margin_temp)(nvmlDevice_t, void*) = nullptr;
   nvmlReturn_t (*clock_reasons)(nvmlDevice_t, unsigned long long*) = nullptr;
   nvmlReturn_t (*ecc_total)(nvmlDevice_t, int, int, unsigned long long*) = nullptr;
+  nvmlReturn_t (*ecc_mode)(nvmlDevice_t, int*, int*) = nullptr;
+  nvmlReturn_t (*ecc_location)(nvmlDevice_t, int, int, int, unsigned long long*) = nullptr;
+  nvmlReturn_t (*remapped_rows)(nvmlDevice_t, unsigned int*, unsigned int*, unsigned int*, unsigned int*) = nullptr;
+  nvmlReturn_t (*field_values)(nvmlDevice_t, int, void*) = nullptr;
+  nvmlReturn_t (*uuid)(nvmlDevice_t, char*, unsigned int) = nullptr;
+  nvmlReturn_t (*count)(unsigned int*) = nullptr;
+  nvmlReturn_t (*by_index)(unsigned int, nvmlDevice_t*) = nullptr;
+  nvmlReturn_t (*pci_info)(nvmlDevice_t, void*) = nullptr;
+  nvmlReturn_t (*driver_version)(char*, unsigned int) = nullptr;
 };
 
 Nvml* nvml() {
@@ -77,6 +86,15 @@ Nvml* nvml() {
       *(void**)&n.clock_reasons = dlsym(n.so, "nvmlDeviceGetCurrentClocksEventReasons");
       if (!n.clock_reasons) *(void**)&n.clock_reasons = dlsym(n.so, "nvmlDeviceGetCurrentClocksThrottleReasons");   // the pre-535 name of the same getter
       *(void**)&n.ecc_total = dlsym(n.so, "nvmlDeviceGetTotalEccErrors");
+      *(void**)&n.ecc_mode = dlsym(n.so, "nvmlDeviceGetEccMode");
+      *(void**)&n.ecc_location = dlsym(n.so, "nvmlDeviceGetMemoryErrorCounter");
+      *(void**)&n.remapped_rows = dlsym(n.so, "nvmlDeviceGetRemappedRows");
+      *(void**)&n.field_values = dlsym(n.so, "nvmlDeviceGetFieldValues");
+      *(void**)&n.uuid = dlsym(n.so, "nvmlDeviceGetUUID");
+      *(void**)&n.count = dlsym(n.so, "nvmlDeviceGetCount_v2");
+      *(void**)&n.by_index = dlsym(n.so, "nvmlDeviceGetHandleByIndex_v2");
+      *(void**)&n.pci_info = dlsym(n.so, "nvmlDeviceGetPciInfo_v3");
+      *(void**)&n.driver_version = dlsym(n.so, "nvmlSystemGetDriverVersion");
       if (!n.init || !n.by_pci || !n.temperature || !n.power || !n.clock || !n.util || !n.memory || n.init() != 0) { dlclose(n.so); n.so = nullptr; }
     }
   }
@@ -97,6 +115,8 @@ struct gpud_poller {
   uint32_t fail_mask = 0;                        // columns that failed at least once since create
   int32_t last_rc[GPUD_POLL_N_FIELDS] = {0};     // the NVML return code of each column's last failure
   uint64_t n_failed[GPUD_POLL_N_FIELDS] = {0};
+  uint64_t* field_rows = nullptr;                // pinned [cap_rows][GPUD_FIELD_ROW_N] (gpud_poller_poll_fields)
+  uint64_t field_held[GPUD_FIELD_ROW_N] = {0};
 };
 
 extern "C" int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* ring, gpud_poller** out) {
@@ -122,6 +142,7 @@ extern "C" int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* rin
 extern "C" void gpud_poller_destroy(gpud_poller* p) {
   if (!p) return;
   if (p->rows) cudaFreeHost(p->rows);
+  if (p->field_rows) cudaFreeHost(p->field_rows);
   delete p;
 }
 
@@ -377,5 +398,250 @@ extern "C" int32_t gpud_nvml_error_strings_from_driver(void) {
   Nvml* N = nvml();
   if (!N || !N->err) return GPUD_E_UNSUPPORTED;
   gpud_set_nvml_error_string((gpud_nvml_error_string_fn)N->err);       // const char* nvmlErrorString(nvmlReturn_t): the same shape
+  return GPUD_OK;
+}
+
+
+// ---- rows A3 / A4 of SURVEY.md 8(a): what the reference's nvml.Instance and its ecc / remapped-rows components read ------------------
+namespace {
+// nvmlPciInfo_t (nvml.h): busIdLegacy[16], domain, bus, device, pciDeviceId, pciSubSystemId, busId[32]
+struct PciInfo { char bus_id_legacy[16]; unsigned int domain, bus, device, pci_device_id, pci_subsystem_id; char bus_id[32]; };
+static_assert(sizeof(PciInfo) == 68, "nvmlPciInfo_t layout");
+// nvmlFieldValue_t (nvml.h:2677)
+struct FieldValue { unsigned int field_id, scope_id; long long timestamp, latency_usec; int value_type; nvmlReturn_t nvml_return; union { double d; unsigned int ui; unsigned long ul; unsigned long long ull; long long sll; int si; unsigned short us; } value; };
+static_assert(sizeof(FieldValue) == 40, "nvmlFieldValue_t layout");
+
+// go-nvlib's device.GetPCIBusID (v0.8.1 pkg/nvlib/device/device.go): the NVML busId lower-cased, with the first four zeros of the
+// eight-digit domain dropped ("00000000:3B:00.0" -> "0000:3b:00.0").
+void gonvlib_bus_id(const char* nvml_bus_id, char* out, size_t cap) {
+  std::string id;
+  for (const char* c = nvml_bus_id; *c; ++c) id.push_back((*c >= 'A' && *c <= 'Z') ? (char)(*c - 'A' + 'a') : *c);
+  if (id != "0000" && id.compare(0, 4, "0000") == 0) id.erase(0, 4);
+  snprintf(out, cap, "%s", id.c_str());
+}
+}  // namespace
+
+extern "C" int32_t gpud_nvml_bus_id(const char* nvml_bus_id, char* out, int32_t cap) {
+  if (!nvml_bus_id || !out || cap < 1) return GPUD_E_INVALID;
+  gonvlib_bus_id(nvml_bus_id, out, (size_t)cap);
+  return GPUD_OK;
+}
+
+// nvml.New's enumeration (pkg/nvidia/nvml/instance.go:197-273): every device's UUID and PCI bus id (the map key and the value
+// device.New keeps, device/device.go:46-70), the product name of device 0 and the driver version; plus the CUDA ordinal of each
+// device so the rest of this library can be pointed at it.
+extern "C" int32_t gpud_nvml_devices(gpud_nvml_device* out, int32_t cap, int32_t* n_out, char* driver_version, int32_t driver_cap) {
+  if (!n_out || cap < 0 || (cap && !out)) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->count || !N->by_index || !N->uuid || !N->pci_info) return GPUD_E_UNSUPPORTED;
+  unsigned int n = 0;
+  if (N->count(&n) != 0) return GPUD_E_STATE;
+  *n_out = (int32_t)n;
+  if (driver_version && driver_cap > 0) { driver_version[0] = 0; if (N->driver_version) N->driver_version(driver_version, (unsigned int)driver_cap); }
+  for (unsigned int i = 0; i < n && (int32_t)i < cap; ++i) {
+    gpud_nvml_device& d = out[i];
+    memset(&d, 0, sizeof d);
+    d.index = (int32_t)i;
+    d.cuda_device = -1;
+    nvmlDevice_t h;
+    nvmlReturn_t rc = N->by_index(i, &h);                    // "error getting device handle for index": the errored-instance case (:190-203)
+    if (rc != 0) { d.nvml_rc = rc; continue; }
+    if ((rc = N->uuid(h, d.uuid, sizeof d.uuid)) != 0) { d.nvml_rc = rc; continue; }
+    PciInfo pi;
+    memset(&pi, 0, sizeof pi);
+    if ((rc = N->pci_info(h, &pi)) != 0) { d.nvml_rc = rc; continue; }
+    gonvlib_bus_id(pi.bus_id, d.bus_id, sizeof d.bus_id);
+    if (N->name) N->name(h, d.name, sizeof d.name);
+    int cd = -1;
+    if (cudaDeviceGetByPCIBusId(&cd, pi.bus_id) == cudaSuccess) d.cuda_device = cd; else cudaGetLastError();
+  }
+  return (int32_t)n > cap ? GPUD_E_CAPACITY : GPUD_OK;
+}
+
+// "uuid=bus_id;uuid=bus_id;..." of the enumerated devices: the `devices` argument of gpud_xid_state_from_store
+extern "C" int32_t gpud_nvml_devices_arg(char* out, int32_t cap) {
+  if (!out || cap < 1) return GPUD_E_INVALID;
+  gpud_nvml_device d[GPUD_MAX_GPUS];
+  int32_t n = 0;
+  const int32_t rc = gpud_nvml_devices(d, GPUD_MAX_GPUS, &n, nullptr, 0);
+  if (rc != GPUD_OK && rc != GPUD_E_CAPACITY) return rc;
+  std::string s;
+  for (int32_t i = 0; i < n && i < GPUD_MAX_GPUS; ++i) {
+    if (d[i].nvml_rc != 0) continue;
+    if (!s.empty()) s += ";";
+    s += d[i].uuid; s += "="; s += d[i].bus_id;
+  }
+  if ((int32_t)s.size() + 1 > cap) return GPUD_E_CAPACITY;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return (int32_t)s.size();
+}
+
+// GetRemappedRows (remapped-rows/remapped_rows.go:52-86)
+extern "C" int32_t gpud_poller_remapped_rows(gpud_poller* p, gpud_remapped_rows* out) {
+  if (!p || !out) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return GPUD_E_UNSUPPORTED;
+  memset(out, 0, sizeof *out);
+  out->supported = 1;
+  if (!N->remapped_rows) { out->supported = 0; return GPUD_OK; }
+  unsigned int corr = 0, unc = 0, pending = 0, failed = 0;
+  const nvmlReturn_t rc = N->remapped_rows(p->h, &corr, &unc, &pending, &failed);
+  if (is_not_supported(N, rc)) { out->supported = 0; return GPUD_OK; }
+  if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+  if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
+  if (rc != 0) return gpud_fail(p->ctx, GPUD_E_STATE, "failed to get device remapped rows: %s", N->err ? N->err(rc) : "error");
+  out->remapped_due_to_correctable_errors = (int32_t)corr;
+  out->remapped_due_to_uncorrectable_errors = (int32_t)unc;
+  out->remapping_pending = pending ? 1 : 0;
+  out->remapping_failed = failed ? 1 : 0;
+  return GPUD_OK;
+}
+
+// The remapped-rows Check over the box's readings (remapped-rows/component.go:197-300): per GPU, in the order given, "<bus id>
+// qualifies for RMA (row remapping failed, remapped due to N uncorrectable error(s))" when the failure flag is set and "<bus id>
+// needs reset (detected pending row remapping)" when a remapping is pending; Unhealthy with the issues joined by ", ", else
+// Healthy "N devices support remapped rows and found no issue".  *action: HardwareInspection once any GPU failed (RMA takes
+// precedence), else RebootSystem when one is pending, else 0.
+extern "C" int32_t gpud_remapped_rows_check(const gpud_remapped_rows* rows, const char* const* bus_ids, int32_t n, int32_t* health, int32_t* action,
+                                            char* reason, int32_t cap) {
+  if (n < 0 || (n && (!rows || !bus_ids)) || !health || !reason || cap < 1) return GPUD_E_INVALID;
+  std::string issues;
+  int act = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const gpud_remapped_rows& r = rows[i];
+    if (r.remapping_pending && act != GPUD_ACT_HARDWARE_INSPECTION) act = GPUD_ACT_REBOOT_SYSTEM;
+    if (r.remapping_failed) act = GPUD_ACT_HARDWARE_INSPECTION;
+    char buf[256];
+    if (r.remapping_failed) {
+      snprintf(buf, sizeof buf, "%s qualifies for RMA (row remapping failed, remapped due to %d uncorrectable error(s))", bus_ids[i] ? bus_ids[i] : "", r.remapped_due_to_uncorrectable_errors);
+      if (!issues.empty()) issues += ", ";
+      issues += buf;
+    }
+    if (r.remapping_pending) {
+      snprintf(buf, sizeof buf, "%s needs reset (detected pending row remapping)", bus_ids[i] ? bus_ids[i] : "");
+      if (!issues.empty()) issues += ", ";
+      issues += buf;
+    }
+  }
+  *health = issues.empty() ? 0 : 2;
+  if (action) *action = act;
+  if (issues.empty()) { char buf[96]; snprintf(buf, sizeof buf, "%d devices support remapped rows and found no issue", n); issues = buf; }
+  if ((int32_t)issues.size() + 1 > cap) return -1;
+  memcpy(reason, issues.c_str(), issues.size() + 1);
+  return (int32_t)issues.size();
+}
+
+// GetECCModeEnabled + GetECCErrors (ecc/ecc_mode.go, ecc/ecc_errors.go:136-880): the four totals, then - only with ECC mode on - the
+// per-location counters in the reference's order; the first "not supported" ends the read with supported = 0 and what was read so
+// far, GPU lost / requires reset fail it.
+extern "C" int32_t gpud_poller_ecc_errors(gpud_poller* p, gpud_ecc_errors* out) {
+  if (!p || !out) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->ecc_total) return GPUD_E_UNSUPPORTED;
+  memset(out, 0, sizeof *out);
+  out->supported = 1;
+  int cur = 0, pend = 0;
+  if (N->ecc_mode && N->ecc_mode(p->h, &cur, &pend) == 0) { out->ecc_mode_current = cur == 1; out->ecc_mode_pending = pend == 1; }
+  auto done = [&](nvmlReturn_t rc, int32_t* fail) -> bool {   // true = stop reading
+    *fail = GPUD_OK;
+    if (rc == 0) return false;
+    if (is_not_supported(N, rc)) { out->supported = 0; return true; }
+    if (is_gpu_lost(N, rc)) { *fail = gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost"); return true; }
+    if (is_reset_required(N, rc)) { *fail = gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset"); return true; }
+    *fail = gpud_fail(p->ctx, GPUD_E_STATE, "failed to get ecc errors: %s", N->err ? N->err(rc) : "error");
+    return true;
+  };
+  int32_t fail;
+  // totals: (corrected, aggregate), (uncorrected, aggregate), (corrected, volatile), (uncorrected, volatile)  (:148-240)
+  if (done(N->ecc_total(p->h, 0, 1, (unsigned long long*)&out->aggregate[GPUD_ECC_TOTAL].corrected), &fail)) return fail;
+  if (done(N->ecc_total(p->h, 1, 1, (unsigned long long*)&out->aggregate[GPUD_ECC_TOTAL].uncorrected), &fail)) return fail;
+  if (done(N->ecc_total(p->h, 0, 0, (unsigned long long*)&out->volatile_[GPUD_ECC_TOTAL].corrected), &fail)) return fail;
+  if (done(N->ecc_total(p->h, 1, 0, (unsigned long long*)&out->volatile_[GPUD_ECC_TOTAL].uncorrected), &fail)) return fail;
+  if (!out->ecc_mode_current || !N->ecc_location) return GPUD_OK;                       // :241-245
+  // nvml.MEMORY_LOCATION_*: L1 0, L2 1, DRAM / DEVICE_MEMORY 2, REGISTER_FILE 3, TEXTURE_MEMORY 4, TEXTURE_SHM 5, SRAM 7
+  static const struct { int slot, loc; } kAgg[] = {{GPUD_ECC_L1, 0}, {GPUD_ECC_L2, 1}, {GPUD_ECC_DRAM, 2}, {GPUD_ECC_SRAM, 7}, {GPUD_ECC_DEVICE_MEMORY, 2},
+                                                   {GPUD_ECC_TEXTURE_MEMORY, 4}, {GPUD_ECC_SHARED_MEMORY, 5}};
+  for (const auto& a : kAgg) {
+    if (done(N->ecc_location(p->h, 0, 1, a.loc, (unsigned long long*)&out->aggregate[a.slot].corrected), &fail)) return fail;
+    if (done(N->ecc_location(p->h, 1, 1, a.loc, (unsigned long long*)&out->aggregate[a.slot].uncorrected), &fail)) return fail;
+  }
+  for (const auto& a : kAgg) {
+    if (done(N->ecc_location(p->h, 0, 0, a.loc, (unsigned long long*)&out->volatile_[a.slot].corrected), &fail)) return fail;
+    if (done(N->ecc_location(p->h, 1, 0, a.loc, (unsigned long long*)&out->volatile_[a.slot].uncorrected), &fail)) return fail;
+  }
+  if (done(N->ecc_location(p->h, 0, 0, 3, (unsigned long long*)&out->volatile_[GPUD_ECC_REGISTER_FILE].corrected), &fail)) return fail;
+  if (done(N->ecc_location(p->h, 1, 0, 3, (unsigned long long*)&out->volatile_[GPUD_ECC_REGISTER_FILE].uncorrected), &fail)) return fail;
+  return GPUD_OK;
+}
+
+// One driver round trip for a whole row of counters: nvmlDeviceGetFieldValues over GPUD_FIELD_ROW.  values[i] is
+// the field widened to u64 (doubles truncated), nvml_rc[i] the field's own return code.
+static const unsigned int kFieldRow[GPUD_FIELD_ROW_N] = {186 /* POWER_INSTANT mW */, 185 /* POWER_AVERAGE mW */, 82 /* MEMORY_TEMP C */, 83 /* TOTAL_ENERGY mJ */,
+                                                         3, 4, 5, 6 /* ECC SBE/DBE volatile, aggregate totals */, 38, 45, 52, 59 /* NVLink CRC flit / CRC data / replay / recovery totals */,
+                                                         142, 143, 144, 145 /* remapped rows: correctable, uncorrectable, pending, failure */, 94 /* PCIe replay counter */};
+static int32_t field_row(Nvml* N, nvmlDevice_t h, uint64_t* values, int32_t* rcs) {
+  FieldValue fv[GPUD_FIELD_ROW_N];
+  memset(fv, 0, sizeof fv);
+  for (int i = 0; i < GPUD_FIELD_ROW_N; ++i) fv[i].field_id = kFieldRow[i];
+  const nvmlReturn_t rc = N->field_values(h, GPUD_FIELD_ROW_N, fv);
+  if (rc != 0) return (int32_t)rc;
+  for (int i = 0; i < GPUD_FIELD_ROW_N; ++i) {
+    if (rcs) rcs[i] = (int32_t)fv[i].nvml_return;
+    uint64_t v = 0;
+    if (fv[i].nvml_return == 0) {
+      switch (fv[i].value_type) {   // nvmlValueType_t: 0 double, 1 uint, 2 ulong, 3 ulonglong, 4 slonglong, 5 sint, 6 ushort
+        case 0: v = fv[i].value.d > 0 ? (uint64_t)fv[i].value.d : 0; break;
+        case 1: v = fv[i].value.ui; break;
+        case 2: v = fv[i].value.ul; break;
+        case 3: v = fv[i].value.ull; break;
+        case 4: v = (uint64_t)fv[i].value.sll; break;
+        case 5: v = (uint64_t)(int64_t)fv[i].value.si; break;
+        case 6: v = fv[i].value.us; break;
+      }
+    }
+    values[i] = v;
+  }
+  return 0;
+}
+
+extern "C" int32_t gpud_poller_field_row(gpud_poller* p, uint64_t* values, int32_t* nvml_rc) {
+  if (!p || !values) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->field_values) return GPUD_E_UNSUPPORTED;
+  const int32_t rc = field_row(N, p->h, values, nvml_rc);
+  return rc == 0 ? GPUD_OK : gpud_fail(p->ctx, GPUD_E_STATE, "nvmlDeviceGetFieldValues: %s", N->err ? N->err(rc) : "error");
+}
+
+// n_polls rows of GPUD_FIELD_ROW, one driver call each, appended to `ring` (GPUD_FIELD_ROW_N fields) as raw uint64 rows through
+// pinned memory; a field whose read fails holds its last good value, like gpud_poller_poll.
+extern "C" int32_t gpud_poller_poll_fields(gpud_poller* p, gpud_ring* ring, int64_t n_polls, int64_t interval_us, double* seconds) {
+  if (!p || !ring || n_polls < 0 || interval_us < 0) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->field_values) return GPUD_E_UNSUPPORTED;
+  if (!p->field_rows) {
+    if (cudaMallocHost(&p->field_rows, (size_t)p->cap_rows * GPUD_FIELD_ROW_N * sizeof(uint64_t)) != cudaSuccess) return gpud_fail(p->ctx, GPUD_E_CUDA, "pinned field rows");
+  }
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  int64_t done = 0;
+  while (done < n_polls) {
+    const int64_t batch = std::min<int64_t>(p->cap_rows, n_polls - done);
+    for (int64_t i = 0; i < batch; ++i) {
+      uint64_t v[GPUD_FIELD_ROW_N];
+      int32_t rcs[GPUD_FIELD_ROW_N];
+      const int32_t rc = field_row(N, p->h, v, rcs);
+      uint64_t* row = p->field_rows + i * GPUD_FIELD_ROW_N;
+      for (int c = 0; c < GPUD_FIELD_ROW_N; ++c) {
+        if (rc == 0 && rcs[c] == 0) p->field_held[c] = v[c];
+        row[c] = p->field_held[c];
+      }
+      if (interval_us) { timespec ts{(time_t)(interval_us / 1000000), (long)(interval_us % 1000000) * 1000L}; nanosleep(&ts, nullptr); }
+    }
+    const int32_t rc = gpud_ring_push_raw(ring, p->field_rows, batch, GPUD_DT_U64);
+    if (rc) return rc;
+    done += batch;
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   return GPUD_OK;
 }

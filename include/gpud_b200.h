@@ -39,7 +39,7 @@ typedef struct gpud_ring gpud_ring;
 int32_t gpud_abi_version(void);
 /* sizeof of the ABI structs for binding layout checks (5 gpud_kmsg_event, 6 gpud_ib_snapshot, 7 gpud_ib_verdict, 8 gpud_metric):
  * 0 gpud_xid_hit, 1 gpud_fabric_raw, 2 gpud_fabric_local,
- * 3 gpud_fabric_verdict, 4 gpud_ring_cfg; -1 otherwise. */
+ * 3 gpud_fabric_verdict, 4 gpud_ring_cfg, 9 gpud_dedup_rule .. 12 gpud_event_row, 13 gpud_nvml_device, 14 gpud_remapped_rows, 15 gpud_ecc_errors; -1 otherwise. */
 int32_t gpud_sizeof(int32_t which);
 
 /* One context per process; `cuda_devs[n]` are the CUDA ordinals this process drives (one per rank when
@@ -159,6 +159,40 @@ int32_t gpud_poller_counters(gpud_poller* poller, gpud_poll_counters* out);
  * the grid's CTAs, which then finishes a whole kernel-time late.  Leaving n_ctas slots out of the grid (work is divided over whatever
  * grid is launched; each slot costs 1/296 of the throughput) lets such kernels run concurrently.  Default 0. */
 int32_t gpud_ring_set_cta_reserve(gpud_ring* ring, int32_t n_ctas);
+/* Rows A3 / A4 of the hot path's NVML side.
+ * gpud_nvml_devices: nvml.New's enumeration (pkg/nvidia/nvml/instance.go:197-273, device/device.go:46-70): per device the UUID, the
+ * PCI bus id in go-nvlib's GetPCIBusID form ("0000:3b:00.0"; gpud_nvml_bus_id is that conversion alone), the product name, the CUDA
+ * ordinal (-1 if CUDA does not see it) and, when a getter failed, its NVML return code (the "errored instance" case).  *n = devices
+ * NVML reports (GPUD_E_CAPACITY if more than cap).  gpud_nvml_devices_arg renders "uuid=bus_id;..." - the `devices` argument of
+ * gpud_xid_state_from_store - and returns its length. */
+typedef struct { int32_t index, cuda_device, nvml_rc, pad; char uuid[96]; char bus_id[32]; char name[96]; } gpud_nvml_device;
+int32_t gpud_nvml_devices(gpud_nvml_device* out, int32_t cap, int32_t* n, char* driver_version, int32_t driver_version_cap);
+int32_t gpud_nvml_devices_arg(char* out, int32_t cap);
+int32_t gpud_nvml_bus_id(const char* nvml_bus_id, char* out, int32_t cap);
+/* GetRemappedRows (remapped-rows/remapped_rows.go:52-86) for the poller's GPU, and the component's Check over the box's readings
+ * (remapped-rows/component.go:197-300): *health 0 Healthy / 2 Unhealthy, *action GPUD_ACT_HARDWARE_INSPECTION once any GPU's remapping
+ * failed, else GPUD_ACT_REBOOT_SYSTEM when one is pending, else 0; returns the reason's length, -1 if it does not fit. */
+typedef struct { int32_t remapped_due_to_correctable_errors, remapped_due_to_uncorrectable_errors; uint8_t remapping_pending, remapping_failed, supported, pad; } gpud_remapped_rows;
+int32_t gpud_poller_remapped_rows(gpud_poller* poller, gpud_remapped_rows* out);
+int32_t gpud_remapped_rows_check(const gpud_remapped_rows* rows, const char* const* bus_ids, int32_t n, int32_t* health, int32_t* action, char* reason, int32_t cap);
+/* GetECCModeEnabled + GetECCErrors (ecc/ecc_mode.go, ecc/ecc_errors.go:136-880): totals and - with ECC mode on - the per-location
+ * counters nvmlDeviceGetMemoryErrorCounter reports, in the slots of the reference's AllECCErrorCounts; the first "not supported" ends
+ * the read with supported = 0. */
+enum { GPUD_ECC_TOTAL = 0, GPUD_ECC_L1 = 1, GPUD_ECC_L2 = 2, GPUD_ECC_DRAM = 3, GPUD_ECC_SRAM = 4, GPUD_ECC_DEVICE_MEMORY = 5, GPUD_ECC_TEXTURE_MEMORY = 6,
+       GPUD_ECC_SHARED_MEMORY = 7, GPUD_ECC_REGISTER_FILE = 8, GPUD_ECC_N_LOCATIONS = 9 };
+typedef struct { uint64_t corrected, uncorrected; } gpud_ecc_counts;
+typedef struct { gpud_ecc_counts aggregate[GPUD_ECC_N_LOCATIONS]; gpud_ecc_counts volatile_[GPUD_ECC_N_LOCATIONS]; uint8_t ecc_mode_current, ecc_mode_pending, supported, pad[5]; } gpud_ecc_errors;
+int32_t gpud_poller_ecc_errors(gpud_poller* poller, gpud_ecc_errors* out);
+/* One driver round trip per poll row: nvmlDeviceGetFieldValues over the GPUD_FIELD_ROW_N counters below, widened to
+ * uint64.  gpud_poller_field_row reads one row (nvml_rc[i] = that field's own return code, may be NULL); gpud_poller_poll_fields takes
+ * n_polls rows and appends them to `ring` (GPUD_FIELD_ROW_N fields) as raw uint64 rows; a field that fails holds its last good value. */
+enum { GPUD_FIELD_POWER_INSTANT_MW = 0, GPUD_FIELD_POWER_AVERAGE_MW = 1, GPUD_FIELD_MEMORY_TEMP_C = 2, GPUD_FIELD_TOTAL_ENERGY_MJ = 3,
+       GPUD_FIELD_ECC_SBE_VOLATILE = 4, GPUD_FIELD_ECC_DBE_VOLATILE = 5, GPUD_FIELD_ECC_SBE_AGGREGATE = 6, GPUD_FIELD_ECC_DBE_AGGREGATE = 7,
+       GPUD_FIELD_NVLINK_CRC_FLIT_TOTAL = 8, GPUD_FIELD_NVLINK_CRC_DATA_TOTAL = 9, GPUD_FIELD_NVLINK_REPLAY_TOTAL = 10, GPUD_FIELD_NVLINK_RECOVERY_TOTAL = 11,
+       GPUD_FIELD_REMAPPED_CORRECTABLE = 12, GPUD_FIELD_REMAPPED_UNCORRECTABLE = 13, GPUD_FIELD_REMAPPED_PENDING = 14, GPUD_FIELD_REMAPPED_FAILURE = 15,
+       GPUD_FIELD_PCIE_REPLAY = 16, GPUD_FIELD_ROW_N = 17 };
+int32_t gpud_poller_field_row(gpud_poller* poller, uint64_t* values, int32_t* nvml_rc);
+int32_t gpud_poller_poll_fields(gpud_poller* poller, gpud_ring* ring, int64_t n_polls, int64_t interval_us, double* seconds);
 int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
 /* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
 int32_t gpud_ring_reduce(gpud_ring* ring);

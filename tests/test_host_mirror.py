@@ -695,3 +695,34 @@ def test_poll_row_holds_the_last_good_value_when_a_getter_fails():
     held2 = [0] * 8
     row, mask = g.capi.poll_row_hold([7] * 8, [3] * 8, held2)
     assert row == [0] * 8 and mask == 0xFF
+
+
+def test_remapped_rows_check_of_the_reference():
+    """remapped-rows/component.go:197-300 with the devices of TestCheckOnceRemappingIssueDetection (component_test.go:405-517) and
+    TestCheckOnceWithMultipleGPUs (:1288-1394): reason fragments, health and the suggested action (RMA takes precedence)."""
+    R = g.capi.RemappedRows
+    rows = [R(0, 0, 0, 0, 1, 0), R(0, 0, 1, 0, 1, 0), R(0, 2, 0, 1, 1, 0)]
+    health, action, reason = g.capi.remapped_rows_check(rows, ["0000:01:00.0", "0000:02:00.0", "0000:03:00.0"])
+    assert health == 2 and action == 3                      # Unhealthy, HARDWARE_INSPECTION
+    assert reason == "0000:02:00.0 needs reset (detected pending row remapping), 0000:03:00.0 qualifies for RMA (row remapping failed, remapped due to 2 uncorrectable error(s))"
+    # the order of the devices does not let a later pending GPU take the action back from an earlier failed one
+    health, action, reason = g.capi.remapped_rows_check(rows[::-1], ["0000:03:00.0", "0000:02:00.0", "0000:01:00.0"])
+    assert health == 2 and action == 3 and reason.startswith("0000:03:00.0 qualifies for RMA")
+    # only pending: reboot
+    health, action, reason = g.capi.remapped_rows_check(rows[:2], ["0000:01:00.0", "0000:02:00.0"])
+    assert (health, action, reason) == (2, 2, "0000:02:00.0 needs reset (detected pending row remapping)")
+    # a GPU that is both failed and pending reports both issues, RMA first (:288-293)
+    health, action, reason = g.capi.remapped_rows_check([R(1, 9, 1, 1, 1, 0)], ["0000:0f:00.0"])
+    assert action == 3 and reason == ("0000:0f:00.0 qualifies for RMA (row remapping failed, remapped due to 9 uncorrectable error(s)), "
+                                      "0000:0f:00.0 needs reset (detected pending row remapping)")
+    # nothing wrong
+    assert g.capi.remapped_rows_check(rows[:1] * 8, ["x"] * 8) == (0, 0, "8 devices support remapped rows and found no issue")
+    assert g.capi.remapped_rows_check([], []) == (0, 0, "0 devices support remapped rows and found no issue")
+
+
+def test_nvml_bus_id_like_go_nvlib():
+    """go-nvlib device.GetPCIBusID: lower case, the first four zeros of NVML's eight-digit domain dropped"""
+    assert g.capi.nvml_bus_id("00000000:3B:00.0") == "0000:3b:00.0"
+    assert g.capi.nvml_bus_id("00000001:0F:00.0") == "0001:0f:00.0"
+    assert g.capi.nvml_bus_id("0000:9b:00.0") == ":9b:00.0"          # what TrimPrefix does to an already short id
+    assert g.capi.nvml_bus_id("0000") == "0000"
