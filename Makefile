@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v
 SRC := gpud_b200/csrc
-OBJS := $(SRC)/api.o $(SRC)/ring.o $(SRC)/select.o $(SRC)/kmsg_scan.o $(SRC)/ib_scan.o $(SRC)/fabric.o $(SRC)/catalog.o $(SRC)/host_component.o $(SRC)/kmsg_stateful.o $(SRC)/poller.o $(SRC)/store_sqlite.o
+OBJS := $(SRC)/api.o $(SRC)/ring.o $(SRC)/select.o $(SRC)/kmsg_scan.o $(SRC)/ib_scan.o $(SRC)/fabric.o $(SRC)/catalog.o $(SRC)/host_component.o $(SRC)/component_abi.o $(SRC)/kmsg_stateful.o $(SRC)/poller.o $(SRC)/store_sqlite.o
 LIB := gpud_b200/libgpud_b200.so
 
 all: $(LIB) oracle
@@ -16,6 +16,9 @@ $(SRC)/catalog.o: $(SRC)/catalog.cpp $(SRC)/catalog.h $(SRC)/catalog_data.inc in
 
 $(SRC)/host_component.o: $(SRC)/host_component.cpp $(SRC)/host_component.h $(SRC)/json_min.h include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
+
+$(SRC)/component_abi.o: $(SRC)/component_abi.cpp $(SRC)/host_component.h $(SRC)/internal.h include/gpud_b200.h
+	g++ -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
 
 $(SRC)/poller.o: $(SRC)/poller.cpp $(SRC)/internal.h include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@

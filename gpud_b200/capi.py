@@ -496,9 +496,114 @@ class KmsgStateful:
             raise GpudError(rc, "gpud_kmsg_stateful_feed")
         return [(out[i].unit_index, out[i].component.decode(), out[i].event.decode(), out[i].message.decode("latin-1")) for i in range(n.value)]
 
+    def feed_units(self, hits, buf: bytes, n_units: int, dropped: bytes, cap: int = 4096):
+        """gpud_kmsg_stateful_feed_units: feed without the units the watcher's dedup dropped (dropped[u] != 0)"""
+        arr = (XidHit * max(1, len(hits)))(*hits)
+        out = (KmsgEvent * cap)()
+        n = C.c_int32()
+        rc = self._L.gpud_kmsg_stateful_feed_units(self._h, arr, len(hits), C.cast(C.c_char_p(buf), C.c_void_p), n_units, C.cast(C.c_char_p(dropped), C.c_void_p),
+                                                   out, cap, C.byref(n))
+        if rc:
+            raise GpudError(rc, "gpud_kmsg_stateful_feed_units")
+        return [(out[i].unit_index, out[i].component.decode(), out[i].event.decode(), out[i].message.decode("latin-1")) for i in range(n.value)]
+
     def close(self):
         if self._h:
             self._L.gpud_kmsg_stateful_destroy(self._h)
+            self._h = None
+
+
+class ComponentCfg(C.Structure):
+    _fields_ = [("row_remapping_supported", C.c_int32), ("reboot_threshold", C.c_int32), ("margin_threshold_c", C.c_int32), ("nvlink_at_least", C.c_int32)]
+
+
+class Component:
+    """gpud_component_*: the mirror of components.Component (components/types.go:20-66) for the xid / temperature / nvlink paths"""
+
+    def __init__(self, ctx: "Context", name: str, **cfg):
+        import json
+        self._json = json
+        self.ctx, self._L = ctx, ctx._L
+        c = ComponentCfg(**cfg)
+        self._h = C.c_void_p()
+        ctx._check(self._L.gpud_component_create(ctx._h, name.encode(), C.byref(c), C.byref(self._h)))
+
+    def name(self) -> str:
+        b = C.create_string_buffer(128)
+        self._L.gpud_component_name(self._h, b, 128)
+        return b.value.decode()
+
+    def start(self, interval_ms: int):
+        self.ctx._check(self._L.gpud_component_start(self._h, interval_ms))
+
+    def check(self):
+        health, b = C.c_int32(), C.create_string_buffer(8192)
+        self.ctx._check(self._L.gpud_component_check(self._h, C.byref(health), b, 8192))
+        return health.value, b.value.decode()
+
+    def last_health_states(self):
+        b = C.create_string_buffer(1 << 16)
+        n = self._L.gpud_component_last_health_states(self._h, b, 1 << 16)
+        if n < 0:
+            raise GpudError(n, "gpud_component_last_health_states")
+        return self._json.loads(b.value.decode())
+
+    def events(self, since_unix: int = 0):
+        b = C.create_string_buffer(1 << 20)
+        n = self._L.gpud_component_events(self._h, since_unix, b, 1 << 20)
+        if n < 0:
+            raise GpudError(n, "gpud_component_events")
+        return self._json.loads(b.value.decode())
+
+    def checks(self) -> int:
+        return int(self._L.gpud_component_checks(self._h))
+
+    def xid_set_source(self, buf: bytes, raw_kmsg: bool = False, boot_unix: int = 0):
+        self.ctx._check(self._L.gpud_component_xid_set_source(self._h, C.cast(C.c_char_p(buf), C.c_void_p), len(buf), int(raw_kmsg), boot_unix))
+
+    def xid_set_healthy(self, now_unix: int):
+        self.ctx._check(self._L.gpud_component_xid_set_healthy(self._h, now_unix))
+
+    def xid_add_reboot(self, unix_s: int):
+        self.ctx._check(self._L.gpud_component_xid_add_reboot(self._h, unix_s))
+
+    def xid_set_devices(self, devices: str):
+        self.ctx._check(self._L.gpud_component_xid_set_devices(self._h, devices.encode()))
+
+    def stop(self):
+        """Close(): stops the ticker; the object stays readable"""
+        self.ctx._check(self._L.gpud_component_close(self._h))
+
+    def ring_handle(self, slot: int = 0):
+        return self._L.gpud_component_ring(self._h, slot)
+
+    def close(self):
+        if self._h:
+            self._L.gpud_component_close(self._h)
+            self._L.gpud_component_destroy(self._h)
+            self._h = None
+
+
+class KmsgDeduper:
+    """the kmsg watcher's duplicate drop (pkg/kmsg/watcher.go:281-286) over the units of a scanned buffer"""
+
+    def __init__(self, ttl_seconds: int = 0, truncate_seconds: int = 0):
+        self._L = lib()
+        self._L.gpud_kmsg_deduper_create.restype = C.c_void_p
+        self._h = C.c_void_p(self._L.gpud_kmsg_deduper_create(C.c_int64(ttl_seconds), C.c_int32(truncate_seconds)))
+
+    def units(self, buf: bytes, n_units: int, mode: int = 0, boot_unix: int = 0, lines_unix: int = 0, now_unix: int = 0) -> bytes:
+        dropped = C.create_string_buffer(max(1, n_units))
+        nd = C.c_int64()
+        rc = self._L.gpud_kmsg_dedup_units(self._h, C.cast(C.c_char_p(buf), C.c_void_p), C.c_int64(len(buf)), C.c_int32(mode), C.c_int64(boot_unix), C.c_int64(lines_unix),
+                                           C.c_int64(now_unix), dropped, C.c_int64(n_units), C.byref(nd))
+        if rc:
+            raise GpudError(rc, "gpud_kmsg_dedup_units")
+        return dropped.raw[:n_units]
+
+    def close(self):
+        if self._h:
+            self._L.gpud_kmsg_deduper_destroy(self._h)
             self._h = None
 
 
@@ -539,7 +644,7 @@ SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destr
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
            "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_record_reboot", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_errors", "gpud_poll_row_hold", "gpud_nvml_devices", "gpud_nvml_devices_arg", "gpud_nvml_bus_id", "gpud_poller_remapped_rows", "gpud_remapped_rows_check", "gpud_poller_ecc_errors", "gpud_poller_field_row", "gpud_poller_poll_fields", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_ring_range_stats", "gpud_ring_set_cta_reserve", "gpud_kmsg_scan", "gpud_kmsg_scan_sharded", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_stats", "gpud_xid_classify",
-           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed",
+           "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed", "gpud_component_create", "gpud_component_destroy", "gpud_component_name", "gpud_component_start", "gpud_component_check", "gpud_component_last_health_states", "gpud_component_events", "gpud_component_close", "gpud_component_checks", "gpud_component_xid_set_source", "gpud_component_xid_set_healthy", "gpud_component_xid_add_reboot", "gpud_component_xid_set_devices", "gpud_component_ring", "gpud_kmsg_stateful_feed_units", "gpud_kmsg_deduper_create", "gpud_kmsg_deduper_destroy", "gpud_kmsg_dedup_units",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_set_nvml_error_string", "gpud_nvml_error_strings_from_driver", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
            "gpud_fabric_gather_p2p"]
 
@@ -616,6 +721,13 @@ def lib() -> C.CDLL:
         "gpud_kmsg_component": (C.c_char_p, [i32]), "gpud_kmsg_hit_message": (i32, [vp, vp, vp, i32]),
         "gpud_kmsg_stateful_create": (i32, [vp]), "gpud_kmsg_stateful_destroy": (None, [vp]),
         "gpud_kmsg_stateful_feed": (i32, [vp, vp, i64, vp, i64, vp, i32, vp]),
+        "gpud_component_create": (i32, [vp, C.c_char_p, vp, vp]), "gpud_component_destroy": (None, [vp]), "gpud_component_name": (i32, [vp, vp, i32]),
+        "gpud_component_start": (i32, [vp, i64]), "gpud_component_check": (i32, [vp, vp, vp, i32]), "gpud_component_last_health_states": (i32, [vp, vp, i32]),
+        "gpud_component_events": (i32, [vp, i64, vp, i32]), "gpud_component_close": (i32, [vp]), "gpud_component_checks": (i64, [vp]),
+        "gpud_component_xid_set_source": (i32, [vp, vp, i64, i32, i64]), "gpud_component_xid_set_healthy": (i32, [vp, i64]),
+        "gpud_component_xid_add_reboot": (i32, [vp, i64]), "gpud_component_xid_set_devices": (i32, [vp, C.c_char_p]), "gpud_component_ring": (vp, [vp, i32]),
+        "gpud_kmsg_stateful_feed_units": (i32, [vp, vp, i64, vp, i64, vp, vp, i32, vp]), "gpud_kmsg_deduper_create": (vp, [i64, i32]),
+        "gpud_kmsg_deduper_destroy": (None, [vp]), "gpud_kmsg_dedup_units": (i32, [vp, vp, i64, i32, i64, i64, i64, vp, i64, vp]),
         "gpud_fabric_pack": (i32, [vp, i32, C.POINTER(FabricRaw), vp, vp]),
         "gpud_fabric_verdict_device": (i32, [vp, i32, vp, i32, i32, C.POINTER(FabricVerdict), vp]),
         "gpud_comm_unique_id": (i32, [vp]), "gpud_comm_init": (i32, [vp, i32, i32, i32, vp]),

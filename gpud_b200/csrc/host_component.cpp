@@ -32,7 +32,7 @@ const char* repair_action_string(int32_t a) {    // api/v1/types.go:183-203
   return "";
 }
 
-static void jstr(std::string& o, const std::string& s) {
+void jstr(std::string& o, const std::string& s) {
   o.push_back('"');
   for (unsigned char c : s) {
     if (c == '"') o += "\\\"";
@@ -825,6 +825,38 @@ extern "C" int32_t gpud_hw_slowdown_check(const int64_t* event_unix, int32_t n, 
   return GPUD_OK;
 }
 
+// ---- the kmsg watcher's duplicate drop (pkg/kmsg/watcher.go:281-286) over the units of a scanned buffer ----------------------------
+// readFollow / ReadAll hand a parsed message to the matchers only the first time its (minute, message) key shows up within the
+// cache TTL (deduper.go:63-125).  dropped[u] = 1 for every unit the watcher would have skipped; the cache lives in `d` across calls.
+extern "C" int32_t gpud_kmsg_dedup_units(void* d, const uint8_t* buf, int64_t len, int32_t mode, int64_t boot_unix, int64_t lines_unix, int64_t now_unix,
+                                         uint8_t* dropped, int64_t n_units, int64_t* n_dropped) {
+  if (!d || len < 0 || (len && !buf) || !dropped || n_units < 0) return GPUD_E_INVALID;
+  gpud::Deduper* dd = static_cast<gpud::Deduper*>(d);
+  const bool raw = (mode & 0xff) == GPUD_SCAN_RAW_KMSG;
+  int64_t u = 0, start = 0, nd = 0;
+  for (int64_t i = 0; i <= len && u < n_units; ++i) {
+    const bool sep = i == len || (buf[i] == '\n' && (!raw || i + 1 >= len || buf[i + 1] != ' '));
+    if (!sep) continue;
+    const std::string unit(reinterpret_cast<const char*>(buf) + start, (size_t)(i - start));
+    dropped[u] = 0;
+    if (!unit.empty()) {                                       // `if len(line) == 0 { continue }` (watcher.go:271-273)
+      if (raw) {
+        gpud::KmsgMessage m;
+        std::string err;
+        if (gpud::parse_kmsg_line(unit, &m, &err)) dropped[u] = dd->add(now_unix, boot_unix + m.usec_since_boot / 1000000, m.message) > 1;
+      } else {
+        dropped[u] = dd->add(now_unix, lines_unix, unit) > 1;
+      }
+    }
+    nd += dropped[u];
+    ++u;
+    start = i + 1;
+  }
+  for (; u < n_units; ++u) dropped[u] = 0;
+  if (n_dropped) *n_dropped = nd;
+  return GPUD_OK;
+}
+
 // ---- flat C entry points so the host mirror is testable through ctypes (not part of gpud_b200.h) ----
 extern "C" {
 
@@ -844,6 +876,8 @@ void* gpudh_deduper_new(int64_t ttl) { return new gpud::Deduper(ttl); }
 void* gpudh_deduper_new2(int64_t ttl, int32_t truncate_seconds) { return new gpud::Deduper(ttl, truncate_seconds > 0 ? truncate_seconds : 60); }   // WithCacheKeyTruncateSeconds
 int32_t gpudh_deduper_add(void* d, int64_t now, int64_t t, const char* msg) { return static_cast<gpud::Deduper*>(d)->add(now, t, msg); }
 void gpudh_deduper_free(void* d) { delete static_cast<gpud::Deduper*>(d); }
+void* gpud_kmsg_deduper_create(int64_t ttl, int32_t truncate_seconds) { return new gpud::Deduper(ttl > 0 ? ttl : 15 * 60, truncate_seconds > 0 ? truncate_seconds : 60); }
+void gpud_kmsg_deduper_destroy(void* d) { delete static_cast<gpud::Deduper*>(d); }
 
 // events: n records of {kind 0 xid / 1 reboot / 2 SetHealthy(ignored here), event_type, xid, n_actions(-1 nil), actions[4]} newest first
 typedef struct { int32_t kind, event_type; uint64_t xid; int32_t n_actions; int32_t actions[4]; } gpudh_event;
@@ -1015,7 +1049,8 @@ int32_t gpudh_xid_component_state_json(void* c, char* out, int32_t cap) {
 }
 int32_t gpudh_xid_component_reboot(void* c, int64_t t) { static_cast<gpud::XidComponent*>(c)->AddRebootEvent(t); static_cast<gpud::XidComponent*>(c)->Start(); return 0; }
 int32_t gpudh_xid_component_set_healthy(void* c, int64_t t) { return static_cast<gpud::XidComponent*>(c)->SetHealthy(t); }
-int32_t gpudh_xid_component_n_events(void* c) { return (int32_t)static_cast<gpud::XidComponent*>(c)->Events(0).size(); }
+int32_t gpudh_xid_component_n_events(void* c) { return (int32_t)static_cast<gpud::XidComponent*>(c)->Events(INT64_MIN).size(); }
+int32_t gpudh_xid_component_n_events_since(void* c, int64_t since) { return (int32_t)static_cast<gpud::XidComponent*>(c)->Events(since).size(); }
 const char* gpudh_xid_component_name(void) { return gpud::XidComponent::kName; }
 int32_t gpudh_hw_slowdown(const int64_t* ev, int32_t n, int64_t now, int64_t window_s, double thr, double* freq, int32_t* distinct) {
   const gpud::SlowdownVerdict v = gpud::evaluate_hw_slowdown(std::vector<int64_t>(ev, ev + n), now, window_s, thr);

@@ -25,6 +25,7 @@ const char* health_string(Health h);            // "Healthy" | "Degraded" | "Unh
 const char* event_type_string(int32_t t);       // GPUD_EVENT_* -> "Unknown" | "Info" | "Warning" | "Critical" | "Fatal"
 const char* repair_action_string(int32_t a);    // GPUD_ACT_*   -> "REBOOT_SYSTEM" ...
 
+void jstr(std::string& out, const std::string& s);   // append s as a JSON string the way encoding/json escapes it
 struct SuggestedActions { std::vector<int32_t> repair_actions; };
 struct HealthState {
   int64_t time_unix = 0;                          // 0 = the zero time (JSON null)

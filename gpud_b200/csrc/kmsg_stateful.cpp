@@ -112,8 +112,8 @@ extern "C" int32_t gpud_kmsg_stateful_create(gpud_kmsg_stateful** out) {
 }
 extern "C" void gpud_kmsg_stateful_destroy(gpud_kmsg_stateful* st) { delete st; }
 
-extern "C" int32_t gpud_kmsg_stateful_feed(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
-                                           gpud_kmsg_event* out, int32_t cap, int32_t* n_out) {
+static int32_t stateful_feed(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
+                             gpud_kmsg_event* out, int32_t cap, int32_t* n_out) {
   if (!st || n_hits < 0 || (n_hits && (!hits || !buf)) || n_units < 0 || cap < 0 || (cap && !out)) return GPUD_E_INVALID;
   Sink sink{out, cap};
   int64_t i = 0;
@@ -189,4 +189,38 @@ extern "C" int32_t gpud_kmsg_stateful_feed(gpud_kmsg_stateful* st, const gpud_xi
   st->base += n_units;
   if (n_out) *n_out = sink.n;
   return sink.n > cap ? GPUD_E_CAPACITY : GPUD_OK;
+}
+
+
+extern "C" int32_t gpud_kmsg_stateful_feed(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
+                                           gpud_kmsg_event* out, int32_t cap, int32_t* n_out) {
+  return stateful_feed(st, hits, n_hits, buf, n_units, out, cap, n_out);
+}
+
+// The same with the units the kmsg watcher would have dropped as duplicates (pkg/kmsg/watcher.go:281-286, see gpud_kmsg_dedup_units)
+// taken out first: the matchers never see such a line, so it neither matches nor counts towards the panic matcher's ten lines.
+// Events are reported with the unit numbers of the scanned buffer.
+extern "C" int32_t gpud_kmsg_stateful_feed_units(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
+                                                 const uint8_t* dropped, gpud_kmsg_event* out, int32_t cap, int32_t* n_out) {
+  if (!dropped) return stateful_feed(st, hits, n_hits, buf, n_units, out, cap, n_out);
+  if (!st || n_hits < 0 || (n_hits && (!hits || !buf)) || n_units < 0 || cap < 0 || (cap && !out)) return GPUD_E_INVALID;
+  std::vector<int64_t> kept;                       // filtered unit number -> unit number in the buffer
+  std::vector<int64_t> renum((size_t)n_units, -1);
+  for (int64_t u = 0; u < n_units; ++u)
+    if (!dropped[u]) { renum[(size_t)u] = (int64_t)kept.size(); kept.push_back(u); }
+  std::vector<gpud_xid_hit> h2;
+  for (int64_t i = 0; i < n_hits; ++i) {
+    const int64_t u = hits[i].unit_index;
+    if (u < 0 || u >= n_units || renum[(size_t)u] < 0) continue;
+    h2.push_back(hits[i]);
+    h2.back().unit_index = renum[(size_t)u];
+  }
+  int32_t n = 0;
+  const int32_t rc = stateful_feed(st, h2.data(), (int64_t)h2.size(), buf, (int64_t)kept.size(), out, cap, &n);
+  for (int32_t i = 0; i < n && i < cap; ++i) {
+    const int64_t f = out[i].unit_index;
+    if (f >= 0 && f < (int64_t)kept.size()) out[i].unit_index = kept[(size_t)f];
+  }
+  if (n_out) *n_out = n;
+  return rc;
 }

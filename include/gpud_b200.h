@@ -222,6 +222,46 @@ enum { GPUD_RANGE_OPEN_SHORT = 1,    /* the range is shorter than the single-pas
 int32_t gpud_ring_range_stats(gpud_ring* ring, float* pass_ms, float* total_ms, int32_t* fields_by_histogram, int32_t* reasons);
 
 /* ------------------------------------------------------------------------------------------------
+ * components.Component (components/types.go:20-66) for the three paths this library replaces, as objects: what a Go file that
+ * implements the interface forwards to, method by method.
+ *   name                                 reference component                           Check()
+ *   "accelerator-nvidia-error-xid"       xid/component.go:255-311, 468-611             scan the kmsg bytes on the GPU, persist new hits in the
+ *                                                                                      event bucket, evolveHealthyState over bucket + reboots
+ *   "accelerator-nvidia-temperature"     temperature/component.go:81-287               one NVML poll row per GPU into its ring (the windowed
+ *                                                                                      aggregates stay readable through gpud_component_ring),
+ *                                                                                      the threshold rules over the current reading
+ *   "accelerator-nvidia-nvlink"          nvlink/component.go:164-311                   every GPU's NVLink / fabric record, gathered over NVLink
+ *                                                                                      peer stores, the replicated box verdict
+ * Start is non-blocking: it spawns a ticker that runs Check at once and then every interval; Check embeds errors in the state and
+ * never fails the call; LastHealthStates is the cached apiv1.HealthStates JSON, a single Healthy "no data yet" state before the first
+ * check; Events is apiv1.Events JSON, newest first, strictly after `since`; Close stops the ticker.  Safe to call from any thread.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct gpud_component gpud_component;
+typedef struct {
+  int32_t row_remapping_supported; /* xid: drop Xid 63 / 64, they belong to the remapped-rows component (xid/component.go:290) */
+  int32_t reboot_threshold;        /* xid: reboots after which the action becomes HARDWARE_INSPECTION (default 2)               */
+  int32_t margin_threshold_c;      /* temperature: thermal-margin rule, 0 = off (temperature/threshold.go:13)                   */
+  int32_t nvlink_at_least;         /* nvlink: GPUs that must have every link up, 0 = no threshold (nvlink/threshold.go)         */
+} gpud_component_cfg;
+int32_t gpud_component_create(gpud_ctx* ctx, const char* name, const gpud_component_cfg* cfg /* NULL = defaults */, gpud_component** out);
+void gpud_component_destroy(gpud_component* c);
+int32_t gpud_component_name(gpud_component* c, char* out, int32_t cap);
+int32_t gpud_component_start(gpud_component* c, int64_t interval_ms);                       /* Start() */
+int32_t gpud_component_check(gpud_component* c, int32_t* health, char* reason, int32_t cap); /* Check(): health 0 Healthy / 1 Degraded / 2 Unhealthy */
+int32_t gpud_component_last_health_states(gpud_component* c, char* json, int32_t cap);       /* returns the length */
+int32_t gpud_component_events(gpud_component* c, int64_t since_unix, char* json, int32_t cap);
+int32_t gpud_component_close(gpud_component* c);                                             /* Close() */
+int64_t gpud_component_checks(gpud_component* c);                                            /* checks run so far (ticker + direct) */
+/* xid: the bytes Check scans (what kmsg.ReadAll returned; raw_kmsg: /dev/kmsg records, event time = boot_unix + usec), SetHealthy
+ * (xid/set_healthy.go:14-35), a reboot event of the os bucket, the UUID -> bus id map ("uuid=bus_id;...", gpud_nvml_devices_arg). */
+int32_t gpud_component_xid_set_source(gpud_component* c, const uint8_t* buf, int64_t len, int32_t raw_kmsg, int64_t boot_unix);
+int32_t gpud_component_xid_set_healthy(gpud_component* c, int64_t now_unix);
+int32_t gpud_component_xid_add_reboot(gpud_component* c, int64_t unix_s);
+int32_t gpud_component_xid_set_devices(gpud_component* c, const char* devices);
+/* temperature: the ring the polls of the ctx's slot-th device land in (NULL otherwise) */
+gpud_ring* gpud_component_ring(gpud_component* c, int32_t slot);
+
+/* ------------------------------------------------------------------------------------------------
  * kmsg Xid / SXid scan + classification.
  * Replaces: xid.Match (components/accelerator/nvidia/xid/kmsg.go:202-245 with the regexes at :22,:29,:38,:43),
  * sxid.Match (sxid/kmsg.go:58-73, regexes :17,:20), the catalog lookups GetDetail / detailFromNVLinkInfo
@@ -382,6 +422,17 @@ int32_t gpud_kmsg_stateful_create(gpud_kmsg_stateful** out);
 void gpud_kmsg_stateful_destroy(gpud_kmsg_stateful* st);
 int32_t gpud_kmsg_stateful_feed(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
                                 gpud_kmsg_event* out, int32_t cap, int32_t* n_out);
+/* The kmsg watcher hands a message to the matchers only the first time its (minute, message) key shows up within the cache TTL
+ * (pkg/kmsg/watcher.go:281-286, deduper.go:63-125).  gpud_kmsg_dedup_units marks the units of a scanned buffer the watcher would have
+ * skipped (dropped[u] = 1); `deduper` is the cache, kept across calls (gpud_kmsg_deduper_create: ttl 0 = the reference's 15 min,
+ * truncate 0 = 60 s).  RAW_KMSG units are timed boot_unix + usec, LINES units all carry lines_unix.  gpud_kmsg_stateful_feed_units is
+ * gpud_kmsg_stateful_feed without those units: a dropped line neither matches nor counts towards the panic matcher's ten lines. */
+void* gpud_kmsg_deduper_create(int64_t ttl_seconds, int32_t truncate_seconds);
+void gpud_kmsg_deduper_destroy(void* deduper);
+int32_t gpud_kmsg_dedup_units(void* deduper, const uint8_t* buf, int64_t len, int32_t mode, int64_t boot_unix, int64_t lines_unix, int64_t now_unix,
+                              uint8_t* dropped, int64_t n_units, int64_t* n_dropped);
+int32_t gpud_kmsg_stateful_feed_units(gpud_kmsg_stateful* st, const gpud_xid_hit* hits, int64_t n_hits, const uint8_t* buf, int64_t n_units,
+                                      const uint8_t* dropped, gpud_kmsg_event* out, int32_t cap, int32_t* n_out);
 
 /* Write path into the reference's SQLite stores: the same tables, columns, indexes and statements as
  * pkg/eventstore/database.go:136-143,198-275 and pkg/metrics/store/sqlite.go:87-164, so gpud's /v1/events and /v1/metrics

@@ -21,6 +21,20 @@ def test_header_symbols_exported():
         assert hasattr(L, s), s
 
 
+def test_every_exported_symbol_is_declared():
+    """the reverse: nothing is exported that a header does not declare - the integrator's header, or the test hooks' own header"""
+    import subprocess
+    decl = set()
+    for h in ("gpud_b200.h", "gpud_b200_hooks.h"):
+        decl |= set(re.findall(r"\b(gpudh?_[a-z0-9_]+)\s*\(", open(os.path.join(ROOT, "include", h)).read()))
+    out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and re.match(r"gpudh?_", l.split()[-1])}
+    internal = {"gpud_ring_range_prepare", "gpud_ring_range_pass", "gpud_ring_range_note", "gpud_ring_quantile", "gpud_scan_state_free", "gpud_comm_state_free",
+                "gpud_parallel_memcpy", "gpud_host_tables"}      # C++-mangled internals never match; these are listed for clarity
+    assert exported - internal <= decl, sorted(exported - internal - decl)
+    assert decl <= exported, sorted(decl - exported)
+
+
 def test_layout_and_version():
     L = g.lib()
     assert L.gpud_abi_version() == 1

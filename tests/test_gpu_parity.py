@@ -1022,3 +1022,70 @@ def test_xid_component_check_and_state(ctx):
         L.gpudh_xid_component_state_json(comp, out, 2048)
         assert json.loads(out.value)["health"] == "Healthy"
         L.gpudh_xid_component_free(comp)
+
+
+def test_component_objects_of_the_three_paths(ctx):
+    """components.Component (components/types.go:20-66) through the C ABI (gpud_component_*): Start is non-blocking and spawns the ticker,
+    LastHealthStates is "no data yet" before the first check, Check embeds its result, Events(since) is strictly after `since`, newest
+    first, Close stops the ticker; one object per path this library replaces."""
+    import time
+    # ---- xid: scan + persist + evolve ----
+    G = synth.golden("xid_kmsg.json")
+    lines = G["dmesg_xid_119"]["lines"] + ["NVRM: Xid (PCI:0000:04:00): 31, pid=1, name=a, mmu fault"]
+    x = g.capi.Component(ctx, "accelerator-nvidia-error-xid", row_remapping_supported=1)
+    assert x.name() == "accelerator-nvidia-error-xid"
+    st = x.last_health_states()
+    assert len(st) == 1 and st[0]["health"] == "Healthy"
+    x.xid_set_source("\n".join(lines).encode())
+    health, reason = x.check()
+    assert health == 2 and reason == "matched 6 xid errors from %d kmsg(s)" % len(lines)
+    st = x.last_health_states()
+    assert st[0]["health"] == "Unhealthy" and st[0]["suggested_actions"]["repair_actions"] == ["REBOOT_SYSTEM"] and "XID 119" in st[0]["reason"]
+    ev = x.events(0)
+    # five identical Xid 119 lines of one second are one event for the bucket (eventBucket.Find, component.go:555-563), the Xid 31 another
+    assert len(ev) == 2 and all(e["component"] == "accelerator-nvidia-error-xid" and e["name"] == "error_xid" for e in ev)
+    assert sorted(e["type"] for e in ev) == ["Fatal", "Warning"]
+    assert [e["time"] for e in ev] == sorted((e["time"] for e in ev), reverse=True)
+    now = int(time.time())
+    assert x.events(now + 5) == []                                  # strictly after `since` (pkg/eventstore/database.go:330)
+    x.check()
+    assert len(x.events(0)) in (2, 4)                               # a check within the same second inserts nothing new
+    x.xid_add_reboot(now + 60)
+    assert x.last_health_states()[0]["health"] == "Healthy"         # a reboot after the errors clears REBOOT_SYSTEM
+    x.close()
+    # ---- temperature: Start -> ticker -> Check every interval; the polls land in the component's ring ----
+    try:
+        t = g.capi.Component(ctx, "accelerator-nvidia-temperature")
+    except g.GpudError as e:
+        pytest.skip("no NVML on this host: %s" % e)
+    assert t.last_health_states()[0]["reason"] == "no data yet"
+    t0 = time.perf_counter()
+    t.start(20)
+    assert time.perf_counter() - t0 < 0.5                           # Start does not block
+    deadline = time.time() + 5
+    while t.checks() < 5 and time.time() < deadline:
+        time.sleep(0.01)
+    assert t.checks() >= 5
+    st = t.last_health_states()[0]
+    assert st["component"] == st["name"] == "accelerator-nvidia-temperature" and st["health"] == "Healthy"
+    assert st["reason"] == "all 1 GPU(s) were checked, no temperature issue found"
+    assert t.events(0) == []
+    t.stop()
+    n = t.checks()
+    time.sleep(0.1)
+    assert t.checks() == n                                          # Close stopped the ticker
+    t.close()
+    t2 = g.capi.Component(ctx, "accelerator-nvidia-temperature", margin_threshold_c=200)
+    health, reason = t2.check()
+    assert health == 1 and "margin left to slowdown" in reason     # Degraded through the margin rule on a real reading
+    assert t2.ring_handle(0)
+    t2.close()
+    # ---- nvlink: NVML records -> peer-store gather -> verdict ----
+    nv = g.capi.Component(ctx, "accelerator-nvidia-nvlink")
+    health, reason = nv.check()
+    assert health == 0 and reason == "all 1 GPU(s) were checked, no nvlink issue found"
+    nv2 = g.capi.Component(ctx, "accelerator-nvidia-nvlink", nvlink_at_least=2)       # a threshold one GPU cannot meet
+    health, reason = nv2.check()
+    assert health == 2 and "nvlink" in reason.lower()
+    assert nv2.last_health_states()[0]["health"] == "Unhealthy"
+    nv.close(); nv2.close()

@@ -726,3 +726,50 @@ def test_nvml_bus_id_like_go_nvlib():
     assert g.capi.nvml_bus_id("00000001:0F:00.0") == "0001:0f:00.0"
     assert g.capi.nvml_bus_id("0000:9b:00.0") == ":9b:00.0"          # what TrimPrefix does to an already short id
     assert g.capi.nvml_bus_id("0000") == "0000"
+
+
+def test_watcher_dedup_in_front_of_the_stateful_matchers():
+    """pkg/kmsg/watcher.go:281-286: a message is handed to the matchers only the first time its (minute, message) key shows up, so a
+    repeated line neither matches nor counts towards the panic matcher's ten lines (os/kmsg_matcher.go:60-125).  Model: the oracle's
+    matchers run over the stream with the duplicates removed by the reference's deduper restatement (O.Deduper)."""
+    import synth
+    base = [l for l in synth.stateful_stream(1500, seed=11)]
+    # repeat lines inside and outside the panic windows: every third line once more, right away and again five lines later
+    lines = []
+    for i, l in enumerate(base):
+        lines.append(l)
+        if i % 3 == 0:
+            lines.append(l)
+        if i % 5 == 0 and i >= 5:
+            lines.append(base[i - 5])
+    enc = [l.encode() for l in lines]
+    buf = b"\n".join(enc)
+    now = 1_700_000_000
+    # the reference model: drop duplicates with the oracle's deduper, run the closures over what is left, report original line numbers
+    seen = set()                                       # deduper.addCache (deduper.go:95-109): the first add of a key returns 1, later ones > 1
+    kept = []
+    for i, l in enumerate(lines):
+        k = O.dedup_key(now, l)
+        if k not in seen:
+            seen.add(k)
+            kept.append(i)
+    want = [(kept[u], c, e, m) for u, c, e, m in O.stateful_events([enc[i] for i in kept])]
+    assert len(kept) < len(lines) * 0.8 and sum(1 for w in want if w[1] == "os") >= 5
+    dd = g.capi.KmsgDeduper()
+    dropped = dd.units(buf, len(enc), mode=g.SCAN_LINES, lines_unix=now, now_unix=now)
+    assert [i for i in range(len(enc)) if not dropped[i]] == kept
+    hits, hbuf = _oracle_prim_hits(enc)
+    assert hbuf == buf
+    st = g.KmsgStateful()
+    got = st.feed_units(hits, buf, len(enc), dropped)
+    assert got == want
+    # without the dedup the repeated lines shift the ten-line window: the results differ (what the gap used to be)
+    st2 = g.KmsgStateful()
+    assert st2.feed(hits, buf, len(enc)) != want
+    st.close(); st2.close(); dd.close()
+    # RAW_KMSG: the key's minute comes from the record's own timestamp - the same message a minute later is not a duplicate
+    recs = [b"6,1,1000000,-;hello", b"6,2,2000000,-;hello", b"6,3,62000000,-;hello", b"bad record", b"6,4,63000000,-;hello\n SUBSYSTEM=x", b"6,5,64000000,-;hello\n SUBSYSTEM=x"]
+    dd = g.capi.KmsgDeduper()
+    dr = dd.units(b"\n".join(recs), len(recs), mode=g.SCAN_RAW_KMSG, boot_unix=now - now % 60, now_unix=now)
+    assert list(dr) == [0, 1, 0, 0, 0, 1]
+    dd.close()
