@@ -6,7 +6,7 @@ SRC := gpud_b200/csrc
 OBJS := $(SRC)/api.o $(SRC)/ring.o $(SRC)/select.o $(SRC)/kmsg_scan.o $(SRC)/ib_scan.o $(SRC)/fabric.o $(SRC)/catalog.o $(SRC)/host_component.o $(SRC)/component_abi.o $(SRC)/kmsg_stateful.o $(SRC)/poller.o $(SRC)/store_sqlite.o
 LIB := gpud_b200/libgpud_b200.so
 
-all: $(LIB) oracle
+all: $(LIB) gpud_b200/gpud-scan oracle
 
 $(SRC)/%.o: $(SRC)/%.cu $(SRC)/internal.h $(SRC)/catalog.h include/gpud_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
@@ -29,6 +29,10 @@ $(SRC)/store_sqlite.o: $(SRC)/store_sqlite.cpp $(SRC)/json_min.h include/gpud_b2
 $(SRC)/kmsg_stateful.o: $(SRC)/kmsg_stateful.cpp include/gpud_b200.h
 	g++ -O2 -std=c++17 -fPIC -Wall -c $< -o $@
 
+# BASELINE configs[0]: the `gpud scan`-shaped one-shot for a CPU-only host; no CUDA, no library
+gpud_b200/gpud-scan: $(SRC)/scan_main.cpp
+	g++ -O2 -std=c++17 -Wall -o $@ $<
+
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl
 
@@ -36,7 +40,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(SRC)/*.o $(SRC)/*.ptxas.log $(LIB)
+	rm -f $(SRC)/*.o $(SRC)/*.ptxas.log $(LIB) gpud_b200/gpud-scan
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

@@ -116,3 +116,20 @@ def test_product_never_touches_the_oracle():
     assert "liboracle" not in out
     blob = open(capi.LIB_PATH, "rb").read()
     assert b"liboracle" not in blob and b"orc_scan_lines" not in blob
+
+
+def test_scan_one_shot_on_a_cpu_only_host():
+    """BASELINE configs[0] (plumbing): the `gpud scan`-shaped driver runs without CUDA and prints one CheckResult per component in the
+    api/v1 HealthState shape (pkg/scan/scan.go:20-28,74-102)."""
+    import json
+    import subprocess
+    exe = os.path.join(ROOT, "gpud_b200", "gpud-scan")
+    if not os.path.exists(exe):
+        pytest.skip("gpud-scan not built")
+    assert "cuda" not in subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout
+    states = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    assert [s["component"] for s in states] == ["cpu", "memory", "os"]
+    for s in states:
+        assert s["name"] == s["component"] and s["health"] in ("Healthy", "Degraded", "Unhealthy") and s["reason"] and s["time"].endswith("Z")
+    assert "scanning the host" in out and "scan complete" in out
