@@ -71,6 +71,7 @@ __host__ __device__ __forceinline__ unsigned long long gpud_key_f64bits(unsigned
 // view of a ring range around the per-window pass (ring.cu <-> select.cu)
 #define GPUD_RANGE_SAMPLED_MIN 65536   /* ranges at least this long take the sampled-pivot single pass */
 #define GPUD_RANGE_LIST_CAP 65536      /* keys between the pivots kept per field */
+#define GPUD_RANGE_SAMPLE_MAX 8192     /* keys per field in the sample the pivots come from */
 struct gpud_range_view {
   const double* ring; int F; int64_t cap, start, n; int Wp, nw;
   const double *w_min, *w_max, *w_mean, *w_ema; const uint32_t* w_nover;
@@ -81,6 +82,8 @@ struct gpud_range_view {
   unsigned* fill;                      // [F]
   uint4* w_cls;                        // [F][nw] {above hi, == hi, == lo, strictly inside}
   unsigned long long* lists;           // [F][list_cap]
+  const double* sample;                // the ring's own sample ring [F][smp_slots] (ring.cu k_ring_append)
+  int smp_shift; int64_t smp_slots;
   cudaEvent_t ev[3];
 };
 int32_t gpud_ring_range_prepare(gpud_ring* r, int64_t n, gpud_range_view* v);

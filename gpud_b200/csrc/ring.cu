@@ -66,9 +66,12 @@ struct WinParams {
 // ---------------------------------------------------------------------------------------------
 // T = the caller's sample type: double, or a raw NVML / DCGM counter type widened here exactly like Go's float64(v)
 // (round-to-nearest-even for 64-bit integers above 2^53).
+// The same kernel keeps the SAMPLE RING: every column whose index is smp_half modulo 2^smp_shift is also stored at
+// sample[f][col >> smp_shift] - a systematic sample of at most 8192 keys per field that is always current, so the whole-range order
+// statistic (select.cu) gets its pivots from 64 KB of contiguous memory per field instead of 8192 scattered 32-byte sectors.
 template <typename T>
 __global__ void __launch_bounds__(256) k_ring_append(const T* __restrict__ src, double* __restrict__ ring, int64_t n, int F,
-                                                      int64_t cap, int64_t head) {
+                                                      int64_t cap, int64_t head, double* __restrict__ sample, int smp_shift, int64_t smp_half, int64_t smp_slots) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const int64_t tiles_f = (F + 31) / 32;
@@ -88,7 +91,9 @@ __global__ void __launch_bounds__(256) k_ring_append(const T* __restrict__ src, 
       if (r < n && f < F) {
         int64_t col = head + r;
         col = col >= cap ? col % cap : col;
-        ring[f * cap + col] = tile[tx][ty + 8 * k];
+        const double val = tile[tx][ty + 8 * k];
+        ring[f * cap + col] = val;
+        if ((col & ((1ll << smp_shift) - 1)) == smp_half) sample[f * smp_slots + (col >> smp_shift)] = val;
       }
     }
     __syncthreads();
@@ -716,6 +721,9 @@ struct gpud_ring {
   cudaEvent_t ev_copied[2] = {nullptr, nullptr};   // the H2D into d_stage[i] has landed
   cudaStream_t copy_stream = nullptr;
   int64_t stage_rows = 0;
+  double* d_sample = nullptr;      // [F][smp_slots]: column c with c % 2^smp_shift == 2^smp_shift / 2 lives at slot c >> smp_shift (kept by the append kernel)
+  int smp_shift = 0;
+  int64_t smp_slots = 0;
   int sm_count = 148;
   int cta_reserve = 0;           // CTA slots the persistent window grid leaves free for kernels of other streams (gpud_ring_set_cta_reserve)
   double* d_rng[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // range-reduce scratch: per-window min,max,mean,ema,partials
@@ -756,8 +764,12 @@ extern "C" int32_t gpud_ring_create(gpud_ctx* ctx, int32_t dev, const gpud_ring_
   r->nw_max = (r->cap + r->W - 1) / r->W;
   const size_t ring_bytes = (size_t)r->F * r->cap * sizeof(double) + 64;   // slack: the 16-byte load of a window's last odd element
   const size_t res_bytes = (size_t)r->F * r->nw_max * sizeof(double);
+  while (((r->cap + (1ll << r->smp_shift) - 1) >> r->smp_shift) > GPUD_RANGE_SAMPLE_MAX) ++r->smp_shift;
+  r->smp_slots = (r->cap + (1ll << r->smp_shift) - 1) >> r->smp_shift;
   cudaError_t e = cudaMalloc(&r->d_ring, ring_bytes);
   if (e == cudaSuccess) e = cudaMemsetAsync(r->d_ring, 0, ring_bytes, 0);
+  if (e == cudaSuccess) e = cudaMalloc(&r->d_sample, (size_t)r->F * r->smp_slots * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemsetAsync(r->d_sample, 0, (size_t)r->F * r->smp_slots * sizeof(double), 0);
   if (e == cudaSuccess) e = cudaMalloc(&r->d_thr, r->F * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&r->d_pw, 127 * sizeof(double));
   for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaMalloc(&r->d_res[i], res_bytes);
@@ -793,7 +805,7 @@ extern "C" int32_t gpud_ring_destroy(gpud_ring* r) {
   if (!r) return GPUD_E_INVALID;
   cudaSetDevice(r->dev);
   if (r->own_stream) cudaStreamSynchronize(r->own_stream);
-  cudaFree(r->d_ring); cudaFree(r->d_thr); cudaFree(r->d_pw); cudaFree(r->d_nover); cudaFree(r->d_part);
+  cudaFree(r->d_ring); cudaFree(r->d_sample); cudaFree(r->d_thr); cudaFree(r->d_pw); cudaFree(r->d_nover); cudaFree(r->d_part);
   for (auto& p : r->d_res) cudaFree(p);
   for (auto& p : r->d_rng) cudaFree(p);
   cudaFree(r->d_rng_nover);
@@ -845,15 +857,15 @@ static int32_t launch_append(gpud_ring* r, const void* d_rows, int64_t n, int32_
   const int64_t tiles = ((r->F + 31) / 32) * ((n + 31) / 32);
   const int grid = (int)std::min<int64_t>(tiles, (int64_t)r->sm_count * 16);
   switch (dt) {
-    case GPUD_DT_F64: k_ring_append<double><<<grid, 256, 0, r->stream>>>((const double*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_U32: k_ring_append<uint32_t><<<grid, 256, 0, r->stream>>>((const uint32_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_I32: k_ring_append<int32_t><<<grid, 256, 0, r->stream>>>((const int32_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_F32: k_ring_append<float><<<grid, 256, 0, r->stream>>>((const float*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_I64: k_ring_append<long long><<<grid, 256, 0, r->stream>>>((const long long*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_U64: k_ring_append<unsigned long long><<<grid, 256, 0, r->stream>>>((const unsigned long long*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_U16: k_ring_append<uint16_t><<<grid, 256, 0, r->stream>>>((const uint16_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_I16: k_ring_append<int16_t><<<grid, 256, 0, r->stream>>>((const int16_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
-    case GPUD_DT_U8: k_ring_append<uint8_t><<<grid, 256, 0, r->stream>>>((const uint8_t*)d_rows, r->d_ring, n, r->F, r->cap, head); break;
+    case GPUD_DT_F64: k_ring_append<double><<<grid, 256, 0, r->stream>>>((const double*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_U32: k_ring_append<uint32_t><<<grid, 256, 0, r->stream>>>((const uint32_t*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_I32: k_ring_append<int32_t><<<grid, 256, 0, r->stream>>>((const int32_t*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_F32: k_ring_append<float><<<grid, 256, 0, r->stream>>>((const float*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_I64: k_ring_append<long long><<<grid, 256, 0, r->stream>>>((const long long*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_U64: k_ring_append<unsigned long long><<<grid, 256, 0, r->stream>>>((const unsigned long long*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_U16: k_ring_append<uint16_t><<<grid, 256, 0, r->stream>>>((const uint16_t*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_I16: k_ring_append<int16_t><<<grid, 256, 0, r->stream>>>((const int16_t*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
+    case GPUD_DT_U8: k_ring_append<uint8_t><<<grid, 256, 0, r->stream>>>((const uint8_t*)d_rows, r->d_ring, n, r->F, r->cap, head, r->d_sample, r->smp_shift, (1ll << r->smp_shift) >> 1, r->smp_slots); break;
     default: return gpud_fail(r->ctx, GPUD_E_INVALID, "unknown sample dtype %d", dt);
   }
   GPUD_CUDA(r->ctx, cudaGetLastError());
@@ -1076,6 +1088,7 @@ int32_t gpud_ring_range_prepare(gpud_ring* r, int64_t n, gpud_range_view* v) {
   v->w_min = r->d_rng[0]; v->w_max = r->d_rng[1]; v->w_mean = r->d_rng[2]; v->w_ema = r->d_rng[3]; v->w_nover = r->d_rng_nover;
   v->q_num = r->q_num; v->q_den = r->q_den; v->stream = r->stream; v->ctx = r->ctx; v->dev = r->dev; v->sm_count = r->sm_count;
   v->sampled = sampled ? 1 : 0;
+  v->sample = r->d_sample; v->smp_shift = r->smp_shift; v->smp_slots = r->smp_slots;
   v->list_cap = list_cap;
   v->piv = sampled ? r->d_rng_piv : nullptr;
   v->fill = sampled ? reinterpret_cast<unsigned*>(r->d_rng_piv + 2 * (size_t)r->F) : nullptr;

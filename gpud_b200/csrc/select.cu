@@ -161,18 +161,46 @@ __device__ void block_select2_smem(const unsigned long long* keys, int cnt, int 
   *outB = z->ans[1];
 }
 
+// The sample comes from the ring's own sample ring when the range covers enough of its slots (the whole-ring case: 64 KB of contiguous
+// memory per field, kept current by the append kernel), else from S strided reads of the ring itself (one 32-byte sector each).
 __global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, int S, int64_t stride,
-                                                       int64_t k_from_top, double* __restrict__ piv, unsigned* __restrict__ fill) {
+                                                       int64_t k_from_top, double* __restrict__ piv, unsigned* __restrict__ fill,
+                                                       const double* __restrict__ sample, int smp_shift, int64_t smp_slots) {
   extern __shared__ __align__(16) unsigned long long s_keys[];
   __shared__ unsigned s_hist[512];
   __shared__ unsigned long long s_red[16];
   __shared__ Sel2 s_z;
+  __shared__ int s_cnt;
   const int f = blockIdx.x, t = threadIdx.x;
-  const double* __restrict__ base = ring + (int64_t)f * cap;
-  for (int j = t; j < S; j += 256) {
-    int64_t a = start + (int64_t)j * stride + (stride >> 1);
-    if (a >= cap) a -= cap;
-    s_keys[j] = gpud_f64_key((unsigned long long)__double_as_longlong(__ldg(base + a)));
+  if (sample) {
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    const double* __restrict__ sb = sample + (int64_t)f * smp_slots;
+    const int64_t half = (1ll << smp_shift) >> 1;
+    for (int64_t s0 = 0; s0 < smp_slots; s0 += 256) {             // slots compacted with one ballot + one counter bump per warp
+      const int64_t sl = s0 + t;
+      bool ok = false;
+      if (sl < smp_slots) {
+        const int64_t col = (sl << smp_shift) + half;            // the column this slot mirrors
+        int64_t c = col - start;                                 // chronological index inside the range?
+        if (c < 0) c += cap;
+        ok = col < cap && c < n;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      int base = 0;
+      if ((t & 31) == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (ok) s_keys[base + __popc(m & ((1u << (t & 31)) - 1u))] = gpud_f64_key((unsigned long long)__double_as_longlong(__ldg(sb + sl)));
+    }
+    __syncthreads();
+    S = s_cnt;
+  } else {
+    const double* __restrict__ base = ring + (int64_t)f * cap;
+    for (int j = t; j < S; j += 256) {
+      int64_t a = start + (int64_t)j * stride + (stride >> 1);
+      if (a >= cap) a -= cap;
+      s_keys[j] = gpud_f64_key((unsigned long long)__double_as_longlong(__ldg(base + a)));
+    }
   }
   __syncthreads();
   const double pr = (double)k_from_top / (double)n;
@@ -473,8 +501,10 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
     r = r < 1 ? 1 : (r > v.n ? v.n : r);
     const int S = (int)std::min<int64_t>(kSampleMax, v.n / 8);
     const int64_t stride = v.n / S;
+    const bool use_ring_sample = (v.n >> v.smp_shift) >= 2048 && v.smp_slots <= kSampleMax;   // else too few of the ring's sample slots fall into the range
     e = cudaFuncSetAttribute(k_range_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleMax * (int)sizeof(unsigned long long));
-    if (e == cudaSuccess) k_range_pivots<<<v.F, 256, (size_t)S * sizeof(unsigned long long), v.stream>>>(v.ring, v.cap, v.start, v.n, S, stride, v.n - r + 1, v.piv, v.fill);
+    if (e == cudaSuccess) k_range_pivots<<<v.F, 256, (size_t)kSampleMax * sizeof(unsigned long long), v.stream>>>(v.ring, v.cap, v.start, v.n, S, stride, v.n - r + 1, v.piv, v.fill,
+                                                                                                          use_ring_sample ? v.sample : nullptr, v.smp_shift, v.smp_slots);
     if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (e == cudaSuccess) {
