@@ -800,6 +800,12 @@ class Context:
         self._check(self._L.gpud_kmsg_scan_sharded(self._h, C.cast(C.c_char_p(buf), C.c_void_p), len(buf), mode, hits, cap, C.byref(nh), C.byref(nu)))
         return [hits[i] for i in range(min(nh.value, cap))], nu.value
 
+    def kmsg_scan_sharded_c(self, buf: bytes, hits, cap: int, mode: int = SCAN_LINES):
+        """the bare C call with a preallocated XidHit array.  Returns (n_hits, n_units)."""
+        nh, nu = C.c_int64(), C.c_int64()
+        self._check(self._L.gpud_kmsg_scan_sharded(self._h, C.cast(C.c_char_p(buf), C.c_void_p), len(buf), mode, hits, cap, C.byref(nh), C.byref(nu)))
+        return nh.value, nu.value
+
     def kmsg_scan_device(self, dev_ptr: int, length: int, mode: int = SCAN_LINES, dev: Optional[int] = None, cap: int = 1 << 16,
                          stream: int = 0):
         dev = self.devices[0] if dev is None else dev

@@ -1595,7 +1595,7 @@ extern "C" int32_t gpud_kmsg_scan_sharded(gpud_ctx* ctx, const uint8_t* buf, int
   std::vector<std::thread> th;
   for (Piece& p : pieces)
     th.emplace_back([&, pp = &p] {
-      int64_t local_cap = std::max<int64_t>(4096, std::min<int64_t>(cap, (pp->e - pp->b) / 32 + 4096));
+      int64_t local_cap = std::max<int64_t>(4096, std::min<int64_t>(cap, (pp->e - pp->b) / 2048 + 4096));   // ~2 hits per 4 KiB to start with; grown on demand
       for (;;) {                                                // a piece denser in hits than expected: once more with room for all
         pp->hits.resize((size_t)local_cap);
         pp->rc = gpud_kmsg_scan(ctx, pp->dev, buf + pp->b, pp->e - pp->b, mode, pp->hits.data(), local_cap, &pp->found, &pp->units);

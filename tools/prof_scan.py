@@ -44,3 +44,20 @@ if cpu:
     assert [(h.line, h.kind, h.code) for h in ch] == [(h.unit_index, h.kind, h.code) for h in hits]
     out.update(cpu_threads=coracle.max_threads(), cpu_ms=dt * 1e3, cpu_GBps=len(buf) / dt / 1e9, cpu_hits_equal=True)
 print(json.dumps(out))
+if len(sys.argv) > 2 and sys.argv[2] == "sharded":
+    # the same 100 MiB buffer over every GPU of the box through gpud_kmsg_scan_sharded (host bytes in, merged hits out)
+    n_gpu = torch.cuda.device_count()
+    res = {}
+    for n in sorted({1, 2, 4, n_gpu} & set(range(1, n_gpu + 1))):
+        c = g.Context(list(range(n)))
+        harr2 = (g.XidHit * (1 << 17))()
+        c.kmsg_scan_sharded_c(buf, harr2, 1 << 17)             # warm-up (allocations, pinned staging)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            nh, nu = c.kmsg_scan_sharded_c(buf, harr2, 1 << 17)
+            ts.append(time.perf_counter() - t0)
+        assert nh == len(hits) and nu == n_units
+        res[n] = {"host_ms": min(ts) * 1e3, "GBps": len(buf) / min(ts) / 1e9}
+        c.close()
+    print(json.dumps({"sharded_scan_100MiB_host_bytes": res}))
