@@ -1413,8 +1413,9 @@ struct CopyPool {
   }
 };
 }  // namespace
+static thread_local bool t_plain_copy = false;   // set by the sharded scan's device threads when there are enough of them to out-copy the pool
 void gpud_parallel_memcpy(void* dst, const void* src, size_t n) {
-  if (n < (1u << 20)) { memcpy(dst, src, n); return; }
+  if (n < (1u << 20) || t_plain_copy) { memcpy(dst, src, n); return; }
   static CopyPool* pool = new CopyPool();     // lives for the process
   static std::mutex one;                      // one staged copy at a time
   std::lock_guard<std::mutex> g(one);
@@ -1594,7 +1595,8 @@ extern "C" int32_t gpud_kmsg_scan_sharded(gpud_ctx* ctx, const uint8_t* buf, int
   if (pieces.size() <= 1) return gpud_kmsg_scan(ctx, ctx->devs[0], buf, len, mode, hits, cap, n_hits, n_units);
   std::vector<std::thread> th;
   for (Piece& p : pieces)
-    th.emplace_back([&, pp = &p] {
+    th.emplace_back([&, pp = &p, many = pieces.size() >= 4] {
+      t_plain_copy = many;                                      // >= 4 device threads copy their own pieces: more streams than the shared pool has workers
       int64_t local_cap = std::max<int64_t>(4096, std::min<int64_t>(cap, (pp->e - pp->b) / 2048 + 4096));   // ~2 hits per 4 KiB to start with; grown on demand
       for (;;) {                                                // a piece denser in hits than expected: once more with room for all
         pp->hits.resize((size_t)local_cap);

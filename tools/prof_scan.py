@@ -59,5 +59,21 @@ if len(sys.argv) > 2 and sys.argv[2] == "sharded":
             ts.append(time.perf_counter() - t0)
         assert nh == len(hits) and nu == n_units
         res[n] = {"host_ms": min(ts) * 1e3, "GBps": len(buf) / min(ts) / 1e9}
+        # the same from pinned caller memory (gpud_host_alloc): no staging copy, every GPU pulls its piece over its own PCIe link
+        import ctypes as C
+        hp = C.c_void_p()
+        assert g.lib().gpud_host_alloc(C.c_int64(len(buf)), C.byref(hp)) == 0
+        C.memmove(hp, buf, len(buf))
+        L = g.lib()
+        nh, nu = C.c_int64(), C.c_int64()
+        tp = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            rc = L.gpud_kmsg_scan_sharded(c._h, hp, C.c_int64(len(buf)), 0, harr2, C.c_int64(1 << 17), C.byref(nh), C.byref(nu))
+            tp.append(time.perf_counter() - t0)
+        assert rc == 0 and nh.value == len(hits)
+        res[n]["pinned_host_ms"] = min(tp[1:]) * 1e3
+        res[n]["pinned_GBps"] = len(buf) / min(tp[1:]) / 1e9
+        L.gpud_host_free(hp)
         c.close()
     print(json.dumps({"sharded_scan_100MiB_host_bytes": res}))
