@@ -78,8 +78,9 @@ __device__ __forceinline__ void for_each_key(const double* __restrict__ base, in
 // from the list.  Any field for which that fails (rank outside the pivots, list overflow, +NaN in the data, NaN pivots) is
 // answered by the histogram path below - results never depend on the sample.
 constexpr int kSampleMax = 8192;
+constexpr int kSelThreads = 512;       // block size of k_range_pivots / k_range_finish: latency-bound, one block per field
 
-// The kkA-th and kkB-th largest (1-based) of keys[0..cnt) in shared memory, both at once; 256 threads.  MSB-first 8-bit digits
+// The kkA-th and kkB-th largest (1-based) of keys[0..cnt) in shared memory, both at once; kSelThreads threads.  MSB-first 8-bit digits
 // starting below the bits all keys share; a target whose chosen bin holds a single key is finished by one more sweep that
 // finds that key (after two digits of an 8 Ki sample almost every bin does).  Warp 0 walks target A's histogram, warp 1 B's.
 struct Sel2 { unsigned long long prefix[2]; unsigned kk[2]; int single[2]; unsigned long long ans[2]; int done[2]; };
@@ -87,15 +88,15 @@ __device__ void block_select2_smem(const unsigned long long* keys, int cnt, int 
                                    unsigned long long* red /*[16]*/, unsigned long long* outA, unsigned long long* outB) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   unsigned long long kmin = ~0ull, kmax = 0ull;
-  for (int i = t; i < cnt; i += 256) { const unsigned long long k = keys[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
+  for (int i = t; i < cnt; i += kSelThreads) { const unsigned long long k = keys[i]; kmin = min(kmin, k); kmax = max(kmax, k); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
     kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
   }
-  if (lane == 0) { red[wid] = kmin; red[8 + wid] = kmax; }
+  if (lane == 0) { red[wid] = kmin; red[kSelThreads / 32 + wid] = kmax; }
   __syncthreads();
-  for (int w = 0; w < 8; ++w) { kmin = min(kmin, red[w]); kmax = max(kmax, red[8 + w]); }
+  for (int w = 0; w < kSelThreads / 32; ++w) { kmin = min(kmin, red[w]); kmax = max(kmax, red[kSelThreads / 32 + w]); }
   if (kmin == kmax) { *outA = *outB = kmax; return; }
   int nfix = __clzll((long long)(kmin ^ kmax));
   if (t == 0) {
@@ -109,9 +110,9 @@ __device__ void block_select2_smem(const unsigned long long* keys, int cnt, int 
     const unsigned long long pA = z->prefix[0], pB = z->prefix[1];
     const bool liveA = !z->done[0], liveB = !z->done[1];
     if (!liveA && !liveB) break;
-    hist[t] = 0; hist[256 + t] = 0;
+    if (t < 512) hist[t] = 0;
     __syncthreads();
-    for (int i = t; i < cnt; i += 256) {
+    for (int i = t; i < cnt; i += kSelThreads) {
       const unsigned long long key = keys[i];
       const unsigned long long top = nfix ? (key >> (64 - nfix)) : 0ull;
       const unsigned bin = (unsigned)(key >> shift) & mask;
@@ -132,11 +133,13 @@ __device__ void block_select2_smem(const unsigned long long* keys, int cnt, int 
         if (lane >= o) incl += u;
       }
       const unsigned before = incl - loc;            // keys in the bins above this lane's
+      const unsigned long long pfx = z->prefix[wid];
+      __syncwarp();                                  // every lane has read kk / prefix before the owner rewrites them
       if (before < kk && kk <= incl) {
         unsigned acc = before;
         int bin = 255 - 8 * lane;
         while (acc + h[bin] < kk) { acc += h[bin]; --bin; }
-        z->prefix[wid] = (z->prefix[wid] << d) | (unsigned long long)bin;
+        z->prefix[wid] = (pfx << d) | (unsigned long long)bin;
         z->kk[wid] = kk - acc;
         z->single[wid] = h[bin] == 1u;
       }
@@ -149,7 +152,7 @@ __device__ void block_select2_smem(const unsigned long long* keys, int cnt, int 
       const bool sA = z->single[0] && !z->done[0], sB = z->single[1] && !z->done[1];
       const unsigned long long qA = z->prefix[0], qB = z->prefix[1];
       __syncthreads();
-      for (int i = t; i < cnt; i += 256) {
+      for (int i = t; i < cnt; i += kSelThreads) {
         const unsigned long long key = keys[i], top = key >> (64 - nfix);
         if (sA && top == qA) { z->ans[0] = key; z->done[0] = 1; }
         if (sB && top == qB) { z->ans[1] = key; z->done[1] = 1; }
@@ -163,12 +166,12 @@ __device__ void block_select2_smem(const unsigned long long* keys, int cnt, int 
 
 // The sample comes from the ring's own sample ring when the range covers enough of its slots (the whole-ring case: 64 KB of contiguous
 // memory per field, kept current by the append kernel), else from S strided reads of the ring itself (one 32-byte sector each).
-__global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, int S, int64_t stride,
+__global__ void __launch_bounds__(kSelThreads) k_range_pivots(const double* __restrict__ ring, int64_t cap, int64_t start, int64_t n, int S, int64_t stride,
                                                        int64_t k_from_top, double* __restrict__ piv, unsigned* __restrict__ fill,
                                                        const double* __restrict__ sample, int smp_shift, int64_t smp_slots) {
   extern __shared__ __align__(16) unsigned long long s_keys[];
   __shared__ unsigned s_hist[512];
-  __shared__ unsigned long long s_red[16];
+  __shared__ unsigned long long s_red[2 * kSelThreads / 32];
   __shared__ Sel2 s_z;
   __shared__ int s_cnt;
   const int f = blockIdx.x, t = threadIdx.x;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__
     __syncthreads();
     const double* __restrict__ sb = sample + (int64_t)f * smp_slots;
     const int64_t half = (1ll << smp_shift) >> 1;
-    for (int64_t s0 = 0; s0 < smp_slots; s0 += 256) {             // slots compacted with one ballot + one counter bump per warp
+    for (int64_t s0 = 0; s0 < smp_slots; s0 += kSelThreads) {             // slots compacted with one ballot + one counter bump per warp
       const int64_t sl = s0 + t;
       bool ok = false;
       if (sl < smp_slots) {
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__
     S = s_cnt;
   } else {
     const double* __restrict__ base = ring + (int64_t)f * cap;
-    for (int j = t; j < S; j += 256) {
+    for (int j = t; j < S; j += kSelThreads) {
       int64_t a = start + (int64_t)j * stride + (stride >> 1);
       if (a >= cap) a -= cap;
       s_keys[j] = gpud_f64_key((unsigned long long)__double_as_longlong(__ldg(base + a)));
@@ -220,22 +223,22 @@ __global__ void __launch_bounds__(256) k_range_pivots(const double* __restrict__
 // One block per field after the window pass: fold the per-window partials into the field's min / max / mean / EMA / n_over,
 // initialise the histogram path's state, and - sampled mode - settle the order statistic from the class counts and the list.
 // Fields left open (done == 0) are counted in *n_open.
-__global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int64_t n, const double* __restrict__ w_min, const double* __restrict__ w_max,
+__global__ void __launch_bounds__(kSelThreads) k_range_finish(int F, int nw, int Wp, int64_t n, const double* __restrict__ w_min, const double* __restrict__ w_max,
                                                        const double* __restrict__ w_mean, const double* __restrict__ w_ema, const uint32_t* __restrict__ w_nover,
                                                        int q_num, int q_den, int sampled, const double* __restrict__ piv, const unsigned* __restrict__ fill,
                                                        const uint4* __restrict__ w_cls, const unsigned long long* __restrict__ lists, unsigned list_cap,
                                                        double* __restrict__ out /*[5][F]*/, uint32_t* __restrict__ out_nover, SelState* __restrict__ st,
                                                        unsigned* __restrict__ n_open, int* __restrict__ open_ids) {
-  __shared__ unsigned long long s_red[8][6];
-  __shared__ double s_sum[8];
+  __shared__ unsigned long long s_red[kSelThreads / 32][6];
+  __shared__ double s_sum[kSelThreads / 32];
   __shared__ unsigned s_hist[kBins];
   __shared__ unsigned long long s_prefix, s_kk;
   __shared__ int s_nbits, s_mode;
-  __shared__ unsigned s_part[256];
+  __shared__ unsigned s_part[kSelThreads / 32];
   const int f = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
   unsigned long long kmin = ~0ull, kmax = 0ull, c_abv = 0, c_eh = 0, c_el = 0, nov = 0;
   double sum = 0.0;
-  for (int w = t; w < nw; w += 256) {
+  for (int w = t; w < nw; w += kSelThreads) {
     const int64_t o = (int64_t)f * nw + w;
     const int m = (int)min((int64_t)Wp, n - (int64_t)w * Wp);
     kmin = min(kmin, gpud_f64_key((unsigned long long)__double_as_longlong(w_min[o])));
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
   if (lane == 0) { s_red[wid][0] = kmin; s_red[wid][1] = kmax; s_red[wid][2] = c_abv; s_red[wid][3] = c_eh; s_red[wid][4] = c_el; s_red[wid][5] = nov; s_sum[wid] = sum; }
   __syncthreads();
   if (t == 0) {
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < kSelThreads / 32; ++w) {
       kmin = min(kmin, s_red[w][0]); kmax = max(kmax, s_red[w][1]);
       c_abv += s_red[w][2]; c_eh += s_red[w][3]; c_el += s_red[w][4]; nov += s_red[w][5];
       sum += s_sum[w];
@@ -324,17 +327,18 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
     const int nbits = s_nbits;
     const unsigned long long prefix = s_prefix;
     const int d = min(kDigit, 64 - nbits), shift = 64 - nbits - d, nb = 1 << d;
-    for (int i = t; i < kBins; i += 256) s_hist[i] = 0;
+    for (int i = t; i < kBins; i += kSelThreads) s_hist[i] = 0;
     __syncthreads();
-    for (unsigned i = t; i < cnt; i += 256) {
+    for (unsigned i = t; i < cnt; i += kSelThreads) {
       const unsigned long long key = list[i];
       if (nbits == 0 || (key >> (64 - nbits)) == prefix) atomicAdd(&s_hist[(unsigned)(key >> shift) & (unsigned)(nb - 1)], 1u);
     }
     __syncthreads();
-    // thread t owns bins nb-1-8t .. nb-8-8t (from the top); block-wide exclusive scan of the per-thread sums finds the owner
+    // thread t owns kBpt bins from the top (nb-1-kBpt t downwards); block-wide exclusive scan of the per-thread sums finds the owner
+    constexpr int kBpt = kBins / kSelThreads;
     unsigned loc = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const int b = nb - 1 - 8 * t - j; if (b >= 0) loc += s_hist[b]; }
+    for (int j = 0; j < kBpt; ++j) { const int b = nb - 1 - kBpt * t - j; if (b >= 0) loc += s_hist[b]; }
     unsigned incl = loc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(256) k_range_finish(int F, int nw, int Wp, int
     __syncthreads();                                   // everyone has read s_kk / s_part before the owner rewrites them
     if ((unsigned long long)before < kk && kk <= (unsigned long long)before + loc) {
       unsigned acc = before;
-      int b = nb - 1 - 8 * t;
+      int b = nb - 1 - kBpt * t;
       while ((unsigned long long)acc + s_hist[b] < kk) { acc += s_hist[b]; --b; }
       s_prefix = (nbits ? (prefix << d) : 0ull) | (unsigned long long)b;
       s_nbits = nbits + d;
@@ -503,7 +507,7 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
     const int64_t stride = v.n / S;
     const bool use_ring_sample = (v.n >> v.smp_shift) >= 2048 && v.smp_slots <= kSampleMax;   // else too few of the ring's sample slots fall into the range
     e = cudaFuncSetAttribute(k_range_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleMax * (int)sizeof(unsigned long long));
-    if (e == cudaSuccess) k_range_pivots<<<v.F, 256, (size_t)kSampleMax * sizeof(unsigned long long), v.stream>>>(v.ring, v.cap, v.start, v.n, S, stride, v.n - r + 1, v.piv, v.fill,
+    if (e == cudaSuccess) k_range_pivots<<<v.F, kSelThreads, (size_t)kSampleMax * sizeof(unsigned long long), v.stream>>>(v.ring, v.cap, v.start, v.n, S, stride, v.n - r + 1, v.piv, v.fill,
                                                                                                           use_ring_sample ? v.sample : nullptr, v.smp_shift, v.smp_slots);
     if (e == cudaSuccess) e = cudaGetLastError();
   }
@@ -513,7 +517,7 @@ extern "C" int32_t gpud_ring_reduce_range(gpud_ring* ring, int64_t last_n, doubl
     e = cudaEventRecord(v.ev[1], v.stream);
   }
   if (e == cudaSuccess) {
-    k_range_finish<<<v.F, 256, 0, v.stream>>>(v.F, v.nw, v.Wp, v.n, v.w_min, v.w_max, v.w_mean, v.w_ema, v.w_nover, v.q_num, v.q_den, v.sampled, v.piv, v.fill,
+    k_range_finish<<<v.F, kSelThreads, 0, v.stream>>>(v.F, v.nw, v.Wp, v.n, v.w_min, v.w_max, v.w_mean, v.w_ema, v.w_nover, v.q_num, v.q_den, v.sampled, v.piv, v.fill,
                                               v.w_cls, v.lists, v.list_cap, d_out, d_nover, d_st, d_open, reinterpret_cast<int*>(d_open + 1));
     e = cudaGetLastError();
   }
