@@ -151,8 +151,7 @@ void orc_windows_fields(const double* ring, int32_t F, int64_t n, int32_t W, con
 
 #include <stdio.h>
 
-#include "../gpud_b200/csrc/catalog.h"
-#include "../gpud_b200/csrc/catalog_data.inc"   /* DATA ONLY: generated tables (tools/gen_catalog.py) */
+#include "oracle_catalog_data.inc"   /* the oracle's own copy of the generated rows (tools/gen_catalog.py); nothing under gpud_b200/ is compiled here */
 
 /* components/accelerator/nvidia/xid/kmsg.go:22,29,38,43 ; sxid/kmsg.go:17,20 — verbatim */
 static const char* RX[28] = {

@@ -1089,3 +1089,35 @@ def test_component_objects_of_the_three_paths(ctx):
     assert health == 2 and "nvlink" in reason.lower()
     assert nv2.last_health_states()[0]["health"] == "Unhealthy"
     nv.close(); nv2.close()
+
+
+def test_ring_full_shape_equals_the_oracle(ctx):
+    """BASELINE configs[3] on one GPU, the WHOLE result: 512 fields x 1 Mi samples of the SURVEY 8(d) stream (gauges + spikes + monotone
+    counters), every one of the 512 x 1049 windows and the W = CAP range against the C oracle - bit-exact min / max / p99 / n_over,
+    mean / EMA within 1e-6 relative to the value (the achieved error is ~1e-14)."""
+    import torch
+    import synth_device as sd
+    from oracle import coracle
+    F, cap, W = 512, 1 << 20, 1000
+    seed = 0x67707564
+    thr = sd.thresholds("survey", F, cap, seed)
+    r = g.Ring(ctx, F, cap, W, thresholds=thr)
+    host = np.empty((F, cap), dtype=np.float64)
+    sd.fill_ring(r, "survey", F, cap, seed, torch.device("cuda", 0), host_copy=host)
+    got = r.reduce_all()
+    want = coracle.windows_fields(host, W, thr)
+    for k in ("min", "max", "p99"):
+        assert np.array_equal(got[k].view(np.uint64), want[k].view(np.uint64)), k
+    assert np.array_equal(got["n_over"].astype(np.uint64), want["n_over"].astype(np.uint64)) and int(want["n_over"].sum()) > 100000
+    for k in ("mean", "ema"):
+        rel = np.abs(got[k] - want[k]) / np.maximum(np.abs(want[k]), 1e-300)
+        assert float(rel.max()) <= 1e-6, (k, float(rel.max()))
+    rr = r.reduce_range(0)
+    assert r.range_stats()[2] == 0                      # no field needed the radix fallback on this stream
+    wr = coracle.windows_fields(host, cap, thr, alpha=2.0 / (W + 1.0))
+    for k in ("min", "max", "p99"):
+        assert np.array_equal(rr[k].view(np.uint64), wr[k][:, 0].view(np.uint64)), k
+    assert np.array_equal(rr["n_over"].astype(np.uint64), wr["n_over"][:, 0].astype(np.uint64))
+    for k in ("mean", "ema"):
+        assert float(np.max(np.abs(rr[k] - wr[k][:, 0]) / np.maximum(np.abs(wr[k][:, 0]), 1e-300))) <= 1e-6, k
+    r.close()

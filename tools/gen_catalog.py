@@ -238,7 +238,15 @@ def main():
     L.append("};")
     with open(os.path.join(ROOT, "gpud_b200/csrc/catalog_data.inc"), "w") as f:
         f.write("\n".join(L) + "\n")
-    print("xid %d, rules %d, sxid %d -> oracle/catalog.json, gpud_b200/csrc/catalog_data.inc" % (len(xid), len(rules), len(sxid)))
+    # the C oracle gets its OWN copy (oracle/ compiles nothing from gpud_b200/): same generator, separate file, own row typedefs
+    with open(os.path.join(ROOT, "oracle/oracle_catalog_data.inc"), "w") as f:
+        f.write("/* TEST INFRASTRUCTURE: the oracle's copy of the generated catalog rows (tools/gen_catalog.py). */\n")
+        f.write("typedef struct { int code; int event; int n_actions; int actions[4]; const char* description; const char* mnemonic; } gpud_cat_xid_row;\n")
+        f.write("typedef struct { int xid; const char* unit; const char* pat_v1; const char* pat_v2; unsigned int error_status; const char* resolution;\n"
+                "                 const char* investigatory; const char* severity; } gpud_cat_rule_row;\n")
+        f.write("typedef struct { int sxid; int event; int n_actions; int actions[4]; int potential_fatal; int always_fatal; const char* name; } gpud_cat_sxid_row;\n")
+        f.write("\n".join(L) + "\n")
+    print("xid %d, rules %d, sxid %d -> oracle/catalog.json, gpud_b200/csrc/catalog_data.inc, oracle/oracle_catalog_data.inc" % (len(xid), len(rules), len(sxid)))
 
 
 if __name__ == "__main__":
