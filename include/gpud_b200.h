@@ -358,8 +358,12 @@ int32_t gpud_kmsg_scan_sharded(gpud_ctx* ctx, const uint8_t* buf, int64_t len, i
 /* Device-resident variant: dev_buf on `dev`; kernels only, results copied to the caller's host arrays. */
 int32_t gpud_kmsg_scan_device(gpud_ctx* ctx, int32_t dev, const uint8_t* dev_buf, int64_t len, int32_t mode,
                               gpud_xid_hit* hits, int64_t cap, int64_t* n_hits, int64_t* n_units, void* cuda_stream);
-/* Device time (ms) of the three kernels of the last scan on `dev`: [0] anchor filter, [1] separator prefix, [2] match. */
+/* Device time (ms) of the last scan on `dev`.  By default the scan's kernels run as one overlapped chain (programmatic dependent
+ * launch, no event between them): ms3[0] = the whole device time, ms3[1] = ms3[2] = 0.  After gpud_kmsg_scan_phase_timing(ctx, dev, 1)
+ * the launches are plain and split by events: [0] anchor filter, [1] separator prefix, [2] match (candidate sort + automata + unit
+ * numbers) - a profiling aid; the results of a scan do not depend on the setting. */
 int32_t gpud_kmsg_scan_kernel_ms(gpud_ctx* ctx, int32_t dev, float* ms3);
+int32_t gpud_kmsg_scan_phase_timing(gpud_ctx* ctx, int32_t dev, int32_t on);
 /* Counters of the last scan on `dev`: [0] verified anchors, [1] hits, [2] unit separators. */
 int32_t gpud_kmsg_scan_stats(gpud_ctx* ctx, int32_t dev, int64_t* out3);
 /* Classify already-extracted hits (fills event_type/actions/rule_index/detail_variant) with the device LUT

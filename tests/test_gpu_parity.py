@@ -267,6 +267,25 @@ def test_scan_ragged_offsets(ctx):
         assert [(h.unit_index, h.code, h.unit_offset) for h in hits] == [(1, 79, pad + 1)], pad
 
 
+def test_scan_anchor_prefilter_alignments(ctx):
+    """the filter's pre-filter ('X' byte / first aligned word of "fallen off the bus") must flag every anchor wherever it falls
+    relative to the 4 / 16 / 512 / 2048-byte boundaries, and the look-alikes ("called", "len 64", lone 'X') must stay silent"""
+    lines = [b"NVRM: GPU 0000:29:00.0: GPU has fallen off the bus.", b"nvidia-nvswitch3: SXid (PCI:0000:05:00.0): 12028, Non-fatal, Link 32 egress",
+             b"NVRM:   The NVIDIA GPU 0000:18:00.0 (PCI ID) has fallen off the bus and is not responding to commands.",
+             b"fallen off the bus", b"SXid", b"XXid SXi called allen len 64 fall alle llen X fallen off the bu",
+             # units longer than the 512-byte window the match kernel settles unit bounds in: the thread's own walk takes over
+             b"x" * 300 + b" NVRM: Xid (PCI:0000:05:00): 79, pid=1, name=p" + b"y" * 400,
+             b"N" * 270 + b"NVRM: GPU 0000:29:00.0: GPU has fallen off the bus." + b"f" * 290,
+             b"SXid (PCI:0000:05:00.0): 1, x " + b"S" * 250 + b" SXid (PCI:0000:05:00.0): 12028, Non-fatal"]
+    for line in lines:
+        for pad in list(range(0, 36)) + [492, 495, 509, 510, 511, 512, 2030, 2044, 2045, 2046, 2047, 2048]:
+            for lead in (b"a" * pad + b"\n", b"a" * pad):
+                buf = lead + line + b"\nfallen off the called len X tail"
+                hits, n_units = ctx.kmsg_scan(buf)
+                assert n_units == buf.count(b"\n") + 1
+                _cmp_hits(hits, O.scan_lines(buf))
+
+
 def test_hit_json_matches_oracle(ctx):
     lines = synth.hit_lines()
     buf = "\n".join(lines).encode()

@@ -3,6 +3,7 @@ sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
 import numpy as np, torch
 import gpud_b200 as g, synth
 ctx = g.Context([0])
+ctx.scan_phase_timing(True)          # per-phase event timing (plain launches)
 def run(name, buf):
     d = torch.frombuffer(bytearray(buf), dtype=torch.uint8).cuda(); torch.cuda.synchronize()
     ms = []
