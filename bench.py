@@ -547,6 +547,11 @@ def main():
                       "fields": len(g.POLL_FIELDS), "polls": int(rows.shape[0]), "polls_per_s": rows.shape[0] / sec,
                       "samples_per_s": rows.shape[0] * len(g.POLL_FIELDS) / sec,
                       "last_row": {k: int(v) for k, v in zip(g.POLL_FIELDS, rows[-1])}, "getter_failures": poller.errors()[0]}
+            try:                                                 # GPM (gpm/gpm.go:65-149): one 250 ms sample interval under whatever is running
+                gm = poller.gpm_metrics(250)
+                ingest["gpm"] = {"supported": bool(gm.supported), "sample_s": gm.sample_seconds, "metrics": gm.as_dict() if gm.supported else None}
+            except Exception as ex:
+                ingest["gpm"] = {"error": repr(ex)}
             poller.close()
             iring.close()
         except Exception as ex:

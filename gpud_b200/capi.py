@@ -345,6 +345,29 @@ class EccErrors(C.Structure):
                 ("pad", C.c_uint8 * 5)]
 
 
+GPM_METRICS = ("sm_occupancy", "integer_util", "any_tensor_util", "dfma_tensor_util", "hmma_tensor_util", "imma_tensor_util", "fp64_util", "fp32_util", "fp16_util")
+GPM_METRIC_IDS = (3, 4, 5, 6, 7, 9, 11, 12, 13)          # nvml.GPM_METRIC_* of the names above (gpm/component.go:56-64)
+
+
+class GpmMetrics(C.Structure):
+    _fields_ = [("value", C.c_double * 9), ("nvml_rc", C.c_int32 * 9), ("supported", C.c_int32), ("sample_seconds", C.c_double)]
+
+    def as_dict(self):
+        return dict(zip(GPM_METRICS, list(self.value)))
+
+
+def gpm_check(metrics):
+    """gpud_gpm_check: (health, reason)"""
+    n = len(metrics)
+    arr = (GpmMetrics * max(n, 1))(*metrics)
+    health = C.c_int32()
+    buf = C.create_string_buffer(256)
+    k = lib().gpud_gpm_check(arr, n, C.byref(health), buf, 256)
+    if k < 0:
+        raise GpudError(k, "gpud_gpm_check")
+    return health.value, buf.value.decode()
+
+
 def nvml_devices(cap: int = 16):
     """gpud_nvml_devices: (list of NvmlDevice, driver version)"""
     arr = (NvmlDevice * cap)()
@@ -425,6 +448,21 @@ class Poller:
         e = EccErrors()
         self.ctx._check(self._L.gpud_poller_ecc_errors(self._h, C.byref(e)))
         return e
+
+    def gpm_supported(self) -> bool:
+        v = C.c_int32()
+        self.ctx._check(self._L.gpud_poller_gpm_supported(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def gpm_metrics(self, sample_ms: int = 5000) -> "GpmMetrics":
+        m = GpmMetrics()
+        self.ctx._check(self._L.gpud_poller_gpm_metrics(self._h, sample_ms, C.byref(m)))
+        return m
+
+    def poll_gpm(self, ring: "Ring", n_polls: int, sample_ms: int = 5000) -> float:
+        sec = C.c_double()
+        self.ctx._check(self._L.gpud_poller_poll_gpm(self._h, ring._h, n_polls, sample_ms, C.byref(sec)))
+        return sec.value
 
     def field_row(self):
         """one nvmlDeviceGetFieldValues call: ({name: value}, {name: nvml return code})"""
@@ -642,7 +680,7 @@ class FabricVerdict(C.Structure):
 # every symbol include/gpud_b200.h declares (tests check the library exports each one)
 SYMBOLS = ["gpud_abi_version", "gpud_sizeof", "gpud_ctx_create", "gpud_ctx_destroy", "gpud_last_error", "gpud_host_alloc",
            "gpud_host_free", "gpud_ring_create", "gpud_ring_destroy", "gpud_ring_set_stream", "gpud_ring_push",
-           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_record_reboot", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_errors", "gpud_poll_row_hold", "gpud_nvml_devices", "gpud_nvml_devices_arg", "gpud_nvml_bus_id", "gpud_poller_remapped_rows", "gpud_remapped_rows_check", "gpud_poller_ecc_errors", "gpud_poller_field_row", "gpud_poller_poll_fields", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
+           "gpud_ring_push_device", "gpud_ring_push_raw", "gpud_clock_event_reasons", "gpud_hw_slowdown_event_message", "gpud_hw_slowdown_check", "gpud_store_insert_hw_slowdown", "gpud_store_open", "gpud_store_close", "gpud_store_last_error", "gpud_store_event_table", "gpud_store_insert_event", "gpud_store_insert_xid_hits", "gpud_store_metrics_table", "gpud_store_record_metrics", "gpud_kmsg_syncer_create", "gpud_kmsg_syncer_destroy", "gpud_kmsg_syncer_feed", "gpud_store_find_event", "gpud_store_record_reboot", "gpud_xid_state_from_store", "gpud_sxid_state_from_store", "gpud_store_get_events", "gpud_store_latest_event", "gpud_store_purge_events", "gpud_kmsg_syncer_configure", "gpud_kmsg_syncer_configure_component", "gpud_kmsg_syncer_offer", "gpud_ib_scan", "gpud_ib_reason", "gpud_poller_create", "gpud_poller_destroy", "gpud_poller_poll", "gpud_poller_last_rows", "gpud_poller_errors", "gpud_poll_row_hold", "gpud_nvml_devices", "gpud_nvml_devices_arg", "gpud_nvml_bus_id", "gpud_poller_remapped_rows", "gpud_remapped_rows_check", "gpud_poller_ecc_errors", "gpud_poller_field_row", "gpud_poller_poll_fields", "gpud_poller_gpm_supported", "gpud_poller_gpm_metrics", "gpud_poller_poll_gpm", "gpud_gpm_check", "gpud_poller_fabric_raw", "gpud_poller_product_name", "gpud_poller_temperature", "gpud_temperature_check", "gpud_temperature_reason", "gpud_poller_counters", "gpud_ring_counts", "gpud_ring_reduce", "gpud_ring_sync", "gpud_ring_kernel_ms", "gpud_ring_read",
            "gpud_ring_result_ptr", "gpud_ring_reduce_range", "gpud_ring_range_stats", "gpud_ring_set_cta_reserve", "gpud_kmsg_scan", "gpud_kmsg_scan_sharded", "gpud_kmsg_scan_device", "gpud_kmsg_scan_kernel_ms", "gpud_kmsg_scan_phase_timing", "gpud_kmsg_scan_stats", "gpud_xid_classify",
            "gpud_hit_detail_json", "gpud_xid_description", "gpud_xid_mnemonic", "gpud_sxid_name", "gpud_nvlink_rule_hint", "gpud_sxid_reason", "gpud_sxid_get_detail", "gpud_store_insert_sxid_hits", "gpud_product_mem_caps", "gpud_product_fm_supported", "gpud_product_fabric_state_supported", "gpud_xid_get_detail", "gpud_xid_detail", "gpud_xid_build_message", "gpud_xid_hit_message", "gpud_xid_device_matches_bus_id", "gpud_kmsg_event_name", "gpud_kmsg_event_message", "gpud_kmsg_component", "gpud_kmsg_hit_message", "gpud_kmsg_stateful_create", "gpud_kmsg_stateful_destroy", "gpud_kmsg_stateful_feed", "gpud_component_create", "gpud_component_destroy", "gpud_component_name", "gpud_component_start", "gpud_component_check", "gpud_component_last_health_states", "gpud_component_events", "gpud_component_close", "gpud_component_checks", "gpud_component_xid_set_source", "gpud_component_xid_set_healthy", "gpud_component_xid_add_reboot", "gpud_component_xid_set_devices", "gpud_component_ring", "gpud_kmsg_stateful_feed_units", "gpud_kmsg_deduper_create", "gpud_kmsg_deduper_destroy", "gpud_kmsg_dedup_units",
            "gpud_fabric_issues", "gpud_fabric_suggest_reboot", "gpud_set_nvml_error_string", "gpud_nvml_error_strings_from_driver", "gpud_fabric_reason", "gpud_fabric_report_reason", "gpud_fabric_pack", "gpud_fabric_verdict_device", "gpud_comm_unique_id", "gpud_comm_init", "gpud_fabric_gather",
@@ -689,6 +727,8 @@ def lib() -> C.CDLL:
         "gpud_nvml_devices": (i32, [vp, i32, vp, vp, i32]), "gpud_nvml_devices_arg": (i32, [vp, i32]), "gpud_nvml_bus_id": (i32, [C.c_char_p, vp, i32]),
         "gpud_poller_remapped_rows": (i32, [vp, vp]), "gpud_remapped_rows_check": (i32, [vp, vp, i32, vp, vp, vp, i32]),
         "gpud_poller_ecc_errors": (i32, [vp, vp]), "gpud_poller_field_row": (i32, [vp, vp, vp]), "gpud_poller_poll_fields": (i32, [vp, vp, i64, i64, vp]),
+        "gpud_poller_gpm_supported": (i32, [vp, vp]), "gpud_poller_gpm_metrics": (i32, [vp, i64, vp]), "gpud_poller_poll_gpm": (i32, [vp, vp, i64, i64, vp]),
+        "gpud_gpm_check": (i32, [vp, i32, vp, vp, i32]),
         "gpud_poller_temperature": (i32, [vp, C.POINTER(Temperature)]), "gpud_temperature_check": (i32, [C.POINTER(Temperature), i32, vp]),
         "gpud_temperature_reason": (i32, [vp, vp, i32, i32, vp, vp, i32]),
         "gpud_poller_counters": (i32, [vp, C.POINTER(PollCounters)]),
@@ -739,7 +779,7 @@ def lib() -> C.CDLL:
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype, fn.argtypes = res, args
-    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters, EventRow, NvmlDevice, RemappedRows, EccErrors)):
+    for which, st in enumerate((XidHit, FabricRaw, FabricLocal, FabricVerdict, RingCfg, KmsgEvent, IbSnapshot, IbVerdict, Metric, DedupRule, Temperature, PollCounters, EventRow, NvmlDevice, RemappedRows, EccErrors, GpmMetrics)):
         if L.gpud_sizeof(which) != C.sizeof(st):
             raise GpudError(-1, "ABI layout mismatch for %s: C %d vs ctypes %d" % (st.__name__, L.gpud_sizeof(which), C.sizeof(st)))
     _lib = L

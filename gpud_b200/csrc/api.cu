@@ -92,6 +92,7 @@ extern "C" int32_t gpud_sizeof(int32_t which) {
     case 13: return (int32_t)sizeof(gpud_nvml_device);
     case 14: return (int32_t)sizeof(gpud_remapped_rows);
     case 15: return (int32_t)sizeof(gpud_ecc_errors);
+    case 16: return (int32_t)sizeof(gpud_gpm_metrics);
   }
   return -1;
 }

@@ -326,10 +326,12 @@ __global__ void __launch_bounds__(256, 4) k_scan_filter(ScanBuf b, uint32_t* __r
     for (int u = 0; u < 4; ++u) q[u] = qn[u];
     const unsigned tail = tailn;              // first word after the 2 KB run (lane 31 of the last chunk needs it)
     if (c0 + n_warps * 4 < n_chunks) load_run(b, aligned, c0 + n_warps * 4, lane, qn, tailn);
+    const int nu = n_chunks - c0 < 4 ? (int)(n_chunks - c0) : 4;     // chunks of this run inside the buffer (warp-uniform)
+    unsigned sep_lo = 0, sep_hi = 0;            // my separator counts of chunks 0, 1 and 2, 3: two 16-bit fields each (a chunk has at most 512)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t chunk = c0 + u;
-      if (chunk >= n_chunks) break;              // warp-uniform
+      if (u >= nu) break;
       // look-ahead word: right neighbour's first word; lane 31 takes lane 0 of the next chunk (or the tail word)
       unsigned nx = __shfl_down_sync(kFull, q[u].x, 1);
       const unsigned nx_chunk = __shfl_sync(kFull, u < 3 ? q[u < 3 ? u + 1 : 3].x : 0u, 0);
@@ -444,8 +446,17 @@ __global__ void __launch_bounds__(256, 4) k_scan_filter(ScanBuf b, uint32_t* __r
           }
         }
       }
-      sep = __reduce_add_sync(kFull, sep);
-      if (lane == 0) chunk_sep[chunk] = sep;
+      if (u < 2) sep_lo |= sep << (16 * u); else sep_hi |= sep << (16 * (u - 2));
+    }
+    // two reductions and one store per run instead of four of each
+    sep_lo = __reduce_add_sync(kFull, sep_lo);
+    sep_hi = __reduce_add_sync(kFull, sep_hi);
+    if (lane == 0) {
+      if (nu == 4) *reinterpret_cast<uint4*>(chunk_sep + c0) = make_uint4(sep_lo & 0xffffu, sep_lo >> 16, sep_hi & 0xffffu, sep_hi >> 16);   // c0 % 4 == 0
+      else {
+        const unsigned v[4] = {sep_lo & 0xffffu, sep_lo >> 16, sep_hi & 0xffffu, sep_hi >> 16};
+        for (int u = 0; u < nu; ++u) chunk_sep[c0 + u] = v[u];
+      }
     }
   }
   if (n_queued) flush_cands(s_queue[threadIdx.x >> 5], n_queued, lane, cands, n_cand, cand_cap, fam_cnt);

@@ -59,6 +59,11 @@ struct Nvml {
   nvmlReturn_t (*by_index)(unsigned int, nvmlDevice_t*) = nullptr;
   nvmlReturn_t (*pci_info)(nvmlDevice_t, void*) = nullptr;
   nvmlReturn_t (*driver_version)(char*, unsigned int) = nullptr;
+  nvmlReturn_t (*gpm_support)(nvmlDevice_t, void*) = nullptr;
+  nvmlReturn_t (*gpm_alloc)(void**) = nullptr;
+  nvmlReturn_t (*gpm_free)(void*) = nullptr;
+  nvmlReturn_t (*gpm_sample)(nvmlDevice_t, void*) = nullptr;
+  nvmlReturn_t (*gpm_metrics)(void*) = nullptr;
 };
 
 Nvml* nvml() {
@@ -95,6 +100,11 @@ Nvml* nvml() {
       *(void**)&n.by_index = dlsym(n.so, "nvmlDeviceGetHandleByIndex_v2");
       *(void**)&n.pci_info = dlsym(n.so, "nvmlDeviceGetPciInfo_v3");
       *(void**)&n.driver_version = dlsym(n.so, "nvmlSystemGetDriverVersion");
+      *(void**)&n.gpm_support = dlsym(n.so, "nvmlGpmQueryDeviceSupport");     // driver >= 520; absent symbols = not supported
+      *(void**)&n.gpm_alloc = dlsym(n.so, "nvmlGpmSampleAlloc");
+      *(void**)&n.gpm_free = dlsym(n.so, "nvmlGpmSampleFree");
+      *(void**)&n.gpm_sample = dlsym(n.so, "nvmlGpmSampleGet");
+      *(void**)&n.gpm_metrics = dlsym(n.so, "nvmlGpmMetricsGet");
       if (!n.init || !n.by_pci || !n.temperature || !n.power || !n.clock || !n.util || !n.memory || n.init() != 0) { dlclose(n.so); n.so = nullptr; }
     }
   }
@@ -117,6 +127,7 @@ struct gpud_poller {
   uint64_t n_failed[GPUD_POLL_N_FIELDS] = {0};
   uint64_t* field_rows = nullptr;                // pinned [cap_rows][GPUD_FIELD_ROW_N] (gpud_poller_poll_fields)
   uint64_t field_held[GPUD_FIELD_ROW_N] = {0};
+  double gpm_held[GPUD_GPM_N] = {0};
 };
 
 extern "C" int32_t gpud_poller_create(gpud_ctx* ctx, int32_t dev, gpud_ring* ring, gpud_poller** out) {
@@ -644,4 +655,147 @@ extern "C" int32_t gpud_poller_poll_fields(gpud_poller* p, gpud_ring* ring, int6
   clock_gettime(CLOCK_MONOTONIC, &t1);
   if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
   return GPUD_OK;
+}
+
+// ---- GPM (components/accelerator/nvidia/gpm) ------------------------------------------------------------------------------------
+// nvml.h's GPM records (version 1 of both): the metric array is sized like go-nvml's binding ([210]; NVML reads numMetrics of them).
+namespace {
+struct NvmlGpmSupport { unsigned int version, is_supported; };
+struct NvmlGpmMetric { unsigned int metric_id; nvmlReturn_t nvml_return; double value; struct { char* short_name; char* long_name; char* unit; } info; };
+struct NvmlGpmMetricsGet { unsigned int version, num_metrics; void* sample1; void* sample2; NvmlGpmMetric metrics[210]; };
+// the component's default ids (gpm/component.go:56-64): SM_OCCUPANCY, INTEGER_UTIL, ANY / DFMA / HMMA / IMMA_TENSOR_UTIL, FP64 / FP32 / FP16_UTIL
+const unsigned int kGpmIds[GPUD_GPM_N] = {3, 4, 5, 6, 7, 9, 11, 12, 13};
+bool is_version_mismatch(Nvml* N, nvmlReturn_t rc) {          // nvmlerrors.IsVersionMismatchError: the return code or its text
+  if (rc == 25 /* NVML_ERROR_ARGUMENT_VERSION_MISMATCH */) return true;
+  const char* e = N->err ? N->err(rc) : nullptr;
+  if (!e) return false;
+  std::string t(e);
+  for (auto& c : t) c = (char)tolower((unsigned char)c);
+  return t.find("version mismatch") != std::string::npos;
+}
+struct GpmSample {
+  Nvml* N; void* h = nullptr;
+  explicit GpmSample(Nvml* n) : N(n) {}
+  ~GpmSample() { if (h && N->gpm_free) N->gpm_free(h); }
+};
+}  // namespace
+
+// SupportedByDevice (gpm/gpm.go:17-45): not-supported and version-mismatch answers mean "no", lost / reset-required GPUs are errors
+extern "C" int32_t gpud_poller_gpm_supported(gpud_poller* p, int32_t* supported) {
+  if (!p || !supported) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return GPUD_E_UNSUPPORTED;
+  *supported = 0;
+  if (!N->gpm_support || !N->gpm_alloc || !N->gpm_free || !N->gpm_sample || !N->gpm_metrics) return GPUD_OK;
+  NvmlGpmSupport q{1u, 0u};
+  const nvmlReturn_t rc = N->gpm_support(p->h, &q);
+  if (is_not_supported(N, rc) || is_version_mismatch(N, rc)) return GPUD_OK;
+  if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+  if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
+  if (rc != 0) return gpud_fail(p->ctx, GPUD_E_STATE, "could not query GPM support: %s", N->err ? N->err(rc) : "error");
+  *supported = q.is_supported != 0;
+  return GPUD_OK;
+}
+
+static int32_t gpm_take(gpud_poller* p, Nvml* N, void* sample) {
+  const nvmlReturn_t rc = N->gpm_sample(p->h, sample);
+  return rc == 0 ? GPUD_OK : gpud_fail(p->ctx, GPUD_E_STATE, "could not get sample: %s", N->err ? N->err(rc) : "error");
+}
+static int32_t gpm_between(gpud_poller* p, Nvml* N, void* s1, void* s2, gpud_gpm_metrics* out) {
+  static thread_local NvmlGpmMetricsGet g;                       // 8.4 KB
+  memset(&g, 0, sizeof g);
+  g.version = 1;
+  g.num_metrics = GPUD_GPM_N;
+  g.sample1 = s1;
+  g.sample2 = s2;
+  for (int i = 0; i < GPUD_GPM_N; ++i) g.metrics[i].metric_id = kGpmIds[i];
+  const nvmlReturn_t rc = N->gpm_metrics(&g);
+  if (rc != 0) return gpud_fail(p->ctx, GPUD_E_STATE, "failed to get gpm metric: %s", N->err ? N->err(rc) : "error");
+  for (int i = 0; i < GPUD_GPM_N; ++i) { out->value[i] = g.metrics[i].value; out->nvml_rc[i] = (int32_t)g.metrics[i].nvml_return; }
+  return GPUD_OK;
+}
+
+// GetGPMMetrics (gpm/gpm.go:65-149): two samples `sample_ms` apart, one nvmlGpmMetricsGet over the nine ids
+extern "C" int32_t gpud_poller_gpm_metrics(gpud_poller* p, int64_t sample_ms, gpud_gpm_metrics* out) {
+  if (!p || !out || sample_ms < 0) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N) return GPUD_E_UNSUPPORTED;
+  memset(out, 0, sizeof *out);
+  if (!N->gpm_support || !N->gpm_alloc || !N->gpm_free || !N->gpm_sample || !N->gpm_metrics) return GPUD_OK;      // supported = 0
+  GpmSample s1(N), s2(N);
+  nvmlReturn_t rc = N->gpm_alloc(&s1.h);
+  if (is_not_supported(N, rc) || is_version_mismatch(N, rc)) return GPUD_OK;
+  if (is_gpu_lost(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU lost");
+  if (is_reset_required(N, rc)) return gpud_fail(p->ctx, GPUD_E_STATE, "GPU requires reset");
+  if (rc != 0) return gpud_fail(p->ctx, GPUD_E_STATE, "could not allocate sample: %s", N->err ? N->err(rc) : "error");
+  rc = N->gpm_alloc(&s2.h);
+  if (rc != 0) return gpud_fail(p->ctx, GPUD_E_STATE, "could not allocate sample: %s", N->err ? N->err(rc) : "error");
+  int32_t r = gpm_take(p, N, s1.h);
+  if (r) return r;
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (sample_ms) { timespec ts{(time_t)(sample_ms / 1000), (long)(sample_ms % 1000) * 1000000L}; nanosleep(&ts, nullptr); }
+  r = gpm_take(p, N, s2.h);
+  if (r) return r;
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  r = gpm_between(p, N, s1.h, s2.h, out);
+  if (r) return r;
+  out->supported = 1;
+  out->sample_seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return GPUD_OK;
+}
+
+// The same getter as a field source of the ring ("GPM f64"): n_polls rows of the nine metrics, one row per sample
+// interval - consecutive rows share a sample (n_polls + 1 nvmlGpmSampleGet calls), so the intervals tile the time line without gaps.
+extern "C" int32_t gpud_poller_poll_gpm(gpud_poller* p, gpud_ring* ring, int64_t n_polls, int64_t sample_ms, double* seconds) {
+  if (!p || !ring || n_polls < 0 || sample_ms < 0) return GPUD_E_INVALID;
+  Nvml* N = nvml();
+  if (!N || !N->gpm_support || !N->gpm_alloc || !N->gpm_free || !N->gpm_sample || !N->gpm_metrics) return GPUD_E_UNSUPPORTED;
+  int32_t sup = 0;
+  int32_t r = gpud_poller_gpm_supported(p, &sup);
+  if (r) return r;
+  if (!sup) return gpud_fail(p->ctx, GPUD_E_UNSUPPORTED, "GPM not supported");
+  GpmSample a(N), b(N);
+  if (N->gpm_alloc(&a.h) != 0 || N->gpm_alloc(&b.h) != 0) return gpud_fail(p->ctx, GPUD_E_STATE, "could not allocate sample");
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  r = gpm_take(p, N, a.h);
+  if (r) return r;
+  void* prev = a.h;
+  void* next = b.h;
+  for (int64_t i = 0; i < n_polls; ++i) {
+    if (sample_ms) { timespec ts{(time_t)(sample_ms / 1000), (long)(sample_ms % 1000) * 1000000L}; nanosleep(&ts, nullptr); }
+    r = gpm_take(p, N, next);
+    if (r) return r;
+    gpud_gpm_metrics m;
+    r = gpm_between(p, N, prev, next, &m);
+    if (r) return r;
+    double row[GPUD_GPM_N];
+    for (int c = 0; c < GPUD_GPM_N; ++c) {                                  // a metric NVML could not compute holds its last good value
+      if (m.nvml_rc[c] == 0) p->gpm_held[c] = m.value[c];
+      row[c] = p->gpm_held[c];
+    }
+    r = gpud_ring_push(ring, row, 1);
+    if (r) return r;
+    std::swap(prev, next);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return GPUD_OK;
+}
+
+// The gpm component's Check over the box's readings (gpm/component.go:196-290): one GPU without GPM -> Healthy "GPM not supported",
+// else Healthy "all N GPU(s) were checked, no GPM issue found"; getter errors are the getters' own return codes.
+extern "C" int32_t gpud_gpm_check(const gpud_gpm_metrics* m, int32_t n, int32_t* health, char* reason, int32_t cap) {
+  if (n < 0 || (n && !m) || !health || !reason || cap < 1) return GPUD_E_INVALID;
+  *health = 0;
+  char buf[96];
+  bool all = true;
+  for (int32_t i = 0; i < n; ++i) all = all && m[i].supported != 0;
+  if (!all) snprintf(buf, sizeof buf, "GPM not supported");
+  else snprintf(buf, sizeof buf, "all %d GPU(s) were checked, no GPM issue found", n);
+  const int len = (int)strlen(buf);
+  if (len + 1 > cap) return -1;
+  memcpy(reason, buf, (size_t)len + 1);
+  return len;
 }

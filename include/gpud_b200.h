@@ -39,7 +39,7 @@ typedef struct gpud_ring gpud_ring;
 int32_t gpud_abi_version(void);
 /* sizeof of the ABI structs for binding layout checks (5 gpud_kmsg_event, 6 gpud_ib_snapshot, 7 gpud_ib_verdict, 8 gpud_metric):
  * 0 gpud_xid_hit, 1 gpud_fabric_raw, 2 gpud_fabric_local,
- * 3 gpud_fabric_verdict, 4 gpud_ring_cfg, 9 gpud_dedup_rule .. 12 gpud_event_row, 13 gpud_nvml_device, 14 gpud_remapped_rows, 15 gpud_ecc_errors; -1 otherwise. */
+ * 3 gpud_fabric_verdict, 4 gpud_ring_cfg, 9 gpud_dedup_rule .. 12 gpud_event_row, 13 gpud_nvml_device, 14 gpud_remapped_rows, 15 gpud_ecc_errors, 16 gpud_gpm_metrics; -1 otherwise. */
 int32_t gpud_sizeof(int32_t which);
 
 /* One context per process; `cuda_devs[n]` are the CUDA ordinals this process drives (one per rank when
@@ -193,6 +193,19 @@ enum { GPUD_FIELD_POWER_INSTANT_MW = 0, GPUD_FIELD_POWER_AVERAGE_MW = 1, GPUD_FI
        GPUD_FIELD_PCIE_REPLAY = 16, GPUD_FIELD_ROW_N = 17 };
 int32_t gpud_poller_field_row(gpud_poller* poller, uint64_t* values, int32_t* nvml_rc);
 int32_t gpud_poller_poll_fields(gpud_poller* poller, gpud_ring* ring, int64_t n_polls, int64_t interval_us, double* seconds);
+/* GPM (components/accelerator/nvidia/gpm): SupportedByDevice (gpm.go:17-45; "not supported" and "version mismatch" answers, or an NVML
+ * without the GPM entry points, mean 0) and GetGPMMetrics (gpm.go:65-149): two nvmlGpmSampleGet `sample_ms` apart (the component: 5000)
+ * and one nvmlGpmMetricsGet over the component's nine metric ids (component.go:56-64), in the order of the enum; supported = 0 and
+ * zeroes where the device has no GPM.  gpud_poller_poll_gpm is the same getter as a field source: n_polls float64 rows of the nine
+ * metrics appended to `ring` (GPUD_GPM_N fields), consecutive rows sharing a sample.  gpud_gpm_check is the component's Check over
+ * the box's readings (component.go:196-290): returns the reason's length, -1 if it does not fit; *health 0 Healthy. */
+enum { GPUD_GPM_SM_OCCUPANCY = 0, GPUD_GPM_INTEGER_UTIL = 1, GPUD_GPM_ANY_TENSOR_UTIL = 2, GPUD_GPM_DFMA_TENSOR_UTIL = 3, GPUD_GPM_HMMA_TENSOR_UTIL = 4,
+       GPUD_GPM_IMMA_TENSOR_UTIL = 5, GPUD_GPM_FP64_UTIL = 6, GPUD_GPM_FP32_UTIL = 7, GPUD_GPM_FP16_UTIL = 8, GPUD_GPM_N = 9 };
+typedef struct { double value[GPUD_GPM_N]; int32_t nvml_rc[GPUD_GPM_N]; int32_t supported; double sample_seconds; } gpud_gpm_metrics;
+int32_t gpud_poller_gpm_supported(gpud_poller* poller, int32_t* supported);
+int32_t gpud_poller_gpm_metrics(gpud_poller* poller, int64_t sample_ms, gpud_gpm_metrics* out);
+int32_t gpud_poller_poll_gpm(gpud_poller* poller, gpud_ring* ring, int64_t n_polls, int64_t sample_ms, double* seconds);
+int32_t gpud_gpm_check(const gpud_gpm_metrics* metrics, int32_t n, int32_t* health, char* reason, int32_t cap);
 int32_t gpud_ring_counts(gpud_ring* ring, int64_t* total_pushed, int64_t* count, int64_t* n_windows);
 /* Launch the fused window-reduce (+ EMA carry) over the ring's current content; asynchronous. */
 int32_t gpud_ring_reduce(gpud_ring* ring);

@@ -1140,3 +1140,68 @@ def test_ring_full_shape_equals_the_oracle(ctx):
     for k in ("mean", "ema"):
         assert float(np.max(np.abs(rr[k] - wr[k][:, 0]) / np.maximum(np.abs(wr[k][:, 0]), 1e-300))) <= 1e-6, k
     r.close()
+
+
+@pytest.mark.gpu
+def test_poller_gpm_metrics_against_nvml(ctx):
+    """GetGPMMetrics (gpm/gpm.go:65-149): support flag equals NVML's; with a float32 / float64 kernel load running, the nine metrics
+    are percentages, the loaded pipes read non-zero, and a second reading through pynvml over the same kind of interval agrees on
+    which of them are busy.  The ring source appends one float64 row per interval."""
+    import threading
+    import pynvml
+    import torch
+    pynvml.nvmlInit()
+    ring = g.Ring(ctx, 9, 64, 8)
+    iring = g.Ring(ctx, len(g.POLL_FIELDS), 64, 8)
+    poller = g.Poller(ctx, iring)
+    devs, _ = g.capi.nvml_devices()
+    h = pynvml.nvmlDeviceGetHandleByIndex([d for d in devs if d.cuda_device == 0][0].index)
+    want_sup = bool(pynvml.nvmlGpmQueryDeviceSupport(h).isSupportedDevice)
+    assert poller.gpm_supported() == want_sup
+    if not want_sup:
+        m = poller.gpm_metrics(50)
+        assert m.supported == 0 and g.capi.gpm_check([m]) == (0, "GPM not supported")
+        return
+    stop = threading.Event()
+
+    def load():
+        a = torch.randn(4096, 4096, device="cuda")
+        d = torch.randn(2048, 2048, device="cuda", dtype=torch.float64)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        while not stop.is_set():
+            (a * 1.0001 + 0.5).sum()
+            (d * 1.0001 + 0.5).sum()
+            torch.cuda.synchronize()
+    t = threading.Thread(target=load)
+    t.start()
+    try:
+        import time
+        time.sleep(0.3)
+        m = poller.gpm_metrics(400)
+        s1, s2 = pynvml.nvmlGpmSampleAlloc(), pynvml.nvmlGpmSampleAlloc()
+        pynvml.nvmlGpmSampleGet(h, s1)
+        time.sleep(0.4)
+        pynvml.nvmlGpmSampleGet(h, s2)
+        q = pynvml.c_nvmlGpmMetricsGet_t()
+        q.version, q.numMetrics, q.sample1, q.sample2 = 1, 9, s1, s2
+        for i, mid in enumerate(g.capi.GPM_METRIC_IDS):
+            q.metrics[i].metricId = mid
+        pynvml.nvmlGpmMetricsGet(q)
+        ref = [q.metrics[i].value for i in range(9)]
+        sec = poller.poll_gpm(ring, 3, 150)
+        pynvml.nvmlGpmSampleFree(s1)
+        pynvml.nvmlGpmSampleFree(s2)
+    finally:
+        stop.set()
+        t.join()
+    assert m.supported == 1 and 0.39 < m.sample_seconds < 1.0
+    got = list(m.value)
+    assert all(rc == 0 for rc in m.nvml_rc), list(m.nvml_rc)
+    assert all(0.0 <= v <= 100.0 for v in got), got
+    d = m.as_dict()
+    assert d["sm_occupancy"] > 0.0 and d["fp32_util"] > 0.0 and d["fp64_util"] > 0.0, d
+    assert [v > 0.05 for v in got] == [v > 0.05 for v in ref] or all(abs(a - b) < 15.0 for a, b in zip(got, ref)), (got, ref)
+    assert g.capi.gpm_check([m]) == (0, "all 1 GPU(s) were checked, no GPM issue found")
+    assert 0.44 < sec < 2.0
+    ring.sync()
+    assert ring.counts()[0] == 3

@@ -773,3 +773,14 @@ def test_watcher_dedup_in_front_of_the_stateful_matchers():
     dr = dd.units(b"\n".join(recs), len(recs), mode=g.SCAN_RAW_KMSG, boot_unix=now - now % 60, now_unix=now)
     assert list(dr) == [0, 1, 0, 0, 0, 1]
     dd.close()
+
+
+def test_gpm_check_of_the_reference():
+    """gpm/component.go:196-290: one GPU without GPM -> Healthy "GPM not supported"; else the all-checked reason"""
+    M = g.capi.GpmMetrics
+    on, off = M(), M()
+    on.supported = 1
+    assert g.capi.gpm_check([on, on, on]) == (0, "all 3 GPU(s) were checked, no GPM issue found")
+    assert g.capi.gpm_check([on, off, on]) == (0, "GPM not supported")
+    assert g.capi.gpm_check([]) == (0, "all 0 GPU(s) were checked, no GPM issue found")
+    assert g.capi.GPM_METRIC_IDS == (3, 4, 5, 6, 7, 9, 11, 12, 13) and len(g.capi.GPM_METRICS) == 9
