@@ -1200,6 +1200,11 @@ __global__ void __launch_bounds__(128, GPUD_MATCH_BLOCKS) k_scan_match(ScanBuf b
   // (candidates per warp) x (one candidate's dependent-load chain), and a second wave of blocks costs a whole chain again.  The grid is
   // exactly what the device holds at once (host: occupancy x SMs) and the candidates per warp are the FEWEST that fit the list into
   // that one wave (it used to be a constant 8, which for the 100 MiB case left 7 % of the candidates to a second wave: 2 chains).
+  // Measured and NOT adopted: (a) a dynamic cursor (a lane claims its next candidate when it is done; working lanes per warp capped
+  // at 2 / 4 / 8 / 16): 142 / 114 / 85 / 77 us against 75 static - the kernel wants every candidate in flight at once, not balance;
+  // (b) 12 .. 32 resident warps per SM (launch bounds 3 .. 8 blocks): 75 us +- 3 throughout; (c) one shared copy of the byte searches
+  // (__noinline__, 10 k instead of 21 k instructions): 78 us.  What moves it is the candidates' own chains: the same buffer without
+  // the 3 % of NVLink5 / fallen-off-the-bus lines takes 54 us.
   const unsigned lane = threadIdx.x & 31;
   const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   unsigned long long per_warp = (n + n_warps - 1) / n_warps;
@@ -1337,6 +1342,9 @@ __device__ __forceinline__ void unit_index_of_hit(const ScanBuf& b, int mode, co
                                                   const unsigned long long* __restrict__ tile_base, gpud_xid_hit* hits, unsigned long long hi, int lane) {
   const int64_t us = hits[hi].unit_offset;
   const int64_t chunk = us / kChunk, c0 = chunk * kChunk;
+  // every lane asks for the two prefix entries NOW (one broadcast each), beside the block load below: behind the reduction they were a
+  // third dependent round trip of a kernel that is nothing but round trips
+  const unsigned long long before = tile_base[chunk >> 10] + chunk_local[chunk];
   unsigned cnt = 0;
   const int64_t lo = c0 + lane * 16;
   if (lo < us) {
@@ -1357,7 +1365,7 @@ __device__ __forceinline__ void unit_index_of_hit(const ScanBuf& b, int mode, co
     }
   }
   cnt = __reduce_add_sync(kFull, cnt);
-  if (lane == 0) hits[hi].unit_index = (int64_t)(tile_base[chunk >> 10] + chunk_local[chunk] + cnt);
+  if (lane == 0) hits[hi].unit_index = (int64_t)(before + cnt);
 }
 
 // detailFromNVLinkInfo for the extended hits of a scan, one WARP per hit: the three table searches (sub-code + status
@@ -1375,8 +1383,9 @@ __global__ void __launch_bounds__(256) k_scan_finish(ScanBuf b, int mode, const 
   const unsigned long long n_warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   for (unsigned long long hi = warp_g; hi < n; hi += n_warps) {
     gpud_xid_hit* h = hits + hi;
+    const int event_type = h->event_type;                            // asked for together with the unit offset (the store below would pin it behind)
     unit_index_of_hit(b, mode, chunk_local, tile_base, hits, hi, lane);
-    if (h->event_type != kPendingExtended) continue;                 // warp-uniform
+    if (event_type != kPendingExtended) continue;                    // warp-uniform
     const int xid = h->code, sub = h->sub_code;
     const uint32_t st = h->error_status, intr = h->intrinfo;
     char unit[40], norm[GPUD_T_ALIAS_LEN];
