@@ -439,6 +439,41 @@ def test_ring_tie_heavy_gauges(ctx, W, qn, qd):
     r.close()
 
 
+@pytest.mark.parametrize("W,qn,qd", [(1000, 99, 100), (1000, 999, 1000), (1000, 97, 100), (1024, 99, 100), (961, 99, 100), (1000, 50, 100)])
+def test_ring_positional_windows(ctx, W, qn, qd):
+    """windows whose high words tie and that are (nearly) in ascending order: the positional shortcut (min = first sample, max = last,
+    k-th largest = sample m - k) must hold exactly where it is taken and must NOT be taken where a sample breaks the order"""
+    n, cap = 8 * W, 8 * W
+    rng = np.random.default_rng(W * 13 + qn)
+    big = 2.0 ** 39
+    cnt = big + np.cumsum(rng.integers(0, 2001, n)).astype(np.float64)               # a monotone counter: high words tie, low words order it
+    k = W - int(np.ceil(W * qn / qd)) + 1                                               # the k-th largest is wanted
+    cols = [cnt,
+            big + np.cumsum(rng.integers(0, 2, n)).astype(np.float64),                  # long runs of equal values (ties at every rank)
+            np.full(n, big + 0.5),                                                      # flat with a non-zero low word
+            2.0 ** 52 + np.cumsum(rng.integers(0, 3, n)).astype(np.float64),            # one unit per ulp
+            cnt.copy(), cnt.copy(), cnt.copy(), cnt.copy(), cnt.copy(), cnt.copy(),
+            -cnt,                                                                       # descending and negative
+            np.sort(rng.random(n)) * 1e-300 + 1e-300,                                   # tiny sorted doubles (one high word)
+            cnt.copy(), cnt.copy()]
+    x = np.ascontiguousarray(np.stack(cols, axis=1))
+    w0 = np.arange(0, n, W)
+    x[w0 + 3, 4] = x[w0 + 700, 4]                   # an early sample as large as a late one, still below T: shortcut stays valid
+    x[w0 + W - 1, 5] = x[w0 + W - 2, 5] - 1.0       # the last sample is not the maximum
+    x[w0 + W - k, 6] = x[w0 + W - 1, 6]             # sample m - k is the largest of the top group
+    x[w0 + 5, 7] = x[w0 + W - 1, 7] + 1.0           # an early outlier above everything
+    x[w0 + 10, 8] = np.nan                          # NaN: the largest key of all
+    x[w0 + 0, 9] = x[w0 + 1, 9] + 1.0               # the first sample is not the minimum
+    x[w0 + 17, 12] = -0.0                           # a negative zero among positive samples: the smallest key
+    x[w0 + W // 2, 13] = np.inf
+    thr = synth.thresholds_for(x)
+    r = g.Ring(ctx, x.shape[1], cap, W, thresholds=thr, q_num=qn, q_den=qd)
+    r.push(x)
+    got = r.reduce_all()
+    _check_windows(got, x, W, thr, 0.0, qn, qd)
+    r.close()
+
+
 @pytest.mark.parametrize("dt", ["uint32", "int32", "float32", "int64", "uint64", "uint16", "int16", "uint8"])
 def test_ring_push_raw_types(ctx, dt):
     """raw NVML / DCGM sample types are widened on the device exactly like float64(v) on the host"""
