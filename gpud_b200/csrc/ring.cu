@@ -521,8 +521,13 @@ __global__ void __launch_bounds__((TMA ? kTmaWarps : kWarpsPerBlock) * 32, TMA ?
       auto at = [&](int t) { return __longlong_as_double((long long)sk[((t & 63) >> 1) * kRowU64 + 2 * (t >> 6) + (t & 1)]); };
       const double e0 = at(0), tv = at(tk), el = at(m - 1);
       bool ok = true;
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
+      const int i_low = tk >= 960 ? 30 : 0;          // the usual case (k <= m - 960): entries 0..29 (t < 960) all lie before sample m - k
+#pragma unroll 5
+      for (int i = 0; i < i_low; ++i) {
+        const double x = __longlong_as_double((long long)sk[lane * kRowU64 + i]);
+        ok = ok && e0 <= x && x <= tv;
+      }
+      for (int i = i_low; i < 32; ++i) {
         const int t = elem_index(lane, i);
         const double x = __longlong_as_double((long long)sk[lane * kRowU64 + i]);
         const bool in_lo = e0 <= x && x <= tv, in_hi = tv <= x && x <= el;
