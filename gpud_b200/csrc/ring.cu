@@ -495,7 +495,11 @@ __global__ void __launch_bounds__((TMA ? kTmaWarps : kWarpsPerBlock) * 32, TMA ?
       ep += __shfl_xor_sync(kFull, ep, o);
     }
     ep *= p.alpha;
-    nov = __reduce_add_sync(kFull, nov);
+    // the positional shortcut's pretest rides on this reduction (no extra warp operation on the common path): bits 16.. count the lanes
+    // whose own 32 samples span more than 8 high words or hold a negative one (nov itself is at most 1024)
+    const unsigned nov_flags = __reduce_add_sync(kFull, nov + ((mh - nh > 8u || (c_umax & 0x80000000u)) ? 0x10000u : 0u));
+    nov = nov_flags & 0xffffu;
+    const bool tied_nonneg = (nov_flags >> 16) == 0u;
 
     // ---- exact minimum: global min of the high words, then the low words of the rows that hold it ----
     // Every raw low word zero (integer readings below 2^21: degrees, %, MHz, MiB, mW): the high words order the window by
@@ -509,14 +513,13 @@ __global__ void __launch_bounds__((TMA ? kTmaWarps : kWarpsPerBlock) * 32, TMA ?
     // for a ring of such fields against 0.69 for gauges.  But its order statistics are positions: min = first sample, max = last,
     // k-th largest = sample m - k.  That holds for ANY window whose samples before t = m - k lie in [first, T] and whose last k lie in
     // [T, last] (T = sample m - k), all non-negative (so that numeric order is totalOrder and no -0 hides in a tie; NaN fails every
-    // compare): checked on the parked rows, 32 LDS.64 and 64 compares per lane.  Tried only where the high words of the whole window
-    // span at most 8 values (one more REDUX on registers; a gauge with noise spans thousands and pays nothing else).  Measured on 512 x
+    // compare): checked on the parked rows, 32 LDS.64 and 64 compares per lane.  Tried only where every lane's own samples span at most
+    // 8 high words (a flag that rides on the n_over reduction; a gauge with noise spans thousands and pays nothing else).  Measured on 512 x
     // 1 Mi: counters 1.24 -> 0.85 ms, survey mix 0.746 -> 0.718 (91 % of the copy peak), white noise 0.689 -> 0.696.  Variants that lost: the
     // check behind a per-lane pretest read from the rows for EVERY window (gauges +9 %), the check out of line in the 64-bit path only
     // (counters 1.12: the minimum scan and the failed gather stay), a lane pretest between the span test and the loop (no change).
     bool positional = false;
-    if (!RANGE && !lo_zero && m == p.W && m > 960 && p.k_full >= 1 && p.k_full <= 32 && __reduce_max_sync(kFull, mh) - wmin.hi <= 8u &&
-        (__reduce_max_sync(kFull, c_umax) & 0x80000000u) == 0u) {
+    if (!RANGE && !lo_zero && tied_nonneg && m == p.W && m > 960 && p.k_full >= 1 && p.k_full <= 32) {
       const int tk = m - p.k_full;
       auto at = [&](int t) { return __longlong_as_double((long long)sk[((t & 63) >> 1) * kRowU64 + 2 * (t >> 6) + (t & 1)]); };
       const double e0 = at(0), tv = at(tk), el = at(m - 1);
