@@ -9,7 +9,9 @@ S=gpud_b200/csrc
 for f in catalog host_component kmsg_stateful store_sqlite; do
   g++ -O1 -g -std=c++17 -fPIC -Wall -fsanitize=address,undefined -fno-omit-frame-pointer -c $S/$f.cpp -o build/${f}_asan.o
 done
-g++ -O1 -g -std=c++17 -fPIC -Wall -fsanitize=address,undefined -fno-omit-frame-pointer -I/usr/local/cuda/include -c $S/poller.cpp -o build/poller_asan.o
+for f in poller component_abi; do
+  g++ -O1 -g -std=c++17 -fPIC -Wall -fsanitize=address,undefined -fno-omit-frame-pointer -I/usr/local/cuda/include -c $S/$f.cpp -o build/${f}_asan.o
+done
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o build/libgpud_asan.so $S/api.o $S/ring.o $S/select.o $S/kmsg_scan.o $S/ib_scan.o $S/fabric.o \
-  build/catalog_asan.o build/host_component_asan.o build/kmsg_stateful_asan.o build/poller_asan.o build/store_sqlite_asan.o -lcudart -ldl -Xlinker -lasan -Xlinker -lubsan
+  build/catalog_asan.o build/host_component_asan.o build/kmsg_stateful_asan.o build/poller_asan.o build/component_abi_asan.o build/store_sqlite_asan.o -lcudart -ldl -Xlinker -lasan -Xlinker -lubsan
 echo built build/libgpud_asan.so
