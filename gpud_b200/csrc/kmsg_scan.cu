@@ -785,6 +785,21 @@ __device__ bool unit_matches_norm(const gpud_t_rule& r, const char* norm) {
   }
   return false;
 }
+// the same test on whole words: alias rows and `norm` are NUL-padded to GPUD_T_ALIAS_LEN, so two strings are equal iff their 12 words
+// are - twelve independent loads per alias instead of a chain of dependent byte loads (the finish kernel's top stall line)
+static_assert(offsetof(gpud_t_rule, alias) % 4 == 0 && sizeof(gpud_t_rule) % 4 == 0 && offsetof(gpud_tables, rules) % 4 == 0 && GPUD_T_ALIAS_LEN % 4 == 0,
+              "alias rows are read as 32-bit words");
+__device__ __forceinline__ bool unit_matches_words(const gpud_t_rule& r, const unsigned* norm_words) {
+  if ((norm_words[0] & 0xffu) == 0u) return false;
+  for (int a = 0; a < r.n_alias; ++a) {
+    const unsigned* __restrict__ aw = reinterpret_cast<const unsigned*>(r.alias[a]);
+    unsigned diff = 0;
+#pragma unroll
+    for (int k = 0; k < GPUD_T_ALIAS_LEN / 4; ++k) diff |= __ldg(aw + k) ^ norm_words[k];
+    if (diff == 0u) return true;
+  }
+  return false;
+}
 __device__ void normalize_unit(const char* unit, char* norm) {          // TrimSpace + ToUpper + '-'->'_' + keep [A-Z0-9_]
   int n = 0;
   for (int i = 0; unit[i] && n < GPUD_T_ALIAS_LEN - 1; ++i) {
@@ -1388,10 +1403,13 @@ __global__ void __launch_bounds__(256) k_scan_finish(ScanBuf b, int mode, const 
     if (event_type != kPendingExtended) continue;                    // warp-uniform
     const int xid = h->code, sub = h->sub_code;
     const uint32_t st = h->error_status, intr = h->intrinfo;
-    char unit[40], norm[GPUD_T_ALIAS_LEN];
+    char unit[40];
+    __align__(4) char norm[GPUD_T_ALIAS_LEN];
     for (int i = 0; i < 40; ++i) unit[i] = h->unit_name[i];
     unit[39] = 0;
+    for (int i = 0; i < GPUD_T_ALIAS_LEN; ++i) norm[i] = 0;         // NUL-padded: compared word by word below
     normalize_unit(unit, norm);
+    const unsigned* norm_words = reinterpret_cast<const unsigned*>(norm);
     int i_status = 0x7fffffff, i_sub = 0x7fffffff, i_sub0 = 0x7fffffff, i_rule = 0x7fffffff;
     for (int i = lane; i < T->n_by_status; i += 32)
       if (i < i_status && T->by_status[i].xid == xid && T->by_status[i].sub_code == sub && T->by_status[i].error_status == st) i_status = i;
@@ -1403,7 +1421,7 @@ __global__ void __launch_bounds__(256) k_scan_finish(ScanBuf b, int mode, const 
     for (int i = lane; i < T->n_rules; i += 32) {
       const gpud_t_rule& r = T->rules[i];
       if (i >= i_rule || r.xid != xid || r.error_status != st) continue;
-      if (!unit_matches_norm(r, norm)) continue;
+      if (!unit_matches_words(r, norm_words)) continue;
       if (pattern_ok(r.v2_kind, r.v2_care, r.v2_val, intr) || pattern_ok(r.v1_kind, r.v1_care, r.v1_val, intr)) i_rule = i;
     }
     i_status = __reduce_min_sync(kFull, i_status);
