@@ -1659,8 +1659,8 @@ static int32_t scan_launch(gpud_ctx* ctx, gpud_scan_state* s, const uint8_t* d_b
     GPUD_CUDA(ctx, cudaMemsetAsync(s->d_chunk_sep, 0, sizeof(uint32_t), st));
   }
   ScanBuf b{d_buf, len};
-  static const int grid_per_sm = [] { const char* e = getenv("GPUD_SCAN_GRID_PER_SM"); return e && atoi(e) > 0 ? atoi(e) : 4; }();
-  const int grid_f = (int)std::min<int64_t>((n_chunks + 31) / 32, (int64_t)ctx->sm_count * grid_per_sm);   // 8 warps x 4 chunks per block step
+  // persistent: 4 blocks of 8 warps per SM (64 registers with the next run's loads in flight); 8, 16 and one-run-per-warp grids measured the same
+  const int grid_f = (int)std::min<int64_t>((n_chunks + 31) / 32, (int64_t)ctx->sm_count * 4);   // 8 warps x 4 chunks per block step
   cudaEventRecord(s->ev[0], st);
   const bool ext = (mode & GPUD_SCAN_EXT_MATCHERS) != 0;
   mode &= kModeMask;
