@@ -230,6 +230,12 @@ def main():
         import torch.distributed as dist
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"        # the version banner goes to stdout; this program prints one JSON line there
+        # the only collective of the step is a 128-byte-per-rank all-gather on the side stream; the persistent reduce grid leaves it ONE
+        # CTA slot (gpud_ring_set_cta_reserve).  Between two GPUs NCCL would otherwise open one channel - one CTA - per NVLink; the
+        # surplus CTAs only get a slot when a reduce kernel drains and then delay the next one's last CTA (measured at N = 2:
+        # 0.776 ms per step against 0.728 at N = 1).
+        os.environ.setdefault("NCCL_MAX_CTAS", "1")
+        os.environ.setdefault("NCCL_MIN_CTAS", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
