@@ -157,7 +157,9 @@ int32_t gpud_poller_counters(gpud_poller* poller, gpud_poll_counters* out);
 /* The fused window reduce runs a persistent grid that fills every CTA slot of the GPU (2 per SM, the whole register file), so a
  * kernel launched meanwhile on another stream - the fabric record's pack / all-gather / verdict - could only start by delaying one of
  * the grid's CTAs, which then finishes a whole kernel-time late.  Leaving n_ctas slots out of the grid (work is divided over whatever
- * grid is launched; each slot costs 1/296 of the throughput) lets such kernels run concurrently.  Default 0. */
+ * grid is launched; each slot costs 1/296 of the throughput) lets such kernels run concurrently.  Default 0.  A collective that runs
+ * beside the reduce needs as many slots as it has CTAs: NCCL opens one channel (one CTA) per NVLink between two GPUs unless it is held
+ * back (NCCL_MAX_CTAS / ncclConfig_t.maxCTAs = 1 is plenty for the 128-byte fabric record; bench.py does that). */
 int32_t gpud_ring_set_cta_reserve(gpud_ring* ring, int32_t n_ctas);
 /* Rows A3 / A4 of the hot path's NVML side.
  * gpud_nvml_devices: nvml.New's enumeration (pkg/nvidia/nvml/instance.go:197-273, device/device.go:46-70): per device the UUID, the
