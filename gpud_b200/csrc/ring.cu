@@ -525,11 +525,12 @@ __global__ void __launch_bounds__((TMA ? kTmaWarps : kWarpsPerBlock) * 32, TMA ?
       const double e0 = at(0), tv = at(tk), el = at(m - 1);
       bool ok = true;
       const int i_low = tk >= 960 ? 30 : 0;          // the usual case (k <= m - 960): entries 0..29 (t < 960) all lie before sample m - k
-#pragma unroll 5
+#pragma unroll 2
       for (int i = 0; i < i_low; ++i) {
         const double x = __longlong_as_double((long long)sk[lane * kRowU64 + i]);
         ok = ok && e0 <= x && x <= tv;
       }
+#pragma unroll 1
       for (int i = i_low; i < 32; ++i) {
         const int t = elem_index(lane, i);
         const double x = __longlong_as_double((long long)sk[lane * kRowU64 + i]);
