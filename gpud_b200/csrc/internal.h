@@ -94,3 +94,6 @@ void gpud_ring_quantile(gpud_ring* r, int* q_num, int* q_den);
 void gpud_scan_state_free(gpud_scan_state*);
 void gpud_comm_state_free(gpud_comm_state*);
 void gpud_parallel_memcpy(void* dst, const void* src, size_t n);
+
+// ring.cu: the ring's field count (the pollers check their row width against it before pushing)
+int gpud_ring_n_fields(const gpud_ring* r);

@@ -1246,6 +1246,8 @@ extern "C" int32_t gpud_ring_push_raw(gpud_ring* r, const void* host_rows_v, int
 
 extern "C" int32_t gpud_ring_push(gpud_ring* r, const double* host_rows, int64_t n) { return gpud_ring_push_raw(r, host_rows, n, GPUD_DT_F64); }
 
+int gpud_ring_n_fields(const gpud_ring* r) { return r ? r->F : 0; }
+
 extern "C" int32_t gpud_ring_counts(gpud_ring* r, int64_t* total, int64_t* count, int64_t* n_windows) {
   if (!r) return GPUD_E_INVALID;
   const int64_t c = ring_count(r);

@@ -1193,6 +1193,12 @@ def test_poller_gpm_metrics_against_nvml(ctx):
     h = pynvml.nvmlDeviceGetHandleByIndex([d for d in devs if d.cuda_device == 0][0].index)
     want_sup = bool(pynvml.nvmlGpmQueryDeviceSupport(h).isSupportedDevice)
     assert poller.gpm_supported() == want_sup
+    with pytest.raises(g.GpudError):                 # every poll source checks its row width against the ring it is to feed
+        g.Poller(ctx, ring)
+    with pytest.raises(g.GpudError):
+        poller.poll_gpm(iring, 1, 10)
+    with pytest.raises(g.GpudError):
+        poller.poll_fields(ring, 1)
     if not want_sup:
         m = poller.gpm_metrics(50)
         assert m.supported == 0 and g.capi.gpm_check([m]) == (0, "GPM not supported")
