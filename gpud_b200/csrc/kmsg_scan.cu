@@ -6,14 +6,18 @@
 //   catalog        xid/xid.go:74-117 (GetDetail...), :2954-2995 (detailFromNVLinkInfo), :3099-3218 (rule lookup)
 // applied to every unit (line / kmsg record) of a buffer, as in xid/kmsg_test.go:252-267 and xid/component.go:274-299.
 //
-// Structure (all HBM-bound integer/byte work, no tensor cores):
-//   k_scan_filter   streams the buffer once with 128-bit loads; per 512-byte warp chunk it counts unit separators and
-//                   flags the two rare bytes that every pattern needs ('V' of "NVRM:", 'X' of "SXid"); flagged bytes are
-//                   verified against their literal context and appended to a candidate list.  1 B/byte algorithmic.
-//   k_scan_prefix   exclusive scan of the per-chunk separator counts (unit numbering).
-//   k_scan_match    one thread per candidate anchor; the first anchor of a unit runs the exact leftmost-first automata
-//                   (every quantifier in R1-R6 is deterministic once the anchor is fixed; see the notes at each matcher),
-//                   then classifies against the device-resident catalog tables.
+// Structure (integer / byte work, no tensor cores), five launches per scan, run as one overlapped chain (pdl_wait / pdl_release):
+//   k_scan_filter        streams the buffer once with 128-bit loads (the next 2 KB run in flight under this run's arithmetic); per
+//                        512-byte warp chunk it counts unit separators exactly and flags - with byte-parallel arithmetic, a superset -
+//                        the lanes that can hold an anchor ("Xid" trigram of "Xid " / "SXid"; first 4-aligned word of "fallen off the
+//                        bus"); the warp re-tests flagged lanes exactly, verifies the literal context and queues the candidates
+//                        (one hand-over per warp).  1 B/byte algorithmic; ALU-pipe bound.
+//   k_scan_prefix_tiles  exclusive scan of the per-chunk separator counts (unit numbering), one launch.
+//   k_cand_scatter       counting sort of the candidates by family (histogram kept by the filter).
+//   k_scan_match         one thread per candidate anchor, all in flight at once; the first anchor of a unit runs the exact
+//                        leftmost-first automata (every quantifier in R1-R6 is deterministic once the anchor is fixed; see the notes
+//                        at each matcher) and classifies plain hits against the device-resident catalog tables.
+//   k_scan_finish        one warp per hit: unit number, and the NVLink5 table searches of extended hits (detailFromNVLinkInfo).
 #include <stdarg.h>
 
 #include <algorithm>
@@ -33,7 +37,7 @@ constexpr unsigned long long kFamX = 1ull;  // "NVRM: Xid (": the candidate is t
 constexpr unsigned long long kFamB = 2ull;  // "fallen off the bus" (every R3 / R4 match holds it): the candidate is the offset of "fall"
 constexpr unsigned long long kFamS = 3ull;  // "SXid"
 // families >= 4: the anchor literals of the extra line matchers (GPUD_SCAN_EXT_MATCHERS), index into kExtLit[]
-constexpr int kPendingExtended = -77;         // event_type of an extended hit whose table searches run in k_classify_ext_coop
+constexpr int kPendingExtended = -77;         // event_type of an extended hit whose table searches run in k_scan_finish
 constexpr int kFamShift = 58;               // candidate word = byte offset | family << 58
 constexpr int kExtFam0 = 4, kNumFam = 25;
 constexpr int kModeMask = 0xff;
@@ -86,15 +90,15 @@ __device__ unsigned long long nvrm_family(const ScanBuf& b, int64_t a, int64_t e
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5a filter.  Every thread owns 16 bytes (one 128-bit load) plus a 4-byte look-ahead from its right neighbour, and
-// tests all 16 four-byte windows against the two anchor words "NVRM" / "SXid" exactly (funnel shifts + chained integer
-// compares): no false positives, so the verification path below only runs where an anchor really starts.  Separators
-// are counted with an exact zero-byte bit trick.  About 5 integer instructions per byte, no shared memory.
+// K5a filter.  Every thread owns 16 bytes (one 128-bit load) plus a 4-byte look-ahead from its right neighbour.  A pre-filter on
+// those five words flags every lane that CAN hold an anchor (details at the loop); flagged lanes are re-tested exactly by the whole
+// warp - all 16 four-byte windows, no false positives from there on - and the literal around the anchor is verified before a
+// candidate is queued.  Separators are counted with an exact zero-byte bit trick.  About 4 integer instructions per byte.
 // ---------------------------------------------------------------------------------------------
 // Anchor words.  Every R1 / R2 match contains "NVRM: Xid (", every R3 / R4 match "fallen off the bus", every R5 / R6 match
-// "SXid" (xid/kmsg.go:22-43, sxid/kmsg.go:17-20).  The filter looks for the RARE four bytes of each - "Xid ", "fall", "SXid" -
-// and walks back to "NVRM: " only from an "Xid " window: the driver's ordinary "NVRM: ..." chatter never reaches the
-// verification path (it used to be 150 of the 251 warp-instructions per 512-byte chunk).
+// "SXid" (xid/kmsg.go:22-43, sxid/kmsg.go:17-20).  The filter looks for the RARE bytes of each - "Xid " / "SXid" through their
+// common "Xid", "fallen off the bus" through its first aligned word - and walks back to "NVRM: " only from an "Xid " window: the
+// driver's ordinary "NVRM: ..." chatter never reaches the verification path (round 1: 150 of 251 warp-instructions per chunk).
 constexpr unsigned kXidSp = 0x20646958u;  // "Xid " little-endian
 constexpr unsigned kSXid = 0x64695853u;   // "SXid"
 // the first 4-aligned word inside "fallen off the bus" when the literal starts 0, 1, 2, 3 bytes before it
