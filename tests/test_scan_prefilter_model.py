@@ -91,3 +91,35 @@ def test_prefilter_is_quiet_on_text_without_the_trigram():
     flags = prefilter_flags(buf)
     own = owners(buf)
     assert flags.sum() <= len(own) + 8                  # only the four aligned words of "fallen ..." can flag here (chance hits are rare)
+
+
+# ---- the separator arithmetic of k_scan_filter / k_scan_finish: exact counts, LINES and RAW_KMSG ---------------------------------
+def _zero_bytes(x):
+    m7 = np.uint32(0x7f7f7f7f)
+    return ~(((x & m7) + m7) | x | m7)
+
+
+def seps_in_block(block16: bytes, next_byte: int, raw_mode: bool, keep: int) -> int:
+    """separators among the first `keep` bytes of a 16-byte block, the kernels' way (word arithmetic, look-ahead byte for RAW mode)"""
+    w = np.frombuffer(block16 + bytes([next_byte, 0, 0, 0]), dtype="<u4")
+    cnt = 0
+    for k in range(4):
+        z = _zero_bytes(w[k] ^ np.uint32(0x0a0a0a0a))
+        if raw_mode:
+            z &= ~_zero_bytes(_funnel(w[k: k + 1], w[k + 1: k + 2], 8)[0] ^ np.uint32(0x20202020))
+        kk = keep - 4 * k
+        if kk < 4:
+            z = np.uint32(0) if kk <= 0 else z & np.uint32((1 << (8 * kk)) - 1)
+        cnt += bin(int(z)).count("1")
+    return cnt
+
+
+def test_separator_arithmetic_is_exact():
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"ab \n\n\x0b\x0a \x09z", dtype=np.uint8)           # newline-heavy, with the bytes next to '\n' in value (VT, TAB)
+    for trial in range(2000):
+        blk = alphabet[rng.integers(0, len(alphabet), 17)].tobytes()
+        keep = int(rng.integers(0, 17))
+        for raw in (False, True):
+            want = sum(1 for i in range(keep) if blk[i] == 0x0a and (not raw or blk[i + 1] != 0x20))
+            assert seps_in_block(blk[:16], blk[16], raw, keep) == want, (trial, raw, keep, blk)
